@@ -1,0 +1,132 @@
+// hl_common.cuh -- shared host/device declarations of the sm_100a warm-start library.
+//
+// Data layout in HBM (see DESIGN.md "Data layout"): one EnvDesc per environment
+// (offsets into pooled SoA arrays) + pools.  Every geometric quantity exists
+// twice: float64 exactly as the host built it (decisions that must be bit-exact)
+// and a float32 copy relative to a per-environment origin (bulk filter).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include "../../include/headland_b200.h"
+
+#define HL_MAX_SEGS 16           // lane capsules per environment (device-side arrays)
+#define HL_OBS32_STRIDE 20       // floats per obstacle: 4 vertices (8) + 4 x (nx, ny, c)
+#define HL_PI 3.141592653589793  // == math.pi
+
+struct EnvDesc {
+    int n_obs, obs_off;
+    int n_field, field_off;
+    int n_seg, seg_off;
+    int n_crit, crit_off;
+    int n_guide, guide_off;
+    int n_aux, aux_off;
+    float eps;              // float32 filter band (metres), scaled to the environment extent
+    float reach;            // poses farther than this from origin skip the float32 filter
+    double origin[2];
+    double default_len;
+    double body_ext[4];
+};
+
+struct EnvBatchDev {
+    const EnvDesc* desc;
+    const float* obs32;       // [n][20]
+    const double* obs64;      // [n][4][2]
+    const float* field32;     // [n][2] relative to origin
+    const double* field64;    // [n][2]
+    const float* seg32;       // [n][4]  ax, ay, bx, by relative to origin
+    const double* seg64;      // [n][4]
+    const double* seg_len;    // [n]
+    const double* seg_poly;   // [n][66][2]
+    const double* crit64;     // [n][2]
+    const double* guide_x;    // SoA guide polyline
+    const double* guide_y;
+    const double* guide_yaw;
+    const double* guide_s;
+    const double* aux64;      // [n][4]
+    int n_env;
+};
+
+struct hl_env_batch {
+    EnvBatchDev dev;
+    void* allocs[20];
+    int n_allocs;
+    int device;
+};
+
+struct hl_ctx {
+    int device;
+    int sm_count;
+    int max_smem_optin;
+    void* astar_ws;           // cached workspace of the search kernel
+    size_t astar_ws_bytes;
+    unsigned int* d_counters; // small device scratch (work-queue counter etc.)
+};
+
+void hl_set_error(const char* fmt, ...);
+#define HL_CUDA_OK(call)                                                            \
+    do {                                                                            \
+        cudaError_t _e = (call);                                                    \
+        if (_e != cudaSuccess) {                                                    \
+            hl_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e),    \
+                         __FILE__, __LINE__);                                       \
+            return 1;                                                               \
+        }                                                                           \
+    } while (0)
+
+// ------------------------------------------------------------------ device math
+#ifdef __CUDACC__
+// float64 arithmetic that must not be contracted into FMAs: the oracle evaluates
+// the same expressions with one rounding per operation.
+__device__ __forceinline__ double xmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double xadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double xsub(double a, double b) { return __dadd_rn(a, -b); }
+__device__ __forceinline__ double xdiv(double a, double b) { return __ddiv_rn(a, b); }
+
+// Python / numpy floored modulo for a positive modulus (CPython float_rem,
+// numpy npy_divmod): fmod, then shift negative remainders up.
+__device__ __forceinline__ double py_mod_pos(double a, double m) {
+    double r = fmod(a, m);           // exact in CUDA
+    if (r != 0.0) {
+        if (r < 0.0) r = xadd(r, m);
+    } else {
+        r = 0.0;                     // copysign(0, m) with m > 0
+    }
+    return r;
+}
+
+// path_utils.angle_wrap: (a + pi) % (2*pi) - pi
+__device__ __forceinline__ double angle_wrap(double a) {
+    return xsub(py_mod_pos(xadd(a, HL_PI), 2.0 * HL_PI), HL_PI);
+}
+
+// reeds_shepp.M: theta % 2pi folded to (-pi, pi]
+__device__ __forceinline__ double rs_mod2pi(double theta) {
+    double phi = py_mod_pos(theta, 2.0 * HL_PI);
+    if (phi < -HL_PI) phi = xadd(phi, 2.0 * HL_PI);
+    if (phi > HL_PI) phi = xsub(phi, 2.0 * HL_PI);
+    return phi;
+}
+
+// reeds_shepp.pi_2_pi
+__device__ __forceinline__ double rs_pi_2_pi(double t) {
+    while (t > HL_PI) t = xsub(t, 2.0 * HL_PI);
+    while (t < -HL_PI) t = xadd(t, 2.0 * HL_PI);
+    return t;
+}
+
+// Correctly rounded hypot for the magnitudes on this path (no over/underflow
+// handling needed: |x|,|y| are metres or unit-circle offsets).  glibc >= 2.35's
+// hypot is correctly rounded, CUDA's is 1-2 ulp; this one follows Borges'
+// "fused" algorithm: h = sqrt(x^2+y^2) with an FMA-computed residual correction.
+__device__ __forceinline__ double hypot_cr(double x, double y) {
+    double ax = fabs(x), ay = fabs(y);
+    if (ax < ay) { double t = ax; ax = ay; ay = t; }
+    if (ay == 0.0) return ax;
+    double h = sqrt(fma(ax, ax, ay * ay));
+    double h_sq = h * h;
+    double ax_sq = ax * ax;
+    double corr = fma(-ay, ay, h_sq - ax_sq) + fma(h, h, -h_sq) - fma(ax, ax, -ax_sq);
+    return h - corr / (2.0 * h);
+}
+#endif

@@ -1,0 +1,458 @@
+// hl_geom.cuh -- footprint predicates (device).
+//
+// Two tiers per predicate (DESIGN.md "Exactness"):
+//   * float32 filter with a conservative band `eps`: answers FREE / HIT when the
+//     separating margin is clear of the band, AMBIG otherwise;
+//   * float64 exact predicate evaluated with one rounding per operation, the same
+//     expression order as oracle/geometry.py -- the boolean the reference's GEOS
+//     calls would give (orchard_geometry_environment.py:423-458,
+//     reference_line_heuristic.py:105-118) restated for rectangles.
+#pragma once
+#include "hl_common.cuh"
+
+enum { HL_FREE = 0, HL_HIT = 1, HL_AMBIG = 2 };
+
+#define HL_LANE_R 6.0
+// 6*cos(pi/64): radius of the circle inscribed in the 16-segments-per-quadrant cap
+#define HL_LANE_RIN 5.992771509254837
+#define HL_BAND_IN (HL_LANE_RIN - 1e-6)
+#define HL_BAND_OUT (HL_LANE_R + 1e-6)
+
+struct Pose64 {
+    double x, y, c, s;     // c, s = cos/sin(yaw) in float64
+};
+
+// ------------------------------------------------------------------- float64
+__device__ __forceinline__ void exact_corners(const Pose64& p, const double* ext, double* cx, double* cy) {
+    // vertex order (x0,y1),(x0,y0),(x1,y0),(x1,y1) -- car_model.py:102-119
+    const double lx[4] = {ext[0], ext[0], ext[1], ext[1]};
+    const double ly[4] = {ext[3], ext[2], ext[2], ext[3]};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        cx[k] = xadd(xsub(xmul(p.c, lx[k]), xmul(p.s, ly[k])), p.x);
+        cy[k] = xadd(xadd(xmul(p.s, lx[k]), xmul(p.c, ly[k])), p.y);
+    }
+}
+
+__device__ __forceinline__ void exact_local(const Pose64& p, double vx, double vy, double& u, double& w) {
+    double dx = xsub(vx, p.x), dy = xsub(vy, p.y);
+    u = xadd(xmul(p.c, dx), xmul(p.s, dy));
+    w = xsub(xmul(p.c, dy), xmul(p.s, dx));
+}
+
+// closed rectangle meets closed convex quad (CCW), strict separation test
+static __device__ bool exact_rect_hits_quad(const Pose64& p, const double* ext, const double* cx,
+                                     const double* cy, const double* V) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int j = (i + 1) & 3;
+        double ex = xsub(V[2 * j], V[2 * i]), ey = xsub(V[2 * j + 1], V[2 * i + 1]);
+        double nx = ey, ny = -ex;
+        double m = INFINITY;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            double d = xadd(xmul(nx, xsub(cx[k], V[2 * i])), xmul(ny, xsub(cy[k], V[2 * i + 1])));
+            m = fmin(m, d);
+        }
+        if (m > 0.0) return false;
+    }
+    double umin = INFINITY, umax = -INFINITY, wmin = INFINITY, wmax = -INFINITY;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        double u, w;
+        exact_local(p, V[2 * v], V[2 * v + 1], u, w);
+        umin = fmin(umin, u); umax = fmax(umax, u);
+        wmin = fmin(wmin, w); wmax = fmax(wmax, w);
+    }
+    if (umin > ext[1] || umax < ext[0] || wmin > ext[3] || wmax < ext[2]) return false;
+    return true;
+}
+
+static __device__ bool exact_point_in_closed_polygon(double px, double py, const double* poly, int n) {
+    bool inside = false;
+    for (int i = 0; i < n; ++i) {
+        int j = (i + 1 == n) ? 0 : i + 1;
+        double ax = poly[2 * i], ay = poly[2 * i + 1], bx = poly[2 * j], by = poly[2 * j + 1];
+        double cross = xsub(xmul(xsub(bx, ax), xsub(py, ay)), xmul(xsub(by, ay), xsub(px, ax)));
+        if (cross == 0.0 && px >= fmin(ax, bx) && px <= fmax(ax, bx) && py >= fmin(ay, by) &&
+            py <= fmax(ay, by))
+            return true;
+        if ((ay > py) != (by > py)) {
+            double xint = xadd(xdiv(xmul(xsub(bx, ax), xsub(py, ay)), xsub(by, ay)), ax);
+            if (px < xint) inside = !inside;
+        }
+    }
+    return inside;
+}
+
+// Liang-Barsky with strict inequalities: segment meets the OPEN rectangle ext
+__device__ __forceinline__ bool exact_seg_meets_open_rect(double ua, double wa, double ub, double wb,
+                                                          const double* ext) {
+    double t0 = 0.0, t1 = 1.0;
+    double a[2] = {ua, wa}, d[2] = {xsub(ub, ua), xsub(wb, wa)};
+    double lo[2] = {ext[0], ext[2]}, hi[2] = {ext[1], ext[3]};
+#pragma unroll
+    for (int ax = 0; ax < 2; ++ax) {
+        if (d[ax] == 0.0) {
+            if (a[ax] <= lo[ax] || a[ax] >= hi[ax]) return false;
+        } else {
+            double tlo = xdiv(xsub(lo[ax], a[ax]), d[ax]);
+            double thi = xdiv(xsub(hi[ax], a[ax]), d[ax]);
+            if (d[ax] > 0.0) { t0 = fmax(t0, tlo); t1 = fmin(t1, thi); }
+            else             { t0 = fmax(t0, thi); t1 = fmin(t1, tlo); }
+        }
+    }
+    return t0 < t1;
+}
+
+// rectangle inside the closed simple polygon (GEOS contains)
+static __device__ bool exact_rect_in_polygon(const Pose64& p, const double* ext, const double* cx,
+                                      const double* cy, const double* poly, int n) {
+    for (int k = 0; k < 4; ++k)
+        if (!exact_point_in_closed_polygon(cx[k], cy[k], poly, n)) return false;
+    double ua, wa;
+    exact_local(p, poly[0], poly[1], ua, wa);
+    double u0 = ua, w0 = wa;
+    for (int i = 0; i < n; ++i) {
+        double ub, wb;
+        if (i + 1 == n) { ub = u0; wb = w0; }
+        else exact_local(p, poly[2 * (i + 1)], poly[2 * (i + 1) + 1], ub, wb);
+        if (exact_seg_meets_open_rect(ua, wa, ub, wb, ext)) return false;
+        ua = ub; wa = wb;
+    }
+    return true;
+}
+
+// ---- lane: union of 66-vertex capsule polygons ------------------------------
+__device__ __forceinline__ double seg_dist64(const double* s, double px, double py) {
+    double ex = s[2] - s[0], ey = s[3] - s[1];
+    double t = ((px - s[0]) * ex + (py - s[1]) * ey) / (ex * ex + ey * ey);
+    t = fmin(fmax(t, 0.0), 1.0);
+    double qx = s[0] + t * ex, qy = s[1] + t * ey;
+    return hypot(px - qx, py - qy);
+}
+
+// g_j = nx_j*(px - vx_j) + ny_j*(py - vy_j), n_j = (e_y, -e_x) of the CCW ring
+__device__ __forceinline__ double capsule_halfplane(const double* poly, int j, double px, double py) {
+    int k = (j + 1 == HL_CAPSULE_VERTS) ? 0 : j + 1;
+    double vx = poly[2 * j], vy = poly[2 * j + 1];
+    double nx = xsub(poly[2 * k + 1], vy), ny = -xsub(poly[2 * k], vx);
+    return xadd(xmul(nx, xsub(px, vx)), xmul(ny, xsub(py, vy)));
+}
+
+static __device__ bool exact_point_in_capsule(const double* seg, const double* poly, double px, double py,
+                                       bool strict) {
+    double d = seg_dist64(seg, px, py);
+    if (d <= HL_BAND_IN) return true;
+    if (d > HL_BAND_OUT) return false;
+    for (int j = 0; j < HL_CAPSULE_VERTS; ++j) {
+        double g = capsule_halfplane(poly, j, px, py);
+        if (strict ? !(g < 0.0) : !(g <= 0.0)) return false;
+    }
+    return true;
+}
+
+// rectangle inside the union of capsule polygons -- oracle/geometry.py Lane.rects_inside
+static __device__ bool exact_rect_in_lane(const Pose64& p, const double* ext, const double* cx, const double* cy,
+                                   const EnvBatchDev& eb, const EnvDesc& e) {
+    const int S = e.n_seg;
+    const double* segs = eb.seg64 + 4 * (size_t)e.seg_off;
+    const double* polys = eb.seg_poly + 2 * HL_CAPSULE_VERTS * (size_t)e.seg_off;
+    unsigned covered = 0;                       // corner k covered by some capsule
+    for (int i = 0; i < S; ++i) {
+        unsigned in = 0;
+        for (int k = 0; k < 4; ++k)
+            if (exact_point_in_capsule(segs + 4 * i, polys + 2 * HL_CAPSULE_VERTS * i, cx[k], cy[k], false))
+                in |= 1u << k;
+        if (in == 0xFu) return true;            // step 0: one convex capsule holds all 4 corners
+        covered |= in;
+    }
+    if (covered != 0xFu) return false;          // step 1
+    for (int k = 0; k < 4; ++k) {               // step 2: every rectangle edge covered
+        int k2 = (k + 1) & 3;
+        double lo_s[HL_MAX_SEGS], hi_s[HL_MAX_SEGS];
+        int ni = 0;
+        for (int i = 0; i < S; ++i) {
+            const double* poly = polys + 2 * HL_CAPSULE_VERTS * i;
+            double lo = 0.0, hi = 1.0;
+            bool ok = true;
+            for (int j = 0; j < HL_CAPSULE_VERTS; ++j) {
+                double g0 = capsule_halfplane(poly, j, cx[k], cy[k]);
+                double g1 = capsule_halfplane(poly, j, cx[k2], cy[k2]);
+                if (g0 <= 0.0 && g1 <= 0.0) continue;
+                if (g0 > 0.0 && g1 > 0.0) { ok = false; break; }
+                double tc = xdiv(g0, xsub(g0, g1));
+                if (g0 > 0.0) lo = fmax(lo, tc); else hi = fmin(hi, tc);
+            }
+            if (ok && lo <= hi) {
+                int q = ni++;                    // insertion sort by (lo, hi)
+                while (q > 0 && (lo_s[q - 1] > lo || (lo_s[q - 1] == lo && hi_s[q - 1] > hi))) {
+                    lo_s[q] = lo_s[q - 1]; hi_s[q] = hi_s[q - 1]; --q;
+                }
+                lo_s[q] = lo; hi_s[q] = hi;
+            }
+        }
+        double cover = 0.0;
+        for (int q = 0; q < ni; ++q) {
+            if (lo_s[q] > cover) return false;
+            cover = fmax(cover, hi_s[q]);
+        }
+        if (cover < 1.0) return false;
+    }
+    const double* crit = eb.crit64 + 2 * (size_t)e.crit_off;   // step 3
+    for (int q = 0; q < e.n_crit; ++q) {
+        double u, w;
+        exact_local(p, crit[2 * q], crit[2 * q + 1], u, w);
+        if (u > ext[0] && u < ext[1] && w > ext[2] && w < ext[3]) return false;
+    }
+    return true;
+}
+
+// reference_line_heuristic.py:120-129: LAST capsule whose interior holds the point
+static __device__ int exact_search_segment(const EnvBatchDev& eb, const EnvDesc& e, double px, double py) {
+    int last = -1;
+    for (int i = 0; i < e.n_seg; ++i)
+        if (exact_point_in_capsule(eb.seg64 + 4 * (size_t)(e.seg_off + i),
+                                   eb.seg_poly + 2 * HL_CAPSULE_VERTS * (size_t)(e.seg_off + i), px, py, true))
+            last = i;
+    return last;
+}
+
+// Full exact check of one footprint rectangle at one pose.  Returns true = infeasible.
+static __device__ bool exact_part_check(const Pose64& p, const double* ext, const EnvBatchDev& eb,
+                                 const EnvDesc& e, unsigned flags) {
+    double cx[4], cy[4];
+    exact_corners(p, ext, cx, cy);
+    if (flags & HL_CHECK_OBSTACLES) {
+        const double* V = eb.obs64 + 8 * (size_t)e.obs_off;
+        for (int k = 0; k < e.n_obs; ++k)
+            if (exact_rect_hits_quad(p, ext, cx, cy, V + 8 * k)) return true;
+    }
+    if (flags & HL_CHECK_BOUNDARY)
+        if (!exact_rect_in_polygon(p, ext, cx, cy, eb.field64 + 2 * (size_t)e.field_off, e.n_field)) return true;
+    if ((flags & HL_CHECK_LANE) && e.n_seg > 0)
+        if (!exact_rect_in_lane(p, ext, cx, cy, eb, e)) return true;
+    return false;
+}
+
+// ------------------------------------------------------------------- float32
+// Environment staged in shared memory for the float32 filter.
+struct EnvSmem {
+    int n_obs, n_field, n_seg;
+    float eps, reach;
+    float ext[4];               // body rectangle
+    const float* obs;           // [n_obs][20]
+    const float* field;         // [n_field][2]
+    const float* seg;           // [n_seg][4]
+};
+
+// One rectangle `ext` at pose (px,py,c,s) [float32, relative to env origin].
+// Returns HL_FREE / HL_HIT / HL_AMBIG per enabled test, combined:
+//   any HIT -> HIT; else any AMBIG -> AMBIG; else FREE.
+__device__ __forceinline__ int filter_part(const EnvSmem& E, float px, float py, float c, float s,
+                                           const float* ext, unsigned flags, unsigned* which_ambig) {
+    const float eps = E.eps;
+    float rx[4], ry[4];
+    {
+        const float lx[4] = {ext[0], ext[0], ext[1], ext[1]};
+        const float ly[4] = {ext[3], ext[2], ext[2], ext[3]};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            rx[k] = fmaf(c, lx[k], fmaf(-s, ly[k], px));
+            ry[k] = fmaf(s, lx[k], fmaf(c, ly[k], py));
+        }
+    }
+    int result = HL_FREE;
+    unsigned amb = 0;
+    if (flags & HL_CHECK_OBSTACLES) {
+        for (int k = 0; k < E.n_obs; ++k) {
+            const float* o = E.obs + HL_OBS32_STRIDE * k;
+            float sep = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float nx = o[8 + 3 * i], ny = o[9 + 3 * i], cc = o[10 + 3 * i];
+                float m = fminf(fminf(fmaf(nx, rx[0], ny * ry[0]), fmaf(nx, rx[1], ny * ry[1])),
+                                fminf(fmaf(nx, rx[2], ny * ry[2]), fmaf(nx, rx[3], ny * ry[3])));
+                sep = fmaxf(sep, m - cc);
+            }
+            if (sep <= eps) {          // obstacle axes did not clearly separate: try the rectangle axes
+                float umin = INFINITY, umax = -INFINITY, wmin = INFINITY, wmax = -INFINITY;
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    float dx = o[2 * v] - px, dy = o[2 * v + 1] - py;
+                    float u = fmaf(c, dx, s * dy), w = fmaf(c, dy, -s * dx);
+                    umin = fminf(umin, u); umax = fmaxf(umax, u);
+                    wmin = fminf(wmin, w); wmax = fmaxf(wmax, w);
+                }
+                sep = fmaxf(sep, fmaxf(fmaxf(umin - ext[1], ext[0] - umax), fmaxf(wmin - ext[3], ext[2] - wmax)));
+                if (sep < -eps) return HL_HIT;
+                if (sep <= eps) amb |= HL_CHECK_OBSTACLES;
+            }
+        }
+    }
+    if (flags & HL_CHECK_BOUNDARY) {
+        // every polygon edge clear of the rectangle (by a rectangle axis or by its own
+        // line) => the rectangle is wholly inside or wholly outside: one crossing test
+        // of the pose-frame rectangle centre decides.  An edge that clearly cuts the
+        // shrunken open rectangle => HIT.  Anything else => AMBIG.
+        const int n = E.n_field;
+        float dx = E.field[0] - px, dy = E.field[1] - py;
+        float ua = fmaf(c, dx, s * dy), wa = fmaf(c, dy, -s * dx);
+        const float u_first = ua, w_first = wa;
+        const float ccx = 0.5f * (ext[0] + ext[1]), ccy = 0.5f * (ext[2] + ext[3]);
+        bool inside = false, all_clear = true, cut = false;
+        for (int i = 0; i < n; ++i) {
+            float ub, wb;
+            if (i + 1 == n) { ub = u_first; wb = w_first; }
+            else {
+                dx = E.field[2 * (i + 1)] - px; dy = E.field[2 * (i + 1) + 1] - py;
+                ub = fmaf(c, dx, s * dy); wb = fmaf(c, dy, -s * dx);
+            }
+            // crossing parity of the rectangle centre, in the pose frame (ray along +u)
+            if ((wa > ccy) != (wb > ccy)) {
+                float uint_ = fmaf((ub - ua), (ccy - wa) / (wb - wa), ua);
+                if (ccx < uint_) inside = !inside;
+            }
+            bool clear = (fminf(ua, ub) > ext[1] + eps) || (fmaxf(ua, ub) < ext[0] - eps) ||
+                         (fminf(wa, wb) > ext[3] + eps) || (fmaxf(wa, wb) < ext[2] - eps);
+            if (!clear) {
+                float du = ub - ua, dw = wb - wa;
+                float inv = rsqrtf(fmaf(du, du, dw * dw));
+                float nx = dw * inv, ny = -du * inv;
+                float base = fmaf(nx, -ua, ny * -wa);
+                float d0 = fmaf(nx, ext[0], fmaf(ny, ext[2], base));
+                float d1 = fmaf(nx, ext[1], fmaf(ny, ext[2], base));
+                float d2 = fmaf(nx, ext[1], fmaf(ny, ext[3], base));
+                float d3 = fmaf(nx, ext[0], fmaf(ny, ext[3], base));
+                float mn = fminf(fminf(d0, d1), fminf(d2, d3)), mx = fmaxf(fmaxf(d0, d1), fmaxf(d2, d3));
+                clear = (mn > eps) || (mx < -eps);
+                if (!clear) {
+                    all_clear = false;
+                    // definite cut: Liang-Barsky against the rectangle shrunk by eps
+                    float t0 = 0.f, t1 = 1.f;
+                    bool dead = false;
+                    const float a2[2] = {ua, wa}, d2v[2] = {du, dw};
+                    const float lo2[2] = {ext[0] + eps, ext[2] + eps}, hi2[2] = {ext[1] - eps, ext[3] - eps};
+#pragma unroll
+                    for (int ax = 0; ax < 2; ++ax) {
+                        if (fabsf(d2v[ax]) < 1e-12f) {
+                            if (a2[ax] <= lo2[ax] || a2[ax] >= hi2[ax]) dead = true;
+                        } else {
+                            float tl = (lo2[ax] - a2[ax]) / d2v[ax], th = (hi2[ax] - a2[ax]) / d2v[ax];
+                            t0 = fmaxf(t0, fminf(tl, th));
+                            t1 = fminf(t1, fmaxf(tl, th));
+                        }
+                    }
+                    // require a clearly non-empty parameter interval
+                    if (!dead && t1 - t0 > 1e-4f) cut = true;
+                }
+            }
+            ua = ub; wa = wb;
+        }
+        if (cut) return HL_HIT;
+        if (all_clear) { if (!inside) return HL_HIT; }
+        else amb |= HL_CHECK_BOUNDARY;
+    }
+    if ((flags & HL_CHECK_LANE) && E.n_seg > 0) {
+        // corner-to-segment distances against the inscribed / circumscribed radii
+        const float rin = (float)HL_LANE_RIN - eps, rout = (float)HL_LANE_R + eps;
+        bool one_holds_all = false;
+        unsigned maybe = 0;                    // corner k possibly inside some capsule
+        for (int i = 0; i < E.n_seg; ++i) {
+            const float* sg = E.seg + 4 * i;
+            float ex = sg[2] - sg[0], ey = sg[3] - sg[1];
+            float inv = 1.0f / fmaf(ex, ex, ey * ey);
+            float dmax = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float qx = rx[k] - sg[0], qy = ry[k] - sg[1];
+                float t = fminf(fmaxf(fmaf(qx, ex, qy * ey) * inv, 0.f), 1.f);
+                float ddx = fmaf(-t, ex, qx), ddy = fmaf(-t, ey, qy);
+                float d2 = fmaf(ddx, ddx, ddy * ddy);
+                dmax = fmaxf(dmax, d2);
+                if (d2 <= rout * rout) maybe |= 1u << k;
+            }
+            if (dmax <= rin * rin) one_holds_all = true;
+        }
+        if (!one_holds_all) {
+            if (maybe != 0xFu) return HL_HIT;
+            amb |= HL_CHECK_LANE;
+        }
+    }
+    if (amb) { result = HL_AMBIG; if (which_ambig) *which_ambig = amb; }
+    return result;
+}
+
+// Resolve one pose against its environment.  Shared by K1 and the search kernels.
+static __device__ bool pose_infeasible(const EnvBatchDev& eb, const EnvDesc& D, const EnvSmem& E,
+                                double x, double y, double yaw, bool with_aux, unsigned flags,
+                                unsigned long long* n_exact) {
+    float px = (float)(x - D.origin[0]), py = (float)(y - D.origin[1]);
+    bool far = fabsf(px) > E.reach || fabsf(py) > E.reach || !(fabs(yaw) < 1e6);
+    float sf, cf;
+    sincosf((float)yaw, &sf, &cf);
+    unsigned amb = flags;
+    int r = far ? HL_AMBIG : filter_part(E, px, py, cf, sf, E.ext, flags, &amb);
+    if (r == HL_HIT) return true;
+    bool bad = false;
+    Pose64 p;
+    bool have64 = false;
+    if (r == HL_AMBIG) {
+        p.x = x; p.y = y; p.c = cos(yaw); p.s = sin(yaw);
+        have64 = true;
+        if (n_exact) atomicAdd(n_exact, 1ULL);
+        bad = exact_part_check(p, D.body_ext, eb, D, amb);
+        if (bad) return true;
+    }
+    if (with_aux && (flags & HL_CHECK_AUX)) {
+        // implement rectangles: obstacles + field polygon, never the lane
+        // (orchard_geometry_environment.py:439-456; reference_line_heuristic.py:105-108)
+        unsigned aflags = flags & (HL_CHECK_OBSTACLES | HL_CHECK_BOUNDARY);
+        for (int a = 0; a < D.n_aux; ++a) {
+            const double* ext64 = eb.aux64 + 4 * (size_t)(D.aux_off + a);
+            float ext32[4] = {(float)ext64[0], (float)ext64[1], (float)ext64[2], (float)ext64[3]};
+            unsigned amb2 = aflags;
+            int r2 = far ? HL_AMBIG : filter_part(E, px, py, cf, sf, ext32, aflags, &amb2);
+            if (r2 == HL_HIT) return true;
+            if (r2 == HL_AMBIG) {
+                if (!have64) { p.x = x; p.y = y; p.c = cos(yaw); p.s = sin(yaw); have64 = true; }
+                if (n_exact) atomicAdd(n_exact, 1ULL);
+                if (exact_part_check(p, ext64, eb, D, amb2)) return true;
+            }
+        }
+    }
+    return false;
+}
+
+__device__ __forceinline__ void stage_env(const EnvBatchDev& eb, const EnvDesc& D, float* sm, int cap_floats,
+                                          EnvSmem& E, bool& staged) {
+    int need = D.n_obs * HL_OBS32_STRIDE + D.n_field * 2 + D.n_seg * 4;
+    E.n_obs = D.n_obs; E.n_field = D.n_field; E.n_seg = D.n_seg;
+    E.eps = D.eps; E.reach = D.reach;
+    for (int k = 0; k < 4; ++k) E.ext[k] = (float)D.body_ext[k];
+    const float* g_obs = eb.obs32 + (size_t)HL_OBS32_STRIDE * D.obs_off;
+    const float* g_field = eb.field32 + 2 * (size_t)D.field_off;
+    const float* g_seg = eb.seg32 + 4 * (size_t)D.seg_off;
+    staged = need <= cap_floats;
+    if (staged) {
+        float* s_obs = sm;
+        float* s_field = s_obs + D.n_obs * HL_OBS32_STRIDE;
+        float* s_seg = s_field + D.n_field * 2;
+        for (int i = threadIdx.x; i < D.n_obs * HL_OBS32_STRIDE; i += blockDim.x) s_obs[i] = g_obs[i];
+        for (int i = threadIdx.x; i < D.n_field * 2; i += blockDim.x) s_field[i] = g_field[i];
+        for (int i = threadIdx.x; i < D.n_seg * 4; i += blockDim.x) s_seg[i] = g_seg[i];
+        E.obs = s_obs; E.field = s_field; E.seg = s_seg;
+    } else {
+        E.obs = g_obs; E.field = g_field; E.seg = g_seg;
+    }
+}
+
+__device__ __forceinline__ void global_env(const EnvBatchDev& eb, const EnvDesc& D, EnvSmem& E) {
+    E.n_obs = D.n_obs; E.n_field = D.n_field; E.n_seg = D.n_seg;
+    E.eps = D.eps; E.reach = D.reach;
+    for (int k = 0; k < 4; ++k) E.ext[k] = (float)D.body_ext[k];
+    E.obs = eb.obs32 + (size_t)HL_OBS32_STRIDE * D.obs_off;
+    E.field = eb.field32 + 2 * (size_t)D.field_off;
+    E.seg = eb.seg32 + 4 * (size_t)D.seg_off;
+}
+

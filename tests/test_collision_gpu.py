@@ -1,0 +1,89 @@
+"""K1 parity: per-pose collision booleans from hl_collision_check (through the C
+ABI) vs the CPU oracle -- bit-exact (north_star tier 1)."""
+import math
+
+import numpy as np
+import pytest
+
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _cmp(gpu_flags, oracle_flags, what):
+    g = gpu_flags.cpu().numpy().astype(bool)
+    bad = np.nonzero(g != oracle_flags)[0]
+    assert len(bad) == 0, f"{what}: {len(bad)} of {len(g)} booleans differ, first at {bad[:5]}"
+
+
+@pytest.mark.parametrize("l_std,slope", [(0.0, 10.0), (1.0, 10.0), (0.5, 0.0)])
+def test_body_obstacles_and_boundary(built_library, l_std, slope):
+    rows = H.canonical_rows(l_std=l_std, slope_deg=slope)
+    (o_env, o_car, _), (g_env, g_car, _) = H.make_pair(rows, obstacles=[(-3.0, 6.0), (24.0, 11.0)])
+    rng = np.random.default_rng(7)
+    poses = np.concatenate([H.random_poses(rng, 60000), H.headland_poses(rng, 60000, rows)])
+    for bc in (False, True):
+        want = o_env.pose_flags(o_car, poses, boundary_check=bc)
+        got = g_env.pose_flags(g_car, poses, boundary_check=bc)
+        _cmp(got, want, f"boundary_check={bc}")
+        assert 0.02 < want.mean() < 0.98
+
+
+@pytest.mark.parametrize("aux", [H.MOWER_AUX, H.PRUNER_AUX, H.SPRAYER_AUX])
+def test_aux_rectangles_stride2(built_library, aux):
+    rows = H.canonical_rows()
+    (o_env, o_car, _), (g_env, g_car, _) = H.make_pair(rows, axle_to_front=2.85, aux=aux)
+    rng = np.random.default_rng(11)
+    poses = H.headland_poses(rng, 40001, rows)
+    want = o_env.pose_flags(o_car, poses, boundary_check=True, aux_check=True)
+    got = g_env.pose_flags(g_car, poses, boundary_check=True, aux_check=True)
+    _cmp(got, want, "aux")
+    # aux only counts at even pose indices (car_model.py:58)
+    body_only = o_env.pose_flags(o_car, poses, boundary_check=True, aux_check=False)
+    assert (want[1::2] == body_only[1::2]).all() and (want[0::2] != body_only[0::2]).any()
+
+
+def test_lane_containment(built_library):
+    rows = H.canonical_rows()
+    start = np.array([0.0, 3.75, math.pi])
+    goal = np.array([-1.5, 11.0, 0.3])
+    way = np.array([[0.0, 3.75], [-4.5, 5.0], [-4.06, 7.5], [-3.62, 10.0], [-1.5, 11.0]])
+    (_, o_car, o_h), (_, g_car, g_h) = H.make_pair(rows, waypoints=way, goal=goal)
+    rng = np.random.default_rng(3)
+    n = 80000
+    ang = rng.uniform(0, 2 * math.pi, n)
+    rad = rng.uniform(0.0, 9.0, n)
+    c = way[rng.integers(0, len(way), n)]
+    poses = np.stack([c[:, 0] + rad * np.cos(ang), c[:, 1] + rad * np.sin(ang),
+                      rng.uniform(-math.pi, math.pi, n)], axis=1)
+    want = o_h.pose_flags(o_car, poses)
+    from headland_trajectory_planning_b200 import ops
+    got, n_exact = ops.collision_check(g_h._env_batch(g_car), poses, flags=ops.CHECK_LANE, count_exact=True)
+    _cmp(got, want, "lane")
+    assert 0.05 < want.mean() < 0.95
+    # the float64 path is an escalation, not the norm
+    assert int(n_exact.item()) < 0.25 * n
+
+
+def test_touching_counts_as_collision(built_library):
+    """GEOS ``intersects`` is closed: a footprint that exactly touches a tree row collides."""
+    rows = np.array([[[0.0, 2.0 * i], [20.0, 2.0 * i]] for i in range(8)])
+    (o_env, o_car, _), (g_env, g_car, _) = H.make_pair(rows, tree_width=0.5, headland_width=8.0)
+    # rows occupy y in [2i-0.25, 2i+0.25]; body half width 0.74 -> touching at y = 2i + 0.25 + 0.74
+    ys = np.array([0.25 + 0.74, 0.25 + 0.74 + 1e-9, 0.25 + 0.74 - 1e-9, 1.0])
+    poses = np.stack([np.full(4, 5.0), ys, np.zeros(4)], axis=1)
+    want = o_env.pose_flags(o_car, poses, boundary_check=False)
+    got = g_env.pose_flags(g_car, poses, boundary_check=False)
+    _cmp(got, want, "touching")
+    assert want.tolist() == [True, want[1], True, True]
+
+
+def test_empty_and_single(built_library):
+    rows = H.canonical_rows()
+    (o_env, o_car, _), (g_env, g_car, _) = H.make_pair(rows)
+    assert g_env.check_path_feasibility(g_car, np.zeros((0, 3))) is True
+    p = np.array([[-3.0, 3.75, math.pi]])
+    assert g_env.check_path_feasibility(g_car, p) == o_env.check_path_feasibility(o_car, p)
+    far = np.array([[1e4, -2e4, 0.3], [float("nan"), 0.0, 0.0]])
+    got = g_env.pose_flags(g_car, far).cpu().numpy().astype(bool)
+    assert got[0]
