@@ -1,0 +1,411 @@
+// hl_rs.cuh -- Reeds-Shepp analytic expansion (device).
+//
+// Replaces path_planner/utils/reeds_shepp.py: the 46 candidate words
+// (SCS 2, CSC 8, CCC 8, CCCC 8, CCSC 16, CCSCC 4; :565-582) are one table, one
+// thread per row; validity flags, lengths, the signed-sum dedup of set_path
+// (:68-87) and the sample COUNT of generate_local_course (:471-530) are float64 in
+// the reference's operation order, because they feed discrete decisions.
+#pragma once
+#include "hl_common.cuh"
+
+enum { RS_SLS = 0, RS_LSL, RS_LSR, RS_LRL, RS_LRLRN, RS_LRLRP, RS_LRSR, RS_LRSL, RS_LRSLR };
+enum { RP_TUV = 0, RP_VUT, RP_TUnUV, RP_TUUV, RP_THUV, RP_VUHT, RP_THUHV };
+enum { RS_S = 0, RS_L = 1, RS_R = 2 };
+
+// row = solver | sx<0 (bit 4) | sy<0 (bit 5) | backwards (bit 6) | pattern << 8 | nseg << 12 | letters << 16 (2 bits each)
+struct RsRow { unsigned char solver, neg_x, neg_y, backwards, pattern, nseg; unsigned short letters; };
+
+#define RS_LET3(a, b, c) ((a) | ((b) << 2) | ((c) << 4))
+#define RS_LET4(a, b, c, d) (RS_LET3(a, b, c) | ((d) << 6))
+#define RS_LET5(a, b, c, d, e) (RS_LET4(a, b, c, d) | ((e) << 8))
+#define RS_QUAD(solver, back, pat, n, pos, neg)                                     \
+    {solver, 0, 0, back, pat, n, pos}, {solver, 1, 0, back, pat, n, pos},           \
+    {solver, 0, 1, back, pat, n, neg}, {solver, 1, 1, back, pat, n, neg}
+
+__constant__ RsRow c_rs_rows[HL_RS_CANDIDATES] = {
+    {RS_SLS, 0, 0, 0, RP_TUV, 3, RS_LET3(RS_S, RS_L, RS_S)},
+    {RS_SLS, 0, 1, 0, RP_TUV, 3, RS_LET3(RS_S, RS_R, RS_S)},
+    RS_QUAD(RS_LSL, 0, RP_TUV, 3, RS_LET3(RS_L, RS_S, RS_L), RS_LET3(RS_R, RS_S, RS_R)),
+    RS_QUAD(RS_LSR, 0, RP_TUV, 3, RS_LET3(RS_L, RS_S, RS_R), RS_LET3(RS_R, RS_S, RS_L)),
+    RS_QUAD(RS_LRL, 0, RP_TUV, 3, RS_LET3(RS_L, RS_R, RS_L), RS_LET3(RS_R, RS_L, RS_R)),
+    RS_QUAD(RS_LRL, 1, RP_VUT, 3, RS_LET3(RS_L, RS_R, RS_L), RS_LET3(RS_R, RS_L, RS_R)),
+    RS_QUAD(RS_LRLRN, 0, RP_TUnUV, 4, RS_LET4(RS_L, RS_R, RS_L, RS_R), RS_LET4(RS_R, RS_L, RS_R, RS_L)),
+    RS_QUAD(RS_LRLRP, 0, RP_TUUV, 4, RS_LET4(RS_L, RS_R, RS_L, RS_R), RS_LET4(RS_R, RS_L, RS_R, RS_L)),
+    RS_QUAD(RS_LRSL, 0, RP_THUV, 4, RS_LET4(RS_L, RS_R, RS_S, RS_L), RS_LET4(RS_R, RS_L, RS_S, RS_R)),
+    RS_QUAD(RS_LRSR, 0, RP_THUV, 4, RS_LET4(RS_L, RS_R, RS_S, RS_R), RS_LET4(RS_R, RS_L, RS_S, RS_L)),
+    RS_QUAD(RS_LRSL, 1, RP_VUHT, 4, RS_LET4(RS_L, RS_S, RS_R, RS_L), RS_LET4(RS_R, RS_S, RS_L, RS_R)),
+    RS_QUAD(RS_LRSR, 1, RP_VUHT, 4, RS_LET4(RS_R, RS_S, RS_R, RS_L), RS_LET4(RS_L, RS_S, RS_L, RS_R)),
+    RS_QUAD(RS_LRSLR, 0, RP_THUHV, 5, RS_LET5(RS_L, RS_R, RS_S, RS_L, RS_R), RS_LET5(RS_R, RS_L, RS_S, RS_R, RS_L)),
+};
+
+__device__ __forceinline__ int rs_letter(unsigned short letters, int i) { return (letters >> (2 * i)) & 3; }
+
+// ---- word solvers: float64, reference operation order -------------------------
+// Each returns validity and (t,u,v).  Products/sums that the reference evaluates
+// as separate Python float operations use xmul/xadd so no FMA is formed.
+__device__ __forceinline__ void rs_polar(double x, double y, double& r, double& th) {
+    r = hypot_cr(x, y);
+    th = atan2(y, x);
+}
+
+__device__ bool rs_solve(int solver, double x, double y, double phi, double& t, double& u, double& v) {
+    const double PI = HL_PI;
+    switch (solver) {
+    case RS_SLS: {                                              // reeds_shepp.py:144-160
+        phi = rs_mod2pi(phi);
+        if ((y > 0.0 || y < 0.0) && 0.0 < phi && phi < xmul(PI, 0.99)) {
+            double tn = tan(phi);
+            double xd = xadd(xdiv(-y, tn), x);
+            double th = tan(xdiv(phi, 2.0));
+            t = xsub(xd, th);
+            u = phi;
+            double dx = xsub(x, xd);
+            double rt = sqrt(xadd(xmul(dx, dx), xmul(y, y)));
+            v = (y > 0.0) ? xsub(rt, th) : xsub(-rt, th);
+            return true;
+        }
+        return false;
+    }
+    case RS_LSL: {                                              // :90-98
+        double r, th;
+        rs_polar(xsub(x, sin(phi)), xadd(xsub(y, 1.0), cos(phi)), r, th);
+        u = r; t = th;
+        if (t >= 0.0) {
+            v = rs_mod2pi(xsub(phi, t));
+            if (v >= 0.0) return true;
+        }
+        return false;
+    }
+    case RS_LSR: {                                              // :101-114
+        double u1, t1;
+        rs_polar(xadd(x, sin(phi)), xsub(xsub(y, 1.0), cos(phi)), u1, t1);
+        u1 = xmul(u1, u1);
+        if (u1 >= 4.0) {
+            u = sqrt(xsub(u1, 4.0));
+            double theta = atan2(2.0, u);
+            t = rs_mod2pi(xadd(t1, theta));
+            v = rs_mod2pi(xsub(t, phi));
+            if (t >= 0.0 && v >= 0.0) return true;
+        }
+        return false;
+    }
+    case RS_LRL: {                                              // :117-128
+        double u1, t1;
+        rs_polar(xsub(x, sin(phi)), xadd(xsub(y, 1.0), cos(phi)), u1, t1);
+        if (u1 <= 4.0) {
+            u = xmul(-2.0, asin(xmul(0.25, u1)));
+            t = rs_mod2pi(xadd(xadd(t1, xmul(0.5, u)), PI));
+            v = rs_mod2pi(xadd(xsub(phi, t), u));
+            if (t >= 0.0 && u <= 0.0) return true;
+        }
+        return false;
+    }
+    case RS_LRLRN:
+    case RS_LRLRP: {                                            // :239-283
+        double xi = xadd(x, sin(phi));
+        double eta = xsub(xsub(y, 1.0), cos(phi));
+        double uu, vv;
+        if (solver == RS_LRLRN) {
+            double rho = xmul(0.25, xadd(2.0, sqrt(xadd(xmul(xi, xi), xmul(eta, eta)))));
+            if (!(rho <= 1.0)) return false;
+            uu = acos(rho);
+            vv = -uu;
+        } else {
+            double rho = xdiv(xsub(xsub(20.0, xmul(xi, xi)), xmul(eta, eta)), 16.0);
+            if (!(0.0 <= rho && rho <= 1.0)) return false;
+            uu = -acos(rho);
+            if (!(uu >= xmul(-0.5, PI))) return false;
+            vv = uu;
+        }
+        // calc_tauOmega(u, v, xi, eta, phi)
+        double delta = rs_mod2pi(xsub(uu, vv));
+        double A = xsub(sin(uu), sin(delta));
+        double B = xsub(xsub(cos(uu), cos(delta)), 1.0);
+        double t1 = atan2(xsub(xmul(eta, A), xmul(xi, B)), xadd(xmul(xi, A), xmul(eta, B)));
+        double t2 = xadd(xmul(2.0, xsub(xsub(cos(delta), cos(vv)), cos(uu))), 3.0);
+        double tau = (t2 < 0) ? rs_mod2pi(xadd(t1, PI)) : rs_mod2pi(t1);
+        double omega = rs_mod2pi(xsub(xadd(xsub(tau, uu), vv), phi));
+        t = tau; u = uu; v = omega;
+        if (solver == RS_LRLRN) return t >= 0.0 && v <= 0.0;
+        return t >= 0.0 && v >= 0.0;
+    }
+    case RS_LRSR: {                                             // :322-334
+        double xi = xadd(x, sin(phi));
+        double eta = xsub(xsub(y, 1.0), cos(phi));
+        double rho, theta;
+        rs_polar(-eta, xi, rho, theta);
+        if (rho >= 2.0) {
+            t = theta;
+            u = xsub(2.0, rho);
+            v = rs_mod2pi(xsub(xadd(t, xmul(0.5, PI)), phi));
+            if (t >= 0.0 && u <= 0.0 && v <= 0.0) return true;
+        }
+        return false;
+    }
+    case RS_LRSL: {                                             // :337-350
+        double xi = xsub(x, sin(phi));
+        double eta = xadd(xsub(y, 1.0), cos(phi));
+        double rho, theta;
+        rs_polar(xi, eta, rho, theta);
+        if (rho >= 2.0) {
+            double r = sqrt(xsub(xmul(rho, rho), 4.0));
+            u = xsub(2.0, r);
+            t = rs_mod2pi(xadd(theta, atan2(r, -2.0)));
+            v = rs_mod2pi(xsub(xsub(phi, xmul(0.5, PI)), t));
+            if (t >= 0.0 && u <= 0.0 && v <= 0.0) return true;
+        }
+        return false;
+    }
+    default: {                                                  // RS_LRSLR :425-440
+        double xi = xadd(x, sin(phi));
+        double eta = xsub(xsub(y, 1.0), cos(phi));
+        double rho, theta;
+        rs_polar(xi, eta, rho, theta);
+        if (rho >= 2.0) {
+            u = xsub(4.0, sqrt(xsub(xmul(rho, rho), 4.0)));
+            if (u <= 0.0) {
+                double num = xsub(xmul(xsub(4.0, u), xi), xmul(2.0, eta));
+                double den = xadd(xmul(-2.0, xi), xmul(xsub(u, 4.0), eta));
+                t = rs_mod2pi(atan2(num, den));
+                v = rs_mod2pi(xsub(t, phi));
+                if (t >= 0.0 && v >= 0.0) return true;
+            }
+        }
+        return false;
+    }
+    }
+}
+
+// Normalised problem of one pose pair (generate_path, :565-572)
+struct RsProblem { double x, y, phi, xb, yb; };
+
+__device__ __forceinline__ RsProblem rs_normalise(const double* q0, const double* q1, double maxc) {
+    RsProblem P;
+    double dx = xsub(q1[0], q0[0]), dy = xsub(q1[1], q0[1]);
+    P.phi = xsub(q1[2], q0[2]);
+    double c = cos(q0[2]), s = sin(q0[2]);
+    P.x = xmul(xadd(xmul(c, dx), xmul(s, dy)), maxc);
+    P.y = xmul(xadd(xmul(-s, dx), xmul(c, dy)), maxc);
+    double cp = cos(P.phi), sp = sin(P.phi);                    // :217-218 / :387-388
+    P.xb = xadd(xmul(P.x, cp), xmul(P.y, sp));
+    P.yb = xsub(xmul(P.x, sp), xmul(P.y, cp));
+    return P;
+}
+
+// Evaluate candidate row `cand`: returns validity, writes nseg normalised lengths.
+__device__ bool rs_candidate(int cand, const RsProblem& P, double* lens) {
+    const RsRow row = c_rs_rows[cand];
+    double ax = row.backwards ? P.xb : P.x, ay = row.backwards ? P.yb : P.y;
+    if (row.neg_x) ax = -ax;
+    if (row.neg_y) ay = -ay;
+    double aphi = (row.neg_x != row.neg_y) ? -P.phi : P.phi;
+    double t, u, v;
+    if (!rs_solve(row.solver, ax, ay, aphi, t, u, v)) return false;
+    const double H = xmul(-0.5, HL_PI);
+    switch (row.pattern) {
+    case RP_TUV:   lens[0] = t; lens[1] = u; lens[2] = v; break;
+    case RP_VUT:   lens[0] = v; lens[1] = u; lens[2] = t; break;
+    case RP_TUnUV: lens[0] = t; lens[1] = u; lens[2] = -u; lens[3] = v; break;
+    case RP_TUUV:  lens[0] = t; lens[1] = u; lens[2] = u; lens[3] = v; break;
+    case RP_THUV:  lens[0] = t; lens[1] = H; lens[2] = u; lens[3] = v; break;
+    case RP_VUHT:  lens[0] = v; lens[1] = u; lens[2] = H; lens[3] = t; break;
+    default:       lens[0] = t; lens[1] = H; lens[2] = u; lens[3] = H; lens[4] = v; break;
+    }
+    if (row.neg_x)
+        for (int i = 0; i < row.nseg; ++i) lens[i] = -lens[i];
+    return true;
+}
+
+// set_path (:68-87) over all 46 candidates, sequential: returns number of accepted
+// words, -1 if the reference's `assert path.L >= 0.01` would fire.
+//   valid[c], lens[c][5]  : candidate results
+//   acc[k]                : accepted candidate indices (reference order)
+//   L[k]                  : normalised total length
+__device__ int rs_select(const unsigned char* valid, const double (*lens)[HL_RS_MAX_SEGS], int* acc, double* L) {
+    int n = 0;
+    for (int c = 0; c < HL_RS_CANDIDATES; ++c) {
+        if (!valid[c]) continue;
+        const RsRow row = c_rs_rows[c];
+        bool dup = false;
+        for (int k = 0; k < n && !dup; ++k) {
+            const RsRow prev = c_rs_rows[acc[k]];
+            if (prev.nseg == row.nseg && prev.letters == row.letters) {
+                double s = 0.0;                                  // Python sum(): 0 + d0 + d1 + ...
+                for (int i = 0; i < row.nseg; ++i) s = xadd(s, xsub(lens[acc[k]][i], lens[c][i]));
+                if (s <= 0.01) dup = true;
+            }
+        }
+        if (dup) continue;
+        double tot = 0.0;
+        for (int i = 0; i < row.nseg; ++i) tot = xadd(tot, fabs(lens[c][i]));
+        if (tot >= 1000.0) continue;                             // MAX_LENGTH
+        if (!(tot >= 0.01)) return -1;
+        acc[n] = c; L[n] = tot; ++n;
+    }
+    return n;
+}
+
+// calculate_reeds_shepp_path_cost (hybrid_a_star_search.py:129-160) with the quirks:
+// +DIRECTION_CHANGE_COST and +MAX_STEER always (len(np.where(..)) == 1); 'L' arcs steer 0.
+// Lengths here may be normalised or metric: only signs matter.
+__device__ double rs_path_cost(double node_cost, int cand, const double* lens, double max_steer,
+                               double reverse_cost, double dir_change_cost, double steer_cost) {
+    const RsRow row = c_rs_rows[cand];
+    int nneg = 0;
+    for (int i = 0; i < row.nseg; ++i) nneg += (lens[i] < 0.0) ? 1 : 0;
+    double cost = node_cost;
+    cost = xadd(cost, xadd(xmul(reverse_cost, (double)nneg), (double)(row.nseg - nneg)));
+    cost = xadd(cost, xmul(1.0, dir_change_cost));
+    cost = xadd(cost, xmul(xmul(max_steer, steer_cost), 1.0));
+    double prev = 0.0, sum = 0.0;
+    for (int i = 0; i < row.nseg; ++i) {
+        double st = (rs_letter(row.letters, i) == RS_R) ? -max_steer : 0.0;
+        if (i > 0) sum = xadd(sum, fabs(xsub(st, prev)));        // np.sum of <= 4 elements: sequential
+        prev = st;
+    }
+    return xadd(cost, sum);
+}
+
+// heapdict pop order of n entries inserted in index order with the given priorities
+// (hybrid_a_star_search.py:265-271).  order[] receives the indices in pop order.
+__device__ void heapdict_order(const double* prio, int n, int* order) {
+    int heap[HL_RS_CANDIDATES];
+    int m = 0;
+    for (int k = 0; k < n; ++k) {                 // __setitem__: append + _decrease_key
+        int i = m++;
+        heap[i] = k;
+        while (i) {
+            int parent = (i - 1) >> 1;
+            if (prio[heap[parent]] < prio[heap[i]]) break;
+            int tmp = heap[i]; heap[i] = heap[parent]; heap[parent] = tmp;
+            i = parent;
+        }
+    }
+    for (int k = 0; k < n; ++k) {                 // popitem: move last to root + _min_heapify
+        order[k] = heap[0];
+        --m;
+        if (m > 0) {
+            heap[0] = heap[m];
+            int i = 0;
+            while (true) {
+                int l = (i << 1) + 1, r = (i + 1) << 1, low = i;
+                if (l < m && prio[heap[l]] < prio[heap[i]]) low = l;
+                if (r < m && prio[heap[r]] < prio[heap[low]]) low = r;
+                if (low == i) break;
+                int tmp = heap[i]; heap[i] = heap[low]; heap[low] = tmp;
+                i = low;
+            }
+        }
+    }
+}
+
+// ---- sampler: generate_local_course + interpolate (:471-562) -----------------
+struct RsSegPlan {
+    double ox, oy, oyaw;     // origin pose of the segment (local frame of the start pose)
+    double pd0, d, l;        // first offset, step, signed normalised length
+    int first, count, letter;  // first emitted index, loop samples, letter
+};
+struct RsPlan {
+    RsSegPlan seg[HL_RS_MAX_SEGS];
+    int nseg;
+    int npts;                // after the trailing `px == 0.0` pops
+    int dir0;
+};
+
+__device__ __forceinline__ void rs_interp(double l, int letter, double maxc, double ox, double oy, double oyaw,
+                                          double& px, double& py, double& pyaw) {
+    if (letter == RS_S) {
+        double lm = xdiv(l, maxc);
+        px = xadd(ox, xmul(lm, cos(oyaw)));
+        py = xadd(oy, xmul(lm, sin(oyaw)));
+        pyaw = oyaw;
+    } else {
+        double ldx = xdiv(sin(l), maxc);
+        double ldy = (letter == RS_L) ? xdiv(xsub(1.0, cos(l)), maxc) : xdiv(xsub(1.0, cos(l)), -maxc);
+        double cn = cos(-oyaw), sn = sin(-oyaw);
+        double gdx = xadd(xmul(cn, ldx), xmul(sn, ldy));
+        double gdy = xadd(xmul(-sn, ldx), xmul(cn, ldy));
+        px = xadd(ox, gdx);
+        py = xadd(oy, gdy);
+        pyaw = (letter == RS_L) ? xadd(oyaw, l) : xsub(oyaw, l);
+    }
+}
+
+// Build the per-segment plan of one word.  `lens` normalised, step = step_size*maxc.
+// The loop offsets are accumulated by repeated addition exactly like the reference, so
+// the sample count is bit-exact.
+__device__ void rs_make_plan(int cand, const double* lens, double maxc, double step, RsPlan& P) {
+    const RsRow row = c_rs_rows[cand];
+    P.nseg = row.nseg;
+    P.dir0 = (lens[0] > 0.0) ? 1 : -1;
+    double ox = 0.0, oy = 0.0, oyaw = 0.0;        // px[1] of the zero-initialised arrays
+    double ll = 0.0;
+    int ind = 1;
+    for (int i = 0; i < row.nseg; ++i) {
+        double l = lens[i];
+        double d = (l > 0.0) ? step : -step;
+        RsSegPlan& S = P.seg[i];
+        S.ox = ox; S.oy = oy; S.oyaw = oyaw; S.l = l; S.d = d; S.letter = rs_letter(row.letters, i);
+        ind -= 1;
+        double pd;
+        if (i >= 1 && xmul(lens[i - 1], lens[i]) > 0.0) pd = xsub(-d, ll);
+        else pd = xsub(d, ll);
+        S.pd0 = pd;
+        S.first = ind + 1;
+        int cnt = 0;
+        double al = fabs(l);
+        while (fabs(pd) <= al) { ++cnt; pd = xadd(pd, d); }
+        S.count = cnt;
+        ind += cnt;
+        ll = xsub(xsub(l, pd), d);
+        ind += 1;                                 // segment end point at `ind`
+        rs_interp(l, S.letter, maxc, S.ox, S.oy, S.oyaw, ox, oy, oyaw);
+    }
+    // `ind` is the index of the final end point; points 0..ind are written.
+    int npts = ind + 1;
+    // trailing pops: while px[-1] == 0.0 (:523-528).  The allocated tail beyond `ind`
+    // is zero and always popped; written samples are popped only if their x is exactly 0.
+    // last written point = end of the last segment = (ox, oy, oyaw) computed above
+    if (ox == 0.0) {
+        npts -= 1;
+        // walk back through loop samples while their x is exactly 0.0
+        while (npts > 1) {
+            int j = npts - 1;
+            int si = P.nseg - 1;
+            while (si > 0 && j < P.seg[si].first) --si;
+            const RsSegPlan& S = P.seg[si];
+            double pd = S.pd0;
+            for (int k = 0; k < j - S.first; ++k) pd = xadd(pd, S.d);
+            double px, py, pyaw;
+            rs_interp(pd, S.letter, maxc, S.ox, S.oy, S.oyaw, px, py, pyaw);
+            if (px != 0.0) break;
+            npts -= 1;
+        }
+        // index 0 is (0,0,0): popping it too would raise IndexError in the reference
+    }
+    P.npts = npts;
+}
+
+// Pose j (0 <= j < npts) of a planned word in the LOCAL frame, plus curvature sign and
+// direction tag.  Loop offsets use pd0 + k*d (differs from the repeated sum by <1e-12).
+__device__ void rs_sample_local(const RsPlan& P, int j, double maxc, double& px, double& py, double& pyaw,
+                                int& cs_sign, int& dir) {
+    if (j == 0) { px = 0.0; py = 0.0; pyaw = 0.0; cs_sign = 0; dir = P.dir0; return; }
+    int si = P.nseg - 1;
+    while (si > 0 && j < P.seg[si].first) --si;
+    const RsSegPlan& S = P.seg[si];
+    int k = j - S.first;
+    double off = (k < S.count) ? (S.pd0 + (double)k * S.d) : S.l;
+    rs_interp(off, S.letter, maxc, S.ox, S.oy, S.oyaw, px, py, pyaw);
+    cs_sign = (S.letter == RS_S) ? 0 : (S.letter == RS_L ? 1 : -1);
+    dir = (off > 0.0) ? 1 : -1;
+}
+
+// Local -> world (calc_all_paths, :50-59)
+__device__ __forceinline__ void rs_to_world(const double* q0, double cq, double sq, double lx, double ly, double lyaw,
+                                            double& wx, double& wy, double& wyaw) {
+    // cq = cos(-q0yaw), sq = sin(-q0yaw)
+    wx = xadd(xadd(xmul(cq, lx), xmul(sq, ly)), q0[0]);
+    wy = xadd(xadd(xmul(-sq, lx), xmul(cq, ly)), q0[1]);
+    wyaw = rs_pi_2_pi(xadd(lyaw, q0[2]));
+}

@@ -53,3 +53,57 @@ def measure_fp32_peak(device=None):
     v = C.c_double()
     _lib.check(lib.hl_measure_fp32_peak(_lib.get_ctx(device), C.byref(v)), "hl_measure_fp32_peak")
     return v.value
+
+
+def rs_all_paths(start_goal, maxc, step, max_steer=0.55, envs=None, env_id=None,
+                 flags=CHECK_OBSTACLES, want_order=True):
+    """Batched Reeds-Shepp words.  Returns (words [N,46] structured CUDA bytes viewed on
+    the host on demand, count [N] int32, order [N,46] int32) as CUDA tensors; use
+    ``rs_words_to_host`` to view the word records."""
+    torch = _torch()
+    lib = _lib.load_library()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    if not torch.is_tensor(start_goal):
+        start_goal = torch.from_numpy(np.ascontiguousarray(start_goal, dtype=np.float64)).to(dev)
+    start_goal = start_goal.contiguous()
+    n = start_goal.shape[0]
+    if env_id is not None and not torch.is_tensor(env_id):
+        env_id = torch.from_numpy(np.ascontiguousarray(env_id, dtype=np.int32)).to(dev)
+    words = torch.zeros((n, _lib.HL_RS_CANDIDATES, _lib.RSWORD_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+    count = torch.empty(n, dtype=torch.int32, device=dev)
+    order = torch.empty((n, _lib.HL_RS_CANDIDATES), dtype=torch.int32, device=dev) if want_order else None
+    ctx = envs.ctx if envs is not None else _lib.get_ctx()
+    _lib.check(lib.hl_rs_all_paths(ctx, envs.handle if envs is not None else None, _lib.ptr(env_id),
+                                   _lib.ptr(start_goal), n, float(maxc), float(step), float(max_steer),
+                                   flags, _lib.ptr(words), _lib.ptr(count), _lib.ptr(order),
+                                   _lib.stream_ptr()), "hl_rs_all_paths")
+    return words, count, order
+
+
+def rs_words_to_host(words):
+    """[N,46,112] uint8 CUDA tensor -> numpy structured array [N,46] (RSWORD_DTYPE)."""
+    a = words.cpu().numpy()
+    return a.view(_lib.RSWORD_DTYPE).reshape(a.shape[0], a.shape[1])
+
+
+def rs_sample(starts, words_host, maxc, step):
+    """Sample M words.  ``starts`` [M,3] float64 host, ``words_host`` structured [M].
+    Returns host arrays (offset [M+1], x, y, yaw, cs, dir)."""
+    torch = _torch()
+    lib = _lib.load_library()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    m = len(words_host)
+    offset = np.zeros(m + 1, dtype=np.int64)
+    np.cumsum(words_host["npts"], out=offset[1:])
+    total = int(offset[-1])
+    d_start = torch.from_numpy(np.ascontiguousarray(starts, dtype=np.float64)).to(dev)
+    d_words = torch.from_numpy(np.ascontiguousarray(words_host).view(np.uint8).reshape(m, -1)).to(dev)
+    d_off = torch.from_numpy(offset).to(dev)
+    x = torch.empty(max(total, 1), dtype=torch.float64, device=dev)
+    y = torch.empty_like(x); yaw = torch.empty_like(x); cs = torch.empty_like(x)
+    dr = torch.empty(max(total, 1), dtype=torch.int8, device=dev)
+    _lib.check(lib.hl_rs_sample(_lib.get_ctx(), _lib.ptr(d_start), _lib.ptr(d_words), m, float(maxc),
+                                float(step), _lib.ptr(d_off), _lib.ptr(x), _lib.ptr(y), _lib.ptr(yaw),
+                                _lib.ptr(cs), _lib.ptr(dr), _lib.stream_ptr()), "hl_rs_sample")
+    return (offset, x[:total].cpu().numpy(), y[:total].cpu().numpy(), yaw[:total].cpu().numpy(),
+            cs[:total].cpu().numpy(), dr[:total].cpu().numpy())

@@ -132,7 +132,8 @@ typedef struct {
     int32_t collide;       /* filled by hl_rs_all_paths when an environment is given   */
     double  L;             /* total length (metres)                                    */
     double  cost;          /* calculate_reeds_shepp_path_cost with node cost 0         */
-    double  len[HL_RS_MAX_SEGS];  /* signed segment lengths (metres)                   */
+    double  len[HL_RS_MAX_SEGS];  /* signed segment lengths (metres) = PATH.lengths    */
+    double  nlen[HL_RS_MAX_SEGS]; /* the same lengths x maxc (normalised), as sampled  */
 } HlRsWord;
 
 /* ---- context ---------------------------------------------------------------- */

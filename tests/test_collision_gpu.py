@@ -5,7 +5,7 @@ import math
 import numpy as np
 import pytest
 
-from tests import helpers as H
+import hl_helpers as H
 
 pytestmark = pytest.mark.gpu
 

@@ -1,0 +1,97 @@
+"""K2/K3 parity: Reeds-Shepp words (set + order + sample counts exact, lengths and
+states <= 1e-5 relative; north_star tier 2) and per-word collision flags (exact)
+from hl_rs_all_paths / hl_rs_sample vs the pinned oracle port."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+import hl_helpers as H
+from oracle import rs_port
+from oracle import planner as OP
+
+pytestmark = pytest.mark.gpu
+MAXC = math.tan(0.55) / 1.9
+RTOL = 1e-5          # north_star: Reeds-Shepp lengths / states within 1e-5 relative
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _pairs(n, seed=0):
+    rng = np.random.default_rng(seed)
+    sg = np.empty((n, 6))
+    sg[:, [0, 1, 3, 4]] = rng.uniform(-10, 10, (n, 4))
+    sg[:, [2, 5]] = rng.uniform(-math.pi, math.pi, (n, 2))
+    return sg
+
+
+@pytest.mark.parametrize("step", [0.1, 0.2])
+def test_words_match_oracle(built_library, step):
+    from headland_trajectory_planning_b200 import ops
+    sg = _pairs(3000, seed=int(step * 10))
+    words, count, order = ops.rs_all_paths(sg, MAXC, step)
+    w = ops.rs_words_to_host(words)
+    count = count.cpu().numpy()
+    for i in range(len(sg)):
+        ref = rs_port.calc_all_paths(*sg[i], MAXC, step)
+        assert count[i] == len(ref), (i, count[i], len(ref))
+        for k, p in enumerate(ref):
+            assert w["cand"][i, k] == p.cand
+            assert w["npts"][i, k] == len(p.x), (i, k)
+            np.testing.assert_allclose(w["len"][i, k, :len(p.lengths)], p.lengths, rtol=RTOL, atol=1e-9)
+            np.testing.assert_allclose(w["L"][i, k], p.L, rtol=RTOL)
+
+
+def test_sampled_states_match_oracle(built_library):
+    from headland_trajectory_planning_b200.utils import reeds_shepp as rs_gpu
+    cases = [(0, 0, 0, 3, 4, 1.0, 0.1), (-1.30805046, 3.75, math.pi, -1.30805046, 8.75, 0, 0.1),
+             (1, 2, -2, -4, 1.5, 2.5, 0.2)]
+    cases += [tuple(q) + (0.1,) for q in _pairs(40, seed=5)]
+    for c in cases:
+        ref = rs_port.calc_all_paths(*c[:6], MAXC, c[6])
+        got = rs_gpu.calc_all_paths(*c[:6], MAXC, c[6])
+        assert [p.ctypes for p in got] == [p.ctypes for p in ref]
+        for a, b in zip(got, ref):
+            assert len(a.x) == len(b.x)
+            assert a.directions == b.directions
+            np.testing.assert_allclose(a.x, b.x, rtol=RTOL, atol=1e-6)
+            np.testing.assert_allclose(a.y, b.y, rtol=RTOL, atol=1e-6)
+            np.testing.assert_allclose(a.yaw, b.yaw, rtol=RTOL, atol=1e-6)
+            np.testing.assert_allclose(a.cs, b.cs, rtol=1e-12)
+            np.testing.assert_allclose(a.lengths, b.lengths, rtol=RTOL, atol=1e-9)
+
+
+def test_pop_order_and_collision_flags(built_library):
+    """Heapdict pop order of the candidates (ties are the norm) and the per-word
+    collision booleans of the shot loop (hybrid_a_star_search.py:265-276)."""
+    from headland_trajectory_planning_b200 import ops
+    from headland_trajectory_planning_b200.env_batch import EnvBatch, make_record
+    rows = H.canonical_rows()
+    (o_env, o_car, _), (g_env, g_car, _) = H.make_pair(rows)
+    rng = np.random.default_rng(2)
+    n = 1500
+    sg = np.empty((n, 6))
+    sg[:, [0, 3]] = rng.uniform(-7.0, 1.0, (n, 2))
+    sg[:, [1, 4]] = rng.uniform(-1.0, 19.0, (n, 2))
+    sg[:, [2, 5]] = rng.uniform(-math.pi, math.pi, (n, 2))
+    envs = EnvBatch([make_record(g_env, g_car)])
+    words, count, order = ops.rs_all_paths(sg, MAXC, 0.2, envs=envs, flags=ops.CHECK_OBSTACLES | ops.CHECK_BOUNDARY)
+    w = ops.rs_words_to_host(words)
+    order = order.cpu().numpy()
+    count = count.cpu().numpy()
+    search = OP.HybridAStarSearch([0, 0, 0], [1, 1, 0], o_env, o_car, None, motion_type="King", plan_resolution=0.2)
+    n_free = 0
+    for i in range(n):
+        node = OP.Node((0, 0, 0), [list(sg[i, :3])], [0], 0, [1], (0, 0, 0))
+        search.goal_node = OP.Node((0, 0, 0), [list(sg[i, 3:])], [0], 0, [1], (0, 0, 0))
+        ref = search.rs_candidates_in_pop_order(node)
+        assert count[i] == len(ref)
+        got_order = [int(w["cand"][i, k]) for k in order[i, :count[i]]]
+        assert got_order == [p.cand for p, _ in ref], i
+        for (p, cost), k in zip(ref, order[i, :count[i]]):
+            assert w["cost"][i, k] == cost
+            traj = np.array([p.x, p.y, p.yaw]).T
+            want = not o_env.check_path_feasibility(o_car, traj)
+            assert bool(w["collide"][i, k]) == want, (i, k)
+            n_free += (not want)
+    assert n_free > 20
