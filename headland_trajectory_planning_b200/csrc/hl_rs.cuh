@@ -22,7 +22,7 @@ struct RsRow { unsigned char solver, neg_x, neg_y, backwards, pattern, nseg; uns
     {solver, 0, 0, back, pat, n, pos}, {solver, 1, 0, back, pat, n, pos},           \
     {solver, 0, 1, back, pat, n, neg}, {solver, 1, 1, back, pat, n, neg}
 
-__constant__ RsRow c_rs_rows[HL_RS_CANDIDATES] = {
+static __constant__ RsRow c_rs_rows[HL_RS_CANDIDATES] = {
     {RS_SLS, 0, 0, 0, RP_TUV, 3, RS_LET3(RS_S, RS_L, RS_S)},
     {RS_SLS, 0, 1, 0, RP_TUV, 3, RS_LET3(RS_S, RS_R, RS_S)},
     RS_QUAD(RS_LSL, 0, RP_TUV, 3, RS_LET3(RS_L, RS_S, RS_L), RS_LET3(RS_R, RS_S, RS_R)),
@@ -48,7 +48,7 @@ __device__ __forceinline__ void rs_polar(double x, double y, double& r, double& 
     th = atan2(y, x);
 }
 
-__device__ bool rs_solve(int solver, double x, double y, double phi, double& t, double& u, double& v) {
+static __device__ bool rs_solve(int solver, double x, double y, double phi, double& t, double& u, double& v) {
     const double PI = HL_PI;
     switch (solver) {
     case RS_SLS: {                                              // reeds_shepp.py:144-160
@@ -193,7 +193,7 @@ __device__ __forceinline__ RsProblem rs_normalise(const double* q0, const double
 }
 
 // Evaluate candidate row `cand`: returns validity, writes nseg normalised lengths.
-__device__ bool rs_candidate(int cand, const RsProblem& P, double* lens) {
+static __device__ bool rs_candidate(int cand, const RsProblem& P, double* lens) {
     const RsRow row = c_rs_rows[cand];
     double ax = row.backwards ? P.xb : P.x, ay = row.backwards ? P.yb : P.y;
     if (row.neg_x) ax = -ax;
@@ -221,7 +221,7 @@ __device__ bool rs_candidate(int cand, const RsProblem& P, double* lens) {
 //   valid[c], lens[c][5]  : candidate results
 //   acc[k]                : accepted candidate indices (reference order)
 //   L[k]                  : normalised total length
-__device__ int rs_select(const unsigned char* valid, const double (*lens)[HL_RS_MAX_SEGS], int* acc, double* L) {
+static __device__ int rs_select(const unsigned char* valid, const double (*lens)[HL_RS_MAX_SEGS], int* acc, double* L) {
     int n = 0;
     for (int c = 0; c < HL_RS_CANDIDATES; ++c) {
         if (!valid[c]) continue;
@@ -248,7 +248,7 @@ __device__ int rs_select(const unsigned char* valid, const double (*lens)[HL_RS_
 // calculate_reeds_shepp_path_cost (hybrid_a_star_search.py:129-160) with the quirks:
 // +DIRECTION_CHANGE_COST and +MAX_STEER always (len(np.where(..)) == 1); 'L' arcs steer 0.
 // Lengths here may be normalised or metric: only signs matter.
-__device__ double rs_path_cost(double node_cost, int cand, const double* lens, double max_steer,
+static __device__ double rs_path_cost(double node_cost, int cand, const double* lens, double max_steer,
                                double reverse_cost, double dir_change_cost, double steer_cost) {
     const RsRow row = c_rs_rows[cand];
     int nneg = 0;
@@ -268,7 +268,7 @@ __device__ double rs_path_cost(double node_cost, int cand, const double* lens, d
 
 // heapdict pop order of n entries inserted in index order with the given priorities
 // (hybrid_a_star_search.py:265-271).  order[] receives the indices in pop order.
-__device__ void heapdict_order(const double* prio, int n, int* order) {
+static __device__ void heapdict_order(const double* prio, int n, int* order) {
     int heap[HL_RS_CANDIDATES];
     int m = 0;
     for (int k = 0; k < n; ++k) {                 // __setitem__: append + _decrease_key
@@ -334,7 +334,7 @@ __device__ __forceinline__ void rs_interp(double l, int letter, double maxc, dou
 // Build the per-segment plan of one word.  `lens` normalised, step = step_size*maxc.
 // The loop offsets are accumulated by repeated addition exactly like the reference, so
 // the sample count is bit-exact.
-__device__ void rs_make_plan(int cand, const double* lens, double maxc, double step, RsPlan& P) {
+static __device__ void rs_make_plan(int cand, const double* lens, double maxc, double step, RsPlan& P) {
     const RsRow row = c_rs_rows[cand];
     P.nseg = row.nseg;
     P.dir0 = (lens[0] > 0.0) ? 1 : -1;
@@ -388,7 +388,7 @@ __device__ void rs_make_plan(int cand, const double* lens, double maxc, double s
 
 // Pose j (0 <= j < npts) of a planned word in the LOCAL frame, plus curvature sign and
 // direction tag.  Loop offsets use pd0 + k*d (differs from the repeated sum by <1e-12).
-__device__ void rs_sample_local(const RsPlan& P, int j, double maxc, double& px, double& py, double& pyaw,
+static __device__ void rs_sample_local(const RsPlan& P, int j, double maxc, double& px, double& py, double& pyaw,
                                 int& cs_sign, int& dir) {
     if (j == 0) { px = 0.0; py = 0.0; pyaw = 0.0; cs_sign = 0; dir = P.dir0; return; }
     int si = P.nseg - 1;

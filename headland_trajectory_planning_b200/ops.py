@@ -107,3 +107,43 @@ def rs_sample(starts, words_host, maxc, step):
                                 _lib.ptr(cs), _lib.ptr(dr), _lib.stream_ptr()), "hl_rs_sample")
     return (offset, x[:total].cpu().numpy(), y[:total].cpu().numpy(), yaw[:total].cpu().numpy(),
             cs[:total].cpu().numpy(), dr[:total].cpu().numpy())
+
+
+def hybrid_astar_batch(envs, scenarios, params, path_capacity=None, to_host=True):
+    """Run ``hl_hybrid_astar_batch`` on a batch of scenarios.
+
+    ``scenarios``: numpy structured array (``_lib.SCENARIO_DTYPE``) on the host (it is
+    copied to the device inside this call) or a uint8 CUDA tensor of the same bytes.
+    Returns a dict with ``results`` (structured), ``expanded`` [B, max_nodes+2, 3] int32 and
+    the pooled path arrays (host numpy when ``to_host``)."""
+    torch = _torch()
+    lib = _lib.load_library()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    if torch.is_tensor(scenarios):
+        d_scen = scenarios
+        n = d_scen.numel() // _lib.SCENARIO_DTYPE.itemsize
+    else:
+        n = len(scenarios)
+        d_scen = torch.from_numpy(np.ascontiguousarray(scenarios).view(np.uint8).reshape(-1)).to(dev, non_blocking=True)
+    if path_capacity is None:
+        path_capacity = max(4096, 1024 * n)
+    mn = params.max_nodes
+    results = torch.empty(n * _lib.RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    expanded = torch.empty((n, mn + 2, 3), dtype=torch.int32, device=dev)
+    px = torch.empty(path_capacity, dtype=torch.float64, device=dev)
+    py = torch.empty_like(px); pyaw = torch.empty_like(px); pk = torch.empty_like(px)
+    pdir = torch.empty(path_capacity, dtype=torch.int8, device=dev)
+    cursor = torch.zeros(1, dtype=torch.int64, device=dev)
+    _lib.check(lib.hl_hybrid_astar_batch(envs.ctx, envs.handle, _lib.ptr(d_scen), n, C.byref(params),
+                                         _lib.ptr(results), _lib.ptr(expanded), _lib.ptr(px), _lib.ptr(py),
+                                         _lib.ptr(pyaw), _lib.ptr(pk), _lib.ptr(pdir), path_capacity,
+                                         _lib.ptr(cursor), _lib.stream_ptr()), "hl_hybrid_astar_batch")
+    out = dict(results=results, expanded=expanded, x=px, y=py, yaw=pyaw, k=pk, dir=pdir, cursor=cursor, n=n)
+    if to_host:
+        used = int(cursor.item())
+        out["results"] = results.cpu().numpy().view(_lib.RESULT_DTYPE)
+        out["expanded"] = expanded.cpu().numpy()
+        for key in ("x", "y", "yaw", "k", "dir"):
+            out[key] = out[key][:min(used, path_capacity)].cpu().numpy()
+        out["used"] = used
+    return out

@@ -70,7 +70,7 @@ def test_touching_counts_as_collision(built_library):
     rows = np.array([[[0.0, 2.0 * i], [20.0, 2.0 * i]] for i in range(8)])
     (o_env, o_car, _), (g_env, g_car, _) = H.make_pair(rows, tree_width=0.5, headland_width=8.0)
     # rows occupy y in [2i-0.25, 2i+0.25]; body half width 0.74 -> touching at y = 2i + 0.25 + 0.74
-    ys = np.array([0.25 + 0.74, 0.25 + 0.74 + 1e-9, 0.25 + 0.74 - 1e-9, 1.0])
+    ys = np.array([0.25 + 0.74, 0.25 + 0.74 + 1e-9, 0.25 + 0.74 - 1e-9, 0.9])
     poses = np.stack([np.full(4, 5.0), ys, np.zeros(4)], axis=1)
     want = o_env.pose_flags(o_car, poses, boundary_check=False)
     got = g_env.pose_flags(g_car, poses, boundary_check=False)
