@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py -- warm-start plans/sec on B200 (BASELINE.json metric), config 5:
+synthetic headland scenarios (varied row spacing, headland width, vehicle length), King
+mode, step 0.2 m, max_nodes 400, sharded over the GPUs of one box.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm
+    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU reference arm
+
+One "step" = one pass of the batched Hybrid A* search over this rank's scenarios.
+`value` = scenarios of ALL ranks / max-over-ranks device time with environments and
+scenarios already resident in HBM; `e2e` = the same through the host-buffer API (H2D of
+environment geometry + scenario records, search, D2H of result records, expanded-key
+sequences and paths, plus the NCCL gather to rank 0 when N > 1).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "warm_start_plans_per_sec"
+UNIT = "plans/s"
+WORKLOAD = "config5: synthetic headland scenarios (8 rows, row spacing U(2.2,4.0) m, headland U(5,9) m, " \
+           "axle_to_front U(2.85,4.5) m), King, step 0.2 m, max_nodes 400"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scenarios-per-gpu", type=int, default=4096)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="scenarios in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--collision-poses", type=int, default=1 << 24)
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[2 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def scenario_indices(args, rank, world):
+    total = args.scenarios_per_gpu * world
+    return list(range(rank, total, world)), total
+
+
+def cpu_sample_size(args, cores):
+    return args.cpu_sample if args.cpu_sample > 0 else int(min(128, max(8, 4 * cores)))
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle port of the reference's Python path on the host cores."""
+    if rank != 0:
+        return
+    from oracle import baseline as OB
+    from headland_trajectory_planning_b200 import scenarios as SC
+    cores = os.cpu_count() or 1
+    steps_total = max(1, args.steps + args.warmup)
+    # size the per-step sample so that the whole run stays within a few minutes:
+    # ~6 s of search per scenario on average, spread over `cores` workers
+    budget_s = 150.0 / steps_total
+    n = args.cpu_sample if args.cpu_sample > 0 else int(max(2, min(64, budget_s * cores / 6.0)))
+    specs = [SC.scenario_spec(i) for i in range(n)]
+    scns = [SC.finalize(sp, OB.candidate_feasibility(sp)) for sp in specs]
+    for _ in range(args.warmup):
+        OB.run_pool(scns[: max(1, n // 8)], cores)
+    wall = 0.0
+    for _ in range(args.steps):
+        _, dt, used = OB.run_pool(scns, cores)
+        wall += dt
+    value = n * args.steps / wall
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": f"scenarios 0..{n - 1} per step"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "port",
+                             "sample": f"scenarios 0..{n - 1} of the workload, oracle port (shapely/heapdict "
+                                       f"unavailable), multiprocessing.Pool({used})"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    import torch
+    import torch.distributed as dist
+    from headland_trajectory_planning_b200 import _lib, ops, scenarios as SC, sweep
+    from headland_trajectory_planning_b200.env_batch import EnvBatch
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    # ---------------- setup (untimed): scenarios, host geometry, resident copies
+    idx, total = scenario_indices(args, rank, world)
+    t_setup = time.time()
+    scns = SC.make_scenarios_gpu(idx)
+    recs, scen, car = sweep.build_records(scns)
+    params = sweep.search_params(car)
+    envs = EnvBatch(recs)
+    n = len(scns)
+    path_cap = 1024 * n
+    d_scen = torch.from_numpy(scen.view(np.uint8).reshape(-1)).to(dev)
+    setup_s = time.time() - t_setup
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident steps
+    for _ in range(args.warmup):
+        out = ops.hybrid_astar_batch(envs, d_scen, params, path_capacity=path_cap, to_host=False)
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        for s in range(args.steps):
+            flush.fill_(s & 0xFF)                       # L2 flush between timed iterations
+            ev[s][0].record()
+            out = ops.hybrid_astar_batch(envs, d_scen, params, path_capacity=path_cap, to_host=False)
+            ev[s][1].record()
+        barrier()
+    kernel_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([kernel_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    max_ms = float(t.item())
+    value = total * args.steps / (max_ms * 1e-3)
+
+    res = out["results"].cpu().numpy().view(_lib.RESULT_DTYPE)
+    flops = sweep.algorithmic_flops(recs, res)
+    n_checks = int(res["n_pose_checks"].sum())
+    n_exact = int(res["n_exact"].sum())
+    status_hist = {_lib.STATUS_NAMES[int(k)]: int(v) for k, v in zip(*np.unique(res["status"], return_counts=True))}
+    expansions = int(res["n_expanded"].sum())
+
+    # ---------------- end-to-end steps: host buffers in, host buffers out
+    host_scen = torch.from_numpy(scen.view(np.uint8).reshape(-1).copy()).pin_memory()
+    h2d = int(sum(r.obs.nbytes + r.field.nbytes + r.seg_xy.nbytes + r.seg_polys.nbytes + r.seg_len.nbytes +
+                  r.crit.nbytes + r.guide.nbytes + r.aux.nbytes + 32 for r in recs) + host_scen.numel())
+    d2h = 0
+    e2e_wall = 0.0
+    for s in range(min(2, args.warmup) + args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        envs_e = EnvBatch(recs)                                             # H2D environment geometry
+        d_s = host_scen.to(dev, non_blocking=True)                          # H2D scenario records
+        o = ops.hybrid_astar_batch(envs_e, d_s, params, path_capacity=path_cap, to_host=True)   # search + D2H
+        if world > 1:
+            sweep.gather_results(o["results"], o["expanded"], world, rank)   # NCCL gather to rank 0
+        barrier()
+        dt = time.perf_counter() - t0
+        envs_e.close()
+        if s >= min(2, args.warmup):
+            e2e_wall += dt
+            d2h = int(o["results"].nbytes + o["expanded"].nbytes + sum(o[k].nbytes for k in ("x", "y", "yaw", "k", "dir")))
+    t = torch.tensor([e2e_wall], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = total * args.steps / float(t.item())
+
+    # ---------------- secondary: stand-alone collision kernel (M2) on the canonical scenario
+    coll = None
+    fp32_peak = None
+    if rank == 0:
+        fp32_peak = ops.measure_fp32_peak(local_rank)
+        coll = collision_microbench(args, dev, fp32_peak)
+
+    # ---------------- CPU baseline (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import baseline as OB
+        cores = os.cpu_count() or 1
+        m = min(n, cpu_sample_size(args, cores))
+        _, dt, used = OB.run_pool(scns[:m], cores)
+        cpu = {"value": m / dt, "unit": UNIT, "cores": used, "kind": "port",
+               "sample": f"first {m} scenarios of rank 0's shard, oracle port of the reference's Python path "
+                         f"(shapely/heapdict unavailable), multiprocessing.Pool({used}), search time only"}
+
+    if rank == 0:
+        ms_per_launch = max_ms / args.steps
+        achieved = flops / (kernel_ms / args.steps * 1e-3) * 1e-12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_launch, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "scenarios_per_gpu": args.scenarios_per_gpu, "total_scenarios": total,
+                       "sharding": "scenario i -> rank i mod N", "l2": "flushed (256 MiB fill) between timed iterations",
+                       "setup_s_untimed": round(setup_s, 1)},
+            "clocks": clocks.summary(),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": args.steps,
+            "roofline": {"bound": "alu_fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+                         "frac": achieved / fp32_peak if fp32_peak else None, "traffic": None,
+                         "kernel": "k_hybrid_astar",
+                         "note": "no tensor cores on this path; algorithmic flop = executed footprint checks x "
+                                 "F_check (SURVEY 8d); peak = FFMA micro-benchmark measured in this run; the kernel "
+                                 "is a latency-bound search, see kernels.k_collision for the ALU-bound kernel"},
+            "kernels": {"k_collision": coll},
+            "search": {"expansions": expansions, "pose_checks": n_checks, "exact_escalations": n_exact,
+                       "status": status_hist},
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def collision_microbench(args, dev, fp32_peak):
+    """Footprint collision checks/sec (metric M2) of hl_collision_check on the canonical
+    scenario (8 tree rows, 16-vertex field polygon, 4-segment lane; obstacles + boundary +
+    lane, body only), poses resident in HBM, CUDA-event timed, L2 flushed."""
+    import math
+    import torch
+    from headland_trajectory_planning_b200 import ops
+    from headland_trajectory_planning_b200.car_model import CarModel
+    from headland_trajectory_planning_b200.env_batch import EnvBatch, make_record
+    from headland_trajectory_planning_b200.orchard_geometry_environment import OrchardGeometryEnvironment
+    from headland_trajectory_planning_b200.reference_line_heuristic import ReferenceLineHeuristic
+    from headland_trajectory_planning_b200.utils import map_utils
+    np.random.seed(1)
+    rows = map_utils.create_tree_rows(8, 2.5, 20, slope_angle=math.radians(10), l_std=0.0)
+    env = OrchardGeometryEnvironment(rows, [], tree_width=0.3, headland_width=6.0)
+    car = CarModel(max_steer=0.55, axle_to_front=3, axle_to_back=0.55, width=1.48)
+    ends = rows[:, 0, :]
+    way = np.vstack(([0.88, 3.75], [[ends[i, 0] - 4.5, ends[i, 1]] for i in (2, 3, 4)], [-1.2, 11.25]))
+    heur = ReferenceLineHeuristic(way, [-1.2, 11.25, 0.0], car)
+    envs = EnvBatch([make_record(env, car, heur)])
+    n = args.collision_poses
+    g = torch.Generator(device=dev).manual_seed(0)
+    poses = torch.empty((n, 3), dtype=torch.float64, device=dev)
+    poses[:, 0] = torch.rand(n, generator=g, device=dev, dtype=torch.float64) * 14.0 - 10.0
+    poses[:, 1] = torch.rand(n, generator=g, device=dev, dtype=torch.float64) * 22.0 - 2.0
+    poses[:, 2] = (torch.rand(n, generator=g, device=dev, dtype=torch.float64) * 2.0 - 1.0) * math.pi
+    flags = ops.CHECK_OBSTACLES | ops.CHECK_BOUNDARY | ops.CHECK_LANE
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(3):
+        out, nex = ops.collision_check(envs, poses, flags=flags, count_exact=True)
+    torch.cuda.synchronize()
+    ms = 0.0
+    reps = 5
+    for r in range(reps):
+        flush.fill_(r)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = ops.collision_check(envs, poses, flags=flags)
+        b.record()
+        torch.cuda.synchronize()
+        ms += a.elapsed_time(b)
+    ms /= reps
+    f_check = 32 + 128 * 8 + 80 * 16 + 48 * 4
+    checks = n / (ms * 1e-3)
+    achieved = checks * f_check * 1e-12
+    return {"metric": "footprint_collision_checks_per_sec", "value": checks, "unit": "checks/s", "poses": n,
+            "ms_per_launch": ms, "f_check_flop": f_check, "infeasible_frac": float(out.float().mean().item()),
+            "exact_escalation_frac": float(nex.item()) / n,
+            "roofline": {"bound": "alu_fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+                         "frac": achieved / fp32_peak if fp32_peak else None,
+                         "hbm_GBps": checks * 25 * 1e-9, "traffic": None}}
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,276 @@
+// hl_grid.cu -- K6: holonomic grid distance field; K7: occupancy-grid footprint check.
+//
+// K6 replaces holonomic_costs_with_obstacles (path_planner/utils/a_star_utils.py:75-142).
+// The reference runs a binary-heap Dijkstra from the goal cell with edge costs 1 and
+// hypot(1,1) accumulated as sequential float64 sums.  Because fl(d + w) is monotone in d,
+// its result is the least fixed point of D(v) = min_m fl(D(v - m) + w(m)), which ANY
+// relaxation order reaches bit-exactly in float64 -- so the GPU runs a tiled wavefront:
+// a CTA pulls a 32x32 tile (+1 halo) into shared memory, relaxes it to its local fixed
+// point there, writes it back and flags the neighbouring tiles whose halo changed.  Only
+// flagged tiles do work in the next launch (the frontier), so the traffic per launch is
+// the frontier's, not the map's.  Roofline: nominally HBM, really launch/dependency
+// depth.
+//
+// K7 is the grid-based footprint check the reference left commented out
+// (orchard_geometry_environment.py:8,35-43,460-461) on the grid layout of
+// occupancy_grid_utils.py:70-101; parity unpinned (no reference implementation).
+#include <cstring>
+#include "hl_common.cuh"
+
+#define DF_TILE 32
+#define DF_THREADS 256
+
+struct DfMoves { int n; int di[8]; int dj[8]; double w[8]; };
+
+__global__ void k_df_init(const uint8_t* __restrict__ occ, int W, int H, int gi, int gj, double* __restrict__ out,
+                          unsigned char* __restrict__ dirty, int tiles_i, int tiles_j, int* __restrict__ bad) {
+    long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (idx >= (long long)W * H) return;
+    int i = (int)(idx / H), j = (int)(idx % H);
+    out[idx] = (i == gi && j == gj) ? 0.0 : INFINITY;
+    if ((i == 0 || j == 0 || i == W - 1 || j == H - 1) && !occ[idx]) atomicOr(bad, 1);   // open border: wrap quirk reachable
+    if (i == gi && j == gj) {
+        int ti = i / DF_TILE, tj = j / DF_TILE;
+        for (int a = -1; a <= 1; ++a)
+            for (int b = -1; b <= 1; ++b) {
+                int x = ti + a, y = tj + b;
+                if (x >= 0 && y >= 0 && x < tiles_i && y < tiles_j) dirty[x * tiles_j + y] = 1;
+            }
+    }
+}
+
+__global__ void __launch_bounds__(DF_THREADS)
+k_df_relax(const uint8_t* __restrict__ occ, int W, int H, int gi, int gj, DfMoves mv, double* __restrict__ D,
+           const unsigned char* __restrict__ dirty_cur, unsigned char* __restrict__ dirty_next, int tiles_i,
+           int tiles_j, int* __restrict__ any_next) {
+    const int tile = blockIdx.x;
+    if (!dirty_cur[tile]) return;
+    __shared__ double sd[DF_TILE + 2][DF_TILE + 3];
+    __shared__ unsigned char so[DF_TILE + 2][DF_TILE + 2];
+    __shared__ int s_border_changed;
+    const int ti = tile / tiles_j, tj = tile % tiles_j;
+    const int i0 = ti * DF_TILE - 1, j0 = tj * DF_TILE - 1;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_border_changed = 0;
+    for (int k = tid; k < (DF_TILE + 2) * (DF_TILE + 2); k += DF_THREADS) {
+        int a = k / (DF_TILE + 2), b = k % (DF_TILE + 2);
+        int i = i0 + a, j = j0 + b;
+        bool in = i >= 0 && j >= 0 && i < W && j < H;
+        sd[a][b] = in ? D[(long long)i * H + j] : INFINITY;
+        so[a][b] = in ? occ[(long long)i * H + j] : 1;
+    }
+    __syncthreads();
+    // each thread owns 4 interior cells; remember their initial values
+    double init[4];
+    int ca[4], cb[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        int k = tid + q * DF_THREADS;
+        ca[q] = 1 + k / DF_TILE; cb[q] = 1 + k % DF_TILE;
+        init[q] = sd[ca[q]][cb[q]];
+    }
+    while (true) {
+        int changed = 0;
+        double nv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int a = ca[q], b = cb[q];
+            double best = sd[a][b];
+            const int gi_ = i0 + a, gj_ = j0 + b;
+            // occupied cells are never entered (the goal cell itself is exempt: it starts closed at 0)
+            if (!so[a][b] && gi_ < W && gj_ < H) {
+                for (int m = 0; m < mv.n; ++m) {
+                    double u = sd[a - mv.di[m]][b - mv.dj[m]];          // predecessor v - m
+                    double c = __dadd_rn(u, mv.w[m]);
+                    if (c < best) best = c;
+                }
+            }
+            nv[q] = best;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (nv[q] < sd[ca[q]][cb[q]]) { sd[ca[q]][cb[q]] = nv[q]; changed = 1; }
+        if (!__syncthreads_or(changed)) break;
+    }
+    int my_border = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int a = ca[q], b = cb[q];
+        const int i = i0 + a, j = j0 + b;
+        double v = sd[a][b];
+        if (v < init[q] && i < W && j < H) {
+            D[(long long)i * H + j] = v;
+            if (a == 1 || b == 1 || a == DF_TILE || b == DF_TILE) my_border = 1;
+        }
+    }
+    if (my_border) s_border_changed = 1;
+    __syncthreads();
+    if (tid == 0 && s_border_changed) {
+        for (int a = -1; a <= 1; ++a)
+            for (int b = -1; b <= 1; ++b) {
+                int x = ti + a, y = tj + b;
+                if ((a || b) && x >= 0 && y >= 0 && x < tiles_i && y < tiles_j) dirty_next[x * tiles_j + y] = 1;
+            }
+        *any_next = 1;
+    }
+}
+
+extern "C" int hl_distance_field(hl_ctx* ctx, const uint8_t* d_occ, int32_t w, int32_t h, int32_t gi,
+                                 int32_t gj, int32_t motion_type, double* d_out, int32_t* h_sweeps,
+                                 void* stream) {
+    if (!ctx || !d_occ || !d_out || w < 3 || h < 3) { hl_set_error("hl_distance_field: bad arguments"); return 1; }
+    if (gi <= 0 || gj <= 0 || gi >= w - 1 || gj >= h - 1) {
+        hl_set_error("hl_distance_field: goal (%d,%d) must be strictly inside the occupied border", gi, gj);
+        return 1;
+    }
+    HL_CUDA_OK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    DfMoves mv;
+    memset(&mv, 0, sizeof(mv));
+    if (motion_type == 0) {                 // a_star_utils.py:8-21
+        const int k[8][2] = {{-1, 0}, {-1, 1}, {0, 1}, {1, 1}, {1, 0}, {1, -1}, {0, -1}, {-1, -1}};
+        mv.n = 8;
+        for (int m = 0; m < 8; ++m) { mv.di[m] = k[m][0]; mv.dj[m] = k[m][1]; mv.w[m] = hypot((double)k[m][0], (double)k[m][1]); }
+    } else if (motion_type == 1) {          // :24-34
+        const int k[5][2] = {{-1, 0}, {0, 1}, {-1, 1}, {1, 1}, {1, 0}};
+        mv.n = 5;
+        for (int m = 0; m < 5; ++m) { mv.di[m] = k[m][0]; mv.dj[m] = k[m][1]; mv.w[m] = hypot((double)k[m][0], (double)k[m][1]); }
+    } else { hl_set_error("hl_distance_field: motion_type must be 0 (King) or 1 (Pawn)"); return 1; }
+    const int tiles_i = (w + DF_TILE - 1) / DF_TILE, tiles_j = (h + DF_TILE - 1) / DF_TILE;
+    const int n_tiles = tiles_i * tiles_j;
+    unsigned char* dirty = nullptr;
+    int* flags = nullptr;
+    HL_CUDA_OK(cudaMalloc(&dirty, 2 * (size_t)n_tiles));
+    HL_CUDA_OK(cudaMalloc(&flags, 2 * sizeof(int)));
+    HL_CUDA_OK(cudaMemsetAsync(dirty, 0, 2 * (size_t)n_tiles, st));
+    HL_CUDA_OK(cudaMemsetAsync(flags, 0, 2 * sizeof(int), st));
+    long long cells = (long long)w * h;
+    k_df_init<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(d_occ, w, h, gi, gj, d_out, dirty, tiles_i, tiles_j, flags);
+    int host_flags[2] = {0, 0};
+    HL_CUDA_OK(cudaMemcpyAsync(host_flags, flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+    HL_CUDA_OK(cudaStreamSynchronize(st));
+    if (host_flags[0]) {
+        cudaFree(dirty); cudaFree(flags);
+        hl_set_error("hl_distance_field: the grid border is not fully occupied; the reference's index wrap-around "
+                     "(a_star_utils.py:54-61) would be reachable and is not reproduced");
+        return 1;
+    }
+    unsigned char* cur = dirty;
+    unsigned char* nxt = dirty + n_tiles;
+    int sweeps = 0;
+    const int max_sweeps = 8 * (tiles_i + tiles_j) * DF_TILE + 64;
+    while (sweeps < max_sweeps) {
+        HL_CUDA_OK(cudaMemsetAsync(nxt, 0, n_tiles, st));
+        HL_CUDA_OK(cudaMemsetAsync(flags + 1, 0, sizeof(int), st));
+        k_df_relax<<<n_tiles, DF_THREADS, 0, st>>>(d_occ, w, h, gi, gj, mv, d_out, cur, nxt, tiles_i, tiles_j, flags + 1);
+        ++sweeps;
+        HL_CUDA_OK(cudaMemcpyAsync(host_flags + 1, flags + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+        HL_CUDA_OK(cudaStreamSynchronize(st));
+        if (!host_flags[1]) break;
+        unsigned char* t = cur; cur = nxt; nxt = t;
+    }
+    HL_CUDA_OK(cudaGetLastError());
+    cudaFree(dirty); cudaFree(flags);
+    if (h_sweeps) *h_sweeps = sweeps;
+    if (sweeps >= max_sweeps) { hl_set_error("hl_distance_field: no convergence after %d launches", sweeps); return 1; }
+    return 0;
+}
+
+// ------------------------------------------------------------------------- K7
+__global__ void k_grid_pack(const uint8_t* __restrict__ occ, long long cells, uint32_t* __restrict__ bits) {
+    long long wd = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long n_words = (cells + 31) / 32;
+    if (wd >= n_words) return;
+    uint32_t v = 0;
+    for (int b = 0; b < 32; ++b) {
+        long long c = wd * 32 + b;
+        if (c < cells && occ[c]) v |= 1u << b;
+    }
+    bits[wd] = v;
+}
+
+extern "C" int hl_grid_pack(hl_ctx* ctx, const uint8_t* d_occ, int32_t w, int32_t h, uint32_t* d_bits, void* stream) {
+    if (!ctx || !d_occ || !d_bits || w <= 0 || h <= 0) { hl_set_error("hl_grid_pack: bad arguments"); return 1; }
+    HL_CUDA_OK(cudaSetDevice(ctx->device));
+    long long cells = (long long)w * h, n_words = (cells + 31) / 32;
+    k_grid_pack<<<(unsigned)((n_words + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_occ, cells, d_bits);
+    HL_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// any occupied bit among cells (i, j0..j1) of the bit-packed grid
+__device__ __forceinline__ bool row_any(const uint32_t* __restrict__ bits, long long base, int j0, int j1) {
+    long long a = base + j0, b = base + j1;
+    long long wa = a >> 5, wb = b >> 5;
+    for (long long wd = wa; wd <= wb; ++wd) {
+        uint32_t m = 0xFFFFFFFFu;
+        if (wd == wa) m &= 0xFFFFFFFFu << (a & 31);
+        if (wd == wb) m &= 0xFFFFFFFFu >> (31 - (b & 31));
+        if (__ldg(bits + wd) & m) return true;
+    }
+    return false;
+}
+
+__global__ void __launch_bounds__(256)
+k_grid_footprint(const uint32_t* __restrict__ bits, int W, int H, double res, const double* __restrict__ poses,
+                 long long n, double x0, double x1, double y0, double y1, uint8_t* __restrict__ out) {
+    long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const double px = poses[3 * idx], py = poses[3 * idx + 1], yaw = poses[3 * idx + 2];
+    const double c = cos(yaw), s = sin(yaw);
+    const double lx[4] = {x0, x0, x1, x1}, ly[4] = {y1, y0, y0, y1};
+    double cx[4], cy[4];
+    double xmin = INFINITY, xmax = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        cx[k] = xadd(xsub(xmul(c, lx[k]), xmul(s, ly[k])), px);
+        cy[k] = xadd(xadd(xmul(s, lx[k]), xmul(c, ly[k])), py);
+        xmin = fmin(xmin, cx[k]); xmax = fmax(xmax, cx[k]);
+    }
+    int ia = (int)floor(xmin / res), ib = (int)floor(xmax / res);
+    // a rectangle that touches x = i*res from above also meets cell i-1 (closed sets)
+    if ((double)ia * res == xmin) ia -= 1;
+    ia = max(ia, 0); ib = min(ib, W - 1);
+    bool hit = false;
+    for (int i = ia; i <= ib && !hit; ++i) {
+        const double a = (double)i * res, b = (double)(i + 1) * res;
+        double ymin = INFINITY, ymax = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (cx[k] >= a && cx[k] <= b) { ymin = fmin(ymin, cy[k]); ymax = fmax(ymax, cy[k]); }
+            const int k2 = (k + 1) & 3;
+            const double ex = cx[k2] - cx[k];
+            if (ex != 0.0) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const double X = e ? b : a;
+                    if ((cx[k] - X) * (cx[k2] - X) < 0.0) {
+                        double y = cy[k] + (X - cx[k]) * (cy[k2] - cy[k]) / ex;
+                        ymin = fmin(ymin, y); ymax = fmax(ymax, y);
+                    }
+                }
+            }
+        }
+        if (ymin > ymax) continue;
+        int ja = (int)floor(ymin / res), jb = (int)floor(ymax / res);
+        if ((double)ja * res == ymin) ja -= 1;
+        ja = max(ja, 0); jb = min(jb, H - 1);
+        if (ja <= jb) hit = row_any(bits, (long long)i * H, ja, jb);
+    }
+    out[idx] = hit ? 1 : 0;
+}
+
+extern "C" int hl_grid_footprint_check(hl_ctx* ctx, const uint32_t* d_occ_bits, int32_t w, int32_t h,
+                                       double res, const double* d_poses, int64_t n,
+                                       const double body_ext[4], uint8_t* d_out, void* stream) {
+    if (!ctx || !d_occ_bits || !d_poses || !d_out || !body_ext || n < 0 || w <= 0 || h <= 0 || !(res > 0)) {
+        hl_set_error("hl_grid_footprint_check: bad arguments"); return 1;
+    }
+    if (n == 0) return 0;
+    HL_CUDA_OK(cudaSetDevice(ctx->device));
+    k_grid_footprint<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        d_occ_bits, w, h, res, d_poses, (long long)n, body_ext[0], body_ext[1], body_ext[2], body_ext[3], d_out);
+    HL_CUDA_OK(cudaGetLastError());
+    return 0;
+}

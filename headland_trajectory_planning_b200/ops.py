@@ -30,6 +30,8 @@ def collision_check(envs, poses, env_id=None, pose_idx=None, flags=CHECK_OBSTACL
         pose_idx = torch.from_numpy(np.ascontiguousarray(pose_idx, dtype=np.int32)).to(dev)
     out = torch.empty(n, dtype=torch.uint8, device=dev)
     n_exact = torch.zeros(1, dtype=torch.int64, device=dev) if count_exact else None
+    if n == 0:
+        return (out, n_exact) if count_exact else out
     _lib.check(lib.hl_collision_check(envs.ctx, envs.handle, _lib.ptr(env_id), _lib.ptr(poses),
                                       _lib.ptr(pose_idx), n, flags, _lib.ptr(out), _lib.ptr(n_exact),
                                       _lib.stream_ptr()), "hl_collision_check")
@@ -146,4 +148,53 @@ def hybrid_astar_batch(envs, scenarios, params, path_capacity=None, to_host=True
         for key in ("x", "y", "yaw", "k", "dir"):
             out[key] = out[key][:min(used, path_capacity)].cpu().numpy()
         out["used"] = used
+    return out
+
+
+def distance_field(occ, goal, motion_type="King"):
+    """Grid distance field from ``goal`` (hl_distance_field).  ``occ``: [W,H] bool/uint8
+    (host array or CUDA tensor).  Returns (float64 CUDA tensor [W,H], relaxation launches)."""
+    torch = _torch()
+    lib = _lib.load_library()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    if not torch.is_tensor(occ):
+        occ = torch.from_numpy(np.ascontiguousarray(np.asarray(occ).astype(np.uint8))).to(dev)
+    occ = occ.to(torch.uint8).contiguous()
+    w, h = occ.shape
+    out = torch.empty((w, h), dtype=torch.float64, device=dev)
+    sweeps = C.c_int32(0)
+    mt = {"King": 0, "Pawn": 1}[motion_type]
+    _lib.check(lib.hl_distance_field(_lib.get_ctx(), _lib.ptr(occ), w, h, int(goal[0]), int(goal[1]), mt,
+                                     _lib.ptr(out), C.byref(sweeps), _lib.stream_ptr()), "hl_distance_field")
+    return out, sweeps.value
+
+
+def grid_pack(occ):
+    torch = _torch()
+    lib = _lib.load_library()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    if not torch.is_tensor(occ):
+        occ = torch.from_numpy(np.ascontiguousarray(np.asarray(occ).astype(np.uint8))).to(dev)
+    occ = occ.to(torch.uint8).contiguous()
+    w, h = occ.shape
+    bits = torch.empty((w * h + 31) // 32, dtype=torch.int32, device=dev)
+    _lib.check(lib.hl_grid_pack(_lib.get_ctx(), _lib.ptr(occ), w, h, _lib.ptr(bits), _lib.stream_ptr()), "hl_grid_pack")
+    return bits
+
+
+def grid_footprint_check(bits, shape, res, poses, body_ext):
+    torch = _torch()
+    lib = _lib.load_library()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    if not torch.is_tensor(poses):
+        poses = torch.from_numpy(np.ascontiguousarray(np.asarray(poses, dtype=np.float64)[:, :3])).to(dev)
+    poses = poses.contiguous()
+    n = poses.shape[0]
+    out = torch.empty(n, dtype=torch.uint8, device=dev)
+    if n == 0:
+        return out
+    ext = (C.c_double * 4)(*[float(v) for v in body_ext])
+    _lib.check(lib.hl_grid_footprint_check(_lib.get_ctx(), _lib.ptr(bits), int(shape[0]), int(shape[1]), float(res),
+                                           _lib.ptr(poses), n, ext, _lib.ptr(out), _lib.stream_ptr()),
+               "hl_grid_footprint_check")
     return out

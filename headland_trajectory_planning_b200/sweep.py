@@ -1,0 +1,63 @@
+"""Scenario sweeps: shard independent headland scenarios across the GPUs of one box
+(one process per GPU, scenario i -> rank i mod world_size), run the batched search on
+each shard, and gather fixed-stride result records on rank 0 (the only collective).
+"""
+import numpy as np
+
+from . import _lib, ops, scenarios as SC
+from .env_batch import make_record
+from .hybrid_a_star_search import make_search_params, scenario_array
+
+
+def shard_indices(n_total, rank, world_size):
+    """Interleaved shard: evens out the 1..401-expansion imbalance between ranks."""
+    return list(range(rank, n_total, world_size))
+
+
+def build_records(scns):
+    """Host geometry of finalized scenarios -> (EnvRecord list, scenario array, car)."""
+    recs, starts, goals = [], [], []
+    car0 = None
+    for scn in scns:
+        env, car, heur = SC.build_host_objects(scn)
+        car0 = car0 or car
+        recs.append(make_record(env, car, heur))
+        starts.append(scn["start"])
+        goals.append(scn["goal"])
+    scen = scenario_array(np.arange(len(scns), dtype=np.int32), starts, goals)
+    return recs, scen, car0
+
+
+def search_params(car, step_size=0.2, max_nodes=400, max_path_poses=16384):
+    p, _ = make_search_params(car, "King", plan_resolution=step_size, max_nodes=max_nodes,
+                              max_path_poses=max_path_poses)
+    return p
+
+
+def algorithmic_flops(recs, results):
+    """FP32 flop of the footprint checks a sweep executed, SURVEY.md 8(d):
+    F_check = 32 + 128*K + 80*E_f + 48*S per pose rectangle."""
+    total = 0.0
+    for rec, r in zip(recs, results):
+        f = 32 + 128 * len(rec.obs) + 80 * len(rec.field) + 48 * len(rec.seg_xy)
+        total += f * float(r["n_pose_checks"])
+    return total
+
+
+def gather_results(results_np, expanded_np, world_size, rank):
+    """NCCL gather of the fixed-stride records to rank 0 (torch.distributed must be
+    initialised; tensors go through the GPU so the transfer rides NVLink)."""
+    import torch
+    import torch.distributed as dist
+    dev = torch.device("cuda", torch.cuda.current_device())
+    t_res = torch.from_numpy(np.ascontiguousarray(results_np).view(np.uint8).reshape(-1)).to(dev)
+    t_exp = torch.from_numpy(np.ascontiguousarray(expanded_np)).to(dev)
+    if rank == 0:
+        g_res = [torch.empty_like(t_res) for _ in range(world_size)]
+        g_exp = [torch.empty_like(t_exp) for _ in range(world_size)]
+        dist.gather(t_res, g_res, dst=0)
+        dist.gather(t_exp, g_exp, dst=0)
+        return ([g.cpu().numpy().view(_lib.RESULT_DTYPE) for g in g_res], [g.cpu().numpy() for g in g_exp])
+    dist.gather(t_res, None, dst=0)
+    dist.gather(t_exp, None, dst=0)
+    return None, None
