@@ -12,6 +12,14 @@ def _torch():
     return torch
 
 
+def _device():
+    """Current CUDA device; without one every op fails loudly (no CPU fallback)."""
+    import torch
+    if not torch.cuda.is_available():
+        raise _lib.HeadlandError("no CUDA device: headland_trajectory_planning_b200 has no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
 def collision_check(envs, poses, env_id=None, pose_idx=None, flags=CHECK_OBSTACLES | CHECK_BOUNDARY,
                     count_exact=False):
     """Per-pose infeasibility flags (uint8 CUDA tensor).  ``poses``: [N,3] float64
@@ -19,7 +27,7 @@ def collision_check(envs, poses, env_id=None, pose_idx=None, flags=CHECK_OBSTACL
     within its path (implement rectangles are tested at even indices only)."""
     torch = _torch()
     lib = _lib.load_library()
-    dev = torch.device("cuda", torch.cuda.current_device())
+    dev = _device()
     if not torch.is_tensor(poses):
         poses = torch.from_numpy(np.ascontiguousarray(np.asarray(poses, dtype=np.float64)[:, :3])).to(dev)
     poses = poses.contiguous()
@@ -64,7 +72,7 @@ def rs_all_paths(start_goal, maxc, step, max_steer=0.55, envs=None, env_id=None,
     ``rs_words_to_host`` to view the word records."""
     torch = _torch()
     lib = _lib.load_library()
-    dev = torch.device("cuda", torch.cuda.current_device())
+    dev = _device()
     if not torch.is_tensor(start_goal):
         start_goal = torch.from_numpy(np.ascontiguousarray(start_goal, dtype=np.float64)).to(dev)
     start_goal = start_goal.contiguous()
@@ -93,7 +101,7 @@ def rs_sample(starts, words_host, maxc, step):
     Returns host arrays (offset [M+1], x, y, yaw, cs, dir)."""
     torch = _torch()
     lib = _lib.load_library()
-    dev = torch.device("cuda", torch.cuda.current_device())
+    dev = _device()
     m = len(words_host)
     offset = np.zeros(m + 1, dtype=np.int64)
     np.cumsum(words_host["npts"], out=offset[1:])
@@ -120,7 +128,7 @@ def hybrid_astar_batch(envs, scenarios, params, path_capacity=None, to_host=True
     the pooled path arrays (host numpy when ``to_host``)."""
     torch = _torch()
     lib = _lib.load_library()
-    dev = torch.device("cuda", torch.cuda.current_device())
+    dev = _device()
     if torch.is_tensor(scenarios):
         d_scen = scenarios
         n = d_scen.numel() // _lib.SCENARIO_DTYPE.itemsize
@@ -156,7 +164,7 @@ def distance_field(occ, goal, motion_type="King"):
     (host array or CUDA tensor).  Returns (float64 CUDA tensor [W,H], relaxation launches)."""
     torch = _torch()
     lib = _lib.load_library()
-    dev = torch.device("cuda", torch.cuda.current_device())
+    dev = _device()
     if not torch.is_tensor(occ):
         occ = torch.from_numpy(np.ascontiguousarray(np.asarray(occ).astype(np.uint8))).to(dev)
     occ = occ.to(torch.uint8).contiguous()
@@ -172,7 +180,7 @@ def distance_field(occ, goal, motion_type="King"):
 def grid_pack(occ):
     torch = _torch()
     lib = _lib.load_library()
-    dev = torch.device("cuda", torch.cuda.current_device())
+    dev = _device()
     if not torch.is_tensor(occ):
         occ = torch.from_numpy(np.ascontiguousarray(np.asarray(occ).astype(np.uint8))).to(dev)
     occ = occ.to(torch.uint8).contiguous()
@@ -185,7 +193,7 @@ def grid_pack(occ):
 def grid_footprint_check(bits, shape, res, poses, body_ext):
     torch = _torch()
     lib = _lib.load_library()
-    dev = torch.device("cuda", torch.cuda.current_device())
+    dev = _device()
     if not torch.is_tensor(poses):
         poses = torch.from_numpy(np.ascontiguousarray(np.asarray(poses, dtype=np.float64)[:, :3])).to(dev)
     poses = poses.contiguous()

@@ -122,7 +122,7 @@ def gpu_candidate_feasibility(specs):
             env_id.append(np.full(len(path), e, dtype=np.int32))
             starts.append(starts[-1] + len(path))
     envs = EnvBatch(recs)
-    dev = torch.device("cuda", torch.cuda.current_device())
+    dev = ops._device()
     bad = ops.collision_check(envs, np.concatenate(poses), env_id=np.concatenate(env_id),
                               flags=ops.CHECK_OBSTACLES | ops.CHECK_BOUNDARY)
     path_bad = ops.path_reduce(envs, bad, torch.from_numpy(np.asarray(starts, dtype=np.int64)).to(dev)).cpu().numpy()

@@ -44,14 +44,15 @@ def algorithmic_flops(recs, results):
     return total
 
 
-def gather_results(results_np, expanded_np, world_size, rank):
-    """NCCL gather of the fixed-stride records to rank 0 (torch.distributed must be
-    initialised; tensors go through the GPU so the transfer rides NVLink)."""
+def gather_results(results_np, expanded_np, world_size, rank, device=None):
+    """Gather of the fixed-stride records to rank 0 -- the only collective of a sweep
+    (torch.distributed must be initialised).  On the GPU box the tensors live on the
+    device so NCCL moves them over NVLink; ``device="cpu"`` is the gloo path the CPU tests use."""
     import torch
     import torch.distributed as dist
-    dev = torch.device("cuda", torch.cuda.current_device())
-    t_res = torch.from_numpy(np.ascontiguousarray(results_np).view(np.uint8).reshape(-1)).to(dev)
-    t_exp = torch.from_numpy(np.ascontiguousarray(expanded_np)).to(dev)
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    t_res = torch.from_numpy(np.ascontiguousarray(results_np).view(np.uint8).reshape(-1).copy()).to(dev)
+    t_exp = torch.from_numpy(np.ascontiguousarray(expanded_np).copy()).to(dev)
     if rank == 0:
         g_res = [torch.empty_like(t_res) for _ in range(world_size)]
         g_exp = [torch.empty_like(t_exp) for _ in range(world_size)]
@@ -61,3 +62,14 @@ def gather_results(results_np, expanded_np, world_size, rank):
     dist.gather(t_res, None, dst=0)
     dist.gather(t_exp, None, dst=0)
     return None, None
+
+
+def merge_shards(per_rank_results, per_rank_expanded, n_total, world_size):
+    """Undo the interleaved sharding: record i of rank r is scenario r + i*world_size."""
+    res = np.zeros(n_total, dtype=_lib.RESULT_DTYPE)
+    exp = np.zeros((n_total,) + per_rank_expanded[0].shape[1:], dtype=np.int32)
+    for r in range(world_size):
+        idx = shard_indices(n_total, r, world_size)
+        res[idx] = per_rank_results[r][:len(idx)]
+        exp[idx] = per_rank_expanded[r][:len(idx)]
+    return res, exp

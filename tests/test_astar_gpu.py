@@ -67,3 +67,41 @@ def test_start_blocked(built_library):
     o, want, g, got = _run_pair(rows, start, goal, way, 0.2, 50)
     assert want == ([], [], [], [], [], 0)
     assert got == ([], [], [], [], [], 0)
+
+
+def test_golden_scenarios_batch(built_library):
+    """Config-5 scenarios 0..N-1 in ONE batched launch vs the committed oracle results
+    (tests/golden/astar_golden.npz, generator oracle/gen_golden.py): Y-park feasibility
+    booleans, status, counter, the full expanded-key sequence and the path of every scenario."""
+    import os
+    from headland_trajectory_planning_b200 import ops, scenarios as SC, sweep
+    from headland_trajectory_planning_b200.env_batch import EnvBatch
+    from headland_trajectory_planning_b200.hybrid_a_star_search import unpack_path
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "astar_golden.npz"))
+    n = len(g["index"])
+    specs = [SC.scenario_spec(int(i)) for i in g["index"]]
+    feas = SC.gpu_candidate_feasibility(specs)
+    assert np.array_equal(np.array(feas), g["feas"])                      # collision booleans, bit-exact
+    scns = [SC.finalize(sp, f) for sp, f in zip(specs, feas)]
+    assert np.allclose(np.array([s["goal"] for s in scns]), g["goal"], rtol=0, atol=0)
+    recs, scen, car = sweep.build_records(scns)
+    out = ops.hybrid_astar_batch(EnvBatch(recs), scen, sweep.search_params(car), path_capacity=2048 * n)
+    res = out["results"]
+    bad = []
+    eo = np.concatenate([[0], np.cumsum(g["n_expanded"])])
+    po = np.concatenate([[0], np.cumsum(g["path_len"])])
+    for i in range(n):
+        ok = (res["status"][i] == g["status"][i] and res["counter"][i] == g["counter"][i]
+              and res["n_expanded"][i] == g["n_expanded"][i]
+              and np.array_equal(out["expanded"][i, :res["n_expanded"][i]], g["expanded"][eo[i]:eo[i + 1]])
+              and res["path_len"][i] == g["path_len"][i])
+        if ok and g["path_len"][i]:
+            x, y, yaw, dirs, ks = unpack_path(out, i)
+            want = g["path"][po[i]:po[i + 1]]
+            ok = (np.allclose(x, want[:, 0], rtol=1e-5, atol=1e-6) and np.allclose(y, want[:, 1], rtol=1e-5, atol=1e-6)
+                  and np.allclose(yaw, want[:, 2], rtol=1e-5, atol=1e-6) and np.allclose(ks, want[:, 3], rtol=1e-12)
+                  and np.array_equal(np.asarray(dirs, dtype=np.float64), want[:, 4]))
+        if not ok:
+            bad.append(i)
+    assert not bad, f"{len(bad)} of {n} scenarios differ from the oracle: {bad[:10]}"
+    assert (res["n_expanded"] > 100).sum() >= 5
