@@ -74,7 +74,7 @@ assert SCENARIO_DTYPE.itemsize == 56 and RESULT_DTYPE.itemsize == 56 and RSWORD_
 EXPORTS = [
     "hl_last_error", "hl_abi_version", "hl_ctx_create", "hl_ctx_destroy", "hl_ctx_sm_count",
     "hl_env_upload", "hl_env_free", "hl_env_count", "hl_collision_check", "hl_path_reduce",
-    "hl_rs_all_paths", "hl_rs_sample", "hl_hybrid_astar_batch", "hl_hybrid_astar_workspace_bytes",
+    "hl_rs_all_paths", "hl_rs_sample", "hl_hybrid_astar_batch", "hl_hybrid_astar_workspace_bytes", "hl_astar_phase_cycles",
     "hl_distance_field", "hl_grid_pack", "hl_grid_footprint_check", "hl_measure_fp32_peak",
 ]
 
@@ -146,6 +146,7 @@ def load_library():
                                               vp, vp, vp, vp, vp, i64, vp, vp]
         lib.hl_hybrid_astar_workspace_bytes.argtypes = [vp, C.POINTER(HlSearchParams)]
         lib.hl_hybrid_astar_workspace_bytes.restype = i64
+        lib.hl_astar_phase_cycles.argtypes = [vp, C.POINTER(C.c_uint64), i32, i32]
         lib.hl_distance_field.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, C.POINTER(i32), vp]
         lib.hl_grid_pack.argtypes = [vp, vp, i32, i32, vp, vp]
         lib.hl_grid_footprint_check.argtypes = [vp, vp, i32, i32, dbl, vp, i64, C.POINTER(dbl), vp, vp]

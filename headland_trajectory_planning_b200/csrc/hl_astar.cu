@@ -24,6 +24,11 @@
 #define AS_MAX_PLANS 12
 #define AS_ROLL (HL_MAX_ROLLOUT + 1)
 #define KEY_EMPTY (-1LL)
+// phase timers (cycles of thread 0 between barriers), the device analogue of the reference's three
+// accumulating timers (hybrid_a_star_search.py:91-94): summed over scenarios into ctx->d_counters
+enum { PH_POP = 0, PH_RS_CAND, PH_RS_SELECT, PH_RS_PLAN, PH_RS_SAMPLE, PH_ARRIVE, PH_ROLLOUT, PH_FILTER, PH_EXACT,
+       PH_COST_HEUR, PH_MERGE, PH_SETUP, PH_OUTPUT, AS_N_PHASES };
+#define TICK(ph) do { if (tid == 0) { long long _n = clock64(); S.t_phase[ph] += _n - S.t_last; S.t_last = _n; } } while (0)
 
 struct AsParams {
     double res, yaw_res, maxc, max_steer, wheel_base;
@@ -188,6 +193,7 @@ struct AsSmem {
     int pkey_ok[HL_MAX_PRIMS];
     // stats
     unsigned long long n_checks, n_exact;
+    long long t_last, t_phase[AS_N_PHASES];
     // backtrack
     int chain_len;
     long long path_off;
@@ -262,7 +268,7 @@ k_hybrid_astar(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen, 
                size_t ws_stride, unsigned int* work_counter, HlPlanResult* __restrict__ results,
                int32_t* __restrict__ expanded_keys, double* __restrict__ path_x, double* __restrict__ path_y,
                double* __restrict__ path_yaw, double* __restrict__ path_k, int8_t* __restrict__ path_dir,
-               long long path_capacity, unsigned long long* path_cursor) {
+               long long path_capacity, unsigned long long* path_cursor, unsigned long long* phase_cycles) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     AsSmem& S = *reinterpret_cast<AsSmem*>(smem_raw);
     float* env_sm = reinterpret_cast<float*>(smem_raw + ((sizeof(AsSmem) + 15) & ~(size_t)15));
@@ -288,6 +294,8 @@ k_hybrid_astar(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen, 
             S.n_nodes = 0; S.heap_n = 0; S.counter = 0; S.n_closed = 0;
             S.status = -1; S.arrival = 0; S.rs_word = -1; S.goal_cost = 0.0;
             S.n_checks = 0; S.n_exact = 0; S.path_len = 0; S.path_off = 0; S.stop_flag = 0;
+            for (int k = 0; k < AS_N_PHASES; ++k) S.t_phase[k] = 0;
+            S.t_last = clock64();
         }
         __syncthreads();
         const EnvDesc& D = eb.desc[S.env];
@@ -331,6 +339,7 @@ k_hybrid_astar(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen, 
         }
         __syncthreads();
 
+        TICK(PH_SETUP);
         // =============================== main loop (:525-596) ===============================
         while (S.status < 0) {
             if (tid == 0) {
@@ -350,6 +359,7 @@ k_hybrid_astar(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen, 
             }
             __syncthreads();
             if (S.status >= 0) break;
+            TICK(PH_POP);
 
             // ---- analytic shot: 46 candidate words (:249-258)
             {
@@ -362,6 +372,7 @@ k_hybrid_astar(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen, 
                     for (int k = 0; k < HL_RS_MAX_SEGS; ++k) S.rs_lens[tid][k] = l[k];
                 }
                 __syncthreads();
+                TICK(PH_RS_CAND);
                 if (tid == 0) {
                     int m = rs_select(S.rs_valid, S.rs_lens, S.rs_acc, S.rs_L);
                     if (m < 0) { S.status = HL_STATUS_RS_ASSERT; m = 0; }
@@ -373,6 +384,7 @@ k_hybrid_astar(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen, 
                 }
                 __syncthreads();
                 if (S.status >= 0) break;
+                TICK(PH_RS_SELECT);
                 const int m = S.rs_n;
                 const double stepn = xmul(P.res, P.maxc);
                 // sampling plans of the first AS_MAX_PLANS words in pop order, one thread each
@@ -381,6 +393,7 @@ k_hybrid_astar(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen, 
                     rs_make_plan(c, S.rs_lens[c], P.maxc, stepn, S.plans[tid]);
                 }
                 __syncthreads();
+                TICK(PH_RS_PLAN);
                 const double cq = cos(-q0[2]), sq = sin(-q0[2]);
                 for (int r = 0; r < m; ++r) {
                     const int k = S.rs_order[r];
@@ -421,6 +434,7 @@ k_hybrid_astar(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen, 
                     __syncthreads();      // plan_tmp is rewritten next round
                 }
                 __syncthreads();
+                TICK(PH_RS_SAMPLE);
             }
             // ---- tolerance arrival (:464-495) overrides the shot
             if (tid == 0) {
@@ -442,6 +456,7 @@ k_hybrid_astar(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen, 
             if (tid < HL_MAX_PRIMS) { S.phit[tid] = 0; S.pany_amb[tid] = 0; }
             __syncthreads();
             if (S.status >= 0) break;
+            TICK(PH_ARRIVE);
             const int n = S.nsteps, np1 = n + 1;
             const int total = P.n_prims * np1;
             // phase A: per (p, i) displacement terms  (res*cos(yaws[i]))*dir, i = 0..n
@@ -469,6 +484,7 @@ k_hybrid_astar(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen, 
                 }
             }
             __syncthreads();
+            TICK(PH_ROLLOUT);
             // phase C: float32 filter of every pose
             for (int idx = tid; idx < total; idx += AS_THREADS) {
                 const int p = idx / np1, j = idx - p * np1;
@@ -480,6 +496,7 @@ k_hybrid_astar(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen, 
             }
             if (tid == 0) S.n_checks += (unsigned long long)total;
             __syncthreads();
+            TICK(PH_FILTER);
             // phase D: float64 escalation only where it can still change the answer
             for (int idx = tid; idx < total; idx += AS_THREADS) {
                 const int p = idx / np1, j = idx - p * np1;
@@ -489,6 +506,7 @@ k_hybrid_astar(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen, 
                 }
             }
             __syncthreads();
+            TICK(PH_EXACT);
             // phase E: cost, key (thread per primitive) and heuristic (warp per primitive)
             if (tid < P.n_prims && !S.phit[tid]) {
                 const int p = tid;
@@ -517,6 +535,7 @@ k_hybrid_astar(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen, 
                 }
             }
             __syncthreads();
+            TICK(PH_COST_HEUR);
             // phase F: merge into the open list in primitive order (:580-596)
             if (tid == 0) {
                 for (int p = 0; p < P.n_prims; ++p) {
@@ -542,6 +561,7 @@ k_hybrid_astar(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen, 
                 }
             }
             __syncthreads();
+            TICK(PH_MERGE);
         }
 
         // =============================== results ===============================
@@ -640,6 +660,8 @@ k_hybrid_astar(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen, 
             r.n_pose_checks = (long long)S.n_checks;
             r.n_exact = (long long)S.n_exact;
             results[sc] = r;
+            long long _n = clock64(); S.t_phase[PH_OUTPUT] += _n - S.t_last;
+            for (int k = 0; k < AS_N_PHASES; ++k) atomicAdd(phase_cycles + k, (unsigned long long)S.t_phase[k]);
         }
         // reset the used hash positions for the next scenario of this CTA
         for (int i = tid; i < S.n_nodes; i += AS_THREADS) W.hkey[W.nhpos[i]] = KEY_EMPTY;
@@ -674,6 +696,14 @@ static int astar_grid(const hl_ctx* ctx, int n_scen, size_t smem) {
 }
 
 static size_t astar_smem() { return ((sizeof(AsSmem) + 15) & ~(size_t)15) + 2048 * sizeof(float); }
+
+extern "C" int hl_astar_phase_cycles(hl_ctx* ctx, uint64_t* h_out, int32_t n, int32_t reset) {
+    if (!ctx || !h_out || n < 1 || n > AS_N_PHASES) { hl_set_error("hl_astar_phase_cycles: bad arguments"); return 1; }
+    HL_CUDA_OK(cudaSetDevice(ctx->device));
+    HL_CUDA_OK(cudaMemcpy(h_out, ctx->d_counters + 16, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost));
+    if (reset) HL_CUDA_OK(cudaMemset(ctx->d_counters + 16, 0, sizeof(uint64_t) * AS_N_PHASES));
+    return 0;
+}
 
 extern "C" int64_t hl_hybrid_astar_workspace_bytes(const hl_ctx* ctx, const HlSearchParams* h) {
     if (!ctx || !h) return -1;
@@ -716,7 +746,7 @@ extern "C" int hl_hybrid_astar_batch(hl_ctx* ctx, const hl_env_batch* envs, cons
     k_hybrid_astar<<<grid, AS_THREADS, smem, st>>>(envs->dev, d_scen, n_scen, P, (char*)ctx->astar_ws, stride,
                                                    ctx->d_counters, d_results, d_expanded_keys, d_path_x, d_path_y,
                                                    d_path_yaw, d_path_k, d_path_dir, (long long)path_capacity,
-                                                   d_path_cursor);
+                                                   d_path_cursor, (unsigned long long*)(ctx->d_counters + 16));
     HL_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -43,12 +43,12 @@ extern "C" int hl_ctx_create(hl_ctx** out, int device) {
     c->astar_ws = nullptr;
     c->astar_ws_bytes = 0;
     c->d_counters = nullptr;
-    if (cudaMalloc(&c->d_counters, 64 * sizeof(unsigned int)) != cudaSuccess) {
+    if (cudaMalloc(&c->d_counters, 256 * sizeof(unsigned int)) != cudaSuccess) {
         hl_set_error("hl_ctx_create: cudaMalloc failed");
         delete c;
         return 1;
     }
-    cudaMemset(c->d_counters, 0, 64 * sizeof(unsigned int));
+    cudaMemset(c->d_counters, 0, 256 * sizeof(unsigned int));
     *out = c;
     return 0;
 }

@@ -206,3 +206,16 @@ def grid_footprint_check(bits, shape, res, poses, body_ext):
                                            _lib.ptr(poses), n, ext, _lib.ptr(out), _lib.stream_ptr()),
                "hl_grid_footprint_check")
     return out
+
+
+PHASE_NAMES = ["pop", "rs_candidates", "rs_select", "rs_plan", "rs_sample", "arrival", "rollout", "filter", "exact",
+               "cost_heuristic", "merge", "setup", "output"]
+
+
+def astar_phase_cycles(reset=True, device=None):
+    """Per-phase cycles of the search kernel summed over scenarios since the last reset."""
+    lib = _lib.load_library()
+    buf = (C.c_uint64 * len(PHASE_NAMES))()
+    _lib.check(lib.hl_astar_phase_cycles(_lib.get_ctx(device), buf, len(PHASE_NAMES), 1 if reset else 0),
+               "hl_astar_phase_cycles")
+    return dict(zip(PHASE_NAMES, [int(v) for v in buf]))

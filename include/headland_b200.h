@@ -214,6 +214,12 @@ int hl_hybrid_astar_batch(hl_ctx* ctx, const hl_env_batch* envs, const HlScenari
 /* Bytes of scratch the search keeps per resident CTA, and how many CTAs it launches
  * (for capacity planning / reporting). */
 int64_t hl_hybrid_astar_workspace_bytes(const hl_ctx* ctx, const HlSearchParams* h_params);
+/* Phase timers of the search kernel (thread-0 cycles between barriers, summed over all scenarios since
+ * the last reset) -- the device analogue of the reference's three accumulating timers
+ * (hybrid_a_star_search.py:91-94).  Order: pop, rs_candidates, rs_select, rs_plan, rs_sample, arrival,
+ * rollout, filter, exact, cost_heuristic, merge, setup, output. */
+#define HL_ASTAR_N_PHASES 13
+int hl_astar_phase_cycles(hl_ctx* ctx, uint64_t* h_out, int32_t n, int32_t reset);
 
 /* ---- K6 grid distance field ---------------------------------------------------
  * Replaces holonomic_costs_with_obstacles (path_planner/utils/a_star_utils.py:75-142)
