@@ -11,7 +11,9 @@
 #include "../../include/headland_b200.h"
 
 #define HL_MAX_SEGS 16           // lane capsules per environment (device-side arrays)
-#define HL_OBS32_STRIDE 20       // floats per obstacle: 4 vertices (8) + 4 x (nx, ny, c)
+#define HL_OBS32_STRIDE 28       // floats per obstacle: 4 vertices (8) + 4 x (nx, ny, c) + box form
+                                 // [20] is_rect, [21..22] centre, [23..24] unit axis a, [25..26] half extents
+#define HL_FIELD32_STRIDE 8      // per field edge: Ax, Ay, nx, ny (unit, outward), c = n.A, t.A, t.B, pad
 #define HL_PI 3.141592653589793  // == math.pi
 
 struct EnvDesc {
@@ -30,9 +32,9 @@ struct EnvDesc {
 
 struct EnvBatchDev {
     const EnvDesc* desc;
-    const float* obs32;       // [n][20]
+    const float* obs32;       // [n][HL_OBS32_STRIDE]
     const double* obs64;      // [n][4][2]
-    const float* field32;     // [n][2] relative to origin
+    const float* field32;     // [n][HL_FIELD32_STRIDE] relative to origin
     const double* field64;    // [n][2]
     const float* seg32;       // [n][4]  ax, ay, bx, by relative to origin
     const double* seg64;      // [n][4]

@@ -137,11 +137,45 @@ extern "C" int hl_env_upload(hl_ctx* ctx, const HlEnvHost* h, int32_t n_env, hl_
                 double cc = nx * (V[2 * i] - D.origin[0]) + ny * (V[2 * i + 1] - D.origin[1]);
                 obs32.push_back((float)nx); obs32.push_back((float)ny); obs32.push_back((float)cc);
             }
+            // box form when the quad is a rectangle (tree rows, obstacle squares): centre, unit axis, half extents
+            {
+                double e0x = V[2] - V[0], e0y = V[3] - V[1], e1x = V[4] - V[2], e1y = V[5] - V[3];
+                double e2x = V[6] - V[4], e2y = V[7] - V[5], e3x = V[0] - V[6], e3y = V[1] - V[7];
+                double l0 = sqrt(e0x * e0x + e0y * e0y), l1 = sqrt(e1x * e1x + e1y * e1y);
+                double scale = fmax(l0, l1);
+                bool para = fabs(e0x + e2x) + fabs(e0y + e2y) + fabs(e1x + e3x) + fabs(e1y + e3y) <= 1e-9 * scale;
+                bool perp = l0 > 0 && l1 > 0 && fabs(e0x * e1x + e0y * e1y) <= 1e-9 * l0 * l1;
+                bool is_rect = para && perp;
+                double cx = 0.25 * (V[0] + V[2] + V[4] + V[6]) - D.origin[0];
+                double cy = 0.25 * (V[1] + V[3] + V[5] + V[7]) - D.origin[1];
+                double ax = is_rect ? e0x / l0 : 1.0, ay = is_rect ? e0y / l0 : 0.0;
+                obs32.push_back(is_rect ? 1.0f : 0.0f);
+                obs32.push_back((float)cx); obs32.push_back((float)cy);
+                obs32.push_back((float)ax); obs32.push_back((float)ay);
+                obs32.push_back((float)(0.5 * l0)); obs32.push_back((float)(0.5 * l1));
+                obs32.push_back(0.0f);
+            }
         }
-        for (int i = 0; i < E.n_field; ++i) {
-            field64.push_back(E.field_xy[2 * i]); field64.push_back(E.field_xy[2 * i + 1]);
-            field32.push_back((float)(E.field_xy[2 * i] - D.origin[0]));
-            field32.push_back((float)(E.field_xy[2 * i + 1] - D.origin[1]));
+        {
+            double area2 = 0.0;
+            for (int i = 0; i < E.n_field; ++i) {
+                int j = (i + 1 == E.n_field) ? 0 : i + 1;
+                area2 += E.field_xy[2 * i] * E.field_xy[2 * j + 1] - E.field_xy[2 * j] * E.field_xy[2 * i + 1];
+            }
+            const double orient = area2 < 0 ? -1.0 : 1.0;
+            for (int i = 0; i < E.n_field; ++i) {
+                int j = (i + 1 == E.n_field) ? 0 : i + 1;
+                field64.push_back(E.field_xy[2 * i]); field64.push_back(E.field_xy[2 * i + 1]);
+                double Ax = E.field_xy[2 * i] - D.origin[0], Ay = E.field_xy[2 * i + 1] - D.origin[1];
+                double Bx = E.field_xy[2 * j] - D.origin[0], By = E.field_xy[2 * j + 1] - D.origin[1];
+                double ex = Bx - Ax, ey = By - Ay, ln = sqrt(ex * ex + ey * ey);
+                double nx = ln > 0 ? orient * ey / ln : 0.0, ny = ln > 0 ? -orient * ex / ln : 0.0;
+                field32.push_back((float)Ax); field32.push_back((float)Ay);
+                field32.push_back((float)nx); field32.push_back((float)ny);
+                field32.push_back((float)(nx * Ax + ny * Ay));
+                field32.push_back((float)(-ny * Ax + nx * Ay)); field32.push_back((float)(-ny * Bx + nx * By));
+                field32.push_back(0.0f);
+            }
         }
         for (int i = 0; i < E.n_seg; ++i) {
             for (int c = 0; c < 4; ++c) {

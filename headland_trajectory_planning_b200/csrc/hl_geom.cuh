@@ -219,7 +219,7 @@ static __device__ int exact_search_segment(const EnvBatchDev& eb, const EnvDesc&
 }
 
 // Full exact check of one footprint rectangle at one pose.  Returns true = infeasible.
-static __device__ bool exact_part_check(const Pose64& p, const double* ext, const EnvBatchDev& eb,
+static __device__ __noinline__ bool exact_part_check(const Pose64& p, const double* ext, const EnvBatchDev& eb,
                                  const EnvDesc& e, unsigned flags) {
     double cx[4], cy[4];
     exact_corners(p, ext, cx, cy);
@@ -241,41 +241,60 @@ struct EnvSmem {
     int n_obs, n_field, n_seg;
     float eps, reach;
     float ext[4];               // body rectangle
-    const float* obs;           // [n_obs][20]
-    const float* field;         // [n_field][2]
+    const float* obs;           // [n_obs][HL_OBS32_STRIDE]
+    const float* field;         // [n_field][HL_FIELD32_STRIDE]
     const float* seg;           // [n_seg][4]
 };
 
 // One rectangle `ext` at pose (px,py,c,s) [float32, relative to env origin].
 // Returns HL_FREE / HL_HIT / HL_AMBIG per enabled test, combined:
 //   any HIT -> HIT; else any AMBIG -> AMBIG; else FREE.
+// Formulation: the rectangle is (centre C, unit axes u=(c,s), v=(-s,c), half extents hx,hy).
+//   * obstacles that are rectangles (tree rows, squares) use the 4-axis box-box separating test on
+//     (centre, axis, half extents) -- ~30 flop instead of the 8-axis vertex form; other convex quads
+//     keep the generic vertex form;
+//   * field polygon: per edge the signed distance of C to the edge's line against the support radius
+//     of the rectangle along the edge normal decides "clear" for most edges in ~12 flop; an edge whose
+//     line the rectangle straddles is checked along the edge direction and in the pose frame; the
+//     crossing parity of C decides inside/outside when every edge is clear;
+//   * lane: one centre-to-segment distance accepts / rejects against (r_in - rho) / (r_out + rho)
+//     before the four corner distances are needed.
 __device__ __forceinline__ int filter_part(const EnvSmem& E, float px, float py, float c, float s,
                                            const float* ext, unsigned flags, unsigned* which_ambig) {
     const float eps = E.eps;
-    float rx[4], ry[4];
-    {
-        const float lx[4] = {ext[0], ext[0], ext[1], ext[1]};
-        const float ly[4] = {ext[3], ext[2], ext[2], ext[3]};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            rx[k] = fmaf(c, lx[k], fmaf(-s, ly[k], px));
-            ry[k] = fmaf(s, lx[k], fmaf(c, ly[k], py));
-        }
-    }
-    int result = HL_FREE;
+    const float hx = 0.5f * (ext[1] - ext[0]), hy = 0.5f * (ext[3] - ext[2]);
+    const float mx = 0.5f * (ext[1] + ext[0]), my = 0.5f * (ext[3] + ext[2]);
+    const float Cx = fmaf(c, mx, fmaf(-s, my, px)), Cy = fmaf(s, mx, fmaf(c, my, py));
     unsigned amb = 0;
     if (flags & HL_CHECK_OBSTACLES) {
         for (int k = 0; k < E.n_obs; ++k) {
             const float* o = E.obs + HL_OBS32_STRIDE * k;
-            float sep = -INFINITY;
+            float sep;
+            if (o[20] != 0.0f) {                                  // rectangle: box-box SAT
+                const float dx = o[21] - Cx, dy = o[22] - Cy;
+                const float ax = o[23], ay = o[24], ha = o[25], hb = o[26];
+                const float p = fabsf(fmaf(ax, c, ay * s)), q = fabsf(fmaf(ay, c, -ax * s));
+                const float du = fabsf(fmaf(dx, c, dy * s)), dv = fabsf(fmaf(dy, c, -dx * s));
+                const float da = fabsf(fmaf(dx, ax, dy * ay)), db = fabsf(fmaf(dy, ax, -dx * ay));
+                sep = fmaxf(fmaxf(du - fmaf(ha, p, fmaf(hb, q, hx)), dv - fmaf(ha, q, fmaf(hb, p, hy))),
+                            fmaxf(da - fmaf(hx, p, fmaf(hy, q, ha)), db - fmaf(hx, q, fmaf(hy, p, hb))));
+            } else {                                              // generic convex quad: 8 axes on vertices
+                float rx[4], ry[4];
+                const float lx[4] = {ext[0], ext[0], ext[1], ext[1]};
+                const float ly[4] = {ext[3], ext[2], ext[2], ext[3]};
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                float nx = o[8 + 3 * i], ny = o[9 + 3 * i], cc = o[10 + 3 * i];
-                float m = fminf(fminf(fmaf(nx, rx[0], ny * ry[0]), fmaf(nx, rx[1], ny * ry[1])),
-                                fminf(fmaf(nx, rx[2], ny * ry[2]), fmaf(nx, rx[3], ny * ry[3])));
-                sep = fmaxf(sep, m - cc);
-            }
-            if (sep <= eps) {          // obstacle axes did not clearly separate: try the rectangle axes
+                for (int j = 0; j < 4; ++j) {
+                    rx[j] = fmaf(c, lx[j], fmaf(-s, ly[j], px));
+                    ry[j] = fmaf(s, lx[j], fmaf(c, ly[j], py));
+                }
+                sep = -INFINITY;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float nx = o[8 + 3 * i], ny = o[9 + 3 * i], cc = o[10 + 3 * i];
+                    float m = fminf(fminf(fmaf(nx, rx[0], ny * ry[0]), fmaf(nx, rx[1], ny * ry[1])),
+                                    fminf(fmaf(nx, rx[2], ny * ry[2]), fmaf(nx, rx[3], ny * ry[3])));
+                    sep = fmaxf(sep, m - cc);
+                }
                 float umin = INFINITY, umax = -INFINITY, wmin = INFINITY, wmax = -INFINITY;
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
@@ -285,102 +304,111 @@ __device__ __forceinline__ int filter_part(const EnvSmem& E, float px, float py,
                     wmin = fminf(wmin, w); wmax = fmaxf(wmax, w);
                 }
                 sep = fmaxf(sep, fmaxf(fmaxf(umin - ext[1], ext[0] - umax), fmaxf(wmin - ext[3], ext[2] - wmax)));
-                if (sep < -eps) return HL_HIT;
-                if (sep <= eps) amb |= HL_CHECK_OBSTACLES;
             }
+            if (sep < -eps) return HL_HIT;
+            if (sep <= eps) amb |= HL_CHECK_OBSTACLES;
         }
     }
     if (flags & HL_CHECK_BOUNDARY) {
-        // every polygon edge clear of the rectangle (by a rectangle axis or by its own
-        // line) => the rectangle is wholly inside or wholly outside: one crossing test
-        // of the pose-frame rectangle centre decides.  An edge that clearly cuts the
-        // shrunken open rectangle => HIT.  Anything else => AMBIG.
         const int n = E.n_field;
-        float dx = E.field[0] - px, dy = E.field[1] - py;
-        float ua = fmaf(c, dx, s * dy), wa = fmaf(c, dy, -s * dx);
-        const float u_first = ua, w_first = wa;
-        const float ccx = 0.5f * (ext[0] + ext[1]), ccy = 0.5f * (ext[2] + ext[3]);
         bool inside = false, all_clear = true, cut = false;
         for (int i = 0; i < n; ++i) {
-            float ub, wb;
-            if (i + 1 == n) { ub = u_first; wb = w_first; }
-            else {
-                dx = E.field[2 * (i + 1)] - px; dy = E.field[2 * (i + 1) + 1] - py;
-                ub = fmaf(c, dx, s * dy); wb = fmaf(c, dy, -s * dx);
+            const float* e = E.field + HL_FIELD32_STRIDE * i;
+            const float Ax = e[0], Ay = e[1], nx = e[2], ny = e[3];
+            const float* e2 = E.field + HL_FIELD32_STRIDE * ((i + 1 == n) ? 0 : i + 1);
+            const float Bx = e2[0], By = e2[1];
+            // crossing parity of the rectangle centre (ray along +x)
+            if ((Ay > Cy) != (By > Cy)) {
+                float xint = fmaf(Bx - Ax, (Cy - Ay) / (By - Ay), Ax);
+                if (Cx < xint) inside = !inside;
             }
-            // crossing parity of the rectangle centre, in the pose frame (ray along +u)
-            if ((wa > ccy) != (wb > ccy)) {
-                float uint_ = fmaf((ub - ua), (ccy - wa) / (wb - wa), ua);
-                if (ccx < uint_) inside = !inside;
-            }
-            bool clear = (fminf(ua, ub) > ext[1] + eps) || (fmaxf(ua, ub) < ext[0] - eps) ||
-                         (fminf(wa, wb) > ext[3] + eps) || (fmaxf(wa, wb) < ext[2] - eps);
-            if (!clear) {
-                float du = ub - ua, dw = wb - wa;
-                float inv = rsqrtf(fmaf(du, du, dw * dw));
-                float nx = dw * inv, ny = -du * inv;
-                float base = fmaf(nx, -ua, ny * -wa);
-                float d0 = fmaf(nx, ext[0], fmaf(ny, ext[2], base));
-                float d1 = fmaf(nx, ext[1], fmaf(ny, ext[2], base));
-                float d2 = fmaf(nx, ext[1], fmaf(ny, ext[3], base));
-                float d3 = fmaf(nx, ext[0], fmaf(ny, ext[3], base));
-                float mn = fminf(fminf(d0, d1), fminf(d2, d3)), mx = fmaxf(fmaxf(d0, d1), fmaxf(d2, d3));
-                clear = (mn > eps) || (mx < -eps);
-                if (!clear) {
-                    all_clear = false;
-                    // definite cut: Liang-Barsky against the rectangle shrunk by eps
-                    float t0 = 0.f, t1 = 1.f;
-                    bool dead = false;
-                    const float a2[2] = {ua, wa}, d2v[2] = {du, dw};
-                    const float lo2[2] = {ext[0] + eps, ext[2] + eps}, hi2[2] = {ext[1] - eps, ext[3] - eps};
+            const float nu = fmaf(nx, c, ny * s), nv = fmaf(ny, c, -nx * s);      // n.u, n.v
+            const float sd = fmaf(nx, Cx, fmaf(ny, Cy, -e[4]));                  // signed distance of C to the line
+            const float rn = fmaf(hx, fabsf(nu), hy * fabsf(nv));                // support radius along n
+            if (fabsf(sd) > rn + eps) continue;                                  // clear of the whole line
+            // along the edge direction t = (-ny, nx):  t.u = -n.v,  t.v = n.u
+            const float ct = fmaf(-ny, Cx, nx * Cy);
+            const float rt = fmaf(hx, fabsf(nv), hy * fabsf(nu));
+            if (ct - rt > fmaxf(e[5], e[6]) + eps || ct + rt < fminf(e[5], e[6]) - eps) continue;
+            // rectangle axes (pose frame)
+            float dxa = Ax - px, dya = Ay - py, dxb = Bx - px, dyb = By - py;
+            float ua = fmaf(c, dxa, s * dya), wa = fmaf(c, dya, -s * dxa);
+            float ub = fmaf(c, dxb, s * dyb), wb = fmaf(c, dyb, -s * dxb);
+            if ((fminf(ua, ub) > ext[1] + eps) || (fmaxf(ua, ub) < ext[0] - eps) ||
+                (fminf(wa, wb) > ext[3] + eps) || (fmaxf(wa, wb) < ext[2] - eps)) continue;
+            all_clear = false;
+            // definite cut: Liang-Barsky against the rectangle shrunk by eps
+            float t0 = 0.f, t1 = 1.f;
+            bool dead = false;
+            const float a2[2] = {ua, wa}, d2v[2] = {ub - ua, wb - wa};
+            const float lo2[2] = {ext[0] + eps, ext[2] + eps}, hi2[2] = {ext[1] - eps, ext[3] - eps};
 #pragma unroll
-                    for (int ax = 0; ax < 2; ++ax) {
-                        if (fabsf(d2v[ax]) < 1e-12f) {
-                            if (a2[ax] <= lo2[ax] || a2[ax] >= hi2[ax]) dead = true;
-                        } else {
-                            float tl = (lo2[ax] - a2[ax]) / d2v[ax], th = (hi2[ax] - a2[ax]) / d2v[ax];
-                            t0 = fmaxf(t0, fminf(tl, th));
-                            t1 = fminf(t1, fmaxf(tl, th));
-                        }
-                    }
-                    // require a clearly non-empty parameter interval
-                    if (!dead && t1 - t0 > 1e-4f) cut = true;
+            for (int ax = 0; ax < 2; ++ax) {
+                if (fabsf(d2v[ax]) < 1e-12f) {
+                    if (a2[ax] <= lo2[ax] || a2[ax] >= hi2[ax]) dead = true;
+                } else {
+                    float tl = (lo2[ax] - a2[ax]) / d2v[ax], th = (hi2[ax] - a2[ax]) / d2v[ax];
+                    t0 = fmaxf(t0, fminf(tl, th));
+                    t1 = fminf(t1, fmaxf(tl, th));
                 }
             }
-            ua = ub; wa = wb;
+            if (!dead && t1 - t0 > 1e-4f) cut = true;
         }
         if (cut) return HL_HIT;
         if (all_clear) { if (!inside) return HL_HIT; }
         else amb |= HL_CHECK_BOUNDARY;
     }
     if ((flags & HL_CHECK_LANE) && E.n_seg > 0) {
-        // corner-to-segment distances against the inscribed / circumscribed radii
+        const float rho = sqrtf(fmaf(hx, hx, hy * hy));
         const float rin = (float)HL_LANE_RIN - eps, rout = (float)HL_LANE_R + eps;
-        bool one_holds_all = false;
-        unsigned maybe = 0;                    // corner k possibly inside some capsule
-        for (int i = 0; i < E.n_seg; ++i) {
+        bool accepted = false, need_corners = false;
+        for (int i = 0; i < E.n_seg && !accepted; ++i) {
             const float* sg = E.seg + 4 * i;
             float ex = sg[2] - sg[0], ey = sg[3] - sg[1];
             float inv = 1.0f / fmaf(ex, ex, ey * ey);
-            float dmax = 0.f;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                float qx = rx[k] - sg[0], qy = ry[k] - sg[1];
-                float t = fminf(fmaxf(fmaf(qx, ex, qy * ey) * inv, 0.f), 1.f);
-                float ddx = fmaf(-t, ex, qx), ddy = fmaf(-t, ey, qy);
-                float d2 = fmaf(ddx, ddx, ddy * ddy);
-                dmax = fmaxf(dmax, d2);
-                if (d2 <= rout * rout) maybe |= 1u << k;
-            }
-            if (dmax <= rin * rin) one_holds_all = true;
+            float qx = Cx - sg[0], qy = Cy - sg[1];
+            float t = fminf(fmaxf(fmaf(qx, ex, qy * ey) * inv, 0.f), 1.f);
+            float ddx = fmaf(-t, ex, qx), ddy = fmaf(-t, ey, qy);
+            float d = sqrtf(fmaf(ddx, ddx, ddy * ddy));
+            if (d + rho <= rin) accepted = true;                 // whole rectangle inside capsule i
+            else if (d - rho <= rout) need_corners = true;       // capsule i may hold some corner
         }
-        if (!one_holds_all) {
-            if (maybe != 0xFu) return HL_HIT;
-            amb |= HL_CHECK_LANE;
+        if (!accepted) {
+            if (!need_corners) return HL_HIT;                    // every point is outside every capsule
+            float rx[4], ry[4];
+            const float lx[4] = {ext[0], ext[0], ext[1], ext[1]};
+            const float ly[4] = {ext[3], ext[2], ext[2], ext[3]};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                rx[j] = fmaf(c, lx[j], fmaf(-s, ly[j], px));
+                ry[j] = fmaf(s, lx[j], fmaf(c, ly[j], py));
+            }
+            bool one_holds_all = false;
+            unsigned maybe = 0;
+            for (int i = 0; i < E.n_seg; ++i) {
+                const float* sg = E.seg + 4 * i;
+                float ex = sg[2] - sg[0], ey = sg[3] - sg[1];
+                float inv = 1.0f / fmaf(ex, ex, ey * ey);
+                float dmax = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float qx = rx[j] - sg[0], qy = ry[j] - sg[1];
+                    float t = fminf(fmaxf(fmaf(qx, ex, qy * ey) * inv, 0.f), 1.f);
+                    float ddx = fmaf(-t, ex, qx), ddy = fmaf(-t, ey, qy);
+                    float d2 = fmaf(ddx, ddx, ddy * ddy);
+                    dmax = fmaxf(dmax, d2);
+                    if (d2 <= rout * rout) maybe |= 1u << j;
+                }
+                if (dmax <= rin * rin) one_holds_all = true;
+            }
+            if (!one_holds_all) {
+                if (maybe != 0xFu) return HL_HIT;
+                amb |= HL_CHECK_LANE;
+            }
         }
     }
-    if (amb) { result = HL_AMBIG; if (which_ambig) *which_ambig = amb; }
-    return result;
+    if (amb) { if (which_ambig) *which_ambig = amb; return HL_AMBIG; }
+    return HL_FREE;
 }
 
 // Resolve one pose against its environment.  Shared by K1 and the search kernels.
@@ -426,20 +454,20 @@ static __device__ bool pose_infeasible(const EnvBatchDev& eb, const EnvDesc& D, 
 
 __device__ __forceinline__ void stage_env(const EnvBatchDev& eb, const EnvDesc& D, float* sm, int cap_floats,
                                           EnvSmem& E, bool& staged) {
-    int need = D.n_obs * HL_OBS32_STRIDE + D.n_field * 2 + D.n_seg * 4;
+    int need = D.n_obs * HL_OBS32_STRIDE + D.n_field * HL_FIELD32_STRIDE + D.n_seg * 4;
     E.n_obs = D.n_obs; E.n_field = D.n_field; E.n_seg = D.n_seg;
     E.eps = D.eps; E.reach = D.reach;
     for (int k = 0; k < 4; ++k) E.ext[k] = (float)D.body_ext[k];
     const float* g_obs = eb.obs32 + (size_t)HL_OBS32_STRIDE * D.obs_off;
-    const float* g_field = eb.field32 + 2 * (size_t)D.field_off;
+    const float* g_field = eb.field32 + HL_FIELD32_STRIDE * (size_t)D.field_off;
     const float* g_seg = eb.seg32 + 4 * (size_t)D.seg_off;
     staged = need <= cap_floats;
     if (staged) {
         float* s_obs = sm;
         float* s_field = s_obs + D.n_obs * HL_OBS32_STRIDE;
-        float* s_seg = s_field + D.n_field * 2;
+        float* s_seg = s_field + D.n_field * HL_FIELD32_STRIDE;
         for (int i = threadIdx.x; i < D.n_obs * HL_OBS32_STRIDE; i += blockDim.x) s_obs[i] = g_obs[i];
-        for (int i = threadIdx.x; i < D.n_field * 2; i += blockDim.x) s_field[i] = g_field[i];
+        for (int i = threadIdx.x; i < D.n_field * HL_FIELD32_STRIDE; i += blockDim.x) s_field[i] = g_field[i];
         for (int i = threadIdx.x; i < D.n_seg * 4; i += blockDim.x) s_seg[i] = g_seg[i];
         E.obs = s_obs; E.field = s_field; E.seg = s_seg;
     } else {
@@ -452,7 +480,7 @@ __device__ __forceinline__ void global_env(const EnvBatchDev& eb, const EnvDesc&
     E.eps = D.eps; E.reach = D.reach;
     for (int k = 0; k < 4; ++k) E.ext[k] = (float)D.body_ext[k];
     E.obs = eb.obs32 + (size_t)HL_OBS32_STRIDE * D.obs_off;
-    E.field = eb.field32 + 2 * (size_t)D.field_off;
+    E.field = eb.field32 + HL_FIELD32_STRIDE * (size_t)D.field_off;
     E.seg = eb.seg32 + 4 * (size_t)D.seg_off;
 }
 
