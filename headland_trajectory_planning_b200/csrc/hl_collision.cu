@@ -14,7 +14,7 @@
 
 #define K1_THREADS 256
 
-__global__ void __launch_bounds__(K1_THREADS)
+__global__ void __launch_bounds__(K1_THREADS, 3)
 k_collision(EnvBatchDev eb, const int32_t* __restrict__ env_id, const double* __restrict__ poses,
             const int32_t* __restrict__ pose_idx, long long n, unsigned flags,
             uint8_t* __restrict__ out, unsigned long long* n_exact, int smem_floats) {

@@ -13,7 +13,7 @@
 #define HL_MAX_SEGS 16           // lane capsules per environment (device-side arrays)
 #define HL_OBS32_STRIDE 28       // floats per obstacle: 4 vertices (8) + 4 x (nx, ny, c) + box form
                                  // [20] is_rect, [21..22] centre, [23..24] unit axis a, [25..26] half extents
-#define HL_FIELD32_STRIDE 8      // per field edge: Ax, Ay, nx, ny (unit, outward), c = n.A, t.A, t.B, pad
+#define HL_FIELD32_STRIDE 12     // per field edge: Ax, Ay, Ex, Ey | nx, ny (unit, outward), c = n.A, By | t.A, t.B, pad x2
 #define HL_PI 3.141592653589793  // == math.pi
 
 struct EnvDesc {
@@ -23,6 +23,7 @@ struct EnvDesc {
     int n_crit, crit_off;
     int n_guide, guide_off;
     int n_aux, aux_off;
+    int all_rect, pad0;     // every obstacle quad is a rectangle (box form usable)
     float eps;              // float32 filter band (metres), scaled to the environment extent
     float reach;            // poses farther than this from origin skip the float32 filter
     double origin[2];

@@ -120,6 +120,7 @@ extern "C" int hl_env_upload(hl_ctx* ctx, const HlEnvHost* h, int32_t n_env, hl_
         double reach = extent + 16.0;
         D.reach = (float)reach;
         D.eps = (float)(32.0 * 1.1920929e-07 * fmax(reach, 8.0));
+        D.all_rect = 1; D.pad0 = 0;
         for (int k = 0; k < E.n_obs; ++k) {
             const double* V = E.obs_xy + 8 * k;
             for (int i = 0; i < 8; ++i) obs64.push_back(V[i]);
@@ -149,6 +150,7 @@ extern "C" int hl_env_upload(hl_ctx* ctx, const HlEnvHost* h, int32_t n_env, hl_
                 double cx = 0.25 * (V[0] + V[2] + V[4] + V[6]) - D.origin[0];
                 double cy = 0.25 * (V[1] + V[3] + V[5] + V[7]) - D.origin[1];
                 double ax = is_rect ? e0x / l0 : 1.0, ay = is_rect ? e0y / l0 : 0.0;
+                if (!is_rect) D.all_rect = 0;
                 obs32.push_back(is_rect ? 1.0f : 0.0f);
                 obs32.push_back((float)cx); obs32.push_back((float)cy);
                 obs32.push_back((float)ax); obs32.push_back((float)ay);
@@ -171,10 +173,12 @@ extern "C" int hl_env_upload(hl_ctx* ctx, const HlEnvHost* h, int32_t n_env, hl_
                 double ex = Bx - Ax, ey = By - Ay, ln = sqrt(ex * ex + ey * ey);
                 double nx = ln > 0 ? orient * ey / ln : 0.0, ny = ln > 0 ? -orient * ex / ln : 0.0;
                 field32.push_back((float)Ax); field32.push_back((float)Ay);
+                field32.push_back((float)(Bx - Ax)); field32.push_back((float)(By - Ay));
                 field32.push_back((float)nx); field32.push_back((float)ny);
                 field32.push_back((float)(nx * Ax + ny * Ay));
+                field32.push_back((float)By);                       // == the next record's (float)Ay, bit for bit
                 field32.push_back((float)(-ny * Ax + nx * Ay)); field32.push_back((float)(-ny * Bx + nx * By));
-                field32.push_back(0.0f);
+                field32.push_back(0.0f); field32.push_back(0.0f);
             }
         }
         for (int i = 0; i < E.n_seg; ++i) {

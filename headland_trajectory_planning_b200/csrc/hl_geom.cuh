@@ -129,7 +129,8 @@ __device__ __forceinline__ double seg_dist64(const double* s, double px, double 
     double t = ((px - s[0]) * ex + (py - s[1]) * ey) / (ex * ex + ey * ey);
     t = fmin(fmax(t, 0.0), 1.0);
     double qx = s[0] + t * ex, qy = s[1] + t * ey;
-    return hypot(px - qx, py - qy);
+    double ddx = px - qx, ddy = py - qy;
+    return sqrt(ddx * ddx + ddy * ddy);
 }
 
 // g_j = nx_j*(px - vx_j) + ny_j*(py - vy_j), n_j = (e_y, -e_x) of the CCW ring
@@ -238,13 +239,45 @@ static __device__ __noinline__ bool exact_part_check(const Pose64& p, const doub
 // ------------------------------------------------------------------- float32
 // Environment staged in shared memory for the float32 filter.
 struct EnvSmem {
-    int n_obs, n_field, n_seg;
+    int n_obs, n_field, n_seg, all_rect;
     float eps, reach;
     float ext[4];               // body rectangle
     const float* obs;           // [n_obs][HL_OBS32_STRIDE]
     const float* field;         // [n_field][HL_FIELD32_STRIDE]
     const float* seg;           // [n_seg][4]
 };
+
+// Membership of a point in capsule POLYGON i (float32).  The polygon is the true capsule of radius 6
+// except in the two round caps, where it is the 32-chord fan with vertices at angle_normal + k*pi/32
+// (geometry_host.capsule_polygon): a cap point at range rho and angular offset delta from the nearest
+// chord midpoint is inside iff rho*cos(delta) <= 6*cos(pi/64).  Returns 1 inside, 0 outside, 2 when
+// the margin is within the float32 band.
+__device__ __forceinline__ int corner_in_capsule(const float* sg, float wx, float wy, float eps) {
+    const float ex = sg[2] - sg[0], ey = sg[3] - sg[1];
+    const float len2 = fmaf(ex, ex, ey * ey);
+    const float qx = wx - sg[0], qy = wy - sg[1];
+    const float tt = fmaf(qx, ex, qy * ey) / len2;
+    const float t = fminf(fmaxf(tt, 0.f), 1.f);
+    const float ddx = fmaf(-t, ex, qx), ddy = fmaf(-t, ey, qy);
+    const float d2 = fmaf(ddx, ddx, ddy * ddy);
+    const float rin = (float)HL_LANE_RIN - eps, rout = (float)HL_LANE_R + eps;
+    if (d2 <= rin * rin) return 1;
+    if (d2 > rout * rout) return 0;
+    float g = sqrtf(d2);                                        // straight part: distance to the axis
+    if (tt < 0.f || tt > 1.f) {                                 // cap: chord fan
+        const float il = rsqrtf(len2);
+        const float along = fabsf(fmaf(ddx, ex, ddy * ey)) * il, across = fabsf(fmaf(ddy, ex, -ddx * ey)) * il;
+        const float phi = atan2f(across, along);                // 0 .. pi/2 from the segment direction
+        const float q = 1.5707963267948966f - phi;              // angle from the first vertex (the normal)
+        const float step = 0.09817477042468103f;                // pi/32
+        const float k = floorf(q / step);
+        const float delta = fabsf(q - (k + 0.5f) * step);
+        g = g * cosf(delta) * 1.0012061467251643f;              // / cos(pi/64)
+    }
+    if (g <= (float)HL_LANE_R - eps) return 1;
+    if (g > (float)HL_LANE_R + eps) return 0;
+    return 2;
+}
 
 // One rectangle `ext` at pose (px,py,c,s) [float32, relative to env origin].
 // Returns HL_FREE / HL_HIT / HL_AMBIG per enabled test, combined:
@@ -266,28 +299,39 @@ __device__ __forceinline__ int filter_part(const EnvSmem& E, float px, float py,
     const float mx = 0.5f * (ext[1] + ext[0]), my = 0.5f * (ext[3] + ext[2]);
     const float Cx = fmaf(c, mx, fmaf(-s, my, px)), Cy = fmaf(s, mx, fmaf(c, my, py));
     unsigned amb = 0;
+    // Branch-light on purpose: the lanes of a warp hold unrelated poses, so every data-dependent
+    // branch is paid by the whole warp.  Obstacles and field edges are evaluated for all lanes and
+    // folded into hit / ambiguous flags; only the rare second-stage edge tests loop per lane.
+    bool hit = false;
     if (flags & HL_CHECK_OBSTACLES) {
-        for (int k = 0; k < E.n_obs; ++k) {
-            const float* o = E.obs + HL_OBS32_STRIDE * k;
-            float sep;
-            if (o[20] != 0.0f) {                                  // rectangle: box-box SAT
-                const float dx = o[21] - Cx, dy = o[22] - Cy;
-                const float ax = o[23], ay = o[24], ha = o[25], hb = o[26];
+        bool a_obs = false;
+        if (E.all_rect) {
+            for (int k = 0; k < E.n_obs; ++k) {
+                const float* o = E.obs + HL_OBS32_STRIDE * k;
+                const float4 b0 = *reinterpret_cast<const float4*>(o + 20);      // flag, cx, cy, ax
+                const float4 b1 = *reinterpret_cast<const float4*>(o + 24);      // ay, ha, hb, pad
+                const float dx = b0.y - Cx, dy = b0.z - Cy;
+                const float ax = b0.w, ay = b1.x, ha = b1.y, hb = b1.z;
                 const float p = fabsf(fmaf(ax, c, ay * s)), q = fabsf(fmaf(ay, c, -ax * s));
                 const float du = fabsf(fmaf(dx, c, dy * s)), dv = fabsf(fmaf(dy, c, -dx * s));
                 const float da = fabsf(fmaf(dx, ax, dy * ay)), db = fabsf(fmaf(dy, ax, -dx * ay));
-                sep = fmaxf(fmaxf(du - fmaf(ha, p, fmaf(hb, q, hx)), dv - fmaf(ha, q, fmaf(hb, p, hy))),
-                            fmaxf(da - fmaf(hx, p, fmaf(hy, q, ha)), db - fmaf(hx, q, fmaf(hy, p, hb))));
-            } else {                                              // generic convex quad: 8 axes on vertices
-                float rx[4], ry[4];
-                const float lx[4] = {ext[0], ext[0], ext[1], ext[1]};
-                const float ly[4] = {ext[3], ext[2], ext[2], ext[3]};
+                const float sep = fmaxf(fmaxf(du - fmaf(ha, p, fmaf(hb, q, hx)), dv - fmaf(ha, q, fmaf(hb, p, hy))),
+                                        fmaxf(da - fmaf(hx, p, fmaf(hy, q, ha)), db - fmaf(hx, q, fmaf(hy, p, hb))));
+                hit |= sep < -eps;
+                a_obs |= fabsf(sep) <= eps;
+            }
+        } else {
+            float rx[4], ry[4];
+            const float lx[4] = {ext[0], ext[0], ext[1], ext[1]};
+            const float ly[4] = {ext[3], ext[2], ext[2], ext[3]};
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    rx[j] = fmaf(c, lx[j], fmaf(-s, ly[j], px));
-                    ry[j] = fmaf(s, lx[j], fmaf(c, ly[j], py));
-                }
-                sep = -INFINITY;
+            for (int j = 0; j < 4; ++j) {
+                rx[j] = fmaf(c, lx[j], fmaf(-s, ly[j], px));
+                ry[j] = fmaf(s, lx[j], fmaf(c, ly[j], py));
+            }
+            for (int k = 0; k < E.n_obs; ++k) {                  // generic convex quads: 8 axes on vertices
+                const float* o = E.obs + HL_OBS32_STRIDE * k;
+                float sep = -INFINITY;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     float nx = o[8 + 3 * i], ny = o[9 + 3 * i], cc = o[10 + 3 * i];
@@ -304,33 +348,43 @@ __device__ __forceinline__ int filter_part(const EnvSmem& E, float px, float py,
                     wmin = fminf(wmin, w); wmax = fmaxf(wmax, w);
                 }
                 sep = fmaxf(sep, fmaxf(fmaxf(umin - ext[1], ext[0] - umax), fmaxf(wmin - ext[3], ext[2] - wmax)));
+                hit |= sep < -eps;
+                a_obs |= fabsf(sep) <= eps;
             }
-            if (sep < -eps) return HL_HIT;
-            if (sep <= eps) amb |= HL_CHECK_OBSTACLES;
         }
+        if (a_obs) amb |= HL_CHECK_OBSTACLES;
     }
     if (flags & HL_CHECK_BOUNDARY) {
         const int n = E.n_field;
-        bool inside = false, all_clear = true, cut = false;
+        bool inside = false;
+        unsigned near_mask = 0;                       // edges whose LINE the rectangle may touch (n <= 32 here)
+        bool overflow = false;
         for (int i = 0; i < n; ++i) {
             const float* e = E.field + HL_FIELD32_STRIDE * i;
-            const float Ax = e[0], Ay = e[1], nx = e[2], ny = e[3];
-            const float* e2 = E.field + HL_FIELD32_STRIDE * ((i + 1 == n) ? 0 : i + 1);
-            const float Bx = e2[0], By = e2[1];
-            // crossing parity of the rectangle centre (ray along +x)
-            if ((Ay > Cy) != (By > Cy)) {
-                float xint = fmaf(Bx - Ax, (Cy - Ay) / (By - Ay), Ax);
-                if (Cx < xint) inside = !inside;
-            }
-            const float nu = fmaf(nx, c, ny * s), nv = fmaf(ny, c, -nx * s);      // n.u, n.v
-            const float sd = fmaf(nx, Cx, fmaf(ny, Cy, -e[4]));                  // signed distance of C to the line
-            const float rn = fmaf(hx, fabsf(nu), hy * fabsf(nv));                // support radius along n
-            if (fabsf(sd) > rn + eps) continue;                                  // clear of the whole line
+            const float4 r0 = *reinterpret_cast<const float4*>(e);               // Ax, Ay, Ex, Ey
+            const float4 r1 = *reinterpret_cast<const float4*>(e + 4);           // nx, ny, c, By
+            // crossing parity of the rectangle centre, division-free: Cx < Ax + Ex*(Cy-Ay)/Ey
+            // By is bit-identical to the next edge's Ay, so the half-open rule stays consistent at vertices
+            const float dyc = Cy - r0.y;
+            const bool straddle = (r0.y > Cy) != (r1.w > Cy);
+            const float lhs = (Cx - r0.x) * r0.w, rhs = r0.z * dyc;
+            inside ^= straddle && ((r0.w > 0.0f) ? (lhs < rhs) : (lhs > rhs));
+            const float nu = fmaf(r1.x, c, r1.y * s), nv = fmaf(r1.y, c, -r1.x * s);      // n.u, n.v
+            const float sd = fmaf(r1.x, Cx, fmaf(r1.y, Cy, -r1.z));                      // signed distance to the line
+            const float rn = fmaf(hx, fabsf(nu), hy * fabsf(nv));                        // support radius along n
+            if (!(fabsf(sd) > rn + eps)) { if (i < 32) near_mask |= 1u << i; else overflow = true; }
+        }
+        bool all_clear = !overflow, cut = false;
+        while (near_mask) {                           // second stage, only for the few nearby edges of this lane
+            const int i = __ffs(near_mask) - 1;
+            near_mask &= near_mask - 1;
+            const float* e = E.field + HL_FIELD32_STRIDE * i;
+            const float Ax = e[0], Ay = e[1], Bx = Ax + e[2], By = e[7], nx = e[4], ny = e[5];
+            const float nu = fmaf(nx, c, ny * s), nv = fmaf(ny, c, -nx * s);
             // along the edge direction t = (-ny, nx):  t.u = -n.v,  t.v = n.u
             const float ct = fmaf(-ny, Cx, nx * Cy);
             const float rt = fmaf(hx, fabsf(nv), hy * fabsf(nu));
-            if (ct - rt > fmaxf(e[5], e[6]) + eps || ct + rt < fminf(e[5], e[6]) - eps) continue;
-            // rectangle axes (pose frame)
+            if (ct - rt > fmaxf(e[8], e[9]) + eps || ct + rt < fminf(e[8], e[9]) - eps) continue;
             float dxa = Ax - px, dya = Ay - py, dxb = Bx - px, dyb = By - py;
             float ua = fmaf(c, dxa, s * dya), wa = fmaf(c, dya, -s * dxa);
             float ub = fmaf(c, dxb, s * dyb), wb = fmaf(c, dyb, -s * dxb);
@@ -347,17 +401,20 @@ __device__ __forceinline__ int filter_part(const EnvSmem& E, float px, float py,
                 if (fabsf(d2v[ax]) < 1e-12f) {
                     if (a2[ax] <= lo2[ax] || a2[ax] >= hi2[ax]) dead = true;
                 } else {
-                    float tl = (lo2[ax] - a2[ax]) / d2v[ax], th = (hi2[ax] - a2[ax]) / d2v[ax];
+                    float inv = 1.0f / d2v[ax];
+                    float tl = (lo2[ax] - a2[ax]) * inv, th = (hi2[ax] - a2[ax]) * inv;
                     t0 = fmaxf(t0, fminf(tl, th));
                     t1 = fminf(t1, fmaxf(tl, th));
                 }
             }
-            if (!dead && t1 - t0 > 1e-4f) cut = true;
+            // the chord inside the shrunken rectangle must be clearly longer than the band
+            if (!dead && (t1 - t0) * sqrtf(fmaf(d2v[0], d2v[0], d2v[1] * d2v[1])) > 8.0f * eps) { cut = true; break; }
         }
-        if (cut) return HL_HIT;
-        if (all_clear) { if (!inside) return HL_HIT; }
+        if (cut) hit = true;
+        else if (all_clear) { if (!inside) hit = true; }
         else amb |= HL_CHECK_BOUNDARY;
     }
+    if (hit) return HL_HIT;
     if ((flags & HL_CHECK_LANE) && E.n_seg > 0) {
         const float rho = sqrtf(fmaf(hx, hx, hy * hy));
         const float rin = (float)HL_LANE_RIN - eps, rout = (float)HL_LANE_R + eps;
@@ -384,26 +441,49 @@ __device__ __forceinline__ int filter_part(const EnvSmem& E, float px, float py,
                 ry[j] = fmaf(s, lx[j], fmaf(c, ly[j], py));
             }
             bool one_holds_all = false;
-            unsigned maybe = 0;
+            unsigned maybe = 0;                    // corner j is inside (or within the band of) some capsule
             for (int i = 0; i < E.n_seg; ++i) {
                 const float* sg = E.seg + 4 * i;
-                float ex = sg[2] - sg[0], ey = sg[3] - sg[1];
-                float inv = 1.0f / fmaf(ex, ex, ey * ey);
-                float dmax = 0.f;
+                bool all_in = true;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    float qx = rx[j] - sg[0], qy = ry[j] - sg[1];
-                    float t = fminf(fmaxf(fmaf(qx, ex, qy * ey) * inv, 0.f), 1.f);
-                    float ddx = fmaf(-t, ex, qx), ddy = fmaf(-t, ey, qy);
-                    float d2 = fmaf(ddx, ddx, ddy * ddy);
-                    dmax = fmaxf(dmax, d2);
-                    if (d2 <= rout * rout) maybe |= 1u << j;
+                    const int st = corner_in_capsule(sg, rx[j], ry[j], eps);
+                    all_in = all_in && (st == 1);
+                    if (st != 0) maybe |= 1u << j;
                 }
-                if (dmax <= rin * rin) one_holds_all = true;
+                if (all_in) one_holds_all = true;
             }
             if (!one_holds_all) {
                 if (maybe != 0xFu) return HL_HIT;
-                amb |= HL_CHECK_LANE;
+                // The corners sit in different capsules.  Certify the union cover piecewise: cut the
+                // rectangle into 4 slices along its long side; a slice whose 4 corners are clearly inside
+                // ONE (convex) capsule is inside the lane.  Only what this cannot certify is ambiguous.
+                unsigned prev = 0;
+                bool covered = true;
+#pragma unroll 1
+                for (int q = 0; q <= 4 && covered; ++q) {
+                    const float lxq = ext[0] + 0.25f * (float)q * (ext[1] - ext[0]);
+                    unsigned m = 0xFFFFu;                 // capsules holding BOTH points of this cross-section
+#pragma unroll
+                    for (int side = 0; side < 2; ++side) {
+                        const float lyq = side ? ext[3] : ext[2];
+                        const float wx = fmaf(c, lxq, fmaf(-s, lyq, px)), wy = fmaf(s, lxq, fmaf(c, lyq, py));
+                        unsigned in = 0;
+                        for (int i = 0; i < E.n_seg; ++i) {
+                            const float* sg = E.seg + 4 * i;
+                            float ex = sg[2] - sg[0], ey = sg[3] - sg[1];
+                            float inv = 1.0f / fmaf(ex, ex, ey * ey);
+                            float qx = wx - sg[0], qy = wy - sg[1];
+                            float t = fminf(fmaxf(fmaf(qx, ex, qy * ey) * inv, 0.f), 1.f);
+                            float ddx = fmaf(-t, ex, qx), ddy = fmaf(-t, ey, qy);
+                            if (fmaf(ddx, ddx, ddy * ddy) <= rin * rin) in |= 1u << i;
+                        }
+                        m &= in;
+                    }
+                    if (q > 0 && (prev & m) == 0) covered = false;
+                    prev = m;
+                }
+                if (!covered) amb |= HL_CHECK_LANE;
             }
         }
     }
@@ -455,7 +535,7 @@ static __device__ bool pose_infeasible(const EnvBatchDev& eb, const EnvDesc& D, 
 __device__ __forceinline__ void stage_env(const EnvBatchDev& eb, const EnvDesc& D, float* sm, int cap_floats,
                                           EnvSmem& E, bool& staged) {
     int need = D.n_obs * HL_OBS32_STRIDE + D.n_field * HL_FIELD32_STRIDE + D.n_seg * 4;
-    E.n_obs = D.n_obs; E.n_field = D.n_field; E.n_seg = D.n_seg;
+    E.n_obs = D.n_obs; E.n_field = D.n_field; E.n_seg = D.n_seg; E.all_rect = D.all_rect;
     E.eps = D.eps; E.reach = D.reach;
     for (int k = 0; k < 4; ++k) E.ext[k] = (float)D.body_ext[k];
     const float* g_obs = eb.obs32 + (size_t)HL_OBS32_STRIDE * D.obs_off;
@@ -476,7 +556,7 @@ __device__ __forceinline__ void stage_env(const EnvBatchDev& eb, const EnvDesc& 
 }
 
 __device__ __forceinline__ void global_env(const EnvBatchDev& eb, const EnvDesc& D, EnvSmem& E) {
-    E.n_obs = D.n_obs; E.n_field = D.n_field; E.n_seg = D.n_seg;
+    E.n_obs = D.n_obs; E.n_field = D.n_field; E.n_seg = D.n_seg; E.all_rect = D.all_rect;
     E.eps = D.eps; E.reach = D.reach;
     for (int k = 0; k < 4; ++k) E.ext[k] = (float)D.body_ext[k];
     E.obs = eb.obs32 + (size_t)HL_OBS32_STRIDE * D.obs_off;
