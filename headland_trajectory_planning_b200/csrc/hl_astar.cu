@@ -180,7 +180,11 @@ struct AsSmem {
     double rs_L[HL_RS_CANDIDATES], rs_prio[HL_RS_CANDIDATES];
     int rs_acc[HL_RS_CANDIDATES], rs_order[HL_RS_CANDIDATES];
     unsigned char rs_valid[HL_RS_CANDIDATES + 2];
+    unsigned char rs_accept[HL_RS_CANDIDATES + 2];
+    double rs_Lc[HL_RS_CANDIDATES];
+    RsProblem rs_prob;
     int rs_n, rs_pick;
+    int vote[2][AS_WARPS];        // per-warp (hit | ambiguous << 1) bits of the current sample chunk
     RsPlan plans[AS_MAX_PLANS];
     RsPlan plan_tmp;
     // primitives
@@ -354,6 +358,8 @@ k_hybrid_astar(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen, 
                         S.cur = cur; S.cx = W.nx[cur]; S.cy = W.ny[cur]; S.cyaw = W.nyaw[cur]; S.cg = W.ng[cur];
                         S.cprim = W.nprim[cur];
                         S.rs_pick = -1;
+                        const double q0n[3] = {S.cx, S.cy, S.cyaw};
+                        S.rs_prob = rs_normalise(q0n, S.goal, P.maxc);      // generate_path (:565-572), once per pop
                     }
                 }
             }
@@ -365,16 +371,17 @@ k_hybrid_astar(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen, 
             {
                 const double q0[3] = {S.cx, S.cy, S.cyaw};
                 if (tid < HL_RS_CANDIDATES) {
-                    RsProblem R = rs_normalise(q0, S.goal, P.maxc);
                     double l[HL_RS_MAX_SEGS] = {0, 0, 0, 0, 0};
-                    bool ok = rs_candidate(tid, R, l);
+                    bool ok = rs_candidate(tid, S.rs_prob, l);
                     S.rs_valid[tid] = ok ? 1 : 0;
                     for (int k = 0; k < HL_RS_MAX_SEGS; ++k) S.rs_lens[tid][k] = l[k];
                 }
                 __syncthreads();
                 TICK(PH_RS_CAND);
+                if (tid < RS_N_GROUPS) rs_select_group(tid, S.rs_valid, S.rs_lens, S.rs_accept, S.rs_Lc);
+                __syncthreads();
                 if (tid == 0) {
-                    int m = rs_select(S.rs_valid, S.rs_lens, S.rs_acc, S.rs_L);
+                    int m = rs_select_compact(S.rs_accept, S.rs_Lc, S.rs_acc, S.rs_L);
                     if (m < 0) { S.status = HL_STATUS_RS_ASSERT; m = 0; }
                     S.rs_n = m;
                     for (int k = 0; k < m; ++k)
@@ -387,19 +394,28 @@ k_hybrid_astar(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen, 
                 TICK(PH_RS_SELECT);
                 const int m = S.rs_n;
                 const double stepn = xmul(P.res, P.maxc);
+                const double cq = cos(-q0[2]), sq = sin(-q0[2]);
                 // sampling plans of the first AS_MAX_PLANS words in pop order, one thread each
                 if (tid < m && tid < AS_MAX_PLANS) {
                     int c = S.rs_acc[S.rs_order[tid]];
                     rs_make_plan(c, S.rs_lens[c], P.maxc, stepn, S.plans[tid]);
+                    rs_plan_world32(S.plans[tid], q0, cq, sq, D.origin);
                 }
                 __syncthreads();
                 TICK(PH_RS_PLAN);
-                const double cq = cos(-q0[2]), sq = sin(-q0[2]);
+                // sampled poses are float32 for the filter (1 sincosf per pose); their error (~1e-5 m) widens the band
+                EnvSmem Ers = E;
+                Ers.eps = E.eps + 6e-5f;
+                const float inv_maxc = (float)(1.0 / P.maxc);
+                int vb = 0;
                 for (int r = 0; r < m; ++r) {
                     const int k = S.rs_order[r];
                     const int c = S.rs_acc[k];
                     if (r >= AS_MAX_PLANS) {
-                        if (tid == 0) rs_make_plan(c, S.rs_lens[c], P.maxc, stepn, S.plan_tmp);
+                        if (tid == 0) {
+                            rs_make_plan(c, S.rs_lens[c], P.maxc, stepn, S.plan_tmp);
+                            rs_plan_world32(S.plan_tmp, q0, cq, sq, D.origin);
+                        }
                         __syncthreads();
                     }
                     const RsPlan& plan = (r < AS_MAX_PLANS) ? S.plans[r] : S.plan_tmp;
@@ -409,19 +425,32 @@ k_hybrid_astar(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen, 
                         const int j = base + tid;
                         int st = HL_FREE;
                         unsigned amb = 0;
-                        double wx = 0, wy = 0, wyaw = 0;
                         if (j < npts) {
-                            double lx, ly, lyaw;
-                            int cs, dir;
-                            rs_sample_local(plan, j, P.maxc, lx, ly, lyaw, cs, dir);
-                            rs_to_world(q0, cq, sq, lx, ly, lyaw, wx, wy, wyaw);
-                            st = pose_filter(D, E, wx, wy, wyaw, FLAGS, &amb);
+                            float fx, fy, fc, fs;
+                            rs_sample_world32(plan, j, inv_maxc, fx, fy, fc, fs);
+                            if (fabsf(fx) > Ers.reach || fabsf(fy) > Ers.reach) { st = HL_AMBIG; amb = FLAGS; }
+                            else st = filter_part(Ers, fx, fy, fc, fs, Ers.ext, FLAGS, &amb);
                         }
-                        infeasible = __syncthreads_or(st == HL_HIT);
-                        if (!infeasible) {
+                        // one barrier per chunk: warps publish (any hit | any ambiguous << 1)
+                        const unsigned hitm = __ballot_sync(0xffffffffu, st == HL_HIT);
+                        const unsigned ambm = __ballot_sync(0xffffffffu, st == HL_AMBIG);
+                        if (lane == 0) S.vote[vb][wid] = (hitm ? 1 : 0) | (ambm ? 2 : 0);
+                        __syncthreads();
+                        int bits = 0;
+#pragma unroll
+                        for (int w = 0; w < AS_WARPS; ++w) bits |= S.vote[vb][w];
+                        vb ^= 1;
+                        infeasible = bits & 1;
+                        if (!infeasible && (bits & 2)) {          // float64 sample + exact predicate, ambiguous poses only
                             int bad = 0;
-                            if (st == HL_AMBIG) bad = pose_exact(eb, D, wx, wy, wyaw, amb) ? 1 : 0;
-                            if (st == HL_AMBIG) atomicAdd(&S.n_exact, 1ULL);
+                            if (st == HL_AMBIG) {
+                                double lx, ly, lyaw, wx, wy, wyaw;
+                                int cs, dir;
+                                rs_sample_local(plan, j, P.maxc, lx, ly, lyaw, cs, dir);
+                                rs_to_world(q0, cq, sq, lx, ly, lyaw, wx, wy, wyaw);
+                                bad = pose_exact(eb, D, wx, wy, wyaw, amb) ? 1 : 0;
+                                atomicAdd(&S.n_exact, 1ULL);
+                            }
                             infeasible = __syncthreads_or(bad);
                         }
                         if (tid == 0) S.n_checks += (unsigned long long)min(AS_THREADS, npts - base);
@@ -431,7 +460,7 @@ k_hybrid_astar(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen, 
                         if (tid == 0) { S.rs_pick = r; S.arrival = 1; S.rs_word = c; S.goal_cost = S.rs_prio[k]; }
                         break;
                     }
-                    __syncthreads();      // plan_tmp is rewritten next round
+                    if (r + 1 >= AS_MAX_PLANS) __syncthreads();      // plan_tmp is rewritten next round
                 }
                 __syncthreads();
                 TICK(PH_RS_SAMPLE);

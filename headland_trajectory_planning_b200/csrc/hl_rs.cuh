@@ -48,7 +48,10 @@ __device__ __forceinline__ void rs_polar(double x, double y, double& r, double& 
     th = atan2(y, x);
 }
 
-static __device__ bool rs_solve(int solver, double x, double y, double phi, double& t, double& u, double& v) {
+// sphi, cphi = sine and cosine of the (already mirrored) phi: sin is odd and cos even bit-for-bit,
+// so the caller derives them from one sincos per pose pair.
+static __device__ bool rs_solve(int solver, double x, double y, double phi, double sphi, double cphi,
+                                double& t, double& u, double& v) {
     const double PI = HL_PI;
     switch (solver) {
     case RS_SLS: {                                              // reeds_shepp.py:144-160
@@ -68,7 +71,7 @@ static __device__ bool rs_solve(int solver, double x, double y, double phi, doub
     }
     case RS_LSL: {                                              // :90-98
         double r, th;
-        rs_polar(xsub(x, sin(phi)), xadd(xsub(y, 1.0), cos(phi)), r, th);
+        rs_polar(xsub(x, sphi), xadd(xsub(y, 1.0), cphi), r, th);
         u = r; t = th;
         if (t >= 0.0) {
             v = rs_mod2pi(xsub(phi, t));
@@ -78,7 +81,7 @@ static __device__ bool rs_solve(int solver, double x, double y, double phi, doub
     }
     case RS_LSR: {                                              // :101-114
         double u1, t1;
-        rs_polar(xadd(x, sin(phi)), xsub(xsub(y, 1.0), cos(phi)), u1, t1);
+        rs_polar(xadd(x, sphi), xsub(xsub(y, 1.0), cphi), u1, t1);
         u1 = xmul(u1, u1);
         if (u1 >= 4.0) {
             u = sqrt(xsub(u1, 4.0));
@@ -91,7 +94,7 @@ static __device__ bool rs_solve(int solver, double x, double y, double phi, doub
     }
     case RS_LRL: {                                              // :117-128
         double u1, t1;
-        rs_polar(xsub(x, sin(phi)), xadd(xsub(y, 1.0), cos(phi)), u1, t1);
+        rs_polar(xsub(x, sphi), xadd(xsub(y, 1.0), cphi), u1, t1);
         if (u1 <= 4.0) {
             u = xmul(-2.0, asin(xmul(0.25, u1)));
             t = rs_mod2pi(xadd(xadd(t1, xmul(0.5, u)), PI));
@@ -102,8 +105,8 @@ static __device__ bool rs_solve(int solver, double x, double y, double phi, doub
     }
     case RS_LRLRN:
     case RS_LRLRP: {                                            // :239-283
-        double xi = xadd(x, sin(phi));
-        double eta = xsub(xsub(y, 1.0), cos(phi));
+        double xi = xadd(x, sphi);
+        double eta = xsub(xsub(y, 1.0), cphi);
         double uu, vv;
         if (solver == RS_LRLRN) {
             double rho = xmul(0.25, xadd(2.0, sqrt(xadd(xmul(xi, xi), xmul(eta, eta)))));
@@ -130,8 +133,8 @@ static __device__ bool rs_solve(int solver, double x, double y, double phi, doub
         return t >= 0.0 && v >= 0.0;
     }
     case RS_LRSR: {                                             // :322-334
-        double xi = xadd(x, sin(phi));
-        double eta = xsub(xsub(y, 1.0), cos(phi));
+        double xi = xadd(x, sphi);
+        double eta = xsub(xsub(y, 1.0), cphi);
         double rho, theta;
         rs_polar(-eta, xi, rho, theta);
         if (rho >= 2.0) {
@@ -143,8 +146,8 @@ static __device__ bool rs_solve(int solver, double x, double y, double phi, doub
         return false;
     }
     case RS_LRSL: {                                             // :337-350
-        double xi = xsub(x, sin(phi));
-        double eta = xadd(xsub(y, 1.0), cos(phi));
+        double xi = xsub(x, sphi);
+        double eta = xadd(xsub(y, 1.0), cphi);
         double rho, theta;
         rs_polar(xi, eta, rho, theta);
         if (rho >= 2.0) {
@@ -157,8 +160,8 @@ static __device__ bool rs_solve(int solver, double x, double y, double phi, doub
         return false;
     }
     default: {                                                  // RS_LRSLR :425-440
-        double xi = xadd(x, sin(phi));
-        double eta = xsub(xsub(y, 1.0), cos(phi));
+        double xi = xadd(x, sphi);
+        double eta = xsub(xsub(y, 1.0), cphi);
         double rho, theta;
         rs_polar(xi, eta, rho, theta);
         if (rho >= 2.0) {
@@ -177,7 +180,7 @@ static __device__ bool rs_solve(int solver, double x, double y, double phi, doub
 }
 
 // Normalised problem of one pose pair (generate_path, :565-572)
-struct RsProblem { double x, y, phi, xb, yb; };
+struct RsProblem { double x, y, phi, xb, yb, sp, cp; };
 
 __device__ __forceinline__ RsProblem rs_normalise(const double* q0, const double* q1, double maxc) {
     RsProblem P;
@@ -198,9 +201,10 @@ static __device__ bool rs_candidate(int cand, const RsProblem& P, double* lens) 
     double ax = row.backwards ? P.xb : P.x, ay = row.backwards ? P.yb : P.y;
     if (row.neg_x) ax = -ax;
     if (row.neg_y) ay = -ay;
-    double aphi = (row.neg_x != row.neg_y) ? -P.phi : P.phi;
+    const bool negphi = row.neg_x != row.neg_y;
+    double aphi = negphi ? -P.phi : P.phi;
     double t, u, v;
-    if (!rs_solve(row.solver, ax, ay, aphi, t, u, v)) return false;
+    if (!rs_solve(row.solver, ax, ay, aphi, negphi ? -P.sp : P.sp, P.cp, t, u, v)) return false;
     const double H = xmul(-0.5, HL_PI);
     switch (row.pattern) {
     case RP_TUV:   lens[0] = t; lens[1] = u; lens[2] = v; break;
@@ -216,33 +220,67 @@ static __device__ bool rs_candidate(int cand, const RsProblem& P, double* lens) 
     return true;
 }
 
-// set_path (:68-87) over all 46 candidates, sequential: returns number of accepted
-// words, -1 if the reference's `assert path.L >= 0.01` would fire.
-//   valid[c], lens[c][5]  : candidate results
-//   acc[k]                : accepted candidate indices (reference order)
-//   L[k]                  : normalised total length
-static __device__ int rs_select(const unsigned char* valid, const double (*lens)[HL_RS_MAX_SEGS], int* acc, double* L) {
-    int n = 0;
-    for (int c = 0; c < HL_RS_CANDIDATES; ++c) {
+// set_path (:68-87).  A candidate is only ever compared with EARLIER accepted candidates of the same
+// letters, so the 46 rows split into 20 independent letter groups (<= 4 rows each, listed in evaluation
+// order).  rs_select_group decides one group; rs_select_compact then lists the accepted rows in
+// evaluation order.  accept[c]: 0 rejected / invalid, 1 accepted, 2 = the reference's
+// `assert path.L >= 0.01` would fire.
+#define RS_N_GROUPS 20
+static __constant__ signed char c_rs_groups[RS_N_GROUPS][4] = {
+    {0, -1, -1, -1}, {1, -1, -1, -1},                       // SLS, SRS
+    {2, 3, -1, -1}, {4, 5, -1, -1},                         // LSL, RSR
+    {6, 7, -1, -1}, {8, 9, -1, -1},                         // LSR, RSL
+    {10, 11, 14, 15}, {12, 13, 16, 17},                     // LRL, RLR
+    {18, 19, 22, 23}, {20, 21, 24, 25},                     // LRLR, RLRL
+    {26, 27, -1, -1}, {28, 29, -1, -1},                     // LRSL, RLSR
+    {30, 31, -1, -1}, {32, 33, -1, -1},                     // LRSR, RLSL
+    {34, 35, -1, -1}, {36, 37, -1, -1},                     // LSRL, RSLR
+    {38, 39, -1, -1}, {40, 41, -1, -1},                     // RSRL, LSLR
+    {42, 43, -1, -1}, {44, 45, -1, -1},                     // LRSLR, RLSRL
+};
+
+static __device__ void rs_select_group(int g, const unsigned char* valid, const double (*lens)[HL_RS_MAX_SEGS],
+                                       unsigned char* accept, double* Lc) {
+    int kept[4];
+    int nk = 0;
+    for (int q = 0; q < 4; ++q) {
+        const int c = c_rs_groups[g][q];
+        if (c < 0) break;
+        accept[c] = 0;
         if (!valid[c]) continue;
-        const RsRow row = c_rs_rows[c];
+        const int nseg = c_rs_rows[c].nseg;
         bool dup = false;
-        for (int k = 0; k < n && !dup; ++k) {
-            const RsRow prev = c_rs_rows[acc[k]];
-            if (prev.nseg == row.nseg && prev.letters == row.letters) {
-                double s = 0.0;                                  // Python sum(): 0 + d0 + d1 + ...
-                for (int i = 0; i < row.nseg; ++i) s = xadd(s, xsub(lens[acc[k]][i], lens[c][i]));
-                if (s <= 0.01) dup = true;
-            }
+        for (int k = 0; k < nk && !dup; ++k) {
+            double s = 0.0;                                  // Python sum(): 0 + d0 + d1 + ...
+            for (int i = 0; i < nseg; ++i) s = xadd(s, xsub(lens[kept[k]][i], lens[c][i]));
+            if (s <= 0.01) dup = true;
         }
         if (dup) continue;
         double tot = 0.0;
-        for (int i = 0; i < row.nseg; ++i) tot = xadd(tot, fabs(lens[c][i]));
-        if (tot >= 1000.0) continue;                             // MAX_LENGTH
-        if (!(tot >= 0.01)) return -1;
-        acc[n] = c; L[n] = tot; ++n;
+        for (int i = 0; i < nseg; ++i) tot = xadd(tot, fabs(lens[c][i]));
+        if (tot >= 1000.0) continue;                         // MAX_LENGTH
+        Lc[c] = tot;
+        if (!(tot >= 0.01)) { accept[c] = 2; continue; }
+        accept[c] = 1;
+        kept[nk++] = c;
+    }
+}
+
+// accepted rows in evaluation order; returns their number or -1 when the assert would fire
+static __device__ int rs_select_compact(const unsigned char* accept, const double* Lc, int* acc, double* L) {
+    int n = 0;
+    for (int c = 0; c < HL_RS_CANDIDATES; ++c) {
+        if (accept[c] == 2) return -1;
+        if (accept[c] == 1) { acc[n] = c; L[n] = Lc[c]; ++n; }
     }
     return n;
+}
+
+static __device__ int rs_select(const unsigned char* valid, const double (*lens)[HL_RS_MAX_SEGS], int* acc, double* L) {
+    unsigned char accept[HL_RS_CANDIDATES];
+    double Lc[HL_RS_CANDIDATES];
+    for (int g = 0; g < RS_N_GROUPS; ++g) rs_select_group(g, valid, lens, accept, Lc);
+    return rs_select_compact(accept, Lc, acc, L);
 }
 
 // calculate_reeds_shepp_path_cost (hybrid_a_star_search.py:129-160) with the quirks:
@@ -304,6 +342,9 @@ struct RsSegPlan {
     double ox, oy, oyaw;     // origin pose of the segment (local frame of the start pose)
     double pd0, d, l;        // first offset, step, signed normalised length
     int first, count, letter;  // first emitted index, loop samples, letter
+    // float32 view for the collision filter (rs_plan_world32): segment origin in the environment's
+    // float32 frame and cos/sin of the world heading there
+    float fox, foy, fc0, fs0;
 };
 struct RsPlan {
     RsSegPlan seg[HL_RS_MAX_SEGS];
@@ -352,9 +393,22 @@ static __device__ void rs_make_plan(int cand, const double* lens, double maxc, d
         else pd = xsub(d, ll);
         S.pd0 = pd;
         S.first = ind + 1;
+        // loop count of `while abs(pd) <= abs(l): pd += d`.  Along the step direction the offsets are
+        // a + k*|d| with a = +-pd, so the count is floor((|l| - a)/|d|) + 1 unless the boundary is within
+        // 1e-7 of a sample, where the reference's repeated addition is replayed exactly.
         int cnt = 0;
-        double al = fabs(l);
-        while (fabs(pd) <= al) { ++cnt; pd = xadd(pd, d); }
+        const double al = fabs(l);
+        if (fabs(pd) <= al) {
+            const double a = (d > 0.0) ? pd : -pd;
+            const double r = (al - a) / step;
+            const double kf = floor(r);
+            if (r - kf > 1e-7 && kf + 1.0 - r > 1e-7 && r < 1e7) {
+                cnt = (int)kf + 1;
+                pd = xadd(pd, xmul((double)cnt, d));
+            } else {
+                while (fabs(pd) <= al) { ++cnt; pd = xadd(pd, d); }
+            }
+        }
         S.count = cnt;
         ind += cnt;
         ll = xsub(xsub(l, pd), d);
@@ -399,6 +453,47 @@ static __device__ void rs_sample_local(const RsPlan& P, int j, double maxc, doub
     rs_interp(off, S.letter, maxc, S.ox, S.oy, S.oyaw, px, py, pyaw);
     cs_sign = (S.letter == RS_S) ? 0 : (S.letter == RS_L ? 1 : -1);
     dir = (off > 0.0) ? 1 : -1;
+}
+
+// float32 view of a plan for the collision filter: per segment the world position of its origin
+// relative to the environment origin and cos/sin of the world heading there.  One call per word.
+static __device__ void rs_plan_world32(RsPlan& P, const double* q0, double cq, double sq, const double* env_origin) {
+    for (int i = 0; i < P.nseg; ++i) {
+        RsSegPlan& S = P.seg[i];
+        double wx = xadd(xadd(xmul(cq, S.ox), xmul(sq, S.oy)), q0[0]);
+        double wy = xadd(xadd(xmul(-sq, S.ox), xmul(cq, S.oy)), q0[1]);
+        S.fox = (float)(wx - env_origin[0]);
+        S.foy = (float)(wy - env_origin[1]);
+        double sn, cs;
+        sincos(S.oyaw + q0[2], &sn, &cs);
+        S.fc0 = (float)cs; S.fs0 = (float)sn;
+    }
+}
+
+// Pose j in the environment's float32 frame: position and cos/sin of the world yaw (1 sincosf).
+__device__ __forceinline__ void rs_sample_world32(const RsPlan& P, int j, float inv_maxc, float& wx, float& wy,
+                                                  float& c, float& s) {
+    int si = P.nseg - 1;
+    while (si > 0 && j < P.seg[si].first) --si;
+    const RsSegPlan& S = P.seg[si];
+    if (j == 0) { wx = P.seg[0].fox; wy = P.seg[0].foy; c = P.seg[0].fc0; s = P.seg[0].fs0; return; }
+    const int k = j - S.first;
+    const float off = (float)((k < S.count) ? (S.pd0 + (double)k * S.d) : S.l);
+    float dx, dy, cy, sy;
+    if (S.letter == RS_S) {
+        dx = off * inv_maxc; dy = 0.f; cy = 1.f; sy = 0.f;
+    } else {
+        float sn, cs;
+        sincosf(off, &sn, &cs);
+        dx = sn * inv_maxc;
+        const float one_m = (1.0f - cs) * inv_maxc;
+        if (S.letter == RS_L) { dy = one_m; cy = cs; sy = sn; }
+        else { dy = -one_m; cy = cs; sy = -sn; }
+    }
+    wx = fmaf(S.fc0, dx, fmaf(-S.fs0, dy, S.fox));
+    wy = fmaf(S.fs0, dx, fmaf(S.fc0, dy, S.foy));
+    c = fmaf(S.fc0, cy, -S.fs0 * sy);
+    s = fmaf(S.fs0, cy, S.fc0 * sy);
 }
 
 // Local -> world (calc_all_paths, :50-59)
