@@ -345,8 +345,11 @@ k_hybrid_astar(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen, 
 
         TICK(PH_SETUP);
         // =============================== main loop (:525-596) ===============================
-        while (S.status < 0) {
-            if (tid == 0) {
+        // Control flow is decided ONLY by reads of S.status that directly follow a barrier, and thread 0
+        // never rewrites S.status between such a read and the next barrier -- otherwise a late warp could
+        // see the new value, leave the loop alone and desynchronise the CTA's barriers.
+        while (true) {
+            if (tid == 0 && S.status < 0) {
                 if (S.counter > P.max_nodes) S.status = HL_STATUS_MAX_NODES;
                 else {
                     S.counter += 1;
@@ -471,16 +474,13 @@ k_hybrid_astar(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen, 
                 double wd = fabs(angle_wrap(xsub(S.cyaw, S.goal[2])));
                 if (xd < P.res && yd < P.res && wd < P.yaw_res) { S.arrival = 2; S.goal_cost = S.cg; S.rs_word = -1; }
                 if (S.arrival) S.status = HL_STATUS_OK;
-            }
-            __syncthreads();
-            if (S.status >= 0) break;
-
-            // ---- primitive expansion (:558-596)
-            if (tid == 0) {
-                int seg = exact_search_segment(eb, D, S.cx, S.cy);              // get_search_length (:368)
-                double len = seg < 0 ? D.default_len : eb.seg_len[D.seg_off + seg];
-                S.nsteps = (int)rint(xdiv(len, P.res));                        // Python round()
-                if (S.nsteps + 1 > HL_MAX_ROLLOUT || S.nsteps < 1) S.status = HL_STATUS_CAPACITY;
+                else {
+                    // ---- primitive expansion (:558-596): search length of this node (get_search_length, :368)
+                    int seg = exact_search_segment(eb, D, S.cx, S.cy);
+                    double len = seg < 0 ? D.default_len : eb.seg_len[D.seg_off + seg];
+                    S.nsteps = (int)rint(xdiv(len, P.res));                    // Python round()
+                    if (S.nsteps + 1 > HL_MAX_ROLLOUT || S.nsteps < 1) S.status = HL_STATUS_CAPACITY;
+                }
             }
             if (tid < HL_MAX_PRIMS) { S.phit[tid] = 0; S.pany_amb[tid] = 0; }
             __syncthreads();
@@ -690,6 +690,7 @@ k_hybrid_astar(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen, 
             r.n_exact = (long long)S.n_exact;
             results[sc] = r;
             long long _n = clock64(); S.t_phase[PH_OUTPUT] += _n - S.t_last;
+            { long long tot = 0; for (int k = 0; k < AS_N_PHASES; ++k) tot += S.t_phase[k]; results[sc].cycles = tot; }
             for (int k = 0; k < AS_N_PHASES; ++k) atomicAdd(phase_cycles + k, (unsigned long long)S.t_phase[k]);
         }
         // reset the used hash positions for the next scenario of this CTA

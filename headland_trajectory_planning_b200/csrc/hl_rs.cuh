@@ -190,6 +190,7 @@ __device__ __forceinline__ RsProblem rs_normalise(const double* q0, const double
     P.x = xmul(xadd(xmul(c, dx), xmul(s, dy)), maxc);
     P.y = xmul(xadd(xmul(-s, dx), xmul(c, dy)), maxc);
     double cp = cos(P.phi), sp = sin(P.phi);                    // :217-218 / :387-388
+    P.sp = sp; P.cp = cp;
     P.xb = xadd(xmul(P.x, cp), xmul(P.y, sp));
     P.yb = xsub(xmul(P.x, sp), xmul(P.y, cp));
     return P;

@@ -122,6 +122,8 @@ typedef struct {
     double  goal_cost;     /* cost of the goal node                                   */
     int64_t n_pose_checks; /* footprint checks executed (primitives + shots)          */
     int64_t n_exact;       /* of which escalated to the float64 predicates            */
+    int64_t cycles;        /* SM clock cycles this scenario occupied its CTA (the reference prints
+                              `hybrid search time`, hybrid_a_star_search.py:603)       */
 } HlPlanResult;
 
 /* Reeds-Shepp word record: hl_rs_all_paths output, one row per accepted word. */
