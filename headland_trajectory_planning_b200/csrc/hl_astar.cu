@@ -15,14 +15,24 @@
 // (oracle/heapdict_port.py).  Footprint tests go through the float32 filter first and
 // escalate to the float64 predicates only inside the error band, and only when no other
 // pose of the same path already decided it.
+// The search kernel runs many different phases on different warps/CTAs at once; with every helper
+// inlined its SASS was 460 KB and 73 % of the non-barrier stall samples were instruction-fetch misses
+// (profiles/r1b).  HL_SHARED_CODE makes the heavy helpers out-of-line so the kernel keeps one copy.
+#define HL_SHARED_CODE 1
 #include <cstring>
 #include "hl_geom.cuh"
 #include "hl_rs.cuh"
 
+#ifndef AS_THREADS
 #define AS_THREADS 128
+#endif
+#ifndef AS_MIN_CTAS
+#define AS_MIN_CTAS 4
+#endif
 #define AS_WARPS (AS_THREADS / 32)
-#define AS_MAX_PLANS 12
+#define AS_MAX_PLANS 8
 #define AS_ROLL (HL_MAX_ROLLOUT + 1)
+#define AS_ENV_FLOATS 768       // staged float32 environment (canonical: 8x28 + 16x12 + 4x4 = 432 floats)
 #define KEY_EMPTY (-1LL)
 // phase timers (cycles of thread 0 between barriers), the device analogue of the reference's three
 // accumulating timers (hybrid_a_star_search.py:91-94): summed over scenarios into ctx->d_counters
@@ -102,7 +112,7 @@ __device__ __forceinline__ unsigned hash_key(long long k) {
 }
 
 // returns slot or -1; *pos = table position where the key is / would be inserted
-__device__ int hash_find(const AsWs& w, int hmask, long long key, int* pos) {
+__device__ __noinline__ int hash_find(const AsWs& w, int hmask, long long key, int* pos) {
     unsigned h = hash_key(key) & hmask;
     while (true) {
         long long k = w.hkey[h];
@@ -120,7 +130,7 @@ __device__ __forceinline__ void heap_swap(const AsWs& w, int i, int j) {
     w.hprio[j] = pi; w.hslot[j] = si; w.nheap[si] = j;
 }
 
-__device__ void heap_decrease_key(const AsWs& w, int i) {
+__device__ __noinline__ void heap_decrease_key(const AsWs& w, int i) {
     while (i) {
         int parent = (i - 1) >> 1;
         if (w.hprio[parent] < w.hprio[i]) break;
@@ -129,7 +139,7 @@ __device__ void heap_decrease_key(const AsWs& w, int i) {
     }
 }
 
-__device__ int heap_popitem(const AsWs& w, int& n) {
+__device__ __noinline__ int heap_popitem(const AsWs& w, int& n) {
     int top = w.hslot[0];
     --n;
     if (n > 0) {
@@ -148,7 +158,7 @@ __device__ int heap_popitem(const AsWs& w, int& n) {
     return top;
 }
 
-__device__ void heap_set(const AsWs& w, int& n, int slot, double prio) {
+__device__ __noinline__ void heap_set(const AsWs& w, int& n, int slot, double prio) {
     if (w.nheap[slot] >= 0) {                      // __setitem__ on an existing key: pop(key) first
         int i = w.nheap[slot];
         while (i) {                                // __delitem__: bubble to the root unconditionally
@@ -205,7 +215,7 @@ struct AsSmem {
 };
 
 // Ternary footprint status of one pose (body only): HL_FREE / HL_HIT / HL_AMBIG(+mask)
-__device__ __forceinline__ int pose_filter(const EnvDesc& D, const EnvSmem& E, double x, double y, double yaw,
+__device__ HL_CODE int pose_filter(const EnvDesc& D, const EnvSmem& E, double x, double y, double yaw,
                                            unsigned flags, unsigned* amb) {
     float px = (float)(x - D.origin[0]), py = (float)(y - D.origin[1]);
     if (fabsf(px) > E.reach || fabsf(py) > E.reach || !(fabs(yaw) < 1e6)) { *amb = flags; return HL_AMBIG; }
@@ -214,15 +224,15 @@ __device__ __forceinline__ int pose_filter(const EnvDesc& D, const EnvSmem& E, d
     return filter_part(E, px, py, cf, sf, E.ext, flags, amb);
 }
 
-__device__ __forceinline__ bool pose_exact(const EnvBatchDev& eb, const EnvDesc& D, double x, double y, double yaw,
+__device__ __noinline__ bool pose_exact(const EnvBatchDev& eb, const EnvDesc& D, double x, double y, double yaw,
                                            unsigned amb) {
     Pose64 p;
-    p.x = x; p.y = y; p.c = cos(yaw); p.s = sin(yaw);
+    p.x = x; p.y = y; p.c = m_cos(yaw); p.s = m_sin(yaw);
     return exact_part_check(p, D.body_ext, eb, D, amb);
 }
 
 // calculate_state_cost (reference_line_heuristic.py:131-158) for one pose, one warp.
-__device__ double warp_state_cost(const EnvBatchDev& eb, const EnvDesc& D, double x, double y, double yaw, int lane) {
+__device__ __noinline__ double warp_state_cost(const EnvBatchDev& eb, const EnvDesc& D, double x, double y, double yaw, int lane) {
     const double* gx = eb.guide_x + D.guide_off;
     const double* gy = eb.guide_y + D.guide_off;
     const int n = D.n_guide;
@@ -259,7 +269,7 @@ __device__ double warp_state_cost(const EnvBatchDev& eb, const EnvDesc& D, doubl
 
 // One step of the kinematic rollout (kinematic_simulation_node, :366-390): yaws[i] of
 // np.linspace(init_yaw, init_yaw + yaw_step*(n+1), n+2) after angle_wrap.
-__device__ __forceinline__ double rollout_yaw(double init_yaw, double stop, double step, double delta, int div, int i) {
+__device__ HL_CODE double rollout_yaw(double init_yaw, double stop, double step, double delta, int div, int i) {
     double v;
     if (i == div) v = stop;                                     // y[-1] = stop
     else if (step != 0.0) v = xadd(xmul((double)i, step), init_yaw);
@@ -267,7 +277,7 @@ __device__ __forceinline__ double rollout_yaw(double init_yaw, double stop, doub
     return angle_wrap(v);
 }
 
-__global__ void __launch_bounds__(AS_THREADS)
+__global__ void __launch_bounds__(AS_THREADS, AS_MIN_CTAS)
 k_hybrid_astar(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen, AsParams P, char* ws_base,
                size_t ws_stride, unsigned int* work_counter, HlPlanResult* __restrict__ results,
                int32_t* __restrict__ expanded_keys, double* __restrict__ path_x, double* __restrict__ path_y,
@@ -280,7 +290,7 @@ k_hybrid_astar(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen, 
     const AsWs W = as_carve(ws_base + (size_t)blockIdx.x * ws_stride, P.cap_nodes, P.hash_size, P.max_nodes);
     const int hmask = P.hash_size - 1;
     const unsigned FLAGS = HL_CHECK_OBSTACLES | HL_CHECK_BOUNDARY | HL_CHECK_LANE;
-    const int env_sm_floats = 2048;
+    const int env_sm_floats = AS_ENV_FLOATS;
 
     // hash table starts empty; afterwards only the used positions are reset
     for (int i = tid; i < P.hash_size; i += AS_THREADS) W.hkey[i] = KEY_EMPTY;
@@ -397,7 +407,7 @@ k_hybrid_astar(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen, 
                 TICK(PH_RS_SELECT);
                 const int m = S.rs_n;
                 const double stepn = xmul(P.res, P.maxc);
-                const double cq = cos(-q0[2]), sq = sin(-q0[2]);
+                const double cq = m_cos(-q0[2]), sq = m_sin(-q0[2]);
                 // sampling plans of the first AS_MAX_PLANS words in pop order, one thread each
                 if (tid < m && tid < AS_MAX_PLANS) {
                     int c = S.rs_acc[S.rs_order[tid]];
@@ -488,7 +498,7 @@ k_hybrid_astar(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen, 
             TICK(PH_ARRIVE);
             const int n = S.nsteps, np1 = n + 1;
             const int total = P.n_prims * np1;
-            // phase A: per (p, i) displacement terms  (res*cos(yaws[i]))*dir, i = 0..n
+            // phase A: per (p, i) displacement terms  (res*m_cos(yaws[i]))*dir, i = 0..n
             for (int idx = tid; idx < total; idx += AS_THREADS) {
                 const int p = idx / np1, i = idx - p * np1;
                 const double ys = P.yaw_step[p];
@@ -497,8 +507,8 @@ k_hybrid_astar(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen, 
                 const double delta = xsub(stop, init_yaw);
                 const double step = xdiv(delta, (double)(n + 1));
                 const double yw = rollout_yaw(init_yaw, stop, step, delta, n + 1, i);
-                S.tx[p][i] = xmul(xmul(P.res, cos(yw)), P.dir[p]);
-                S.ty[p][i] = xmul(xmul(P.res, sin(yw)), P.dir[p]);
+                S.tx[p][i] = xmul(xmul(P.res, m_cos(yw)), P.dir[p]);
+                S.ty[p][i] = xmul(xmul(P.res, m_sin(yw)), P.dir[p]);
                 S.pyaw[p][i] = rollout_yaw(init_yaw, stop, step, delta, n + 1, i + 1);
             }
             __syncthreads();
@@ -648,8 +658,8 @@ k_hybrid_astar(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen, 
                 double ax = 0.0, ay = 0.0;
                 for (int i = 0; i <= n; ++i) {
                     const double yw = rollout_yaw(init_yaw, stop, step, delta, n + 1, i);
-                    const double txv = xmul(xmul(P.res, cos(yw)), P.dir[p]);
-                    const double tyv = xmul(xmul(P.res, sin(yw)), P.dir[p]);
+                    const double txv = xmul(xmul(P.res, m_cos(yw)), P.dir[p]);
+                    const double tyv = xmul(xmul(P.res, m_sin(yw)), P.dir[p]);
                     ax = (i == 0) ? txv : xadd(ax, txv);
                     ay = (i == 0) ? tyv : xadd(ay, tyv);
                     path_x[off + i] = xadd(W.nx[par], ax);
@@ -662,7 +672,7 @@ k_hybrid_astar(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen, 
             if (S.arrival == 1) {
                 const RsPlan& plan = (S.rs_pick < AS_MAX_PLANS) ? S.plans[S.rs_pick] : S.plan_tmp;
                 const double q0[3] = {S.cx, S.cy, S.cyaw};
-                const double cq = cos(-q0[2]), sq = sin(-q0[2]);
+                const double cq = m_cos(-q0[2]), sq = m_sin(-q0[2]);
                 const long long off = S.path_off + (S.path_len - plan.npts);
                 for (int j = tid; j < plan.npts; j += AS_THREADS) {
                     double lx, ly, lyaw, wx, wy, wyaw;
@@ -725,7 +735,7 @@ static int astar_grid(const hl_ctx* ctx, int n_scen, size_t smem) {
     return (int)(g < n_scen ? g : n_scen);
 }
 
-static size_t astar_smem() { return ((sizeof(AsSmem) + 15) & ~(size_t)15) + 2048 * sizeof(float); }
+static size_t astar_smem() { return ((sizeof(AsSmem) + 15) & ~(size_t)15) + AS_ENV_FLOATS * sizeof(float); }
 
 extern "C" int hl_astar_phase_cycles(hl_ctx* ctx, uint64_t* h_out, int32_t n, int32_t reset) {
     if (!ctx || !h_out || n < 1 || n > AS_N_PHASES) { hl_set_error("hl_astar_phase_cycles: bad arguments"); return 1; }

@@ -79,17 +79,32 @@ void hl_set_error(const char* fmt, ...);
 
 // ------------------------------------------------------------------ device math
 #ifdef __CUDACC__
+// HL_CODE: helpers are force-inlined by default (K1/K2 want that); a translation unit that defines
+// HL_SHARED_CODE gets them out-of-line instead (one copy, instruction-cache friendly).
+#ifdef HL_SHARED_CODE
+#define HL_CODE __noinline__
+#else
+#define HL_CODE __forceinline__
+#endif
+static __device__ HL_CODE double m_sin(double x) { return sin(x); }
+static __device__ HL_CODE double m_cos(double x) { return cos(x); }
+static __device__ HL_CODE double m_tan(double x) { return tan(x); }
+static __device__ HL_CODE double m_atan2(double y, double x) { return atan2(y, x); }
+static __device__ HL_CODE double m_asin(double x) { return asin(x); }
+static __device__ HL_CODE double m_acos(double x) { return acos(x); }
+static __device__ HL_CODE double m_fmod(double a, double b) { return fmod(a, b); }
+static __device__ HL_CODE void m_sincos(double x, double* s, double* c) { sincos(x, s, c); }
 // float64 arithmetic that must not be contracted into FMAs: the oracle evaluates
 // the same expressions with one rounding per operation.
 __device__ __forceinline__ double xmul(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double xadd(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double xsub(double a, double b) { return __dadd_rn(a, -b); }
-__device__ __forceinline__ double xdiv(double a, double b) { return __ddiv_rn(a, b); }
+static __device__ HL_CODE double xdiv(double a, double b) { return __ddiv_rn(a, b); }
 
 // Python / numpy floored modulo for a positive modulus (CPython float_rem,
 // numpy npy_divmod): fmod, then shift negative remainders up.
-__device__ __forceinline__ double py_mod_pos(double a, double m) {
-    double r = fmod(a, m);           // exact in CUDA
+static __device__ HL_CODE double py_mod_pos(double a, double m) {
+    double r = m_fmod(a, m);         // exact in CUDA
     if (r != 0.0) {
         if (r < 0.0) r = xadd(r, m);
     } else {
@@ -122,7 +137,7 @@ __device__ __forceinline__ double rs_pi_2_pi(double t) {
 // handling needed: |x|,|y| are metres or unit-circle offsets).  glibc >= 2.35's
 // hypot is correctly rounded, CUDA's is 1-2 ulp; this one follows Borges'
 // "fused" algorithm: h = sqrt(x^2+y^2) with an FMA-computed residual correction.
-__device__ __forceinline__ double hypot_cr(double x, double y) {
+static __device__ HL_CODE double hypot_cr(double x, double y) {
     double ax = fabs(x), ay = fabs(y);
     if (ax < ay) { double t = ax; ax = ay; ay = t; }
     if (ay == 0.0) return ax;

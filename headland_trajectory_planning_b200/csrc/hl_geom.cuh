@@ -13,13 +13,13 @@
 enum { HL_FREE = 0, HL_HIT = 1, HL_AMBIG = 2 };
 
 #define HL_LANE_R 6.0
-// 6*cos(pi/64): radius of the circle inscribed in the 16-segments-per-quadrant cap
+// 6*m_cos(pi/64): radius of the circle inscribed in the 16-segments-per-quadrant cap
 #define HL_LANE_RIN 5.992771509254837
 #define HL_BAND_IN (HL_LANE_RIN - 1e-6)
 #define HL_BAND_OUT (HL_LANE_R + 1e-6)
 
 struct Pose64 {
-    double x, y, c, s;     // c, s = cos/sin(yaw) in float64
+    double x, y, c, s;     // c, s = cos/m_sin(yaw) in float64
 };
 
 // ------------------------------------------------------------------- float64
@@ -250,9 +250,9 @@ struct EnvSmem {
 // Membership of a point in capsule POLYGON i (float32).  The polygon is the true capsule of radius 6
 // except in the two round caps, where it is the 32-chord fan with vertices at angle_normal + k*pi/32
 // (geometry_host.capsule_polygon): a cap point at range rho and angular offset delta from the nearest
-// chord midpoint is inside iff rho*cos(delta) <= 6*cos(pi/64).  Returns 1 inside, 0 outside, 2 when
+// chord midpoint is inside iff rho*m_cos(delta) <= 6*m_cos(pi/64).  Returns 1 inside, 0 outside, 2 when
 // the margin is within the float32 band.
-__device__ __forceinline__ int corner_in_capsule(const float* sg, float wx, float wy, float eps) {
+static __device__ HL_CODE int corner_in_capsule(const float* sg, float wx, float wy, float eps) {
     const float ex = sg[2] - sg[0], ey = sg[3] - sg[1];
     const float len2 = fmaf(ex, ex, ey * ey);
     const float qx = wx - sg[0], qy = wy - sg[1];
@@ -272,7 +272,7 @@ __device__ __forceinline__ int corner_in_capsule(const float* sg, float wx, floa
         const float step = 0.09817477042468103f;                // pi/32
         const float k = floorf(q / step);
         const float delta = fabsf(q - (k + 0.5f) * step);
-        g = g * cosf(delta) * 1.0012061467251643f;              // / cos(pi/64)
+        g = g * cosf(delta) * 1.0012061467251643f;              // / m_cos(pi/64)
     }
     if (g <= (float)HL_LANE_R - eps) return 1;
     if (g > (float)HL_LANE_R + eps) return 0;
@@ -292,7 +292,7 @@ __device__ __forceinline__ int corner_in_capsule(const float* sg, float wx, floa
 //     crossing parity of C decides inside/outside when every edge is clear;
 //   * lane: one centre-to-segment distance accepts / rejects against (r_in - rho) / (r_out + rho)
 //     before the four corner distances are needed.
-__device__ __forceinline__ int filter_part(const EnvSmem& E, float px, float py, float c, float s,
+static __device__ HL_CODE int filter_part(const EnvSmem& E, float px, float py, float c, float s,
                                            const float* ext, unsigned flags, unsigned* which_ambig) {
     const float eps = E.eps;
     const float hx = 0.5f * (ext[1] - ext[0]), hy = 0.5f * (ext[3] - ext[2]);
@@ -506,7 +506,7 @@ static __device__ bool pose_infeasible(const EnvBatchDev& eb, const EnvDesc& D, 
     Pose64 p;
     bool have64 = false;
     if (r == HL_AMBIG) {
-        p.x = x; p.y = y; p.c = cos(yaw); p.s = sin(yaw);
+        p.x = x; p.y = y; p.c = m_cos(yaw); p.s = m_sin(yaw);
         have64 = true;
         if (n_exact) atomicAdd(n_exact, 1ULL);
         bad = exact_part_check(p, D.body_ext, eb, D, amb);
@@ -523,7 +523,7 @@ static __device__ bool pose_infeasible(const EnvBatchDev& eb, const EnvDesc& D, 
             int r2 = far ? HL_AMBIG : filter_part(E, px, py, cf, sf, ext32, aflags, &amb2);
             if (r2 == HL_HIT) return true;
             if (r2 == HL_AMBIG) {
-                if (!have64) { p.x = x; p.y = y; p.c = cos(yaw); p.s = sin(yaw); have64 = true; }
+                if (!have64) { p.x = x; p.y = y; p.c = m_cos(yaw); p.s = m_sin(yaw); have64 = true; }
                 if (n_exact) atomicAdd(n_exact, 1ULL);
                 if (exact_part_check(p, ext64, eb, D, amb2)) return true;
             }

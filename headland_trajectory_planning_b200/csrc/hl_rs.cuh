@@ -7,6 +7,11 @@
 // the reference's operation order, because they feed discrete decisions.
 #pragma once
 #include "hl_common.cuh"
+#ifdef HL_SHARED_CODE
+#define HL_CODE2 __noinline__
+#else
+#define HL_CODE2
+#endif
 
 enum { RS_SLS = 0, RS_LSL, RS_LSR, RS_LRL, RS_LRLRN, RS_LRLRP, RS_LRSR, RS_LRSL, RS_LRSLR };
 enum { RP_TUV = 0, RP_VUT, RP_TUnUV, RP_TUUV, RP_THUV, RP_VUHT, RP_THUHV };
@@ -45,21 +50,21 @@ __device__ __forceinline__ int rs_letter(unsigned short letters, int i) { return
 // as separate Python float operations use xmul/xadd so no FMA is formed.
 __device__ __forceinline__ void rs_polar(double x, double y, double& r, double& th) {
     r = hypot_cr(x, y);
-    th = atan2(y, x);
+    th = m_atan2(y, x);
 }
 
 // sphi, cphi = sine and cosine of the (already mirrored) phi: sin is odd and cos even bit-for-bit,
 // so the caller derives them from one sincos per pose pair.
-static __device__ bool rs_solve(int solver, double x, double y, double phi, double sphi, double cphi,
+static __device__ HL_CODE2 bool rs_solve(int solver, double x, double y, double phi, double sphi, double cphi,
                                 double& t, double& u, double& v) {
     const double PI = HL_PI;
     switch (solver) {
     case RS_SLS: {                                              // reeds_shepp.py:144-160
         phi = rs_mod2pi(phi);
         if ((y > 0.0 || y < 0.0) && 0.0 < phi && phi < xmul(PI, 0.99)) {
-            double tn = tan(phi);
+            double tn = m_tan(phi);
             double xd = xadd(xdiv(-y, tn), x);
-            double th = tan(xdiv(phi, 2.0));
+            double th = m_tan(xdiv(phi, 2.0));
             t = xsub(xd, th);
             u = phi;
             double dx = xsub(x, xd);
@@ -85,7 +90,7 @@ static __device__ bool rs_solve(int solver, double x, double y, double phi, doub
         u1 = xmul(u1, u1);
         if (u1 >= 4.0) {
             u = sqrt(xsub(u1, 4.0));
-            double theta = atan2(2.0, u);
+            double theta = m_atan2(2.0, u);
             t = rs_mod2pi(xadd(t1, theta));
             v = rs_mod2pi(xsub(t, phi));
             if (t >= 0.0 && v >= 0.0) return true;
@@ -96,7 +101,7 @@ static __device__ bool rs_solve(int solver, double x, double y, double phi, doub
         double u1, t1;
         rs_polar(xsub(x, sphi), xadd(xsub(y, 1.0), cphi), u1, t1);
         if (u1 <= 4.0) {
-            u = xmul(-2.0, asin(xmul(0.25, u1)));
+            u = xmul(-2.0, m_asin(xmul(0.25, u1)));
             t = rs_mod2pi(xadd(xadd(t1, xmul(0.5, u)), PI));
             v = rs_mod2pi(xadd(xsub(phi, t), u));
             if (t >= 0.0 && u <= 0.0) return true;
@@ -111,21 +116,21 @@ static __device__ bool rs_solve(int solver, double x, double y, double phi, doub
         if (solver == RS_LRLRN) {
             double rho = xmul(0.25, xadd(2.0, sqrt(xadd(xmul(xi, xi), xmul(eta, eta)))));
             if (!(rho <= 1.0)) return false;
-            uu = acos(rho);
+            uu = m_acos(rho);
             vv = -uu;
         } else {
             double rho = xdiv(xsub(xsub(20.0, xmul(xi, xi)), xmul(eta, eta)), 16.0);
             if (!(0.0 <= rho && rho <= 1.0)) return false;
-            uu = -acos(rho);
+            uu = -m_acos(rho);
             if (!(uu >= xmul(-0.5, PI))) return false;
             vv = uu;
         }
         // calc_tauOmega(u, v, xi, eta, phi)
         double delta = rs_mod2pi(xsub(uu, vv));
-        double A = xsub(sin(uu), sin(delta));
-        double B = xsub(xsub(cos(uu), cos(delta)), 1.0);
-        double t1 = atan2(xsub(xmul(eta, A), xmul(xi, B)), xadd(xmul(xi, A), xmul(eta, B)));
-        double t2 = xadd(xmul(2.0, xsub(xsub(cos(delta), cos(vv)), cos(uu))), 3.0);
+        double A = xsub(m_sin(uu), m_sin(delta));
+        double B = xsub(xsub(m_cos(uu), m_cos(delta)), 1.0);
+        double t1 = m_atan2(xsub(xmul(eta, A), xmul(xi, B)), xadd(xmul(xi, A), xmul(eta, B)));
+        double t2 = xadd(xmul(2.0, xsub(xsub(m_cos(delta), m_cos(vv)), m_cos(uu))), 3.0);
         double tau = (t2 < 0) ? rs_mod2pi(xadd(t1, PI)) : rs_mod2pi(t1);
         double omega = rs_mod2pi(xsub(xadd(xsub(tau, uu), vv), phi));
         t = tau; u = uu; v = omega;
@@ -153,7 +158,7 @@ static __device__ bool rs_solve(int solver, double x, double y, double phi, doub
         if (rho >= 2.0) {
             double r = sqrt(xsub(xmul(rho, rho), 4.0));
             u = xsub(2.0, r);
-            t = rs_mod2pi(xadd(theta, atan2(r, -2.0)));
+            t = rs_mod2pi(xadd(theta, m_atan2(r, -2.0)));
             v = rs_mod2pi(xsub(xsub(phi, xmul(0.5, PI)), t));
             if (t >= 0.0 && u <= 0.0 && v <= 0.0) return true;
         }
@@ -169,7 +174,7 @@ static __device__ bool rs_solve(int solver, double x, double y, double phi, doub
             if (u <= 0.0) {
                 double num = xsub(xmul(xsub(4.0, u), xi), xmul(2.0, eta));
                 double den = xadd(xmul(-2.0, xi), xmul(xsub(u, 4.0), eta));
-                t = rs_mod2pi(atan2(num, den));
+                t = rs_mod2pi(m_atan2(num, den));
                 v = rs_mod2pi(xsub(t, phi));
                 if (t >= 0.0 && v >= 0.0) return true;
             }
@@ -182,14 +187,14 @@ static __device__ bool rs_solve(int solver, double x, double y, double phi, doub
 // Normalised problem of one pose pair (generate_path, :565-572)
 struct RsProblem { double x, y, phi, xb, yb, sp, cp; };
 
-__device__ __forceinline__ RsProblem rs_normalise(const double* q0, const double* q1, double maxc) {
+static __device__ HL_CODE RsProblem rs_normalise(const double* q0, const double* q1, double maxc) {
     RsProblem P;
     double dx = xsub(q1[0], q0[0]), dy = xsub(q1[1], q0[1]);
     P.phi = xsub(q1[2], q0[2]);
-    double c = cos(q0[2]), s = sin(q0[2]);
+    double c = m_cos(q0[2]), s = m_sin(q0[2]);
     P.x = xmul(xadd(xmul(c, dx), xmul(s, dy)), maxc);
     P.y = xmul(xadd(xmul(-s, dx), xmul(c, dy)), maxc);
-    double cp = cos(P.phi), sp = sin(P.phi);                    // :217-218 / :387-388
+    double cp = m_cos(P.phi), sp = m_sin(P.phi);                    // :217-218 / :387-388
     P.sp = sp; P.cp = cp;
     P.xb = xadd(xmul(P.x, cp), xmul(P.y, sp));
     P.yb = xsub(xmul(P.x, sp), xmul(P.y, cp));
@@ -197,7 +202,7 @@ __device__ __forceinline__ RsProblem rs_normalise(const double* q0, const double
 }
 
 // Evaluate candidate row `cand`: returns validity, writes nseg normalised lengths.
-static __device__ bool rs_candidate(int cand, const RsProblem& P, double* lens) {
+static __device__ HL_CODE2 bool rs_candidate(int cand, const RsProblem& P, double* lens) {
     const RsRow row = c_rs_rows[cand];
     double ax = row.backwards ? P.xb : P.x, ay = row.backwards ? P.yb : P.y;
     if (row.neg_x) ax = -ax;
@@ -240,7 +245,7 @@ static __constant__ signed char c_rs_groups[RS_N_GROUPS][4] = {
     {42, 43, -1, -1}, {44, 45, -1, -1},                     // LRSLR, RLSRL
 };
 
-static __device__ void rs_select_group(int g, const unsigned char* valid, const double (*lens)[HL_RS_MAX_SEGS],
+static __device__ HL_CODE2 void rs_select_group(int g, const unsigned char* valid, const double (*lens)[HL_RS_MAX_SEGS],
                                        unsigned char* accept, double* Lc) {
     int kept[4];
     int nk = 0;
@@ -268,7 +273,7 @@ static __device__ void rs_select_group(int g, const unsigned char* valid, const 
 }
 
 // accepted rows in evaluation order; returns their number or -1 when the assert would fire
-static __device__ int rs_select_compact(const unsigned char* accept, const double* Lc, int* acc, double* L) {
+static __device__ HL_CODE2 int rs_select_compact(const unsigned char* accept, const double* Lc, int* acc, double* L) {
     int n = 0;
     for (int c = 0; c < HL_RS_CANDIDATES; ++c) {
         if (accept[c] == 2) return -1;
@@ -287,7 +292,7 @@ static __device__ int rs_select(const unsigned char* valid, const double (*lens)
 // calculate_reeds_shepp_path_cost (hybrid_a_star_search.py:129-160) with the quirks:
 // +DIRECTION_CHANGE_COST and +MAX_STEER always (len(np.where(..)) == 1); 'L' arcs steer 0.
 // Lengths here may be normalised or metric: only signs matter.
-static __device__ double rs_path_cost(double node_cost, int cand, const double* lens, double max_steer,
+static __device__ HL_CODE2 double rs_path_cost(double node_cost, int cand, const double* lens, double max_steer,
                                double reverse_cost, double dir_change_cost, double steer_cost) {
     const RsRow row = c_rs_rows[cand];
     int nneg = 0;
@@ -307,7 +312,7 @@ static __device__ double rs_path_cost(double node_cost, int cand, const double* 
 
 // heapdict pop order of n entries inserted in index order with the given priorities
 // (hybrid_a_star_search.py:265-271).  order[] receives the indices in pop order.
-static __device__ void heapdict_order(const double* prio, int n, int* order) {
+static __device__ HL_CODE2 void heapdict_order(const double* prio, int n, int* order) {
     int heap[HL_RS_CANDIDATES];
     int m = 0;
     for (int k = 0; k < n; ++k) {                 // __setitem__: append + _decrease_key
@@ -354,17 +359,17 @@ struct RsPlan {
     int dir0;
 };
 
-__device__ __forceinline__ void rs_interp(double l, int letter, double maxc, double ox, double oy, double oyaw,
+static __device__ HL_CODE void rs_interp(double l, int letter, double maxc, double ox, double oy, double oyaw,
                                           double& px, double& py, double& pyaw) {
     if (letter == RS_S) {
         double lm = xdiv(l, maxc);
-        px = xadd(ox, xmul(lm, cos(oyaw)));
-        py = xadd(oy, xmul(lm, sin(oyaw)));
+        px = xadd(ox, xmul(lm, m_cos(oyaw)));
+        py = xadd(oy, xmul(lm, m_sin(oyaw)));
         pyaw = oyaw;
     } else {
-        double ldx = xdiv(sin(l), maxc);
-        double ldy = (letter == RS_L) ? xdiv(xsub(1.0, cos(l)), maxc) : xdiv(xsub(1.0, cos(l)), -maxc);
-        double cn = cos(-oyaw), sn = sin(-oyaw);
+        double ldx = xdiv(m_sin(l), maxc);
+        double ldy = (letter == RS_L) ? xdiv(xsub(1.0, m_cos(l)), maxc) : xdiv(xsub(1.0, m_cos(l)), -maxc);
+        double cn = m_cos(-oyaw), sn = m_sin(-oyaw);
         double gdx = xadd(xmul(cn, ldx), xmul(sn, ldy));
         double gdy = xadd(xmul(-sn, ldx), xmul(cn, ldy));
         px = xadd(ox, gdx);
@@ -376,7 +381,7 @@ __device__ __forceinline__ void rs_interp(double l, int letter, double maxc, dou
 // Build the per-segment plan of one word.  `lens` normalised, step = step_size*maxc.
 // The loop offsets are accumulated by repeated addition exactly like the reference, so
 // the sample count is bit-exact.
-static __device__ void rs_make_plan(int cand, const double* lens, double maxc, double step, RsPlan& P) {
+static __device__ HL_CODE2 void rs_make_plan(int cand, const double* lens, double maxc, double step, RsPlan& P) {
     const RsRow row = c_rs_rows[cand];
     P.nseg = row.nseg;
     P.dir0 = (lens[0] > 0.0) ? 1 : -1;
@@ -443,7 +448,7 @@ static __device__ void rs_make_plan(int cand, const double* lens, double maxc, d
 
 // Pose j (0 <= j < npts) of a planned word in the LOCAL frame, plus curvature sign and
 // direction tag.  Loop offsets use pd0 + k*d (differs from the repeated sum by <1e-12).
-static __device__ void rs_sample_local(const RsPlan& P, int j, double maxc, double& px, double& py, double& pyaw,
+static __device__ HL_CODE2 void rs_sample_local(const RsPlan& P, int j, double maxc, double& px, double& py, double& pyaw,
                                 int& cs_sign, int& dir) {
     if (j == 0) { px = 0.0; py = 0.0; pyaw = 0.0; cs_sign = 0; dir = P.dir0; return; }
     int si = P.nseg - 1;
@@ -458,7 +463,7 @@ static __device__ void rs_sample_local(const RsPlan& P, int j, double maxc, doub
 
 // float32 view of a plan for the collision filter: per segment the world position of its origin
 // relative to the environment origin and cos/sin of the world heading there.  One call per word.
-static __device__ void rs_plan_world32(RsPlan& P, const double* q0, double cq, double sq, const double* env_origin) {
+static __device__ HL_CODE2 void rs_plan_world32(RsPlan& P, const double* q0, double cq, double sq, const double* env_origin) {
     for (int i = 0; i < P.nseg; ++i) {
         RsSegPlan& S = P.seg[i];
         double wx = xadd(xadd(xmul(cq, S.ox), xmul(sq, S.oy)), q0[0]);
@@ -466,13 +471,13 @@ static __device__ void rs_plan_world32(RsPlan& P, const double* q0, double cq, d
         S.fox = (float)(wx - env_origin[0]);
         S.foy = (float)(wy - env_origin[1]);
         double sn, cs;
-        sincos(S.oyaw + q0[2], &sn, &cs);
+        m_sincos(S.oyaw + q0[2], &sn, &cs);
         S.fc0 = (float)cs; S.fs0 = (float)sn;
     }
 }
 
 // Pose j in the environment's float32 frame: position and cos/sin of the world yaw (1 sincosf).
-__device__ __forceinline__ void rs_sample_world32(const RsPlan& P, int j, float inv_maxc, float& wx, float& wy,
+static __device__ HL_CODE void rs_sample_world32(const RsPlan& P, int j, float inv_maxc, float& wx, float& wy,
                                                   float& c, float& s) {
     int si = P.nseg - 1;
     while (si > 0 && j < P.seg[si].first) --si;
@@ -498,9 +503,9 @@ __device__ __forceinline__ void rs_sample_world32(const RsPlan& P, int j, float 
 }
 
 // Local -> world (calc_all_paths, :50-59)
-__device__ __forceinline__ void rs_to_world(const double* q0, double cq, double sq, double lx, double ly, double lyaw,
+static __device__ HL_CODE void rs_to_world(const double* q0, double cq, double sq, double lx, double ly, double lyaw,
                                             double& wx, double& wy, double& wyaw) {
-    // cq = cos(-q0yaw), sq = sin(-q0yaw)
+    // cq = m_cos(-q0yaw), sq = m_sin(-q0yaw)
     wx = xadd(xadd(xmul(cq, lx), xmul(sq, ly)), q0[0]);
     wy = xadd(xadd(xmul(-sq, lx), xmul(cq, ly)), q0[1]);
     wyaw = rs_pi_2_pi(xadd(lyaw, q0[2]));

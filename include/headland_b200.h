@@ -31,7 +31,7 @@ extern "C" {
 
 /* ---- limits (compile-time capacities of the kernels) ---------------------- */
 #define HL_MAX_PRIMS        16   /* motion primitives per expansion (King: 14, Pawn: 8) */
-#define HL_MAX_ROLLOUT      32   /* poses of one primitive rollout (round(L/res)+1)      */
+#define HL_MAX_ROLLOUT      16   /* poses of one primitive rollout (round(L/res)+1)      */
 #define HL_CAPSULE_VERTS    66   /* GEOS round-cap buffer of a 2-point line, quad_segs=16 */
 #define HL_RS_CANDIDATES    46   /* Reeds-Shepp candidate words, reeds_shepp.py:565-582   */
 #define HL_RS_MAX_SEGS       5
