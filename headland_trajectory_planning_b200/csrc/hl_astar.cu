@@ -1,207 +1,52 @@
-// hl_astar.cu -- K4: batched Hybrid A* warm-start search, one CTA per scenario.
+// hl_astar.cu -- K4: batched Hybrid A* warm-start search, ONE WARP PER SCENARIO, phase-aligned CTAs.
 //
 // Replaces HybridAStarSearch.hybrid_a_star_search (path_planner/hybrid_a_star_search.py:497-607,
-// King mode): every popped node first gets a Reeds-Shepp analytic shot over all words
-// (:232-287), then the 14 motion primitives are rolled out (:357-410), collision-checked
-// against obstacles + field polygon + guide lane (:412-427), costed (:306-329) and merged
-// into the open list (:580-596).  The pop->expand->push chain of ONE scenario is sequential;
-// the parallelism is (a) scenarios across CTAs (persistent CTAs pull scenario ids from an
-// atomic counter), (b) inside an expansion: 46 word solvers, the poses of a word, the
-// 14 x (n+1) primitive poses, the guide-point argmin.
+// King mode).  Shared pieces (workspace, keys, hash, heapdict replay, filter, heuristic) are in
+// hl_astar_common.cuh; the float64/float32 split is described there and in DESIGN.md.
 //
-// Exactness: everything that feeds a discrete decision (rollout, grid keys, g-cost,
-// heuristic, priorities, word validity/dedup/cost, heap order, sample counts) is float64 in
-// the reference's operation order; the open list replays heapdict's tie behaviour
-// (oracle/heapdict_port.py).  Footprint tests go through the float32 filter first and
-// escalate to the float64 predicates only inside the error band, and only when no other
-// pose of the same path already decided it.
-// The search kernel runs many different phases on different warps/CTAs at once; with every helper
-// inlined its SASS was 460 KB and 73 % of the non-barrier stall samples were instruction-fetch misses
-// (profiles/r1b).  HL_SHARED_CODE makes the heavy helpers out-of-line so the kernel keeps one copy.
-#define HL_SHARED_CODE 1
-#include <cstring>
-#include "hl_geom.cuh"
-#include "hl_rs.cuh"
+// Why a warp and not a CTA per scenario: the first version (hl_astar_cta.cuh, kept for reference) gave a
+// scenario 128 threads.  Its profile (profiles/r1b_*) showed 52 % of warp samples waiting at CTA barriers
+// for the serial thread, and 73 % of the remaining stalls were INSTRUCTION-FETCH misses: one expansion walks
+// ~100 KB of straight-line float64 code exactly once, and four co-resident CTAs in four different phases
+// evict each other from the 32 KB instruction cache.  Here every scenario owns one warp (serial sections on
+// lane 0, parallel sections on 32 lanes, __syncwarp instead of __syncthreads), a CTA carries AW_WARPS
+// scenarios, and two CTA-wide alignment barriers per expansion keep all warps of the SM inside the same
+// code region, so an instruction line fetched once serves AW_WARPS scenarios.  Warps pull scenario ids from
+// an atomic counter as soon as theirs finishes.
+#include "hl_astar_common.cuh"
 
-#ifndef AS_THREADS
-#define AS_THREADS 128
+#ifndef AW_WARPS
+#define AW_WARPS 12
 #endif
-#ifndef AS_MIN_CTAS
-#define AS_MIN_CTAS 4
+#ifndef AW_LOCKSTEP
+#define AW_LOCKSTEP 1
 #endif
-#define AS_WARPS (AS_THREADS / 32)
-#define AS_MAX_PLANS 8
-#define AS_ROLL (HL_MAX_ROLLOUT + 1)
-#define AS_ENV_FLOATS 768       // staged float32 environment (canonical: 8x28 + 16x12 + 4x4 = 432 floats)
-#define KEY_EMPTY (-1LL)
-// phase timers (cycles of thread 0 between barriers), the device analogue of the reference's three
-// accumulating timers (hybrid_a_star_search.py:91-94): summed over scenarios into ctx->d_counters
-enum { PH_POP = 0, PH_RS_CAND, PH_RS_SELECT, PH_RS_PLAN, PH_RS_SAMPLE, PH_ARRIVE, PH_ROLLOUT, PH_FILTER, PH_EXACT,
-       PH_COST_HEUR, PH_MERGE, PH_SETUP, PH_OUTPUT, AS_N_PHASES };
-#define TICK(ph) do { if (tid == 0) { long long _n = clock64(); S.t_phase[ph] += _n - S.t_last; S.t_last = _n; } } while (0)
+#define AW_ENV_FLOATS 512
+#define AW_MAX_PLANS 6
+#define FULL 0xffffffffu
+enum { ST_IDLE = 0, ST_SEARCH = 1, ST_DONE = 2 };
 
-struct AsParams {
-    double res, yaw_res, maxc, max_steer, wheel_base;
-    int n_prims;
-    double steer[HL_MAX_PRIMS], dir[HL_MAX_PRIMS], yaw_step[HL_MAX_PRIMS], curv[HL_MAX_PRIMS], steer_eff[HL_MAX_PRIMS];
-    double steer_cost, delta_steer_cost, dir_change_cost, reverse_cost, hybrid_cost, min_len_goal;
-    int max_nodes, max_path_poses;
-    int cap_nodes, hash_size;
-};
-
-// per-CTA workspace in global memory (L2 resident while the scenario runs)
-struct AsWs {
-    double* nx; double* ny; double* nyaw; double* ng;
-    long long* nkey;
-    int* nparent; int* nheap; int* nhpos;
-    signed char* nprim; signed char* nsteps; signed char* nstate;
-    long long* hkey; int* hval;
-    double* hprio; int* hslot;
-    int* corder;
-};
-
-__host__ __device__ inline size_t as_align(size_t x) { return (x + 255) & ~(size_t)255; }
-
-__host__ __device__ inline size_t as_ws_bytes(int cap, int hsize, int max_nodes) {
-    size_t b = 0;
-    b += 4 * as_align(sizeof(double) * cap);           // nx ny nyaw ng
-    b += as_align(sizeof(long long) * cap);            // nkey
-    b += 3 * as_align(sizeof(int) * cap);              // nparent nheap nhpos
-    b += 3 * as_align(cap);                            // nprim nsteps nstate
-    b += as_align(sizeof(long long) * hsize) + as_align(sizeof(int) * hsize);
-    b += as_align(sizeof(double) * cap) + as_align(sizeof(int) * cap);
-    b += as_align(sizeof(int) * (max_nodes + 4));
-    return b;
-}
-
-__device__ inline AsWs as_carve(char* base, int cap, int hsize, int max_nodes) {
-    AsWs w;
-    char* p = base;
-    auto take = [&](size_t bytes) { char* r = p; p += as_align(bytes); return r; };
-    w.nx = (double*)take(sizeof(double) * cap); w.ny = (double*)take(sizeof(double) * cap);
-    w.nyaw = (double*)take(sizeof(double) * cap); w.ng = (double*)take(sizeof(double) * cap);
-    w.nkey = (long long*)take(sizeof(long long) * cap);
-    w.nparent = (int*)take(sizeof(int) * cap); w.nheap = (int*)take(sizeof(int) * cap);
-    w.nhpos = (int*)take(sizeof(int) * cap);
-    w.nprim = (signed char*)take(cap); w.nsteps = (signed char*)take(cap); w.nstate = (signed char*)take(cap);
-    w.hkey = (long long*)take(sizeof(long long) * hsize); w.hval = (int*)take(sizeof(int) * hsize);
-    w.hprio = (double*)take(sizeof(double) * cap); w.hslot = (int*)take(sizeof(int) * cap);
-    w.corder = (int*)take(sizeof(int) * (max_nodes + 4));
-    return w;
-}
-
-// ---- grid key (calculate_node_index, :82-89): Python round() = half-to-even = rint
-__device__ __forceinline__ bool make_key(double x, double y, double yaw, double res, double yaw_res,
-                                         int& ix, int& iy, int& iyaw, long long& key) {
-    double fx = rint(xdiv(x, res)), fy = rint(xdiv(y, res)), fw = rint(xdiv(yaw, yaw_res));
-    if (!(fabs(fx) < 8388607.0) || !(fabs(fy) < 8388607.0) || !(fabs(fw) < 127.0)) return false;
-    ix = (int)fx; iy = (int)fy; iyaw = (int)fw;
-    key = ((long long)(ix + 8388608) << 32) | ((long long)(iy + 8388608) << 8) | (long long)(iyaw + 128);
-    return true;
-}
-
-__device__ __forceinline__ void unpack_key(long long key, int& ix, int& iy, int& iyaw) {
-    ix = (int)(key >> 32) - 8388608;
-    iy = (int)((key >> 8) & 0xFFFFFF) - 8388608;
-    iyaw = (int)(key & 0xFF) - 128;
-}
-
-__device__ __forceinline__ unsigned hash_key(long long k) {
-    unsigned long long z = (unsigned long long)k * 0x9E3779B97F4A7C15ULL;
-    return (unsigned)(z >> 40);
-}
-
-// returns slot or -1; *pos = table position where the key is / would be inserted
-__device__ __noinline__ int hash_find(const AsWs& w, int hmask, long long key, int* pos) {
-    unsigned h = hash_key(key) & hmask;
-    while (true) {
-        long long k = w.hkey[h];
-        if (k == key) { *pos = (int)h; return w.hval[h]; }
-        if (k == KEY_EMPTY) { *pos = (int)h; return -1; }
-        h = (h + 1) & hmask;
-    }
-}
-
-// ---- heapdict replay (oracle/heapdict_port.py) on (hprio, hslot) with nheap[] positions
-__device__ __forceinline__ void heap_swap(const AsWs& w, int i, int j) {
-    double pi = w.hprio[i], pj = w.hprio[j];
-    int si = w.hslot[i], sj = w.hslot[j];
-    w.hprio[i] = pj; w.hslot[i] = sj; w.nheap[sj] = i;
-    w.hprio[j] = pi; w.hslot[j] = si; w.nheap[si] = j;
-}
-
-__device__ __noinline__ void heap_decrease_key(const AsWs& w, int i) {
-    while (i) {
-        int parent = (i - 1) >> 1;
-        if (w.hprio[parent] < w.hprio[i]) break;
-        heap_swap(w, i, parent);
-        i = parent;
-    }
-}
-
-__device__ __noinline__ int heap_popitem(const AsWs& w, int& n) {
-    int top = w.hslot[0];
-    --n;
-    if (n > 0) {
-        w.hprio[0] = w.hprio[n]; w.hslot[0] = w.hslot[n]; w.nheap[w.hslot[0]] = 0;
-        int i = 0;
-        while (true) {
-            int l = (i << 1) + 1, r = (i + 1) << 1, low = i;
-            if (l < n && w.hprio[l] < w.hprio[i]) low = l;
-            if (r < n && w.hprio[r] < w.hprio[low]) low = r;
-            if (low == i) break;
-            heap_swap(w, i, low);
-            i = low;
-        }
-    }
-    w.nheap[top] = -1;
-    return top;
-}
-
-__device__ __noinline__ void heap_set(const AsWs& w, int& n, int slot, double prio) {
-    if (w.nheap[slot] >= 0) {                      // __setitem__ on an existing key: pop(key) first
-        int i = w.nheap[slot];
-        while (i) {                                // __delitem__: bubble to the root unconditionally
-            int parent = (i - 1) >> 1;
-            heap_swap(w, i, parent);
-            i = parent;
-        }
-        heap_popitem(w, n);
-    }
-    int i = n++;
-    w.hprio[i] = prio; w.hslot[i] = slot; w.nheap[slot] = i;
-    heap_decrease_key(w, i);
-}
-
-struct AsSmem {
-    // scenario
+struct AwSmem {                          // one per warp
     double start[3], goal[3];
-    int env, scen;
     long long start_key, goal_key;
-    // search state (owned by thread 0)
+    int env, scen, state;
     int n_nodes, heap_n, counter, n_closed;
     int status, arrival, rs_word;
     double goal_cost;
-    // current node
     int cur; double cx, cy, cyaw, cg; int cprim; int nsteps;
-    int stop_flag;
     // Reeds-Shepp shot
     double rs_lens[HL_RS_CANDIDATES][HL_RS_MAX_SEGS];
-    double rs_L[HL_RS_CANDIDATES], rs_prio[HL_RS_CANDIDATES];
+    double rs_L[HL_RS_CANDIDATES], rs_prio[HL_RS_CANDIDATES], rs_Lc[HL_RS_CANDIDATES];
     int rs_acc[HL_RS_CANDIDATES], rs_order[HL_RS_CANDIDATES];
-    unsigned char rs_valid[HL_RS_CANDIDATES + 2];
-    unsigned char rs_accept[HL_RS_CANDIDATES + 2];
-    double rs_Lc[HL_RS_CANDIDATES];
+    unsigned char rs_valid[HL_RS_CANDIDATES + 2], rs_accept[HL_RS_CANDIDATES + 2];
     RsProblem rs_prob;
     int rs_n, rs_pick;
-    int vote[2][AS_WARPS];        // per-warp (hit | ambiguous << 1) bits of the current sample chunk
-    RsPlan plans[AS_MAX_PLANS];
+    RsPlan plans[AW_MAX_PLANS];
     RsPlan plan_tmp;
     // primitives
-    double tx[HL_MAX_PRIMS][AS_ROLL], ty[HL_MAX_PRIMS][AS_ROLL];    // terms, then positions
-    double pyaw[HL_MAX_PRIMS][AS_ROLL];                             // pose yaw (yaws[j+1])
+    double tx[HL_MAX_PRIMS][AS_ROLL], ty[HL_MAX_PRIMS][AS_ROLL], pyaw[HL_MAX_PRIMS][AS_ROLL];
     unsigned char pamb[HL_MAX_PRIMS][AS_ROLL];
-    int phit[HL_MAX_PRIMS], pany_amb[HL_MAX_PRIMS];
+    int phit[HL_MAX_PRIMS];
     double pg[HL_MAX_PRIMS], pprio[HL_MAX_PRIMS];
     long long pkey[HL_MAX_PRIMS];
     int pkey_ok[HL_MAX_PRIMS];
@@ -209,157 +54,246 @@ struct AsSmem {
     unsigned long long n_checks, n_exact;
     long long t_last, t_phase[AS_N_PHASES];
     // backtrack
-    int chain_len;
+    int chain_len, path_len;
     long long path_off;
-    int path_len;
+    __align__(16) float envf[AW_ENV_FLOATS];
 };
 
-// Ternary footprint status of one pose (body only): HL_FREE / HL_HIT / HL_AMBIG(+mask)
-__device__ HL_CODE int pose_filter(const EnvDesc& D, const EnvSmem& E, double x, double y, double yaw,
-                                           unsigned flags, unsigned* amb) {
-    float px = (float)(x - D.origin[0]), py = (float)(y - D.origin[1]);
-    if (fabsf(px) > E.reach || fabsf(py) > E.reach || !(fabs(yaw) < 1e6)) { *amb = flags; return HL_AMBIG; }
-    float sf, cf;
-    sincosf((float)yaw, &sf, &cf);
-    return filter_part(E, px, py, cf, sf, E.ext, flags, amb);
-}
+static_assert(sizeof(AwSmem) * AW_WARPS <= 227 * 1024, "per-CTA shared memory exceeds 227 KB");
+#undef TICK
+#define TICK(ph) do { if (lane == 0) { long long _n = clock64(); S.t_phase[ph] += _n - S.t_last; S.t_last = _n; } } while (0)
 
-__device__ __noinline__ bool pose_exact(const EnvBatchDev& eb, const EnvDesc& D, double x, double y, double yaw,
-                                           unsigned amb) {
-    Pose64 p;
-    p.x = x; p.y = y; p.c = m_cos(yaw); p.s = m_sin(yaw);
-    return exact_part_check(p, D.body_ext, eb, D, amb);
-}
-
-// calculate_state_cost (reference_line_heuristic.py:131-158) for one pose, one warp.
-__device__ __noinline__ double warp_state_cost(const EnvBatchDev& eb, const EnvDesc& D, double x, double y, double yaw, int lane) {
-    const double* gx = eb.guide_x + D.guide_off;
-    const double* gy = eb.guide_y + D.guide_off;
-    const int n = D.n_guide;
-    if (n <= 0) return 0.0;
-    // pass 1: minimum squared distance (ordering filter only)
-    double best = INFINITY;
-    for (int i = lane; i < n; i += 32) {
-        double dx = gx[i] - x, dy = gy[i] - y;
-        best = fmin(best, dx * dx + dy * dy);
+// float32 environment of this warp's scenario into its shared-memory slice (falls back to global pointers)
+__device__ __noinline__ void stage_env_warp(const EnvBatchDev& eb, const EnvDesc& D, float* sm, int cap_floats,
+                                            EnvSmem& E, int lane) {
+    const int n_o = D.n_obs * HL_OBS32_STRIDE, n_f = D.n_field * HL_FIELD32_STRIDE, n_s = D.n_seg * 4;
+    E.n_obs = D.n_obs; E.n_field = D.n_field; E.n_seg = D.n_seg; E.all_rect = D.all_rect;
+    E.eps = D.eps; E.reach = D.reach;
+    for (int k = 0; k < 4; ++k) E.ext[k] = (float)D.body_ext[k];
+    const float* g_obs = eb.obs32 + (size_t)HL_OBS32_STRIDE * D.obs_off;
+    const float* g_field = eb.field32 + HL_FIELD32_STRIDE * (size_t)D.field_off;
+    const float* g_seg = eb.seg32 + 4 * (size_t)D.seg_off;
+    if (n_o + n_f + n_s <= cap_floats) {
+        float* s_obs = sm;
+        float* s_field = s_obs + n_o;
+        float* s_seg = s_field + n_f;
+        for (int i = lane; i < n_o; i += 32) s_obs[i] = g_obs[i];
+        for (int i = lane; i < n_f; i += 32) s_field[i] = g_field[i];
+        for (int i = lane; i < n_s; i += 32) s_seg[i] = g_seg[i];
+        E.obs = s_obs; E.field = s_field; E.seg = s_seg;
+    } else {
+        E.obs = g_obs; E.field = g_field; E.seg = g_seg;
     }
-    for (int o = 16; o; o >>= 1) best = fmin(best, __shfl_xor_sync(0xffffffffu, best, o));
-    // pass 2: exact hypot on the near-minimal candidates, first minimum wins (np.argmin)
-    const double thr = best * (1.0 + 1e-9) + 1e-300;
-    double bh = INFINITY;
-    int bi = 0x7fffffff;
-    for (int i = lane; i < n; i += 32) {
-        double dx = xsub(gx[i], x), dy = xsub(gy[i], y);
-        if (dx * dx + dy * dy <= thr) {
-            double h = hypot_cr(dx, dy);
-            if (h < bh || (h == bh && i < bi)) { bh = h; bi = i; }
+    __syncwarp();
+}
+
+struct AwOut {
+    HlPlanResult* results;
+    int32_t* expanded_keys;
+    double* path_x; double* path_y; double* path_yaw; double* path_k;
+    int8_t* path_dir;
+    long long path_capacity;
+    unsigned long long* path_cursor;
+    unsigned long long* phase_cycles;
+};
+
+// Results of a finished scenario: expanded keys, path (get_path_from_expanded_nodes, :429-454), record.
+__device__ __noinline__ void finalize_scenario(AwSmem& S, const AsWs& W, const AsParams& P, const AwOut& O, int lane) {
+    const int sc = S.scen;
+    {
+        int32_t* ek = O.expanded_keys + (size_t)sc * (P.max_nodes + 2) * 3;
+        for (int i = lane; i < S.n_closed; i += 32) {
+            int ix, iy, iw;
+            unpack_key(W.nkey[W.corder[i]], ix, iy, iw);
+            ek[3 * i] = ix; ek[3 * i + 1] = iy; ek[3 * i + 2] = iw;
         }
     }
-    for (int o = 16; o; o >>= 1) {
-        double oh = __shfl_xor_sync(0xffffffffu, bh, o);
-        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (oh < bh || (oh == bh && oi < bi)) { bh = oh; bi = oi; }
+    if (lane == 0 && S.status == HL_STATUS_OK) {
+        // Walk cur -> parent -> ... -> start (slot 0 is the only node with the start key).  The chain is
+        // kept in hslot[] (the heap is dead once the search is over), goal side first.  closed_set[goal_key]
+        // is the goal node, so a goal in the start's own cell makes the reference's
+        // `while current_node_index != start_node_index` loop a no-op: empty path.
+        int len = 0, poses = 0, rs_pts = 0;
+        bool ok = true;
+        if (S.goal_key != S.start_key) {
+            for (int node = S.cur; node != 0; node = W.nparent[node]) {
+                if (len >= P.cap_nodes) { ok = false; break; }
+                W.hslot[len++] = node;
+                poses += W.nsteps[node] + 1;
+            }
+            if (S.arrival == 1) rs_pts = (S.rs_pick < AW_MAX_PLANS ? S.plans[S.rs_pick] : S.plan_tmp).npts;
+        }
+        S.chain_len = len;
+        S.path_len = poses + rs_pts;
+        if (!ok || S.path_len > P.max_path_poses) { S.status = HL_STATUS_CAPACITY; S.path_len = 0; }
+        else if (S.path_len > 0) {
+            unsigned long long off = atomicAdd(O.path_cursor, (unsigned long long)S.path_len);
+            if ((long long)(off + S.path_len) > O.path_capacity) { S.status = HL_STATUS_CAPACITY; S.path_len = 0; }
+            S.path_off = (long long)off;
+        }
     }
-    double dist = xmul(bh, 100.0);
-    double yaw_diff = fabs(angle_wrap(xsub(eb.guide_yaw[D.guide_off + bi], yaw)));
-    if (dist > 2.0) dist = 100.0;
-    double to_goal = xsub(eb.guide_s[D.guide_off + n - 1], eb.guide_s[D.guide_off + bi]);
-    return xadd(xadd(dist, xmul(yaw_diff, 0.2)), xmul(to_goal, 5.0));
+    __syncwarp();
+    if (S.status == HL_STATUS_OK && S.path_len > 0) {
+        const int len = S.chain_len;
+        for (int c = lane; c < len; c += 32) {
+            const int node = W.hslot[len - 1 - c];          // c-th node from the start side
+            long long off = S.path_off;
+            for (int q = 0; q < c; ++q) off += W.nsteps[W.hslot[len - 1 - q]] + 1;
+            const int par = W.nparent[node];
+            const int p = W.nprim[node], n = W.nsteps[node];
+            const double ys = P.yaw_step[p];
+            const double init_yaw = angle_wrap(xadd(W.nyaw[par], ys));
+            const double stop = xadd(init_yaw, xmul(ys, (double)(n + 1)));
+            const double delta = xsub(stop, init_yaw);
+            const double step = xdiv(delta, (double)(n + 1));
+            double ax = 0.0, ay = 0.0;
+            for (int i = 0; i <= n; ++i) {
+                const double yw = rollout_yaw(init_yaw, stop, step, delta, n + 1, i);
+                const double txv = xmul(xmul(P.res, m_cos(yw)), P.dir[p]);
+                const double tyv = xmul(xmul(P.res, m_sin(yw)), P.dir[p]);
+                ax = (i == 0) ? txv : xadd(ax, txv);
+                ay = (i == 0) ? tyv : xadd(ay, tyv);
+                O.path_x[off + i] = xadd(W.nx[par], ax);
+                O.path_y[off + i] = xadd(W.ny[par], ay);
+                O.path_yaw[off + i] = rollout_yaw(init_yaw, stop, step, delta, n + 1, i + 1);
+                O.path_k[off + i] = P.curv[p];
+                O.path_dir[off + i] = (int8_t)P.dir[p];
+            }
+        }
+        if (S.arrival == 1) {
+            const RsPlan& plan = (S.rs_pick < AW_MAX_PLANS) ? S.plans[S.rs_pick] : S.plan_tmp;
+            const double q0[3] = {S.cx, S.cy, S.cyaw};
+            const double cq = m_cos(-q0[2]), sq = m_sin(-q0[2]);
+            const long long off = S.path_off + (S.path_len - plan.npts);
+            for (int j = lane; j < plan.npts; j += 32) {
+                double lx, ly, lyaw, wx, wy, wyaw;
+                int cs, dir;
+                rs_sample_local(plan, j, P.maxc, lx, ly, lyaw, cs, dir);
+                rs_to_world(q0, cq, sq, lx, ly, lyaw, wx, wy, wyaw);
+                O.path_x[off + j] = wx; O.path_y[off + j] = wy; O.path_yaw[off + j] = wyaw;
+                O.path_k[off + j] = cs == 0 ? 0.0 : (cs > 0 ? P.maxc : -P.maxc);
+                O.path_dir[off + j] = (int8_t)dir;
+            }
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        HlPlanResult r;
+        r.status = S.status;
+        r.counter = (S.status == HL_STATUS_START_GOAL_BLOCKED) ? 0 : S.counter;
+        r.n_expanded = S.n_closed;
+        r.arrival = S.arrival;
+        r.path_len = S.path_len;
+        r.rs_word = S.rs_word;
+        r.path_offset = S.path_off;
+        r.goal_cost = S.goal_cost;
+        r.n_pose_checks = (long long)S.n_checks;
+        r.n_exact = (long long)S.n_exact;
+        long long _n = clock64();
+        S.t_phase[PH_OUTPUT] += _n - S.t_last;
+        long long tot = 0;
+        for (int k = 0; k < AS_N_PHASES; ++k) tot += S.t_phase[k];
+        r.cycles = tot;
+        O.results[sc] = r;
+        for (int k = 0; k < AS_N_PHASES; ++k) atomicAdd(O.phase_cycles + k, (unsigned long long)S.t_phase[k]);
+    }
+    // reset the used hash positions for the next scenario of this warp
+    for (int i = lane; i < S.n_nodes; i += 32) W.hkey[W.nhpos[i]] = KEY_EMPTY;
+    __syncwarp();
 }
 
-// One step of the kinematic rollout (kinematic_simulation_node, :366-390): yaws[i] of
-// np.linspace(init_yaw, init_yaw + yaw_step*(n+1), n+2) after angle_wrap.
-__device__ HL_CODE double rollout_yaw(double init_yaw, double stop, double step, double delta, int div, int i) {
-    double v;
-    if (i == div) v = stop;                                     // y[-1] = stop
-    else if (step != 0.0) v = xadd(xmul((double)i, step), init_yaw);
-    else v = xadd(xmul(xdiv((double)i, (double)div), delta), init_yaw);
-    return angle_wrap(v);
+// Start / goal feasibility (:76-80, :516-519), start node and its priority (:500-510).
+__device__ __noinline__ void setup_scenario(AwSmem& S, const AsWs& W, const AsParams& P, const EnvBatchDev& eb,
+                                            const EnvDesc& D, const EnvSmem& E, int hmask, unsigned FLAGS, int lane) {
+    int bad = 0;
+    if (lane < 2) {
+        const double* q = lane == 0 ? S.start : S.goal;
+        unsigned amb = FLAGS;
+        int r = pose_filter(D, E, q[0], q[1], q[2], FLAGS, &amb);
+        bad = (r == HL_HIT) || (r == HL_AMBIG && pose_exact(eb, D, q[0], q[1], q[2], amb));
+    }
+    bad = __any_sync(FULL, bad);
+    double h = warp_state_cost(eb, D, S.start[0], S.start[1], S.start[2], lane);
+    if (lane == 0) {
+        int ix, iy, iw;
+        long long sk = 0, gk = 0;
+        bool ok = make_key(S.start[0], S.start[1], S.start[2], P.res, P.yaw_res, ix, iy, iw, sk);
+        ok = make_key(S.goal[0], S.goal[1], S.goal[2], P.res, P.yaw_res, ix, iy, iw, gk) && ok;
+        S.start_key = sk; S.goal_key = gk;
+        if (!ok) S.status = HL_STATUS_CAPACITY;
+        else if (bad) S.status = HL_STATUS_START_GOAL_BLOCKED;
+        else {
+            W.nx[0] = S.start[0]; W.ny[0] = S.start[1]; W.nyaw[0] = S.start[2]; W.ng[0] = 0.0;
+            W.nkey[0] = sk; W.nparent[0] = 0; W.nprim[0] = -1; W.nsteps[0] = 0; W.nstate[0] = 0;
+            W.nheap[0] = -1;
+            int pos;
+            hash_find(W, hmask, sk, &pos);
+            W.hkey[pos] = sk; W.hval[pos] = 0; W.nhpos[0] = pos;
+            S.n_nodes = 1;
+            double prio = xmul(P.hybrid_cost, h);
+            prio = (prio > 0.0) ? prio : 0.0;           // max(start.cost = 0, 50*h)
+            heap_set(W, S.heap_n, 0, prio);
+        }
+    }
+    __syncwarp();
 }
 
-__global__ void __launch_bounds__(AS_THREADS, AS_MIN_CTAS)
-k_hybrid_astar(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen, AsParams P, char* ws_base,
-               size_t ws_stride, unsigned int* work_counter, HlPlanResult* __restrict__ results,
-               int32_t* __restrict__ expanded_keys, double* __restrict__ path_x, double* __restrict__ path_y,
-               double* __restrict__ path_yaw, double* __restrict__ path_k, int8_t* __restrict__ path_dir,
-               long long path_capacity, unsigned long long* path_cursor, unsigned long long* phase_cycles) {
+__global__ void __launch_bounds__(AW_WARPS * 32, 1)
+k_hybrid_astar_w(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen, AsParams P, char* ws_base,
+                 size_t ws_stride, unsigned int* work_counter, AwOut O) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    AsSmem& S = *reinterpret_cast<AsSmem*>(smem_raw);
-    float* env_sm = reinterpret_cast<float*>(smem_raw + ((sizeof(AsSmem) + 15) & ~(size_t)15));
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const AsWs W = as_carve(ws_base + (size_t)blockIdx.x * ws_stride, P.cap_nodes, P.hash_size, P.max_nodes);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    AwSmem& S = reinterpret_cast<AwSmem*>(smem_raw)[wid];
+    const AsWs W = as_carve(ws_base + ((size_t)blockIdx.x * AW_WARPS + wid) * ws_stride, P.cap_nodes, P.hash_size,
+                            P.max_nodes);
     const int hmask = P.hash_size - 1;
     const unsigned FLAGS = HL_CHECK_OBSTACLES | HL_CHECK_BOUNDARY | HL_CHECK_LANE;
-    const int env_sm_floats = AS_ENV_FLOATS;
 
     // hash table starts empty; afterwards only the used positions are reset
-    for (int i = tid; i < P.hash_size; i += AS_THREADS) W.hkey[i] = KEY_EMPTY;
-    __syncthreads();
+    for (int i = lane; i < P.hash_size; i += 32) W.hkey[i] = KEY_EMPTY;
+    if (lane == 0) S.state = ST_IDLE;
+    __syncwarp();
+
+    EnvSmem E;
+    E.n_obs = E.n_field = E.n_seg = E.all_rect = 0; E.eps = 0.f; E.reach = 0.f; E.obs = E.field = E.seg = nullptr;
+    const EnvDesc* Dp = eb.desc;
 
     while (true) {
-        if (tid == 0) S.scen = (int)atomicAdd(work_counter, 1u);
-        __syncthreads();
-        const int sc = S.scen;
-        if (sc >= n_scen) break;
-        if (tid == 0) {
-            const HlScenario s = scen[sc];
-            S.env = s.env_id;
-            for (int k = 0; k < 3; ++k) { S.start[k] = s.start[k]; S.goal[k] = s.goal[k]; }
-            S.n_nodes = 0; S.heap_n = 0; S.counter = 0; S.n_closed = 0;
-            S.status = -1; S.arrival = 0; S.rs_word = -1; S.goal_cost = 0.0;
-            S.n_checks = 0; S.n_exact = 0; S.path_len = 0; S.path_off = 0; S.stop_flag = 0;
-            for (int k = 0; k < AS_N_PHASES; ++k) S.t_phase[k] = 0;
-            S.t_last = clock64();
-        }
-        __syncthreads();
-        const EnvDesc& D = eb.desc[S.env];
-        EnvSmem E;
-        bool staged;
-        stage_env(eb, D, env_sm, env_sm_floats, E, staged);
-        __syncthreads();
-
-        // ---- start / goal feasibility (:76-80, :516-519) and start node (:500-510)
-        if (wid == 0) {
-            int bad = 0;
-            if (lane < 2) {
-                const double* q = lane == 0 ? S.start : S.goal;
-                unsigned amb = FLAGS;
-                int r = pose_filter(D, E, q[0], q[1], q[2], FLAGS, &amb);
-                bad = (r == HL_HIT) || (r == HL_AMBIG && pose_exact(eb, D, q[0], q[1], q[2], amb));
-            }
-            bad = __any_sync(0xffffffffu, bad);
-            double h = warp_state_cost(eb, D, S.start[0], S.start[1], S.start[2], lane);
+        // ---- refill: a warp without a scenario takes the next one from the global queue
+        while (S.state == ST_IDLE) {
+            int sc = 0;
+            if (lane == 0) sc = (int)atomicAdd(work_counter, 1u);
+            sc = __shfl_sync(FULL, sc, 0);
+            if (sc >= n_scen) { if (lane == 0) S.state = ST_DONE; __syncwarp(); break; }
             if (lane == 0) {
-                int ix, iy, iw;
-                long long sk = 0, gk = 0;
-                bool ok = make_key(S.start[0], S.start[1], S.start[2], P.res, P.yaw_res, ix, iy, iw, sk);
-                ok = make_key(S.goal[0], S.goal[1], S.goal[2], P.res, P.yaw_res, ix, iy, iw, gk) && ok;
-                S.start_key = sk; S.goal_key = gk;
-                if (!ok) S.status = HL_STATUS_CAPACITY;
-                else if (bad) S.status = HL_STATUS_START_GOAL_BLOCKED;
-                else {
-                    W.nx[0] = S.start[0]; W.ny[0] = S.start[1]; W.nyaw[0] = S.start[2]; W.ng[0] = 0.0;
-                    W.nkey[0] = sk; W.nparent[0] = 0; W.nprim[0] = -1; W.nsteps[0] = 0; W.nstate[0] = 0;
-                    W.nheap[0] = -1;
-                    int pos;
-                    hash_find(W, hmask, sk, &pos);
-                    W.hkey[pos] = sk; W.hval[pos] = 0; W.nhpos[0] = pos;
-                    S.n_nodes = 1;
-                    double prio = xmul(P.hybrid_cost, h);
-                    prio = (prio > 0.0) ? prio : 0.0;           // max(start.cost = 0, 50*h)
-                    heap_set(W, S.heap_n, 0, prio);
-                }
+                const HlScenario s = scen[sc];
+                S.scen = sc; S.env = s.env_id;
+                for (int k = 0; k < 3; ++k) { S.start[k] = s.start[k]; S.goal[k] = s.goal[k]; }
+                S.n_nodes = 0; S.heap_n = 0; S.counter = 0; S.n_closed = 0;
+                S.status = -1; S.arrival = 0; S.rs_word = -1; S.goal_cost = 0.0; S.rs_pick = -1;
+                S.n_checks = 0; S.n_exact = 0; S.path_len = 0; S.path_off = 0; S.chain_len = 0;
+                for (int k = 0; k < AS_N_PHASES; ++k) S.t_phase[k] = 0;
+                S.t_last = clock64();
             }
+            __syncwarp();
+            Dp = eb.desc + S.env;
+            stage_env_warp(eb, *Dp, S.envf, AW_ENV_FLOATS, E, lane);
+            setup_scenario(S, W, P, eb, *Dp, E, hmask, FLAGS, lane);
+            TICK(PH_SETUP);
+            if (S.status >= 0) finalize_scenario(S, W, P, O, lane);        // blocked / capacity: done already
+            else if (lane == 0) S.state = ST_SEARCH;
+            __syncwarp();
         }
-        __syncthreads();
-
-        TICK(PH_SETUP);
-        // =============================== main loop (:525-596) ===============================
-        // Control flow is decided ONLY by reads of S.status that directly follow a barrier, and thread 0
-        // never rewrites S.status between such a read and the next barrier -- otherwise a late warp could
-        // see the new value, leave the loop alone and desynchronise the CTA's barriers.
-        while (true) {
-            if (tid == 0 && S.status < 0) {
+#if AW_LOCKSTEP
+        if (__syncthreads_and(S.state == ST_DONE)) break;                   // alignment point 1
+#else
+        if (S.state == ST_DONE) break;
+#endif
+        const bool live = (S.state == ST_SEARCH);
+        const EnvDesc& D = *Dp;
+        if (live) {
+            // ---- pop (:526-545)
+            if (lane == 0) {
                 if (S.counter > P.max_nodes) S.status = HL_STATUS_MAX_NODES;
                 else {
                     S.counter += 1;
@@ -376,130 +310,126 @@ k_hybrid_astar(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen, 
                     }
                 }
             }
-            __syncthreads();
-            if (S.status >= 0) break;
+            __syncwarp();
             TICK(PH_POP);
-
+        }
+        if (live && S.status < 0) {
             // ---- analytic shot: 46 candidate words (:249-258)
-            {
-                const double q0[3] = {S.cx, S.cy, S.cyaw};
-                if (tid < HL_RS_CANDIDATES) {
-                    double l[HL_RS_MAX_SEGS] = {0, 0, 0, 0, 0};
-                    bool ok = rs_candidate(tid, S.rs_prob, l);
-                    S.rs_valid[tid] = ok ? 1 : 0;
-                    for (int k = 0; k < HL_RS_MAX_SEGS; ++k) S.rs_lens[tid][k] = l[k];
-                }
-                __syncthreads();
-                TICK(PH_RS_CAND);
-                if (tid < RS_N_GROUPS) rs_select_group(tid, S.rs_valid, S.rs_lens, S.rs_accept, S.rs_Lc);
-                __syncthreads();
-                if (tid == 0) {
-                    int m = rs_select_compact(S.rs_accept, S.rs_Lc, S.rs_acc, S.rs_L);
-                    if (m < 0) { S.status = HL_STATUS_RS_ASSERT; m = 0; }
-                    S.rs_n = m;
-                    for (int k = 0; k < m; ++k)
-                        S.rs_prio[k] = rs_path_cost(S.cg, S.rs_acc[k], S.rs_lens[S.rs_acc[k]], P.max_steer,
-                                                    P.reverse_cost, P.dir_change_cost, P.steer_cost);
-                    if (m > 0) heapdict_order(S.rs_prio, m, S.rs_order);
-                }
-                __syncthreads();
-                if (S.status >= 0) break;
-                TICK(PH_RS_SELECT);
-                const int m = S.rs_n;
-                const double stepn = xmul(P.res, P.maxc);
-                const double cq = m_cos(-q0[2]), sq = m_sin(-q0[2]);
-                // sampling plans of the first AS_MAX_PLANS words in pop order, one thread each
-                if (tid < m && tid < AS_MAX_PLANS) {
-                    int c = S.rs_acc[S.rs_order[tid]];
-                    rs_make_plan(c, S.rs_lens[c], P.maxc, stepn, S.plans[tid]);
-                    rs_plan_world32(S.plans[tid], q0, cq, sq, D.origin);
-                }
-                __syncthreads();
-                TICK(PH_RS_PLAN);
-                // sampled poses are float32 for the filter (1 sincosf per pose); their error (~1e-5 m) widens the band
-                EnvSmem Ers = E;
-                Ers.eps = E.eps + 6e-5f;
-                const float inv_maxc = (float)(1.0 / P.maxc);
-                int vb = 0;
-                for (int r = 0; r < m; ++r) {
-                    const int k = S.rs_order[r];
-                    const int c = S.rs_acc[k];
-                    if (r >= AS_MAX_PLANS) {
-                        if (tid == 0) {
-                            rs_make_plan(c, S.rs_lens[c], P.maxc, stepn, S.plan_tmp);
-                            rs_plan_world32(S.plan_tmp, q0, cq, sq, D.origin);
-                        }
-                        __syncthreads();
-                    }
-                    const RsPlan& plan = (r < AS_MAX_PLANS) ? S.plans[r] : S.plan_tmp;
-                    const int npts = plan.npts;
-                    int infeasible = 0;
-                    for (int base = 0; base < npts && !infeasible; base += AS_THREADS) {
-                        const int j = base + tid;
-                        int st = HL_FREE;
-                        unsigned amb = 0;
-                        if (j < npts) {
-                            float fx, fy, fc, fs;
-                            rs_sample_world32(plan, j, inv_maxc, fx, fy, fc, fs);
-                            if (fabsf(fx) > Ers.reach || fabsf(fy) > Ers.reach) { st = HL_AMBIG; amb = FLAGS; }
-                            else st = filter_part(Ers, fx, fy, fc, fs, Ers.ext, FLAGS, &amb);
-                        }
-                        // one barrier per chunk: warps publish (any hit | any ambiguous << 1)
-                        const unsigned hitm = __ballot_sync(0xffffffffu, st == HL_HIT);
-                        const unsigned ambm = __ballot_sync(0xffffffffu, st == HL_AMBIG);
-                        if (lane == 0) S.vote[vb][wid] = (hitm ? 1 : 0) | (ambm ? 2 : 0);
-                        __syncthreads();
-                        int bits = 0;
-#pragma unroll
-                        for (int w = 0; w < AS_WARPS; ++w) bits |= S.vote[vb][w];
-                        vb ^= 1;
-                        infeasible = bits & 1;
-                        if (!infeasible && (bits & 2)) {          // float64 sample + exact predicate, ambiguous poses only
-                            int bad = 0;
-                            if (st == HL_AMBIG) {
-                                double lx, ly, lyaw, wx, wy, wyaw;
-                                int cs, dir;
-                                rs_sample_local(plan, j, P.maxc, lx, ly, lyaw, cs, dir);
-                                rs_to_world(q0, cq, sq, lx, ly, lyaw, wx, wy, wyaw);
-                                bad = pose_exact(eb, D, wx, wy, wyaw, amb) ? 1 : 0;
-                                atomicAdd(&S.n_exact, 1ULL);
-                            }
-                            infeasible = __syncthreads_or(bad);
-                        }
-                        if (tid == 0) S.n_checks += (unsigned long long)min(AS_THREADS, npts - base);
-                    }
-                    const bool short_enough = xdiv(S.rs_L[k], P.maxc) < P.min_len_goal;     // path.L < MIN_LENGTH_TO_GOAL
-                    if (!infeasible && short_enough) {
-                        if (tid == 0) { S.rs_pick = r; S.arrival = 1; S.rs_word = c; S.goal_cost = S.rs_prio[k]; }
-                        break;
-                    }
-                    if (r + 1 >= AS_MAX_PLANS) __syncthreads();      // plan_tmp is rewritten next round
-                }
-                __syncthreads();
-                TICK(PH_RS_SAMPLE);
+            const double q0[3] = {S.cx, S.cy, S.cyaw};
+            for (int c = lane; c < HL_RS_CANDIDATES; c += 32) {
+                double l[HL_RS_MAX_SEGS] = {0, 0, 0, 0, 0};
+                bool ok = rs_candidate(c, S.rs_prob, l);
+                S.rs_valid[c] = ok ? 1 : 0;
+                for (int k = 0; k < HL_RS_MAX_SEGS; ++k) S.rs_lens[c][k] = l[k];
             }
-            // ---- tolerance arrival (:464-495) overrides the shot
-            if (tid == 0) {
+            __syncwarp();
+            TICK(PH_RS_CAND);
+            if (lane < RS_N_GROUPS) rs_select_group(lane, S.rs_valid, S.rs_lens, S.rs_accept, S.rs_Lc);
+            __syncwarp();
+            if (lane == 0) {
+                int m = rs_select_compact(S.rs_accept, S.rs_Lc, S.rs_acc, S.rs_L);
+                if (m < 0) { S.status = HL_STATUS_RS_ASSERT; m = 0; }
+                S.rs_n = m;
+                for (int k = 0; k < m; ++k)
+                    S.rs_prio[k] = rs_path_cost(S.cg, S.rs_acc[k], S.rs_lens[S.rs_acc[k]], P.max_steer,
+                                                P.reverse_cost, P.dir_change_cost, P.steer_cost);
+                if (m > 0) heapdict_order(S.rs_prio, m, S.rs_order);
+            }
+            __syncwarp();
+            TICK(PH_RS_SELECT);
+        }
+        if (live && S.status < 0) {
+            const double q0[3] = {S.cx, S.cy, S.cyaw};
+            const int m = S.rs_n;
+            const double stepn = xmul(P.res, P.maxc);
+            const double cq = m_cos(-q0[2]), sq = m_sin(-q0[2]);
+            // sampling plans of the first AW_MAX_PLANS words in pop order, one lane each
+            if (lane < m && lane < AW_MAX_PLANS) {
+                int c = S.rs_acc[S.rs_order[lane]];
+                rs_make_plan(c, S.rs_lens[c], P.maxc, stepn, S.plans[lane]);
+                rs_plan_world32(S.plans[lane], q0, cq, sq, D.origin);
+            }
+            __syncwarp();
+            TICK(PH_RS_PLAN);
+            // sampled poses are float32 for the filter (1 sincosf per pose); their error (~1e-5 m) widens the band
+            EnvSmem Ers = E;
+            Ers.eps = E.eps + 6e-5f;
+            const float inv_maxc = (float)(1.0 / P.maxc);
+            for (int r = 0; r < m; ++r) {
+                const int k = S.rs_order[r];
+                const int c = S.rs_acc[k];
+                if (r >= AW_MAX_PLANS) {
+                    __syncwarp();
+                    if (lane == 0) {
+                        rs_make_plan(c, S.rs_lens[c], P.maxc, stepn, S.plan_tmp);
+                        rs_plan_world32(S.plan_tmp, q0, cq, sq, D.origin);
+                    }
+                    __syncwarp();
+                }
+                const RsPlan& plan = (r < AW_MAX_PLANS) ? S.plans[r] : S.plan_tmp;
+                const int npts = plan.npts;
+                int infeasible = 0;
+                for (int base = 0; base < npts && !infeasible; base += 32) {
+                    const int j = base + lane;
+                    int st = HL_FREE;
+                    unsigned amb = 0;
+                    if (j < npts) {
+                        float fx, fy, fc, fs;
+                        rs_sample_world32(plan, j, inv_maxc, fx, fy, fc, fs);
+                        if (fabsf(fx) > Ers.reach || fabsf(fy) > Ers.reach) { st = HL_AMBIG; amb = FLAGS; }
+                        else st = filter_part(Ers, fx, fy, fc, fs, Ers.ext, FLAGS, &amb);
+                    }
+                    const unsigned hitm = __ballot_sync(FULL, st == HL_HIT);
+                    const unsigned ambm = __ballot_sync(FULL, st == HL_AMBIG);
+                    infeasible = hitm != 0;
+                    if (!infeasible && ambm) {          // float64 sample + exact predicate, ambiguous poses only
+                        int bad = 0;
+                        if (st == HL_AMBIG) {
+                            double lx, ly, lyaw, wx, wy, wyaw;
+                            int cs, dir;
+                            rs_sample_local(plan, j, P.maxc, lx, ly, lyaw, cs, dir);
+                            rs_to_world(q0, cq, sq, lx, ly, lyaw, wx, wy, wyaw);
+                            bad = pose_exact(eb, D, wx, wy, wyaw, amb) ? 1 : 0;
+                        }
+                        if (lane == 0) S.n_exact += (unsigned long long)__popc(ambm);
+                        infeasible = __any_sync(FULL, bad);
+                    }
+                    if (lane == 0) S.n_checks += (unsigned long long)min(32, npts - base);
+                }
+                const bool short_enough = xdiv(S.rs_L[k], P.maxc) < P.min_len_goal;     // path.L < MIN_LENGTH_TO_GOAL
+                if (!infeasible && short_enough) {
+                    if (lane == 0) { S.rs_pick = r; S.arrival = 1; S.rs_word = c; S.goal_cost = S.rs_prio[k]; }
+                    break;
+                }
+            }
+            __syncwarp();
+            TICK(PH_RS_SAMPLE);
+            // ---- tolerance arrival (:464-495) overrides the shot; else the search length of this node (:368)
+            if (lane == 0) {
                 double xd = fabs(xsub(S.cx, S.goal[0])), yd = fabs(xsub(S.cy, S.goal[1]));
                 double wd = fabs(angle_wrap(xsub(S.cyaw, S.goal[2])));
                 if (xd < P.res && yd < P.res && wd < P.yaw_res) { S.arrival = 2; S.goal_cost = S.cg; S.rs_word = -1; }
                 if (S.arrival) S.status = HL_STATUS_OK;
                 else {
-                    // ---- primitive expansion (:558-596): search length of this node (get_search_length, :368)
                     int seg = exact_search_segment(eb, D, S.cx, S.cy);
                     double len = seg < 0 ? D.default_len : eb.seg_len[D.seg_off + seg];
                     S.nsteps = (int)rint(xdiv(len, P.res));                    // Python round()
                     if (S.nsteps + 1 > HL_MAX_ROLLOUT || S.nsteps < 1) S.status = HL_STATUS_CAPACITY;
                 }
             }
-            if (tid < HL_MAX_PRIMS) { S.phit[tid] = 0; S.pany_amb[tid] = 0; }
-            __syncthreads();
-            if (S.status >= 0) break;
+            if (lane < HL_MAX_PRIMS) S.phit[lane] = 0;
+            __syncwarp();
             TICK(PH_ARRIVE);
+        }
+#if AW_LOCKSTEP
+        __syncthreads();                                                    // alignment point 2
+#endif
+        if (live && S.status < 0) {
+            // ---- primitive expansion (:558-596)
             const int n = S.nsteps, np1 = n + 1;
             const int total = P.n_prims * np1;
-            // phase A: per (p, i) displacement terms  (res*m_cos(yaws[i]))*dir, i = 0..n
-            for (int idx = tid; idx < total; idx += AS_THREADS) {
+            // phase A: per (p, i) displacement terms  (res*cos(yaws[i]))*dir, i = 0..n
+            for (int idx = lane; idx < total; idx += 32) {
                 const int p = idx / np1, i = idx - p * np1;
                 const double ys = P.yaw_step[p];
                 const double init_yaw = angle_wrap(xadd(S.cyaw, ys));
@@ -511,44 +441,43 @@ k_hybrid_astar(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen, 
                 S.ty[p][i] = xmul(xmul(P.res, m_sin(yw)), P.dir[p]);
                 S.pyaw[p][i] = rollout_yaw(init_yaw, stop, step, delta, n + 1, i + 1);
             }
-            __syncthreads();
+            __syncwarp();
             // phase B: sequential cumsum per primitive (np.cumsum), then + init
-            if (tid < P.n_prims) {
+            if (lane < P.n_prims) {
                 double ax = 0.0, ay = 0.0;
                 for (int i = 0; i < np1; ++i) {
-                    ax = (i == 0) ? S.tx[tid][0] : xadd(ax, S.tx[tid][i]);
-                    ay = (i == 0) ? S.ty[tid][0] : xadd(ay, S.ty[tid][i]);
-                    S.tx[tid][i] = xadd(S.cx, ax);
-                    S.ty[tid][i] = xadd(S.cy, ay);
+                    ax = (i == 0) ? S.tx[lane][0] : xadd(ax, S.tx[lane][i]);
+                    ay = (i == 0) ? S.ty[lane][0] : xadd(ay, S.ty[lane][i]);
+                    S.tx[lane][i] = xadd(S.cx, ax);
+                    S.ty[lane][i] = xadd(S.cy, ay);
                 }
             }
-            __syncthreads();
+            __syncwarp();
             TICK(PH_ROLLOUT);
             // phase C: float32 filter of every pose
-            for (int idx = tid; idx < total; idx += AS_THREADS) {
+            for (int idx = lane; idx < total; idx += 32) {
                 const int p = idx / np1, j = idx - p * np1;
                 unsigned amb = 0;
                 int st = pose_filter(D, E, S.tx[p][j], S.ty[p][j], S.pyaw[p][j], FLAGS, &amb);
                 S.pamb[p][j] = (st == HL_AMBIG) ? (unsigned char)amb : 0;
                 if (st == HL_HIT) atomicOr(&S.phit[p], 1);
-                else if (st == HL_AMBIG) atomicOr(&S.pany_amb[p], 1);
             }
-            if (tid == 0) S.n_checks += (unsigned long long)total;
-            __syncthreads();
+            if (lane == 0) S.n_checks += (unsigned long long)total;
+            __syncwarp();
             TICK(PH_FILTER);
             // phase D: float64 escalation only where it can still change the answer
-            for (int idx = tid; idx < total; idx += AS_THREADS) {
+            for (int idx = lane; idx < total; idx += 32) {
                 const int p = idx / np1, j = idx - p * np1;
                 if (S.pamb[p][j] && !S.phit[p]) {
                     atomicAdd(&S.n_exact, 1ULL);
                     if (pose_exact(eb, D, S.tx[p][j], S.ty[p][j], S.pyaw[p][j], S.pamb[p][j])) atomicOr(&S.phit[p], 2);
                 }
             }
-            __syncthreads();
+            __syncwarp();
             TICK(PH_EXACT);
-            // phase E: cost, key (thread per primitive) and heuristic (warp per primitive)
-            if (tid < P.n_prims && !S.phit[tid]) {
-                const int p = tid;
+            // phase E: cost and key (lane per primitive), heuristic (whole warp per primitive)
+            if (lane < P.n_prims && !S.phit[lane]) {
+                const int p = lane;
                 double len = 0.0;                                   // calculate_path_length (path_utils.py:5-12)
                 for (int i = 0; i + 1 < np1; ++i) {
                     double ds = hypot_cr(xsub(S.tx[p][i + 1], S.tx[p][i]), xsub(S.ty[p][i + 1], S.ty[p][i]));
@@ -567,16 +496,17 @@ k_hybrid_astar(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen, 
                 S.pkey_ok[p] = make_key(S.tx[p][n], S.ty[p][n], S.pyaw[p][n], P.res, P.yaw_res, ix, iy, iw, key) ? 1 : 0;
                 S.pkey[p] = key;
             }
-            for (int p = wid; p < P.n_prims; p += AS_WARPS) {
+            __syncwarp();
+            for (int p = 0; p < P.n_prims; ++p) {
                 if (!S.phit[p]) {
                     double h = warp_state_cost(eb, D, S.tx[p][n], S.ty[p][n], S.pyaw[p][n], lane);
                     if (lane == 0) S.pprio[p] = xmul(P.hybrid_cost, h);
                 }
             }
-            __syncthreads();
+            __syncwarp();
             TICK(PH_COST_HEUR);
             // phase F: merge into the open list in primitive order (:580-596)
-            if (tid == 0) {
+            if (lane == 0) {
                 for (int p = 0; p < P.n_prims; ++p) {
                     if (S.phit[p]) continue;
                     if (!S.pkey_ok[p]) { S.status = HL_STATUS_CAPACITY; break; }
@@ -599,116 +529,18 @@ k_hybrid_astar(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen, 
                     heap_set(W, S.heap_n, slot, prio);
                 }
             }
-            __syncthreads();
+            __syncwarp();
             TICK(PH_MERGE);
         }
-
-        // =============================== results ===============================
-        // expanded keys in pop order
-        {
-            int32_t* ek = expanded_keys + (size_t)sc * (P.max_nodes + 2) * 3;
-            for (int i = tid; i < S.n_closed; i += AS_THREADS) {
-                int ix, iy, iw;
-                unpack_key(W.nkey[W.corder[i]], ix, iy, iw);
-                ek[3 * i] = ix; ek[3 * i + 1] = iy; ek[3 * i + 2] = iw;
-            }
+        if (live && S.status >= 0) {
+            finalize_scenario(S, W, P, O, lane);
+            if (lane == 0) S.state = ST_IDLE;
+            __syncwarp();
         }
-        // path (get_path_from_expanded_nodes, :429-454)
-        if (tid == 0 && S.status == HL_STATUS_OK) {
-            // Walk cur -> parent -> ... -> start (slot 0 is the only node with the start key: the
-            // start cell is closed at the first pop and never re-inserted).  The chain is kept in
-            // hslot[] (the heap is dead once the search is over), goal side first.
-            // closed_set[goal_key] is the goal node, so a goal in the start's own cell makes the
-            // reference's `while current_node_index != start_node_index` loop a no-op: empty path.
-            int len = 0, poses = 0, rs_pts = 0;
-            bool ok = true;
-            if (S.goal_key != S.start_key) {
-                for (int node = S.cur; node != 0; node = W.nparent[node]) {
-                    if (len >= P.cap_nodes) { ok = false; break; }
-                    W.hslot[len++] = node;
-                    poses += W.nsteps[node] + 1;
-                }
-                if (S.arrival == 1) rs_pts = (S.rs_pick < AS_MAX_PLANS ? S.plans[S.rs_pick] : S.plan_tmp).npts;
-            }
-            S.chain_len = len;
-            S.path_len = poses + rs_pts;
-            if (!ok || S.path_len > P.max_path_poses) { S.status = HL_STATUS_CAPACITY; S.path_len = 0; }
-            else if (S.path_len > 0) {
-                unsigned long long off = atomicAdd(path_cursor, (unsigned long long)S.path_len);
-                if ((long long)(off + S.path_len) > path_capacity) { S.status = HL_STATUS_CAPACITY; S.path_len = 0; }
-                S.path_off = (long long)off;
-            }
-        }
-        __syncthreads();
-        if (S.status == HL_STATUS_OK && S.path_len > 0) {
-            // node trajectories, start side first (the chain in hslot[] is goal side first); each
-            // thread re-derives its write offset from the step counts of the nodes before it.
-            const int len = S.chain_len;
-            for (int c = tid; c < len; c += AS_THREADS) {
-                const int node = W.hslot[len - 1 - c];          // c-th node from the start side
-                long long off = S.path_off;
-                for (int q = 0; q < c; ++q) off += W.nsteps[W.hslot[len - 1 - q]] + 1;
-                const int par = W.nparent[node];
-                const int p = W.nprim[node], n = W.nsteps[node];
-                const double ys = P.yaw_step[p];
-                const double init_yaw = angle_wrap(xadd(W.nyaw[par], ys));
-                const double stop = xadd(init_yaw, xmul(ys, (double)(n + 1)));
-                const double delta = xsub(stop, init_yaw);
-                const double step = xdiv(delta, (double)(n + 1));
-                double ax = 0.0, ay = 0.0;
-                for (int i = 0; i <= n; ++i) {
-                    const double yw = rollout_yaw(init_yaw, stop, step, delta, n + 1, i);
-                    const double txv = xmul(xmul(P.res, m_cos(yw)), P.dir[p]);
-                    const double tyv = xmul(xmul(P.res, m_sin(yw)), P.dir[p]);
-                    ax = (i == 0) ? txv : xadd(ax, txv);
-                    ay = (i == 0) ? tyv : xadd(ay, tyv);
-                    path_x[off + i] = xadd(W.nx[par], ax);
-                    path_y[off + i] = xadd(W.ny[par], ay);
-                    path_yaw[off + i] = rollout_yaw(init_yaw, stop, step, delta, n + 1, i + 1);
-                    path_k[off + i] = P.curv[p];
-                    path_dir[off + i] = (int8_t)P.dir[p];
-                }
-            }
-            if (S.arrival == 1) {
-                const RsPlan& plan = (S.rs_pick < AS_MAX_PLANS) ? S.plans[S.rs_pick] : S.plan_tmp;
-                const double q0[3] = {S.cx, S.cy, S.cyaw};
-                const double cq = m_cos(-q0[2]), sq = m_sin(-q0[2]);
-                const long long off = S.path_off + (S.path_len - plan.npts);
-                for (int j = tid; j < plan.npts; j += AS_THREADS) {
-                    double lx, ly, lyaw, wx, wy, wyaw;
-                    int cs, dir;
-                    rs_sample_local(plan, j, P.maxc, lx, ly, lyaw, cs, dir);
-                    rs_to_world(q0, cq, sq, lx, ly, lyaw, wx, wy, wyaw);
-                    path_x[off + j] = wx; path_y[off + j] = wy; path_yaw[off + j] = wyaw;
-                    path_k[off + j] = cs == 0 ? 0.0 : (cs > 0 ? P.maxc : -P.maxc);
-                    path_dir[off + j] = (int8_t)dir;
-                }
-            }
-        }
-        __syncthreads();
-        if (tid == 0) {
-            HlPlanResult r;
-            r.status = S.status;
-            r.counter = (S.status == HL_STATUS_START_GOAL_BLOCKED) ? 0 : S.counter;
-            r.n_expanded = S.n_closed;
-            r.arrival = S.arrival;
-            r.path_len = S.path_len;
-            r.rs_word = S.rs_word;
-            r.path_offset = S.path_off;
-            r.goal_cost = S.goal_cost;
-            r.n_pose_checks = (long long)S.n_checks;
-            r.n_exact = (long long)S.n_exact;
-            results[sc] = r;
-            long long _n = clock64(); S.t_phase[PH_OUTPUT] += _n - S.t_last;
-            { long long tot = 0; for (int k = 0; k < AS_N_PHASES; ++k) tot += S.t_phase[k]; results[sc].cycles = tot; }
-            for (int k = 0; k < AS_N_PHASES; ++k) atomicAdd(phase_cycles + k, (unsigned long long)S.t_phase[k]);
-        }
-        // reset the used hash positions for the next scenario of this CTA
-        for (int i = tid; i < S.n_nodes; i += AS_THREADS) W.hkey[W.nhpos[i]] = KEY_EMPTY;
-        __syncthreads();
     }
 }
 
+// ------------------------------------------------------------------------------ host side
 static void fill_params(const hl_ctx* ctx, const HlSearchParams* h, AsParams& P) {
     memset(&P, 0, sizeof(P));
     P.res = h->plan_resolution; P.yaw_res = h->yaw_resolution; P.maxc = h->maxc;
@@ -727,15 +559,7 @@ static void fill_params(const hl_ctx* ctx, const HlSearchParams* h, AsParams& P)
     P.hash_size = hs;
 }
 
-static int astar_grid(const hl_ctx* ctx, int n_scen, size_t smem) {
-    int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_hybrid_astar, AS_THREADS, smem);
-    if (per_sm < 1) per_sm = 1;
-    long long g = (long long)ctx->sm_count * per_sm;
-    return (int)(g < n_scen ? g : n_scen);
-}
-
-static size_t astar_smem() { return ((sizeof(AsSmem) + 15) & ~(size_t)15) + AS_ENV_FLOATS * sizeof(float); }
+static size_t astar_smem() { return sizeof(AwSmem) * AW_WARPS; }
 
 extern "C" int hl_astar_phase_cycles(hl_ctx* ctx, uint64_t* h_out, int32_t n, int32_t reset) {
     if (!ctx || !h_out || n < 1 || n > AS_N_PHASES) { hl_set_error("hl_astar_phase_cycles: bad arguments"); return 1; }
@@ -770,10 +594,19 @@ extern "C" int hl_hybrid_astar_batch(hl_ctx* ctx, const hl_env_batch* envs, cons
     AsParams P;
     fill_params(ctx, h_params, P);
     const size_t smem = astar_smem();
-    HL_CUDA_OK(cudaFuncSetAttribute(k_hybrid_astar, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = astar_grid(ctx, n_scen, smem);
+    if ((int)smem > ctx->max_smem_optin) {
+        hl_set_error("hl_hybrid_astar_batch: %zu B of shared memory per CTA exceed the device limit %d", smem, ctx->max_smem_optin);
+        return 1;
+    }
+    HL_CUDA_OK(cudaFuncSetAttribute(k_hybrid_astar_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    HL_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_hybrid_astar_w, AW_WARPS * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long want = ((long long)n_scen + AW_WARPS - 1) / AW_WARPS;
+    long long cap = (long long)ctx->sm_count * per_sm;
+    const int grid = (int)(want < cap ? want : cap);
     const size_t stride = as_ws_bytes(P.cap_nodes, P.hash_size, P.max_nodes);
-    const size_t need = stride * (size_t)grid;
+    const size_t need = stride * (size_t)grid * AW_WARPS;
     if (need > ctx->astar_ws_bytes) {
         if (ctx->astar_ws) cudaFree(ctx->astar_ws);
         ctx->astar_ws = nullptr; ctx->astar_ws_bytes = 0;
@@ -783,10 +616,13 @@ extern "C" int hl_hybrid_astar_batch(hl_ctx* ctx, const hl_env_batch* envs, cons
     cudaStream_t st = (cudaStream_t)stream;
     HL_CUDA_OK(cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned int), st));
     HL_CUDA_OK(cudaMemsetAsync(d_path_cursor, 0, sizeof(unsigned long long), st));
-    k_hybrid_astar<<<grid, AS_THREADS, smem, st>>>(envs->dev, d_scen, n_scen, P, (char*)ctx->astar_ws, stride,
-                                                   ctx->d_counters, d_results, d_expanded_keys, d_path_x, d_path_y,
-                                                   d_path_yaw, d_path_k, d_path_dir, (long long)path_capacity,
-                                                   d_path_cursor, (unsigned long long*)(ctx->d_counters + 16));
+    AwOut O;
+    O.results = d_results; O.expanded_keys = d_expanded_keys;
+    O.path_x = d_path_x; O.path_y = d_path_y; O.path_yaw = d_path_yaw; O.path_k = d_path_k; O.path_dir = d_path_dir;
+    O.path_capacity = (long long)path_capacity; O.path_cursor = d_path_cursor;
+    O.phase_cycles = (unsigned long long*)(ctx->d_counters + 16);
+    k_hybrid_astar_w<<<grid, AW_WARPS * 32, smem, st>>>(envs->dev, d_scen, n_scen, P, (char*)ctx->astar_ws, stride,
+                                                        ctx->d_counters, O);
     HL_CUDA_OK(cudaGetLastError());
     return 0;
 }
