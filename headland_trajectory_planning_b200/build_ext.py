@@ -37,6 +37,7 @@ def build(force=False, verbose=False):
         o = s[:-3] + ".o"
         cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo",
                "-std=c++17", "-Xcompiler", "-fPIC", "--fmad=true", "-c", s, "-o", o]
+        cmd[1:1] = os.environ.get("HL_NVCC_FLAGS", "").split()
         if verbose:
             cmd.insert(1, "-Xptxas")
             cmd.insert(2, "-v")

@@ -18,11 +18,16 @@
 #ifndef AW_WARPS
 #define AW_WARPS 12
 #endif
+#ifndef AW_MIN_CTAS
+#define AW_MIN_CTAS 1
+#endif
 #ifndef AW_LOCKSTEP
 #define AW_LOCKSTEP 1
 #endif
 #define AW_ENV_FLOATS 512
+#ifndef AW_MAX_PLANS
 #define AW_MAX_PLANS 6
+#endif
 #define FULL 0xffffffffu
 enum { ST_IDLE = 0, ST_SEARCH = 1, ST_DONE = 2 };
 
@@ -34,22 +39,28 @@ struct AwSmem {                          // one per warp
     int status, arrival, rs_word;
     double goal_cost;
     int cur; double cx, cy, cyaw, cg; int cprim; int nsteps;
-    // Reeds-Shepp shot
-    double rs_lens[HL_RS_CANDIDATES][HL_RS_MAX_SEGS];
-    double rs_L[HL_RS_CANDIDATES], rs_prio[HL_RS_CANDIDATES], rs_Lc[HL_RS_CANDIDATES];
-    int rs_acc[HL_RS_CANDIDATES], rs_order[HL_RS_CANDIDATES];
-    unsigned char rs_valid[HL_RS_CANDIDATES + 2], rs_accept[HL_RS_CANDIDATES + 2];
+    // The Reeds-Shepp shot and the primitive expansion of one node never overlap in time (a successful shot
+    // ends the search before any primitive is rolled out), so their scratch shares storage.
+    union {
+        struct {
+            double rs_lens[HL_RS_CANDIDATES][HL_RS_MAX_SEGS];
+            double rs_L[HL_RS_CANDIDATES], rs_prio[HL_RS_CANDIDATES], rs_Lc[HL_RS_CANDIDATES];
+            int rs_acc[HL_RS_CANDIDATES], rs_order[HL_RS_CANDIDATES];
+            unsigned char rs_valid[HL_RS_CANDIDATES + 2], rs_accept[HL_RS_CANDIDATES + 2];
+            RsPlan plans[AW_MAX_PLANS];
+            RsPlan plan_tmp;
+        };
+        struct {
+            double tx[HL_MAX_PRIMS][AS_ROLL], ty[HL_MAX_PRIMS][AS_ROLL], pyaw[HL_MAX_PRIMS][AS_ROLL];
+            unsigned char pamb[HL_MAX_PRIMS][AS_ROLL];
+            double pg[HL_MAX_PRIMS], pprio[HL_MAX_PRIMS];
+            long long pkey[HL_MAX_PRIMS];
+            int pkey_ok[HL_MAX_PRIMS], pslot[HL_MAX_PRIMS], ppos[HL_MAX_PRIMS], pneed[HL_MAX_PRIMS];
+        };
+    };
     RsProblem rs_prob;
     int rs_n, rs_pick;
-    RsPlan plans[AW_MAX_PLANS];
-    RsPlan plan_tmp;
-    // primitives
-    double tx[HL_MAX_PRIMS][AS_ROLL], ty[HL_MAX_PRIMS][AS_ROLL], pyaw[HL_MAX_PRIMS][AS_ROLL];
-    unsigned char pamb[HL_MAX_PRIMS][AS_ROLL];
     int phit[HL_MAX_PRIMS];
-    double pg[HL_MAX_PRIMS], pprio[HL_MAX_PRIMS];
-    long long pkey[HL_MAX_PRIMS];
-    int pkey_ok[HL_MAX_PRIMS];
     // stats
     unsigned long long n_checks, n_exact;
     long long t_last, t_phase[AS_N_PHASES];
@@ -238,7 +249,7 @@ __device__ __noinline__ void setup_scenario(AwSmem& S, const AsWs& W, const AsPa
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(AW_WARPS * 32, 1)
+__global__ void __launch_bounds__(AW_WARPS * 32, AW_MIN_CTAS)
 k_hybrid_astar_w(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen, AsParams P, char* ws_base,
                  size_t ws_stride, unsigned int* work_counter, AwOut O) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -326,14 +337,27 @@ k_hybrid_astar_w(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
             TICK(PH_RS_CAND);
             if (lane < RS_N_GROUPS) rs_select_group(lane, S.rs_valid, S.rs_lens, S.rs_accept, S.rs_Lc);
             __syncwarp();
-            if (lane == 0) {
-                int m = rs_select_compact(S.rs_accept, S.rs_Lc, S.rs_acc, S.rs_L);
-                if (m < 0) { S.status = HL_STATUS_RS_ASSERT; m = 0; }
-                S.rs_n = m;
-                for (int k = 0; k < m; ++k)
+            {
+                // accepted rows in evaluation order: ballot + prefix count instead of a serial scan
+                const int a0 = S.rs_accept[lane];
+                const int a1 = (lane + 32 < HL_RS_CANDIDATES) ? S.rs_accept[lane + 32] : 0;
+                const unsigned b0 = __ballot_sync(FULL, a0 == 1), b1 = __ballot_sync(FULL, a1 == 1);
+                const unsigned bad = __ballot_sync(FULL, a0 == 2 || a1 == 2);      // `assert path.L >= 0.01`
+                const unsigned lt = (1u << lane) - 1u;
+                const int n0 = __popc(b0);
+                if (a0 == 1) { int k = __popc(b0 & lt); S.rs_acc[k] = lane; S.rs_L[k] = S.rs_Lc[lane]; }
+                if (a1 == 1) { int k = n0 + __popc(b1 & lt); S.rs_acc[k] = lane + 32; S.rs_L[k] = S.rs_Lc[lane + 32]; }
+                const int m = bad ? 0 : n0 + __popc(b1);
+                __syncwarp();
+                for (int k = lane; k < m; k += 32)
                     S.rs_prio[k] = rs_path_cost(S.cg, S.rs_acc[k], S.rs_lens[S.rs_acc[k]], P.max_steer,
                                                 P.reverse_cost, P.dir_change_cost, P.steer_cost);
-                if (m > 0) heapdict_order(S.rs_prio, m, S.rs_order);
+                __syncwarp();
+                if (lane == 0) {
+                    if (bad) S.status = HL_STATUS_RS_ASSERT;
+                    S.rs_n = m;
+                    if (m > 0) heapdict_order(S.rs_prio, m, S.rs_order);
+                }
             }
             __syncwarp();
             TICK(PH_RS_SELECT);
@@ -369,8 +393,11 @@ k_hybrid_astar_w(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                 const RsPlan& plan = (r < AW_MAX_PLANS) ? S.plans[r] : S.plan_tmp;
                 const int npts = plan.npts;
                 int infeasible = 0;
-                for (int base = 0; base < npts && !infeasible; base += 32) {
-                    const int j = base + lane;
+                // Poses are visited with stride `passes` (lane*passes + pass): the first pass already spans the
+                // whole word, so an infeasible word is almost always rejected after one 32-pose pass.
+                const int passes = (npts + 31) >> 5;
+                for (int pass = 0; pass < passes && !infeasible; ++pass) {
+                    const int j = lane * passes + pass;
                     int st = HL_FREE;
                     unsigned amb = 0;
                     if (j < npts) {
@@ -379,6 +406,7 @@ k_hybrid_astar_w(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                         if (fabsf(fx) > Ers.reach || fabsf(fy) > Ers.reach) { st = HL_AMBIG; amb = FLAGS; }
                         else st = filter_part(Ers, fx, fy, fc, fs, Ers.ext, FLAGS, &amb);
                     }
+                    const unsigned livem = __ballot_sync(FULL, j < npts);
                     const unsigned hitm = __ballot_sync(FULL, st == HL_HIT);
                     const unsigned ambm = __ballot_sync(FULL, st == HL_AMBIG);
                     infeasible = hitm != 0;
@@ -394,7 +422,7 @@ k_hybrid_astar_w(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                         if (lane == 0) S.n_exact += (unsigned long long)__popc(ambm);
                         infeasible = __any_sync(FULL, bad);
                     }
-                    if (lane == 0) S.n_checks += (unsigned long long)min(32, npts - base);
+                    if (lane == 0) S.n_checks += (unsigned long long)__popc(livem);
                 }
                 const bool short_enough = xdiv(S.rs_L[k], P.maxc) < P.min_len_goal;     // path.L < MIN_LENGTH_TO_GOAL
                 if (!infeasible && short_enough) {
@@ -421,7 +449,7 @@ k_hybrid_astar_w(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
             __syncwarp();
             TICK(PH_ARRIVE);
         }
-#if AW_LOCKSTEP
+#if AW_LOCKSTEP == 1
         __syncthreads();                                                    // alignment point 2
 #endif
         if (live && S.status < 0) {
@@ -476,6 +504,8 @@ k_hybrid_astar_w(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
             __syncwarp();
             TICK(PH_EXACT);
             // phase E: cost and key (lane per primitive), heuristic (whole warp per primitive)
+            if (lane < HL_MAX_PRIMS) S.pneed[lane] = 1;
+            __syncwarp();
             if (lane < P.n_prims && !S.phit[lane]) {
                 const int p = lane;
                 double len = 0.0;                                   // calculate_path_length (path_utils.py:5-12)
@@ -495,10 +525,18 @@ k_hybrid_astar_w(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                 long long key = 0;
                 S.pkey_ok[p] = make_key(S.tx[p][n], S.ty[p][n], S.pyaw[p][n], P.res, P.yaw_res, ix, iy, iw, key) ? 1 : 0;
                 S.pkey[p] = key;
+                // look the key up now, all primitives in parallel (the table only changes in the merge below)
+                int pos = -1;
+                const int slot = S.pkey_ok[p] ? hash_find(W, hmask, key, &pos) : -1;
+                S.pslot[p] = slot;
+                S.ppos[p] = pos;
+                // the heuristic is only needed if the merge will insert or improve this cell: a closed cell
+                // stays closed and an open cell's g can only drop further during this merge
+                if (slot >= 0 && (W.nstate[slot] == 1 || !(cost < W.ng[slot]))) S.pneed[p] = 0;
             }
             __syncwarp();
             for (int p = 0; p < P.n_prims; ++p) {
-                if (!S.phit[p]) {
+                if (!S.phit[p] && S.pneed[p]) {
                     double h = warp_state_cost(eb, D, S.tx[p][n], S.ty[p][n], S.pyaw[p][n], lane);
                     if (lane == 0) S.pprio[p] = xmul(P.hybrid_cost, h);
                 }
@@ -510,13 +548,16 @@ k_hybrid_astar_w(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                 for (int p = 0; p < P.n_prims; ++p) {
                     if (S.phit[p]) continue;
                     if (!S.pkey_ok[p]) { S.status = HL_STATUS_CAPACITY; break; }
-                    int pos;
-                    int slot = hash_find(W, hmask, S.pkey[p], &pos);
+                    // the prefetched lookup is still valid unless this merge touched its probe position
+                    int pos = S.ppos[p];
+                    int slot = S.pslot[p];
+                    if (slot < 0 ? (W.hkey[pos] != KEY_EMPTY) : false) slot = hash_find(W, hmask, S.pkey[p], &pos);
                     const double g = S.pg[p];
                     const double prio = (S.pprio[p] > g) ? S.pprio[p] : g;      // max(sim.cost, 50*h)
                     if (slot >= 0) {
                         if (W.nstate[slot] == 1) continue;                         // in closed_set
                         if (!(g < W.ng[slot])) continue;                           // not strictly better
+                        if (!S.pneed[p]) { S.status = HL_STATUS_CAPACITY; break; } // cannot happen (see above)
                     } else {
                         if (S.n_nodes >= P.cap_nodes) { S.status = HL_STATUS_CAPACITY; break; }
                         slot = S.n_nodes++;
