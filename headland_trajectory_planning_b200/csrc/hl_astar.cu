@@ -22,7 +22,7 @@
 #define AW_MIN_CTAS 1
 #endif
 #ifndef AW_LOCKSTEP
-#define AW_LOCKSTEP 1
+#define AW_LOCKSTEP 1      // 0 free-running, 1 two alignment barriers per expansion, 2 one, 3 one every other expansion
 #endif
 #define AW_ENV_FLOATS 512
 #ifndef AW_MAX_PLANS
@@ -101,6 +101,8 @@ __device__ __noinline__ void stage_env_warp(const EnvBatchDev& eb, const EnvDesc
 struct AwOut {
     HlPlanResult* results;
     int32_t* expanded_keys;
+    long long keys_capacity;
+    unsigned long long* keys_cursor;
     double* path_x; double* path_y; double* path_yaw; double* path_k;
     int8_t* path_dir;
     long long path_capacity;
@@ -111,8 +113,15 @@ struct AwOut {
 // Results of a finished scenario: expanded keys, path (get_path_from_expanded_nodes, :429-454), record.
 __device__ __noinline__ void finalize_scenario(AwSmem& S, const AsWs& W, const AsParams& P, const AwOut& O, int lane) {
     const int sc = S.scen;
+    long long koff = 0;
+    if (lane == 0 && S.n_closed > 0) {
+        koff = (long long)atomicAdd(O.keys_cursor, (unsigned long long)S.n_closed);
+        if (koff + S.n_closed > O.keys_capacity) { koff = -1; }
+    }
+    koff = __shfl_sync(FULL, koff, 0);
+    if (koff < 0) { if (lane == 0) { S.status = HL_STATUS_CAPACITY; S.n_closed = 0; } koff = 0; __syncwarp(); }
     {
-        int32_t* ek = O.expanded_keys + (size_t)sc * (P.max_nodes + 2) * 3;
+        int32_t* ek = O.expanded_keys + (size_t)koff * 3;
         for (int i = lane; i < S.n_closed; i += 32) {
             int ix, iy, iw;
             unpack_key(W.nkey[W.corder[i]], ix, iy, iw);
@@ -197,6 +206,7 @@ __device__ __noinline__ void finalize_scenario(AwSmem& S, const AsWs& W, const A
         r.path_len = S.path_len;
         r.rs_word = S.rs_word;
         r.path_offset = S.path_off;
+        r.keys_offset = koff;
         r.goal_cost = S.goal_cost;
         r.n_pose_checks = (long long)S.n_checks;
         r.n_exact = (long long)S.n_exact;
@@ -268,6 +278,8 @@ k_hybrid_astar_w(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
     EnvSmem E;
     E.n_obs = E.n_field = E.n_seg = E.all_rect = 0; E.eps = 0.f; E.reach = 0.f; E.obs = E.field = E.seg = nullptr;
     const EnvDesc* Dp = eb.desc;
+    int iter = 0;
+    (void)iter;
 
     while (true) {
         // ---- refill: a warp without a scenario takes the next one from the global queue
@@ -295,7 +307,12 @@ k_hybrid_astar_w(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
             else if (lane == 0) S.state = ST_SEARCH;
             __syncwarp();
         }
-#if AW_LOCKSTEP
+#if AW_LOCKSTEP == 3
+        {   // alignment every other expansion only
+            if ((iter++ & 1) == 0) { if (__syncthreads_and(S.state == ST_DONE)) break; }
+            else if (S.state == ST_DONE) { /* keep pace: wait at the next aligned iteration */ }
+        }
+#elif AW_LOCKSTEP
         if (__syncthreads_and(S.state == ST_DONE)) break;                   // alignment point 1
 #else
         if (S.state == ST_DONE) break;
@@ -619,12 +636,12 @@ extern "C" int64_t hl_hybrid_astar_workspace_bytes(const hl_ctx* ctx, const HlSe
 
 extern "C" int hl_hybrid_astar_batch(hl_ctx* ctx, const hl_env_batch* envs, const HlScenario* d_scen,
                                      int32_t n_scen, const HlSearchParams* h_params,
-                                     HlPlanResult* d_results, int32_t* d_expanded_keys,
-                                     double* d_path_x, double* d_path_y, double* d_path_yaw,
+                                     HlPlanResult* d_results, int32_t* d_expanded_keys, int64_t keys_capacity,
+                                     unsigned long long* d_keys_cursor, double* d_path_x, double* d_path_y, double* d_path_yaw,
                                      double* d_path_k, int8_t* d_path_dir, int64_t path_capacity,
                                      unsigned long long* d_path_cursor, void* stream) {
     if (!ctx || !envs || !d_scen || !h_params || !d_results || !d_expanded_keys || !d_path_x || !d_path_y ||
-        !d_path_yaw || !d_path_k || !d_path_dir || !d_path_cursor || n_scen < 0) {
+        !d_path_yaw || !d_path_k || !d_path_dir || !d_path_cursor || !d_keys_cursor || n_scen < 0) {
         hl_set_error("hl_hybrid_astar_batch: bad arguments"); return 1;
     }
     if (n_scen == 0) return 0;
@@ -657,8 +674,10 @@ extern "C" int hl_hybrid_astar_batch(hl_ctx* ctx, const hl_env_batch* envs, cons
     cudaStream_t st = (cudaStream_t)stream;
     HL_CUDA_OK(cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned int), st));
     HL_CUDA_OK(cudaMemsetAsync(d_path_cursor, 0, sizeof(unsigned long long), st));
+    HL_CUDA_OK(cudaMemsetAsync(d_keys_cursor, 0, sizeof(unsigned long long), st));
     AwOut O;
     O.results = d_results; O.expanded_keys = d_expanded_keys;
+    O.keys_capacity = (long long)keys_capacity; O.keys_cursor = d_keys_cursor;
     O.path_x = d_path_x; O.path_y = d_path_y; O.path_yaw = d_path_yaw; O.path_k = d_path_k; O.path_dir = d_path_dir;
     O.path_capacity = (long long)path_capacity; O.path_cursor = d_path_cursor;
     O.phase_cycles = (unsigned long long*)(ctx->d_counters + 16);

@@ -60,13 +60,18 @@ def make_record(env, car, heuristic=None):
     return EnvRecord(env.obstacle_quads(), env.field_ring(), car.body_ext, car.aux_exts, **kw)
 
 
+def pack_structs(records):
+    """ctypes array of HlEnvHost pointing at the records' host buffers (reusable across uploads)."""
+    return (_lib.HlEnvHost * len(records))(*[r.as_struct() for r in records])
+
+
 class EnvBatch:
     """Device-resident environments.  ``records`` are EnvRecord objects."""
 
-    def __init__(self, records, device=None):
+    def __init__(self, records, device=None, structs=None):
         self.records = list(records)
         self.ctx = _lib.get_ctx(device)
-        arr = (_lib.HlEnvHost * len(self.records))(*[r.as_struct() for r in self.records])
+        arr = structs if structs is not None else pack_structs(self.records)
         h = C.c_void_p()
         _lib.check(_lib.load_library().hl_env_upload(self.ctx, arr, len(self.records), C.byref(h)),
                    "hl_env_upload")

@@ -134,7 +134,7 @@ class HybridAStarSearch(object):
         r = out["results"][0]
         self.last_result = r
         self.status = _lib.STATUS_NAMES[int(r["status"])]
-        self.expanded = [tuple(int(v) for v in k) for k in out["expanded"][0, :int(r["n_expanded"])]]
+        self.expanded = [tuple(int(v) for v in k) for k in ops.expanded_of(out, 0)]
         if r["status"] in (4, 5):
             raise _lib.HeadlandError(f"hybrid_a_star_search: device status {self.status}")
         if r["status"] == 1:

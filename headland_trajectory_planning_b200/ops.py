@@ -124,8 +124,8 @@ def hybrid_astar_batch(envs, scenarios, params, path_capacity=None, to_host=True
 
     ``scenarios``: numpy structured array (``_lib.SCENARIO_DTYPE``) on the host (it is
     copied to the device inside this call) or a uint8 CUDA tensor of the same bytes.
-    Returns a dict with ``results`` (structured), ``expanded`` [B, max_nodes+2, 3] int32 and
-    the pooled path arrays (host numpy when ``to_host``)."""
+    Returns a dict with ``results`` (structured), the pooled ``expanded`` keys [rows, 3] int32 (slice
+    of scenario i: ``expanded_of(out, i)``) and the pooled path arrays (host numpy when ``to_host``)."""
     torch = _torch()
     lib = _lib.load_library()
     dev = _device()
@@ -139,20 +139,26 @@ def hybrid_astar_batch(envs, scenarios, params, path_capacity=None, to_host=True
         path_capacity = max(4096, 1024 * n)
     mn = params.max_nodes
     results = torch.empty(n * _lib.RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
-    expanded = torch.empty((n, mn + 2, 3), dtype=torch.int32, device=dev)
+    keys_cap = n * (mn + 2)
+    expanded = torch.empty((keys_cap, 3), dtype=torch.int32, device=dev)
+    kcursor = torch.zeros(1, dtype=torch.int64, device=dev)
     px = torch.empty(path_capacity, dtype=torch.float64, device=dev)
     py = torch.empty_like(px); pyaw = torch.empty_like(px); pk = torch.empty_like(px)
     pdir = torch.empty(path_capacity, dtype=torch.int8, device=dev)
     cursor = torch.zeros(1, dtype=torch.int64, device=dev)
     _lib.check(lib.hl_hybrid_astar_batch(envs.ctx, envs.handle, _lib.ptr(d_scen), n, C.byref(params),
-                                         _lib.ptr(results), _lib.ptr(expanded), _lib.ptr(px), _lib.ptr(py),
+                                         _lib.ptr(results), _lib.ptr(expanded), keys_cap, _lib.ptr(kcursor),
+                                         _lib.ptr(px), _lib.ptr(py),
                                          _lib.ptr(pyaw), _lib.ptr(pk), _lib.ptr(pdir), path_capacity,
                                          _lib.ptr(cursor), _lib.stream_ptr()), "hl_hybrid_astar_batch")
-    out = dict(results=results, expanded=expanded, x=px, y=py, yaw=pyaw, k=pk, dir=pdir, cursor=cursor, n=n)
+    out = dict(results=results, expanded=expanded, x=px, y=py, yaw=pyaw, k=pk, dir=pdir, cursor=cursor,
+               kcursor=kcursor, n=n)
     if to_host:
-        used = int(cursor.item())
+        both = torch.cat([cursor, kcursor]).cpu().numpy()
+        used, kused = int(both[0]), int(both[1])
         out["results"] = results.cpu().numpy().view(_lib.RESULT_DTYPE)
-        out["expanded"] = expanded.cpu().numpy()
+        out["expanded"] = expanded[:min(kused, keys_cap)].cpu().numpy()
+        out["keys_used"] = kused
         for key in ("x", "y", "yaw", "k", "dir"):
             out[key] = out[key][:min(used, path_capacity)].cpu().numpy()
         out["used"] = used
@@ -219,3 +225,10 @@ def astar_phase_cycles(reset=True, device=None):
     _lib.check(lib.hl_astar_phase_cycles(_lib.get_ctx(device), buf, len(PHASE_NAMES), 1 if reset else 0),
                "hl_astar_phase_cycles")
     return dict(zip(PHASE_NAMES, [int(v) for v in buf]))
+
+
+def expanded_of(out, i):
+    """Popped grid keys [n_expanded, 3] of scenario ``i`` from a host result dict."""
+    r = out["results"][i]
+    a = int(r["keys_offset"])
+    return out["expanded"][a:a + int(r["n_expanded"])]

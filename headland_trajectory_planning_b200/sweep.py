@@ -45,14 +45,19 @@ def algorithmic_flops(recs, results):
 
 
 def gather_results(results_np, expanded_np, world_size, rank, device=None):
-    """Gather of the fixed-stride records to rank 0 -- the only collective of a sweep
-    (torch.distributed must be initialised).  On the GPU box the tensors live on the
-    device so NCCL moves them over NVLink; ``device="cpu"`` is the gloo path the CPU tests use."""
+    """Gather of the result records and pooled expanded keys to rank 0 -- the only collective of a sweep
+    (torch.distributed must be initialised).  Records are fixed-stride; the key pools are padded to the
+    largest pool (one all_reduce of a scalar).  On the GPU box the tensors live on the device so NCCL moves
+    them over NVLink; ``device="cpu"`` is the gloo path the CPU tests use."""
     import torch
     import torch.distributed as dist
     dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
     t_res = torch.from_numpy(np.ascontiguousarray(results_np).view(np.uint8).reshape(-1).copy()).to(dev)
-    t_exp = torch.from_numpy(np.ascontiguousarray(expanded_np).copy()).to(dev)
+    rows = torch.tensor([len(expanded_np)], dtype=torch.int64, device=dev)
+    dist.all_reduce(rows, op=dist.ReduceOp.MAX)
+    pad = np.zeros((int(rows.item()), 3), dtype=np.int32)
+    pad[:len(expanded_np)] = expanded_np
+    t_exp = torch.from_numpy(pad).to(dev)
     if rank == 0:
         g_res = [torch.empty_like(t_res) for _ in range(world_size)]
         g_exp = [torch.empty_like(t_exp) for _ in range(world_size)]
@@ -65,11 +70,18 @@ def gather_results(results_np, expanded_np, world_size, rank, device=None):
 
 
 def merge_shards(per_rank_results, per_rank_expanded, n_total, world_size):
-    """Undo the interleaved sharding: record i of rank r is scenario r + i*world_size."""
+    """Undo the interleaved sharding: record i of rank r is scenario r + i*world_size.  Returns the
+    merged records (keys_offset rewritten) and one pooled key array in scenario order."""
     res = np.zeros(n_total, dtype=_lib.RESULT_DTYPE)
-    exp = np.zeros((n_total,) + per_rank_expanded[0].shape[1:], dtype=np.int32)
+    chunks = [None] * n_total
     for r in range(world_size):
         idx = shard_indices(n_total, r, world_size)
-        res[idx] = per_rank_results[r][:len(idx)]
-        exp[idx] = per_rank_expanded[r][:len(idx)]
+        rr = per_rank_results[r][:len(idx)]
+        res[idx] = rr
+        for k, i in enumerate(idx):
+            a = int(rr[k]["keys_offset"])
+            chunks[i] = per_rank_expanded[r][a:a + int(rr[k]["n_expanded"])]
+    off = np.concatenate([[0], np.cumsum([len(c) for c in chunks])])
+    res["keys_offset"] = off[:-1]
+    exp = np.concatenate(chunks) if n_total else np.zeros((0, 3), np.int32)
     return res, exp

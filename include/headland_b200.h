@@ -122,6 +122,7 @@ typedef struct {
     double  goal_cost;     /* cost of the goal node                                   */
     int64_t n_pose_checks; /* footprint checks executed (primitives + shots)          */
     int64_t n_exact;       /* of which escalated to the float64 predicates            */
+    int64_t keys_offset;   /* first row of this scenario's slice of the pooled expanded-key buffer */
     int64_t cycles;        /* SM clock cycles this scenario occupied its CTA (the reference prints
                               `hybrid search time`, hybrid_a_star_search.py:603)       */
 } HlPlanResult;
@@ -203,14 +204,16 @@ int hl_rs_sample(hl_ctx* ctx, const double* d_start, const HlRsWord* d_words, in
  * (path_planner/hybrid_a_star_search.py:497-607), King mode, one CTA per scenario.
  *   d_scen          [B] HlScenario
  *   d_results       [B] HlPlanResult
- *   d_expanded_keys [B][max_nodes+2][3] int32 popped grid indices in pop order
+ *   d_expanded_keys pooled [keys_capacity][3] int32: popped grid indices in pop order, one slice per
+ *                   scenario (HlPlanResult.keys_offset, n_expanded); keys_capacity = B*(max_nodes+1) always fits
+ *   d_keys_cursor   device int64 bump allocator for that pool, zeroed by the callee
  *   d_path_*        pooled output path (x,y,yaw,k float64, dir int8), capacity
  *                   path_capacity poses in total; slices via HlPlanResult.path_offset
  *   d_path_cursor   device int64 bump allocator, zeroed by the callee                 */
 int hl_hybrid_astar_batch(hl_ctx* ctx, const hl_env_batch* envs, const HlScenario* d_scen,
                           int32_t n_scen, const HlSearchParams* h_params,
-                          HlPlanResult* d_results, int32_t* d_expanded_keys,
-                          double* d_path_x, double* d_path_y, double* d_path_yaw,
+                          HlPlanResult* d_results, int32_t* d_expanded_keys, int64_t keys_capacity,
+                          unsigned long long* d_keys_cursor, double* d_path_x, double* d_path_y, double* d_path_yaw,
                           double* d_path_k, int8_t* d_path_dir, int64_t path_capacity,
                           unsigned long long* d_path_cursor, void* stream);
 /* Bytes of scratch the search keeps per resident CTA, and how many CTAs it launches

@@ -19,13 +19,16 @@ def _worker(rank, world, port, n_total, tmp):
     idx = sweep.shard_indices(n_total, rank, world)
     # stand-in shard results: fields derived from the global scenario id
     res = np.zeros(len(sweep.shard_indices(n_total, 0, world)), dtype=_lib.RESULT_DTYPE)
-    exp = np.zeros((len(res), 6, 3), dtype=np.int32)
+    rows = []
     for k, i in enumerate(idx):
         res[k]["status"] = i % 4
         res[k]["counter"] = 1000 + i
         res[k]["path_offset"] = 7 * i
         res[k]["goal_cost"] = 0.5 * i
-        exp[k, :, :] = i
+        res[k]["keys_offset"] = sum(len(r) for r in rows)
+        res[k]["n_expanded"] = 1 + i % 3                      # ragged key slices
+        rows.append(np.full((1 + i % 3, 3), i, dtype=np.int32))
+    exp = np.concatenate(rows)
     g_res, g_exp = sweep.gather_results(res, exp, world, rank, device="cpu")
     if rank == 0:
         m_res, m_exp = sweep.merge_shards(g_res, g_exp, n_total, world)
@@ -45,4 +48,8 @@ def test_two_rank_shard_and_gather(tmp_path):
     assert list(res["counter"]) == [1000 + i for i in range(n_total)]
     assert list(res["status"]) == [i % 4 for i in range(n_total)]
     assert list(res["path_offset"]) == [7 * i for i in range(n_total)]
-    assert (exp[:, 0, 0] == np.arange(n_total)).all()
+    assert list(res["n_expanded"]) == [1 + i % 3 for i in range(n_total)]
+    for i in range(n_total):
+        a = int(res["keys_offset"][i])
+        assert (exp[a:a + int(res["n_expanded"][i])] == i).all()
+    assert len(exp) == int(res["n_expanded"].sum())

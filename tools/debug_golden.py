@@ -13,7 +13,7 @@ eo = np.concatenate([[0], np.cumsum(g["n_expanded"])])
 for k, i in enumerate(ids):
     r = out["results"][k]
     want = g["expanded"][eo[i]:eo[i + 1]]
-    got = out["expanded"][k, :r["n_expanded"]]
+    got = ops.expanded_of(out, k)
     n = min(len(want), len(got))
     d = np.nonzero((want[:n] != got[:n]).any(axis=1))[0]
     print(i, "status", r["status"], g["status"][i], "counter", r["counter"], g["counter"][i], "n_exp", len(got), len(want),

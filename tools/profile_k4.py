@@ -9,12 +9,14 @@ recs, scen, car = sweep.build_records(scns)
 envs = EnvBatch(recs)
 params = sweep.search_params(car)
 d_scen = torch.from_numpy(scen.view(np.uint8).reshape(-1)).cuda()
-for rep in range(2):
+times = []
+for rep in range(int(os.environ.get('REPS', '6'))):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     o = ops.hybrid_astar_batch(envs, d_scen, params, path_capacity=1024 * n, to_host=False)
     b.record(); torch.cuda.synchronize()
-    print("rep", rep, "ms", a.elapsed_time(b))
+    times.append(round(a.elapsed_time(b), 1))
+print("ms", times, "min", min(times), "median", sorted(times)[len(times) // 2])
 ph = ops.astar_phase_cycles()
 tot = sum(ph.values())
 print({k: round(100 * v / tot, 1) for k, v in ph.items()})
