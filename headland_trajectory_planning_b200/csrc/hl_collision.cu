@@ -14,11 +14,37 @@
 
 #define K1_THREADS 256
 
+// Ambiguous poses of a warp are resolved one at a time by the WHOLE warp (warp_exact_part_check): the pose
+// is broadcast with shuffles and the exact float64 predicate runs on 32 lanes.
+__device__ __forceinline__ void warp_resolve(bool need, double x, double y, double yaw, int env, const double* ext,
+                                             unsigned amb, bool& bad, const EnvBatchDev& eb,
+                                             unsigned long long* n_exact, int lane) {
+    unsigned m = __ballot_sync(0xffffffffu, need);
+    if (m && n_exact && lane == 0) atomicAdd(n_exact, (unsigned long long)__popc(m));
+    while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        Pose64 p;
+        p.x = __shfl_sync(0xffffffffu, x, src);
+        p.y = __shfl_sync(0xffffffffu, y, src);
+        const double byaw = __shfl_sync(0xffffffffu, yaw, src);
+        p.c = cos(byaw); p.s = sin(byaw);
+        double e4[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) e4[k] = __shfl_sync(0xffffffffu, ext[k], src);
+        const int be = __shfl_sync(0xffffffffu, env, src);
+        const unsigned ba = __shfl_sync(0xffffffffu, amb, src);
+        const bool res = warp_exact_part_check(p, e4, eb, eb.desc[be], ba, lane);
+        if (lane == src) bad = res;
+    }
+}
+
 __global__ void __launch_bounds__(K1_THREADS, 3)
 k_collision(EnvBatchDev eb, const int32_t* __restrict__ env_id, const double* __restrict__ poses,
             const int32_t* __restrict__ pose_idx, long long n, unsigned flags,
             uint8_t* __restrict__ out, unsigned long long* n_exact, int smem_floats) {
     extern __shared__ float sm[];
+    const int lane = threadIdx.x & 31;
     const long long n_tiles = (n + K1_THREADS - 1) / K1_THREADS;
     int staged_env = -1;
     EnvSmem Es;
@@ -32,21 +58,53 @@ k_collision(EnvBatchDev eb, const int32_t* __restrict__ env_id, const double* __
             staged_env = e0;
             __syncthreads();
         }
-        long long i = base + threadIdx.x;
-        if (i < n) {
-            int e = env_id ? env_id[i] : 0;
-            double x = poses[3 * i], y = poses[3 * i + 1], yaw = poses[3 * i + 2];
-            bool with_aux = pose_idx ? ((pose_idx[i] & 1) == 0) : true;
-            bool bad;
-            if (e == e0) {
-                bad = pose_infeasible(eb, eb.desc[e], Es, x, y, yaw, with_aux, flags, n_exact);
-            } else {
-                EnvSmem Eg;
-                global_env(eb, eb.desc[e], Eg);
-                bad = pose_infeasible(eb, eb.desc[e], Eg, x, y, yaw, with_aux, flags, n_exact);
-            }
-            out[i] = bad ? 1 : 0;
+        const long long i = base + threadIdx.x;
+        const bool active = i < n;
+        const int e = active ? (env_id ? env_id[i] : 0) : e0;
+        const EnvDesc& D = eb.desc[e];
+        EnvSmem Eg;
+        if (e != e0) global_env(eb, D, Eg);
+        const EnvSmem& E = (e == e0) ? Es : Eg;
+        double x = 0.0, y = 0.0, yaw = 0.0;
+        bool with_aux = false;
+        if (active) {
+            x = poses[3 * i]; y = poses[3 * i + 1]; yaw = poses[3 * i + 2];
+            with_aux = pose_idx ? ((pose_idx[i] & 1) == 0) : true;
         }
+        const float px = (float)(x - D.origin[0]), py = (float)(y - D.origin[1]);
+        const bool far = fabsf(px) > E.reach || fabsf(py) > E.reach || !(fabs(yaw) < 1e6);
+        float sf, cf;
+        sincosf((float)yaw, &sf, &cf);
+        // ---- body rectangle
+        bool bad = false;
+        unsigned amb = flags;
+        int r = HL_FREE;
+        if (active) r = far ? HL_AMBIG : filter_part(E, px, py, cf, sf, E.ext, flags, &amb);
+        if (r == HL_HIT) bad = true;
+        warp_resolve(r == HL_AMBIG, x, y, yaw, e, D.body_ext, amb, bad, eb, n_exact, lane);
+        // ---- implement rectangles: obstacles + field polygon, never the lane, poses 0,2,4,.. of a path
+        // (orchard_geometry_environment.py:439-456; car_model.py:58)
+        if (flags & HL_CHECK_AUX) {
+            const unsigned aflags = flags & (HL_CHECK_OBSTACLES | HL_CHECK_BOUNDARY);
+            int na = (active && with_aux) ? D.n_aux : 0;
+            int na_max = na;
+            for (int o = 16; o; o >>= 1) na_max = max(na_max, __shfl_xor_sync(0xffffffffu, na_max, o));
+            for (int a = 0; a < na_max; ++a) {
+                const bool mine = a < na && !bad;
+                const double* ext64 = eb.aux64 + 4 * (size_t)(D.aux_off + (a < D.n_aux ? a : 0));
+                unsigned amb2 = aflags;
+                int r2 = HL_FREE;
+                if (mine) {
+                    float ext32[4] = {(float)ext64[0], (float)ext64[1], (float)ext64[2], (float)ext64[3]};
+                    r2 = far ? HL_AMBIG : filter_part(E, px, py, cf, sf, ext32, aflags, &amb2);
+                    if (r2 == HL_HIT) bad = true;
+                }
+                bool bad2 = false;
+                warp_resolve(r2 == HL_AMBIG, x, y, yaw, e, D.n_aux > 0 ? ext64 : D.body_ext, amb2, bad2, eb, n_exact, lane);
+                bad = bad || bad2;
+            }
+        }
+        if (active) out[i] = bad ? 1 : 0;
     }
 }
 

@@ -236,6 +236,138 @@ static __device__ __noinline__ bool exact_part_check(const Pose64& p, const doub
     return false;
 }
 
+// ---- warp-cooperative exact predicates ------------------------------------------------------------
+// Same float64 expressions as the single-thread versions above, evaluated by all 32 lanes of a warp for ONE
+// pose (every lane passes the same arguments): obstacles / polygon edges / capsule half-planes are spread
+// over the lanes and combined with ballots and shuffles.  A single lane needs ~50k instructions for an
+// ambiguous lane-union case; the warp needs ~1.5k.
+__device__ __forceinline__ double warp_max(double v) {
+    for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+    for (int o = 16; o; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+static __device__ __noinline__ bool warp_exact_rect_in_lane(const Pose64& p, const double* ext, const double* cx,
+                                                            const double* cy, const EnvBatchDev& eb, const EnvDesc& e,
+                                                            int lane) {
+    const int S = e.n_seg;
+    const double* segs = eb.seg64 + 4 * (size_t)e.seg_off;
+    const double* polys = eb.seg_poly + 2 * HL_CAPSULE_VERTS * (size_t)e.seg_off;
+    // steps 0/1: corner k in capsule i, one (i, k) pair per lane (S <= 16 -> two rounds of 32)
+    unsigned covered = 0;
+    bool one_holds_all = false;
+    for (int base = 0; base < 4 * S; base += 32) {
+        const int q = base + lane;
+        bool in = false;
+        if (q < 4 * S) {
+            const int i = q >> 2, k = q & 3;
+            in = exact_point_in_capsule(segs + 4 * i, polys + 2 * HL_CAPSULE_VERTS * i, cx[k], cy[k], false);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, in);
+        for (int i = 0; i < 8; ++i) {
+            const unsigned four = (m >> (4 * i)) & 0xFu;
+            if (four == 0xFu) one_holds_all = true;
+            covered |= four;
+        }
+    }
+    if (one_holds_all) return true;
+    if (covered != 0xFu) return false;
+    // step 2: every rectangle edge covered by the union of clip intervals; the 66 half-planes of a capsule
+    // are spread over the lanes (j = lane, lane+32, lane+64)
+    for (int k = 0; k < 4; ++k) {
+        const int k2 = (k + 1) & 3;
+        double lo_s[HL_MAX_SEGS], hi_s[HL_MAX_SEGS];
+        int ni = 0;
+        for (int i = 0; i < S; ++i) {
+            const double* poly = polys + 2 * HL_CAPSULE_VERTS * i;
+            double lo = 0.0, hi = 1.0;
+            int dead = 0;
+            for (int j = lane; j < HL_CAPSULE_VERTS; j += 32) {
+                const double g0 = capsule_halfplane(poly, j, cx[k], cy[k]);
+                const double g1 = capsule_halfplane(poly, j, cx[k2], cy[k2]);
+                if (g0 <= 0.0 && g1 <= 0.0) continue;
+                if (g0 > 0.0 && g1 > 0.0) { dead = 1; continue; }
+                const double tc = xdiv(g0, xsub(g0, g1));
+                if (g0 > 0.0) lo = fmax(lo, tc); else hi = fmin(hi, tc);
+            }
+            dead = __any_sync(0xffffffffu, dead);
+            lo = warp_max(lo);
+            hi = warp_min(hi);
+            if (!dead && lo <= hi) {
+                int q = ni++;                    // insertion sort by (lo, hi), identical on every lane
+                while (q > 0 && (lo_s[q - 1] > lo || (lo_s[q - 1] == lo && hi_s[q - 1] > hi))) {
+                    lo_s[q] = lo_s[q - 1]; hi_s[q] = hi_s[q - 1]; --q;
+                }
+                lo_s[q] = lo; hi_s[q] = hi;
+            }
+        }
+        double cover = 0.0;
+        for (int q = 0; q < ni; ++q) {
+            if (lo_s[q] > cover) return false;
+            cover = fmax(cover, hi_s[q]);
+        }
+        if (cover < 1.0) return false;
+    }
+    // step 3: vertices of the union boundary strictly inside the rectangle
+    const double* crit = eb.crit64 + 2 * (size_t)e.crit_off;
+    int inside = 0;
+    for (int q = lane; q < e.n_crit; q += 32) {
+        double u, w;
+        exact_local(p, crit[2 * q], crit[2 * q + 1], u, w);
+        if (u > ext[0] && u < ext[1] && w > ext[2] && w < ext[3]) inside = 1;
+    }
+    return !__any_sync(0xffffffffu, inside);
+}
+
+// Full exact check of one rectangle at one pose, by the whole warp.  Returns true = infeasible (uniform).
+static __device__ __noinline__ bool warp_exact_part_check(const Pose64& p, const double* ext, const EnvBatchDev& eb,
+                                                          const EnvDesc& e, unsigned flags, int lane) {
+    double cx[4], cy[4];
+    exact_corners(p, ext, cx, cy);
+    if (flags & HL_CHECK_OBSTACLES) {
+        const double* V = eb.obs64 + 8 * (size_t)e.obs_off;
+        int hit = 0;
+        for (int k = lane; k < e.n_obs; k += 32)
+            if (exact_rect_hits_quad(p, ext, cx, cy, V + 8 * k)) hit = 1;
+        if (__any_sync(0xffffffffu, hit)) return true;
+    }
+    if (flags & HL_CHECK_BOUNDARY) {
+        // one polygon edge per lane: crossing parity and on-edge test of the 4 corners, edge vs open rectangle
+        const double* poly = eb.field64 + 2 * (size_t)e.field_off;
+        const int n = e.n_field;
+        unsigned par = 0, on = 0;
+        int cut = 0;
+        for (int i = lane; i < n; i += 32) {
+            const int j = (i + 1 == n) ? 0 : i + 1;
+            const double ax = poly[2 * i], ay = poly[2 * i + 1], bx = poly[2 * j], by = poly[2 * j + 1];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double px = cx[k], py = cy[k];
+                const double cross = xsub(xmul(xsub(bx, ax), xsub(py, ay)), xmul(xsub(by, ay), xsub(px, ax)));
+                if (cross == 0.0 && px >= fmin(ax, bx) && px <= fmax(ax, bx) && py >= fmin(ay, by) && py <= fmax(ay, by))
+                    on |= 1u << k;
+                if ((ay > py) != (by > py)) {
+                    const double xint = xadd(xdiv(xmul(xsub(bx, ax), xsub(py, ay)), xsub(by, ay)), ax);
+                    if (px < xint) par ^= 1u << k;
+                }
+            }
+            double ua, wa, ub, wb;
+            exact_local(p, ax, ay, ua, wa);
+            exact_local(p, bx, by, ub, wb);
+            if (exact_seg_meets_open_rect(ua, wa, ub, wb, ext)) cut = 1;
+        }
+        for (int o = 16; o; o >>= 1) { par ^= __shfl_xor_sync(0xffffffffu, par, o); on |= __shfl_xor_sync(0xffffffffu, on, o); }
+        if (((par | on) & 0xFu) != 0xFu) return true;            // some corner outside the closed polygon
+        if (__any_sync(0xffffffffu, cut)) return true;
+    }
+    if ((flags & HL_CHECK_LANE) && e.n_seg > 0)
+        if (!warp_exact_rect_in_lane(p, ext, cx, cy, eb, e, lane)) return true;
+    return false;
+}
+
 // ------------------------------------------------------------------- float32
 // Environment staged in shared memory for the float32 filter.
 struct EnvSmem {
