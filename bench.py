@@ -223,10 +223,14 @@ def main():
 
     # ---------------- secondary: stand-alone collision kernel (M2) on the canonical scenario
     coll = None
+    coll_paths = None
     fp32_peak = None
     if rank == 0:
         fp32_peak = ops.measure_fp32_peak(local_rank)
         coll = collision_microbench(args, dev, fp32_peak)
+        args.collision_mode = "paths"
+        args.collision_poses = min(args.collision_poses, 1 << 23)
+        coll_paths = collision_microbench(args, dev, fp32_peak)
 
     # ---------------- CPU baseline (rank 0, N = 1 only)
     cpu = None
@@ -258,7 +262,7 @@ def main():
                          "note": "no tensor cores on this path; algorithmic flop = executed footprint checks x "
                                  "F_check (SURVEY 8d); peak = FFMA micro-benchmark measured in this run; the kernel "
                                  "is a latency-bound search, see kernels.k_collision for the ALU-bound kernel"},
-            "kernels": {"k_collision": coll},
+            "kernels": {"k_collision": coll, "k_collision_path_ordered": coll_paths},
             "search": {"expansions": expansions, "pose_checks": n_checks, "exact_escalations": n_exact,
                        "status": status_hist},
         }
@@ -291,11 +295,30 @@ def collision_microbench(args, dev, fp32_peak):
     envs = EnvBatch([make_record(env, car, heur)])
     n = args.collision_poses
     g = torch.Generator(device=dev).manual_seed(0)
-    poses = torch.empty((n, 3), dtype=torch.float64, device=dev)
-    poses[:, 0] = torch.rand(n, generator=g, device=dev, dtype=torch.float64) * 14.0 - 10.0
-    poses[:, 1] = torch.rand(n, generator=g, device=dev, dtype=torch.float64) * 22.0 - 2.0
-    poses[:, 2] = (torch.rand(n, generator=g, device=dev, dtype=torch.float64) * 2.0 - 1.0) * math.pi
-    flags = ops.CHECK_OBSTACLES | ops.CHECK_BOUNDARY | ops.CHECK_LANE
+    if getattr(args, "collision_mode", "random") == "paths":
+        # poses in PATH order (what check_path_feasibility sees): Reeds-Shepp words between random headland
+        # poses, sampled on the GPU at 0.1 m (hl_rs_all_paths + hl_rs_sample), concatenated
+        rng = np.random.default_rng(0)
+        n_pairs = max(1024, n // 640)
+        sg = np.empty((n_pairs, 6))
+        sg[:, [0, 3]] = rng.uniform(-8.0, 1.0, (n_pairs, 2))
+        sg[:, [1, 4]] = rng.uniform(0.0, 18.0, (n_pairs, 2))
+        sg[:, [2, 5]] = rng.uniform(-math.pi, math.pi, (n_pairs, 2))
+        words, count, _ = ops.rs_all_paths(sg, car.curvature, 0.1, want_order=False)
+        w = ops.rs_words_to_host(words)
+        cnt = count.cpu().numpy()
+        sel = [(i, k) for i in range(n_pairs) for k in range(cnt[i])]
+        starts = np.array([sg[i, :3] for i, _ in sel])
+        wsel = np.array([w[i, k] for i, k in sel])
+        _, px, py, pyaw, _, _ = ops.rs_sample(starts, wsel, car.curvature, 0.1)
+        poses = torch.from_numpy(np.stack([px, py, pyaw], axis=1)[:n].copy()).to(dev)
+        n = poses.shape[0]
+    else:
+        poses = torch.empty((n, 3), dtype=torch.float64, device=dev)
+        poses[:, 0] = torch.rand(n, generator=g, device=dev, dtype=torch.float64) * 14.0 - 10.0
+        poses[:, 1] = torch.rand(n, generator=g, device=dev, dtype=torch.float64) * 22.0 - 2.0
+        poses[:, 2] = (torch.rand(n, generator=g, device=dev, dtype=torch.float64) * 2.0 - 1.0) * math.pi
+    flags = int(os.environ.get("HL_K1_FLAGS", ops.CHECK_OBSTACLES | ops.CHECK_BOUNDARY | ops.CHECK_LANE))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     for _ in range(3):
         out, nex = ops.collision_check(envs, poses, flags=flags, count_exact=True)
@@ -315,6 +338,7 @@ def collision_microbench(args, dev, fp32_peak):
     checks = n / (ms * 1e-3)
     achieved = checks * f_check * 1e-12
     return {"metric": "footprint_collision_checks_per_sec", "value": checks, "unit": "checks/s", "poses": n,
+            "pose_order": getattr(args, "collision_mode", "random"),
             "ms_per_launch": ms, "f_check_flop": f_check, "infeasible_frac": float(out.float().mean().item()),
             "exact_escalation_frac": float(nex.item()) / n,
             "roofline": {"bound": "alu_fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",

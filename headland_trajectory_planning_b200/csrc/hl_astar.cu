@@ -420,7 +420,8 @@ k_hybrid_astar_w(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                     if (j < npts) {
                         float fx, fy, fc, fs;
                         rs_sample_world32(plan, j, inv_maxc, fx, fy, fc, fs);
-                        if (fabsf(fx) > Ers.reach || fabsf(fy) > Ers.reach) { st = HL_AMBIG; amb = FLAGS; }
+                        if (fabsf(fx) > Ers.reach || fabsf(fy) > Ers.reach) st = far_status(FLAGS, Ers.n_seg);
+                        else if (!(fx == fx) || !(fy == fy) || !(fc == fc)) { st = HL_AMBIG; amb = FLAGS; }
                         else st = filter_part(Ers, fx, fy, fc, fs, Ers.ext, FLAGS, &amb);
                     }
                     const unsigned livem = __ballot_sync(FULL, j < npts);

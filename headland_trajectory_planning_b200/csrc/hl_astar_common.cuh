@@ -179,7 +179,8 @@ __device__ __noinline__ void heap_set(const AsWs& w, int& n, int slot, double pr
 __device__ HL_CODE int pose_filter(const EnvDesc& D, const EnvSmem& E, double x, double y, double yaw,
                                            unsigned flags, unsigned* amb) {
     float px = (float)(x - D.origin[0]), py = (float)(y - D.origin[1]);
-    if (fabsf(px) > E.reach || fabsf(py) > E.reach || !(fabs(yaw) < 1e6)) { *amb = flags; return HL_AMBIG; }
+    if (fabsf(px) > E.reach || fabsf(py) > E.reach) return far_status(flags, E.n_seg);
+    if (!(fabs(yaw) < 1e6) || !(px == px) || !(py == py)) { *amb = flags; return HL_AMBIG; }
     float sf, cf;
     sincosf((float)yaw, &sf, &cf);
     return filter_part(E, px, py, cf, sf, E.ext, flags, amb);

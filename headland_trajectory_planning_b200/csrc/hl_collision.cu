@@ -72,21 +72,22 @@ k_collision(EnvBatchDev eb, const int32_t* __restrict__ env_id, const double* __
             with_aux = pose_idx ? ((pose_idx[i] & 1) == 0) : true;
         }
         const float px = (float)(x - D.origin[0]), py = (float)(y - D.origin[1]);
-        const bool far = fabsf(px) > E.reach || fabsf(py) > E.reach || !(fabs(yaw) < 1e6);
+        const bool beyond = fabsf(px) > E.reach || fabsf(py) > E.reach;    // decided without a test (far_status)
+        const bool far = !beyond && (!(fabs(yaw) < 1e6) || !(px == px) || !(py == py));
         float sf, cf;
         sincosf((float)yaw, &sf, &cf);
         // ---- body rectangle
         bool bad = false;
         unsigned amb = flags;
         int r = HL_FREE;
-        if (active) r = far ? HL_AMBIG : filter_part(E, px, py, cf, sf, E.ext, flags, &amb);
+        if (active) r = beyond ? far_status(flags, E.n_seg) : (far ? HL_AMBIG : filter_part(E, px, py, cf, sf, E.ext, flags, &amb));
         if (r == HL_HIT) bad = true;
         warp_resolve(r == HL_AMBIG, x, y, yaw, e, D.body_ext, amb, bad, eb, n_exact, lane);
         // ---- implement rectangles: obstacles + field polygon, never the lane, poses 0,2,4,.. of a path
         // (orchard_geometry_environment.py:439-456; car_model.py:58)
         if (flags & HL_CHECK_AUX) {
             const unsigned aflags = flags & (HL_CHECK_OBSTACLES | HL_CHECK_BOUNDARY);
-            int na = (active && with_aux) ? D.n_aux : 0;
+            int na = (active && with_aux && !beyond) ? D.n_aux : 0;
             int na_max = na;
             for (int o = 16; o; o >>= 1) na_max = max(na_max, __shfl_xor_sync(0xffffffffu, na_max, o));
             for (int a = 0; a < na_max; ++a) {

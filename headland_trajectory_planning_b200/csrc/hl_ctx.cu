@@ -117,7 +117,13 @@ extern "C" int hl_env_upload(hl_ctx* ctx, const HlEnvHost* h, int32_t n_env, hl_
         D.origin[0] = 0.5 * (lo[0] + hi[0]);
         D.origin[1] = 0.5 * (lo[1] + hi[1]);
         double extent = 0.5 * fmax(hi[0] - lo[0], hi[1] - lo[1]) * 1.4142135623730951;
-        double reach = extent + 16.0;
+        double foot = 0.0;                                    // farthest footprint corner from the base link
+        for (int k = 0; k < 4; k += 2) foot = fmax(foot, hypot(fmax(fabs(E.body_ext[0]), fabs(E.body_ext[1])), fmax(fabs(E.body_ext[2]), fabs(E.body_ext[3]))));
+        for (int a = 0; a < E.n_aux; ++a) {
+            const double* x = E.aux_ext + 4 * a;
+            foot = fmax(foot, hypot(fmax(fabs(x[0]), fabs(x[1])), fmax(fabs(x[2]), fabs(x[3]))));
+        }
+        double reach = extent + 6.0 + foot + 4.0;            // lane radius 6 m (reference_line_heuristic.py:66) + margin
         D.reach = (float)reach;
         D.eps = (float)(32.0 * 1.1920929e-07 * fmax(reach, 8.0));
         D.all_rect = 1; D.pad0 = 0;

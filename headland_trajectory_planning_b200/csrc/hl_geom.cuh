@@ -12,6 +12,14 @@
 
 enum { HL_FREE = 0, HL_HIT = 1, HL_AMBIG = 2 };
 
+// A pose whose reference point is farther than EnvDesc.reach from the centre of the environment's bounding
+// box (reach = half diagonal of all geometry + lane radius + footprint reach + margin, hl_env_upload) cannot
+// touch an obstacle and lies wholly outside the field polygon and every lane capsule: no test needed.
+// Long Reeds-Shepp words (hundreds of metres) produce thousands of such poses.
+__device__ __forceinline__ int far_status(unsigned flags, int n_seg) {
+    return ((flags & HL_CHECK_BOUNDARY) || ((flags & HL_CHECK_LANE) && n_seg > 0)) ? HL_HIT : HL_FREE;
+}
+
 #define HL_LANE_R 6.0
 // 6*m_cos(pi/64): radius of the circle inscribed in the 16-segments-per-quadrant cap
 #define HL_LANE_RIN 5.992771509254837
@@ -628,7 +636,8 @@ static __device__ bool pose_infeasible(const EnvBatchDev& eb, const EnvDesc& D, 
                                 double x, double y, double yaw, bool with_aux, unsigned flags,
                                 unsigned long long* n_exact) {
     float px = (float)(x - D.origin[0]), py = (float)(y - D.origin[1]);
-    bool far = fabsf(px) > E.reach || fabsf(py) > E.reach || !(fabs(yaw) < 1e6);
+    if (fabsf(px) > E.reach || fabsf(py) > E.reach) return far_status(flags, E.n_seg) == HL_HIT;
+    bool far = !(fabs(yaw) < 1e6) || !(px == px) || !(py == py);       // NaN / absurd input: exact path decides
     float sf, cf;
     sincosf((float)yaw, &sf, &cf);
     unsigned amb = flags;
