@@ -39,7 +39,10 @@ __device__ __forceinline__ void warp_resolve(bool need, double x, double y, doub
     }
 }
 
-__global__ void __launch_bounds__(K1_THREADS, 3)
+#ifndef K1_MIN_CTAS
+#define K1_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(K1_THREADS, K1_MIN_CTAS)
 k_collision(EnvBatchDev eb, const int32_t* __restrict__ env_id, const double* __restrict__ poses,
             const int32_t* __restrict__ pose_idx, long long n, unsigned flags,
             uint8_t* __restrict__ out, unsigned long long* n_exact, int smem_floats) {
@@ -49,6 +52,13 @@ k_collision(EnvBatchDev eb, const int32_t* __restrict__ env_id, const double* __
     int staged_env = -1;
     EnvSmem Es;
     bool staged = false;
+    // software pipeline: the pose of the NEXT tile is loaded before this tile's arithmetic starts, so the
+    // HBM latency of the (only) streaming input overlaps ~1.4k instructions of filter work
+    double nx = 0.0, ny = 0.0, nyaw = 0.0;
+    {
+        const long long i0 = (long long)blockIdx.x * K1_THREADS + threadIdx.x;
+        if (blockIdx.x < n_tiles && i0 < n) { nx = poses[3 * i0]; ny = poses[3 * i0 + 1]; nyaw = poses[3 * i0 + 2]; }
+    }
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         long long base = tile * K1_THREADS;
         int e0 = env_id ? env_id[base] : 0;
@@ -65,12 +75,13 @@ k_collision(EnvBatchDev eb, const int32_t* __restrict__ env_id, const double* __
         EnvSmem Eg;
         if (e != e0) global_env(eb, D, Eg);
         const EnvSmem& E = (e == e0) ? Es : Eg;
-        double x = 0.0, y = 0.0, yaw = 0.0;
-        bool with_aux = false;
-        if (active) {
-            x = poses[3 * i]; y = poses[3 * i + 1]; yaw = poses[3 * i + 2];
-            with_aux = pose_idx ? ((pose_idx[i] & 1) == 0) : true;
+        const double x = nx, y = ny, yaw = nyaw;
+        {
+            const long long in = (tile + gridDim.x) * K1_THREADS + threadIdx.x;
+            if (tile + gridDim.x < n_tiles && in < n) { nx = poses[3 * in]; ny = poses[3 * in + 1]; nyaw = poses[3 * in + 2]; }
         }
+        bool with_aux = false;
+        if (active) with_aux = pose_idx ? ((pose_idx[i] & 1) == 0) : true;
         const float px = (float)(x - D.origin[0]), py = (float)(y - D.origin[1]);
         const bool beyond = fabsf(px) > E.reach || fabsf(py) > E.reach;    // decided without a test (far_status)
         const bool far = !beyond && (!(fabs(yaw) < 1e6) || !(px == px) || !(py == py));

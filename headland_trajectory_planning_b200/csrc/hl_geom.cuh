@@ -496,6 +496,7 @@ static __device__ HL_CODE int filter_part(const EnvSmem& E, float px, float py, 
     }
     if (flags & HL_CHECK_BOUNDARY) {
         const int n = E.n_field;
+        const float rho_eps = sqrtf(fmaf(hx, hx, hy * hy)) + eps;
         bool inside = false;
         unsigned near_mask = 0;                       // edges whose LINE the rectangle may touch (n <= 32 here)
         bool overflow = false;
@@ -509,10 +510,12 @@ static __device__ HL_CODE int filter_part(const EnvSmem& E, float px, float py, 
             const bool straddle = (r0.y > Cy) != (r1.w > Cy);
             const float lhs = (Cx - r0.x) * r0.w, rhs = r0.z * dyc;
             inside ^= straddle && ((r0.w > 0.0f) ? (lhs < rhs) : (lhs > rhs));
-            const float nu = fmaf(r1.x, c, r1.y * s), nv = fmaf(r1.y, c, -r1.x * s);      // n.u, n.v
             const float sd = fmaf(r1.x, Cx, fmaf(r1.y, Cy, -r1.z));                      // signed distance to the line
-            const float rn = fmaf(hx, fabsf(nu), hy * fabsf(nv));                        // support radius along n
-            if (!(fabsf(sd) > rn + eps)) { if (i < 32) near_mask |= 1u << i; else overflow = true; }
+            if (!(fabsf(sd) > rho_eps)) {                     // within the circumradius: use the exact support radius
+                const float nu = fmaf(r1.x, c, r1.y * s), nv = fmaf(r1.y, c, -r1.x * s);  // n.u, n.v
+                const float rn = fmaf(hx, fabsf(nu), hy * fabsf(nv));                    // support radius along n
+                if (!(fabsf(sd) > rn + eps)) { if (i < 32) near_mask |= 1u << i; else overflow = true; }
+            }
         }
         bool all_clear = !overflow, cut = false;
         while (near_mask) {                           // second stage, only for the few nearby edges of this lane
