@@ -13,6 +13,7 @@
 // scenarios, and two CTA-wide alignment barriers per expansion keep all warps of the SM inside the same
 // code region, so an instruction line fetched once serves AW_WARPS scenarios.  Warps pull scenario ids from
 // an atomic counter as soon as theirs finishes.
+#include <cstdlib>
 #include "hl_astar_common.cuh"
 
 #ifndef AW_WARPS
@@ -599,6 +600,8 @@ k_hybrid_astar_w(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
     }
 }
 
+#include "hl_astar_spec.cuh"
+
 // ------------------------------------------------------------------------------ host side
 static void fill_params(const hl_ctx* ctx, const HlSearchParams* h, AsParams& P) {
     memset(&P, 0, sizeof(P));
@@ -652,20 +655,31 @@ extern "C" int hl_hybrid_astar_batch(hl_ctx* ctx, const hl_env_batch* envs, cons
     HL_CUDA_OK(cudaSetDevice(ctx->device));
     AsParams P;
     fill_params(ctx, h_params, P);
-    const size_t smem = astar_smem();
+    // variant: "spec" = two warps per scenario with the analytic shot decoupled (hl_astar_spec.cuh),
+    // "warp" = one warp per scenario.  HL_ASTAR_VARIANT overrides the default for A/B runs.
+    const char* var = getenv("HL_ASTAR_VARIANT");
+    const bool spec = var ? (strcmp(var, "warp") != 0) : true;
+    const int slots = spec ? AQ_SLOTS : AW_WARPS;
+    const int threads = spec ? AQ_SLOTS * 64 : AW_WARPS * 32;
+    const size_t smem = spec ? sizeof(AqSmem) * AQ_SLOTS : astar_smem();
     if ((int)smem > ctx->max_smem_optin) {
         hl_set_error("hl_hybrid_astar_batch: %zu B of shared memory per CTA exceed the device limit %d", smem, ctx->max_smem_optin);
         return 1;
     }
-    HL_CUDA_OK(cudaFuncSetAttribute(k_hybrid_astar_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    HL_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_hybrid_astar_w, AW_WARPS * 32, smem));
+    if (spec) {
+        HL_CUDA_OK(cudaFuncSetAttribute(k_hybrid_astar_s, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HL_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_hybrid_astar_s, threads, smem));
+    } else {
+        HL_CUDA_OK(cudaFuncSetAttribute(k_hybrid_astar_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HL_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_hybrid_astar_w, threads, smem));
+    }
     if (per_sm < 1) per_sm = 1;
-    long long want = ((long long)n_scen + AW_WARPS - 1) / AW_WARPS;
+    long long want = ((long long)n_scen + slots - 1) / slots;
     long long cap = (long long)ctx->sm_count * per_sm;
     const int grid = (int)(want < cap ? want : cap);
     const size_t stride = as_ws_bytes(P.cap_nodes, P.hash_size, P.max_nodes);
-    const size_t need = stride * (size_t)grid * AW_WARPS;
+    const size_t need = stride * (size_t)grid * slots;
     if (need > ctx->astar_ws_bytes) {
         if (ctx->astar_ws) cudaFree(ctx->astar_ws);
         ctx->astar_ws = nullptr; ctx->astar_ws_bytes = 0;
@@ -682,8 +696,12 @@ extern "C" int hl_hybrid_astar_batch(hl_ctx* ctx, const hl_env_batch* envs, cons
     O.path_x = d_path_x; O.path_y = d_path_y; O.path_yaw = d_path_yaw; O.path_k = d_path_k; O.path_dir = d_path_dir;
     O.path_capacity = (long long)path_capacity; O.path_cursor = d_path_cursor;
     O.phase_cycles = (unsigned long long*)(ctx->d_counters + 16);
-    k_hybrid_astar_w<<<grid, AW_WARPS * 32, smem, st>>>(envs->dev, d_scen, n_scen, P, (char*)ctx->astar_ws, stride,
-                                                        ctx->d_counters, O);
+    if (spec)
+        k_hybrid_astar_s<<<grid, threads, smem, st>>>(envs->dev, d_scen, n_scen, P, (char*)ctx->astar_ws, stride,
+                                                      ctx->d_counters, O);
+    else
+        k_hybrid_astar_w<<<grid, threads, smem, st>>>(envs->dev, d_scen, n_scen, P, (char*)ctx->astar_ws, stride,
+                                                      ctx->d_counters, O);
     HL_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -1,0 +1,630 @@
+// hl_astar_spec.cuh -- K4 variant C: two warps per scenario, speculative decoupling of the analytic shot.
+//
+// In the reference every popped node first gets a Reeds-Shepp shot and is expanded only if the shot fails
+// (hybrid_a_star_search.py:542-596).  A FAILED shot has no side effect, and a successful one ends the search
+// with a result that depends only on nodes closed up to that pop (closed nodes are immutable).  So the two
+// halves of an expansion can run concurrently and even out of step:
+//   * the EXPANDER warp pops, tests the tolerance arrival, rolls out / checks / costs / merges the
+//     primitives and keeps going, assuming shots fail (true for 400 of 401 pops of a hard scenario);
+//   * the SHOOTER warp walks the closed list in pop order and evaluates the shot of each node;
+//   * if the shooter finds a free word at pop i the search ends THERE: the record is truncated to the first
+//     i+1 closed nodes, exactly what the reference returns; the expander's extra work is discarded.
+// The critical path per pop becomes max(shot, expansion) instead of their sum.
+#pragma once
+#include "hl_astar_common.cuh"
+
+#ifndef AQ_SLOTS
+#define AQ_SLOTS 6                     // scenarios per CTA (2 warps each)
+#endif
+#define AQ_MAX_PLANS 6
+
+struct AqSmem {                          // one per scenario slot, shared by its two warps
+    double start[3], goal[3];
+    long long start_key, goal_key;
+    int env, scen;
+    volatile int state;                  // ST_IDLE / ST_SEARCH / ST_DONE (written by the expander)
+    volatile int epoch;                  // bumped by the expander when a scenario is ready for the shooter
+    volatile int popped;                 // closed nodes published to the shooter
+    volatile int ew_done;                // expander stopped; shots needed for nodes < shot_limit
+    volatile int shot_limit;
+    volatile int shot_success;           // pop index of the first free word, or -1
+    volatile int sw_done;                // shooter finished this epoch
+    // expander state
+    int n_nodes, heap_n, counter, n_closed, ew_status, ew_arrival2;
+    int cur; double cx, cy, cyaw, cg; int cprim; int nsteps;
+    // shooter state
+    int s_cur; double sx, sy, syaw, sg;
+    double rs_lens[HL_RS_CANDIDATES][HL_RS_MAX_SEGS];
+    double rs_L[HL_RS_CANDIDATES], rs_prio[HL_RS_CANDIDATES], rs_Lc[HL_RS_CANDIDATES];
+    int rs_acc[HL_RS_CANDIDATES], rs_order[HL_RS_CANDIDATES];
+    unsigned char rs_valid[HL_RS_CANDIDATES + 2], rs_accept[HL_RS_CANDIDATES + 2];
+    RsProblem rs_prob;
+    int rs_n, rs_pick, rs_word, rs_assert;
+    double rs_goal_cost;
+    RsPlan plans[AQ_MAX_PLANS];
+    RsPlan plan_tmp;
+    // expander scratch
+    double tx[HL_MAX_PRIMS][AS_ROLL], ty[HL_MAX_PRIMS][AS_ROLL], pyaw[HL_MAX_PRIMS][AS_ROLL];
+    unsigned char pamb[HL_MAX_PRIMS][AS_ROLL];
+    int phit[HL_MAX_PRIMS];
+    double pg[HL_MAX_PRIMS], pprio[HL_MAX_PRIMS];
+    long long pkey[HL_MAX_PRIMS];
+    int pkey_ok[HL_MAX_PRIMS], pslot[HL_MAX_PRIMS], ppos[HL_MAX_PRIMS], pneed[HL_MAX_PRIMS];
+    // stats (per role)
+    unsigned long long e_checks, e_exact, s_checks, s_exact;
+    long long t0;
+    // result assembly
+    int status, arrival, fin_closed, fin_counter, chain_len, path_len;
+    double goal_cost;
+    long long path_off;
+    __align__(16) float envf[AW_ENV_FLOATS];
+};
+static_assert(sizeof(AqSmem) * AQ_SLOTS <= 227 * 1024, "per-CTA shared memory exceeds 227 KB");
+
+// Alignment of the AQ_SLOTS warps of one role (named barrier `id`, all threads of those warps) with an AND
+// reduction: keeps the role's warps inside the same code region (instruction cache) and tells them when
+// every one of them is finished.
+__device__ __forceinline__ bool role_barrier_all(int id, bool pred) {
+    int r;
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.s32 p, %1, 0;\n\tbarrier.red.and.pred q, %2, %3, p;\n\tselp.s32 %0, 1, 0, q;\n\t}"
+                 : "=r"(r) : "r"((int)pred), "r"(id), "r"(AQ_SLOTS * 32) : "memory");
+    return r != 0;
+}
+
+__device__ __forceinline__ int warp_read(volatile int* p, int lane) {
+    int v = 0;
+    if (lane == 0) v = *p;
+    return __shfl_sync(FULL, v, 0);
+}
+
+// Result record + path of a finished scenario (expander warp, after the shooter reported).
+__device__ __noinline__ void finalize_spec(AqSmem& S, const AsWs& W, const AsParams& P, const AwOut& O, int lane) {
+    const int sc = S.scen;
+    const int n_closed = S.fin_closed;
+    long long koff = 0;
+    if (lane == 0 && n_closed > 0) {
+        koff = (long long)atomicAdd(O.keys_cursor, (unsigned long long)n_closed);
+        if (koff + n_closed > O.keys_capacity) koff = -1;
+    }
+    koff = __shfl_sync(FULL, koff, 0);
+    int nk = n_closed;
+    if (koff < 0) { if (lane == 0) S.status = HL_STATUS_CAPACITY; nk = 0; koff = 0; }
+    __syncwarp();
+    {
+        int32_t* ek = O.expanded_keys + (size_t)koff * 3;
+        for (int i = lane; i < nk; i += 32) {
+            int ix, iy, iw;
+            unpack_key(W.nkey[W.corder[i]], ix, iy, iw);
+            ek[3 * i] = ix; ek[3 * i + 1] = iy; ek[3 * i + 2] = iw;
+        }
+    }
+    const int cur = (n_closed > 0) ? W.corder[n_closed - 1] : 0;       // the node the search ended on
+    if (lane == 0 && S.status == HL_STATUS_OK) {
+        int len = 0, poses = 0, rs_pts = 0;
+        bool ok = true;
+        if (S.goal_key != S.start_key) {
+            for (int node = cur; node != 0; node = W.nparent[node]) {
+                if (len >= P.cap_nodes) { ok = false; break; }
+                W.hslot[len++] = node;                                   // the heap is dead by now
+                poses += W.nsteps[node] + 1;
+            }
+            if (S.arrival == 1) rs_pts = (S.rs_pick < AQ_MAX_PLANS ? S.plans[S.rs_pick] : S.plan_tmp).npts;
+        }
+        S.chain_len = len;
+        S.path_len = poses + rs_pts;
+        if (!ok || S.path_len > P.max_path_poses) { S.status = HL_STATUS_CAPACITY; S.path_len = 0; }
+        else if (S.path_len > 0) {
+            unsigned long long off = atomicAdd(O.path_cursor, (unsigned long long)S.path_len);
+            if ((long long)(off + S.path_len) > O.path_capacity) { S.status = HL_STATUS_CAPACITY; S.path_len = 0; }
+            S.path_off = (long long)off;
+        }
+    }
+    __syncwarp();
+    if (S.status == HL_STATUS_OK && S.path_len > 0) {
+        const int len = S.chain_len;
+        for (int c = lane; c < len; c += 32) {
+            const int node = W.hslot[len - 1 - c];
+            long long off = S.path_off;
+            for (int q = 0; q < c; ++q) off += W.nsteps[W.hslot[len - 1 - q]] + 1;
+            const int par = W.nparent[node];
+            const int p = W.nprim[node], n = W.nsteps[node];
+            const double ys = P.yaw_step[p];
+            const double init_yaw = angle_wrap(xadd(W.nyaw[par], ys));
+            const double stop = xadd(init_yaw, xmul(ys, (double)(n + 1)));
+            const double delta = xsub(stop, init_yaw);
+            const double step = xdiv(delta, (double)(n + 1));
+            double ax = 0.0, ay = 0.0;
+            for (int i = 0; i <= n; ++i) {
+                const double yw = rollout_yaw(init_yaw, stop, step, delta, n + 1, i);
+                const double txv = xmul(xmul(P.res, m_cos(yw)), P.dir[p]);
+                const double tyv = xmul(xmul(P.res, m_sin(yw)), P.dir[p]);
+                ax = (i == 0) ? txv : xadd(ax, txv);
+                ay = (i == 0) ? tyv : xadd(ay, tyv);
+                O.path_x[off + i] = xadd(W.nx[par], ax);
+                O.path_y[off + i] = xadd(W.ny[par], ay);
+                O.path_yaw[off + i] = rollout_yaw(init_yaw, stop, step, delta, n + 1, i + 1);
+                O.path_k[off + i] = P.curv[p];
+                O.path_dir[off + i] = (int8_t)P.dir[p];
+            }
+        }
+        if (S.arrival == 1) {
+            const RsPlan& plan = (S.rs_pick < AQ_MAX_PLANS) ? S.plans[S.rs_pick] : S.plan_tmp;
+            const double q0[3] = {W.nx[cur], W.ny[cur], W.nyaw[cur]};
+            const double cq = m_cos(-q0[2]), sq = m_sin(-q0[2]);
+            const long long off = S.path_off + (S.path_len - plan.npts);
+            for (int j = lane; j < plan.npts; j += 32) {
+                double lx, ly, lyaw, wx, wy, wyaw;
+                int cs, dir;
+                rs_sample_local(plan, j, P.maxc, lx, ly, lyaw, cs, dir);
+                rs_to_world(q0, cq, sq, lx, ly, lyaw, wx, wy, wyaw);
+                O.path_x[off + j] = wx; O.path_y[off + j] = wy; O.path_yaw[off + j] = wyaw;
+                O.path_k[off + j] = cs == 0 ? 0.0 : (cs > 0 ? P.maxc : -P.maxc);
+                O.path_dir[off + j] = (int8_t)dir;
+            }
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        HlPlanResult r;
+        r.status = S.status;
+        r.counter = (S.status == HL_STATUS_START_GOAL_BLOCKED) ? 0 : S.fin_counter;
+        r.n_expanded = nk;
+        r.arrival = S.arrival;
+        r.path_len = S.path_len;
+        r.rs_word = (S.arrival == 1) ? S.rs_word : -1;
+        r.path_offset = S.path_off;
+        r.goal_cost = S.goal_cost;
+        r.n_pose_checks = (long long)(S.e_checks + S.s_checks);
+        r.n_exact = (long long)(S.e_exact + S.s_exact);
+        r.keys_offset = koff;
+        r.cycles = clock64() - S.t0;
+        O.results[sc] = r;
+        atomicAdd(O.phase_cycles + PH_OUTPUT, (unsigned long long)r.cycles);
+    }
+    for (int i = lane; i < S.n_nodes; i += 32) W.hkey[W.nhpos[i]] = KEY_EMPTY;
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(AQ_SLOTS * 64, 1)
+k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen, AsParams P, char* ws_base,
+                 size_t ws_stride, unsigned int* work_counter, AwOut O) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int slot = wid >> 1, role = wid & 1;                 // role 0 = expander, 1 = shooter
+    AqSmem& S = reinterpret_cast<AqSmem*>(smem_raw)[slot];
+    const AsWs W = as_carve(ws_base + ((size_t)blockIdx.x * AQ_SLOTS + slot) * ws_stride, P.cap_nodes, P.hash_size,
+                            P.max_nodes);
+    const int hmask = P.hash_size - 1;
+    const unsigned FLAGS = HL_CHECK_OBSTACLES | HL_CHECK_BOUNDARY | HL_CHECK_LANE;
+    if (role == 0) {
+        for (int i = lane; i < P.hash_size; i += 32) W.hkey[i] = KEY_EMPTY;
+        if (lane == 0) { S.state = ST_IDLE; S.epoch = 0; S.sw_done = 0; S.popped = 0; S.ew_done = 0; S.shot_success = -1; }
+    }
+    __syncthreads();
+
+    EnvSmem E;
+    E.n_obs = E.n_field = E.n_seg = E.all_rect = 0; E.eps = 0.f; E.reach = 0.f; E.obs = E.field = E.seg = nullptr;
+
+    if (role == 1) {
+        // =========================================== SHOOTER ===========================================
+        int my_epoch = 0;
+        int i = 0;
+        bool active = false;            // a scenario is attached and its shots are not finished
+        bool finished = false;          // queue drained
+        const EnvDesc* Dp = eb.desc;
+        EnvSmem Ers = E;
+        const float inv_maxc = (float)(1.0 / P.maxc);
+        const double stepn = xmul(P.res, P.maxc);
+        while (true) {
+            if (role_barrier_all(1, finished)) break;              // alignment point of the shooters
+            if (finished) continue;
+            if (!active) {
+                const int st = warp_read(&S.state, lane);
+                const int ep = warp_read(&S.epoch, lane);
+                if (ep != my_epoch) {
+                    my_epoch = ep;
+                    __threadfence_block();
+                    Dp = eb.desc + S.env;
+                    const EnvDesc& D0 = *Dp;
+                    // same float32 environment the expander staged in this slot
+                    const int n_o = D0.n_obs * HL_OBS32_STRIDE, n_f = D0.n_field * HL_FIELD32_STRIDE, n_s = D0.n_seg * 4;
+                    E.n_obs = D0.n_obs; E.n_field = D0.n_field; E.n_seg = D0.n_seg; E.all_rect = D0.all_rect;
+                    E.eps = D0.eps; E.reach = D0.reach;
+                    for (int k = 0; k < 4; ++k) E.ext[k] = (float)D0.body_ext[k];
+                    if (n_o + n_f + n_s <= AW_ENV_FLOATS) { E.obs = S.envf; E.field = S.envf + n_o; E.seg = S.envf + n_o + n_f; }
+                    else {
+                        E.obs = eb.obs32 + (size_t)HL_OBS32_STRIDE * D0.obs_off;
+                        E.field = eb.field32 + HL_FIELD32_STRIDE * (size_t)D0.field_off;
+                        E.seg = eb.seg32 + 4 * (size_t)D0.seg_off;
+                    }
+                    Ers = E;
+                    Ers.eps = E.eps + 6e-5f;
+                    if (lane == 0) { S.s_checks = 0; S.s_exact = 0; S.rs_assert = 0; }
+                    __syncwarp();
+                    i = 0;
+                    active = true;
+                } else if (st == ST_DONE) { finished = true; continue; }
+                else { __nanosleep(200); continue; }
+            }
+            const EnvDesc& D = *Dp;
+            bool success = false;
+            {
+                // is pop i available, or has the expander stopped short of it?
+                const int done = warp_read(&S.ew_done, lane);
+                __threadfence_block();
+                const int popped = warp_read(&S.popped, lane);
+                bool stop = false, have = false;
+                if (done) { if (i >= warp_read(&S.shot_limit, lane)) stop = true; else have = true; }   // limit <= popped
+                else if (popped > i) have = true;
+                if (stop) {
+                    if (lane == 0) { __threadfence_block(); S.sw_done = my_epoch; }
+                    __syncwarp();
+                    active = false;
+                    continue;
+                }
+                if (!have) { __nanosleep(100); continue; }
+                __threadfence_block();
+                if (lane == 0) {
+                    const int cur = W.corder[i];
+                    S.s_cur = cur; S.sx = W.nx[cur]; S.sy = W.ny[cur]; S.syaw = W.nyaw[cur]; S.sg = W.ng[cur];
+                    const double q0n[3] = {S.sx, S.sy, S.syaw};
+                    S.rs_prob = rs_normalise(q0n, S.goal, P.maxc);
+                    S.rs_pick = -1;
+                }
+                __syncwarp();
+                const double q0[3] = {S.sx, S.sy, S.syaw};
+                for (int c = lane; c < HL_RS_CANDIDATES; c += 32) {
+                    double l[HL_RS_MAX_SEGS] = {0, 0, 0, 0, 0};
+                    bool ok = rs_candidate(c, S.rs_prob, l);
+                    S.rs_valid[c] = ok ? 1 : 0;
+                    for (int k = 0; k < HL_RS_MAX_SEGS; ++k) S.rs_lens[c][k] = l[k];
+                }
+                __syncwarp();
+                if (lane < RS_N_GROUPS) rs_select_group(lane, S.rs_valid, S.rs_lens, S.rs_accept, S.rs_Lc);
+                __syncwarp();
+                int m;
+                {
+                    const int a0 = S.rs_accept[lane];
+                    const int a1 = (lane + 32 < HL_RS_CANDIDATES) ? S.rs_accept[lane + 32] : 0;
+                    const unsigned b0 = __ballot_sync(FULL, a0 == 1), b1 = __ballot_sync(FULL, a1 == 1);
+                    const unsigned bad = __ballot_sync(FULL, a0 == 2 || a1 == 2);
+                    const unsigned lt = (1u << lane) - 1u;
+                    const int n0 = __popc(b0);
+                    if (a0 == 1) { int k = __popc(b0 & lt); S.rs_acc[k] = lane; S.rs_L[k] = S.rs_Lc[lane]; }
+                    if (a1 == 1) { int k = n0 + __popc(b1 & lt); S.rs_acc[k] = lane + 32; S.rs_L[k] = S.rs_Lc[lane + 32]; }
+                    m = bad ? 0 : n0 + __popc(b1);
+                    __syncwarp();
+                    for (int k = lane; k < m; k += 32)
+                        S.rs_prio[k] = rs_path_cost(S.sg, S.rs_acc[k], S.rs_lens[S.rs_acc[k]], P.max_steer,
+                                                    P.reverse_cost, P.dir_change_cost, P.steer_cost);
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (bad) S.rs_assert = 1;
+                        S.rs_n = m;
+                        if (m > 0) heapdict_order(S.rs_prio, m, S.rs_order);
+                    }
+                    __syncwarp();
+                    if (bad) success = true;     // the reference would raise here: report it as the end of the search
+                }
+                const double cq = m_cos(-q0[2]), sq = m_sin(-q0[2]);
+                if (lane < m && lane < AQ_MAX_PLANS) {
+                    int c = S.rs_acc[S.rs_order[lane]];
+                    rs_make_plan(c, S.rs_lens[c], P.maxc, stepn, S.plans[lane]);
+                    rs_plan_world32(S.plans[lane], q0, cq, sq, D.origin);
+                }
+                __syncwarp();
+                for (int r = 0; r < m; ++r) {
+                    const int k = S.rs_order[r];
+                    const int c = S.rs_acc[k];
+                    if (r >= AQ_MAX_PLANS) {
+                        __syncwarp();
+                        if (lane == 0) {
+                            rs_make_plan(c, S.rs_lens[c], P.maxc, stepn, S.plan_tmp);
+                            rs_plan_world32(S.plan_tmp, q0, cq, sq, D.origin);
+                        }
+                        __syncwarp();
+                    }
+                    const RsPlan& plan = (r < AQ_MAX_PLANS) ? S.plans[r] : S.plan_tmp;
+                    const int npts = plan.npts;
+                    int infeasible = 0;
+                    const int passes = (npts + 31) >> 5;
+                    for (int pass = 0; pass < passes && !infeasible; ++pass) {
+                        const int j = lane * passes + pass;
+                        int st2 = HL_FREE;
+                        unsigned amb = 0;
+                        if (j < npts) {
+                            float fx, fy, fc, fs;
+                            rs_sample_world32(plan, j, inv_maxc, fx, fy, fc, fs);
+                            if (fabsf(fx) > Ers.reach || fabsf(fy) > Ers.reach) st2 = far_status(FLAGS, Ers.n_seg);
+                            else if (!(fx == fx) || !(fy == fy) || !(fc == fc)) { st2 = HL_AMBIG; amb = FLAGS; }
+                            else st2 = filter_part(Ers, fx, fy, fc, fs, Ers.ext, FLAGS, &amb);
+                        }
+                        const unsigned livem = __ballot_sync(FULL, j < npts);
+                        const unsigned hitm = __ballot_sync(FULL, st2 == HL_HIT);
+                        const unsigned ambm = __ballot_sync(FULL, st2 == HL_AMBIG);
+                        infeasible = hitm != 0;
+                        if (!infeasible && ambm) {
+                            int bad2 = 0;
+                            if (st2 == HL_AMBIG) {
+                                double lx, ly, lyaw, wx, wy, wyaw;
+                                int cs, dir;
+                                rs_sample_local(plan, j, P.maxc, lx, ly, lyaw, cs, dir);
+                                rs_to_world(q0, cq, sq, lx, ly, lyaw, wx, wy, wyaw);
+                                bad2 = pose_exact(eb, D, wx, wy, wyaw, amb) ? 1 : 0;
+                            }
+                            if (lane == 0) S.s_exact += (unsigned long long)__popc(ambm);
+                            infeasible = __any_sync(FULL, bad2);
+                        }
+                        if (lane == 0) S.s_checks += (unsigned long long)__popc(livem);
+                    }
+                    const bool short_enough = xdiv(S.rs_L[k], P.maxc) < P.min_len_goal;
+                    if (!infeasible && short_enough) {
+                        if (lane == 0) { S.rs_pick = r; S.rs_word = c; S.rs_goal_cost = S.rs_prio[k]; }
+                        success = true;
+                        break;
+                    }
+                }
+                __syncwarp();
+            }
+            if (success) {
+                if (lane == 0) { __threadfence_block(); S.shot_success = i; __threadfence_block(); S.sw_done = my_epoch; }
+                __syncwarp();
+                active = false;
+            } else ++i;
+        }
+        return;
+    }
+
+    // ============================================ EXPANDER ============================================
+    // One alignment barrier per loop iteration (role barrier 2): an iteration is either "attach a scenario",
+    // "expand one node" or "wait for the shooter / write the result".
+    int mode = 0;                       // 0 need a scenario, 1 expanding, 2 waiting for the shooter
+    bool finished = false;
+    int my_epoch = 0;
+    const EnvDesc* Dp = eb.desc;
+    while (true) {
+        if (role_barrier_all(2, finished)) break;
+        if (finished) continue;
+        if (mode == 0) {
+        // ---- next scenario
+        int sc = 0;
+        if (lane == 0) sc = (int)atomicAdd(work_counter, 1u);
+        sc = __shfl_sync(FULL, sc, 0);
+        if (sc >= n_scen) { if (lane == 0) { __threadfence_block(); S.state = ST_DONE; } finished = true; continue; }
+        if (lane == 0) {
+            const HlScenario s = scen[sc];
+            S.scen = sc; S.env = s.env_id;
+            for (int k = 0; k < 3; ++k) { S.start[k] = s.start[k]; S.goal[k] = s.goal[k]; }
+            S.n_nodes = 0; S.heap_n = 0; S.counter = 0; S.n_closed = 0;
+            S.status = -1; S.arrival = 0; S.goal_cost = 0.0; S.ew_status = -1; S.ew_arrival2 = 0;
+            S.e_checks = 0; S.e_exact = 0; S.s_checks = 0; S.s_exact = 0;
+            S.path_len = 0; S.path_off = 0; S.chain_len = 0; S.fin_closed = 0; S.fin_counter = 0;
+            S.popped = 0; S.ew_done = 0; S.shot_limit = 0; S.shot_success = -1;
+            S.t0 = clock64();
+        }
+        __syncwarp();
+        Dp = eb.desc + S.env;
+        const EnvDesc& D = *Dp;
+        stage_env_warp(eb, D, S.envf, AW_ENV_FLOATS, E, lane);
+        // start / goal feasibility and start node (shared helper works on an AwSmem-like view)
+        {
+            int bad = 0;
+            if (lane < 2) {
+                const double* q = lane == 0 ? S.start : S.goal;
+                unsigned amb = FLAGS;
+                int r = pose_filter(D, E, q[0], q[1], q[2], FLAGS, &amb);
+                bad = (r == HL_HIT) || (r == HL_AMBIG && pose_exact(eb, D, q[0], q[1], q[2], amb));
+            }
+            bad = __any_sync(FULL, bad);
+            double h = warp_state_cost(eb, D, S.start[0], S.start[1], S.start[2], lane);
+            if (lane == 0) {
+                int ix, iy, iw;
+                long long sk = 0, gk = 0;
+                bool ok = make_key(S.start[0], S.start[1], S.start[2], P.res, P.yaw_res, ix, iy, iw, sk);
+                ok = make_key(S.goal[0], S.goal[1], S.goal[2], P.res, P.yaw_res, ix, iy, iw, gk) && ok;
+                S.start_key = sk; S.goal_key = gk;
+                if (!ok) S.ew_status = HL_STATUS_CAPACITY;
+                else if (bad) S.ew_status = HL_STATUS_START_GOAL_BLOCKED;
+                else {
+                    W.nx[0] = S.start[0]; W.ny[0] = S.start[1]; W.nyaw[0] = S.start[2]; W.ng[0] = 0.0;
+                    W.nkey[0] = sk; W.nparent[0] = 0; W.nprim[0] = -1; W.nsteps[0] = 0; W.nstate[0] = 0;
+                    W.nheap[0] = -1;
+                    int pos;
+                    hash_find(W, hmask, sk, &pos);
+                    W.hkey[pos] = sk; W.hval[pos] = 0; W.nhpos[0] = pos;
+                    S.n_nodes = 1;
+                    double prio = xmul(P.hybrid_cost, h);
+                    prio = (prio > 0.0) ? prio : 0.0;
+                    heap_set(W, S.heap_n, 0, prio);
+                }
+            }
+            __syncwarp();
+        }
+        if (S.ew_status >= 0) {                       // blocked / capacity: no shooter involved
+            if (lane == 0) { S.status = S.ew_status; S.fin_closed = 0; S.fin_counter = 0; }
+            __syncwarp();
+            finalize_spec(S, W, P, O, lane);
+            continue;
+        }
+        // hand the scenario to the shooter
+        if (lane == 0) { __threadfence_block(); S.state = ST_SEARCH; S.epoch = S.epoch + 1; }
+        __syncwarp();
+        my_epoch = warp_read(&S.epoch, lane);
+
+            mode = 1;
+            continue;
+        }
+        const EnvDesc& D = *Dp;
+        if (mode == 1) {
+            if (lane == 0) {
+                if (S.shot_success >= 0) S.ew_status = HL_STATUS_OK;             // the shooter ended the search
+                else if (S.counter > P.max_nodes) S.ew_status = HL_STATUS_MAX_NODES;
+                else {
+                    S.counter += 1;
+                    if (S.heap_n == 0) S.ew_status = HL_STATUS_OPEN_EMPTY;
+                    else {
+                        int cur = heap_popitem(W, S.heap_n);
+                        W.nstate[cur] = 1;
+                        W.corder[S.n_closed++] = cur;
+                        S.cur = cur; S.cx = W.nx[cur]; S.cy = W.ny[cur]; S.cyaw = W.nyaw[cur]; S.cg = W.ng[cur];
+                        S.cprim = W.nprim[cur];
+                        __threadfence_block();
+                        S.popped = S.n_closed;                                   // publish to the shooter
+                        // tolerance arrival (:464-495) ends the search at this pop (if no earlier shot succeeds)
+                        double xd = fabs(xsub(S.cx, S.goal[0])), yd = fabs(xsub(S.cy, S.goal[1]));
+                        double wd = fabs(angle_wrap(xsub(S.cyaw, S.goal[2])));
+                        if (xd < P.res && yd < P.res && wd < P.yaw_res) { S.ew_arrival2 = 1; S.ew_status = HL_STATUS_OK; }
+                        else {
+                            int seg = exact_search_segment(eb, D, S.cx, S.cy);
+                            double len = seg < 0 ? D.default_len : eb.seg_len[D.seg_off + seg];
+                            S.nsteps = (int)rint(xdiv(len, P.res));
+                            if (S.nsteps + 1 > HL_MAX_ROLLOUT || S.nsteps < 1) S.ew_status = HL_STATUS_CAPACITY;
+                        }
+                    }
+                }
+            }
+            if (lane < HL_MAX_PRIMS) { S.phit[lane] = 0; S.pneed[lane] = 1; }
+            __syncwarp();
+            if (S.ew_status >= 0) { mode = 2; goto stopped; }
+            {
+            const int n = S.nsteps, np1 = n + 1;
+            const int total = P.n_prims * np1;
+            for (int idx = lane; idx < total; idx += 32) {
+                const int p = idx / np1, i = idx - p * np1;
+                const double ys = P.yaw_step[p];
+                const double init_yaw = angle_wrap(xadd(S.cyaw, ys));
+                const double stop = xadd(init_yaw, xmul(ys, (double)(n + 1)));
+                const double delta = xsub(stop, init_yaw);
+                const double step = xdiv(delta, (double)(n + 1));
+                const double yw = rollout_yaw(init_yaw, stop, step, delta, n + 1, i);
+                S.tx[p][i] = xmul(xmul(P.res, m_cos(yw)), P.dir[p]);
+                S.ty[p][i] = xmul(xmul(P.res, m_sin(yw)), P.dir[p]);
+                S.pyaw[p][i] = rollout_yaw(init_yaw, stop, step, delta, n + 1, i + 1);
+            }
+            __syncwarp();
+            if (lane < P.n_prims) {
+                double ax = 0.0, ay = 0.0;
+                for (int i = 0; i < np1; ++i) {
+                    ax = (i == 0) ? S.tx[lane][0] : xadd(ax, S.tx[lane][i]);
+                    ay = (i == 0) ? S.ty[lane][0] : xadd(ay, S.ty[lane][i]);
+                    S.tx[lane][i] = xadd(S.cx, ax);
+                    S.ty[lane][i] = xadd(S.cy, ay);
+                }
+            }
+            __syncwarp();
+            for (int idx = lane; idx < total; idx += 32) {
+                const int p = idx / np1, j = idx - p * np1;
+                unsigned amb = 0;
+                int st = pose_filter(D, E, S.tx[p][j], S.ty[p][j], S.pyaw[p][j], FLAGS, &amb);
+                S.pamb[p][j] = (st == HL_AMBIG) ? (unsigned char)amb : 0;
+                if (st == HL_HIT) atomicOr(&S.phit[p], 1);
+            }
+            if (lane == 0) S.e_checks += (unsigned long long)total;
+            __syncwarp();
+            for (int idx = lane; idx < total; idx += 32) {
+                const int p = idx / np1, j = idx - p * np1;
+                if (S.pamb[p][j] && !S.phit[p]) {
+                    atomicAdd(&S.e_exact, 1ULL);
+                    if (pose_exact(eb, D, S.tx[p][j], S.ty[p][j], S.pyaw[p][j], S.pamb[p][j])) atomicOr(&S.phit[p], 2);
+                }
+            }
+            __syncwarp();
+            if (lane < P.n_prims && !S.phit[lane]) {
+                const int p = lane;
+                double len = 0.0;
+                for (int i = 0; i + 1 < np1; ++i) {
+                    double ds = hypot_cr(xsub(S.tx[p][i + 1], S.tx[p][i]), xsub(S.ty[p][i + 1], S.ty[p][i]));
+                    len = (i == 0) ? ds : xadd(len, ds);
+                }
+                double cost = xadd(S.cg, len);
+                if (P.dir[p] == -1.0) cost = xadd(cost, P.reverse_cost);
+                cost = xadd(cost, xmul(P.steer[p], P.steer_cost));
+                const double parent_steer = S.cprim < 0 ? 0.0 : P.steer_eff[S.cprim];
+                cost = xadd(cost, xmul(fabs(xsub(P.steer[p], parent_steer)), P.delta_steer_cost));
+                const double parent_dir = S.cprim < 0 ? 1.0 : P.dir[S.cprim];
+                if (parent_dir != P.dir[p]) cost = xadd(cost, P.dir_change_cost);
+                S.pg[p] = cost;
+                int ix, iy, iw;
+                long long key = 0;
+                S.pkey_ok[p] = make_key(S.tx[p][n], S.ty[p][n], S.pyaw[p][n], P.res, P.yaw_res, ix, iy, iw, key) ? 1 : 0;
+                S.pkey[p] = key;
+                int pos = -1;
+                const int slot2 = S.pkey_ok[p] ? hash_find(W, hmask, key, &pos) : -1;
+                S.pslot[p] = slot2;
+                S.ppos[p] = pos;
+                if (slot2 >= 0 && (W.nstate[slot2] == 1 || !(cost < W.ng[slot2]))) S.pneed[p] = 0;
+            }
+            __syncwarp();
+            for (int p = 0; p < P.n_prims; ++p) {
+                if (!S.phit[p] && S.pneed[p]) {
+                    double h = warp_state_cost(eb, D, S.tx[p][n], S.ty[p][n], S.pyaw[p][n], lane);
+                    if (lane == 0) S.pprio[p] = xmul(P.hybrid_cost, h);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                for (int p = 0; p < P.n_prims; ++p) {
+                    if (S.phit[p]) continue;
+                    if (!S.pkey_ok[p]) { S.ew_status = HL_STATUS_CAPACITY; break; }
+                    int pos = S.ppos[p];
+                    int slot2 = S.pslot[p];
+                    if (slot2 < 0 ? (W.hkey[pos] != KEY_EMPTY) : false) slot2 = hash_find(W, hmask, S.pkey[p], &pos);
+                    const double g = S.pg[p];
+                    const double prio = (S.pprio[p] > g) ? S.pprio[p] : g;
+                    if (slot2 >= 0) {
+                        if (W.nstate[slot2] == 1) continue;
+                        if (!(g < W.ng[slot2])) continue;
+                        if (!S.pneed[p]) { S.ew_status = HL_STATUS_CAPACITY; break; }
+                    } else {
+                        if (S.n_nodes >= P.cap_nodes) { S.ew_status = HL_STATUS_CAPACITY; break; }
+                        slot2 = S.n_nodes++;
+                        W.hkey[pos] = S.pkey[p]; W.hval[pos] = slot2; W.nhpos[slot2] = pos;
+                        W.nkey[slot2] = S.pkey[p]; W.nstate[slot2] = 0; W.nheap[slot2] = -1;
+                    }
+                    W.nx[slot2] = S.tx[p][n]; W.ny[slot2] = S.ty[p][n]; W.nyaw[slot2] = S.pyaw[p][n];
+                    W.ng[slot2] = g; W.nparent[slot2] = S.cur; W.nprim[slot2] = (signed char)p;
+                    W.nsteps[slot2] = (signed char)n;
+                    heap_set(W, S.heap_n, slot2, prio);
+                }
+            }
+            __syncwarp();
+            }
+            if (S.ew_status >= 0) { mode = 2; goto stopped; }
+            continue;
+        }
+    stopped:
+        if (mode == 2 && !S.ew_done) {
+        // ---- tell the shooter how far its shots are needed, wait for it, assemble the result
+        if (lane == 0) {
+            // tolerance arrival at pop j: only shots of pops < j matter (the arrival overrides pop j's shot);
+            // otherwise every popped node was shot before the loop ended
+            S.shot_limit = S.ew_arrival2 ? (S.n_closed - 1) : S.n_closed;
+            __threadfence_block();
+            S.ew_done = 1;
+        }
+        __syncwarp();
+        }
+        if (mode == 2) {
+            if (warp_read(&S.sw_done, lane) != my_epoch) { __nanosleep(100); continue; }
+        __threadfence_block();
+        if (lane == 0) {
+            const int hit = S.shot_success;
+            if (hit >= 0 && S.rs_assert && !(S.ew_arrival2 && hit >= S.n_closed - 1)) {
+                S.status = HL_STATUS_RS_ASSERT; S.fin_closed = hit + 1; S.fin_counter = hit + 1; S.arrival = 0;
+            } else if (hit >= 0 && !(S.ew_arrival2 && hit >= S.n_closed - 1)) {     // first free word at pop `hit`
+                // (a shot raced at the tolerance-arrival pop itself does not count: the arrival overrides it)
+                S.status = HL_STATUS_OK; S.arrival = 1; S.fin_closed = hit + 1; S.fin_counter = hit + 1;
+                S.goal_cost = S.rs_goal_cost;
+            } else if (S.ew_arrival2) {
+                S.status = HL_STATUS_OK; S.arrival = 2; S.fin_closed = S.n_closed; S.fin_counter = S.counter;
+                S.goal_cost = S.cg;
+            } else {
+                S.status = S.ew_status; S.arrival = 0; S.fin_closed = S.n_closed; S.fin_counter = S.counter;
+            }
+        }
+        __syncwarp();
+        finalize_spec(S, W, P, O, lane);
+            mode = 0;
+        }
+    }
+}
