@@ -660,7 +660,7 @@ extern "C" int hl_hybrid_astar_batch(hl_ctx* ctx, const hl_env_batch* envs, cons
     const char* var = getenv("HL_ASTAR_VARIANT");
     const bool spec = var ? (strcmp(var, "warp") != 0) : true;
     const int slots = spec ? AQ_SLOTS : AW_WARPS;
-    const int threads = spec ? AQ_SLOTS * 64 : AW_WARPS * 32;
+    const int threads = spec ? AQ_SLOTS * AQ_WARPS_PER_SLOT * 32 : AW_WARPS * 32;
     const size_t smem = spec ? sizeof(AqSmem) * AQ_SLOTS : astar_smem();
     if ((int)smem > ctx->max_smem_optin) {
         hl_set_error("hl_hybrid_astar_batch: %zu B of shared memory per CTA exceed the device limit %d", smem, ctx->max_smem_optin);

@@ -17,22 +17,14 @@
 #define AQ_SLOTS 6                     // scenarios per CTA (2 warps each)
 #endif
 #define AQ_MAX_PLANS 6
+#ifndef AQ_SHOOTERS
+#define AQ_SHOOTERS 1                  // shooter warps per scenario (shots of different pops are independent;
+                                       // 2-3 shooters measured slower: the expander is the critical path)
+#endif
+#define AQ_WARPS_PER_SLOT (1 + AQ_SHOOTERS)
+#define AQ_NO_HIT 0x7fffffff
 
-struct AqSmem {                          // one per scenario slot, shared by its two warps
-    double start[3], goal[3];
-    long long start_key, goal_key;
-    int env, scen;
-    volatile int state;                  // ST_IDLE / ST_SEARCH / ST_DONE (written by the expander)
-    volatile int epoch;                  // bumped by the expander when a scenario is ready for the shooter
-    volatile int popped;                 // closed nodes published to the shooter
-    volatile int ew_done;                // expander stopped; shots needed for nodes < shot_limit
-    volatile int shot_limit;
-    volatile int shot_success;           // pop index of the first free word, or -1
-    volatile int sw_done;                // shooter finished this epoch
-    // expander state
-    int n_nodes, heap_n, counter, n_closed, ew_status, ew_arrival2;
-    int cur; double cx, cy, cyaw, cg; int cprim; int nsteps;
-    // shooter state
+struct AqShot {                          // scratch of one shooter warp
     int s_cur; double sx, sy, syaw, sg;
     double rs_lens[HL_RS_CANDIDATES][HL_RS_MAX_SEGS];
     double rs_L[HL_RS_CANDIDATES], rs_prio[HL_RS_CANDIDATES], rs_Lc[HL_RS_CANDIDATES];
@@ -43,6 +35,25 @@ struct AqSmem {                          // one per scenario slot, shared by its
     double rs_goal_cost;
     RsPlan plans[AQ_MAX_PLANS];
     RsPlan plan_tmp;
+    unsigned long long s_checks, s_exact;
+    volatile int done_epoch;             // this shooter finished the epoch
+};
+
+struct AqSmem {                          // one per scenario slot, shared by its two warps
+    double start[3], goal[3];
+    long long start_key, goal_key;
+    int env, scen;
+    volatile int state;                  // ST_IDLE / ST_SEARCH / ST_DONE (written by the expander)
+    volatile int epoch;                  // bumped by the expander when a scenario is ready for the shooter
+    volatile int popped;                 // closed nodes published to the shooter
+    volatile int ew_done;                // expander stopped; shots needed for nodes < shot_limit
+    volatile int shot_limit;
+    int shot_best;                       // smallest pop index with a free word (atomicMin), AQ_NO_HIT if none
+    // expander state
+    int n_nodes, heap_n, counter, n_closed, ew_status, ew_arrival2;
+    int cur; double cx, cy, cyaw, cg; int cprim; int nsteps;
+    // shooters (AQ_SHOOTERS warps; shooter k takes pops k, k + AQ_SHOOTERS, ...)
+    AqShot sh[AQ_SHOOTERS];
     // expander scratch
     double tx[HL_MAX_PRIMS][AS_ROLL], ty[HL_MAX_PRIMS][AS_ROLL], pyaw[HL_MAX_PRIMS][AS_ROLL];
     unsigned char pamb[HL_MAX_PRIMS][AS_ROLL];
@@ -51,10 +62,10 @@ struct AqSmem {                          // one per scenario slot, shared by its
     long long pkey[HL_MAX_PRIMS];
     int pkey_ok[HL_MAX_PRIMS], pslot[HL_MAX_PRIMS], ppos[HL_MAX_PRIMS], pneed[HL_MAX_PRIMS];
     // stats (per role)
-    unsigned long long e_checks, e_exact, s_checks, s_exact;
+    unsigned long long e_checks, e_exact;
     long long t0;
     // result assembly
-    int status, arrival, fin_closed, fin_counter, chain_len, path_len;
+    int status, arrival, fin_closed, fin_counter, chain_len, path_len, win;
     double goal_cost;
     long long path_off;
     __align__(16) float envf[AW_ENV_FLOATS];
@@ -64,10 +75,10 @@ static_assert(sizeof(AqSmem) * AQ_SLOTS <= 227 * 1024, "per-CTA shared memory ex
 // Alignment of the AQ_SLOTS warps of one role (named barrier `id`, all threads of those warps) with an AND
 // reduction: keeps the role's warps inside the same code region (instruction cache) and tells them when
 // every one of them is finished.
-__device__ __forceinline__ bool role_barrier_all(int id, bool pred) {
+__device__ __forceinline__ bool role_barrier_all(int id, int nthreads, bool pred) {
     int r;
     asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.s32 p, %1, 0;\n\tbarrier.red.and.pred q, %2, %3, p;\n\tselp.s32 %0, 1, 0, q;\n\t}"
-                 : "=r"(r) : "r"((int)pred), "r"(id), "r"(AQ_SLOTS * 32) : "memory");
+                 : "=r"(r) : "r"((int)pred), "r"(id), "r"(nthreads) : "memory");
     return r != 0;
 }
 
@@ -108,7 +119,7 @@ __device__ __noinline__ void finalize_spec(AqSmem& S, const AsWs& W, const AsPar
                 W.hslot[len++] = node;                                   // the heap is dead by now
                 poses += W.nsteps[node] + 1;
             }
-            if (S.arrival == 1) rs_pts = (S.rs_pick < AQ_MAX_PLANS ? S.plans[S.rs_pick] : S.plan_tmp).npts;
+            if (S.arrival == 1) { const AqShot& T = S.sh[S.win]; rs_pts = (T.rs_pick < AQ_MAX_PLANS ? T.plans[T.rs_pick] : T.plan_tmp).npts; }
         }
         S.chain_len = len;
         S.path_len = poses + rs_pts;
@@ -148,7 +159,8 @@ __device__ __noinline__ void finalize_spec(AqSmem& S, const AsWs& W, const AsPar
             }
         }
         if (S.arrival == 1) {
-            const RsPlan& plan = (S.rs_pick < AQ_MAX_PLANS) ? S.plans[S.rs_pick] : S.plan_tmp;
+            const AqShot& T = S.sh[S.win];
+            const RsPlan& plan = (T.rs_pick < AQ_MAX_PLANS) ? T.plans[T.rs_pick] : T.plan_tmp;
             const double q0[3] = {W.nx[cur], W.ny[cur], W.nyaw[cur]};
             const double cq = m_cos(-q0[2]), sq = m_sin(-q0[2]);
             const long long off = S.path_off + (S.path_len - plan.npts);
@@ -171,11 +183,13 @@ __device__ __noinline__ void finalize_spec(AqSmem& S, const AsWs& W, const AsPar
         r.n_expanded = nk;
         r.arrival = S.arrival;
         r.path_len = S.path_len;
-        r.rs_word = (S.arrival == 1) ? S.rs_word : -1;
+        r.rs_word = (S.arrival == 1) ? S.sh[S.win].rs_word : -1;
         r.path_offset = S.path_off;
         r.goal_cost = S.goal_cost;
-        r.n_pose_checks = (long long)(S.e_checks + S.s_checks);
-        r.n_exact = (long long)(S.e_exact + S.s_exact);
+        unsigned long long sc_ = S.e_checks, se_ = S.e_exact;
+        for (int k = 0; k < AQ_SHOOTERS; ++k) { sc_ += S.sh[k].s_checks; se_ += S.sh[k].s_exact; }
+        r.n_pose_checks = (long long)sc_;
+        r.n_exact = (long long)se_;
         r.keys_offset = koff;
         r.cycles = clock64() - S.t0;
         O.results[sc] = r;
@@ -185,12 +199,12 @@ __device__ __noinline__ void finalize_spec(AqSmem& S, const AsWs& W, const AsPar
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(AQ_SLOTS * 64, 1)
+__global__ void __launch_bounds__(AQ_SLOTS * AQ_WARPS_PER_SLOT * 32, 1)
 k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen, AsParams P, char* ws_base,
                  size_t ws_stride, unsigned int* work_counter, AwOut O) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int slot = wid >> 1, role = wid & 1;                 // role 0 = expander, 1 = shooter
+    const int slot = wid / AQ_WARPS_PER_SLOT, role = wid % AQ_WARPS_PER_SLOT;   // role 0 = expander, 1.. = shooters
     AqSmem& S = reinterpret_cast<AqSmem*>(smem_raw)[slot];
     const AsWs W = as_carve(ws_base + ((size_t)blockIdx.x * AQ_SLOTS + slot) * ws_stride, P.cap_nodes, P.hash_size,
                             P.max_nodes);
@@ -198,15 +212,20 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
     const unsigned FLAGS = HL_CHECK_OBSTACLES | HL_CHECK_BOUNDARY | HL_CHECK_LANE;
     if (role == 0) {
         for (int i = lane; i < P.hash_size; i += 32) W.hkey[i] = KEY_EMPTY;
-        if (lane == 0) { S.state = ST_IDLE; S.epoch = 0; S.sw_done = 0; S.popped = 0; S.ew_done = 0; S.shot_success = -1; }
+        if (lane == 0) {
+            S.state = ST_IDLE; S.epoch = 0; S.popped = 0; S.ew_done = 0; S.shot_best = AQ_NO_HIT;
+            for (int k = 0; k < AQ_SHOOTERS; ++k) S.sh[k].done_epoch = 0;
+        }
     }
     __syncthreads();
 
     EnvSmem E;
     E.n_obs = E.n_field = E.n_seg = E.all_rect = 0; E.eps = 0.f; E.reach = 0.f; E.obs = E.field = E.seg = nullptr;
 
-    if (role == 1) {
+    if (role >= 1) {
         // =========================================== SHOOTER ===========================================
+        const int shooter = role - 1;
+        AqShot& T = S.sh[shooter];
         int my_epoch = 0;
         int i = 0;
         bool active = false;            // a scenario is attached and its shots are not finished
@@ -216,7 +235,7 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
         const float inv_maxc = (float)(1.0 / P.maxc);
         const double stepn = xmul(P.res, P.maxc);
         while (true) {
-            if (role_barrier_all(1, finished)) break;              // alignment point of the shooters
+            if (role_barrier_all(1, AQ_SLOTS * AQ_SHOOTERS * 32, finished)) break;   // alignment point of the shooters
             if (finished) continue;
             if (!active) {
                 const int st = warp_read(&S.state, lane);
@@ -239,9 +258,9 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                     }
                     Ers = E;
                     Ers.eps = E.eps + 6e-5f;
-                    if (lane == 0) { S.s_checks = 0; S.s_exact = 0; S.rs_assert = 0; }
+                    if (lane == 0) { T.s_checks = 0; T.s_exact = 0; T.rs_assert = 0; }
                     __syncwarp();
-                    i = 0;
+                    i = shooter;                     // pops shooter, shooter + AQ_SHOOTERS, ...
                     active = true;
                 } else if (st == ST_DONE) { finished = true; continue; }
                 else { __nanosleep(200); continue; }
@@ -249,15 +268,17 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
             const EnvDesc& D = *Dp;
             bool success = false;
             {
-                // is pop i available, or has the expander stopped short of it?
+                // is pop i available, has the expander stopped short of it, or did an EARLIER pop already succeed?
                 const int done = warp_read(&S.ew_done, lane);
                 __threadfence_block();
                 const int popped = warp_read(&S.popped, lane);
+                const int best = warp_read((volatile int*)&S.shot_best, lane);
                 bool stop = false, have = false;
-                if (done) { if (i >= warp_read(&S.shot_limit, lane)) stop = true; else have = true; }   // limit <= popped
+                if (best < i) stop = true;                         // the search ends before this pop
+                else if (done) { if (i >= warp_read(&S.shot_limit, lane)) stop = true; else have = true; }   // limit <= popped
                 else if (popped > i) have = true;
                 if (stop) {
-                    if (lane == 0) { __threadfence_block(); S.sw_done = my_epoch; }
+                    if (lane == 0) { __threadfence_block(); T.done_epoch = my_epoch; }
                     __syncwarp();
                     active = false;
                     continue;
@@ -266,65 +287,65 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                 __threadfence_block();
                 if (lane == 0) {
                     const int cur = W.corder[i];
-                    S.s_cur = cur; S.sx = W.nx[cur]; S.sy = W.ny[cur]; S.syaw = W.nyaw[cur]; S.sg = W.ng[cur];
-                    const double q0n[3] = {S.sx, S.sy, S.syaw};
-                    S.rs_prob = rs_normalise(q0n, S.goal, P.maxc);
-                    S.rs_pick = -1;
+                    T.s_cur = cur; T.sx = W.nx[cur]; T.sy = W.ny[cur]; T.syaw = W.nyaw[cur]; T.sg = W.ng[cur];
+                    const double q0n[3] = {T.sx, T.sy, T.syaw};
+                    T.rs_prob = rs_normalise(q0n, S.goal, P.maxc);
+                    T.rs_pick = -1;
                 }
                 __syncwarp();
-                const double q0[3] = {S.sx, S.sy, S.syaw};
+                const double q0[3] = {T.sx, T.sy, T.syaw};
                 for (int c = lane; c < HL_RS_CANDIDATES; c += 32) {
                     double l[HL_RS_MAX_SEGS] = {0, 0, 0, 0, 0};
-                    bool ok = rs_candidate(c, S.rs_prob, l);
-                    S.rs_valid[c] = ok ? 1 : 0;
-                    for (int k = 0; k < HL_RS_MAX_SEGS; ++k) S.rs_lens[c][k] = l[k];
+                    bool ok = rs_candidate(c, T.rs_prob, l);
+                    T.rs_valid[c] = ok ? 1 : 0;
+                    for (int k = 0; k < HL_RS_MAX_SEGS; ++k) T.rs_lens[c][k] = l[k];
                 }
                 __syncwarp();
-                if (lane < RS_N_GROUPS) rs_select_group(lane, S.rs_valid, S.rs_lens, S.rs_accept, S.rs_Lc);
+                if (lane < RS_N_GROUPS) rs_select_group(lane, T.rs_valid, T.rs_lens, T.rs_accept, T.rs_Lc);
                 __syncwarp();
                 int m;
                 {
-                    const int a0 = S.rs_accept[lane];
-                    const int a1 = (lane + 32 < HL_RS_CANDIDATES) ? S.rs_accept[lane + 32] : 0;
+                    const int a0 = T.rs_accept[lane];
+                    const int a1 = (lane + 32 < HL_RS_CANDIDATES) ? T.rs_accept[lane + 32] : 0;
                     const unsigned b0 = __ballot_sync(FULL, a0 == 1), b1 = __ballot_sync(FULL, a1 == 1);
                     const unsigned bad = __ballot_sync(FULL, a0 == 2 || a1 == 2);
                     const unsigned lt = (1u << lane) - 1u;
                     const int n0 = __popc(b0);
-                    if (a0 == 1) { int k = __popc(b0 & lt); S.rs_acc[k] = lane; S.rs_L[k] = S.rs_Lc[lane]; }
-                    if (a1 == 1) { int k = n0 + __popc(b1 & lt); S.rs_acc[k] = lane + 32; S.rs_L[k] = S.rs_Lc[lane + 32]; }
+                    if (a0 == 1) { int k = __popc(b0 & lt); T.rs_acc[k] = lane; T.rs_L[k] = T.rs_Lc[lane]; }
+                    if (a1 == 1) { int k = n0 + __popc(b1 & lt); T.rs_acc[k] = lane + 32; T.rs_L[k] = T.rs_Lc[lane + 32]; }
                     m = bad ? 0 : n0 + __popc(b1);
                     __syncwarp();
                     for (int k = lane; k < m; k += 32)
-                        S.rs_prio[k] = rs_path_cost(S.sg, S.rs_acc[k], S.rs_lens[S.rs_acc[k]], P.max_steer,
+                        T.rs_prio[k] = rs_path_cost(T.sg, T.rs_acc[k], T.rs_lens[T.rs_acc[k]], P.max_steer,
                                                     P.reverse_cost, P.dir_change_cost, P.steer_cost);
                     __syncwarp();
                     if (lane == 0) {
-                        if (bad) S.rs_assert = 1;
-                        S.rs_n = m;
-                        if (m > 0) heapdict_order(S.rs_prio, m, S.rs_order);
+                        if (bad) T.rs_assert = 1;
+                        T.rs_n = m;
+                        if (m > 0) heapdict_order(T.rs_prio, m, T.rs_order);
                     }
                     __syncwarp();
                     if (bad) success = true;     // the reference would raise here: report it as the end of the search
                 }
                 const double cq = m_cos(-q0[2]), sq = m_sin(-q0[2]);
                 if (lane < m && lane < AQ_MAX_PLANS) {
-                    int c = S.rs_acc[S.rs_order[lane]];
-                    rs_make_plan(c, S.rs_lens[c], P.maxc, stepn, S.plans[lane]);
-                    rs_plan_world32(S.plans[lane], q0, cq, sq, D.origin);
+                    int c = T.rs_acc[T.rs_order[lane]];
+                    rs_make_plan(c, T.rs_lens[c], P.maxc, stepn, T.plans[lane]);
+                    rs_plan_world32(T.plans[lane], q0, cq, sq, D.origin);
                 }
                 __syncwarp();
                 for (int r = 0; r < m; ++r) {
-                    const int k = S.rs_order[r];
-                    const int c = S.rs_acc[k];
+                    const int k = T.rs_order[r];
+                    const int c = T.rs_acc[k];
                     if (r >= AQ_MAX_PLANS) {
                         __syncwarp();
                         if (lane == 0) {
-                            rs_make_plan(c, S.rs_lens[c], P.maxc, stepn, S.plan_tmp);
-                            rs_plan_world32(S.plan_tmp, q0, cq, sq, D.origin);
+                            rs_make_plan(c, T.rs_lens[c], P.maxc, stepn, T.plan_tmp);
+                            rs_plan_world32(T.plan_tmp, q0, cq, sq, D.origin);
                         }
                         __syncwarp();
                     }
-                    const RsPlan& plan = (r < AQ_MAX_PLANS) ? S.plans[r] : S.plan_tmp;
+                    const RsPlan& plan = (r < AQ_MAX_PLANS) ? T.plans[r] : T.plan_tmp;
                     const int npts = plan.npts;
                     int infeasible = 0;
                     const int passes = (npts + 31) >> 5;
@@ -352,14 +373,14 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                                 rs_to_world(q0, cq, sq, lx, ly, lyaw, wx, wy, wyaw);
                                 bad2 = pose_exact(eb, D, wx, wy, wyaw, amb) ? 1 : 0;
                             }
-                            if (lane == 0) S.s_exact += (unsigned long long)__popc(ambm);
+                            if (lane == 0) T.s_exact += (unsigned long long)__popc(ambm);
                             infeasible = __any_sync(FULL, bad2);
                         }
-                        if (lane == 0) S.s_checks += (unsigned long long)__popc(livem);
+                        if (lane == 0) T.s_checks += (unsigned long long)__popc(livem);
                     }
-                    const bool short_enough = xdiv(S.rs_L[k], P.maxc) < P.min_len_goal;
+                    const bool short_enough = xdiv(T.rs_L[k], P.maxc) < P.min_len_goal;
                     if (!infeasible && short_enough) {
-                        if (lane == 0) { S.rs_pick = r; S.rs_word = c; S.rs_goal_cost = S.rs_prio[k]; }
+                        if (lane == 0) { T.rs_pick = r; T.rs_word = c; T.rs_goal_cost = T.rs_prio[k]; }
                         success = true;
                         break;
                     }
@@ -367,10 +388,10 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                 __syncwarp();
             }
             if (success) {
-                if (lane == 0) { __threadfence_block(); S.shot_success = i; __threadfence_block(); S.sw_done = my_epoch; }
+                if (lane == 0) { __threadfence_block(); atomicMin(&S.shot_best, i); __threadfence_block(); T.done_epoch = my_epoch; }
                 __syncwarp();
                 active = false;
-            } else ++i;
+            } else i += AQ_SHOOTERS;
         }
         return;
     }
@@ -383,7 +404,7 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
     int my_epoch = 0;
     const EnvDesc* Dp = eb.desc;
     while (true) {
-        if (role_barrier_all(2, finished)) break;
+        if (role_barrier_all(2, AQ_SLOTS * 32, finished)) break;
         if (finished) continue;
         if (mode == 0) {
         // ---- next scenario
@@ -397,9 +418,10 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
             for (int k = 0; k < 3; ++k) { S.start[k] = s.start[k]; S.goal[k] = s.goal[k]; }
             S.n_nodes = 0; S.heap_n = 0; S.counter = 0; S.n_closed = 0;
             S.status = -1; S.arrival = 0; S.goal_cost = 0.0; S.ew_status = -1; S.ew_arrival2 = 0;
-            S.e_checks = 0; S.e_exact = 0; S.s_checks = 0; S.s_exact = 0;
+            S.e_checks = 0; S.e_exact = 0; S.win = 0;
+            for (int k = 0; k < AQ_SHOOTERS; ++k) { S.sh[k].s_checks = 0; S.sh[k].s_exact = 0; S.sh[k].rs_assert = 0; }
             S.path_len = 0; S.path_off = 0; S.chain_len = 0; S.fin_closed = 0; S.fin_counter = 0;
-            S.popped = 0; S.ew_done = 0; S.shot_limit = 0; S.shot_success = -1;
+            S.popped = 0; S.ew_done = 0; S.shot_limit = 0; S.shot_best = AQ_NO_HIT;
             S.t0 = clock64();
         }
         __syncwarp();
@@ -457,7 +479,7 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
         const EnvDesc& D = *Dp;
         if (mode == 1) {
             if (lane == 0) {
-                if (S.shot_success >= 0) S.ew_status = HL_STATUS_OK;             // the shooter ended the search
+                if (*(volatile int*)&S.shot_best != AQ_NO_HIT) S.ew_status = HL_STATUS_OK;   // a shooter ended the search
                 else if (S.counter > P.max_nodes) S.ew_status = HL_STATUS_MAX_NODES;
                 else {
                     S.counter += 1;
@@ -489,17 +511,22 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
             {
             const int n = S.nsteps, np1 = n + 1;
             const int total = P.n_prims * np1;
-            for (int idx = lane; idx < total; idx += 32) {
-                const int p = idx / np1, i = idx - p * np1;
+            // yaws[0..n+1] of every primitive once (the pose yaw of step i is yaws[i+1]), one sincos each
+            for (int idx = lane; idx < P.n_prims * (np1 + 1); idx += 32) {
+                const int p = idx / (np1 + 1), i = idx - p * (np1 + 1);
                 const double ys = P.yaw_step[p];
                 const double init_yaw = angle_wrap(xadd(S.cyaw, ys));
                 const double stop = xadd(init_yaw, xmul(ys, (double)(n + 1)));
                 const double delta = xsub(stop, init_yaw);
                 const double step = xdiv(delta, (double)(n + 1));
                 const double yw = rollout_yaw(init_yaw, stop, step, delta, n + 1, i);
-                S.tx[p][i] = xmul(xmul(P.res, m_cos(yw)), P.dir[p]);
-                S.ty[p][i] = xmul(xmul(P.res, m_sin(yw)), P.dir[p]);
-                S.pyaw[p][i] = rollout_yaw(init_yaw, stop, step, delta, n + 1, i + 1);
+                if (i >= 1) S.pyaw[p][i - 1] = yw;
+                if (i <= n) {
+                    double sn, cs;
+                    m_sincos(yw, &sn, &cs);
+                    S.tx[p][i] = xmul(xmul(P.res, cs), P.dir[p]);
+                    S.ty[p][i] = xmul(xmul(P.res, sn), P.dir[p]);
+                }
             }
             __syncwarp();
             if (lane < P.n_prims) {
@@ -605,16 +632,22 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
         __syncwarp();
         }
         if (mode == 2) {
-            if (warp_read(&S.sw_done, lane) != my_epoch) { __nanosleep(100); continue; }
+            {
+                bool all = true;
+                for (int k = 0; k < AQ_SHOOTERS; ++k) all = all && (warp_read(&S.sh[k].done_epoch, lane) == my_epoch);
+                if (!all) { __nanosleep(100); continue; }
+            }
         __threadfence_block();
         if (lane == 0) {
-            const int hit = S.shot_success;
-            if (hit >= 0 && S.rs_assert && !(S.ew_arrival2 && hit >= S.n_closed - 1)) {
+            const int best = *(volatile int*)&S.shot_best;
+            const int hit = (best == AQ_NO_HIT) ? -1 : best;
+            if (hit >= 0) S.win = hit % AQ_SHOOTERS;
+            if (hit >= 0 && S.sh[S.win].rs_assert && !(S.ew_arrival2 && hit >= S.n_closed - 1)) {
                 S.status = HL_STATUS_RS_ASSERT; S.fin_closed = hit + 1; S.fin_counter = hit + 1; S.arrival = 0;
             } else if (hit >= 0 && !(S.ew_arrival2 && hit >= S.n_closed - 1)) {     // first free word at pop `hit`
                 // (a shot raced at the tolerance-arrival pop itself does not count: the arrival overrides it)
                 S.status = HL_STATUS_OK; S.arrival = 1; S.fin_closed = hit + 1; S.fin_counter = hit + 1;
-                S.goal_cost = S.rs_goal_cost;
+                S.goal_cost = S.sh[S.win].rs_goal_cost;
             } else if (S.ew_arrival2) {
                 S.status = HL_STATUS_OK; S.arrival = 2; S.fin_closed = S.n_closed; S.fin_counter = S.counter;
                 S.goal_cost = S.cg;
