@@ -23,6 +23,8 @@
 #endif
 #define AQ_WARPS_PER_SLOT (1 + AQ_SHOOTERS)
 #define AQ_NO_HIT 0x7fffffff
+#define ETICK(ph) do { if (lane == 0) { long long _n = clock64(); S.te[ph] += _n - S.te_last; S.te_last = _n; } } while (0)
+#define STICK(ph) do { if (lane == 0) { long long _n = clock64(); S.ts[ph] += _n - S.ts_last; S.ts_last = _n; } } while (0)
 
 struct AqShot {                          // scratch of one shooter warp
     int s_cur; double sx, sy, syaw, sg;
@@ -64,6 +66,8 @@ struct AqSmem {                          // one per scenario slot, shared by its
     // stats (per role)
     unsigned long long e_checks, e_exact;
     long long t0;
+    long long te_last, te[AS_N_PHASES];      // expander phase timers (lane 0 cycles)
+    long long ts_last, ts[AS_N_PHASES];      // shooter phase timers
     // result assembly
     int status, arrival, fin_closed, fin_counter, chain_len, path_len, win;
     double goal_cost;
@@ -193,7 +197,10 @@ __device__ __noinline__ void finalize_spec(AqSmem& S, const AsWs& W, const AsPar
         r.keys_offset = koff;
         r.cycles = clock64() - S.t0;
         O.results[sc] = r;
-        atomicAdd(O.phase_cycles + PH_OUTPUT, (unsigned long long)r.cycles);
+        for (int k = 0; k < AS_N_PHASES; ++k) {
+            const long long v = S.te[k] + S.ts[k];
+            if (v) atomicAdd(O.phase_cycles + k, (unsigned long long)v);
+        }
     }
     for (int i = lane; i < S.n_nodes; i += 32) W.hkey[W.nhpos[i]] = KEY_EMPTY;
     __syncwarp();
@@ -237,6 +244,7 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
         while (true) {
             if (role_barrier_all(1, AQ_SLOTS * AQ_SHOOTERS * 32, finished)) break;   // alignment point of the shooters
             if (finished) continue;
+            if (active) STICK(PH_OUTPUT);     // shooter time in the alignment barrier / waiting for pops
             if (!active) {
                 const int st = warp_read(&S.state, lane);
                 const int ep = warp_read(&S.epoch, lane);
@@ -301,6 +309,7 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                     for (int k = 0; k < HL_RS_MAX_SEGS; ++k) T.rs_lens[c][k] = l[k];
                 }
                 __syncwarp();
+                STICK(PH_RS_CAND);
                 if (lane < RS_N_GROUPS) rs_select_group(lane, T.rs_valid, T.rs_lens, T.rs_accept, T.rs_Lc);
                 __syncwarp();
                 int m;
@@ -327,6 +336,7 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                     __syncwarp();
                     if (bad) success = true;     // the reference would raise here: report it as the end of the search
                 }
+                STICK(PH_RS_SELECT);
                 const double cq = m_cos(-q0[2]), sq = m_sin(-q0[2]);
                 if (lane < m && lane < AQ_MAX_PLANS) {
                     int c = T.rs_acc[T.rs_order[lane]];
@@ -334,6 +344,7 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                     rs_plan_world32(T.plans[lane], q0, cq, sq, D.origin);
                 }
                 __syncwarp();
+                STICK(PH_RS_PLAN);
                 for (int r = 0; r < m; ++r) {
                     const int k = T.rs_order[r];
                     const int c = T.rs_acc[k];
@@ -386,6 +397,7 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                     }
                 }
                 __syncwarp();
+                STICK(PH_RS_SAMPLE);
             }
             if (success) {
                 if (lane == 0) { __threadfence_block(); atomicMin(&S.shot_best, i); __threadfence_block(); T.done_epoch = my_epoch; }
@@ -406,6 +418,7 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
     while (true) {
         if (role_barrier_all(2, AQ_SLOTS * 32, finished)) break;
         if (finished) continue;
+        ETICK(PH_SETUP);                 // time spent in the alignment barrier (+ attach / wait modes)
         if (mode == 0) {
         // ---- next scenario
         int sc = 0;
@@ -423,6 +436,8 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
             S.path_len = 0; S.path_off = 0; S.chain_len = 0; S.fin_closed = 0; S.fin_counter = 0;
             S.popped = 0; S.ew_done = 0; S.shot_limit = 0; S.shot_best = AQ_NO_HIT;
             S.t0 = clock64();
+            for (int k = 0; k < AS_N_PHASES; ++k) { S.te[k] = 0; S.ts[k] = 0; }
+            S.te_last = S.t0; S.ts_last = S.t0;
         }
         __syncwarp();
         Dp = eb.desc + S.env;
@@ -507,6 +522,7 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
             }
             if (lane < HL_MAX_PRIMS) { S.phit[lane] = 0; S.pneed[lane] = 1; }
             __syncwarp();
+            ETICK(PH_POP);
             if (S.ew_status >= 0) { mode = 2; goto stopped; }
             {
             const int n = S.nsteps, np1 = n + 1;
@@ -539,6 +555,7 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                 }
             }
             __syncwarp();
+            ETICK(PH_ROLLOUT);
             for (int idx = lane; idx < total; idx += 32) {
                 const int p = idx / np1, j = idx - p * np1;
                 unsigned amb = 0;
@@ -548,6 +565,7 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
             }
             if (lane == 0) S.e_checks += (unsigned long long)total;
             __syncwarp();
+            ETICK(PH_FILTER);
             for (int idx = lane; idx < total; idx += 32) {
                 const int p = idx / np1, j = idx - p * np1;
                 if (S.pamb[p][j] && !S.phit[p]) {
@@ -556,6 +574,7 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                 }
             }
             __syncwarp();
+            ETICK(PH_EXACT);
             if (lane < P.n_prims && !S.phit[lane]) {
                 const int p = lane;
                 double len = 0.0;
@@ -589,6 +608,7 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                 }
             }
             __syncwarp();
+            ETICK(PH_COST_HEUR);
             if (lane == 0) {
                 for (int p = 0; p < P.n_prims; ++p) {
                     if (S.phit[p]) continue;
@@ -616,6 +636,7 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
             }
             __syncwarp();
             }
+            ETICK(PH_MERGE);
             if (S.ew_status >= 0) { mode = 2; goto stopped; }
             continue;
         }
