@@ -50,11 +50,14 @@ struct EnvBatchDev {
     int n_env;
 };
 
+struct hl_ctx;
 struct hl_env_batch {
     EnvBatchDev dev;
     void* allocs[20];
     int n_allocs;
     int device;
+    hl_ctx* owner;
+    size_t block_bytes;
 };
 
 struct hl_ctx {
@@ -64,6 +67,10 @@ struct hl_ctx {
     void* astar_ws;           // cached workspace of the search kernel
     size_t astar_ws_bytes;
     unsigned int* d_counters; // small device scratch (work-queue counter etc.)
+    void* stage;              // pinned staging buffer of hl_env_upload (grow-only)
+    size_t stage_bytes;
+    void* env_cache;          // device block of the last freed environment batch, reused by the next upload
+    size_t env_cache_bytes;
 };
 
 void hl_set_error(const char* fmt, ...);
