@@ -14,6 +14,7 @@
 // code region, so an instruction line fetched once serves AW_WARPS scenarios.  Warps pull scenario ids from
 // an atomic counter as soon as theirs finishes.
 #include <cstdlib>
+#include <cstdio>
 #include "hl_astar_common.cuh"
 
 #ifndef AW_WARPS
@@ -601,6 +602,7 @@ k_hybrid_astar_w(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
 }
 
 #include "hl_astar_spec.cuh"
+#include "hl_astar_level.cuh"
 
 // ------------------------------------------------------------------------------ host side
 static void fill_params(const hl_ctx* ctx, const HlSearchParams* h, AsParams& P) {
@@ -619,6 +621,156 @@ static void fill_params(const hl_ctx* ctx, const HlSearchParams* h, AsParams& P)
     int hs = 1024;
     while (hs < 2 * P.cap_nodes) hs <<= 1;
     P.hash_size = hs;
+}
+
+
+// ---- level-synchronous variant: per-context state (pools, the iteration graph, its two streams)
+struct LsState {
+    LsCall* d_call; LsCall* h_call;          // device block + pinned staging copy
+    int* h_nact;                             // pinned read-back of the active count
+    char* pool; size_t pool_bytes;
+    cudaGraph_t graph; cudaGraphExec_t exec;
+    cudaStream_t s1, s2;
+    cudaEvent_t ev_fork, ev_join;
+    int grid;
+};
+
+static void ls_state_free(void* p) {
+    LsState* L = (LsState*)p;
+    if (!L) return;
+    if (L->exec) cudaGraphExecDestroy(L->exec);
+    if (L->graph) cudaGraphDestroy(L->graph);
+    if (L->ev_fork) cudaEventDestroy(L->ev_fork);
+    if (L->ev_join) cudaEventDestroy(L->ev_join);
+    if (L->s1) cudaStreamDestroy(L->s1);
+    if (L->s2) cudaStreamDestroy(L->s2);
+    if (L->pool) cudaFree(L->pool);
+    if (L->d_call) cudaFree(L->d_call);
+    if (L->h_call) cudaFreeHost(L->h_call);
+    if (L->h_nact) cudaFreeHost(L->h_nact);
+    delete L;
+}
+
+static int ls_state_get(hl_ctx* ctx, LsState** out) {
+    if (ctx->ls_state) { *out = (LsState*)ctx->ls_state; return 0; }
+    LsState* L = new LsState();
+    memset(L, 0, sizeof(*L));
+    ctx->ls_state = L; ctx->ls_free = ls_state_free;
+    L->grid = ctx->sm_count * LS_GRID_MULT;
+    HL_CUDA_OK(cudaMalloc(&L->d_call, sizeof(LsCall)));
+    HL_CUDA_OK(cudaMallocHost(&L->h_call, sizeof(LsCall)));
+    HL_CUDA_OK(cudaMallocHost(&L->h_nact, 64));
+    HL_CUDA_OK(cudaStreamCreateWithFlags(&L->s1, cudaStreamNonBlocking));
+    HL_CUDA_OK(cudaStreamCreateWithFlags(&L->s2, cudaStreamNonBlocking));
+    HL_CUDA_OK(cudaEventCreateWithFlags(&L->ev_fork, cudaEventDisableTiming));
+    HL_CUDA_OK(cudaEventCreateWithFlags(&L->ev_join, cudaEventDisableTiming));
+    // LS_CHUNK iterations; the first one reads the list the initial step(0) filled (parity 1)
+    const int g = L->grid;
+    HL_CUDA_OK(cudaStreamBeginCapture(L->s1, cudaStreamCaptureModeThreadLocal));
+    for (int it = 0; it < LS_CHUNK; ++it) {
+        const int parity = (it & 1) ^ 1;
+        HL_CUDA_OK(cudaEventRecord(L->ev_fork, L->s1));
+        HL_CUDA_OK(cudaStreamWaitEvent(L->s2, L->ev_fork, 0));
+        ls_cand<<<g, LS_THREADS, 0, L->s1>>>(L->d_call, parity);
+        ls_select<<<g, LS_THREADS, 0, L->s1>>>(L->d_call, parity);
+        ls_sample<<<g, LS_THREADS, 0, L->s1>>>(L->d_call);
+        ls_rollout<<<g, LS_THREADS, 0, L->s2>>>(L->d_call, parity);
+        ls_filter<<<g, LS_THREADS, 0, L->s2>>>(L->d_call, parity);
+        ls_cost<<<g, LS_THREADS, 0, L->s2>>>(L->d_call, parity);
+        HL_CUDA_OK(cudaEventRecord(L->ev_join, L->s2));
+        HL_CUDA_OK(cudaStreamWaitEvent(L->s1, L->ev_join, 0));
+        ls_step<<<g, LS_THREADS, 0, L->s1>>>(L->d_call, parity);
+    }
+    HL_CUDA_OK(cudaStreamEndCapture(L->s1, &L->graph));
+    HL_CUDA_OK(cudaGraphInstantiate(&L->exec, L->graph, 0));
+    *out = L;
+    return 0;
+}
+
+static int ls_run(hl_ctx* ctx, const hl_env_batch* envs, const HlScenario* d_scen, int n_scen, const AsParams& P,
+                  const AwOut& O, cudaStream_t st) {
+    LsState* L = nullptr;
+    if (ls_state_get(ctx, &L)) return 1;
+    const size_t stride = as_ws_bytes(P.cap_nodes, P.hash_size, P.max_nodes);
+    const int nb_max = n_scen < LS_MAX_BATCH ? n_scen : LS_MAX_BATCH;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t r = off; off += as_align(bytes); return r; };
+    const size_t o_ws = take(stride * (size_t)nb_max);
+    const size_t o_scn = take(sizeof(LsScn) * (size_t)nb_max);
+    const size_t o_prim = take(sizeof(LsPrim) * (size_t)nb_max * P.n_prims);
+    const size_t o_shot = take(sizeof(LsShot) * (size_t)nb_max);
+    const size_t o_act0 = take(sizeof(int) * (size_t)nb_max);
+    const size_t o_act1 = take(sizeof(int) * (size_t)nb_max);
+    const size_t o_cnt = take(sizeof(int) * 8);
+    const size_t o_words = take(sizeof(int2) * (size_t)nb_max * HL_RS_CANDIDATES);
+    if (off > L->pool_bytes) {
+        if (L->pool) cudaFree(L->pool);
+        L->pool = nullptr; L->pool_bytes = 0;
+        HL_CUDA_OK(cudaMalloc(&L->pool, off));
+        L->pool_bytes = off;
+    }
+    const int max_iters = P.max_nodes + 3;
+    for (int base = 0; base < n_scen; base += nb_max) {
+        const int nb = (n_scen - base) < nb_max ? (n_scen - base) : nb_max;
+        LsCall& H = *L->h_call;
+        H.eb = envs->dev; H.scen = d_scen + base; H.n_scen = nb; H.P = P;
+        H.ws = L->pool + o_ws; H.ws_stride = stride;
+        H.scn = (LsScn*)(L->pool + o_scn); H.prim = (LsPrim*)(L->pool + o_prim); H.shot = (LsShot*)(L->pool + o_shot);
+        H.act[0] = (int*)(L->pool + o_act0); H.act[1] = (int*)(L->pool + o_act1);
+        H.n_act = (int*)(L->pool + o_cnt); H.n_words = H.n_act + 2;
+        H.words = (int2*)(L->pool + o_words);
+        H.O = O; H.O.results = O.results + base;
+        HL_CUDA_OK(cudaMemcpyAsync(L->d_call, L->h_call, sizeof(LsCall), cudaMemcpyHostToDevice, st));
+        HL_CUDA_OK(cudaMemsetAsync(H.n_act, 0, sizeof(int) * 8, st));
+        ls_setup<<<L->grid, LS_THREADS, 0, st>>>(L->d_call);
+        ls_step<<<L->grid, LS_THREADS, 0, st>>>(L->d_call, 0);
+        if (getenv("HL_LS_TIMING")) {
+            // debug: the same kernels one by one on the caller's stream with an event pair around each
+            const char* names[7] = {"cand", "select", "sample", "rollout", "filter", "cost", "step"};
+            double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+            cudaEvent_t e0, e1;
+            cudaEventCreate(&e0); cudaEventCreate(&e1);
+            const int g = L->grid;
+            int iters = 0;
+            for (int it = 0; it < max_iters; ++it, ++iters) {
+                const int parity = (it & 1) ^ 1;
+                for (int k = 0; k < 7; ++k) {
+                    cudaEventRecord(e0, st);
+                    switch (k) {
+                        case 0: ls_cand<<<g, LS_THREADS, 0, st>>>(L->d_call, parity); break;
+                        case 1: ls_select<<<g, LS_THREADS, 0, st>>>(L->d_call, parity); break;
+                        case 2: ls_sample<<<g, LS_THREADS, 0, st>>>(L->d_call); break;
+                        case 3: ls_rollout<<<g, LS_THREADS, 0, st>>>(L->d_call, parity); break;
+                        case 4: ls_filter<<<g, LS_THREADS, 0, st>>>(L->d_call, parity); break;
+                        case 5: ls_cost<<<g, LS_THREADS, 0, st>>>(L->d_call, parity); break;
+                        default: ls_step<<<g, LS_THREADS, 0, st>>>(L->d_call, parity); break;
+                    }
+                    cudaEventRecord(e1, st);
+                    cudaEventSynchronize(e1);
+                    float ms = 0.f;
+                    cudaEventElapsedTime(&ms, e0, e1);
+                    if (it >= 100) acc[k] += ms;
+                }
+                cudaMemcpyAsync(L->h_nact, H.n_act + (parity ^ 1), sizeof(int), cudaMemcpyDeviceToHost, st);
+                cudaStreamSynchronize(st);
+                if (*L->h_nact == 0) break;
+            }
+            fprintf(stderr, "[ls timing] %d iterations; mean us per kernel over iterations >= 100:", iters);
+            for (int k = 0; k < 7; ++k) fprintf(stderr, " %s %.1f", names[k], iters > 100 ? 1000.0 * acc[k] / (iters - 100) : 0.0);
+            fprintf(stderr, "\n");
+            cudaEventDestroy(e0); cudaEventDestroy(e1);
+        } else
+        for (int done = 0; done < max_iters; done += LS_CHUNK) {
+            HL_CUDA_OK(cudaGraphLaunch(L->exec, st));
+            HL_CUDA_OK(cudaMemcpyAsync(L->h_nact, H.n_act + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+            HL_CUDA_OK(cudaStreamSynchronize(st));             // also keeps h_call stable until it was consumed
+            if (*L->h_nact == 0) break;
+        }
+        ls_finalize<<<L->grid, LS_THREADS, 0, st>>>(L->d_call);
+        HL_CUDA_OK(cudaGetLastError());
+        if (base + nb_max < n_scen) HL_CUDA_OK(cudaStreamSynchronize(st));   // the pinned call block is rewritten next
+    }
+    return 0;
 }
 
 static size_t astar_smem() { return sizeof(AwSmem) * AW_WARPS; }
@@ -658,7 +810,20 @@ extern "C" int hl_hybrid_astar_batch(hl_ctx* ctx, const hl_env_batch* envs, cons
     // variant: "spec" = two warps per scenario with the analytic shot decoupled (hl_astar_spec.cuh),
     // "warp" = one warp per scenario.  HL_ASTAR_VARIANT overrides the default for A/B runs.
     const char* var = getenv("HL_ASTAR_VARIANT");
+    const bool level = var ? (strcmp(var, "level") == 0) : false;
     const bool spec = var ? (strcmp(var, "warp") != 0) : true;
+    cudaStream_t st = (cudaStream_t)stream;
+    AwOut O;
+    O.results = d_results; O.expanded_keys = d_expanded_keys;
+    O.keys_capacity = (long long)keys_capacity; O.keys_cursor = d_keys_cursor;
+    O.path_x = d_path_x; O.path_y = d_path_y; O.path_yaw = d_path_yaw; O.path_k = d_path_k; O.path_dir = d_path_dir;
+    O.path_capacity = (long long)path_capacity; O.path_cursor = d_path_cursor;
+    O.phase_cycles = (unsigned long long*)(ctx->d_counters + 16);
+    if (level) {
+        HL_CUDA_OK(cudaMemsetAsync(d_path_cursor, 0, sizeof(unsigned long long), st));
+        HL_CUDA_OK(cudaMemsetAsync(d_keys_cursor, 0, sizeof(unsigned long long), st));
+        return ls_run(ctx, envs, d_scen, n_scen, P, O, st);
+    }
     const int slots = spec ? AQ_SLOTS : AW_WARPS;
     const int threads = spec ? AQ_SLOTS * AQ_WARPS_PER_SLOT * 32 : AW_WARPS * 32;
     const size_t smem = spec ? sizeof(AqSmem) * AQ_SLOTS : astar_smem();
@@ -686,16 +851,9 @@ extern "C" int hl_hybrid_astar_batch(hl_ctx* ctx, const hl_env_batch* envs, cons
         HL_CUDA_OK(cudaMalloc(&ctx->astar_ws, need));
         ctx->astar_ws_bytes = need;
     }
-    cudaStream_t st = (cudaStream_t)stream;
     HL_CUDA_OK(cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned int), st));
     HL_CUDA_OK(cudaMemsetAsync(d_path_cursor, 0, sizeof(unsigned long long), st));
     HL_CUDA_OK(cudaMemsetAsync(d_keys_cursor, 0, sizeof(unsigned long long), st));
-    AwOut O;
-    O.results = d_results; O.expanded_keys = d_expanded_keys;
-    O.keys_capacity = (long long)keys_capacity; O.keys_cursor = d_keys_cursor;
-    O.path_x = d_path_x; O.path_y = d_path_y; O.path_yaw = d_path_yaw; O.path_k = d_path_k; O.path_dir = d_path_dir;
-    O.path_capacity = (long long)path_capacity; O.path_cursor = d_path_cursor;
-    O.phase_cycles = (unsigned long long*)(ctx->d_counters + 16);
     if (spec)
         k_hybrid_astar_s<<<grid, threads, smem, st>>>(envs->dev, d_scen, n_scen, P, (char*)ctx->astar_ws, stride,
                                                       ctx->d_counters, O);

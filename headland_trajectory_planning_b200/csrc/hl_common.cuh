@@ -71,6 +71,8 @@ struct hl_ctx {
     size_t stage_bytes;
     void* env_cache;          // device block of the last freed environment batch, reused by the next upload
     size_t env_cache_bytes;
+    void* ls_state;           // level-synchronous search: graph, streams, pools (hl_astar.cu)
+    void (*ls_free)(void*);
 };
 
 void hl_set_error(const char* fmt, ...);

@@ -48,6 +48,8 @@ extern "C" int hl_ctx_create(hl_ctx** out, int device) {
     c->stage_bytes = 0;
     c->env_cache = nullptr;
     c->env_cache_bytes = 0;
+    c->ls_state = nullptr;
+    c->ls_free = nullptr;
     if (cudaMalloc(&c->d_counters, 256 * sizeof(unsigned int)) != cudaSuccess) {
         hl_set_error("hl_ctx_create: cudaMalloc failed");
         delete c;
@@ -65,6 +67,7 @@ extern "C" void hl_ctx_destroy(hl_ctx* ctx) {
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->stage) cudaFreeHost(ctx->stage);
     if (ctx->env_cache) cudaFree(ctx->env_cache);
+    if (ctx->ls_state && ctx->ls_free) ctx->ls_free(ctx->ls_state);
     delete ctx;
 }
 

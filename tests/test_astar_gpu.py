@@ -75,11 +75,15 @@ def test_start_blocked(built_library):
     assert got == ([], [], [], [], [], 0)
 
 
-def test_golden_scenarios_batch(built_library):
+@pytest.mark.parametrize("variant", ["spec", "warp", "level"])
+def test_golden_scenarios_batch(built_library, variant, monkeypatch):
     """Config-5 scenarios 0..N-1 in ONE batched launch vs the committed oracle results
     (tests/golden/astar_golden.npz, generator oracle/gen_golden.py): Y-park feasibility
-    booleans, status, counter, the full expanded-key sequence and the path of every scenario."""
+    booleans, status, counter, the full expanded-key sequence and the path of every scenario.
+    Every search-kernel variant (two warps per scenario with the shot decoupled = default, one warp
+    per scenario, level-synchronous graph of phase kernels) must give the same answer."""
     import os
+    monkeypatch.setenv("HL_ASTAR_VARIANT", variant)
     from headland_trajectory_planning_b200 import ops, scenarios as SC, sweep
     from headland_trajectory_planning_b200.env_batch import EnvBatch
     from headland_trajectory_planning_b200.hybrid_a_star_search import unpack_path

@@ -18,5 +18,5 @@ for rep in range(int(os.environ.get('REPS', '6'))):
     times.append(round(a.elapsed_time(b), 1))
 print("ms", times, "min", min(times), "median", sorted(times)[len(times) // 2])
 ph = ops.astar_phase_cycles()
-tot = sum(ph.values())
+tot = sum(ph.values()) or 1
 print({k: round(100 * v / tot, 1) for k, v in ph.items()})
