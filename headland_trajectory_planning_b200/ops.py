@@ -58,6 +58,27 @@ def path_reduce(envs, pose_bad, path_start):
     return out
 
 
+def ypark_paths(cand, step):
+    """Candidate paths of the Y-type parking sweep (K5, ``hl_ypark_paths``).  ``cand``: [n,8] float64 rows
+    (backward_length, forward_length, signed backward_steer, signed forward_steer, end_x, end_y, end_yaw,
+    wheel_base).  Returns (poses [total,3] float64 CUDA tensor, offsets [n+1] int64 host array)."""
+    torch = _torch()
+    lib = _lib.load_library()
+    dev = _device()
+    cand = np.ascontiguousarray(np.asarray(cand, dtype=np.float64).reshape(-1, 8))
+    n = cand.shape[0]
+    counts = (np.rint(cand[:, 0] / step) + np.rint(cand[:, 1] / step) + 2).astype(np.int64)   # Python round()
+    offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    poses = torch.empty((int(offsets[-1]), 3), dtype=torch.float64, device=dev)
+    if n == 0:
+        return poses, offsets
+    d_cand = torch.from_numpy(cand).to(dev)
+    d_off = torch.from_numpy(offsets).to(dev)
+    _lib.check(lib.hl_ypark_paths(_lib.get_ctx(dev.index), _lib.ptr(d_cand), _lib.ptr(d_off), n, float(step),
+                                  _lib.ptr(poses), _lib.stream_ptr()), "hl_ypark_paths")
+    return poses, offsets
+
+
 def measure_fp32_peak(device=None):
     lib = _lib.load_library()
     v = C.c_double()

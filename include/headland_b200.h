@@ -175,6 +175,23 @@ int hl_collision_check(hl_ctx* ctx, const hl_env_batch* envs, const int32_t* d_e
 int hl_path_reduce(hl_ctx* ctx, const uint8_t* d_pose_bad, const int64_t* d_path_start,
                    int64_t n_paths, uint8_t* d_path_bad, void* stream);
 
+/* ---- K5 Y-type parking candidates ------------------------
+ * Replaces the loop body of search_y_type_parking_path
+ * (path_planner/headland_path_planning.py:405-427): get_y_type_parking_path (:488-516, two
+ * calculate_motion_path rollouts :455-485) + get_path_in_odom (:519-527) for EVERY candidate
+ * of one or many sweeps in one launch.
+ *   d_cand    [n][8] float64: backward_length, forward_length, backward_steer (signed),
+ *             forward_steer (signed), end_x, end_y, end_yaw, wheel_base
+ *   d_offsets [n+1] int64: first pose of each candidate in d_poses;
+ *             offsets[i+1]-offsets[i] must be round(bl/step) + round(fl/step) + 2
+ *             (Python round); a mismatching candidate is written as NaN poses (= infeasible)
+ *   d_poses   [offsets[n]][3] float64 out: x, y, yaw in the odom frame, in the reference's row
+ *             order (forward arc reversed, then backward arc reversed, ending on the end pose)
+ * Feed d_poses to hl_collision_check and d_offsets to hl_path_reduce; the first feasible
+ * candidate in loop order is the reference's result. */
+int hl_ypark_paths(hl_ctx* ctx, const double* d_cand, const int64_t* d_offsets, int64_t n, double step,
+                   double* d_poses, void* stream);
+
 /* ---- K2/K3 Reeds-Shepp --------------------------------------------------------
  * Replaces reeds_shepp.calc_all_paths (path_planner/utils/reeds_shepp.py:39-65):
  * generate_path + set_path dedup (:565-582, :68-87) and the sample count of

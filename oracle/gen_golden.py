@@ -3,6 +3,8 @@ container, where ``/root/reference`` exists):
 
     python -m oracle.gen_golden rs df        # from the reference's OWN modules (pins the ports)
     python -m oracle.gen_golden astar N      # oracle Hybrid A* on config-5 scenarios 0..N-1
+    python -m oracle.gen_golden astar_ref N  # the REFERENCE's own search loop on scenarios 0..N-1
+    python -m oracle.gen_golden ypark N      # the REFERENCE's own Y-park sweep on N scenarios
 
 TEST INFRASTRUCTURE (see ``oracle/__init__.py``).
 
@@ -14,6 +16,15 @@ TEST INFRASTRUCTURE (see ``oracle/__init__.py``).
 * ``astar_golden.npz`` -- the ORACLE's search results (status, counter, expanded keys, path)
   on config-5 scenarios: lets the GPU tests check node-sequence parity at a scale the oracle
   cannot run on the GPU box in test time.  (parity unpinned at the GEOS/heapdict boundary.)
+* ``astar_ref_golden.npz`` -- ``HybridAStarSearch.hybrid_a_star_search`` of the REFERENCE
+  (``path_planner/hybrid_a_star_search.py`` imported unmodified through
+  ``ref_loader.load_planner``: shapely/dubins stubbed, ``heapdict`` -> ``oracle.heapdict_port``)
+  fed the oracle's environment / car / heuristic objects: pins the oracle's search loop, costs,
+  rollout and Reeds-Shepp shot against the reference itself; only the GEOS predicates and the
+  heapdict port stay restated.
+* ``ypark_golden.npz`` -- ``search_y_type_parking_path`` of the REFERENCE
+  (``headland_path_planning.py:382-451``, same loader) on config-5 environments with the
+  notebook's and the function's default parameter sets.
 """
 import math
 import os
@@ -148,6 +159,92 @@ def gen_astar(n):
     print("astar_golden.npz:", n, "scenarios; counters", [r["counter"] for r in res][:20], "...")
 
 
+YPARK_PARAM_SETS = [
+    # (max_steer_backward, max_steer_forward, max_backward_distance, max_forward_distance,
+    #  min_forward_distance, min_backward_distance, min_steer_backward, min_steer_forward, step)
+    (0.15, 0.55, 3.0, 2.0, 1.0, 1.0, 0.0, 0.5, 0.2),        # test/obca.ipynb cell 9
+    (0.35, 0.55, 2.0, 2.5, 1.4, 0.7, 0.22, 0.50, 0.1),      # headland_planner_y_type_park defaults (:131-139)
+    (0.4, 0.45, 3.5, 2.0, 1.4, 0.7, 0.3, 0.3, 0.1),         # search_y_type_parking_path defaults (:388-396)
+]
+
+
+def _quiet(fn, *a, **k):
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def _ypark_one(i):
+    from . import planner as OP
+    from . import ref_loader
+    sys.path.insert(0, os.path.dirname(HERE))
+    from headland_trajectory_planning_b200 import scenarios as SC
+    H = ref_loader.load_planner("headland_path_planning")
+    sp = SC.scenario_spec(i)
+    env = OP.OrchardGeometryEnvironment(sp["rows"], [], tree_width=sp["tree_width"], headland_width=sp["headland_width"])
+    car = OP.CarModel(**sp["car"])
+    out = []
+    # the row-enter pose pulled back into the headland by 0 / 1.5 / 3 m so that the sweeps end in a mix of
+    # early hits, late hits and failures
+    shift = (0.0, 1.5, 3.0)[i % 3]
+    end = np.array(sp["end"], dtype=np.float64)
+    end[0] -= shift * math.cos(end[2])
+    end[1] -= shift * math.sin(end[2])
+    for k, ps in enumerate(YPARK_PARAM_SETS):
+        bdir = H.get_backward_steer_dir_for_y_type_parking(sp["start"], end)
+        path, par = _quiet(H.search_y_type_parking_path, car, env, end, bdir, -bdir, *ps[:8], step_size=ps[8], debug=True)
+        out.append(dict(index=i, pset=k, bdir=float(bdir), found=len(par) > 0, end=end,
+                        par=np.array(par if len(par) else [np.nan] * 4, dtype=np.float64),
+                        path=np.asarray(path, dtype=np.float64).reshape(-1, 5)))
+    return out
+
+
+def gen_ypark(n):
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(os.cpu_count()) as pool:
+        res = [r for rs in pool.map(_ypark_one, range(n), chunksize=1) for r in rs]
+    np.savez_compressed(
+        os.path.join(GOLD, "ypark_golden.npz"), param_sets=np.array(YPARK_PARAM_SETS),
+        index=np.array([r["index"] for r in res]), pset=np.array([r["pset"] for r in res]),
+        bdir=np.array([r["bdir"] for r in res]), found=np.array([r["found"] for r in res]),
+        end=np.array([r["end"] for r in res]),
+        par=np.array([r["par"] for r in res]), path_len=np.array([len(r["path"]) for r in res]),
+        path=np.concatenate([r["path"] for r in res]))
+    print("ypark_golden.npz:", len(res), "sweeps;", int(sum(r["found"] for r in res)), "found a path")
+
+
+def _astar_ref_one(i):
+    from . import baseline as OB
+    from . import planner as OP
+    from . import ref_loader
+    sys.path.insert(0, os.path.dirname(HERE))
+    from headland_trajectory_planning_b200 import scenarios as SC
+    R = ref_loader.load_planner("hybrid_a_star_search")
+    sp = SC.scenario_spec(i)
+    scn = SC.finalize(sp, OB.candidate_feasibility(sp))
+    env = OP.OrchardGeometryEnvironment(scn["rows"], [], tree_width=scn["tree_width"], headland_width=scn["headland_width"])
+    car = OP.CarModel(**scn["car"])
+    heur = OP.ReferenceLineHeuristic(scn["waypoints"], scn["goal"], car)
+    s = _quiet(R.HybridAStarSearch, scn["start"], scn["goal"], env, car, heur, motion_type="King",
+               plan_resolution=scn["step_size"])
+    x, y, yaw, dirs, ks, counter = _quiet(s.hybrid_a_star_search, max_nodes=400)
+    path = np.stack([np.asarray(x, float), np.asarray(y, float), np.asarray(yaw, float), np.asarray(ks, float),
+                     np.asarray(dirs, float)], axis=1).reshape(-1, 5)
+    return dict(index=i, counter=int(counter), path=path)
+
+
+def gen_astar_ref(n):
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(os.cpu_count()) as pool:
+        res = pool.map(_astar_ref_one, range(n), chunksize=1)
+    np.savez_compressed(os.path.join(GOLD, "astar_ref_golden.npz"), index=np.array([r["index"] for r in res]),
+                        counter=np.array([r["counter"] for r in res]), path_len=np.array([len(r["path"]) for r in res]),
+                        path=np.concatenate([r["path"] for r in res]))
+    print("astar_ref_golden.npz:", n, "scenarios run by the reference's own search loop; counters",
+          [r["counter"] for r in res][:24])
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     args = sys.argv[1:]
@@ -157,3 +254,7 @@ if __name__ == "__main__":
         gen_df()
     if "astar" in args:
         gen_astar(int(args[args.index("astar") + 1]))
+    if "astar_ref" in args:
+        gen_astar_ref(int(args[args.index("astar_ref") + 1]))
+    if "ypark" in args:
+        gen_ypark(int(args[args.index("ypark") + 1]))

@@ -529,3 +529,94 @@ class HybridAStarSearch:
                         self.stats["pushes"] += 1
         x, y, yaw, ks, dirs = self.get_path_from_expanded_nodes(closed_set)
         return (x, y, yaw, dirs, ks, counter)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the Y-type parking parameter sweep that runs right before every Hybrid A*
+# call and produces its goal pose (path_planner/headland_path_planning.py:352-527).  Pinned against the
+# reference's OWN functions run in the build container (oracle/ref_loader.load_planner, tests/golden/
+# ypark_golden.npz): only ``check_path_feasibility`` is the restated geometry.
+
+def get_backward_steer_dir_for_y_type_parking(start_pose, end_pose):
+    """headland_path_planning.py:360-368."""
+    if end_pose[1] - start_pose[1] > 0:
+        return np.sign(1 * math.cos(start_pose[2]))
+    return np.sign(-1 * math.cos(start_pose[2]))
+
+
+def calculate_motion_path(init_pose, motion_command, search_length, wheel_base, step):
+    """headland_path_planning.py:455-485: [P+1, 5] rows (x, y, yaw, curvature, direction)."""
+    steer_angle, speed_direction = motion_command[0], motion_command[1]
+    num_steps = round(search_length / step)
+    yaw_step = speed_direction * step / wheel_base * math.tan(steer_angle)
+    init_yaw = angle_wrap(init_pose[-1] + yaw_step)
+    yaws = angle_wrap(np.linspace(init_yaw, init_yaw + yaw_step * num_steps, num_steps + 1))
+    xs = init_pose[0] + np.cumsum(step * np.cos(yaws[:-1]) * speed_direction)
+    ys = init_pose[1] + np.cumsum(step * np.sin(yaws[:-1]) * speed_direction)
+    path = np.vstack([init_pose, np.vstack([xs, ys, yaws[1:]]).T])
+    curvature = math.tan(steer_angle) / wheel_base if abs(steer_angle) > 0.00001 else 0
+    return np.hstack((path, np.ones((len(path), 1)) * curvature, np.ones((len(path), 1)) * speed_direction))
+
+
+def get_y_type_parking_path(car_model, backward_length, backward_steer, forward_length, forward_steer, step):
+    """headland_path_planning.py:488-516: planned inversely from the end pose, in the base-link frame."""
+    back_path = calculate_motion_path([0, 0, 0], [backward_steer, -1], backward_length, car_model.WHEEL_BASE, step)
+    forward_path = calculate_motion_path(back_path[-1, :3], [forward_steer, 1], forward_length,
+                                         car_model.WHEEL_BASE, step)
+    back_path[:, -1] = 1
+    back_path = back_path[::-1]
+    forward_path[:, -1] = -1
+    forward_path = forward_path[::-1]
+    return np.vstack([forward_path, back_path])
+
+
+def get_path_in_odom(end_pose, path):
+    """headland_path_planning.py:519-527 with utils/transformation.py:7-61 and
+    navigation_utils.py:196-203 restated for a planar pose: the yaw offset is atan2(sin, cos) of the end
+    yaw (rotationMatrixToEulerAngles), positions go through the homogeneous 4x4 product (row sums in the
+    order x*R00 + y*R01 + 0*R02 + 1*tx; BLAS may fuse/reorder, hence the 1e-12 tolerance of the pin)."""
+    c, s = math.cos(end_pose[2]), math.sin(end_pose[2])
+    out = np.copy(path)
+    out[:, 2] += math.atan2(s, c)
+    x, y = path[:, 0], path[:, 1]
+    out[:, 0] = c * x + (-s) * y + end_pose[0]
+    out[:, 1] = s * x + c * y + end_pose[1]
+    return out
+
+
+def y_park_candidates(backward_steer_dir, forward_steer_dir, max_steer_backward=0.4, max_steer_forward=0.45,
+                      max_backward_distance=3.5, max_forward_distance=2.0, min_forward_distance=1.4,
+                      min_backward_distance=0.7, min_steer_backward=0.3, min_steer_forward=0.3):
+    """The 4-deep candidate enumeration of search_y_type_parking_path (:405-420) in loop order:
+    rows (backward_length, forward_length, steer_backward, steer_forward), unsigned steers."""
+    steer_backwards = list(np.arange(min_steer_backward, max_steer_backward + 0.1, 0.1))
+    if np.max(steer_backwards) < max_steer_backward:
+        steer_backwards.append(max_steer_backward)
+    steer_forwards = list(np.arange(min_steer_forward, max_steer_forward + 0.1, 0.1))
+    if np.max(steer_forwards) < max_steer_forward:
+        steer_forwards.append(max_steer_forward)
+    out = []
+    for backward_length in np.arange(max_backward_distance, min_backward_distance, -0.1):
+        for forward_length in np.arange(max_forward_distance, min_forward_distance, -0.1):
+            for steer_backward in steer_backwards:
+                for steer_forward in steer_forwards:
+                    out.append((backward_length, forward_length, steer_backward, steer_forward))
+    return np.array(out, dtype=np.float64).reshape(-1, 4)
+
+
+def search_y_type_parking_path(car_model, config_env, end_pose, backward_steer_dir, forward_steer_dir,
+                               max_steer_backward=0.4, max_steer_forward=0.45, max_backward_distance=3.5,
+                               max_forward_distance=2.0, min_forward_distance=1.4, min_backward_distance=0.7,
+                               min_steer_backward=0.3, min_steer_forward=0.3, step_size=0.1, debug=False):
+    """headland_path_planning.py:382-451: the first feasible candidate in loop order wins."""
+    if not config_env.check_path_feasibility(car_model, np.array([end_pose])):
+        return ([], []) if debug else []
+    cands = y_park_candidates(backward_steer_dir, forward_steer_dir, max_steer_backward, max_steer_forward,
+                              max_backward_distance, max_forward_distance, min_forward_distance,
+                              min_backward_distance, min_steer_backward, min_steer_forward)
+    for bl, fl, sb, sf in cands:
+        local = get_y_type_parking_path(car_model, bl, sb * backward_steer_dir, fl, sf * forward_steer_dir, step_size)
+        path = get_path_in_odom(end_pose, local)
+        if config_env.check_path_feasibility(car_model, path):
+            return (path, [bl, fl, sb, sf]) if debug else path
+    return ([], []) if debug else []

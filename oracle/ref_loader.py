@@ -45,3 +45,73 @@ def load(name):
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
+
+
+class _Anything:
+    """Attribute sink standing in for classes / functions of an absent third-party package."""
+
+    def __init__(self, *a, **k):
+        pass
+
+    def __call__(self, *a, **k):
+        raise RuntimeError("stub of an absent third-party package was called")
+
+    def __getattr__(self, name):
+        return _Anything()
+
+
+class _StubModule(types.ModuleType):
+    __path__ = []
+
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return _Anything
+
+
+_ABSENT = ("shapely", "heapdict", "dubins", "skspatial", "matplotlib", "casadi", "cv2")
+
+
+def load_planner(name, heapdict_port=True):
+    """Import ``path_planner/<name>.py`` of the reference FOR REAL, with the absent third-party packages
+    (shapely, heapdict, dubins, skspatial, ...) replaced by inert stubs.  Everything that does not touch those
+    packages -- the Y-type parking sweep, the motion-path rollout, the odom transform
+    (``headland_path_planning.py:382-527``) -- then runs as the reference wrote it; geometry objects are passed
+    in duck-typed (the oracle's environment / car model).  With ``heapdict_port`` the ``heapdict`` import
+    resolves to ``oracle.heapdict_port`` so that the reference's own search loop
+    (``hybrid_a_star_search.py``) runs too.  ``sys.modules`` / ``sys.path`` are restored."""
+    import importlib
+    import importlib.abc
+    import importlib.machinery
+
+    class _Finder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+        def find_spec(self, fullname, path=None, target=None):
+            if fullname.split(".")[0] in _ABSENT:
+                return importlib.machinery.ModuleSpec(fullname, self, is_package=True)
+            return None
+
+        def create_module(self, spec):
+            return _StubModule(spec.name)
+
+        def exec_module(self, module):
+            pass
+
+    saved_mods = dict(sys.modules)
+    saved_path = list(sys.path)
+    finder = _Finder()
+    try:
+        sys.meta_path.insert(0, finder)
+        if heapdict_port:
+            from . import heapdict_port as _hp
+            hd = types.ModuleType("heapdict")
+            hd.heapdict = _hp.HeapDict
+            sys.modules["heapdict"] = hd
+        sys.path.insert(0, os.path.join(REFERENCE_ROOT, "path_planner", "utils"))   # notebooks put both on sys.path
+        sys.path.insert(0, os.path.join(REFERENCE_ROOT, "path_planner"))
+        return importlib.import_module(name)
+    finally:
+        sys.meta_path.remove(finder)
+        for k in list(sys.modules):
+            if k not in saved_mods:
+                del sys.modules[k]
+        sys.path[:] = saved_path
