@@ -99,6 +99,9 @@ def load_planner(name, heapdict_port=True):
     saved_mods = dict(sys.modules)
     saved_path = list(sys.path)
     finder = _Finder()
+    # flat stubs an earlier load() left behind (e.g. a non-package ``matplotlib``) would shadow the finder
+    stash = {k: sys.modules.pop(k) for k in list(sys.modules)
+             if k.split(".")[0] in _ABSENT and getattr(sys.modules[k], "__file__", None) is None}
     try:
         sys.meta_path.insert(0, finder)
         if heapdict_port:
@@ -114,4 +117,5 @@ def load_planner(name, heapdict_port=True):
         for k in list(sys.modules):
             if k not in saved_mods:
                 del sys.modules[k]
+        sys.modules.update(stash)
         sys.path[:] = saved_path
