@@ -201,6 +201,7 @@ __device__ __noinline__ double warp_state_cost(const EnvBatchDev& eb, const EnvD
     if (n <= 0) return 0.0;
     // pass 1: minimum squared distance (ordering filter only)
     double best = INFINITY;
+#pragma unroll 1
     for (int i = lane; i < n; i += 32) {
         double dx = gx[i] - x, dy = gy[i] - y;
         best = fmin(best, dx * dx + dy * dy);
@@ -210,6 +211,7 @@ __device__ __noinline__ double warp_state_cost(const EnvBatchDev& eb, const EnvD
     const double thr = best * (1.0 + 1e-9) + 1e-300;
     double bh = INFINITY;
     int bi = 0x7fffffff;
+#pragma unroll 1
     for (int i = lane; i < n; i += 32) {
         double dx = xsub(gx[i], x), dy = xsub(gy[i], y);
         if (dx * dx + dy * dy <= thr) {

@@ -79,11 +79,26 @@ static_assert(sizeof(AqSmem) * AQ_SLOTS <= 227 * 1024, "per-CTA shared memory ex
 // Alignment of the AQ_SLOTS warps of one role (named barrier `id`, all threads of those warps) with an AND
 // reduction: keeps the role's warps inside the same code region (instruction cache) and tells them when
 // every one of them is finished.
+#ifndef AQ_ALIGN
+#define AQ_ALIGN 1                     // 0: no role alignment (each warp leaves when its own queue is drained)
+#endif
 __device__ __forceinline__ bool role_barrier_all(int id, int nthreads, bool pred) {
+#if !AQ_ALIGN
+    return pred;
+#endif
     int r;
     asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.s32 p, %1, 0;\n\tbarrier.red.and.pred q, %2, %3, p;\n\tselp.s32 %0, 1, 0, q;\n\t}"
                  : "=r"(r) : "r"((int)pred), "r"(id), "r"(nthreads) : "memory");
     return r != 0;
+}
+
+#ifndef AQ_MID
+#define AQ_MID 0                       // extra alignment points inside an iteration (0 none, 1 one per role, 2 two for the expander)
+#endif
+__device__ __forceinline__ void role_sync(int id, int nthreads) {
+#if AQ_ALIGN
+    asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
+#endif
 }
 
 __device__ __forceinline__ int warp_read(volatile int* p, int lane) {
@@ -243,7 +258,11 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
         const double stepn = xmul(P.res, P.maxc);
         while (true) {
             if (role_barrier_all(1, AQ_SLOTS * AQ_SHOOTERS * 32, finished)) break;   // alignment point of the shooters
-            if (finished) continue;
+            bool shooting = false, success = false;
+            int m = 0;
+            double q0[3] = {0.0, 0.0, 0.0}, cq = 1.0, sq = 0.0;
+            do {
+            if (finished) break;
             if (active) STICK(PH_OUTPUT);     // shooter time in the alignment barrier / waiting for pops
             if (!active) {
                 const int st = warp_read(&S.state, lane);
@@ -270,11 +289,9 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                     __syncwarp();
                     i = shooter;                     // pops shooter, shooter + AQ_SHOOTERS, ...
                     active = true;
-                } else if (st == ST_DONE) { finished = true; continue; }
-                else { __nanosleep(200); continue; }
+                } else if (st == ST_DONE) { finished = true; break; }
+                else { __nanosleep(200); break; }
             }
-            const EnvDesc& D = *Dp;
-            bool success = false;
             {
                 // is pop i available, has the expander stopped short of it, or did an EARLIER pop already succeed?
                 const int done = warp_read(&S.ew_done, lane);
@@ -289,9 +306,9 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                     if (lane == 0) { __threadfence_block(); T.done_epoch = my_epoch; }
                     __syncwarp();
                     active = false;
-                    continue;
+                    break;
                 }
-                if (!have) { __nanosleep(100); continue; }
+                if (!have) { __nanosleep(100); break; }
                 __threadfence_block();
                 if (lane == 0) {
                     const int cur = W.corder[i];
@@ -301,7 +318,7 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                     T.rs_pick = -1;
                 }
                 __syncwarp();
-                const double q0[3] = {T.sx, T.sy, T.syaw};
+                q0[0] = T.sx; q0[1] = T.sy; q0[2] = T.syaw;
                 for (int c = lane; c < HL_RS_CANDIDATES; c += 32) {
                     double l[HL_RS_MAX_SEGS] = {0, 0, 0, 0, 0};
                     bool ok = rs_candidate(c, T.rs_prob, l);
@@ -312,7 +329,6 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                 STICK(PH_RS_CAND);
                 if (lane < RS_N_GROUPS) rs_select_group(lane, T.rs_valid, T.rs_lens, T.rs_accept, T.rs_Lc);
                 __syncwarp();
-                int m;
                 {
                     const int a0 = T.rs_accept[lane];
                     const int a1 = (lane + 32 < HL_RS_CANDIDATES) ? T.rs_accept[lane + 32] : 0;
@@ -337,14 +353,24 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                     if (bad) success = true;     // the reference would raise here: report it as the end of the search
                 }
                 STICK(PH_RS_SELECT);
-                const double cq = m_cos(-q0[2]), sq = m_sin(-q0[2]);
+                cq = m_cos(-q0[2]); sq = m_sin(-q0[2]);
                 if (lane < m && lane < AQ_MAX_PLANS) {
                     int c = T.rs_acc[T.rs_order[lane]];
                     rs_make_plan(c, T.rs_lens[c], P.maxc, stepn, T.plans[lane]);
-                    rs_plan_world32(T.plans[lane], q0, cq, sq, D.origin);
+                    rs_plan_world32(T.plans[lane], q0, cq, sq, Dp->origin);
                 }
                 __syncwarp();
                 STICK(PH_RS_PLAN);
+                shooting = true;
+            }
+            } while (0);
+#if AQ_MID >= 1
+            role_sync(1, AQ_SLOTS * AQ_SHOOTERS * 32);                  // shooters enter the sampling code together
+            if (shooting) STICK(PH_OUTPUT);
+#endif
+            if (!shooting) continue;
+            const EnvDesc& D = *Dp;
+            {
                 for (int r = 0; r < m; ++r) {
                     const int k = T.rs_order[r];
                     const int c = T.rs_acc[k];
@@ -417,14 +443,16 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
     const EnvDesc* Dp = eb.desc;
     while (true) {
         if (role_barrier_all(2, AQ_SLOTS * 32, finished)) break;
-        if (finished) continue;
+        bool expanding = false;
+        do {
+        if (finished) break;
         ETICK(PH_SETUP);                 // time spent in the alignment barrier (+ attach / wait modes)
         if (mode == 0) {
         // ---- next scenario
         int sc = 0;
         if (lane == 0) sc = (int)atomicAdd(work_counter, 1u);
         sc = __shfl_sync(FULL, sc, 0);
-        if (sc >= n_scen) { if (lane == 0) { __threadfence_block(); S.state = ST_DONE; } finished = true; continue; }
+        if (sc >= n_scen) { if (lane == 0) { __threadfence_block(); S.state = ST_DONE; } finished = true; break; }
         if (lane == 0) {
             const HlScenario s = scen[sc];
             S.scen = sc; S.env = s.env_id;
@@ -481,7 +509,7 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
             if (lane == 0) { S.status = S.ew_status; S.fin_closed = 0; S.fin_counter = 0; }
             __syncwarp();
             finalize_spec(S, W, P, O, lane);
-            continue;
+            break;
         }
         // hand the scenario to the shooter
         if (lane == 0) { __threadfence_block(); S.state = ST_SEARCH; S.epoch = S.epoch + 1; }
@@ -489,10 +517,10 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
         my_epoch = warp_read(&S.epoch, lane);
 
             mode = 1;
-            continue;
+            break;
         }
-        const EnvDesc& D = *Dp;
         if (mode == 1) {
+            const EnvDesc& D = *Dp;
             if (lane == 0) {
                 if (*(volatile int*)&S.shot_best != AQ_NO_HIT) S.ew_status = HL_STATUS_OK;   // a shooter ended the search
                 else if (S.counter > P.max_nodes) S.ew_status = HL_STATUS_MAX_NODES;
@@ -523,7 +551,15 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
             if (lane < HL_MAX_PRIMS) { S.phit[lane] = 0; S.pneed[lane] = 1; }
             __syncwarp();
             ETICK(PH_POP);
-            if (S.ew_status >= 0) { mode = 2; goto stopped; }
+            if (S.ew_status >= 0) mode = 2; else expanding = true;
+        }
+        } while (0);
+#if AQ_MID >= 1
+        role_sync(2, AQ_SLOTS * 32);                         // expanders enter the rollout / filter code together
+        if (expanding) ETICK(PH_SETUP);
+#endif
+        const EnvDesc& D = *Dp;
+        if (expanding) {
             {
             const int n = S.nsteps, np1 = n + 1;
             const int total = P.n_prims * np1;
@@ -575,6 +611,15 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
             }
             __syncwarp();
             ETICK(PH_EXACT);
+            }
+        }
+#if AQ_MID >= 2
+        role_sync(2, AQ_SLOTS * 32);                         // ... and the cost / heuristic / merge code
+        if (expanding) ETICK(PH_SETUP);
+#endif
+        if (expanding) {
+            {
+            const int n = S.nsteps, np1 = n + 1;
             if (lane < P.n_prims && !S.phit[lane]) {
                 const int p = lane;
                 double len = 0.0;
@@ -637,10 +682,9 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
             __syncwarp();
             }
             ETICK(PH_MERGE);
-            if (S.ew_status >= 0) { mode = 2; goto stopped; }
-            continue;
+            if (S.ew_status >= 0) mode = 2;
         }
-    stopped:
+        if (finished) continue;
         if (mode == 2 && !S.ew_done) {
         // ---- tell the shooter how far its shots are needed, wait for it, assemble the result
         if (lane == 0) {

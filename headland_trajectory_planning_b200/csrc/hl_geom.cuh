@@ -432,6 +432,13 @@ static __device__ HL_CODE int corner_in_capsule(const float* sg, float wx, float
 //     crossing parity of C decides inside/outside when every edge is clear;
 //   * lane: one centre-to-segment distance accepts / rejects against (r_in - rho) / (r_out + rho)
 //     before the four corner distances are needed.
+// In the search kernels (HL_SHARED_CODE) code bytes are the bottleneck (32 KB instruction cache), so the runtime
+// loops of the filter are kept rolled there; K1 lets the compiler unroll them for throughput.
+#ifdef HL_SHARED_CODE
+#define HL_LOOP _Pragma("unroll 1")
+#else
+#define HL_LOOP
+#endif
 static __device__ HL_CODE int filter_part(const EnvSmem& E, float px, float py, float c, float s,
                                            const float* ext, unsigned flags, unsigned* which_ambig) {
     const float eps = E.eps;
@@ -446,6 +453,7 @@ static __device__ HL_CODE int filter_part(const EnvSmem& E, float px, float py, 
     if (flags & HL_CHECK_OBSTACLES) {
         bool a_obs = false;
         if (E.all_rect) {
+            HL_LOOP
             for (int k = 0; k < E.n_obs; ++k) {
                 const float* o = E.obs + HL_OBS32_STRIDE * k;
                 const float4 b0 = *reinterpret_cast<const float4*>(o + 20);      // flag, cx, cy, ax
@@ -469,6 +477,7 @@ static __device__ HL_CODE int filter_part(const EnvSmem& E, float px, float py, 
                 rx[j] = fmaf(c, lx[j], fmaf(-s, ly[j], px));
                 ry[j] = fmaf(s, lx[j], fmaf(c, ly[j], py));
             }
+            HL_LOOP
             for (int k = 0; k < E.n_obs; ++k) {                  // generic convex quads: 8 axes on vertices
                 const float* o = E.obs + HL_OBS32_STRIDE * k;
                 float sep = -INFINITY;
@@ -500,6 +509,7 @@ static __device__ HL_CODE int filter_part(const EnvSmem& E, float px, float py, 
         bool inside = false;
         unsigned near_mask = 0;                       // edges whose LINE the rectangle may touch (n <= 32 here)
         bool overflow = false;
+        HL_LOOP
         for (int i = 0; i < n; ++i) {
             const float* e = E.field + HL_FIELD32_STRIDE * i;
             const float4 r0 = *reinterpret_cast<const float4*>(e);               // Ax, Ay, Ex, Ey
@@ -562,6 +572,7 @@ static __device__ HL_CODE int filter_part(const EnvSmem& E, float px, float py, 
         const float rho = sqrtf(fmaf(hx, hx, hy * hy));
         const float rin = (float)HL_LANE_RIN - eps, rout = (float)HL_LANE_R + eps;
         bool accepted = false, need_corners = false;
+        HL_LOOP
         for (int i = 0; i < E.n_seg && !accepted; ++i) {
             const float* sg = E.seg + 4 * i;
             float ex = sg[2] - sg[0], ey = sg[3] - sg[1];
@@ -585,6 +596,7 @@ static __device__ HL_CODE int filter_part(const EnvSmem& E, float px, float py, 
             }
             bool one_holds_all = false;
             unsigned maybe = 0;                    // corner j is inside (or within the band of) some capsule
+            HL_LOOP
             for (int i = 0; i < E.n_seg; ++i) {
                 const float* sg = E.seg + 4 * i;
                 bool all_in = true;
@@ -612,6 +624,7 @@ static __device__ HL_CODE int filter_part(const EnvSmem& E, float px, float py, 
                         const float lyq = side ? ext[3] : ext[2];
                         const float wx = fmaf(c, lxq, fmaf(-s, lyq, px)), wy = fmaf(s, lxq, fmaf(c, lyq, py));
                         unsigned in = 0;
+                        HL_LOOP
                         for (int i = 0; i < E.n_seg; ++i) {
                             const float* sg = E.seg + 4 * i;
                             float ex = sg[2] - sg[0], ey = sg[3] - sg[1];
