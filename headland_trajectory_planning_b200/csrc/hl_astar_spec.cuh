@@ -233,6 +233,7 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
     const int hmask = P.hash_size - 1;
     const unsigned FLAGS = HL_CHECK_OBSTACLES | HL_CHECK_BOUNDARY | HL_CHECK_LANE;
     if (role == 0) {
+#pragma unroll 1
         for (int i = lane; i < P.hash_size; i += 32) W.hkey[i] = KEY_EMPTY;
         if (lane == 0) {
             S.state = ST_IDLE; S.epoch = 0; S.popped = 0; S.ew_done = 0; S.shot_best = AQ_NO_HIT;
@@ -319,6 +320,7 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                 }
                 __syncwarp();
                 q0[0] = T.sx; q0[1] = T.sy; q0[2] = T.syaw;
+#pragma unroll 1
                 for (int c = lane; c < HL_RS_CANDIDATES; c += 32) {
                     double l[HL_RS_MAX_SEGS] = {0, 0, 0, 0, 0};
                     bool ok = rs_candidate(c, T.rs_prob, l);
@@ -340,6 +342,7 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                     if (a1 == 1) { int k = n0 + __popc(b1 & lt); T.rs_acc[k] = lane + 32; T.rs_L[k] = T.rs_Lc[lane + 32]; }
                     m = bad ? 0 : n0 + __popc(b1);
                     __syncwarp();
+#pragma unroll 1
                     for (int k = lane; k < m; k += 32)
                         T.rs_prio[k] = rs_path_cost(T.sg, T.rs_acc[k], T.rs_lens[T.rs_acc[k]], P.max_steer,
                                                     P.reverse_cost, P.dir_change_cost, P.steer_cost);
@@ -371,6 +374,7 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
             if (!shooting) continue;
             const EnvDesc& D = *Dp;
             {
+#pragma unroll 1
                 for (int r = 0; r < m; ++r) {
                     const int k = T.rs_order[r];
                     const int c = T.rs_acc[k];
@@ -386,6 +390,7 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                     const int npts = plan.npts;
                     int infeasible = 0;
                     const int passes = (npts + 31) >> 5;
+#pragma unroll 1
                     for (int pass = 0; pass < passes && !infeasible; ++pass) {
                         const int j = lane * passes + pass;
                         int st2 = HL_FREE;
@@ -564,6 +569,7 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
             const int n = S.nsteps, np1 = n + 1;
             const int total = P.n_prims * np1;
             // yaws[0..n+1] of every primitive once (the pose yaw of step i is yaws[i+1]), one sincos each
+#pragma unroll 1
             for (int idx = lane; idx < P.n_prims * (np1 + 1); idx += 32) {
                 const int p = idx / (np1 + 1), i = idx - p * (np1 + 1);
                 const double ys = P.yaw_step[p];
@@ -583,6 +589,7 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
             __syncwarp();
             if (lane < P.n_prims) {
                 double ax = 0.0, ay = 0.0;
+#pragma unroll 1
                 for (int i = 0; i < np1; ++i) {
                     ax = (i == 0) ? S.tx[lane][0] : xadd(ax, S.tx[lane][i]);
                     ay = (i == 0) ? S.ty[lane][0] : xadd(ay, S.ty[lane][i]);
@@ -592,6 +599,7 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
             }
             __syncwarp();
             ETICK(PH_ROLLOUT);
+#pragma unroll 1
             for (int idx = lane; idx < total; idx += 32) {
                 const int p = idx / np1, j = idx - p * np1;
                 unsigned amb = 0;
@@ -602,6 +610,7 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
             if (lane == 0) S.e_checks += (unsigned long long)total;
             __syncwarp();
             ETICK(PH_FILTER);
+#pragma unroll 1
             for (int idx = lane; idx < total; idx += 32) {
                 const int p = idx / np1, j = idx - p * np1;
                 if (S.pamb[p][j] && !S.phit[p]) {
@@ -623,6 +632,7 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
             if (lane < P.n_prims && !S.phit[lane]) {
                 const int p = lane;
                 double len = 0.0;
+#pragma unroll 1
                 for (int i = 0; i + 1 < np1; ++i) {
                     double ds = hypot_cr(xsub(S.tx[p][i + 1], S.tx[p][i]), xsub(S.ty[p][i + 1], S.ty[p][i]));
                     len = (i == 0) ? ds : xadd(len, ds);
@@ -646,6 +656,7 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                 if (slot2 >= 0 && (W.nstate[slot2] == 1 || !(cost < W.ng[slot2]))) S.pneed[p] = 0;
             }
             __syncwarp();
+#pragma unroll 1
             for (int p = 0; p < P.n_prims; ++p) {
                 if (!S.phit[p] && S.pneed[p]) {
                     double h = warp_state_cost(eb, D, S.tx[p][n], S.ty[p][n], S.pyaw[p][n], lane);
@@ -655,6 +666,7 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
             __syncwarp();
             ETICK(PH_COST_HEUR);
             if (lane == 0) {
+#pragma unroll 1
                 for (int p = 0; p < P.n_prims; ++p) {
                     if (S.phit[p]) continue;
                     if (!S.pkey_ok[p]) { S.ew_status = HL_STATUS_CAPACITY; break; }
@@ -699,6 +711,7 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
         if (mode == 2) {
             {
                 bool all = true;
+#pragma unroll 1
                 for (int k = 0; k < AQ_SHOOTERS; ++k) all = all && (warp_read(&S.sh[k].done_epoch, lane) == my_epoch);
                 if (!all) { __nanosleep(100); continue; }
             }

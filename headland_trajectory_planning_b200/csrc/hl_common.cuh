@@ -90,6 +90,13 @@ void hl_set_error(const char* fmt, ...);
 #ifdef __CUDACC__
 // HL_CODE: helpers are force-inlined by default (K1/K2 want that); a translation unit that defines
 // HL_SHARED_CODE gets them out-of-line instead (one copy, instruction-cache friendly).
+// HL_LOOP: in the search kernels (HL_SHARED_CODE) code bytes are the bottleneck (32 KB instruction cache), so
+// runtime loops are kept rolled there; K1/K2 let the compiler unroll them for throughput.
+#ifdef HL_SHARED_CODE
+#define HL_LOOP _Pragma("unroll 1")
+#else
+#define HL_LOOP
+#endif
 #ifdef HL_SHARED_CODE
 #define HL_CODE __noinline__
 #else

@@ -432,13 +432,6 @@ static __device__ HL_CODE int corner_in_capsule(const float* sg, float wx, float
 //     crossing parity of C decides inside/outside when every edge is clear;
 //   * lane: one centre-to-segment distance accepts / rejects against (r_in - rho) / (r_out + rho)
 //     before the four corner distances are needed.
-// In the search kernels (HL_SHARED_CODE) code bytes are the bottleneck (32 KB instruction cache), so the runtime
-// loops of the filter are kept rolled there; K1 lets the compiler unroll them for throughput.
-#ifdef HL_SHARED_CODE
-#define HL_LOOP _Pragma("unroll 1")
-#else
-#define HL_LOOP
-#endif
 static __device__ HL_CODE int filter_part(const EnvSmem& E, float px, float py, float c, float s,
                                            const float* ext, unsigned flags, unsigned* which_ambig) {
     const float eps = E.eps;

@@ -222,6 +222,7 @@ static __device__ HL_CODE2 bool rs_candidate(int cand, const RsProblem& P, doubl
     default:       lens[0] = t; lens[1] = H; lens[2] = u; lens[3] = H; lens[4] = v; break;
     }
     if (row.neg_x)
+        HL_LOOP
         for (int i = 0; i < row.nseg; ++i) lens[i] = -lens[i];
     return true;
 }
@@ -249,6 +250,7 @@ static __device__ HL_CODE2 void rs_select_group(int g, const unsigned char* vali
                                        unsigned char* accept, double* Lc) {
     int kept[4];
     int nk = 0;
+    HL_LOOP
     for (int q = 0; q < 4; ++q) {
         const int c = c_rs_groups[g][q];
         if (c < 0) break;
@@ -256,13 +258,16 @@ static __device__ HL_CODE2 void rs_select_group(int g, const unsigned char* vali
         if (!valid[c]) continue;
         const int nseg = c_rs_rows[c].nseg;
         bool dup = false;
+        HL_LOOP
         for (int k = 0; k < nk && !dup; ++k) {
             double s = 0.0;                                  // Python sum(): 0 + d0 + d1 + ...
+            HL_LOOP
             for (int i = 0; i < nseg; ++i) s = xadd(s, xsub(lens[kept[k]][i], lens[c][i]));
             if (s <= 0.01) dup = true;
         }
         if (dup) continue;
         double tot = 0.0;
+        HL_LOOP
         for (int i = 0; i < nseg; ++i) tot = xadd(tot, fabs(lens[c][i]));
         if (tot >= 1000.0) continue;                         // MAX_LENGTH
         Lc[c] = tot;
@@ -296,12 +301,14 @@ static __device__ HL_CODE2 double rs_path_cost(double node_cost, int cand, const
                                double reverse_cost, double dir_change_cost, double steer_cost) {
     const RsRow row = c_rs_rows[cand];
     int nneg = 0;
+    HL_LOOP
     for (int i = 0; i < row.nseg; ++i) nneg += (lens[i] < 0.0) ? 1 : 0;
     double cost = node_cost;
     cost = xadd(cost, xadd(xmul(reverse_cost, (double)nneg), (double)(row.nseg - nneg)));
     cost = xadd(cost, xmul(1.0, dir_change_cost));
     cost = xadd(cost, xmul(xmul(max_steer, steer_cost), 1.0));
     double prev = 0.0, sum = 0.0;
+    HL_LOOP
     for (int i = 0; i < row.nseg; ++i) {
         double st = (rs_letter(row.letters, i) == RS_R) ? -max_steer : 0.0;
         if (i > 0) sum = xadd(sum, fabs(xsub(st, prev)));        // np.sum of <= 4 elements: sequential
@@ -315,9 +322,11 @@ static __device__ HL_CODE2 double rs_path_cost(double node_cost, int cand, const
 static __device__ HL_CODE2 void heapdict_order(const double* prio, int n, int* order) {
     int heap[HL_RS_CANDIDATES];
     int m = 0;
+    HL_LOOP
     for (int k = 0; k < n; ++k) {                 // __setitem__: append + _decrease_key
         int i = m++;
         heap[i] = k;
+        HL_LOOP
         while (i) {
             int parent = (i - 1) >> 1;
             if (prio[heap[parent]] < prio[heap[i]]) break;
@@ -325,12 +334,14 @@ static __device__ HL_CODE2 void heapdict_order(const double* prio, int n, int* o
             i = parent;
         }
     }
+    HL_LOOP
     for (int k = 0; k < n; ++k) {                 // popitem: move last to root + _min_heapify
         order[k] = heap[0];
         --m;
         if (m > 0) {
             heap[0] = heap[m];
             int i = 0;
+            HL_LOOP
             while (true) {
                 int l = (i << 1) + 1, r = (i + 1) << 1, low = i;
                 if (l < m && prio[heap[l]] < prio[heap[i]]) low = l;
@@ -388,6 +399,7 @@ static __device__ HL_CODE2 void rs_make_plan(int cand, const double* lens, doubl
     double ox = 0.0, oy = 0.0, oyaw = 0.0;        // px[1] of the zero-initialised arrays
     double ll = 0.0;
     int ind = 1;
+    HL_LOOP
     for (int i = 0; i < row.nseg; ++i) {
         double l = lens[i];
         double d = (l > 0.0) ? step : -step;
@@ -412,6 +424,7 @@ static __device__ HL_CODE2 void rs_make_plan(int cand, const double* lens, doubl
                 cnt = (int)kf + 1;
                 pd = xadd(pd, xmul((double)cnt, d));
             } else {
+                HL_LOOP
                 while (fabs(pd) <= al) { ++cnt; pd = xadd(pd, d); }
             }
         }
@@ -429,12 +442,15 @@ static __device__ HL_CODE2 void rs_make_plan(int cand, const double* lens, doubl
     if (ox == 0.0) {
         npts -= 1;
         // walk back through loop samples while their x is exactly 0.0
+        HL_LOOP
         while (npts > 1) {
             int j = npts - 1;
             int si = P.nseg - 1;
+            HL_LOOP
             while (si > 0 && j < P.seg[si].first) --si;
             const RsSegPlan& S = P.seg[si];
             double pd = S.pd0;
+            HL_LOOP
             for (int k = 0; k < j - S.first; ++k) pd = xadd(pd, S.d);
             double px, py, pyaw;
             rs_interp(pd, S.letter, maxc, S.ox, S.oy, S.oyaw, px, py, pyaw);
@@ -452,6 +468,7 @@ static __device__ HL_CODE2 void rs_sample_local(const RsPlan& P, int j, double m
                                 int& cs_sign, int& dir) {
     if (j == 0) { px = 0.0; py = 0.0; pyaw = 0.0; cs_sign = 0; dir = P.dir0; return; }
     int si = P.nseg - 1;
+    HL_LOOP
     while (si > 0 && j < P.seg[si].first) --si;
     const RsSegPlan& S = P.seg[si];
     int k = j - S.first;
@@ -464,6 +481,7 @@ static __device__ HL_CODE2 void rs_sample_local(const RsPlan& P, int j, double m
 // float32 view of a plan for the collision filter: per segment the world position of its origin
 // relative to the environment origin and cos/sin of the world heading there.  One call per word.
 static __device__ HL_CODE2 void rs_plan_world32(RsPlan& P, const double* q0, double cq, double sq, const double* env_origin) {
+    HL_LOOP
     for (int i = 0; i < P.nseg; ++i) {
         RsSegPlan& S = P.seg[i];
         double wx = xadd(xadd(xmul(cq, S.ox), xmul(sq, S.oy)), q0[0]);
@@ -480,6 +498,7 @@ static __device__ HL_CODE2 void rs_plan_world32(RsPlan& P, const double* q0, dou
 static __device__ HL_CODE void rs_sample_world32(const RsPlan& P, int j, float inv_maxc, float& wx, float& wy,
                                                   float& c, float& s) {
     int si = P.nseg - 1;
+    HL_LOOP
     while (si > 0 && j < P.seg[si].first) --si;
     const RsSegPlan& S = P.seg[si];
     if (j == 0) { wx = P.seg[0].fox; wy = P.seg[0].foy; c = P.seg[0].fc0; s = P.seg[0].fs0; return; }
