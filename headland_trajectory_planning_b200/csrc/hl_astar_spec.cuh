@@ -98,6 +98,9 @@ __device__ __forceinline__ bool role_barrier_all(int id, int nthreads, bool pred
     return r != 0;
 }
 
+#ifndef AQ_COARSE
+#define AQ_COARSE 1                    // shooter: probe all words coarsely before the per-word passes
+#endif
 #ifndef AQ_MID
 #define AQ_MID 0                       // extra alignment points inside an iteration (0 none, 1 one per role, 2 two for the expander)
 #endif
@@ -386,8 +389,39 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
             if (!shooting) continue;
             const EnvDesc& D = *Dp;
             {
+                // Coarse pass: almost every word of a failing shot collides somewhere, and ONE hit kills a word.  Probe
+                // the first min(m, AQ_MAX_PLANS) words together, 32 / nw evenly spaced poses each, before any word
+                // gets its own 32-pose passes.  Only definite float32 HITs count; everything else goes on below.
+                unsigned dead = 0;
+#if AQ_COARSE
+                if (m >= 2) {
+                    const int nw = m < AQ_MAX_PLANS ? m : AQ_MAX_PLANS;
+                    const int per = 32 / nw;
+                    const int r = lane / per, q = lane - r * per;
+                    int st2 = HL_FREE;
+                    if (r < nw) {
+                        const RsPlan& plan = T.plans[r];
+                        const int npts = plan.npts;
+                        const int j = (int)(((long long)(2 * q + 1) * npts) / (2 * per));
+                        if (j < npts) {
+                            float fx, fy, fc, fs;
+                            unsigned amb = 0;
+                            rs_sample_world32(plan, j, inv_maxc, fx, fy, fc, fs);
+                            if (fabsf(fx) > Ers.reach || fabsf(fy) > Ers.reach) st2 = far_status(FLAGS, Ers.n_seg);
+                            else if (!(fx == fx) || !(fy == fy) || !(fc == fc)) st2 = HL_AMBIG;
+                            else st2 = filter_part(Ers, fx, fy, fc, fs, Ers.ext, FLAGS, &amb);
+                        }
+                    }
+                    const unsigned hitm = __ballot_sync(FULL, st2 == HL_HIT);
+                    const unsigned livem = __ballot_sync(FULL, r < nw);
+                    for (int w = 0; w < nw; ++w)
+                        if (hitm & (((per >= 32) ? 0xffffffffu : ((1u << per) - 1u)) << (w * per))) dead |= 1u << w;
+                    if (lane == 0) T.s_checks += (unsigned long long)__popc(livem);
+                }
+#endif
 #pragma unroll 1
                 for (int r = 0; r < m; ++r) {
+                    if (dead & (1u << r)) continue;
                     const int k = T.rs_order[r];
                     const int c = T.rs_acc[k];
                     if (r >= AQ_MAX_PLANS) {
