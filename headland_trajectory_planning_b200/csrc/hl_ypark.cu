@@ -26,11 +26,13 @@ __device__ __forceinline__ double yp_yaw(double init_yaw, double stop, double ls
 }
 
 // One calculate_motion_path: poses 1..n of the rollout into (xs, ys, yw) [n]; returns the last pose.
-__device__ void yp_rollout(double ix, double iy, double iyaw, double steer, double dir, int n, double wheel_base,
-                           double step, double* tx, double* ty, double* yw, int lane) {
+// stop_mult: the linspace end is init_yaw + yaw_step * stop_mult (n in headland_path_planning.py:466, n + 1 in
+// CarModel.calculate_motion_path, car_model.py:213-215)
+__device__ void yp_rollout(double ix, double iy, double iyaw, double steer, double dir, int n, int stop_mult,
+                           double wheel_base, double step, double* tx, double* ty, double* yw, int lane) {
     const double yaw_step = xmul(xdiv(xmul(dir, step), wheel_base), m_tan(steer));
     const double init_yaw = angle_wrap(xadd(iyaw, yaw_step));
-    const double stop = xadd(init_yaw, xmul(yaw_step, (double)n));
+    const double stop = xadd(init_yaw, xmul(yaw_step, (double)stop_mult));
     const double delta = xsub(stop, init_yaw);
     const double lstep = n > 0 ? xdiv(delta, (double)n) : 0.0;
     for (int i = lane; i < n; i += 32) {
@@ -74,9 +76,9 @@ __global__ void __launch_bounds__(128) k_ypark_paths(const double* __restrict__ 
             for (long long i = lane; i < 3 * room; i += 32) out[i] = __longlong_as_double(0x7ff8000000000000LL);
             continue;
         }
-        yp_rollout(0.0, 0.0, 0.0, sb, -1.0, nb, wb, step, bx, by, bw, lane);
+        yp_rollout(0.0, 0.0, 0.0, sb, -1.0, nb, nb, wb, step, bx, by, bw, lane);
         const double jx = nb ? bx[nb - 1] : 0.0, jy = nb ? by[nb - 1] : 0.0, jw = nb ? bw[nb - 1] : 0.0;
-        yp_rollout(jx, jy, jw, sf, 1.0, nf, wb, step, fx, fy, fw, lane);
+        yp_rollout(jx, jy, jw, sf, 1.0, nf, nf, wb, step, fx, fy, fw, lane);
         // odom frame (transformation.py:7-61, navigation_utils.py:196-203)
         double se, ce;
         m_sincos(eyaw, &se, &ce);
@@ -100,7 +102,51 @@ __global__ void __launch_bounds__(128) k_ypark_paths(const double* __restrict__ 
     }
 }
 
+// CarModel.calculate_motion_path (car_model.py:202-234) for many (init pose, command) rows: [init pose; n poses].
+__global__ void __launch_bounds__(128) k_arc_paths(const double* __restrict__ cand, const long long* __restrict__ offs,
+                                                   long long n, double step, double* __restrict__ poses) {
+    extern __shared__ double sm[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    double* ax = sm + (size_t)wib * 3 * YP_MAX_STEPS;
+    double* ay = ax + YP_MAX_STEPS; double* aw = ay + YP_MAX_STEPS;
+    const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long c = warp; c < n; c += n_warps) {
+        const double* q = cand + 8 * c;
+        const double ix = q[0], iy = q[1], iyaw = q[2], steer = q[3], dir = q[4], len = q[5], wb = q[6];
+        const int ns = (int)rint(xdiv(len, step));
+        double* out = poses + 3 * offs[c];
+        const long long room = offs[c + 1] - offs[c];
+        if (ns < 1 || ns > YP_MAX_STEPS || room != (long long)ns + 1) {
+            for (long long i = lane; i < 3 * room; i += 32) out[i] = __longlong_as_double(0x7ff8000000000000LL);
+            continue;
+        }
+        yp_rollout(ix, iy, iyaw, steer, dir, ns, ns + 1, wb, step, ax, ay, aw, lane);
+        if (lane == 0) { out[0] = ix; out[1] = iy; out[2] = iyaw; }
+        for (int r = lane; r < ns; r += 32) { out[3 * (r + 1)] = ax[r]; out[3 * (r + 1) + 1] = ay[r]; out[3 * (r + 1) + 2] = aw[r]; }
+        __syncwarp();
+    }
+}
+
 }  // namespace
+
+extern "C" int hl_arc_paths(hl_ctx* ctx, const double* d_cand, const int64_t* d_offsets, int64_t n, double step,
+                            double* d_poses, void* stream) {
+    if (!ctx || !d_cand || !d_offsets || !d_poses || n < 0 || !(step > 0.0)) {
+        hl_set_error("hl_arc_paths: bad arguments"); return 1;
+    }
+    if (n == 0) return 0;
+    HL_CUDA_OK(cudaSetDevice(ctx->device));
+    const int threads = 128;
+    const size_t smem = (size_t)(threads / 32) * 3 * YP_MAX_STEPS * sizeof(double);      // 48 KB
+    HL_CUDA_OK(cudaFuncSetAttribute(k_arc_paths, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long want = (n + 3) / 4;
+    const long long cap = (long long)ctx->sm_count * 4;
+    const int grid = (int)(want < cap ? want : cap);
+    k_arc_paths<<<grid, threads, smem, (cudaStream_t)stream>>>(d_cand, (const long long*)d_offsets, (long long)n, step, d_poses);
+    HL_CUDA_OK(cudaGetLastError());
+    return 0;
+}
 
 extern "C" int hl_ypark_paths(hl_ctx* ctx, const double* d_cand, const int64_t* d_offsets, int64_t n, double step,
                               double* d_poses, void* stream) {

@@ -79,6 +79,27 @@ def ypark_paths(cand, step):
     return poses, offsets
 
 
+def arc_paths(cand, step):
+    """Single-arc rollouts (``hl_arc_paths``, CarModel.calculate_motion_path).  ``cand``: [n,8] float64 rows
+    (init_x, init_y, init_yaw, signed steer, direction, search_length, wheel_base, unused).
+    Returns (poses [total,3] CUDA tensor, offsets [n+1] int64 host array)."""
+    torch = _torch()
+    lib = _lib.load_library()
+    dev = _device()
+    cand = np.ascontiguousarray(np.asarray(cand, dtype=np.float64).reshape(-1, 8))
+    n = cand.shape[0]
+    counts = (np.rint(cand[:, 5] / step) + 1).astype(np.int64)
+    offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    poses = torch.empty((int(offsets[-1]), 3), dtype=torch.float64, device=dev)
+    if n == 0:
+        return poses, offsets
+    d_cand = torch.from_numpy(cand).to(dev)
+    d_off = torch.from_numpy(offsets).to(dev)
+    _lib.check(lib.hl_arc_paths(_lib.get_ctx(dev.index), _lib.ptr(d_cand), _lib.ptr(d_off), n, float(step),
+                                _lib.ptr(poses), _lib.stream_ptr()), "hl_arc_paths")
+    return poses, offsets
+
+
 def measure_fp32_peak(device=None):
     lib = _lib.load_library()
     v = C.c_double()

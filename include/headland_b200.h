@@ -192,6 +192,15 @@ int hl_path_reduce(hl_ctx* ctx, const uint8_t* d_pose_bad, const int64_t* d_path
 int hl_ypark_paths(hl_ctx* ctx, const double* d_cand, const int64_t* d_offsets, int64_t n, double step,
                    double* d_poses, void* stream);
 
+/* Single-arc rollouts of CarModel.calculate_motion_path (path_planner/car_model.py:202-234), the candidate
+ * generator of get_offset_pose (path_planner/safety_forward_path_plan.py:248-283).
+ *   d_cand    [n][8] float64: init_x, init_y, init_yaw, steer (signed), direction (+1/-1),
+ *             search_length (= delta_yaw / curvature), wheel_base, unused
+ *   d_offsets [n+1] int64; offsets[i+1]-offsets[i] must be round(search_length/step) + 1
+ *   d_poses   out: the init pose followed by the arc poses (NaN rows on a count mismatch)             */
+int hl_arc_paths(hl_ctx* ctx, const double* d_cand, const int64_t* d_offsets, int64_t n, double step,
+                 double* d_poses, void* stream);
+
 /* ---- K2/K3 Reeds-Shepp --------------------------------------------------------
  * Replaces reeds_shepp.calc_all_paths (path_planner/utils/reeds_shepp.py:39-65):
  * generate_path + set_path dedup (:565-582, :68-87) and the sample count of

@@ -5,6 +5,7 @@ container, where ``/root/reference`` exists):
     python -m oracle.gen_golden astar N      # oracle Hybrid A* on config-5 scenarios 0..N-1
     python -m oracle.gen_golden astar_ref N  # the REFERENCE's own search loop on scenarios 0..N-1
     python -m oracle.gen_golden ypark N      # the REFERENCE's own Y-park sweep on N scenarios
+    python -m oracle.gen_golden offset N     # the REFERENCE's own get_offset_pose on N scenarios
 
 TEST INFRASTRUCTURE (see ``oracle/__init__.py``).
 
@@ -25,6 +26,8 @@ TEST INFRASTRUCTURE (see ``oracle/__init__.py``).
 * ``ypark_golden.npz`` -- ``search_y_type_parking_path`` of the REFERENCE
   (``headland_path_planning.py:382-451``, same loader) on config-5 environments with the
   notebook's and the function's default parameter sets.
+* ``offset_golden.npz`` -- ``safety_forward_path_plan.get_offset_pose`` of the REFERENCE (:248-283) with the
+  reference's ``CarModel.calculate_motion_path`` (car_model.py:202-234) grafted onto the oracle car.
 """
 import math
 import os
@@ -245,6 +248,43 @@ def gen_astar_ref(n):
           [r["counter"] for r in res][:24])
 
 
+def _offset_one(i):
+    from . import planner as OP
+    from . import ref_loader
+    sys.path.insert(0, os.path.dirname(HERE))
+    from headland_trajectory_planning_b200 import scenarios as SC
+    S = ref_loader.load_planner("safety_forward_path_plan")
+    C = ref_loader.load_planner("car_model")
+
+    class Car(OP.CarModel):
+        calculate_motion_path = C.CarModel.calculate_motion_path
+
+    sp = SC.scenario_spec(i)
+    env = OP.OrchardGeometryEnvironment(sp["rows"], [], tree_width=sp["tree_width"], headland_width=sp["headland_width"])
+    car = Car(**sp["car"])
+    turn = S.get_steer_dir_for_enter_calculation(sp["start"], sp["end"])
+    out = []
+    for steer in (0.55, 0.5):
+        for pose, typ in ((sp["start"], S.LEAVE_POSE), (sp["end"], S.ENTER_POSE)):
+            d, p, path = _quiet(S.get_offset_pose, pose, typ, turn, car, env, steer_angle=steer)
+            out.append(dict(index=i, steer=steer, pose_type=typ, turn=float(turn), init=np.array(pose, float),
+                            dist=float(d), pose=np.array(p, float), path=np.asarray(path, float).reshape(-1, 5)))
+    return out
+
+
+def gen_offset(n):
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(os.cpu_count()) as pool:
+        res = [r for rs in pool.map(_offset_one, range(n), chunksize=1) for r in rs]
+    np.savez_compressed(
+        os.path.join(GOLD, "offset_golden.npz"), index=np.array([r["index"] for r in res]),
+        steer=np.array([r["steer"] for r in res]), pose_type=np.array([r["pose_type"] for r in res]),
+        turn=np.array([r["turn"] for r in res]), init=np.array([r["init"] for r in res]),
+        dist=np.array([r["dist"] for r in res]), pose=np.array([r["pose"] for r in res]),
+        path_len=np.array([len(r["path"]) for r in res]), path=np.concatenate([r["path"] for r in res]))
+    print("offset_golden.npz:", len(res), "sweeps; distances", sorted(set(np.round([r["dist"] for r in res], 1)))[:30])
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     args = sys.argv[1:]
@@ -256,5 +296,7 @@ if __name__ == "__main__":
         gen_astar(int(args[args.index("astar") + 1]))
     if "astar_ref" in args:
         gen_astar_ref(int(args[args.index("astar_ref") + 1]))
+    if "offset" in args:
+        gen_offset(int(args[args.index("offset") + 1]))
     if "ypark" in args:
         gen_ypark(int(args[args.index("ypark") + 1]))

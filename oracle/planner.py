@@ -620,3 +620,39 @@ def search_y_type_parking_path(car_model, config_env, end_pose, backward_steer_d
         if config_env.check_path_feasibility(car_model, path):
             return (path, [bl, fl, sb, sf]) if debug else path
     return ([], []) if debug else []
+
+
+# ---------------------------------------------------------------------------------------------------------
+# SURVEY.md section 8(f) rank 2 (first part): the offset-pose sweep of safety_forward_path_plan.py:248-283.
+# Pinned against the reference's OWN get_offset_pose + CarModel.calculate_motion_path
+# (oracle/ref_loader.load_planner, tests/golden/offset_golden.npz).
+
+def car_calculate_motion_path(car, init_pose, motion_command, delta_yaw, step):
+    """CarModel.calculate_motion_path, car_model.py:202-234 (note the linspace end yaw_step*(num_steps+1))."""
+    steer_angle, speed_direction = motion_command[0], motion_command[1]
+    search_length = delta_yaw / car.curvature
+    num_steps = round(search_length / step)
+    yaw_step = speed_direction * step / car.WHEEL_BASE * math.tan(steer_angle)
+    init_yaw = angle_wrap(init_pose[-1] + yaw_step)
+    yaws = angle_wrap(np.linspace(init_yaw, init_yaw + yaw_step * (num_steps + 1), num_steps + 1))
+    xs = init_pose[0] + np.cumsum(step * np.cos(yaws[:-1]) * speed_direction)
+    ys = init_pose[1] + np.cumsum(step * np.sin(yaws[:-1]) * speed_direction)
+    path = np.vstack([init_pose, np.vstack([xs, ys, yaws[1:]]).T])
+    curvature = math.tan(steer_angle) / car.WHEEL_BASE if abs(steer_angle) > 0.00001 else 0
+    return np.hstack((path, np.ones((len(path), 1)) * curvature, np.ones((len(path), 1)) * speed_direction))
+
+
+def get_offset_pose(init_pose, pose_type, turn_out_dir, car, config_env, steer_angle=0.55,
+                    delta_yaw=math.radians(45), max_offset=5, accuracy=0.1):
+    """safety_forward_path_plan.py:248-283."""
+    init_x, init_y, init_yaw = init_pose[0], init_pose[1], init_pose[2]
+    motion_dir = -1 if pose_type == ENTER_POSE else 1
+    offset_dir = -1 if pose_type == ENTER_POSE else 1
+    for dist in np.arange(0, max_offset + accuracy, accuracy):
+        x = init_x + dist * np.cos(init_yaw) * offset_dir
+        y = init_y + dist * np.sin(init_yaw) * offset_dir
+        pose = np.array([x, y, init_yaw])
+        path = car_calculate_motion_path(car, pose, [steer_angle * turn_out_dir, motion_dir], delta_yaw, accuracy)
+        if config_env.check_path_feasibility(car, path, boundary_check=False):
+            break
+    return dist, pose, path
