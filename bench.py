@@ -224,6 +224,7 @@ def main():
     # ---------------- secondary: stand-alone collision kernel (M2) on the canonical scenario
     coll = None
     coll_paths = None
+    ypark = None
     fp32_peak = None
     if rank == 0:
         fp32_peak = ops.measure_fp32_peak(local_rank)
@@ -231,6 +232,7 @@ def main():
         args.collision_mode = "paths"
         args.collision_poses = min(args.collision_poses, 1 << 23)
         coll_paths = collision_microbench(args, dev, fp32_peak)
+        ypark = ypark_microbench(args, dev, world == 1 and not args.no_cpu_baseline)
 
     # ---------------- CPU baseline (rank 0, N = 1 only)
     cpu = None
@@ -258,11 +260,11 @@ def main():
             "gpu_launches": args.steps,
             "roofline": {"bound": "alu_fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp32_peak if fp32_peak else None, "traffic": None,
-                         "kernel": "k_hybrid_astar",
+                         "kernel": "k_hybrid_astar_s",
                          "note": "no tensor cores on this path; algorithmic flop = executed footprint checks x "
                                  "F_check (SURVEY 8d); peak = FFMA micro-benchmark measured in this run; the kernel "
                                  "is a latency-bound search, see kernels.k_collision for the ALU-bound kernel"},
-            "kernels": {"k_collision": coll, "k_collision_path_ordered": coll_paths},
+            "kernels": {"k_collision": coll, "k_collision_path_ordered": coll_paths, "ypark_sweep": ypark},
             "search": {"expansions": expansions, "pose_checks": n_checks, "exact_escalations": n_exact,
                        "status": status_hist},
         }
@@ -344,6 +346,70 @@ def collision_microbench(args, dev, fp32_peak):
             "roofline": {"bound": "alu_fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp32_peak if fp32_peak else None,
                          "hbm_GBps": checks * 25 * 1e-9, "traffic": None}}
+
+
+def ypark_microbench(args, dev, with_cpu):
+    """the Y-type parking sweep that produces the search goal, as a batch stage
+    (hl_ypark_paths + hl_collision_check + hl_path_reduce) over 256 config-5 environments with the defaults of
+    headland_planner_y_type_park (858 candidates each, step 0.1 m); host arrays in, chosen candidates out."""
+    import time
+    import torch
+    from headland_trajectory_planning_b200 import headland_path_planning as HP, scenarios as SC
+    from headland_trajectory_planning_b200.car_model import CarModel
+    from headland_trajectory_planning_b200.env_batch import EnvBatch, make_record
+    from headland_trajectory_planning_b200.orchard_geometry_environment import OrchardGeometryEnvironment
+    n = 256
+    ps = (0.35, 0.55, 2.0, 2.5, 1.4, 0.7, 0.22, 0.50)
+    step = 0.1
+    specs = [SC.scenario_spec(i) for i in range(n)]
+    recs, ends, bdirs, wbs = [], [], [], []
+    for i, sp in enumerate(specs):
+        env = OrchardGeometryEnvironment(sp["rows"], [], tree_width=sp["tree_width"], headland_width=sp["headland_width"])
+        car = CarModel(**sp["car"])
+        recs.append(make_record(env, car))
+        end = np.array(sp["end"], dtype=np.float64)
+        shift = (0.0, 1.5, 3.0)[i % 3]
+        end[0] -= shift * np.cos(end[2]); end[1] -= shift * np.sin(end[2])
+        ends.append(end)
+        bdirs.append(float(HP.get_backward_steer_dir_for_y_type_parking(sp["start"], end)))
+        wbs.append(car.WHEEL_BASE)
+    envs = EnvBatch(recs)
+    cands = HP.y_park_candidates(*ps)
+    for _ in range(2):
+        first, feas, goal = HP.search_y_type_parking_path_batch(envs, np.arange(n), np.array(ends), bdirs, wbs, cands, step)
+    torch.cuda.synchronize()
+    reps, ms = 3, 0.0
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        first, feas, goal = HP.search_y_type_parking_path_batch(envs, np.arange(n), np.array(ends), bdirs, wbs, cands, step)
+        b.record()
+        torch.cuda.synchronize()
+        ms += a.elapsed_time(b)
+    ms /= reps
+    poses = int(((np.rint(cands[:, 0] / step) + np.rint(cands[:, 1] / step) + 2).sum()) * n)
+    out = {"metric": "ypark_sweeps_per_sec", "value": n / (ms * 1e-3), "unit": "sweeps/s", "sweeps": n,
+           "candidates_per_sweep": int(len(cands)), "poses_checked": poses, "ms_per_batch": ms,
+           "candidates_per_sec": n * len(cands) / (ms * 1e-3), "found": int((first >= 0).sum())}
+    if with_cpu:
+        from oracle import planner as OP
+        import contextlib
+        import io
+        m = 6
+        t0 = time.perf_counter()
+        agree = 0
+        for i in range(m):
+            sp = specs[i]
+            env = OP.OrchardGeometryEnvironment(sp["rows"], [], tree_width=sp["tree_width"], headland_width=sp["headland_width"])
+            car = OP.CarModel(**sp["car"])
+            with contextlib.redirect_stdout(io.StringIO()):
+                _, par = OP.search_y_type_parking_path(car, env, ends[i], bdirs[i], -bdirs[i], *ps, step_size=step, debug=True)
+            agree += int((len(par) > 0) == (first[i] >= 0) and (len(par) == 0 or np.array_equal(np.array(par), cands[first[i]])))
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": m / dt, "unit": "sweeps/s", "cores": 1, "kind": "port",
+                               "sample": f"first {m} sweeps, oracle port (stops at the first feasible candidate)",
+                               "agree_with_gpu": agree}
+    return out
 
 
 if __name__ == "__main__":

@@ -143,8 +143,10 @@ def search_y_type_parking_path_batch(envs, env_ids, end_poses, backward_steer_di
     rows[:, :, 4:7] = end_poses[:, None, :]
     rows[:, :, 7] = np.asarray(wheel_bases, dtype=np.float64)[:, None]
     poses, offsets = ops.ypark_paths(rows.reshape(-1, 8), step_size)
-    counts = np.diff(offsets)
-    pose_env = np.repeat(np.repeat(env_ids, c), counts).astype(np.int32)
+    # environment id of every pose, expanded on the device (plumbing only)
+    counts = torch.from_numpy(np.diff(offsets)).to(poses.device)
+    cand_env = torch.from_numpy(np.repeat(env_ids, c)).to(poses.device)
+    pose_env = torch.repeat_interleave(cand_env, counts).to(torch.int32)
     bad = ops.collision_check(envs, poses, env_id=pose_env, flags=ops.CHECK_OBSTACLES | ops.CHECK_BOUNDARY)
     path_bad = ops.path_reduce(envs, bad, torch.from_numpy(offsets).to(bad.device))
     feasible = (path_bad.reshape(n, c) == 0)
