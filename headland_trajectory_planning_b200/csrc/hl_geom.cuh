@@ -392,18 +392,24 @@ struct EnvSmem {
 // (geometry_host.capsule_polygon): a cap point at range rho and angular offset delta from the nearest
 // chord midpoint is inside iff rho*m_cos(delta) <= 6*m_cos(pi/64).  Returns 1 inside, 0 outside, 2 when
 // the margin is within the float32 band.
+// The filter only has to be RIGHT when it is sure: its divisions and square roots feed comparisons that carry a
+// margin of eps (~2e-4 m), so the 2-ulp hardware approximations (MUFU.RCP / MUFU.RSQ) are used instead of the
+// IEEE-rounded sequences (~8 instructions + slow path each; 15 % of K1's instructions before this change).
+__device__ __forceinline__ float f_rcp(float x) { return __fdividef(1.0f, x); }
+__device__ __forceinline__ float f_sqrt(float x) { return x > 0.0f ? x * rsqrtf(x) : 0.0f; }
+
 static __device__ HL_CODE int corner_in_capsule(const float* sg, float wx, float wy, float eps) {
     const float ex = sg[2] - sg[0], ey = sg[3] - sg[1];
     const float len2 = fmaf(ex, ex, ey * ey);
     const float qx = wx - sg[0], qy = wy - sg[1];
-    const float tt = fmaf(qx, ex, qy * ey) / len2;
+    const float tt = fmaf(qx, ex, qy * ey) * f_rcp(len2);
     const float t = fminf(fmaxf(tt, 0.f), 1.f);
     const float ddx = fmaf(-t, ex, qx), ddy = fmaf(-t, ey, qy);
     const float d2 = fmaf(ddx, ddx, ddy * ddy);
     const float rin = (float)HL_LANE_RIN - eps, rout = (float)HL_LANE_R + eps;
     if (d2 <= rin * rin) return 1;
     if (d2 > rout * rout) return 0;
-    float g = sqrtf(d2);                                        // straight part: distance to the axis
+    float g = f_sqrt(d2);                                       // straight part: distance to the axis
     if (tt < 0.f || tt > 1.f) {                                 // cap: chord fan
         const float il = rsqrtf(len2);
         const float along = fabsf(fmaf(ddx, ex, ddy * ey)) * il, across = fabsf(fmaf(ddy, ex, -ddx * ey)) * il;
@@ -547,14 +553,14 @@ static __device__ HL_CODE int filter_part(const EnvSmem& E, float px, float py, 
                 if (fabsf(d2v[ax]) < 1e-12f) {
                     if (a2[ax] <= lo2[ax] || a2[ax] >= hi2[ax]) dead = true;
                 } else {
-                    float inv = 1.0f / d2v[ax];
+                    float inv = f_rcp(d2v[ax]);
                     float tl = (lo2[ax] - a2[ax]) * inv, th = (hi2[ax] - a2[ax]) * inv;
                     t0 = fmaxf(t0, fminf(tl, th));
                     t1 = fminf(t1, fmaxf(tl, th));
                 }
             }
             // the chord inside the shrunken rectangle must be clearly longer than the band
-            if (!dead && (t1 - t0) * sqrtf(fmaf(d2v[0], d2v[0], d2v[1] * d2v[1])) > 8.0f * eps) { cut = true; break; }
+            if (!dead && (t1 - t0) * f_sqrt(fmaf(d2v[0], d2v[0], d2v[1] * d2v[1])) > 8.0f * eps) { cut = true; break; }
         }
         if (cut) hit = true;
         else if (all_clear) { if (!inside) hit = true; }
@@ -569,11 +575,11 @@ static __device__ HL_CODE int filter_part(const EnvSmem& E, float px, float py, 
         for (int i = 0; i < E.n_seg && !accepted; ++i) {
             const float* sg = E.seg + 4 * i;
             float ex = sg[2] - sg[0], ey = sg[3] - sg[1];
-            float inv = 1.0f / fmaf(ex, ex, ey * ey);
+            float inv = f_rcp(fmaf(ex, ex, ey * ey));
             float qx = Cx - sg[0], qy = Cy - sg[1];
             float t = fminf(fmaxf(fmaf(qx, ex, qy * ey) * inv, 0.f), 1.f);
             float ddx = fmaf(-t, ex, qx), ddy = fmaf(-t, ey, qy);
-            float d = sqrtf(fmaf(ddx, ddx, ddy * ddy));
+            float d = f_sqrt(fmaf(ddx, ddx, ddy * ddy));
             if (d + rho <= rin) accepted = true;                 // whole rectangle inside capsule i
             else if (d - rho <= rout) need_corners = true;       // capsule i may hold some corner
         }
@@ -621,7 +627,7 @@ static __device__ HL_CODE int filter_part(const EnvSmem& E, float px, float py, 
                         for (int i = 0; i < E.n_seg; ++i) {
                             const float* sg = E.seg + 4 * i;
                             float ex = sg[2] - sg[0], ey = sg[3] - sg[1];
-                            float inv = 1.0f / fmaf(ex, ex, ey * ey);
+                            float inv = f_rcp(fmaf(ex, ex, ey * ey));
                             float qx = wx - sg[0], qy = wy - sg[1];
                             float t = fminf(fmaxf(fmaf(qx, ex, qy * ey) * inv, 0.f), 1.f);
                             float ddx = fmaf(-t, ex, qx), ddy = fmaf(-t, ey, qy);
