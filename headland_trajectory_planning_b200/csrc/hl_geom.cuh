@@ -438,8 +438,16 @@ static __device__ HL_CODE int corner_in_capsule(const float* sg, float wx, float
 //     crossing parity of C decides inside/outside when every edge is clear;
 //   * lane: one centre-to-segment distance accepts / rejects against (r_in - rho) / (r_out + rho)
 //     before the four corner distances are needed.
-static __device__ HL_CODE int filter_part(const EnvSmem& E, float px, float py, float c, float s,
-                                           const float* ext, unsigned flags, unsigned* which_ambig) {
+// ---- the filter in three stages (K1 runs them as separate, compacted passes; filter_part chains them) ----
+struct FiltState {                 // what stage 1 leaves for the later stages
+    unsigned near_mask;            // field edges whose line the rectangle may touch
+    unsigned amb;                  // HL_CHECK_* bits that are inside the float32 band so far
+    bool hit, inside, overflow;
+};
+
+// Stage 1: obstacles + first pass over the field edges (crossing parity of the centre, nearby-edge mask).
+static __device__ __forceinline__ void filt_stage1(const EnvSmem& E, float px, float py, float c, float s,
+                                                   const float* ext, unsigned flags, FiltState& F) {
     const float eps = E.eps;
     const float hx = 0.5f * (ext[1] - ext[0]), hy = 0.5f * (ext[3] - ext[2]);
     const float mx = 0.5f * (ext[1] + ext[0]), my = 0.5f * (ext[3] + ext[2]);
@@ -447,7 +455,7 @@ static __device__ HL_CODE int filter_part(const EnvSmem& E, float px, float py, 
     unsigned amb = 0;
     // Branch-light on purpose: the lanes of a warp hold unrelated poses, so every data-dependent
     // branch is paid by the whole warp.  Obstacles and field edges are evaluated for all lanes and
-    // folded into hit / ambiguous flags; only the rare second-stage edge tests loop per lane.
+    // folded into hit / ambiguous flags; the rare second-stage edge tests are a separate stage.
     bool hit = false;
     if (flags & HL_CHECK_OBSTACLES) {
         bool a_obs = false;
@@ -502,12 +510,11 @@ static __device__ HL_CODE int filter_part(const EnvSmem& E, float px, float py, 
         }
         if (a_obs) amb |= HL_CHECK_OBSTACLES;
     }
+    bool inside = false, overflow = false;
+    unsigned near_mask = 0;                           // edges whose LINE the rectangle may touch (n <= 32 here)
     if (flags & HL_CHECK_BOUNDARY) {
         const int n = E.n_field;
         const float rho_eps = sqrtf(fmaf(hx, hx, hy * hy)) + eps;
-        bool inside = false;
-        unsigned near_mask = 0;                       // edges whose LINE the rectangle may touch (n <= 32 here)
-        bool overflow = false;
         HL_LOOP
         for (int i = 0; i < n; ++i) {
             const float* e = E.field + HL_FIELD32_STRIDE * i;
@@ -526,121 +533,154 @@ static __device__ HL_CODE int filter_part(const EnvSmem& E, float px, float py, 
                 if (!(fabsf(sd) > rn + eps)) { if (i < 32) near_mask |= 1u << i; else overflow = true; }
             }
         }
-        bool all_clear = !overflow, cut = false;
-        while (near_mask) {                           // second stage, only for the few nearby edges of this lane
-            const int i = __ffs(near_mask) - 1;
-            near_mask &= near_mask - 1;
-            const float* e = E.field + HL_FIELD32_STRIDE * i;
-            const float Ax = e[0], Ay = e[1], Bx = Ax + e[2], By = e[7], nx = e[4], ny = e[5];
-            const float nu = fmaf(nx, c, ny * s), nv = fmaf(ny, c, -nx * s);
-            // along the edge direction t = (-ny, nx):  t.u = -n.v,  t.v = n.u
-            const float ct = fmaf(-ny, Cx, nx * Cy);
-            const float rt = fmaf(hx, fabsf(nv), hy * fabsf(nu));
-            if (ct - rt > fmaxf(e[8], e[9]) + eps || ct + rt < fminf(e[8], e[9]) - eps) continue;
-            float dxa = Ax - px, dya = Ay - py, dxb = Bx - px, dyb = By - py;
-            float ua = fmaf(c, dxa, s * dya), wa = fmaf(c, dya, -s * dxa);
-            float ub = fmaf(c, dxb, s * dyb), wb = fmaf(c, dyb, -s * dxb);
-            if ((fminf(ua, ub) > ext[1] + eps) || (fmaxf(ua, ub) < ext[0] - eps) ||
-                (fminf(wa, wb) > ext[3] + eps) || (fmaxf(wa, wb) < ext[2] - eps)) continue;
-            all_clear = false;
-            // definite cut: Liang-Barsky against the rectangle shrunk by eps
-            float t0 = 0.f, t1 = 1.f;
-            bool dead = false;
-            const float a2[2] = {ua, wa}, d2v[2] = {ub - ua, wb - wa};
-            const float lo2[2] = {ext[0] + eps, ext[2] + eps}, hi2[2] = {ext[1] - eps, ext[3] - eps};
-#pragma unroll
-            for (int ax = 0; ax < 2; ++ax) {
-                if (fabsf(d2v[ax]) < 1e-12f) {
-                    if (a2[ax] <= lo2[ax] || a2[ax] >= hi2[ax]) dead = true;
-                } else {
-                    float inv = f_rcp(d2v[ax]);
-                    float tl = (lo2[ax] - a2[ax]) * inv, th = (hi2[ax] - a2[ax]) * inv;
-                    t0 = fmaxf(t0, fminf(tl, th));
-                    t1 = fminf(t1, fmaxf(tl, th));
-                }
-            }
-            // the chord inside the shrunken rectangle must be clearly longer than the band
-            if (!dead && (t1 - t0) * f_sqrt(fmaf(d2v[0], d2v[0], d2v[1] * d2v[1])) > 8.0f * eps) { cut = true; break; }
-        }
-        if (cut) hit = true;
-        else if (all_clear) { if (!inside) hit = true; }
-        else amb |= HL_CHECK_BOUNDARY;
     }
-    if (hit) return HL_HIT;
-    if ((flags & HL_CHECK_LANE) && E.n_seg > 0) {
-        const float rho = sqrtf(fmaf(hx, hx, hy * hy));
-        const float rin = (float)HL_LANE_RIN - eps, rout = (float)HL_LANE_R + eps;
-        bool accepted = false, need_corners = false;
-        HL_LOOP
-        for (int i = 0; i < E.n_seg && !accepted; ++i) {
-            const float* sg = E.seg + 4 * i;
-            float ex = sg[2] - sg[0], ey = sg[3] - sg[1];
-            float inv = f_rcp(fmaf(ex, ex, ey * ey));
-            float qx = Cx - sg[0], qy = Cy - sg[1];
-            float t = fminf(fmaxf(fmaf(qx, ex, qy * ey) * inv, 0.f), 1.f);
-            float ddx = fmaf(-t, ex, qx), ddy = fmaf(-t, ey, qy);
-            float d = f_sqrt(fmaf(ddx, ddx, ddy * ddy));
-            if (d + rho <= rin) accepted = true;                 // whole rectangle inside capsule i
-            else if (d - rho <= rout) need_corners = true;       // capsule i may hold some corner
-        }
-        if (!accepted) {
-            if (!need_corners) return HL_HIT;                    // every point is outside every capsule
-            float rx[4], ry[4];
-            const float lx[4] = {ext[0], ext[0], ext[1], ext[1]};
-            const float ly[4] = {ext[3], ext[2], ext[2], ext[3]};
+    F.near_mask = near_mask; F.amb = amb; F.hit = hit; F.inside = inside; F.overflow = overflow;
+}
+
+// Stage 2: the few nearby field edges of this pose (Liang-Barsky against the shrunken rectangle), then the
+// field verdict.  Needs only F.near_mask / inside / overflow; updates F.hit / F.amb.
+static __device__ __forceinline__ void filt_field2(const EnvSmem& E, float px, float py, float c, float s,
+                                                   const float* ext, FiltState& F) {
+    const float eps = E.eps;
+    const float hx = 0.5f * (ext[1] - ext[0]), hy = 0.5f * (ext[3] - ext[2]);
+    const float mx = 0.5f * (ext[1] + ext[0]), my = 0.5f * (ext[3] + ext[2]);
+    const float Cx = fmaf(c, mx, fmaf(-s, my, px)), Cy = fmaf(s, mx, fmaf(c, my, py));
+    unsigned near_mask = F.near_mask;
+    bool all_clear = !F.overflow, cut = false;
+    while (near_mask) {                           // second stage, only for the few nearby edges of this lane
+        const int i = __ffs(near_mask) - 1;
+        near_mask &= near_mask - 1;
+        const float* e = E.field + HL_FIELD32_STRIDE * i;
+        const float Ax = e[0], Ay = e[1], Bx = Ax + e[2], By = e[7], nx = e[4], ny = e[5];
+        const float nu = fmaf(nx, c, ny * s), nv = fmaf(ny, c, -nx * s);
+        // along the edge direction t = (-ny, nx):  t.u = -n.v,  t.v = n.u
+        const float ct = fmaf(-ny, Cx, nx * Cy);
+        const float rt = fmaf(hx, fabsf(nv), hy * fabsf(nu));
+        if (ct - rt > fmaxf(e[8], e[9]) + eps || ct + rt < fminf(e[8], e[9]) - eps) continue;
+        float dxa = Ax - px, dya = Ay - py, dxb = Bx - px, dyb = By - py;
+        float ua = fmaf(c, dxa, s * dya), wa = fmaf(c, dya, -s * dxa);
+        float ub = fmaf(c, dxb, s * dyb), wb = fmaf(c, dyb, -s * dxb);
+        if ((fminf(ua, ub) > ext[1] + eps) || (fmaxf(ua, ub) < ext[0] - eps) ||
+            (fminf(wa, wb) > ext[3] + eps) || (fmaxf(wa, wb) < ext[2] - eps)) continue;
+        all_clear = false;
+        // definite cut: Liang-Barsky against the rectangle shrunk by eps
+        float t0 = 0.f, t1 = 1.f;
+        bool dead = false;
+        const float a2[2] = {ua, wa}, d2v[2] = {ub - ua, wb - wa};
+        const float lo2[2] = {ext[0] + eps, ext[2] + eps}, hi2[2] = {ext[1] - eps, ext[3] - eps};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                rx[j] = fmaf(c, lx[j], fmaf(-s, ly[j], px));
-                ry[j] = fmaf(s, lx[j], fmaf(c, ly[j], py));
+        for (int ax = 0; ax < 2; ++ax) {
+            if (fabsf(d2v[ax]) < 1e-12f) {
+                if (a2[ax] <= lo2[ax] || a2[ax] >= hi2[ax]) dead = true;
+            } else {
+                float inv = f_rcp(d2v[ax]);
+                float tl = (lo2[ax] - a2[ax]) * inv, th = (hi2[ax] - a2[ax]) * inv;
+                t0 = fmaxf(t0, fminf(tl, th));
+                t1 = fminf(t1, fmaxf(tl, th));
             }
-            bool one_holds_all = false;
-            unsigned maybe = 0;                    // corner j is inside (or within the band of) some capsule
+        }
+        // the chord inside the shrunken rectangle must be clearly longer than the band
+        if (!dead && (t1 - t0) * f_sqrt(fmaf(d2v[0], d2v[0], d2v[1] * d2v[1])) > 8.0f * eps) { cut = true; break; }
+    }
+    if (cut) F.hit = true;
+    else if (all_clear) { if (!F.inside) F.hit = true; }
+    else F.amb |= HL_CHECK_BOUNDARY;
+}
+
+// Stage 3: the guide lane (union of capsule polygons).  Returns HL_HIT, or HL_FREE with *lane_amb set when the
+// cover could not be certified in float32.
+static __device__ __forceinline__ int filt_lane(const EnvSmem& E, float px, float py, float c, float s,
+                                                const float* ext, bool* lane_amb) {
+    const float eps = E.eps;
+    const float hx = 0.5f * (ext[1] - ext[0]), hy = 0.5f * (ext[3] - ext[2]);
+    const float mx = 0.5f * (ext[1] + ext[0]), my = 0.5f * (ext[3] + ext[2]);
+    const float Cx = fmaf(c, mx, fmaf(-s, my, px)), Cy = fmaf(s, mx, fmaf(c, my, py));
+    *lane_amb = false;
+    const float rho = sqrtf(fmaf(hx, hx, hy * hy));
+    const float rin = (float)HL_LANE_RIN - eps, rout = (float)HL_LANE_R + eps;
+    bool accepted = false, need_corners = false;
+    HL_LOOP
+    for (int i = 0; i < E.n_seg && !accepted; ++i) {
+        const float* sg = E.seg + 4 * i;
+        float ex = sg[2] - sg[0], ey = sg[3] - sg[1];
+        float inv = f_rcp(fmaf(ex, ex, ey * ey));
+        float qx = Cx - sg[0], qy = Cy - sg[1];
+        float t = fminf(fmaxf(fmaf(qx, ex, qy * ey) * inv, 0.f), 1.f);
+        float ddx = fmaf(-t, ex, qx), ddy = fmaf(-t, ey, qy);
+        float d = f_sqrt(fmaf(ddx, ddx, ddy * ddy));
+        if (d + rho <= rin) accepted = true;                 // whole rectangle inside capsule i
+        else if (d - rho <= rout) need_corners = true;       // capsule i may hold some corner
+    }
+    if (accepted) return HL_FREE;
+    if (!need_corners) return HL_HIT;                        // every point is outside every capsule
+    float rx[4], ry[4];
+    const float lx[4] = {ext[0], ext[0], ext[1], ext[1]};
+    const float ly[4] = {ext[3], ext[2], ext[2], ext[3]};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        rx[j] = fmaf(c, lx[j], fmaf(-s, ly[j], px));
+        ry[j] = fmaf(s, lx[j], fmaf(c, ly[j], py));
+    }
+    bool one_holds_all = false;
+    unsigned maybe = 0;                    // corner j is inside (or within the band of) some capsule
+    HL_LOOP
+    for (int i = 0; i < E.n_seg; ++i) {
+        const float* sg = E.seg + 4 * i;
+        bool all_in = true;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int st = corner_in_capsule(sg, rx[j], ry[j], eps);
+            all_in = all_in && (st == 1);
+            if (st != 0) maybe |= 1u << j;
+        }
+        if (all_in) one_holds_all = true;
+    }
+    if (one_holds_all) return HL_FREE;
+    if (maybe != 0xFu) return HL_HIT;
+    // The corners sit in different capsules.  Certify the union cover piecewise: cut the
+    // rectangle into 4 slices along its long side; a slice whose 4 corners are clearly inside
+    // ONE (convex) capsule is inside the lane.  Only what this cannot certify is ambiguous.
+    unsigned prev = 0;
+    bool covered = true;
+#pragma unroll 1
+    for (int q = 0; q <= 4 && covered; ++q) {
+        const float lxq = ext[0] + 0.25f * (float)q * (ext[1] - ext[0]);
+        unsigned m = 0xFFFFu;                 // capsules holding BOTH points of this cross-section
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            const float lyq = side ? ext[3] : ext[2];
+            const float wx = fmaf(c, lxq, fmaf(-s, lyq, px)), wy = fmaf(s, lxq, fmaf(c, lyq, py));
+            unsigned in = 0;
             HL_LOOP
             for (int i = 0; i < E.n_seg; ++i) {
                 const float* sg = E.seg + 4 * i;
-                bool all_in = true;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int st = corner_in_capsule(sg, rx[j], ry[j], eps);
-                    all_in = all_in && (st == 1);
-                    if (st != 0) maybe |= 1u << j;
-                }
-                if (all_in) one_holds_all = true;
+                float ex = sg[2] - sg[0], ey = sg[3] - sg[1];
+                float inv = f_rcp(fmaf(ex, ex, ey * ey));
+                float qx = wx - sg[0], qy = wy - sg[1];
+                float t = fminf(fmaxf(fmaf(qx, ex, qy * ey) * inv, 0.f), 1.f);
+                float ddx = fmaf(-t, ex, qx), ddy = fmaf(-t, ey, qy);
+                if (fmaf(ddx, ddx, ddy * ddy) <= rin * rin) in |= 1u << i;
             }
-            if (!one_holds_all) {
-                if (maybe != 0xFu) return HL_HIT;
-                // The corners sit in different capsules.  Certify the union cover piecewise: cut the
-                // rectangle into 4 slices along its long side; a slice whose 4 corners are clearly inside
-                // ONE (convex) capsule is inside the lane.  Only what this cannot certify is ambiguous.
-                unsigned prev = 0;
-                bool covered = true;
-#pragma unroll 1
-                for (int q = 0; q <= 4 && covered; ++q) {
-                    const float lxq = ext[0] + 0.25f * (float)q * (ext[1] - ext[0]);
-                    unsigned m = 0xFFFFu;                 // capsules holding BOTH points of this cross-section
-#pragma unroll
-                    for (int side = 0; side < 2; ++side) {
-                        const float lyq = side ? ext[3] : ext[2];
-                        const float wx = fmaf(c, lxq, fmaf(-s, lyq, px)), wy = fmaf(s, lxq, fmaf(c, lyq, py));
-                        unsigned in = 0;
-                        HL_LOOP
-                        for (int i = 0; i < E.n_seg; ++i) {
-                            const float* sg = E.seg + 4 * i;
-                            float ex = sg[2] - sg[0], ey = sg[3] - sg[1];
-                            float inv = f_rcp(fmaf(ex, ex, ey * ey));
-                            float qx = wx - sg[0], qy = wy - sg[1];
-                            float t = fminf(fmaxf(fmaf(qx, ex, qy * ey) * inv, 0.f), 1.f);
-                            float ddx = fmaf(-t, ex, qx), ddy = fmaf(-t, ey, qy);
-                            if (fmaf(ddx, ddx, ddy * ddy) <= rin * rin) in |= 1u << i;
-                        }
-                        m &= in;
-                    }
-                    if (q > 0 && (prev & m) == 0) covered = false;
-                    prev = m;
-                }
-                if (!covered) amb |= HL_CHECK_LANE;
-            }
+            m &= in;
         }
+        if (q > 0 && (prev & m) == 0) covered = false;
+        prev = m;
+    }
+    if (!covered) *lane_amb = true;
+    return HL_FREE;
+}
+
+static __device__ HL_CODE int filter_part(const EnvSmem& E, float px, float py, float c, float s,
+                                           const float* ext, unsigned flags, unsigned* which_ambig) {
+    FiltState F;
+    filt_stage1(E, px, py, c, s, ext, flags, F);
+    if (flags & HL_CHECK_BOUNDARY) filt_field2(E, px, py, c, s, ext, F);
+    if (F.hit) return HL_HIT;
+    unsigned amb = F.amb;
+    if ((flags & HL_CHECK_LANE) && E.n_seg > 0) {
+        bool lane_amb;
+        if (filt_lane(E, px, py, c, s, ext, &lane_amb) == HL_HIT) return HL_HIT;
+        if (lane_amb) amb |= HL_CHECK_LANE;
     }
     if (amb) { if (which_ambig) *which_ambig = amb; return HL_AMBIG; }
     return HL_FREE;
