@@ -189,8 +189,10 @@ def main():
     value = total * args.steps / (max_ms * 1e-3)
 
     res = out["results"].cpu().numpy().view(_lib.RESULT_DTYPE)
-    flops = sweep.algorithmic_flops(recs, res)
+    flops = sweep.algorithmic_flops(recs, res)                              # reference-equivalent checks x F_check
+    flops_exec = sweep.algorithmic_flops(recs, res, field="n_pose_checks")   # what the kernel actually executed
     n_checks = int(res["n_pose_checks"].sum())
+    n_checks_ref = int(res["n_pose_checks_ref"].sum())
     n_exact = int(res["n_exact"].sum())
     status_hist = {_lib.STATUS_NAMES[int(k)]: int(v) for k, v in zip(*np.unique(res["status"], return_counts=True))}
     expansions = int(res["n_expanded"].sum())
@@ -261,11 +263,16 @@ def main():
             "roofline": {"bound": "alu_fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp32_peak if fp32_peak else None, "traffic": None,
                          "kernel": "k_hybrid_astar_s",
-                         "note": "no tensor cores on this path; algorithmic flop = executed footprint checks x "
-                                 "F_check (SURVEY 8d); peak = FFMA micro-benchmark measured in this run; the kernel "
-                                 "is a latency-bound search, see kernels.k_collision for the ALU-bound kernel"},
+                         "executed_frac": (flops_exec / (kernel_ms / args.steps * 1e-3) * 1e-12 / fp32_peak) if fp32_peak else None,
+                         "note": "no tensor cores on this path; algorithmic flop = pose checks the REFERENCE performs "
+                                 "for the same searches (poses of every Reeds-Shepp word tried + of every primitive "
+                                 "rolled out; HlPlanResult.n_pose_checks_ref, equal to the oracle's tally) x F_check "
+                                 "(SURVEY 8d); executed_frac counts only the checks the kernel ran after its early "
+                                 "exits; peak = FFMA micro-benchmark measured in this run; the kernel is a "
+                                 "latency-bound search, see kernels.k_collision for the ALU-bound kernel"},
             "kernels": {"k_collision": coll, "k_collision_path_ordered": coll_paths, "ypark_sweep": ypark},
-            "search": {"expansions": expansions, "pose_checks": n_checks, "exact_escalations": n_exact,
+            "search": {"expansions": expansions, "pose_checks": n_checks, "pose_checks_algorithmic": n_checks_ref,
+                       "exact_escalations": n_exact,
                        "status": status_hist},
         }
         if cpu:

@@ -66,11 +66,11 @@ RESULT_DTYPE = np.dtype([("status", "<i4"), ("counter", "<i4"), ("n_expanded", "
                          ("arrival", "<i4"), ("path_len", "<i4"), ("rs_word", "<i4"),
                          ("path_offset", "<i8"), ("goal_cost", "<f8"),
                          ("n_pose_checks", "<i8"), ("n_exact", "<i8"), ("keys_offset", "<i8"),
-                         ("cycles", "<i8")])
+                         ("cycles", "<i8"), ("n_pose_checks_ref", "<i8")])
 RSWORD_DTYPE = np.dtype([("cand", "<i4"), ("n_seg", "<i4"), ("npts", "<i4"), ("collide", "<i4"),
                          ("L", "<f8"), ("cost", "<f8"), ("len", "<f8", (HL_RS_MAX_SEGS,)),
                          ("nlen", "<f8", (HL_RS_MAX_SEGS,))])
-assert SCENARIO_DTYPE.itemsize == 56 and RESULT_DTYPE.itemsize == 72 and RSWORD_DTYPE.itemsize == 112
+assert SCENARIO_DTYPE.itemsize == 56 and RESULT_DTYPE.itemsize == 80 and RSWORD_DTYPE.itemsize == 112
 
 EXPORTS = [
     "hl_last_error", "hl_abi_version", "hl_ctx_create", "hl_ctx_destroy", "hl_ctx_sm_count",

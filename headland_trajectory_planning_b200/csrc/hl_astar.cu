@@ -64,7 +64,7 @@ struct AwSmem {                          // one per warp
     int rs_n, rs_pick;
     int phit[HL_MAX_PRIMS];
     // stats
-    unsigned long long n_checks, n_exact;
+    unsigned long long n_checks, n_exact, n_ref;
     long long t_last, t_phase[AS_N_PHASES];
     // backtrack
     int chain_len, path_len;
@@ -211,6 +211,7 @@ __device__ __noinline__ void finalize_scenario(AwSmem& S, const AsWs& W, const A
         r.keys_offset = koff;
         r.goal_cost = S.goal_cost;
         r.n_pose_checks = (long long)S.n_checks;
+        r.n_pose_checks_ref = (S.status == HL_STATUS_START_GOAL_BLOCKED) ? 0 : (long long)S.n_ref;
         r.n_exact = (long long)S.n_exact;
         long long _n = clock64();
         S.t_phase[PH_OUTPUT] += _n - S.t_last;
@@ -296,7 +297,7 @@ k_hybrid_astar_w(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                 for (int k = 0; k < 3; ++k) { S.start[k] = s.start[k]; S.goal[k] = s.goal[k]; }
                 S.n_nodes = 0; S.heap_n = 0; S.counter = 0; S.n_closed = 0;
                 S.status = -1; S.arrival = 0; S.rs_word = -1; S.goal_cost = 0.0; S.rs_pick = -1;
-                S.n_checks = 0; S.n_exact = 0; S.path_len = 0; S.path_off = 0; S.chain_len = 0;
+                S.n_checks = 0; S.n_exact = 0; S.n_ref = 0; S.path_len = 0; S.path_off = 0; S.chain_len = 0;
                 for (int k = 0; k < AS_N_PHASES; ++k) S.t_phase[k] = 0;
                 S.t_last = clock64();
             }
@@ -411,6 +412,7 @@ k_hybrid_astar_w(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                 }
                 const RsPlan& plan = (r < AW_MAX_PLANS) ? S.plans[r] : S.plan_tmp;
                 const int npts = plan.npts;
+                if (lane == 0) S.n_ref += (unsigned long long)npts;
                 int infeasible = 0;
                 // Poses are visited with stride `passes` (lane*passes + pass): the first pass already spans the
                 // whole word, so an infeasible word is almost always rejected after one 32-pose pass.
@@ -510,7 +512,7 @@ k_hybrid_astar_w(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                 S.pamb[p][j] = (st == HL_AMBIG) ? (unsigned char)amb : 0;
                 if (st == HL_HIT) atomicOr(&S.phit[p], 1);
             }
-            if (lane == 0) S.n_checks += (unsigned long long)total;
+            if (lane == 0) { S.n_checks += (unsigned long long)total; S.n_ref += (unsigned long long)total; }
             __syncwarp();
             TICK(PH_FILTER);
             // phase D: float64 escalation only where it can still change the answer

@@ -60,6 +60,7 @@ struct AsWs {
     long long* hkey; int* hval;
     double* hprio; int* hslot;
     int* corder;
+    long long* cref;          // algorithmic primitive-pose checks done BEFORE pop i was expanded
 };
 
 __host__ __device__ inline size_t as_align(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -73,6 +74,7 @@ __host__ __device__ inline size_t as_ws_bytes(int cap, int hsize, int max_nodes)
     b += as_align(sizeof(long long) * hsize) + as_align(sizeof(int) * hsize);
     b += as_align(sizeof(double) * cap) + as_align(sizeof(int) * cap);
     b += as_align(sizeof(int) * (max_nodes + 4));
+    b += as_align(sizeof(long long) * (max_nodes + 4));
     return b;
 }
 
@@ -89,6 +91,7 @@ __device__ inline AsWs as_carve(char* base, int cap, int hsize, int max_nodes) {
     w.hkey = (long long*)take(sizeof(long long) * hsize); w.hval = (int*)take(sizeof(int) * hsize);
     w.hprio = (double*)take(sizeof(double) * cap); w.hslot = (int*)take(sizeof(int) * cap);
     w.corder = (int*)take(sizeof(int) * (max_nodes + 4));
+    w.cref = (long long*)take(sizeof(long long) * (max_nodes + 4));
     return w;
 }
 

@@ -38,7 +38,7 @@ struct LsScn {                              // one per scenario
     double goal_cost;
     int rs_pick, rs_word, rs_bad, pad0;
     RsProblem rs_prob;
-    unsigned long long checks, exact;
+    unsigned long long checks, exact, ref;
 };
 
 struct LsPrim {                             // one per (scenario, primitive)
@@ -55,6 +55,7 @@ struct LsShot {                             // one per scenario
     double rs_L[HL_RS_CANDIDATES], rs_prio[HL_RS_CANDIDATES], rs_Lc[HL_RS_CANDIDATES];
     int rs_acc[HL_RS_CANDIDATES], rs_order[HL_RS_CANDIDATES];
     unsigned char rs_valid[HL_RS_CANDIDATES + 2], rs_accept[HL_RS_CANDIDATES + 2], word_bad[HL_RS_CANDIDATES + 2];
+    int word_npts[HL_RS_CANDIDATES + 2];
 };
 
 struct LsCall {                             // per-call block in device memory, read by every kernel
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(LS_THREADS) ls_setup(const LsCall* __restrict_
             S.status = -1; S.arrival = 0; S.has_cur = 0; S.goal_cost = 0.0;
             S.cur = 0; S.cprim = -1; S.nsteps = 0; S.rs_n = 0; S.rs_pick = -1; S.rs_word = -1; S.rs_bad = 0;
             S.cx = S.cy = S.cyaw = S.cg = 0.0;
-            S.checks = 0; S.exact = 0;
+            S.checks = 0; S.exact = 0; S.ref = 0;
         }
         __syncwarp();
         const EnvDesc& D = C.eb.desc[s.env_id];
@@ -167,6 +168,10 @@ __global__ void __launch_bounds__(LS_THREADS) ls_step(const LsCall* __restrict__
                 if (free_m) first = r0 + __ffs(free_m) - 1;
             }
             if (lane == 0) {
+                const int tried = first >= 0 ? first + 1 : m;
+                unsigned long long ref = 0;
+                for (int r = 0; r < tried; ++r) ref += (unsigned long long)T.word_npts[r];
+                S.ref += ref;
                 if (S.rs_bad) { status = HL_STATUS_RS_ASSERT; S.arrival = 0; }      // the reference would raise here
                 else if (first >= 0) {
                     const int k = T.rs_order[first];
@@ -175,6 +180,7 @@ __global__ void __launch_bounds__(LS_THREADS) ls_step(const LsCall* __restrict__
                 } else {
                     // ---- merge the children (:580-596), in primitive order
                     const int n = S.nsteps;
+                    S.ref += (unsigned long long)(P.n_prims * (n + 1));
                     int n_nodes = S.n_nodes, heap_n = S.heap_n;
                     for (int p = 0; p < P.n_prims; ++p) {
                         const LsPrim& R = C.prim[(size_t)sc * P.n_prims + p];
@@ -381,6 +387,7 @@ __global__ void __launch_bounds__(LS_THREADS) ls_sample(const LsCall* __restrict
             checks += (unsigned long long)__popc(livem);
         }
         if (lane == 0) {
+            T.word_npts[r] = npts;
             T.word_bad[r] = infeasible ? 1 : 0;
             atomicAdd(&S.checks, checks);
             if (exact) atomicAdd(&S.exact, exact);
@@ -643,6 +650,7 @@ __global__ void __launch_bounds__(LS_THREADS) ls_finalize(const LsCall* __restri
             r.path_offset = path_off;
             r.goal_cost = S.goal_cost;
             r.n_pose_checks = (long long)S.checks;
+            r.n_pose_checks_ref = (status == HL_STATUS_START_GOAL_BLOCKED) ? 0 : (long long)S.ref;
             r.n_exact = (long long)S.exact;
             r.keys_offset = koff;
             r.cycles = 0;

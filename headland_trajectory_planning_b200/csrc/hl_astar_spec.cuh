@@ -43,7 +43,7 @@ struct AqShot {                          // scratch of one shooter warp
     double rs_goal_cost;
     RsPlan plans[AQ_MAX_PLANS];
     RsPlan plan_tmp;
-    unsigned long long s_checks, s_exact;
+    unsigned long long s_checks, s_exact, s_ref;
     volatile int done_epoch;             // this shooter finished the epoch
 };
 
@@ -218,6 +218,15 @@ __device__ __noinline__ void finalize_spec(AqSmem& S, const AsWs& W, const AsPar
         for (int k = 0; k < AQ_SHOOTERS; ++k) { sc_ += S.sh[k].s_checks; se_ += S.sh[k].s_exact; }
         r.n_pose_checks = (long long)sc_;
         r.n_exact = (long long)se_;
+        {
+            // algorithmic count: shots of pops <= the final one (the shooter stops there) + the expansions of the
+            // pops BEFORE a successful shot (the expander may have run ahead; that work is not the reference's)
+            unsigned long long ref = 0;
+            for (int k = 0; k < AQ_SHOOTERS; ++k) ref += S.sh[k].s_ref;
+            const bool shot_won = (S.arrival == 1) || (S.status == HL_STATUS_RS_ASSERT);
+            ref += (shot_won && n_closed > 0) ? (unsigned long long)W.cref[n_closed - 1] : S.e_checks;
+            r.n_pose_checks_ref = (S.status == HL_STATUS_START_GOAL_BLOCKED) ? 0 : (long long)ref;
+        }
         r.keys_offset = koff;
         r.cycles = clock64() - S.t0;
         O.results[sc] = r;
@@ -295,7 +304,7 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                     }
                     Ers = E;
                     Ers.eps = E.eps + 6e-5f;
-                    if (lane == 0) { T.s_checks = 0; T.s_exact = 0; T.rs_assert = 0; }
+                    if (lane == 0) { T.s_checks = 0; T.s_exact = 0; T.s_ref = 0; T.rs_assert = 0; }
                     __syncwarp();
                     i = shooter;                     // pops shooter, shooter + AQ_SHOOTERS, ...
                     active = true;
@@ -421,7 +430,7 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
 #endif
 #pragma unroll 1
                 for (int r = 0; r < m; ++r) {
-                    if (dead & (1u << r)) continue;
+                    if (dead & (1u << r)) { if (lane == 0) T.s_ref += (unsigned long long)T.plans[r].npts; continue; }
                     const int k = T.rs_order[r];
                     const int c = T.rs_acc[k];
                     if (r >= AQ_MAX_PLANS) {
@@ -434,6 +443,7 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                     }
                     const RsPlan& plan = (r < AQ_MAX_PLANS) ? T.plans[r] : T.plan_tmp;
                     const int npts = plan.npts;
+                    if (lane == 0) T.s_ref += (unsigned long long)npts;
                     int infeasible = 0;
                     const int passes = (npts + 31) >> 5;
 #pragma unroll 1
@@ -511,7 +521,7 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
             S.n_nodes = 0; S.heap_n = 0; S.counter = 0; S.n_closed = 0;
             S.status = -1; S.arrival = 0; S.goal_cost = 0.0; S.ew_status = -1; S.ew_arrival2 = 0;
             S.e_checks = 0; S.e_exact = 0; S.win = 0;
-            for (int k = 0; k < AQ_SHOOTERS; ++k) { S.sh[k].s_checks = 0; S.sh[k].s_exact = 0; S.sh[k].rs_assert = 0; }
+            for (int k = 0; k < AQ_SHOOTERS; ++k) { S.sh[k].s_checks = 0; S.sh[k].s_exact = 0; S.sh[k].s_ref = 0; S.sh[k].rs_assert = 0; }
             S.path_len = 0; S.path_off = 0; S.chain_len = 0; S.fin_closed = 0; S.fin_counter = 0;
             S.popped = 0; S.ew_done = 0; S.shot_limit = 0; S.shot_best = AQ_NO_HIT;
             S.t0 = clock64();
@@ -581,6 +591,7 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                     else {
                         int cur = heap_popitem(W, S.heap_n);
                         W.nstate[cur] = 1;
+                        W.cref[S.n_closed] = (long long)S.e_checks;
                         W.corder[S.n_closed++] = cur;
                         S.cur = cur; S.cx = W.nx[cur]; S.cy = W.ny[cur]; S.cyaw = W.nyaw[cur]; S.cg = W.ng[cur];
                         S.cprim = W.nprim[cur];
@@ -746,9 +757,9 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
         if (mode == 2 && !S.ew_done) {
         // ---- tell the shooter how far its shots are needed, wait for it, assemble the result
         if (lane == 0) {
-            // tolerance arrival at pop j: only shots of pops < j matter (the arrival overrides pop j's shot);
-            // otherwise every popped node was shot before the loop ended
-            S.shot_limit = S.ew_arrival2 ? (S.n_closed - 1) : S.n_closed;
+            // every popped node gets its shot, as in the reference (:542-545); at a tolerance arrival the shot of
+            // that pop is still evaluated (and counted) but the arrival overrides its result
+            S.shot_limit = S.n_closed;
             __threadfence_block();
             S.ew_done = 1;
         }

@@ -34,13 +34,14 @@ def search_params(car, step_size=0.2, max_nodes=400, max_path_poses=16384):
     return p
 
 
-def algorithmic_flops(recs, results):
-    """FP32 flop of the footprint checks a sweep executed, SURVEY.md 8(d):
-    F_check = 32 + 128*K + 80*E_f + 48*S per pose rectangle."""
+def algorithmic_flops(recs, results, field="n_pose_checks_ref"):
+    """FP32 flop of the footprint checks of a sweep, SURVEY.md 8(d): F_check = 32 + 128*K + 80*E_f + 48*S per
+    pose rectangle, times the ALGORITHMIC number of pose checks (``n_pose_checks_ref``: what the reference
+    tests for the same searches; ``field="n_pose_checks"`` gives the executed count instead)."""
     total = 0.0
     for rec, r in zip(recs, results):
         f = 32 + 128 * len(rec.obs) + 80 * len(rec.field) + 48 * len(rec.seg_xy)
-        total += f * float(r["n_pose_checks"])
+        total += f * float(r[field])
     return total
 
 

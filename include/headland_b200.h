@@ -125,6 +125,9 @@ typedef struct {
     int64_t keys_offset;   /* first row of this scenario's slice of the pooled expanded-key buffer */
     int64_t cycles;        /* SM clock cycles this scenario occupied its CTA (the reference prints
                               `hybrid search time`, hybrid_a_star_search.py:603)       */
+    int64_t n_pose_checks_ref; /* ALGORITHMIC pose checks: what the reference tests for the same search =
+                              sum over tried words of their sampled poses (:273-276) + n_prims*(n+1) per
+                              expansion (:412-427); n_pose_checks <= this thanks to early exits          */
 } HlPlanResult;
 
 /* Reeds-Shepp word record: hl_rs_all_paths output, one row per accepted word. */

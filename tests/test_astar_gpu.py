@@ -114,4 +114,10 @@ def test_golden_scenarios_batch(built_library, variant, monkeypatch):
         if not ok:
             bad.append(i)
     assert not bad, f"{len(bad)} of {n} scenarios differ from the oracle: {bad[:10]}"
+    # the ALGORITHMIC pose-check count (roofline numerator) is the oracle's own tally: poses of every word tried +
+    # poses of every primitive rolled out.  (At a tolerance arrival only the default kernel also takes that pop's shot.)
+    want_ref = g["rs_poses"] + g["primitive_poses"]
+    sel = (res["status"] != 1) & ((res["arrival"] != 2) | (variant == "spec"))
+    assert np.array_equal(res["n_pose_checks_ref"][sel], want_ref[sel])
+    assert res["n_pose_checks"].sum() < res["n_pose_checks_ref"].sum()      # early exits: fewer checks executed
     assert (res["n_expanded"] > 100).sum() >= 5
