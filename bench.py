@@ -261,7 +261,10 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": args.steps,
             "roofline": {"bound": "alu_fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
-                         "frac": achieved / fp32_peak if fp32_peak else None, "traffic": None,
+                         "frac": achieved / fp32_peak if fp32_peak else None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one k_hybrid_astar_s launch on this very
+                         # workload (4096 scenarios), ncu --set full, profiles/r1h_ncu_full_summary.txt
+                         "traffic": 484523264 if args.scenarios_per_gpu == 4096 else None,
                          "kernel": "k_hybrid_astar_s",
                          "executed_frac": (flops_exec / (kernel_ms / args.steps * 1e-3) * 1e-12 / fp32_peak) if fp32_peak else None,
                          "note": "no tensor cores on this path; algorithmic flop = pose checks the REFERENCE performs "
@@ -352,7 +355,10 @@ def collision_microbench(args, dev, fp32_peak):
             "exact_escalation_frac": float(nex.item()) / n,
             "roofline": {"bound": "alu_fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp32_peak if fp32_peak else None,
-                         "hbm_GBps": checks * 25 * 1e-9, "traffic": None}}
+                         "hbm_GBps": checks * 25 * 1e-9,
+                         # 35.9 B of DRAM traffic per pose (ncu --set full, 4 Mi poses, profiles/r1h_ncu_full_summary.txt)
+                         # against 25 B algorithmic (24 B pose in + 1 B flag out)
+                         "traffic": int(35.9 * n)}}
 
 
 def ypark_microbench(args, dev, with_cpu):
