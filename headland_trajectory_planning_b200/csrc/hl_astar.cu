@@ -4,7 +4,7 @@
 // King mode).  Shared pieces (workspace, keys, hash, heapdict replay, filter, heuristic) are in
 // hl_astar_common.cuh; the float64/float32 split is described there and in DESIGN.md.
 //
-// Why a warp and not a CTA per scenario: the first version (hl_astar_cta.cuh, kept for reference) gave a
+// Why a warp and not a CTA per scenario: the first version (one CTA per scenario, removed; profiles/r1b_*) gave a
 // scenario 128 threads.  Its profile (profiles/r1b_*) showed 52 % of warp samples waiting at CTA barriers
 // for the serial thread, and 73 % of the remaining stalls were INSTRUCTION-FETCH misses: one expansion walks
 // ~100 KB of straight-line float64 code exactly once, and four co-resident CTAs in four different phases

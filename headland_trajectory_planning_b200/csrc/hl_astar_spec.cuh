@@ -70,7 +70,7 @@ struct AqSmem {                          // one per scenario slot, shared by its
     long long pkey[HL_MAX_PRIMS];
     int pkey_ok[HL_MAX_PRIMS], pslot[HL_MAX_PRIMS], ppos[HL_MAX_PRIMS], pneed[HL_MAX_PRIMS];
     // stats (per role)
-    unsigned long long e_checks, e_exact;
+    unsigned long long e_checks, e_exact, e_ref;
     long long t0;
     long long te_last, te[AS_N_PHASES];      // expander phase timers (lane 0 cycles)
     long long ts_last, ts[AS_N_PHASES];      // shooter phase timers
@@ -224,7 +224,7 @@ __device__ __noinline__ void finalize_spec(AqSmem& S, const AsWs& W, const AsPar
             unsigned long long ref = 0;
             for (int k = 0; k < AQ_SHOOTERS; ++k) ref += S.sh[k].s_ref;
             const bool shot_won = (S.arrival == 1) || (S.status == HL_STATUS_RS_ASSERT);
-            ref += (shot_won && n_closed > 0) ? (unsigned long long)W.cref[n_closed - 1] : S.e_checks;
+            ref += (shot_won && n_closed > 0) ? (unsigned long long)W.cref[n_closed - 1] : S.e_ref;
             r.n_pose_checks_ref = (S.status == HL_STATUS_START_GOAL_BLOCKED) ? 0 : (long long)ref;
         }
         r.keys_offset = koff;
@@ -520,7 +520,7 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
             for (int k = 0; k < 3; ++k) { S.start[k] = s.start[k]; S.goal[k] = s.goal[k]; }
             S.n_nodes = 0; S.heap_n = 0; S.counter = 0; S.n_closed = 0;
             S.status = -1; S.arrival = 0; S.goal_cost = 0.0; S.ew_status = -1; S.ew_arrival2 = 0;
-            S.e_checks = 0; S.e_exact = 0; S.win = 0;
+            S.e_checks = 0; S.e_exact = 0; S.e_ref = 0; S.win = 0;
             for (int k = 0; k < AQ_SHOOTERS; ++k) { S.sh[k].s_checks = 0; S.sh[k].s_exact = 0; S.sh[k].s_ref = 0; S.sh[k].rs_assert = 0; }
             S.path_len = 0; S.path_off = 0; S.chain_len = 0; S.fin_closed = 0; S.fin_counter = 0;
             S.popped = 0; S.ew_done = 0; S.shot_limit = 0; S.shot_best = AQ_NO_HIT;
@@ -591,7 +591,7 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                     else {
                         int cur = heap_popitem(W, S.heap_n);
                         W.nstate[cur] = 1;
-                        W.cref[S.n_closed] = (long long)S.e_checks;
+                        W.cref[S.n_closed] = (long long)S.e_ref;
                         W.corder[S.n_closed++] = cur;
                         S.cur = cur; S.cx = W.nx[cur]; S.cy = W.ny[cur]; S.cyaw = W.nyaw[cur]; S.cg = W.ng[cur];
                         S.cprim = W.nprim[cur];
@@ -656,15 +656,33 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
             }
             __syncwarp();
             ETICK(PH_ROLLOUT);
+            // One hit kills a primitive, and a primitive that collides does so far from the (feasible) node it starts
+            // at: test the two farthest poses of every primitive first, then only the live primitives' other poses.
+            {
+                const int far_cnt = np1 < 2 ? np1 : 2;
 #pragma unroll 1
-            for (int idx = lane; idx < total; idx += 32) {
-                const int p = idx / np1, j = idx - p * np1;
-                unsigned amb = 0;
-                int st = pose_filter(D, E, S.tx[p][j], S.ty[p][j], S.pyaw[p][j], FLAGS, &amb);
-                S.pamb[p][j] = (st == HL_AMBIG) ? (unsigned char)amb : 0;
-                if (st == HL_HIT) atomicOr(&S.phit[p], 1);
+                for (int idx = lane; idx < P.n_prims * far_cnt; idx += 32) {
+                    const int p = idx / far_cnt, j = n - (idx - p * far_cnt);
+                    unsigned amb = 0;
+                    int st = pose_filter(D, E, S.tx[p][j], S.ty[p][j], S.pyaw[p][j], FLAGS, &amb);
+                    S.pamb[p][j] = (st == HL_AMBIG) ? (unsigned char)amb : 0;
+                    if (st == HL_HIT) atomicOr(&S.phit[p], 1);
+                }
+                __syncwarp();
+                const unsigned live = __ballot_sync(FULL, lane < P.n_prims && S.phit[lane] == 0);
+                const int rem = np1 - far_cnt;
+                const int total2 = __popc(live) * rem;
+#pragma unroll 1
+                for (int idx = lane; idx < total2; idx += 32) {
+                    const int q = idx / rem, j = idx - q * rem;
+                    const int p = __fns(live, 0, q + 1);
+                    unsigned amb = 0;
+                    int st = pose_filter(D, E, S.tx[p][j], S.ty[p][j], S.pyaw[p][j], FLAGS, &amb);
+                    S.pamb[p][j] = (st == HL_AMBIG) ? (unsigned char)amb : 0;
+                    if (st == HL_HIT) atomicOr(&S.phit[p], 1);
+                }
+                if (lane == 0) { S.e_checks += (unsigned long long)(P.n_prims * far_cnt + total2); S.e_ref += (unsigned long long)total; }
             }
-            if (lane == 0) S.e_checks += (unsigned long long)total;
             __syncwarp();
             ETICK(PH_FILTER);
 #pragma unroll 1
