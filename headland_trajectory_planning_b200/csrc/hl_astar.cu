@@ -798,11 +798,16 @@ extern "C" int hl_hybrid_astar_batch(hl_ctx* ctx, const hl_env_batch* envs, cons
                                      unsigned long long* d_keys_cursor, double* d_path_x, double* d_path_y, double* d_path_yaw,
                                      double* d_path_k, int8_t* d_path_dir, int64_t path_capacity,
                                      unsigned long long* d_path_cursor, void* stream) {
+    if (ctx && n_scen == 0 && d_path_cursor && d_keys_cursor) {          // empty batch: nothing but the cursors is touched
+        HL_CUDA_OK(cudaSetDevice(ctx->device));
+        HL_CUDA_OK(cudaMemsetAsync(d_path_cursor, 0, sizeof(unsigned long long), (cudaStream_t)stream));
+        HL_CUDA_OK(cudaMemsetAsync(d_keys_cursor, 0, sizeof(unsigned long long), (cudaStream_t)stream));
+        return 0;
+    }
     if (!ctx || !envs || !d_scen || !h_params || !d_results || !d_expanded_keys || !d_path_x || !d_path_y ||
         !d_path_yaw || !d_path_k || !d_path_dir || !d_path_cursor || !d_keys_cursor || n_scen < 0) {
         hl_set_error("hl_hybrid_astar_batch: bad arguments"); return 1;
     }
-    if (n_scen == 0) return 0;
     if (h_params->n_prims < 1 || h_params->n_prims > HL_MAX_PRIMS || h_params->max_nodes < 0) {
         hl_set_error("hl_hybrid_astar_batch: n_prims/max_nodes out of range"); return 1;
     }

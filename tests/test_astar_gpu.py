@@ -121,3 +121,61 @@ def test_golden_scenarios_batch(built_library, variant, monkeypatch):
     assert np.array_equal(res["n_pose_checks_ref"][sel], want_ref[sel])
     assert res["n_pose_checks"].sum() < res["n_pose_checks_ref"].sum()      # early exits: fewer checks executed
     assert (res["n_expanded"] > 100).sum() >= 5
+
+
+def _golden_batch(n):
+    import os
+    from headland_trajectory_planning_b200 import scenarios as SC, sweep
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "astar_golden.npz"))
+    specs = [SC.scenario_spec(int(i)) for i in g["index"][:n]]
+    scns = [SC.finalize(sp, f) for sp, f in zip(specs, g["feas"][:n])]
+    return sweep.build_records(scns), g
+
+
+@pytest.mark.parametrize("variant", ["spec", "warp", "level"])
+def test_edge_cases_empty_and_capacity(built_library, variant, monkeypatch):
+    """Empty batch, and a path pool that is too small: scenarios whose path does not fit report
+    HL_STATUS_CAPACITY (never a truncated path), everything else is unaffected."""
+    from headland_trajectory_planning_b200 import ops, sweep
+    from headland_trajectory_planning_b200.env_batch import EnvBatch
+    monkeypatch.setenv("HL_ASTAR_VARIANT", variant)
+    (recs, scen, car), g = _golden_batch(48)
+    envs = EnvBatch(recs)
+    params = sweep.search_params(car)
+    out0 = ops.hybrid_astar_batch(envs, scen[:0], params)
+    assert len(out0["results"]) == 0 and out0["used"] == 0
+    full = ops.hybrid_astar_batch(envs, scen, params, path_capacity=2048 * 48)
+    assert (full["results"]["status"] == g["status"][:48]).all()
+    small = ops.hybrid_astar_batch(envs, scen, params, path_capacity=150)
+    rs, rf = small["results"], full["results"]
+    ok = rs["status"] == 0
+    cap = rs["status"] == 4
+    assert cap.any() and (ok | cap | (rs["status"] == rf["status"])).all()
+    assert (rs["path_len"][cap] == 0).all()
+    assert int(rs["path_len"][ok].sum()) <= 150
+    assert (rs["counter"] == rf["counter"]).all() and (rs["n_expanded"] == rf["n_expanded"]).all()
+    for i in np.nonzero(ok)[0]:
+        a, b = int(rs["path_offset"][i]), int(rf["path_offset"][i])
+        n_i = int(rs["path_len"][i])
+        assert n_i == rf["path_len"][i]
+        assert np.array_equal(small["x"][a:a + n_i], full["x"][b:b + n_i])
+
+
+def test_level_variant_sub_batches(built_library, monkeypatch):
+    """More scenarios than one pass of the level-synchronous variant holds (LS_MAX_BATCH = 8192): the passes are
+    chained and every record equals the default kernel's."""
+    from headland_trajectory_planning_b200 import ops, sweep
+    from headland_trajectory_planning_b200.env_batch import EnvBatch
+    (recs, scen, car), g = _golden_batch(32)
+    envs = EnvBatch(recs)
+    params = sweep.search_params(car)
+    easy = np.nonzero(g["counter"][:32] <= 4)[0]
+    big = scen[easy][np.arange(8192 + 300) % len(easy)].copy()
+    monkeypatch.setenv("HL_ASTAR_VARIANT", "spec")
+    a = ops.hybrid_astar_batch(envs, big, params, path_capacity=256 * len(big))
+    monkeypatch.setenv("HL_ASTAR_VARIANT", "level")
+    b = ops.hybrid_astar_batch(envs, big, params, path_capacity=256 * len(big))
+    for f in ("status", "counter", "n_expanded", "arrival", "path_len", "rs_word", "goal_cost", "n_pose_checks_ref"):
+        assert np.array_equal(a["results"][f], b["results"][f]), f
+    for i in (0, 5000, 8191, 8192, len(big) - 1):
+        assert np.array_equal(ops.expanded_of(a, i), ops.expanded_of(b, i))
