@@ -95,3 +95,77 @@ def test_pop_order_and_collision_flags(built_library):
             assert bool(w["collide"][i, k]) == want, (i, k)
             n_free += (not want)
     assert n_free > 20
+
+
+def test_words_match_reference_golden(built_library):
+    """tests/golden/rs_golden.npz = the REFERENCE's own ``reeds_shepp.calc_all_paths`` (403 pairs incl. the three
+    known-answer cases of SURVEY 8c): word set + order + sample counts exact, lengths <= 1e-5 relative."""
+    from headland_trajectory_planning_b200 import ops
+    g = np.load(os.path.join(GOLD, "rs_golden.npz"))
+    for step in np.unique(g["steps"]):
+        idx = np.nonzero(g["steps"] == step)[0]
+        words, count, _ = ops.rs_all_paths(g["sg"][idx], MAXC, float(step), want_order=False)
+        w = ops.rs_words_to_host(words)
+        count = count.cpu().numpy()
+        assert np.array_equal(count, g["count"][idx])
+        for a, i in enumerate(idx):
+            for k in range(count[a]):
+                nseg = int(w["n_seg"][a, k])
+                assert np.array_equal(np.nonzero(g["letters"][i, k] >= 0)[0], np.arange(nseg)) or nseg == (g["letters"][i, k] != -1).sum()
+                assert w["npts"][a, k] == g["npts"][i, k], (i, k)
+                np.testing.assert_allclose(w["len"][a, k, :nseg], g["lens"][i, k, :nseg], rtol=RTOL, atol=1e-9)
+                np.testing.assert_allclose(w["L"][a, k], g["L"][i, k], rtol=RTOL)
+
+
+def test_rs_sweep_config3_full_size(built_library):
+    """1 048 576 pose pairs (default_rng(0), U([-10,10]^2 x [-pi,pi))), step 0.1, every word
+    sampled and collision-checked against the canonical 8-row orchard (body only, boundary_check=False).
+    Full size: size-independent properties + determinism; a 1024-pair subsample against the oracle
+    (word set / order / npts exact, lengths 1e-5, collision flags exact)."""
+    import torch
+    from headland_trajectory_planning_b200 import ops
+    from headland_trajectory_planning_b200.env_batch import EnvBatch, make_record
+    n = 1 << 20
+    rng = np.random.default_rng(0)
+    sg = np.empty((n, 6))
+    sg[:, [0, 1, 3, 4]] = rng.uniform(-10, 10, (n, 4))
+    sg[:, [2, 5]] = rng.uniform(-math.pi, math.pi, (n, 2))
+    rows = H.canonical_rows()
+    (o_env, o_car, _), (g_env, g_car, _) = H.make_pair(rows)
+    envs = EnvBatch([make_record(g_env, g_car)])
+    d_sg = torch.from_numpy(sg).cuda()
+    ops.rs_all_paths(d_sg[:4096], MAXC, 0.1, envs=envs, flags=ops.CHECK_OBSTACLES, want_order=False)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    words, count, _ = ops.rs_all_paths(d_sg, MAXC, 0.1, envs=envs, flags=ops.CHECK_OBSTACLES, want_order=False)
+    b.record()
+    torch.cuda.synchronize()
+    print(f"config 3: {n} pairs in {a.elapsed_time(b):.1f} ms = {n / a.elapsed_time(b) / 1e3:.2f} M pairs/s")
+    wi = words.view(torch.int32).reshape(n, 46, 28)
+    wf = words.view(torch.float64).reshape(n, 46, 14)
+    valid = torch.arange(46, device="cuda")[None, :] < count[:, None]
+    assert int(count.min()) >= 1 and int(count.max()) <= 46
+    nseg, npts, coll = wi[..., 1], wi[..., 2], wi[..., 3]
+    L, lens = wf[..., 2], wf[..., 4:9]
+    assert bool(((nseg >= 3) & (nseg <= 5))[valid].all())
+    assert bool(((coll == 0) | (coll == 1))[valid].all())
+    seg_ok = torch.arange(5, device="cuda")[None, None, :] < nseg[..., None]
+    Lsum = (lens.abs() * seg_ok).sum(-1)
+    assert bool(((Lsum - L).abs() <= 1e-9 * (1 + L))[valid].all())            # L = sum |l_i| (metric)
+    diff = (npts.double() - L / 0.1)[valid]                                     # one sample per step + a few per segment end
+    print("npts - L/step: min %.2f max %.2f" % (float(diff.min()), float(diff.max())))
+    assert float(diff.min()) > -6.0 and float(diff.max()) < 13.0            # |npts - L/step| <= a sample or two per segment
+    assert bool((L[valid] < 1000.0 / MAXC).all()) and bool((L[valid] >= 0.01 / MAXC - 1e-12).all())   # MAX_LENGTH, assert L >= 0.01
+    words2, count2, _ = ops.rs_all_paths(d_sg, MAXC, 0.1, envs=envs, flags=ops.CHECK_OBSTACLES, want_order=False)
+    assert torch.equal(count, count2) and torch.equal(words, words2)                                   # deterministic
+    sub = np.arange(0, n, n // 1024)[:1024]
+    w = ops.rs_words_to_host(words[torch.from_numpy(sub).cuda()])
+    cnt = count.cpu().numpy()[sub]
+    for a_i, i in enumerate(sub):
+        ref = rs_port.calc_all_paths(*sg[i], MAXC, 0.1)
+        assert cnt[a_i] == len(ref)
+        for k, p in enumerate(ref):
+            assert w["cand"][a_i, k] == p.cand and w["npts"][a_i, k] == len(p.x)
+            np.testing.assert_allclose(w["len"][a_i, k, :len(p.lengths)], p.lengths, rtol=RTOL, atol=1e-9)
+            want = not o_env.check_path_feasibility(o_car, np.array([p.x, p.y, p.yaw]).T, boundary_check=False)
+            assert bool(w["collide"][a_i, k]) == want, (i, k)
