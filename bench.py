@@ -227,6 +227,7 @@ def main():
     coll = None
     coll_paths = None
     ypark = None
+    rs_sweep = None
     fp32_peak = None
     if rank == 0:
         fp32_peak = ops.measure_fp32_peak(local_rank)
@@ -235,6 +236,7 @@ def main():
         args.collision_poses = min(args.collision_poses, 1 << 23)
         coll_paths = collision_microbench(args, dev, fp32_peak)
         ypark = ypark_microbench(args, dev, world == 1 and not args.no_cpu_baseline)
+        rs_sweep = rs_microbench(args, dev, world == 1 and not args.no_cpu_baseline)
 
     # ---------------- CPU baseline (rank 0, N = 1 only)
     cpu = None
@@ -273,7 +275,7 @@ def main():
                                  "(SURVEY 8d); executed_frac counts only the checks the kernel ran after its early "
                                  "exits; peak = FFMA micro-benchmark measured in this run; the kernel is a "
                                  "latency-bound search, see kernels.k_collision for the ALU-bound kernel"},
-            "kernels": {"k_collision": coll, "k_collision_path_ordered": coll_paths, "ypark_sweep": ypark},
+            "kernels": {"k_collision": coll, "k_collision_path_ordered": coll_paths, "ypark_sweep": ypark, "rs_sweep": rs_sweep},
             "search": {"expansions": expansions, "pose_checks": n_checks, "pose_checks_algorithmic": n_checks_ref,
                        "exact_escalations": n_exact,
                        "status": status_hist},
@@ -359,6 +361,58 @@ def collision_microbench(args, dev, fp32_peak):
                          # 35.9 B of DRAM traffic per pose (ncu --set full, 4 Mi poses, profiles/r1h_ncu_full_summary.txt)
                          # against 25 B algorithmic (24 B pose in + 1 B flag out)
                          "traffic": int(35.9 * n)}}
+
+
+def rs_microbench(args, dev, with_cpu):
+    """Reeds-Shepp words of 1 Mi random pose pairs, every word sampled at 0.1 m and
+    collision-checked against the canonical orchard (k_rs_all_paths)."""
+    import math
+    import time
+    import torch
+    from headland_trajectory_planning_b200 import ops
+    from headland_trajectory_planning_b200.car_model import CarModel
+    from headland_trajectory_planning_b200.env_batch import EnvBatch, make_record
+    from headland_trajectory_planning_b200.orchard_geometry_environment import OrchardGeometryEnvironment
+    from headland_trajectory_planning_b200.utils import map_utils
+    n = 1 << 20
+    rng = np.random.default_rng(0)
+    sg = np.empty((n, 6))
+    sg[:, [0, 1, 3, 4]] = rng.uniform(-10, 10, (n, 4))
+    sg[:, [2, 5]] = rng.uniform(-math.pi, math.pi, (n, 2))
+    np.random.seed(1)
+    rows = map_utils.create_tree_rows(8, 2.5, 20, slope_angle=math.radians(10), l_std=0.0)
+    env = OrchardGeometryEnvironment(rows, [], tree_width=0.3, headland_width=6.0)
+    car = CarModel(max_steer=0.55, axle_to_front=3, axle_to_back=0.55, width=1.48)
+    envs = EnvBatch([make_record(env, car)])
+    d_sg = torch.from_numpy(sg).to(dev)
+    ops.rs_all_paths(d_sg[:65536], car.curvature, 0.1, envs=envs, flags=ops.CHECK_OBSTACLES, want_order=False)
+    torch.cuda.synchronize()
+    ms = 0.0
+    for _ in range(2):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        words, count, _ = ops.rs_all_paths(d_sg, car.curvature, 0.1, envs=envs, flags=ops.CHECK_OBSTACLES, want_order=False)
+        b.record()
+        torch.cuda.synchronize()
+        ms += a.elapsed_time(b) / 2
+    out = {"metric": "rs_pairs_per_sec", "value": n / (ms * 1e-3), "unit": "pairs/s", "pairs": n, "ms_per_launch": ms,
+           "words": int(count.sum().item())}
+    del words
+    if with_cpu:
+        from oracle import planner as OP
+        from oracle import rs_port
+        o_env = OP.OrchardGeometryEnvironment(rows, [], tree_width=0.3, headland_width=6.0)
+        o_car = OP.CarModel(max_steer=0.55, axle_to_front=3, axle_to_back=0.55, width=1.48)
+        m = 128
+        t0 = time.perf_counter()
+        for i in range(m):
+            for p in rs_port.calc_all_paths(*sg[i], o_car.curvature, 0.1):
+                o_env.check_path_feasibility(o_car, np.array([p.x, p.y, p.yaw]).T, boundary_check=False)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": m / dt, "unit": "pairs/s", "cores": 1, "kind": "port",
+                               "sample": f"first {m} pairs: rs_port.calc_all_paths (bit-equal to the reference's "
+                                         "reeds_shepp.py) + oracle collision check of every word"}
+    return out
 
 
 def ypark_microbench(args, dev, with_cpu):
