@@ -101,6 +101,12 @@ __device__ __forceinline__ bool role_barrier_all(int id, int nthreads, bool pred
 #ifndef AQ_COARSE
 #define AQ_COARSE 1                    // shooter: probe all words coarsely before the per-word passes
 #endif
+#ifndef AQ_EVERY_E
+#define AQ_EVERY_E 1                   // expanders align every AQ_EVERY_E-th iteration
+#endif
+#ifndef AQ_EVERY_S
+#define AQ_EVERY_S 1                   // shooters align every AQ_EVERY_S-th iteration
+#endif
 #ifndef AQ_MID
 #define AQ_MID 0                       // extra alignment points inside an iteration (0 none, 1 one per role, 2 two for the expander)
 #endif
@@ -275,8 +281,10 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
         EnvSmem Ers = E;
         const float inv_maxc = (float)(1.0 / P.maxc);
         const double stepn = xmul(P.res, P.maxc);
+        unsigned s_iter = 0;
         while (true) {
-            if (role_barrier_all(1, AQ_SLOTS * AQ_SHOOTERS * 32, finished)) break;   // alignment point of the shooters
+            if ((s_iter++ % AQ_EVERY_S) == 0 &&
+                role_barrier_all(1, AQ_SLOTS * AQ_SHOOTERS * 32, finished)) break;   // alignment point of the shooters
             bool shooting = false, success = false;
             int m = 0;
             double q0[3] = {0.0, 0.0, 0.0}, cq = 1.0, sq = 0.0;
@@ -502,8 +510,9 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
     bool finished = false;
     int my_epoch = 0;
     const EnvDesc* Dp = eb.desc;
+    unsigned e_iter = 0;
     while (true) {
-        if (role_barrier_all(2, AQ_SLOTS * 32, finished)) break;
+        if ((e_iter++ % AQ_EVERY_E) == 0 && role_barrier_all(2, AQ_SLOTS * 32, finished)) break;
         bool expanding = false;
         do {
         if (finished) break;
