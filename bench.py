@@ -55,7 +55,29 @@ class ClockSampler:
         self._stop = threading.Event()
         self._t = None
 
+    def _run_nvml(self):
+        """Dense sampling through NVML (a few ms per sample) so that even a 150 ms timed region gets a median."""
+        nv, h, mx = self._nvml
+        bits = [(0x8, 2), (0x40, 3), (0x20, 4), (0x4, 5)]      # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap
+        while not self._stop.is_set():
+            sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            try:
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+            except Exception:
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            row = [str(sm), str(mx), "", "", "", ""]
+            for mask, col in bits:
+                row[col] = "Active" if (r & mask) else "Not Active"
+            self.rows.append(row)
+            self._stop.wait(0.005)
+
     def _run(self):
+        if self._nvml is not None:
+            try:
+                self._run_nvml()
+                return
+            except Exception:
+                pass
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
@@ -68,6 +90,14 @@ class ClockSampler:
             self._stop.wait(0.2)
 
     def __enter__(self):
+        self._nvml = None
+        try:                                   # initialise NVML BEFORE the timed region starts
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self._nvml = (nv, h, nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        except Exception:
+            self._nvml = None
         self._t = threading.Thread(target=self._run, daemon=True)
         self._t.start()
         return self
