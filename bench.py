@@ -154,11 +154,28 @@ def run_reference(args, rank, world):
                              "sample": f"scenarios 0..{n - 1} of the workload, oracle port (shapely/heapdict "
                                        f"unavailable), multiprocessing.Pool({used})"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_JSON_FD = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the process's real stdout; everything libraries print to fd 1 meanwhile (NCCL's
+    version banner, worker chatter) has been diverted to stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
+    global _JSON_FD
     args = parse()
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -312,7 +329,7 @@ def main():
         }
         if cpu:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
