@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstring>
 #include <vector>
+#include <cstdlib>
 #include <thread>
 #include <cmath>
 #include "hl_common.cuh"
@@ -247,6 +248,10 @@ extern "C" int hl_env_upload(hl_ctx* ctx, const HlEnvHost* h, int32_t n_env, hl_
     };
     {
         int nt = (int)std::thread::hardware_concurrency();
+        // one process per GPU: share the host cores between the ranks of this node (torchrun exports LOCAL_WORLD_SIZE)
+        const char* lws = getenv("LOCAL_WORLD_SIZE");
+        const int ranks = lws ? atoi(lws) : 1;
+        if (ranks > 1) nt /= ranks;
         nt = nt < 1 ? 1 : (nt > 8 ? 8 : nt);
         if (n_env < 256) nt = 1;
         std::vector<std::thread> th;
