@@ -81,7 +81,7 @@ extern "C" void hl_env_free(hl_env_batch* envs) {
     for (int i = 0; i < envs->n_allocs; ++i) {
         // keep one block per context for the next upload (cudaFree synchronises the device)
         if (i == 0 && c && envs->block_bytes > c->env_cache_bytes) {
-            cudaStreamSynchronize(0);
+            cudaDeviceSynchronize();               // like cudaFree: no kernel on any stream may still read the block
             if (c->env_cache) cudaFree(c->env_cache);
             c->env_cache = envs->allocs[0]; c->env_cache_bytes = envs->block_bytes;
         } else cudaFree(envs->allocs[i]);
