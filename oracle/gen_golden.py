@@ -269,6 +269,13 @@ def _offset_one(i):
             d, p, path = _quiet(S.get_offset_pose, pose, typ, turn, car, env, steer_angle=steer)
             out.append(dict(index=i, steer=steer, pose_type=typ, turn=float(turn), init=np.array(pose, float),
                             dist=float(d), pose=np.array(p, float), path=np.asarray(path, float).reshape(-1, 5)))
+    # get_start_end_pose_for_reeds_shepp (:300-364) for the rows of this scenario, reference code end to end
+    rng = np.random.default_rng(99 + i)
+    r0 = int(rng.integers(0, 5)); r1 = r0 + int(rng.integers(1, 3))
+    side = int(sp["side"])
+    res = _quiet(S.get_start_end_pose_for_reeds_shepp, sp["rows"], r0, r1, car, env, side=side)
+    out.append(dict(index=i, steer=-1.0, pose_type=100 + side, turn=float(r0 * 10 + r1), init=np.array(res[0], float),
+                    dist=float(res[2]), pose=np.array(res[1], float), path=np.array([[res[3], 0, 0, 0, 0]], float)))
     return out
 
 

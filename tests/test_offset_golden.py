@@ -24,8 +24,21 @@ def _cases():
     g = np.load(GOLD)
     po = np.concatenate([[0], np.cumsum(g["path_len"])])
     for k in range(len(g["index"])):
+        if g["pose_type"][k] >= 100:
+            continue
         yield (k, SC.scenario_spec(int(g["index"][k])), g["init"][k], int(g["pose_type"][k]), g["turn"][k], g["steer"][k],
                g["dist"][k], g["pose"][k], g["path"][po[k]:po[k + 1]])
+
+
+def _start_end_cases():
+    """Rows written by get_start_end_pose_for_reeds_shepp of the reference (:300-364)."""
+    from headland_trajectory_planning_b200 import scenarios as SC
+    g = np.load(GOLD)
+    po = np.concatenate([[0], np.cumsum(g["path_len"])])
+    for k in np.nonzero(g["pose_type"] >= 100)[0]:
+        r0, r1 = int(g["turn"][k]) // 10, int(g["turn"][k]) % 10
+        yield (SC.scenario_spec(int(g["index"][k])), r0, r1, int(g["pose_type"][k]) - 100, g["init"][k], g["pose"][k],
+               g["dist"][k], g["path"][po[k]][0])
 
 
 def test_oracle_matches_reference_golden():
@@ -55,6 +68,36 @@ def test_gpu_offset_pose_matches_reference_golden(built_library):
         np.testing.assert_allclose(pa[:, :3], path[:, :3], rtol=1e-5, atol=1e-9)
         np.testing.assert_allclose(pa[:, 3], path[:, 3], rtol=1e-12)
         assert np.array_equal(pa[:, 4], path[:, 4])
+
+
+@pytest.mark.gpu
+def test_gpu_start_end_pose_for_reeds_shepp(built_library):
+    """get_start_end_pose_for_reeds_shepp (two GPU offset sweeps + the common outmost x) and
+    get_all_reeds_shepp_paths_full against the reference's own results / the pinned RS port."""
+    import math
+    from oracle import rs_port
+    from headland_trajectory_planning_b200 import safety_forward_path_plan as SF
+    from headland_trajectory_planning_b200.car_model import CarModel
+    from headland_trajectory_planning_b200.orchard_geometry_environment import OrchardGeometryEnvironment
+    n = 0
+    for sp, r0, r1, side, start, end, leave, enter in _start_end_cases():
+        env = OrchardGeometryEnvironment(sp["rows"], [], tree_width=sp["tree_width"], headland_width=sp["headland_width"])
+        car = CarModel(**sp["car"])
+        with contextlib.redirect_stdout(io.StringIO()):
+            s2, e2, l2, n2 = SF.get_start_end_pose_for_reeds_shepp(sp["rows"], r0, r1, car, env, side=side)
+        assert np.array_equal(s2, start) and np.array_equal(e2, end) and l2 == leave and n2 == enter
+        if n < 4:
+            got = SF.get_all_reeds_shepp_paths_full(s2, e2, 1.0 / car.curvature)
+            maxc = 1.0 / (1.0 / car.curvature)            # what the reference passes (:375); differs from curvature by an ulp
+            ref = rs_port.calc_all_paths(s2[0], s2[1], s2[2], e2[0], e2[1], e2[2], maxc, 0.1)
+            assert len(got) == len(ref)
+            for a, p in zip(got, ref):
+                assert a.shape == (len(p.x), 5)
+                np.testing.assert_allclose(a[:, 0], p.x, rtol=1e-5, atol=1e-6)
+                np.testing.assert_allclose(a[:, 1], p.y, rtol=1e-5, atol=1e-6)
+                assert np.array_equal(a[:, 4], np.array(p.directions, dtype=float))
+        n += 1
+    assert n >= 16
 
 
 @pytest.mark.gpu
