@@ -11,6 +11,7 @@
 // running sums are then added by lane 0 in sequence, exactly like np.cumsum, so the poses agree
 // with numpy to the last bit wherever CUDA's cos/sin/tan agree with libm.
 #include "hl_common.cuh"
+#include "hl_crmath.cuh"
 
 #define YP_MAX_STEPS 512        // per rollout (5 m at 0.01 m); longer candidates are rejected by the host side
 
@@ -38,7 +39,7 @@ __device__ void yp_rollout(double ix, double iy, double iyaw, double steer, doub
     for (int i = lane; i < n; i += 32) {
         const double y0 = yp_yaw(init_yaw, stop, lstep, delta, n, i);        // yaws[:-1][i]
         double sn, cs;
-        m_sincos(y0, &sn, &cs);
+        cr_sincos(y0, &sn, &cs);       // correctly rounded like numpy's / glibc's (hl_crmath.cuh): these kernels are tiny
         tx[i] = xmul(xmul(step, cs), dir);
         ty[i] = xmul(xmul(step, sn), dir);
         yw[i] = yp_yaw(init_yaw, stop, lstep, delta, n, i + 1);              // yaws[1:][i]
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(128) k_ypark_paths(const double* __restrict__ 
         yp_rollout(jx, jy, jw, sf, 1.0, nf, nf, wb, step, fx, fy, fw, lane);
         // odom frame (transformation.py:7-61, navigation_utils.py:196-203)
         double se, ce;
-        m_sincos(eyaw, &se, &ce);
+        cr_sincos(eyaw, &se, &ce);
         const double dyaw = m_atan2(se, ce);
         const int total = nb + nf + 2;
         for (int r = lane; r < total; r += 32) {
