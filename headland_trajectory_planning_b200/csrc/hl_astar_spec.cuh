@@ -13,15 +13,19 @@
 #pragma once
 #include "hl_astar_common.cuh"
 
+#ifndef AQ_EXPANDERS
+#define AQ_EXPANDERS 2                 // expander warps per scenario: warp 0 + a helper that shares the rollout / filter / heuristic
+#endif
 #ifndef AQ_SLOTS
-#define AQ_SLOTS 6                     // scenarios per CTA (2 warps each)
+#define AQ_SLOTS (AQ_EXPANDERS > 1 ? 5 : 6)   // scenarios per CTA: 5 x 3 warps (128 registers) or 6 x 2 warps (168)
 #endif
 #define AQ_MAX_PLANS 6
 #ifndef AQ_SHOOTERS
 #define AQ_SHOOTERS 1                  // shooter warps per scenario (shots of different pops are independent;
                                        // 2-3 shooters measured slower: the expander is the critical path)
 #endif
-#define AQ_WARPS_PER_SLOT (1 + AQ_SHOOTERS)
+#define AQ_WARPS_PER_SLOT (AQ_EXPANDERS + AQ_SHOOTERS)
+#define AQ_TEAM (32 * AQ_EXPANDERS)
 #define AQ_NO_HIT 0x7fffffff
 #define ETICK(ph) do { if (lane == 0) { long long _n = clock64(); S.te[ph] += _n - S.te_last; S.te_last = _n; } } while (0)
 #define STICK(ph) do { if (lane == 0) { long long _n = clock64(); S.ts[ph] += _n - S.ts_last; S.ts_last = _n; } } while (0)
@@ -56,6 +60,7 @@ struct AqSmem {                          // one per scenario slot, shared by its
     volatile int popped;                 // closed nodes published to the shooter
     volatile int ew_done;                // expander stopped; shots needed for nodes < shot_limit
     volatile int shot_limit;
+    volatile int x_expanding, x_finished;   // expander warp 0 -> helper warp(s)
     int shot_best;                       // smallest pop index with a free word (atomicMin), AQ_NO_HIT if none
     // expander state
     int n_nodes, heap_n, counter, n_closed, ew_status, ew_arrival2;
@@ -113,6 +118,15 @@ __device__ __forceinline__ bool role_barrier_all(int id, int nthreads, bool pred
 __device__ __forceinline__ void role_sync(int id, int nthreads) {
 #if AQ_ALIGN
     asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
+#endif
+}
+
+// the warps of one scenario's expander team (named barrier 3 + slot)
+__device__ __forceinline__ void team_sync(int slot) {
+#if AQ_EXPANDERS > 1
+    asm volatile("bar.sync %0, %1;" :: "r"(3 + slot), "r"(AQ_TEAM) : "memory");
+#else
+    __syncwarp();
 #endif
 }
 
@@ -250,16 +264,21 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                  size_t ws_stride, unsigned int* work_counter, AwOut O) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int slot = wid / AQ_WARPS_PER_SLOT, role = wid % AQ_WARPS_PER_SLOT;   // role 0 = expander, 1.. = shooters
+    const int slot = wid / AQ_WARPS_PER_SLOT;
+    const int wrole = wid % AQ_WARPS_PER_SLOT;          // 0 .. AQ_EXPANDERS-1 = expander team, then the shooters
+    const int ew = wrole;                               // index inside the expander team
+    const int role = wrole < AQ_EXPANDERS ? 0 : wrole - AQ_EXPANDERS + 1;   // 0 = expander, 1.. = shooters
+    const int tl = ew * 32 + lane;                      // lane inside the expander team
     AqSmem& S = reinterpret_cast<AqSmem*>(smem_raw)[slot];
     const AsWs W = as_carve(ws_base + ((size_t)blockIdx.x * AQ_SLOTS + slot) * ws_stride, P.cap_nodes, P.hash_size,
                             P.max_nodes);
     const int hmask = P.hash_size - 1;
     const unsigned FLAGS = HL_CHECK_OBSTACLES | HL_CHECK_BOUNDARY | HL_CHECK_LANE;
-    if (role == 0) {
+    if (role == 0 && ew == 0) {
 #pragma unroll 1
         for (int i = lane; i < P.hash_size; i += 32) W.hkey[i] = KEY_EMPTY;
         if (lane == 0) {
+            S.x_expanding = 0; S.x_finished = 0;
             S.state = ST_IDLE; S.epoch = 0; S.popped = 0; S.ew_done = 0; S.shot_best = AQ_NO_HIT;
             for (int k = 0; k < AQ_SHOOTERS; ++k) S.sh[k].done_epoch = 0;
         }
@@ -511,9 +530,11 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
     int my_epoch = 0;
     const EnvDesc* Dp = eb.desc;
     unsigned e_iter = 0;
+    int helper_epoch = 0;
     while (true) {
-        if ((e_iter++ % AQ_EVERY_E) == 0 && role_barrier_all(2, AQ_SLOTS * 32, finished)) break;
+        if ((e_iter++ % AQ_EVERY_E) == 0 && role_barrier_all(2, AQ_SLOTS * AQ_TEAM, finished)) break;
         bool expanding = false;
+        if (ew == 0) {
         do {
         if (finished) break;
         ETICK(PH_SETUP);                 // time spent in the alignment barrier (+ attach / wait modes)
@@ -625,9 +646,29 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
             if (S.ew_status >= 0) mode = 2; else expanding = true;
         }
         } while (0);
-#if AQ_MID >= 1
-        role_sync(2, AQ_SLOTS * 32);                         // expanders enter the rollout / filter code together
-        if (expanding) ETICK(PH_SETUP);
+        }
+#if AQ_EXPANDERS > 1
+        if (ew == 0 && lane == 0) { S.x_expanding = expanding ? 1 : 0; S.x_finished = finished ? 1 : 0; }
+        team_sync(slot);
+        if (ew != 0) {                                       // the helper follows warp 0's decisions
+            expanding = S.x_expanding != 0; finished = S.x_finished != 0;
+            const int ep = S.epoch;
+            if (expanding && ep != helper_epoch) {           // new scenario: the float32 environment warp 0 staged
+                helper_epoch = ep;
+                Dp = eb.desc + S.env;
+                const EnvDesc& D0 = *Dp;
+                const int n_o = D0.n_obs * HL_OBS32_STRIDE, n_f = D0.n_field * HL_FIELD32_STRIDE, n_s = D0.n_seg * 4;
+                E.n_obs = D0.n_obs; E.n_field = D0.n_field; E.n_seg = D0.n_seg; E.all_rect = D0.all_rect;
+                E.eps = D0.eps; E.reach = D0.reach;
+                for (int k = 0; k < 4; ++k) E.ext[k] = (float)D0.body_ext[k];
+                if (n_o + n_f + n_s <= AW_ENV_FLOATS) { E.obs = S.envf; E.field = S.envf + n_o; E.seg = S.envf + n_o + n_f; }
+                else {
+                    E.obs = eb.obs32 + (size_t)HL_OBS32_STRIDE * D0.obs_off;
+                    E.field = eb.field32 + HL_FIELD32_STRIDE * (size_t)D0.field_off;
+                    E.seg = eb.seg32 + 4 * (size_t)D0.seg_off;
+                }
+            }
+        }
 #endif
         const EnvDesc& D = *Dp;
         if (expanding) {
@@ -636,7 +677,7 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
             const int total = P.n_prims * np1;
             // yaws[0..n+1] of every primitive once (the pose yaw of step i is yaws[i+1]), one sincos each
 #pragma unroll 1
-            for (int idx = lane; idx < P.n_prims * (np1 + 1); idx += 32) {
+            for (int idx = tl; idx < P.n_prims * (np1 + 1); idx += AQ_TEAM) {
                 const int p = idx / (np1 + 1), i = idx - p * (np1 + 1);
                 const double ys = P.yaw_step[p];
                 const double init_yaw = angle_wrap(xadd(S.cyaw, ys));
@@ -652,8 +693,8 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                     S.ty[p][i] = xmul(xmul(P.res, sn), P.dir[p]);
                 }
             }
-            __syncwarp();
-            if (lane < P.n_prims) {
+            team_sync(slot);
+            if (tl < P.n_prims) {
                 double ax = 0.0, ay = 0.0;
 #pragma unroll 1
                 for (int i = 0; i < np1; ++i) {
@@ -663,26 +704,26 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                     S.ty[lane][i] = xadd(S.cy, ay);
                 }
             }
-            __syncwarp();
-            ETICK(PH_ROLLOUT);
+            team_sync(slot);
+            if (ew == 0) ETICK(PH_ROLLOUT);
             // One hit kills a primitive, and a primitive that collides does so far from the (feasible) node it starts
             // at: test the two farthest poses of every primitive first, then only the live primitives' other poses.
             {
                 const int far_cnt = np1 < 2 ? np1 : 2;
 #pragma unroll 1
-                for (int idx = lane; idx < P.n_prims * far_cnt; idx += 32) {
+                for (int idx = tl; idx < P.n_prims * far_cnt; idx += AQ_TEAM) {
                     const int p = idx / far_cnt, j = n - (idx - p * far_cnt);
                     unsigned amb = 0;
                     int st = pose_filter(D, E, S.tx[p][j], S.ty[p][j], S.pyaw[p][j], FLAGS, &amb);
                     S.pamb[p][j] = (st == HL_AMBIG) ? (unsigned char)amb : 0;
                     if (st == HL_HIT) atomicOr(&S.phit[p], 1);
                 }
-                __syncwarp();
+                team_sync(slot);
                 const unsigned live = __ballot_sync(FULL, lane < P.n_prims && S.phit[lane] == 0);
                 const int rem = np1 - far_cnt;
                 const int total2 = __popc(live) * rem;
 #pragma unroll 1
-                for (int idx = lane; idx < total2; idx += 32) {
+                for (int idx = tl; idx < total2; idx += AQ_TEAM) {
                     const int q = idx / rem, j = idx - q * rem;
                     const int p = __fns(live, 0, q + 1);
                     unsigned amb = 0;
@@ -690,30 +731,26 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                     S.pamb[p][j] = (st == HL_AMBIG) ? (unsigned char)amb : 0;
                     if (st == HL_HIT) atomicOr(&S.phit[p], 1);
                 }
-                if (lane == 0) { S.e_checks += (unsigned long long)(P.n_prims * far_cnt + total2); S.e_ref += (unsigned long long)total; }
+                if (tl == 0) { S.e_checks += (unsigned long long)(P.n_prims * far_cnt + total2); S.e_ref += (unsigned long long)total; }
             }
-            __syncwarp();
-            ETICK(PH_FILTER);
+            team_sync(slot);
+            if (ew == 0) ETICK(PH_FILTER);
 #pragma unroll 1
-            for (int idx = lane; idx < total; idx += 32) {
+            for (int idx = tl; idx < total; idx += AQ_TEAM) {
                 const int p = idx / np1, j = idx - p * np1;
                 if (S.pamb[p][j] && !S.phit[p]) {
                     atomicAdd(&S.e_exact, 1ULL);
                     if (pose_exact(eb, D, S.tx[p][j], S.ty[p][j], S.pyaw[p][j], S.pamb[p][j])) atomicOr(&S.phit[p], 2);
                 }
             }
-            __syncwarp();
-            ETICK(PH_EXACT);
+            team_sync(slot);
+            if (ew == 0) ETICK(PH_EXACT);
             }
         }
-#if AQ_MID >= 2
-        role_sync(2, AQ_SLOTS * 32);                         // ... and the cost / heuristic / merge code
-        if (expanding) ETICK(PH_SETUP);
-#endif
         if (expanding) {
             {
             const int n = S.nsteps, np1 = n + 1;
-            if (lane < P.n_prims && !S.phit[lane]) {
+            if (tl < P.n_prims && !S.phit[lane]) {
                 const int p = lane;
                 double len = 0.0;
 #pragma unroll 1
@@ -739,17 +776,23 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                 S.ppos[p] = pos;
                 if (slot2 >= 0 && (W.nstate[slot2] == 1 || !(cost < W.ng[slot2]))) S.pneed[p] = 0;
             }
-            __syncwarp();
+            team_sync(slot);
+            {
+                int q = 0;                                   // needed primitives are dealt round-robin to the team's warps
 #pragma unroll 1
-            for (int p = 0; p < P.n_prims; ++p) {
-                if (!S.phit[p] && S.pneed[p]) {
-                    double h = warp_state_cost(eb, D, S.tx[p][n], S.ty[p][n], S.pyaw[p][n], lane);
-                    if (lane == 0) S.pprio[p] = xmul(P.hybrid_cost, h);
+                for (int p = 0; p < P.n_prims; ++p) {
+                    if (!S.phit[p] && S.pneed[p]) {
+                        if ((q % AQ_EXPANDERS) == ew) {
+                            double h = warp_state_cost(eb, D, S.tx[p][n], S.ty[p][n], S.pyaw[p][n], lane);
+                            if (lane == 0) S.pprio[p] = xmul(P.hybrid_cost, h);
+                        }
+                        ++q;
+                    }
                 }
             }
-            __syncwarp();
-            ETICK(PH_COST_HEUR);
-            if (lane == 0) {
+            team_sync(slot);
+            if (ew == 0) ETICK(PH_COST_HEUR);
+            if (tl == 0) {
 #pragma unroll 1
                 for (int p = 0; p < P.n_prims; ++p) {
                     if (S.phit[p]) continue;
@@ -777,9 +820,9 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
             }
             __syncwarp();
             }
-            ETICK(PH_MERGE);
-            if (S.ew_status >= 0) mode = 2;
+            if (ew == 0) { ETICK(PH_MERGE); if (S.ew_status >= 0) mode = 2; }
         }
+        if (ew != 0) continue;                               // the bookkeeping below is warp 0's
         if (finished) continue;
         if (mode == 2 && !S.ew_done) {
         // ---- tell the shooter how far its shots are needed, wait for it, assemble the result
