@@ -76,8 +76,8 @@ class ClockSampler:
             try:
                 self._run_nvml()
                 return
-            except Exception:
-                pass
+            except Exception as exc:           # fall back to nvidia-smi below
+                print(f"[bench] NVML sampling failed ({exc!r}); using nvidia-smi", file=sys.stderr)
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
