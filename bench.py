@@ -312,8 +312,8 @@ def main():
             "roofline": {"bound": "alu_fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp32_peak if fp32_peak else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one k_hybrid_astar_s launch on this very
-                         # workload (4096 scenarios), ncu --set full, profiles/r1h_ncu_full_summary.txt
-                         "traffic": 484523264 if args.scenarios_per_gpu == 4096 else None,
+                         # workload (4096 scenarios), ncu --set full, profiles/r1j_ncu_full_summary.txt
+                         "traffic": 504707840 if args.scenarios_per_gpu == 4096 else None,
                          "kernel": "k_hybrid_astar_s",
                          "executed_frac": (flops_exec / (kernel_ms / args.steps * 1e-3) * 1e-12 / fp32_peak) if fp32_peak else None,
                          "note": "no tensor cores on this path; algorithmic flop = pose checks the REFERENCE performs "
