@@ -30,12 +30,6 @@
 #define ETICK(ph) do { if (lane == 0) { long long _n = clock64(); S.te[ph] += _n - S.te_last; S.te_last = _n; } } while (0)
 #define STICK(ph) do { if (lane == 0) { long long _n = clock64(); S.ts[ph] += _n - S.ts_last; S.ts_last = _n; } } while (0)
 
-// candidate row of (pass, lane): pass 0 = SLS, LSL, LRL, LRSL, LRSR rows; pass 1 = LSR, LRLRN, LRLRP, LRSLR rows
-static __constant__ signed char c_aq_cand[2][32] = {
-    {0, 1, 2, 3, 4, 5, 10, 11, 12, 13, 14, 15, 16, 17, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 36, 37, 38, 39, 40, 41, -1, -1},
-    {6, 7, 8, 9, 18, 19, 20, 21, 22, 23, 24, 25, 42, 43, 44, 45, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1},
-};
-
 struct AqShot {                          // scratch of one shooter warp
     int s_cur; double sx, sy, syaw, sg;
     double rs_lens[HL_RS_CANDIDATES][HL_RS_MAX_SEGS];
@@ -369,7 +363,7 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                 // switch, so each formula's code runs once per shot instead of once per pass
 #pragma unroll 1
                 for (int pass = 0; pass < 2; ++pass) {
-                    const int c = c_aq_cand[pass][lane];
+                    const int c = c_rs_pass_cand[pass][lane];
                     if (c >= 0) {
                         double l[HL_RS_MAX_SEGS] = {0, 0, 0, 0, 0};
                         bool ok = rs_candidate(c, T.rs_prob, l);

@@ -43,6 +43,14 @@ static __constant__ RsRow c_rs_rows[HL_RS_CANDIDATES] = {
     RS_QUAD(RS_LRSLR, 0, RP_THUHV, 5, RS_LET5(RS_L, RS_R, RS_S, RS_L, RS_R), RS_LET5(RS_R, RS_L, RS_S, RS_R, RS_L)),
 };
 
+// candidate row of (pass, lane) when a warp evaluates the 46 rows in two passes with DISJOINT solver sets
+// (pass 0 = SLS, LSL, LRL, LRSL, LRSR rows; pass 1 = LSR, LRLRN, LRLRP, LRSLR rows): the lanes of a pass diverge
+// over the solver switch, so each formula's code then runs once per pair instead of once per pass
+static __constant__ signed char c_rs_pass_cand[2][32] = {
+    {0, 1, 2, 3, 4, 5, 10, 11, 12, 13, 14, 15, 16, 17, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 36, 37, 38, 39, 40, 41, -1, -1},
+    {6, 7, 8, 9, 18, 19, 20, 21, 22, 23, 24, 25, 42, 43, 44, 45, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1},
+};
+
 __device__ __forceinline__ int rs_letter(unsigned short letters, int i) { return (letters >> (2 * i)) & 3; }
 
 // ---- word solvers: float64, reference operation order -------------------------
