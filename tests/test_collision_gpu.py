@@ -87,3 +87,23 @@ def test_empty_and_single(built_library):
     far = np.array([[1e4, -2e4, 0.3], [float("nan"), 0.0, 0.0]])
     got = g_env.pose_flags(g_car, far).cpu().numpy().astype(bool)
     assert got[0]
+
+
+def test_non_finite_poses_are_infeasible(built_library):
+    """A pose with NaN / infinite coordinates can never be certified free: K1 reports it infeasible (this is also
+    how hl_ypark_paths poisons a candidate whose pose count disagrees with the host's)."""
+    rows = H.canonical_rows()
+    (o_env, o_car, _), (g_env, g_car, _) = H.make_pair(rows)
+    poses = np.array([[np.nan, 1.0, 0.0], [1.0, np.nan, 0.0], [-3.0, 8.0, np.nan], [np.inf, 0.0, 0.0],
+                      [-3.0, 8.0, np.inf], [-4.0, 9.0, 0.3]])
+    got = g_env.pose_flags(g_car, poses).cpu().numpy().astype(bool)
+    assert got[:5].all()
+    assert got[5] == o_env.pose_flags(o_car, poses[5:6])[0]
+
+
+def test_candidate_generators_empty(built_library):
+    from headland_trajectory_planning_b200 import ops
+    p, o = ops.ypark_paths(np.zeros((0, 8)), 0.1)
+    assert p.shape == (0, 3) and list(o) == [0]
+    p, o = ops.arc_paths(np.zeros((0, 8)), 0.1)
+    assert p.shape == (0, 3) and list(o) == [0]
