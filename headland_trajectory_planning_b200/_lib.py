@@ -76,7 +76,7 @@ EXPORTS = [
     "hl_last_error", "hl_abi_version", "hl_ctx_create", "hl_ctx_destroy", "hl_ctx_sm_count",
     "hl_env_upload", "hl_env_free", "hl_env_count", "hl_collision_check", "hl_path_reduce",
     "hl_rs_all_paths", "hl_rs_sample", "hl_hybrid_astar_batch", "hl_hybrid_astar_workspace_bytes", "hl_astar_phase_cycles",
-    "hl_distance_field", "hl_grid_pack", "hl_grid_footprint_check", "hl_measure_fp32_peak", "hl_ypark_paths", "hl_arc_paths",
+    "hl_distance_field", "hl_grid_pack", "hl_grid_footprint_check", "hl_measure_fp32_peak", "hl_ypark_paths", "hl_arc_paths", "hl_ref_path_count", "hl_ref_path_fill",
 ]
 
 
@@ -154,6 +154,8 @@ def load_library():
         lib.hl_measure_fp32_peak.argtypes = [vp, C.POINTER(dbl)]
         lib.hl_ypark_paths.argtypes = [vp, vp, vp, i64, dbl, vp, vp]
         lib.hl_arc_paths.argtypes = [vp, vp, vp, i64, dbl, vp, vp]
+        lib.hl_ref_path_count.argtypes = [vp, vp, vp, vp, vp, i64, dbl, vp, vp, vp]
+        lib.hl_ref_path_fill.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, dbl, dbl, dbl, vp, vp, vp]
         if lib.hl_abi_version() != 1:
             raise HeadlandError("libheadland_b200.so ABI version mismatch")
         _lib = lib

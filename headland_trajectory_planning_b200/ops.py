@@ -100,6 +100,41 @@ def arc_paths(cand, step):
     return poses, offsets
 
 
+def ref_path_batch(x, y, direction, in_offsets, wheel_base, desired_v=0.5, ds=0.1):
+    """OBCA initial guesses of many planner paths (K8, ``hl_ref_path_count`` + ``hl_ref_path_fill``).
+    ``x, y`` float64 and ``direction`` int8 pooled pose arrays (CUDA tensors or host arrays), ``in_offsets`` [n+1].
+    Returns (traj [T,5] float64 CUDA tensor: x, y, v, yaw, steer; out_offsets [n+1] int64 host; status [n] int32 host,
+    1 = a direction piece with fewer than two distinct poses, no rows)."""
+    torch = _torch()
+    lib = _lib.load_library()
+    dev = _device()
+    def dev_t(a, dt):
+        if torch.is_tensor(a):
+            return a.to(dev).to(dt).contiguous()
+        return torch.from_numpy(np.ascontiguousarray(a)).to(dev).to(dt).contiguous()
+    x, y = dev_t(x, torch.float64), dev_t(y, torch.float64)
+    direction = dev_t(direction, torch.int8)
+    in_off = dev_t(np.asarray(in_offsets, dtype=np.int64), torch.int64)
+    n = in_off.numel() - 1
+    counts = torch.zeros(max(n, 1), dtype=torch.int64, device=dev)
+    status = torch.zeros(max(n, 1), dtype=torch.int32, device=dev)
+    ctx = _lib.get_ctx(dev.index)
+    if n > 0:
+        _lib.check(lib.hl_ref_path_count(ctx, _lib.ptr(x), _lib.ptr(y), _lib.ptr(direction), _lib.ptr(in_off), n, float(ds),
+                                         _lib.ptr(counts), _lib.ptr(status), _lib.stream_ptr()), "hl_ref_path_count")
+    out_off = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    if n > 0:
+        out_off[1:] = torch.cumsum(counts[:n], 0)
+    total = int(out_off[-1].item())
+    traj = torch.empty((total, 5), dtype=torch.float64, device=dev)
+    if n > 0 and total > 0:
+        ws = torch.empty(8 * max(int(x.numel()), 1), dtype=torch.float64, device=dev)
+        _lib.check(lib.hl_ref_path_fill(ctx, _lib.ptr(x), _lib.ptr(y), _lib.ptr(direction), _lib.ptr(in_off), _lib.ptr(out_off),
+                                        _lib.ptr(status), n, float(wheel_base), float(desired_v), float(ds), _lib.ptr(ws),
+                                        _lib.ptr(traj), _lib.stream_ptr()), "hl_ref_path_fill")
+    return traj, out_off.cpu().numpy(), status[:n].cpu().numpy()
+
+
 def measure_fp32_peak(device=None):
     lib = _lib.load_library()
     v = C.c_double()

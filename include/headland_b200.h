@@ -204,6 +204,23 @@ int hl_ypark_paths(hl_ctx* ctx, const double* d_cand, const int64_t* d_offsets, 
 int hl_arc_paths(hl_ctx* ctx, const double* d_cand, const int64_t* d_offsets, int64_t n, double step,
                  double* d_poses, void* stream);
 
+/* ---- K8 warm-start path -> OBCA initial guess -------------
+ * Replaces get_init_ref_path (obca_py/util.py:62-113) + calc_spline_course / Spline2D
+ * (path_planner/utils/cubic_spline.py:19-112) for many paths at once.  Input = the pooled path
+ * arrays of hl_hybrid_astar_batch (x, y, direction) with per-path offsets.
+ *   hl_ref_path_count: d_counts[p] = rows of path p's trajectory (0 and d_status[p] = 1 when a
+ *                      direction piece has fewer than 2 distinct poses -- the reference raises there);
+ *                      the caller turns the counts into d_out_offsets [n+1] (exclusive prefix sum)
+ *   hl_ref_path_fill:  d_out [offsets[n]][5] float64 rows (x, y, v, yaw, steer), yaw unwrapped along
+ *                      each path (process_angle, util.py:16-44); d_workspace = 8 doubles per INPUT pose */
+int hl_ref_path_count(hl_ctx* ctx, const double* d_x, const double* d_y, const int8_t* d_dir,
+                      const int64_t* d_in_offsets, int64_t n_paths, double ds, int64_t* d_counts,
+                      int32_t* d_status, void* stream);
+int hl_ref_path_fill(hl_ctx* ctx, const double* d_x, const double* d_y, const int8_t* d_dir,
+                     const int64_t* d_in_offsets, const int64_t* d_out_offsets, const int32_t* d_status,
+                     int64_t n_paths, double wheel_base, double desired_v, double ds, double* d_workspace,
+                     double* d_out, void* stream);
+
 /* ---- K2/K3 Reeds-Shepp --------------------------------------------------------
  * Replaces reeds_shepp.calc_all_paths (path_planner/utils/reeds_shepp.py:39-65):
  * generate_path + set_path dedup (:565-582, :68-87) and the sample count of

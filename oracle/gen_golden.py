@@ -6,6 +6,7 @@ container, where ``/root/reference`` exists):
     python -m oracle.gen_golden astar_ref N  # the REFERENCE's own search loop on scenarios 0..N-1
     python -m oracle.gen_golden ypark N      # the REFERENCE's own Y-park sweep on N scenarios
     python -m oracle.gen_golden offset N     # the REFERENCE's own get_offset_pose on N scenarios
+    python -m oracle.gen_golden refpath      # the REFERENCE's own get_init_ref_path on the golden planner paths
 
 TEST INFRASTRUCTURE (see ``oracle/__init__.py``).
 
@@ -292,6 +293,45 @@ def gen_offset(n):
     print("offset_golden.npz:", len(res), "sweeps; distances", sorted(set(np.round([r["dist"] for r in res], 1)))[:30])
 
 
+def gen_refpath():
+    """obca_py/util.get_init_ref_path of the REFERENCE on the paths of astar_golden.npz (+ synthetic paths with
+    several direction changes, repeated poses and 2- / 3-pose pieces)."""
+    from . import ref_loader
+    U = ref_loader.load_obca_util()
+
+    class Car:
+        WHEEL_BASE = 1.9
+
+    g = np.load(os.path.join(GOLD, "astar_golden.npz"))
+    po = np.concatenate([[0], np.cumsum(g["path_len"])])
+    paths = [g["path"][po[i]:po[i + 1]] for i in range(96) if g["path_len"][i] >= 4]
+    rng = np.random.default_rng(7)
+    for k in range(24):                                   # synthetic: arcs glued with direction flips
+        n_seg = int(rng.integers(1, 5))
+        pts, d = [], 1.0
+        x, y, yaw = rng.uniform(-5, 5), rng.uniform(-5, 5), rng.uniform(-3, 3)
+        for sgi in range(n_seg):
+            m = int(rng.choice([2, 3, 4, 9, 30]))
+            kap = rng.uniform(-0.3, 0.3)
+            for j in range(m):
+                pts.append([x, y, yaw, kap, d])
+                if rng.random() < 0.1:
+                    pts.append([x, y, yaw, kap, d])        # repeated pose (singular point)
+                x += d * 0.2 * math.cos(yaw); y += d * 0.2 * math.sin(yaw); yaw += d * 0.2 * kap
+            d = -d
+        paths.append(np.array(pts))
+    keep, trajs = [], []
+    for p in paths:
+        try:
+            t = U.get_init_ref_path(Car(), p[:, 0], p[:, 1], p[:, 2], p[:, 3], p[:, 4])
+        except ValueError:
+            t = np.zeros((0, 5))                           # a piece with fewer than 2 distinct poses: the reference raises
+        keep.append(p); trajs.append(np.asarray(t, dtype=np.float64).reshape(-1, 5))
+    np.savez_compressed(os.path.join(GOLD, "refpath_golden.npz"), path_len=np.array([len(p) for p in keep]),
+                        path=np.concatenate(keep), traj_len=np.array([len(t) for t in trajs]), traj=np.concatenate(trajs))
+    print("refpath_golden.npz:", len(keep), "paths;", int(sum(len(t) == 0 for t in trajs)), "raise in the reference")
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     args = sys.argv[1:]
@@ -303,6 +343,8 @@ if __name__ == "__main__":
         gen_astar(int(args[args.index("astar") + 1]))
     if "astar_ref" in args:
         gen_astar_ref(int(args[args.index("astar_ref") + 1]))
+    if "refpath" in args:
+        gen_refpath()
     if "offset" in args:
         gen_offset(int(args[args.index("offset") + 1]))
     if "ypark" in args:

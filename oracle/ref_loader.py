@@ -119,3 +119,25 @@ def load_planner(name, heapdict_port=True):
                 del sys.modules[k]
         sys.modules.update(stash)
         sys.path[:] = saved_path
+
+
+def load_obca_util():
+    """``obca_py/util.py`` of the reference for real (its ``car_model_obca`` import -- casadi -- is replaced by a stub;
+    ``cubic_spline`` resolves to ``path_planner/utils/cubic_spline.py``, scipy is installed)."""
+    saved_mods = dict(sys.modules)
+    saved_path = list(sys.path)
+    try:
+        stub = types.ModuleType("car_model_obca")
+        stub.CarModel = object
+        sys.modules["car_model_obca"] = stub
+        sys.path.insert(0, os.path.join(REFERENCE_ROOT, "path_planner", "utils"))
+        path = os.path.join(REFERENCE_ROOT, "obca_py", "util.py")
+        spec = importlib.util.spec_from_file_location("_hl_reference_obca_util", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+    finally:
+        for k in list(sys.modules):
+            if k not in saved_mods:
+                del sys.modules[k]
+        sys.path[:] = saved_path
