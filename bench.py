@@ -275,6 +275,7 @@ def main():
     coll_paths = None
     ypark = None
     rs_sweep = None
+    refpath = None
     fp32_peak = None
     if rank == 0:
         fp32_peak = ops.measure_fp32_peak(local_rank)
@@ -284,6 +285,7 @@ def main():
         coll_paths = collision_microbench(args, dev, fp32_peak)
         ypark = ypark_microbench(args, dev, world == 1 and not args.no_cpu_baseline)
         rs_sweep = rs_microbench(args, dev, world == 1 and not args.no_cpu_baseline)
+        refpath = refpath_microbench(out, car.WHEEL_BASE, world == 1 and not args.no_cpu_baseline)
 
     # ---------------- CPU baseline (rank 0, N = 1 only)
     cpu = None
@@ -322,7 +324,7 @@ def main():
                                  "(SURVEY 8d); executed_frac counts only the checks the kernel ran after its early "
                                  "exits; peak = FFMA micro-benchmark measured in this run; the kernel is a "
                                  "latency-bound search, see kernels.k_collision for the ALU-bound kernel"},
-            "kernels": {"k_collision": coll, "k_collision_path_ordered": coll_paths, "ypark_sweep": ypark, "rs_sweep": rs_sweep},
+            "kernels": {"k_collision": coll, "k_collision_path_ordered": coll_paths, "ypark_sweep": ypark, "rs_sweep": rs_sweep, "ref_path": refpath},
             "search": {"expansions": expansions, "pose_checks": n_checks, "pose_checks_algorithmic": n_checks_ref,
                        "exact_escalations": n_exact,
                        "status": status_hist},
@@ -408,6 +410,41 @@ def collision_microbench(args, dev, fp32_peak):
                          # 35.9 B of DRAM traffic per pose (ncu --set full, 4 Mi poses, profiles/r1h_ncu_full_summary.txt)
                          # against 25 B algorithmic (24 B pose in + 1 B flag out)
                          "traffic": int(35.9 * n)}}
+
+
+def refpath_microbench(out, wheel_base, with_cpu):
+    """the sweep's paths (still on the GPU) -> OBCA initial guesses (K8)."""
+    import time
+    import torch
+    from headland_trajectory_planning_b200 import _lib, obca_util as GU
+    GU.get_init_ref_path_batch(out, wheel_base)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        traj, off, status = GU.get_init_ref_path_batch(out, wheel_base)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / reps
+    n_paths = int((np.diff(off) > 0).sum())
+    res = {"metric": "ref_paths_per_sec", "value": n_paths / dt, "unit": "paths/s", "paths": n_paths,
+           "rows": int(off[-1]), "ms_per_batch": dt * 1e3, "scenarios_without_rows": int(status.sum())}
+    if with_cpu:
+        from oracle import obca_util as OU
+        r = out["results"].cpu().numpy().view(_lib.RESULT_DTYPE)
+        x, y, d = out["x"].cpu().numpy(), out["y"].cpu().numpy(), out["dir"].cpu().numpy()
+        picks = [i for i in range(len(r)) if r["path_len"][i] > 4][:32]
+        t0 = time.perf_counter()
+        done = 0
+        for i in picks:
+            a, b = int(r["path_offset"][i]), int(r["path_offset"][i] + r["path_len"][i])
+            try:
+                OU.get_init_ref_path(wheel_base, x[a:b], y[a:b], x[a:b] * 0, x[a:b] * 0, d[a:b].astype(np.float64))
+            except ValueError:
+                pass
+            done += 1
+        res["cpu_baseline"] = {"value": done / (time.perf_counter() - t0), "unit": "paths/s", "cores": 1, "kind": "port",
+                               "sample": f"first {done} paths, oracle (scipy CubicSpline like the reference)"}
+    return res
 
 
 def rs_microbench(args, dev, with_cpu):
