@@ -27,8 +27,16 @@
 #define AQ_WARPS_PER_SLOT (AQ_EXPANDERS + AQ_SHOOTERS)
 #define AQ_TEAM (32 * AQ_EXPANDERS)
 #define AQ_NO_HIT 0x7fffffff
+#ifndef AQ_TIMERS
+#define AQ_TIMERS 1                    // per-role phase timers (hl_astar_phase_cycles); 0 removes ~26 hot timing sites
+#endif
+#if AQ_TIMERS
 #define ETICK(ph) do { if (lane == 0) { long long _n = clock64(); S.te[ph] += _n - S.te_last; S.te_last = _n; } } while (0)
 #define STICK(ph) do { if (lane == 0) { long long _n = clock64(); S.ts[ph] += _n - S.ts_last; S.ts_last = _n; } } while (0)
+#else
+#define ETICK(ph) do { } while (0)
+#define STICK(ph) do { } while (0)
+#endif
 
 struct AqShot {                          // scratch of one shooter warp
     int s_cur; double sx, sy, syaw, sg;
