@@ -12,7 +12,9 @@
 // predicates.  Roofline: FP32 ALU (12..24 B of HBM traffic per ~2.5 kflop check).
 #include "hl_geom.cuh"
 
+#ifndef K1_THREADS
 #define K1_THREADS 256
+#endif
 
 // Ambiguous poses of a warp are resolved one at a time by the WHOLE warp (warp_exact_part_check): the pose
 // is broadcast with shuffles and the exact float64 predicate runs on 32 lanes.
