@@ -69,8 +69,10 @@ struct hl_ctx {
     unsigned int* d_counters; // small device scratch (work-queue counter etc.)
     void* stage;              // pinned staging buffer of hl_env_upload (grow-only)
     size_t stage_bytes;
-    void* env_cache;          // device block of the last freed environment batch, reused by the next upload
-    size_t env_cache_bytes;
+    void* env_cache[2];       // device blocks of freed environment batches, reused by later uploads (two: double buffering)
+    size_t env_cache_bytes[2];
+    void* copy_stream;        // non-blocking stream of hl_env_upload's H2D copy (does not wait for running kernels)
+    void* mu;                 // std::mutex*: one upload / cache hand-over at a time (uploads may come from a prefetch thread)
     void* ls_state;           // level-synchronous search: graph, streams, pools (hl_astar.cu)
     void (*ls_free)(void*);
 };

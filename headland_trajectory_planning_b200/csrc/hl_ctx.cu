@@ -5,6 +5,7 @@
 #include <vector>
 #include <cstdlib>
 #include <thread>
+#include <mutex>
 #include <cmath>
 #include "hl_common.cuh"
 
@@ -47,10 +48,16 @@ extern "C" int hl_ctx_create(hl_ctx** out, int device) {
     c->d_counters = nullptr;
     c->stage = nullptr;
     c->stage_bytes = 0;
-    c->env_cache = nullptr;
-    c->env_cache_bytes = 0;
+    c->env_cache[0] = c->env_cache[1] = nullptr;
+    c->env_cache_bytes[0] = c->env_cache_bytes[1] = 0;
     c->ls_state = nullptr;
     c->ls_free = nullptr;
+    c->copy_stream = nullptr;
+    c->mu = new std::mutex();
+    {
+        cudaStream_t cs = nullptr;
+        if (cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) == cudaSuccess) c->copy_stream = cs;
+    }
     if (cudaMalloc(&c->d_counters, 256 * sizeof(unsigned int)) != cudaSuccess) {
         hl_set_error("hl_ctx_create: cudaMalloc failed");
         delete c;
@@ -67,8 +74,10 @@ extern "C" void hl_ctx_destroy(hl_ctx* ctx) {
     if (ctx->astar_ws) cudaFree(ctx->astar_ws);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->stage) cudaFreeHost(ctx->stage);
-    if (ctx->env_cache) cudaFree(ctx->env_cache);
+    for (int k = 0; k < 2; ++k) if (ctx->env_cache[k]) cudaFree(ctx->env_cache[k]);
     if (ctx->ls_state && ctx->ls_free) ctx->ls_free(ctx->ls_state);
+    if (ctx->copy_stream) cudaStreamDestroy((cudaStream_t)ctx->copy_stream);
+    delete (std::mutex*)ctx->mu;
     delete ctx;
 }
 
@@ -78,12 +87,24 @@ extern "C" void hl_env_free(hl_env_batch* envs) {
     if (!envs) return;
     cudaSetDevice(envs->device);
     hl_ctx* c = envs->owner;
+    std::unique_lock<std::mutex> lock;
+    if (c && c->mu) lock = std::unique_lock<std::mutex>(*(std::mutex*)c->mu);
     for (int i = 0; i < envs->n_allocs; ++i) {
-        // keep one block per context for the next upload (cudaFree synchronises the device)
-        if (i == 0 && c && envs->block_bytes > c->env_cache_bytes) {
+        // keep up to two blocks per context for later uploads (cudaFree synchronises the device): the smallest
+        // cached block gives way to a bigger one
+        int slot = -1;
+        if (i == 0 && c) {
+            if (!c->env_cache[0]) slot = 0;
+            else if (!c->env_cache[1]) slot = 1;
+            else {
+                const int small = c->env_cache_bytes[0] <= c->env_cache_bytes[1] ? 0 : 1;
+                if (envs->block_bytes > c->env_cache_bytes[small]) slot = small;
+            }
+        }
+        if (slot >= 0) {
             cudaDeviceSynchronize();               // like cudaFree: no kernel on any stream may still read the block
-            if (c->env_cache) cudaFree(c->env_cache);
-            c->env_cache = envs->allocs[0]; c->env_cache_bytes = envs->block_bytes;
+            if (c->env_cache[slot]) cudaFree(c->env_cache[slot]);
+            c->env_cache[slot] = envs->allocs[0]; c->env_cache_bytes[slot] = envs->block_bytes;
         } else cudaFree(envs->allocs[i]);
     }
     delete envs;
@@ -104,6 +125,7 @@ static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 extern "C" int hl_env_upload(hl_ctx* ctx, const HlEnvHost* h, int32_t n_env, hl_env_batch** out) {
     if (!ctx || !h || !out || n_env <= 0) { hl_set_error("hl_env_upload: bad arguments"); return 1; }
     HL_CUDA_OK(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> lock(*(std::mutex*)ctx->mu);      // the staging buffer and the block cache are shared
     size_t n_obs = 0, n_field = 0, n_seg = 0, n_crit = 0, n_guide = 0, n_aux = 0;
     std::vector<size_t> offs(6 * (size_t)n_env);
     for (int e = 0; e < n_env; ++e) {
@@ -266,12 +288,17 @@ extern "C" int hl_env_upload(hl_ctx* ctx, const HlEnvHost* h, int32_t n_env, hl_
     char* d = nullptr;
     b->owner = ctx;
     b->block_bytes = L.total;
-    if (ctx->env_cache && ctx->env_cache_bytes >= L.total) {          // reuse the block of a batch freed earlier
-        d = (char*)ctx->env_cache; b->block_bytes = ctx->env_cache_bytes;
-        ctx->env_cache = nullptr; ctx->env_cache_bytes = 0;
+    int pick = -1;                                                    // smallest cached block that is big enough
+    for (int k = 0; k < 2; ++k)
+        if (ctx->env_cache[k] && ctx->env_cache_bytes[k] >= L.total &&
+            (pick < 0 || ctx->env_cache_bytes[k] < ctx->env_cache_bytes[pick])) pick = k;
+    if (pick >= 0) {                                                  // reuse the block of a batch freed earlier
+        d = (char*)ctx->env_cache[pick]; b->block_bytes = ctx->env_cache_bytes[pick];
+        ctx->env_cache[pick] = nullptr; ctx->env_cache_bytes[pick] = 0;
     } else if (cudaMalloc(&d, L.total) != cudaSuccess) { delete b; hl_set_error("hl_env_upload: cudaMalloc(%zu) failed", L.total); return 1; }
     b->allocs[b->n_allocs++] = d;
-    if (cudaMemcpyAsync(d, S, L.total, cudaMemcpyHostToDevice, 0) != cudaSuccess || cudaStreamSynchronize(0) != cudaSuccess) {
+    cudaStream_t cs = (cudaStream_t)ctx->copy_stream;       // nullptr = legacy default stream
+    if (cudaMemcpyAsync(d, S, L.total, cudaMemcpyHostToDevice, cs) != cudaSuccess || cudaStreamSynchronize(cs) != cudaSuccess) {
         hl_env_free(b); hl_set_error("hl_env_upload: copy failed"); return 1;
     }
     b->dev.desc = (const EnvDesc*)(d + L.off[0]);

@@ -86,3 +86,34 @@ def merge_shards(per_rank_results, per_rank_expanded, n_total, world_size):
     res["keys_offset"] = off[:-1]
     exp = np.concatenate(chunks) if n_total else np.zeros((0, 3), np.int32)
     return res, exp
+
+
+class UploadPrefetcher:
+    """Double buffering for back-to-back sweeps: ``hl_env_upload`` of the NEXT batch (host packing + H2D copy on the
+    context's own copy stream) runs in a worker thread while the current batch is being searched, so the
+    upload disappears from the critical path.  ctypes releases the GIL inside the C calls.
+
+        pf = UploadPrefetcher()
+        pf.submit(records, structs)                 # batch 0
+        for k in range(n):
+            envs = pf.result()
+            if k + 1 < n: pf.submit(records_next, structs_next)
+            out = ops.hybrid_astar_batch(envs, scen, params)
+            envs.close()
+    """
+
+    def __init__(self):
+        from concurrent.futures import ThreadPoolExecutor
+        self._ex = ThreadPoolExecutor(max_workers=1)
+        self._fut = None
+
+    def submit(self, records, structs=None):
+        from .env_batch import EnvBatch
+        self._fut = self._ex.submit(EnvBatch, records, structs=structs)
+
+    def result(self):
+        fut, self._fut = self._fut, None
+        return fut.result()
+
+    def close(self):
+        self._ex.shutdown(wait=True)
