@@ -236,7 +236,7 @@ __device__ __noinline__ double warp_state_cost(const EnvBatchDev& eb, const EnvD
 
 // One step of the kinematic rollout (kinematic_simulation_node, :366-390): yaws[i] of
 // np.linspace(init_yaw, init_yaw + yaw_step*(n+1), n+2) after angle_wrap.
-__device__ HL_CODE double rollout_yaw(double init_yaw, double stop, double step, double delta, int div, int i) {
+__device__ HL_TINY double rollout_yaw(double init_yaw, double stop, double step, double delta, int div, int i) {
     double v;
     if (i == div) v = stop;                                     // y[-1] = stop
     else if (step != 0.0) v = xadd(xmul((double)i, step), init_yaw);

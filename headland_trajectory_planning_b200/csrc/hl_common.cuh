@@ -99,6 +99,9 @@ void hl_set_error(const char* fmt, ...);
 #else
 #define HL_LOOP
 #endif
+#ifndef HL_TINY
+#define HL_TINY __forceinline__          // tiny helpers: a call frame costs as much as their body
+#endif
 #ifdef HL_SHARED_CODE
 #define HL_CODE __noinline__
 #else
@@ -117,11 +120,11 @@ static __device__ HL_CODE void m_sincos(double x, double* s, double* c) { sincos
 __device__ __forceinline__ double xmul(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double xadd(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double xsub(double a, double b) { return __dadd_rn(a, -b); }
-static __device__ HL_CODE double xdiv(double a, double b) { return __ddiv_rn(a, b); }
+static __device__ HL_TINY double xdiv(double a, double b) { return __ddiv_rn(a, b); }
 
 // Python / numpy floored modulo for a positive modulus (CPython float_rem,
 // numpy npy_divmod): fmod, then shift negative remainders up.
-static __device__ HL_CODE double py_mod_pos(double a, double m) {
+static __device__ HL_TINY double py_mod_pos(double a, double m) {
     double r = m_fmod(a, m);         // exact in CUDA
     if (r != 0.0) {
         if (r < 0.0) r = xadd(r, m);
