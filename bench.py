@@ -330,6 +330,9 @@ def main():
                          # workload (4096 scenarios), ncu --set full, profiles/r1j_ncu_full_summary.txt
                          "traffic": 504707840 if args.scenarios_per_gpu == 4096 else None,
                          "kernel": "k_hybrid_astar_s",
+                         # the same launch against the HBM roof (this path is not bandwidth-bound): algorithmic
+                         # bytes = environments + scenario records in, result records + key sequences + paths out
+                         "hbm": hbm_view(h2d + d2h, kernel_ms / args.steps),
                          "executed_frac": (flops_exec / (kernel_ms / args.steps * 1e-3) * 1e-12 / fp32_peak) if fp32_peak else None,
                          "note": "no tensor cores on this path; algorithmic flop = pose checks the REFERENCE performs "
                                  "for the same searches (poses of every Reeds-Shepp word tried + of every primitive "
@@ -423,6 +426,16 @@ def collision_microbench(args, dev, fp32_peak):
                          # 35.9 B of DRAM traffic per pose (ncu --set full, 4 Mi poses, profiles/r1h_ncu_full_summary.txt)
                          # against 25 B algorithmic (24 B pose in + 1 B flag out)
                          "traffic": int(35.9 * n)}}
+
+
+def hbm_view(bytes_per_launch, ms_per_launch):
+    peak = None
+    try:
+        peak = float(json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        peak = 6549.1                   # the pool's measured copy bandwidth (MEASURED_PEAKS.json at build time)
+    achieved = bytes_per_launch / (ms_per_launch * 1e-3) * 1e-9
+    return {"achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak}
 
 
 def refpath_microbench(out, wheel_base, with_cpu):
