@@ -72,7 +72,7 @@ struct hl_ctx {
     void* env_cache[2];       // device blocks of freed environment batches, reused by later uploads (two: double buffering)
     size_t env_cache_bytes[2];
     void* copy_stream;        // non-blocking stream of hl_env_upload's H2D copy (does not wait for running kernels)
-    void* mu;                 // std::mutex*: one upload / cache hand-over at a time (uploads may come from a prefetch thread)
+    void* mu;                 // std::recursive_mutex*: one upload / cache hand-over at a time (uploads may come from a prefetch thread)
     void* ls_state;           // level-synchronous search: graph, streams, pools (hl_astar.cu)
     void (*ls_free)(void*);
 };

@@ -53,7 +53,7 @@ extern "C" int hl_ctx_create(hl_ctx** out, int device) {
     c->ls_state = nullptr;
     c->ls_free = nullptr;
     c->copy_stream = nullptr;
-    c->mu = new std::mutex();
+    c->mu = new std::recursive_mutex();
     {
         cudaStream_t cs = nullptr;
         if (cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) == cudaSuccess) c->copy_stream = cs;
@@ -77,7 +77,7 @@ extern "C" void hl_ctx_destroy(hl_ctx* ctx) {
     for (int k = 0; k < 2; ++k) if (ctx->env_cache[k]) cudaFree(ctx->env_cache[k]);
     if (ctx->ls_state && ctx->ls_free) ctx->ls_free(ctx->ls_state);
     if (ctx->copy_stream) cudaStreamDestroy((cudaStream_t)ctx->copy_stream);
-    delete (std::mutex*)ctx->mu;
+    delete (std::recursive_mutex*)ctx->mu;
     delete ctx;
 }
 
@@ -87,8 +87,8 @@ extern "C" void hl_env_free(hl_env_batch* envs) {
     if (!envs) return;
     cudaSetDevice(envs->device);
     hl_ctx* c = envs->owner;
-    std::unique_lock<std::mutex> lock;
-    if (c && c->mu) lock = std::unique_lock<std::mutex>(*(std::mutex*)c->mu);
+    std::unique_lock<std::recursive_mutex> lock;
+    if (c && c->mu) lock = std::unique_lock<std::recursive_mutex>(*(std::recursive_mutex*)c->mu);
     for (int i = 0; i < envs->n_allocs; ++i) {
         // keep up to two blocks per context for later uploads (cudaFree synchronises the device): the smallest
         // cached block gives way to a bigger one
@@ -125,7 +125,7 @@ static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 extern "C" int hl_env_upload(hl_ctx* ctx, const HlEnvHost* h, int32_t n_env, hl_env_batch** out) {
     if (!ctx || !h || !out || n_env <= 0) { hl_set_error("hl_env_upload: bad arguments"); return 1; }
     HL_CUDA_OK(cudaSetDevice(ctx->device));
-    std::lock_guard<std::mutex> lock(*(std::mutex*)ctx->mu);      // the staging buffer and the block cache are shared
+    std::lock_guard<std::recursive_mutex> lock(*(std::recursive_mutex*)ctx->mu);      // the staging buffer and the block cache are shared
     size_t n_obs = 0, n_field = 0, n_seg = 0, n_crit = 0, n_guide = 0, n_aux = 0;
     std::vector<size_t> offs(6 * (size_t)n_env);
     for (int e = 0; e < n_env; ++e) {
