@@ -1,4 +1,5 @@
-// hl_astar_spec.cuh -- K4 variant C: two warps per scenario, speculative decoupling of the analytic shot.
+// hl_astar_spec.cuh -- K4 (default): an expander team and a shooter warp per scenario, speculative decoupling of
+// the analytic shot.
 //
 // In the reference every popped node first gets a Reeds-Shepp shot and is expanded only if the shot fails
 // (hybrid_a_star_search.py:542-596).  A FAILED shot has no side effect, and a successful one ends the search
@@ -10,6 +11,9 @@
 //   * if the shooter finds a free word at pop i the search ends THERE: the record is truncated to the first
 //     i+1 closed nodes, exactly what the reference returns; the expander's extra work is discarded.
 // The critical path per pop becomes max(shot, expansion) instead of their sum.
+// The expander is a TEAM of AQ_EXPANDERS warps (warp 0 owns the open list; the helper shares rollout, filter,
+// escalation and heuristics); same-role warps of a CTA are kept in step by named barriers so that they share
+// instruction-cache fills -- a pop is bound by the ~86 KB of distinct code it walks, see DESIGN.md section 5.
 #pragma once
 #include "hl_astar_common.cuh"
 
