@@ -25,7 +25,7 @@ Pinning status (see DESIGN.md "Oracle"):
     ``path_planner/hybrid_a_star_search.py`` / ``headland_path_planning.py`` unmodified
     (shapely / dubins / skspatial replaced by inert stubs, ``heapdict`` resolved to
     ``oracle/heapdict_port``) and runs them on the oracle's duck-typed environment, car and
-    heuristic objects; 64 config-5 scenarios (counters 1 .. 401) and 108 sweeps agree bit for
+    heuristic objects; 192 config-5 scenarios (counters 1 .. 401) and 108 sweeps agree bit for
     bit / to 1 ulp (``tests/golden/astar_ref_golden.npz``, ``ypark_golden.npz``,
     ``tests/test_ypark_golden.py::test_live_reference_sweep_and_search_loop``).
   * What sits on shapely/GEOS, heapdict or pydubins in the reference
