@@ -132,11 +132,12 @@ def run_reference(args, rank, world):
     from oracle import baseline as OB
     from headland_trajectory_planning_b200 import scenarios as SC
     cores = os.cpu_count() or 1
-    steps_total = max(1, args.steps + args.warmup)
     # size the per-step sample so that the whole run stays within a few minutes:
     # ~6 s of search per scenario on average, spread over `cores` workers
-    budget_s = 150.0 / steps_total
-    n = args.cpu_sample if args.cpu_sample > 0 else int(max(2, min(64, budget_s * cores / 6.0)))
+    # At least 4 scenarios per core and step: with one scenario per core the wall of every step is the ONE slowest
+    # (401-pop, ~30 s) scenario and the pool idles -- that understated the CPU arm 3.7x in round 1.
+    # (64 scenarios take ~7.5 s on 16 cores, so the driver's 20 + 5 steps stay within ~3 minutes.)
+    n = args.cpu_sample if args.cpu_sample > 0 else int(min(128, max(32, 4 * cores)))
     specs = [SC.scenario_spec(i) for i in range(n)]
     scns = [SC.finalize(sp, OB.candidate_feasibility(sp)) for sp in specs]
     for _ in range(args.warmup):
@@ -149,7 +150,7 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": f"scenarios 0..{n - 1} per step"},
+            "config": {"workload": WORKLOAD, "sample": f"scenarios 0..{n - 1} per step ({n / used:.1f} per core)"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "port",
                              "sample": f"scenarios 0..{n - 1} of the workload, oracle port (shapely/heapdict "
                                        f"unavailable), multiprocessing.Pool({used})"},
@@ -261,11 +262,17 @@ def main():
             if s + 1 < k_steps:
                 pf.submit(recs, host_structs)                               # ... of step s+1, behind step s's search
             d_s = host_scen.to(dev, non_blocking=True)                      # H2D scenario records
-            o = ops.hybrid_astar_batch(envs_e, d_s, params, path_capacity=path_cap, to_host=True)   # search + D2H
-            if world > 1:
-                sweep.gather_results(o["results"], o["expanded"], world, rank)   # NCCL gather to rank 0
+            if world == 1:
+                o = ops.hybrid_astar_batch(envs_e, d_s, params, path_capacity=path_cap, to_host=True)   # search + D2H
+            else:
+                # search; the output stays on the device, goes to rank 0 over NCCL/NVLink and is copied to the host
+                # once, there (records, key sequences AND paths of all ranks), then merged into scenario order
+                o = ops.hybrid_astar_batch(envs_e, d_s, params, path_capacity=path_cap, to_host=False)
+                shards = sweep.gather_sweep(o, world, rank)
+                o = sweep.merge_shards(shards, total, world) if rank == 0 else None
             envs_e.close()
-            nbytes = int(o["results"].nbytes + o["expanded"].nbytes + sum(o[k].nbytes for k in ("x", "y", "yaw", "k", "dir")))
+            if o is not None:
+                nbytes = int(o["results"].nbytes + o["expanded"].nbytes + sum(o[k].nbytes for k in ("x", "y", "yaw", "k", "dir")))
         return nbytes
 
     pf = sweep.UploadPrefetcher()
@@ -278,10 +285,12 @@ def main():
     barrier()
     e2e_wall = time.perf_counter() - t0
     pf.close()
-    t = torch.tensor([e2e_wall], dtype=torch.float64, device=dev)
+    t = torch.tensor([e2e_wall, float(h2d)], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = total * args.steps / float(t.item())
+        dist.all_reduce(t[:1], op=dist.ReduceOp.MAX)
+        dist.all_reduce(t[1:], op=dist.ReduceOp.SUM)
+    e2e_value = total * args.steps / float(t[0].item())
+    h2d = int(t[1].item())                                                  # whole job: every rank uploads its shard
 
     # ---------------- secondary: stand-alone collision kernel (M2) on the canonical scenario
     coll = None
@@ -592,4 +601,12 @@ def ypark_microbench(args, dev, with_cpu):
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except BaseException as exc:                    # torchrun swallows child tracebacks: say which rank died and why
+        if not isinstance(exc, SystemExit) or exc.code not in (0, None):
+            import traceback
+            sys.stderr.write(f"[bench] rank {os.environ.get('RANK', '0')} (local {os.environ.get('LOCAL_RANK', '0')}) failed:\n")
+            traceback.print_exc()
+            sys.stderr.flush()
+        raise

@@ -12,6 +12,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_NAME = "libheadland_b200.so"
 
+ABI_VERSION = 2
 HL_MAX_PRIMS = 16
 HL_CAPSULE_VERTS = 66
 HL_RS_CANDIDATES = 46
@@ -73,8 +74,8 @@ RSWORD_DTYPE = np.dtype([("cand", "<i4"), ("n_seg", "<i4"), ("npts", "<i4"), ("c
 assert SCENARIO_DTYPE.itemsize == 56 and RESULT_DTYPE.itemsize == 80 and RSWORD_DTYPE.itemsize == 112
 
 EXPORTS = [
-    "hl_last_error", "hl_abi_version", "hl_ctx_create", "hl_ctx_destroy", "hl_ctx_sm_count",
-    "hl_env_upload", "hl_env_free", "hl_env_count", "hl_collision_check", "hl_path_reduce",
+    "hl_last_error", "hl_abi_version", "hl_ctx_create", "hl_ctx_destroy", "hl_ctx_sm_count", "hl_ctx_device",
+    "hl_ctx_set_astar_variant", "hl_env_upload", "hl_env_free", "hl_env_count", "hl_env_device", "hl_collision_check", "hl_path_reduce",
     "hl_rs_all_paths", "hl_rs_sample", "hl_hybrid_astar_batch", "hl_hybrid_astar_workspace_bytes", "hl_astar_phase_cycles",
     "hl_distance_field", "hl_grid_pack", "hl_grid_footprint_check", "hl_measure_fp32_peak", "hl_ypark_paths", "hl_arc_paths", "hl_ref_path_count", "hl_ref_path_fill",
 ]
@@ -107,7 +108,7 @@ class _Tolerant:
 
 
 _lib = None
-_lock = threading.Lock()
+_lock = threading.RLock()      # re-entrant: check() -> last_error() -> load_library() under get_ctx's lock
 _ctxs = {}
 
 
@@ -134,6 +135,9 @@ def load_library():
         lib.hl_ctx_destroy.argtypes = [vp]
         lib.hl_ctx_destroy.restype = None
         lib.hl_ctx_sm_count.argtypes = [vp]
+        lib.hl_ctx_device.argtypes = [vp]
+        lib.hl_ctx_set_astar_variant.argtypes = [vp, C.c_int]
+        lib.hl_env_device.argtypes = [vp]
         lib.hl_env_upload.argtypes = [vp, C.POINTER(HlEnvHost), i32, C.POINTER(vp)]
         lib.hl_env_free.argtypes = [vp]
         lib.hl_env_free.restype = None
@@ -156,7 +160,7 @@ def load_library():
         lib.hl_arc_paths.argtypes = [vp, vp, vp, i64, dbl, vp, vp]
         lib.hl_ref_path_count.argtypes = [vp, vp, vp, vp, vp, i64, dbl, vp, vp, vp]
         lib.hl_ref_path_fill.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, dbl, dbl, dbl, vp, vp, vp]
-        if lib.hl_abi_version() != 1:
+        if lib.hl_abi_version() != ABI_VERSION:
             raise HeadlandError("libheadland_b200.so ABI version mismatch")
         _lib = lib
         return lib
@@ -189,11 +193,26 @@ def get_ctx(device=None):
         device = torch.cuda.current_device()
     device = int(device)
     with _lock:
-        if device not in _ctxs:
-            h = C.c_void_p()
-            check(lib.hl_ctx_create(C.byref(h), device), "hl_ctx_create")
+        if device in _ctxs:
+            return _ctxs[device]
+        h = C.c_void_p()
+        rc = lib.hl_ctx_create(C.byref(h), device)
+        msg = lib.hl_last_error().decode("utf-8", "replace") if rc != 0 else ""
+        if rc == 0:
             _ctxs[device] = h
-        return _ctxs[device]
+    if rc != 0:                           # raised outside the lock
+        raise HeadlandError(f"hl_ctx_create: {msg}")
+    return h
+
+
+ASTAR_VARIANTS = {"spec": 0, "warp": 1, "level": 2}
+
+
+def apply_astar_variant(ctx):
+    """A/B switch of the search kernel (``HL_ASTAR_VARIANT`` = spec | warp | level).  The C library reads the
+    variable once, at context creation; the Python binding forwards later changes (the tests flip it per case)."""
+    v = os.environ.get("HL_ASTAR_VARIANT", "spec")
+    check(load_library().hl_ctx_set_astar_variant(ctx, ASTAR_VARIANTS.get(v, 0)), "hl_ctx_set_astar_variant")
 
 
 def ptr(t):

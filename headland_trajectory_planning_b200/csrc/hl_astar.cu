@@ -15,6 +15,7 @@
 // an atomic counter as soon as theirs finishes.
 #include <cstdlib>
 #include <cstdio>
+#include <mutex>
 #include "hl_astar_common.cuh"
 
 #ifndef AW_WARPS
@@ -653,11 +654,10 @@ static void ls_state_free(void* p) {
     delete L;
 }
 
-static int ls_state_get(hl_ctx* ctx, LsState** out) {
-    if (ctx->ls_state) { *out = (LsState*)ctx->ls_state; return 0; }
-    LsState* L = new LsState();
-    memset(L, 0, sizeof(*L));
-    ctx->ls_state = L; ctx->ls_free = ls_state_free;
+// Builds the state into a local object and publishes it in the context only after the graph was instantiated: a
+// failure half-way (allocation, capture, instantiate) ends the capture, frees everything and leaves ctx->ls_state NULL,
+// so the next call starts over instead of launching a half-built graph.
+static int ls_state_build(hl_ctx* ctx, LsState* L, bool* capturing) {
     L->grid = ctx->sm_count * LS_GRID_MULT;
     HL_CUDA_OK(cudaMalloc(&L->d_call, sizeof(LsCall)));
     HL_CUDA_OK(cudaMallocHost(&L->h_call, sizeof(LsCall)));
@@ -669,6 +669,7 @@ static int ls_state_get(hl_ctx* ctx, LsState** out) {
     // LS_CHUNK iterations; the first one reads the list the initial step(0) filled (parity 1)
     const int g = L->grid;
     HL_CUDA_OK(cudaStreamBeginCapture(L->s1, cudaStreamCaptureModeThreadLocal));
+    *capturing = true;
     for (int it = 0; it < LS_CHUNK; ++it) {
         const int parity = (it & 1) ^ 1;
         HL_CUDA_OK(cudaEventRecord(L->ev_fork, L->s1));
@@ -683,8 +684,28 @@ static int ls_state_get(hl_ctx* ctx, LsState** out) {
         HL_CUDA_OK(cudaStreamWaitEvent(L->s1, L->ev_join, 0));
         ls_step<<<g, LS_THREADS, 0, L->s1>>>(L->d_call, parity);
     }
+    *capturing = false;
     HL_CUDA_OK(cudaStreamEndCapture(L->s1, &L->graph));
     HL_CUDA_OK(cudaGraphInstantiate(&L->exec, L->graph, 0));
+    return 0;
+}
+
+static int ls_state_get(hl_ctx* ctx, LsState** out) {
+    if (ctx->ls_state) { *out = (LsState*)ctx->ls_state; return 0; }
+    LsState* L = new LsState();
+    memset(L, 0, sizeof(*L));
+    bool capturing = false;
+    if (ls_state_build(ctx, L, &capturing)) {
+        if (capturing) {                               // leave s1 out of capture mode; the partial graph is dropped
+            cudaGraph_t g = nullptr;
+            cudaStreamEndCapture(L->s1, &g);
+            if (g) cudaGraphDestroy(g);
+            cudaGetLastError();
+        }
+        ls_state_free(L);
+        return 1;
+    }
+    ctx->ls_state = L; ctx->ls_free = ls_state_free;
     *out = L;
     return 0;
 }
@@ -779,7 +800,7 @@ static size_t astar_smem() { return sizeof(AwSmem) * AW_WARPS; }
 
 extern "C" int hl_astar_phase_cycles(hl_ctx* ctx, uint64_t* h_out, int32_t n, int32_t reset) {
     if (!ctx || !h_out || n < 1 || n > AS_N_PHASES) { hl_set_error("hl_astar_phase_cycles: bad arguments"); return 1; }
-    HL_CUDA_OK(cudaSetDevice(ctx->device));
+    if (hl_enter(ctx, nullptr, nullptr, "hl_astar_phase_cycles")) return 1;
     HL_CUDA_OK(cudaMemcpy(h_out, ctx->d_counters + 16, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost));
     if (reset) HL_CUDA_OK(cudaMemset(ctx->d_counters + 16, 0, sizeof(uint64_t) * AS_N_PHASES));
     return 0;
@@ -799,7 +820,7 @@ extern "C" int hl_hybrid_astar_batch(hl_ctx* ctx, const hl_env_batch* envs, cons
                                      double* d_path_k, int8_t* d_path_dir, int64_t path_capacity,
                                      unsigned long long* d_path_cursor, void* stream) {
     if (ctx && n_scen == 0 && d_path_cursor && d_keys_cursor) {          // empty batch: nothing but the cursors is touched
-        HL_CUDA_OK(cudaSetDevice(ctx->device));
+        if (hl_enter(ctx, envs, d_path_cursor, "hl_hybrid_astar_batch")) return 1;
         HL_CUDA_OK(cudaMemsetAsync(d_path_cursor, 0, sizeof(unsigned long long), (cudaStream_t)stream));
         HL_CUDA_OK(cudaMemsetAsync(d_keys_cursor, 0, sizeof(unsigned long long), (cudaStream_t)stream));
         return 0;
@@ -811,15 +832,20 @@ extern "C" int hl_hybrid_astar_batch(hl_ctx* ctx, const hl_env_batch* envs, cons
     if (h_params->n_prims < 1 || h_params->n_prims > HL_MAX_PRIMS || h_params->max_nodes < 0) {
         hl_set_error("hl_hybrid_astar_batch: n_prims/max_nodes out of range"); return 1;
     }
-    HL_CUDA_OK(cudaSetDevice(ctx->device));
+    if (hl_enter(ctx, envs, d_results, "hl_hybrid_astar_batch")) return 1;
     AsParams P;
     fill_params(ctx, h_params, P);
+    // The node/hash workspace, the work-queue counter and the level variant's state are PER CONTEXT: the host part
+    // runs under the context mutex and the launch waits for the previous search of this context (event recorded
+    // below), so searches issued from several threads or streams of one device serialise instead of sharing scratch.
+    std::lock_guard<std::recursive_mutex> lock(*(std::recursive_mutex*)ctx->mu);
     // variant: "spec" = two warps per scenario with the analytic shot decoupled (hl_astar_spec.cuh),
-    // "warp" = one warp per scenario.  HL_ASTAR_VARIANT overrides the default for A/B runs.
-    const char* var = getenv("HL_ASTAR_VARIANT");
-    const bool level = var ? (strcmp(var, "level") == 0) : false;
-    const bool spec = var ? (strcmp(var, "warp") != 0) : true;
+    // "warp" = one warp per scenario, "level" = level-synchronous graph (hl_ctx_set_astar_variant / HL_ASTAR_VARIANT
+    // at context creation; A/B runs only, the results are identical).
+    const bool level = ctx->astar_variant == HL_ASTAR_LEVEL;
+    const bool spec = ctx->astar_variant != HL_ASTAR_WARP;
     cudaStream_t st = (cudaStream_t)stream;
+    HL_CUDA_OK(cudaStreamWaitEvent(st, (cudaEvent_t)ctx->astar_done, 0));      // no-op until the first record
     AwOut O;
     O.results = d_results; O.expanded_keys = d_expanded_keys;
     O.keys_capacity = (long long)keys_capacity; O.keys_cursor = d_keys_cursor;
@@ -829,7 +855,9 @@ extern "C" int hl_hybrid_astar_batch(hl_ctx* ctx, const hl_env_batch* envs, cons
     if (level) {
         HL_CUDA_OK(cudaMemsetAsync(d_path_cursor, 0, sizeof(unsigned long long), st));
         HL_CUDA_OK(cudaMemsetAsync(d_keys_cursor, 0, sizeof(unsigned long long), st));
-        return ls_run(ctx, envs, d_scen, n_scen, P, O, st);
+        const int rc = ls_run(ctx, envs, d_scen, n_scen, P, O, st);
+        if (rc == 0) HL_CUDA_OK(cudaEventRecord((cudaEvent_t)ctx->astar_done, st));
+        return rc;
     }
     const int slots = spec ? AQ_SLOTS : AW_WARPS;
     const int threads = spec ? AQ_SLOTS * AQ_WARPS_PER_SLOT * 32 : AW_WARPS * 32;
@@ -853,7 +881,7 @@ extern "C" int hl_hybrid_astar_batch(hl_ctx* ctx, const hl_env_batch* envs, cons
     const size_t stride = as_ws_bytes(P.cap_nodes, P.hash_size, P.max_nodes);
     const size_t need = stride * (size_t)grid * slots;
     if (need > ctx->astar_ws_bytes) {
-        if (ctx->astar_ws) cudaFree(ctx->astar_ws);
+        if (ctx->astar_ws) cudaFree(ctx->astar_ws);          // synchronises the device: the previous search is done
         ctx->astar_ws = nullptr; ctx->astar_ws_bytes = 0;
         HL_CUDA_OK(cudaMalloc(&ctx->astar_ws, need));
         ctx->astar_ws_bytes = need;
@@ -868,5 +896,6 @@ extern "C" int hl_hybrid_astar_batch(hl_ctx* ctx, const hl_env_batch* envs, cons
         k_hybrid_astar_w<<<grid, threads, smem, st>>>(envs->dev, d_scen, n_scen, P, (char*)ctx->astar_ws, stride,
                                                       ctx->d_counters, O);
     HL_CUDA_OK(cudaGetLastError());
+    HL_CUDA_OK(cudaEventRecord((cudaEvent_t)ctx->astar_done, st));
     return 0;
 }

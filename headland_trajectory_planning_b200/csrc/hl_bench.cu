@@ -19,7 +19,7 @@ __global__ void __launch_bounds__(1024) k_ffma_peak(float* out, int iters, float
 
 extern "C" int hl_measure_fp32_peak(hl_ctx* ctx, double* h_tflops) {
     if (!ctx || !h_tflops) { hl_set_error("hl_measure_fp32_peak: bad arguments"); return 1; }
-    HL_CUDA_OK(cudaSetDevice(ctx->device));
+    if (hl_enter(ctx, nullptr, nullptr, "hl_measure_fp32_peak")) return 1;
     float* d = nullptr;
     HL_CUDA_OK(cudaMalloc(&d, 4));
     cudaEvent_t e0, e1;

@@ -207,7 +207,7 @@ extern "C" int hl_collision_check(hl_ctx* ctx, const hl_env_batch* envs, const i
                                   void* stream) {
     if (!ctx || !envs || !d_poses || !d_out || n < 0) { hl_set_error("hl_collision_check: bad arguments"); return 1; }
     if (n == 0) return 0;
-    HL_CUDA_OK(cudaSetDevice(ctx->device));
+    if (hl_enter(ctx, envs, d_out, "hl_collision_check")) return 1;
     const int smem_bytes = 32 * 1024;
     long long tiles = (n + K1_THREADS - 1) / K1_THREADS;
     int grid = (int)(tiles < (long long)ctx->sm_count * 8 ? tiles : (long long)ctx->sm_count * 8);
@@ -222,7 +222,7 @@ extern "C" int hl_path_reduce(hl_ctx* ctx, const uint8_t* d_pose_bad, const int6
                               int64_t n_paths, uint8_t* d_path_bad, void* stream) {
     if (!ctx || !d_pose_bad || !d_path_start || !d_path_bad || n_paths < 0) { hl_set_error("hl_path_reduce: bad arguments"); return 1; }
     if (n_paths == 0) return 0;
-    HL_CUDA_OK(cudaSetDevice(ctx->device));
+    if (hl_enter(ctx, nullptr, d_path_bad, "hl_path_reduce")) return 1;
     long long threads = n_paths * 32;
     int grid = (int)((threads + 255) / 256);
     k_path_reduce<<<grid, 256, 0, (cudaStream_t)stream>>>(d_pose_bad, (const long long*)d_path_start, n_paths, d_path_bad);

@@ -75,9 +75,19 @@ struct hl_ctx {
     void* mu;                 // std::recursive_mutex*: one upload / cache hand-over at a time (uploads may come from a prefetch thread)
     void* ls_state;           // level-synchronous search: graph, streams, pools (hl_astar.cu)
     void (*ls_free)(void*);
+    int astar_variant;        // HL_ASTAR_SPEC / _WARP / _LEVEL (HL_ASTAR_VARIANT read ONCE at hl_ctx_create; hl_ctx_set_astar_variant)
+    void* astar_done;         // cudaEvent_t recorded after the last search launch: the workspace / work counter are
+                              // per context, so a search on another stream waits for it (searches serialise per ctx)
 };
+#define HL_ASTAR_SPEC 0
+#define HL_ASTAR_WARP 1
+#define HL_ASTAR_LEVEL 2
 
 void hl_set_error(const char* fmt, ...);
+// Every entry point calls this first: selects the context's device and rejects an environment batch or a
+// device pointer that lives on ANOTHER device (or is not device memory at all) with an hl_last_error text
+// instead of launching on the wrong GPU.  `probe` may be NULL.
+int hl_enter(const hl_ctx* ctx, const hl_env_batch* envs, const void* probe, const char* what);
 #define HL_CUDA_OK(call)                                                            \
     do {                                                                            \
         cudaError_t _e = (call);                                                    \

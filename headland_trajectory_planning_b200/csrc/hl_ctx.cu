@@ -34,7 +34,7 @@ extern "C" int hl_ctx_create(hl_ctx** out, int device) {
     HL_CUDA_OK(cudaSetDevice(device));
     cudaDeviceProp prop;
     HL_CUDA_OK(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10) {
+    if (prop.major != 10) {                 // only sm_100a SASS is in the library (no PTX): sm_12x has no kernel image either
         hl_set_error("hl_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only",
                      device, prop.major, prop.minor);
         return 1;
@@ -58,13 +58,61 @@ extern "C" int hl_ctx_create(hl_ctx** out, int device) {
         cudaStream_t cs = nullptr;
         if (cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) == cudaSuccess) c->copy_stream = cs;
     }
-    if (cudaMalloc(&c->d_counters, 256 * sizeof(unsigned int)) != cudaSuccess) {
-        hl_set_error("hl_ctx_create: cudaMalloc failed");
+    c->astar_variant = HL_ASTAR_SPEC;
+    if (const char* var = getenv("HL_ASTAR_VARIANT")) {       // read once; hl_ctx_set_astar_variant changes it later
+        if (strcmp(var, "warp") == 0) c->astar_variant = HL_ASTAR_WARP;
+        else if (strcmp(var, "level") == 0) c->astar_variant = HL_ASTAR_LEVEL;
+    }
+    c->astar_done = nullptr;
+    {
+        cudaEvent_t ev = nullptr;
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess) c->astar_done = ev;
+    }
+    if (!c->astar_done || cudaMalloc(&c->d_counters, 256 * sizeof(unsigned int)) != cudaSuccess) {
+        hl_set_error("hl_ctx_create: cudaMalloc / cudaEventCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
+        if (c->astar_done) cudaEventDestroy((cudaEvent_t)c->astar_done);
+        if (c->copy_stream) cudaStreamDestroy((cudaStream_t)c->copy_stream);
+        delete (std::recursive_mutex*)c->mu;
         delete c;
         return 1;
     }
     cudaMemset(c->d_counters, 0, 256 * sizeof(unsigned int));
     *out = c;
+    return 0;
+}
+
+extern "C" int hl_ctx_device(const hl_ctx* ctx) { return ctx ? ctx->device : -1; }
+extern "C" int hl_env_device(const hl_env_batch* envs) { return envs ? envs->device : -1; }
+
+extern "C" int hl_ctx_set_astar_variant(hl_ctx* ctx, int variant) {
+    if (!ctx || variant < HL_ASTAR_SPEC || variant > HL_ASTAR_LEVEL) { hl_set_error("hl_ctx_set_astar_variant: bad arguments"); return 1; }
+    std::lock_guard<std::recursive_mutex> lock(*(std::recursive_mutex*)ctx->mu);
+    ctx->astar_variant = variant;
+    return 0;
+}
+
+int hl_enter(const hl_ctx* ctx, const hl_env_batch* envs, const void* probe, const char* what) {
+    if (!ctx) { hl_set_error("%s: ctx is NULL", what); return 1; }
+    if (envs && envs->device != ctx->device) {
+        hl_set_error("%s: the environment batch lives on device %d but the context is for device %d "
+                     "(upload it through the context of the device that runs the kernels)", what, envs->device, ctx->device);
+        return 1;
+    }
+    if (envs && envs->owner != ctx) { hl_set_error("%s: the environment batch belongs to another context", what); return 1; }
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) { hl_set_error("%s: cudaSetDevice(%d) failed: %s", what, ctx->device, cudaGetErrorString(e)); return 1; }
+    if (probe) {
+        cudaPointerAttributes a;
+        e = cudaPointerGetAttributes(&a, probe);
+        if (e != cudaSuccess) { cudaGetLastError(); hl_set_error("%s: cudaPointerGetAttributes failed: %s", what, cudaGetErrorString(e)); return 1; }
+        if (a.type != cudaMemoryTypeDevice && a.type != cudaMemoryTypeManaged) {
+            hl_set_error("%s: a d_* argument is not device memory (host pointer passed?)", what); return 1;
+        }
+        if (a.type == cudaMemoryTypeDevice && a.device != ctx->device) {
+            hl_set_error("%s: a d_* argument lives on device %d but the context is for device %d", what, a.device, ctx->device);
+            return 1;
+        }
+    }
     return 0;
 }
 
@@ -77,6 +125,7 @@ extern "C" void hl_ctx_destroy(hl_ctx* ctx) {
     for (int k = 0; k < 2; ++k) if (ctx->env_cache[k]) cudaFree(ctx->env_cache[k]);
     if (ctx->ls_state && ctx->ls_free) ctx->ls_free(ctx->ls_state);
     if (ctx->copy_stream) cudaStreamDestroy((cudaStream_t)ctx->copy_stream);
+    if (ctx->astar_done) cudaEventDestroy((cudaEvent_t)ctx->astar_done);
     delete (std::recursive_mutex*)ctx->mu;
     delete ctx;
 }
@@ -112,19 +161,144 @@ extern "C" void hl_env_free(hl_env_batch* envs) {
 
 extern "C" int32_t hl_env_count(const hl_env_batch* envs) { return envs ? envs->dev.n_env : 0; }
 
-// One device block + one pinned staging block per upload: sizes are computed in a first pass, the second
-// pass writes every pool straight into the (context-cached, grow-only) pinned buffer, and ONE
-// cudaMemcpyAsync moves it.  (The first version used 15 std::vectors with push_back and 15 pageable
-// copies: 37 ms for 4096 environments, as long as the search itself.)
+// One device block + one pinned staging block per upload.  The host only lays the caller's float64 arrays end to
+// end in the (context-cached, grow-only) pinned buffer -- memcpy, no arithmetic -- and ONE cudaMemcpyAsync moves them;
+// everything DERIVED (float32 frame origin, filter band, float32 obstacle / field-edge / lane records, the SoA
+// transposition of the guide polyline) is computed on the device by k_env_derive, one CTA per environment.
+// History: 15 std::vectors + 15 pageable copies 37 ms per 4096 environments; host-side derivation into one pinned
+// block 3.5 ms on 8 threads (but 8 ranks share the host cores of a box); device-side derivation: see DESIGN.md.
+enum { P_DESC = 0, P_OBS64, P_FIELD64, P_SEG64, P_SEGLEN, P_SEGPOLY, P_CRIT64, P_AUX64, P_GUIDE_AOS,   // host-filled
+       P_OBS32, P_FIELD32, P_SEG32, P_GX, P_GY, P_GYAW, P_GS, P_COUNT };                               // device-derived
+#define P_HOST_POOLS P_OBS32
 struct PoolLayout {
-    size_t off[15];
+    size_t off[P_COUNT];
+    size_t host_bytes;      // the first P_HOST_POOLS pools, copied from the staging block
     size_t total;
 };
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+struct EnvDerive {
+    EnvDesc* desc;
+    const double* obs64; const double* field64; const double* seg64; const double* aux64; const double* guide_aos;
+    float* obs32; float* field32; float* seg32;
+    double* gx; double* gy; double* gyaw; double* gs;
+};
+
+// float64 in the host's operation order (one rounding per operation, no FMA contraction): the records are bit for
+// bit the ones the round-1 host code produced.
+__global__ void __launch_bounds__(128) k_env_derive(EnvDerive A, int n_env) {
+    const int e = blockIdx.x;
+    if (e >= n_env) return;
+    EnvDesc& D = A.desc[e];
+    const int t = threadIdx.x, nt = blockDim.x;
+    __shared__ double s_lo[2][128], s_hi[2][128];
+    __shared__ double s_origin[2], s_orient;
+    __shared__ int s_all_rect;
+    const double* obs = A.obs64 + 8 * (size_t)D.obs_off;
+    const double* fld = A.field64 + 2 * (size_t)D.field_off;
+    const double* seg = A.seg64 + 4 * (size_t)D.seg_off;
+    double lo[2] = {1e300, 1e300}, hi[2] = {-1e300, -1e300};
+    for (int i = t; i < 4 * D.n_obs; i += nt)
+        for (int c = 0; c < 2; ++c) { lo[c] = fmin(lo[c], obs[2 * i + c]); hi[c] = fmax(hi[c], obs[2 * i + c]); }
+    for (int i = t; i < D.n_field; i += nt)
+        for (int c = 0; c < 2; ++c) { lo[c] = fmin(lo[c], fld[2 * i + c]); hi[c] = fmax(hi[c], fld[2 * i + c]); }
+    for (int i = t; i < 2 * D.n_seg; i += nt)
+        for (int c = 0; c < 2; ++c) { lo[c] = fmin(lo[c], seg[2 * i + c]); hi[c] = fmax(hi[c], seg[2 * i + c]); }
+    for (int c = 0; c < 2; ++c) { s_lo[c][t] = lo[c]; s_hi[c][t] = hi[c]; }
+    if (t == 0) s_all_rect = 1;
+    __syncthreads();
+    for (int w = nt / 2; w > 0; w >>= 1) {
+        if (t < w)
+            for (int c = 0; c < 2; ++c) { s_lo[c][t] = fmin(s_lo[c][t], s_lo[c][t + w]); s_hi[c][t] = fmax(s_hi[c][t], s_hi[c][t + w]); }
+        __syncthreads();
+    }
+    if (t == 0) {
+        double l0 = s_lo[0][0], l1 = s_lo[1][0], h0 = s_hi[0][0], h1 = s_hi[1][0];
+        if (l0 > h0) { l0 = l1 = h0 = h1 = 0.0; }
+        const double ox = xmul(0.5, xadd(l0, h0)), oy = xmul(0.5, xadd(l1, h1));
+        s_origin[0] = ox; s_origin[1] = oy;
+        D.origin[0] = ox; D.origin[1] = oy;
+        // origin of the float32 frame = centre of the bounding box of all geometry; band scaled to the extent
+        const double extent = xmul(xmul(0.5, fmax(xsub(h0, l0), xsub(h1, l1))), 1.4142135623730951);
+        double foot = hypot_cr(fmax(fabs(D.body_ext[0]), fabs(D.body_ext[1])), fmax(fabs(D.body_ext[2]), fabs(D.body_ext[3])));
+        for (int a = 0; a < D.n_aux; ++a) {
+            const double* x = A.aux64 + 4 * (size_t)(D.aux_off + a);
+            foot = fmax(foot, hypot_cr(fmax(fabs(x[0]), fabs(x[1])), fmax(fabs(x[2]), fabs(x[3]))));
+        }
+        const double reach = xadd(xadd(xadd(extent, 6.0), foot), 4.0);     // lane radius 6 m (reference_line_heuristic.py:66) + margin
+        D.reach = (float)reach;
+        D.eps = (float)xmul(xmul(32.0, 1.1920929e-07), fmax(reach, 8.0));
+        double area2 = 0.0;
+        for (int i = 0; i < D.n_field; ++i) {
+            const int j = (i + 1 == D.n_field) ? 0 : i + 1;
+            area2 = xadd(area2, xsub(xmul(fld[2 * i], fld[2 * j + 1]), xmul(fld[2 * j], fld[2 * i + 1])));
+        }
+        s_orient = area2 < 0 ? -1.0 : 1.0;
+    }
+    __syncthreads();
+    const double ox = s_origin[0], oy = s_origin[1];
+    for (int k = t; k < D.n_obs; k += nt) {
+        const double* V = obs + 8 * k;
+        float* o = A.obs32 + HL_OBS32_STRIDE * (size_t)(D.obs_off + k);
+        for (int i = 0; i < 4; ++i) {
+            o[2 * i] = (float)xsub(V[2 * i], ox);
+            o[2 * i + 1] = (float)xsub(V[2 * i + 1], oy);
+        }
+        for (int i = 0; i < 4; ++i) {
+            const int j = (i + 1) & 3;
+            const double ex = xsub(V[2 * j], V[2 * i]), ey = xsub(V[2 * j + 1], V[2 * i + 1]);
+            const double ln = sqrt(xadd(xmul(ex, ex), xmul(ey, ey)));
+            const double nx = ln > 0 ? xdiv(ey, ln) : 0.0, ny = ln > 0 ? xdiv(-ex, ln) : 0.0;
+            const double cc = xadd(xmul(nx, xsub(V[2 * i], ox)), xmul(ny, xsub(V[2 * i + 1], oy)));
+            o[8 + 3 * i] = (float)nx; o[9 + 3 * i] = (float)ny; o[10 + 3 * i] = (float)cc;
+        }
+        // box form when the quad is a rectangle (tree rows, obstacle squares): centre, unit axis, half extents
+        const double e0x = xsub(V[2], V[0]), e0y = xsub(V[3], V[1]), e1x = xsub(V[4], V[2]), e1y = xsub(V[5], V[3]);
+        const double e2x = xsub(V[6], V[4]), e2y = xsub(V[7], V[5]), e3x = xsub(V[0], V[6]), e3y = xsub(V[1], V[7]);
+        const double l0 = sqrt(xadd(xmul(e0x, e0x), xmul(e0y, e0y))), l1 = sqrt(xadd(xmul(e1x, e1x), xmul(e1y, e1y)));
+        const double scale = fmax(l0, l1);
+        const bool para = xadd(xadd(xadd(fabs(xadd(e0x, e2x)), fabs(xadd(e0y, e2y))), fabs(xadd(e1x, e3x))), fabs(xadd(e1y, e3y))) <= xmul(1e-9, scale);
+        const bool perp = l0 > 0 && l1 > 0 && fabs(xadd(xmul(e0x, e1x), xmul(e0y, e1y))) <= xmul(xmul(1e-9, l0), l1);
+        const bool is_rect = para && perp;
+        if (!is_rect) s_all_rect = 0;
+        o[20] = is_rect ? 1.0f : 0.0f;
+        o[21] = (float)xsub(xmul(0.25, xadd(xadd(xadd(V[0], V[2]), V[4]), V[6])), ox);
+        o[22] = (float)xsub(xmul(0.25, xadd(xadd(xadd(V[1], V[3]), V[5]), V[7])), oy);
+        o[23] = (float)(is_rect ? xdiv(e0x, l0) : 1.0); o[24] = (float)(is_rect ? xdiv(e0y, l0) : 0.0);
+        o[25] = (float)xmul(0.5, l0); o[26] = (float)xmul(0.5, l1); o[27] = 0.0f;
+    }
+    {
+        const double orient = s_orient;
+        for (int i = t; i < D.n_field; i += nt) {
+            const int j = (i + 1 == D.n_field) ? 0 : i + 1;
+            const double Ax = xsub(fld[2 * i], ox), Ay = xsub(fld[2 * i + 1], oy);
+            const double Bx = xsub(fld[2 * j], ox), By = xsub(fld[2 * j + 1], oy);
+            const double ex = xsub(Bx, Ax), ey = xsub(By, Ay), ln = sqrt(xadd(xmul(ex, ex), xmul(ey, ey)));
+            const double nx = ln > 0 ? xdiv(xmul(orient, ey), ln) : 0.0, ny = ln > 0 ? xdiv(xmul(-orient, ex), ln) : 0.0;
+            float* f = A.field32 + HL_FIELD32_STRIDE * (size_t)(D.field_off + i);
+            f[0] = (float)Ax; f[1] = (float)Ay; f[2] = (float)xsub(Bx, Ax); f[3] = (float)xsub(By, Ay);
+            f[4] = (float)nx; f[5] = (float)ny; f[6] = (float)xadd(xmul(nx, Ax), xmul(ny, Ay));
+            f[7] = (float)By;                                   // == the next record's (float)Ay, bit for bit
+            f[8] = (float)xadd(xmul(-ny, Ax), xmul(nx, Ay)); f[9] = (float)xadd(xmul(-ny, Bx), xmul(nx, By));
+            f[10] = 0.0f; f[11] = 0.0f;
+        }
+    }
+    for (int i = t; i < 4 * D.n_seg; i += nt)
+        A.seg32[4 * (size_t)D.seg_off + i] = (float)xsub(seg[i], (i & 1) ? oy : ox);
+    {
+        const double* g = A.guide_aos + 4 * (size_t)D.guide_off;
+        const size_t go = (size_t)D.guide_off;
+        for (int i = t; i < D.n_guide; i += nt) {
+            A.gx[go + i] = g[4 * i]; A.gy[go + i] = g[4 * i + 1]; A.gyaw[go + i] = g[4 * i + 2]; A.gs[go + i] = g[4 * i + 3];
+        }
+    }
+    __syncthreads();
+    if (t == 0) { D.all_rect = s_all_rect; D.pad0 = 0; }
+}
+
 extern "C" int hl_env_upload(hl_ctx* ctx, const HlEnvHost* h, int32_t n_env, hl_env_batch** out) {
     if (!ctx || !h || !out || n_env <= 0) { hl_set_error("hl_env_upload: bad arguments"); return 1; }
-    HL_CUDA_OK(cudaSetDevice(ctx->device));
+    if (hl_enter(ctx, nullptr, nullptr, "hl_env_upload")) return 1;
     std::lock_guard<std::recursive_mutex> lock(*(std::recursive_mutex*)ctx->mu);      // the staging buffer and the block cache are shared
     size_t n_obs = 0, n_field = 0, n_seg = 0, n_crit = 0, n_guide = 0, n_aux = 0;
     std::vector<size_t> offs(6 * (size_t)n_env);
@@ -138,33 +312,35 @@ extern "C" int hl_env_upload(hl_ctx* ctx, const HlEnvHost* h, int32_t n_env, hl_
         }
         n_obs += E.n_obs; n_field += E.n_field; n_seg += E.n_seg; n_crit += E.n_crit; n_guide += E.n_guide; n_aux += E.n_aux;
     }
-    const size_t bytes[15] = {
-        sizeof(EnvDesc) * (size_t)n_env,
-        sizeof(float) * HL_OBS32_STRIDE * n_obs, sizeof(double) * 8 * n_obs,
-        sizeof(float) * HL_FIELD32_STRIDE * n_field, sizeof(double) * 2 * n_field,
-        sizeof(float) * 4 * n_seg, sizeof(double) * 4 * n_seg, sizeof(double) * n_seg,
-        sizeof(double) * 2 * HL_CAPSULE_VERTS * n_seg, sizeof(double) * 2 * n_crit,
-        sizeof(double) * n_guide, sizeof(double) * n_guide, sizeof(double) * n_guide, sizeof(double) * n_guide,
-        sizeof(double) * 4 * n_aux};
+    size_t bytes[P_COUNT];
+    bytes[P_DESC] = sizeof(EnvDesc) * (size_t)n_env;
+    bytes[P_OBS64] = sizeof(double) * 8 * n_obs;       bytes[P_FIELD64] = sizeof(double) * 2 * n_field;
+    bytes[P_SEG64] = sizeof(double) * 4 * n_seg;       bytes[P_SEGLEN] = sizeof(double) * n_seg;
+    bytes[P_SEGPOLY] = sizeof(double) * 2 * HL_CAPSULE_VERTS * n_seg;
+    bytes[P_CRIT64] = sizeof(double) * 2 * n_crit;     bytes[P_AUX64] = sizeof(double) * 4 * n_aux;
+    bytes[P_GUIDE_AOS] = sizeof(double) * 4 * n_guide;
+    bytes[P_OBS32] = sizeof(float) * HL_OBS32_STRIDE * n_obs;
+    bytes[P_FIELD32] = sizeof(float) * HL_FIELD32_STRIDE * n_field;
+    bytes[P_SEG32] = sizeof(float) * 4 * n_seg;
+    bytes[P_GX] = bytes[P_GY] = bytes[P_GYAW] = bytes[P_GS] = sizeof(double) * n_guide;
     PoolLayout L;
     L.total = 0;
-    for (int k = 0; k < 15; ++k) { L.off[k] = L.total; L.total += al256(bytes[k] ? bytes[k] : 1); }
-    if (L.total > ctx->stage_bytes) {
+    for (int k = 0; k < P_COUNT; ++k) {
+        if (k == P_HOST_POOLS) L.host_bytes = L.total;
+        L.off[k] = L.total; L.total += al256(bytes[k] ? bytes[k] : 1);
+    }
+    if (L.host_bytes > ctx->stage_bytes) {
         if (ctx->stage) cudaFreeHost(ctx->stage);
         ctx->stage = nullptr; ctx->stage_bytes = 0;
-        HL_CUDA_OK(cudaMallocHost(&ctx->stage, L.total));
-        ctx->stage_bytes = L.total;
+        HL_CUDA_OK(cudaMallocHost(&ctx->stage, L.host_bytes));
+        ctx->stage_bytes = L.host_bytes;
     }
     char* S = (char*)ctx->stage;
-    EnvDesc* desc = (EnvDesc*)(S + L.off[0]);
-    float* obs32 = (float*)(S + L.off[1]);   double* obs64 = (double*)(S + L.off[2]);
-    float* field32 = (float*)(S + L.off[3]); double* field64 = (double*)(S + L.off[4]);
-    float* seg32 = (float*)(S + L.off[5]);   double* seg64 = (double*)(S + L.off[6]);
-    double* seg_len = (double*)(S + L.off[7]); double* seg_poly = (double*)(S + L.off[8]);
-    double* crit64 = (double*)(S + L.off[9]);
-    double* gx = (double*)(S + L.off[10]); double* gy = (double*)(S + L.off[11]);
-    double* gyaw = (double*)(S + L.off[12]); double* gs = (double*)(S + L.off[13]);
-    double* aux64 = (double*)(S + L.off[14]);
+    EnvDesc* desc = (EnvDesc*)(S + L.off[P_DESC]);
+    double* obs64 = (double*)(S + L.off[P_OBS64]);     double* field64 = (double*)(S + L.off[P_FIELD64]);
+    double* seg64 = (double*)(S + L.off[P_SEG64]);     double* seg_len = (double*)(S + L.off[P_SEGLEN]);
+    double* seg_poly = (double*)(S + L.off[P_SEGPOLY]); double* crit64 = (double*)(S + L.off[P_CRIT64]);
+    double* aux64 = (double*)(S + L.off[P_AUX64]);     double* guide = (double*)(S + L.off[P_GUIDE_AOS]);
     auto fill = [&](int e_lo, int e_hi) {
     for (int e = e_lo; e < e_hi; ++e) {
         const HlEnvHost& E = h[e];
@@ -179,92 +355,16 @@ extern "C" int hl_env_upload(hl_ctx* ctx, const HlEnvHost* h, int32_t n_env, hl_
         D.n_aux = E.n_aux;     D.aux_off = (int)c_aux;
         D.default_len = E.default_search_length;
         for (int k = 0; k < 4; ++k) D.body_ext[k] = E.body_ext[k];
-        // origin of the float32 frame: centre of the bounding box of all geometry
-        double lo[2] = {1e300, 1e300}, hi[2] = {-1e300, -1e300};
-        auto acc = [&](const double* p, int npts) {
-            for (int i = 0; i < npts; ++i)
-                for (int c = 0; c < 2; ++c) { lo[c] = fmin(lo[c], p[2 * i + c]); hi[c] = fmax(hi[c], p[2 * i + c]); }
-        };
-        acc(E.obs_xy, 4 * E.n_obs);
-        acc(E.field_xy, E.n_field);
-        acc(E.seg_xy, 2 * E.n_seg);
-        if (lo[0] > hi[0]) { lo[0] = lo[1] = hi[0] = hi[1] = 0.0; }
-        D.origin[0] = 0.5 * (lo[0] + hi[0]);
-        D.origin[1] = 0.5 * (lo[1] + hi[1]);
-        double extent = 0.5 * fmax(hi[0] - lo[0], hi[1] - lo[1]) * 1.4142135623730951;
-        double foot = hypot(fmax(fabs(E.body_ext[0]), fabs(E.body_ext[1])), fmax(fabs(E.body_ext[2]), fabs(E.body_ext[3])));
-        for (int a = 0; a < E.n_aux; ++a) {
-            const double* x = E.aux_ext + 4 * a;
-            foot = fmax(foot, hypot(fmax(fabs(x[0]), fabs(x[1])), fmax(fabs(x[2]), fabs(x[3]))));
-        }
-        double reach = extent + 6.0 + foot + 4.0;            // lane radius 6 m (reference_line_heuristic.py:66) + margin
-        D.reach = (float)reach;
-        D.eps = (float)(32.0 * 1.1920929e-07 * fmax(reach, 8.0));
-        D.all_rect = 1; D.pad0 = 0;
+        D.origin[0] = D.origin[1] = 0.0; D.reach = 0.f; D.eps = 0.f; D.all_rect = 1; D.pad0 = 0;   // k_env_derive fills these
         if (E.n_obs) memcpy(obs64 + 8 * c_obs, E.obs_xy, sizeof(double) * 8 * E.n_obs);
-        for (int k = 0; k < E.n_obs; ++k) {
-            const double* V = E.obs_xy + 8 * k;
-            float* o = obs32 + HL_OBS32_STRIDE * (c_obs + k);
-            for (int i = 0; i < 4; ++i) {
-                o[2 * i] = (float)(V[2 * i] - D.origin[0]);
-                o[2 * i + 1] = (float)(V[2 * i + 1] - D.origin[1]);
-            }
-            for (int i = 0; i < 4; ++i) {
-                int j = (i + 1) & 3;
-                double ex = V[2 * j] - V[2 * i], ey = V[2 * j + 1] - V[2 * i + 1];
-                double ln = sqrt(ex * ex + ey * ey);
-                double nx = ln > 0 ? ey / ln : 0.0, ny = ln > 0 ? -ex / ln : 0.0;
-                double cc = nx * (V[2 * i] - D.origin[0]) + ny * (V[2 * i + 1] - D.origin[1]);
-                o[8 + 3 * i] = (float)nx; o[9 + 3 * i] = (float)ny; o[10 + 3 * i] = (float)cc;
-            }
-            // box form when the quad is a rectangle (tree rows, obstacle squares): centre, unit axis, half extents
-            double e0x = V[2] - V[0], e0y = V[3] - V[1], e1x = V[4] - V[2], e1y = V[5] - V[3];
-            double e2x = V[6] - V[4], e2y = V[7] - V[5], e3x = V[0] - V[6], e3y = V[1] - V[7];
-            double l0 = sqrt(e0x * e0x + e0y * e0y), l1 = sqrt(e1x * e1x + e1y * e1y);
-            double scale = fmax(l0, l1);
-            bool para = fabs(e0x + e2x) + fabs(e0y + e2y) + fabs(e1x + e3x) + fabs(e1y + e3y) <= 1e-9 * scale;
-            bool perp = l0 > 0 && l1 > 0 && fabs(e0x * e1x + e0y * e1y) <= 1e-9 * l0 * l1;
-            bool is_rect = para && perp;
-            if (!is_rect) D.all_rect = 0;
-            o[20] = is_rect ? 1.0f : 0.0f;
-            o[21] = (float)(0.25 * (V[0] + V[2] + V[4] + V[6]) - D.origin[0]);
-            o[22] = (float)(0.25 * (V[1] + V[3] + V[5] + V[7]) - D.origin[1]);
-            o[23] = (float)(is_rect ? e0x / l0 : 1.0); o[24] = (float)(is_rect ? e0y / l0 : 0.0);
-            o[25] = (float)(0.5 * l0); o[26] = (float)(0.5 * l1); o[27] = 0.0f;
-        }
         if (E.n_field) memcpy(field64 + 2 * c_field, E.field_xy, sizeof(double) * 2 * E.n_field);
-        {
-            double area2 = 0.0;
-            for (int i = 0; i < E.n_field; ++i) {
-                int j = (i + 1 == E.n_field) ? 0 : i + 1;
-                area2 += E.field_xy[2 * i] * E.field_xy[2 * j + 1] - E.field_xy[2 * j] * E.field_xy[2 * i + 1];
-            }
-            const double orient = area2 < 0 ? -1.0 : 1.0;
-            for (int i = 0; i < E.n_field; ++i) {
-                int j = (i + 1 == E.n_field) ? 0 : i + 1;
-                double Ax = E.field_xy[2 * i] - D.origin[0], Ay = E.field_xy[2 * i + 1] - D.origin[1];
-                double Bx = E.field_xy[2 * j] - D.origin[0], By = E.field_xy[2 * j + 1] - D.origin[1];
-                double ex = Bx - Ax, ey = By - Ay, ln = sqrt(ex * ex + ey * ey);
-                double nx = ln > 0 ? orient * ey / ln : 0.0, ny = ln > 0 ? -orient * ex / ln : 0.0;
-                float* f = field32 + HL_FIELD32_STRIDE * (c_field + i);
-                f[0] = (float)Ax; f[1] = (float)Ay; f[2] = (float)(Bx - Ax); f[3] = (float)(By - Ay);
-                f[4] = (float)nx; f[5] = (float)ny; f[6] = (float)(nx * Ax + ny * Ay);
-                f[7] = (float)By;                                   // == the next record's (float)Ay, bit for bit
-                f[8] = (float)(-ny * Ax + nx * Ay); f[9] = (float)(-ny * Bx + nx * By);
-                f[10] = 0.0f; f[11] = 0.0f;
-            }
-        }
         if (E.n_seg) {
             memcpy(seg64 + 4 * c_seg, E.seg_xy, sizeof(double) * 4 * E.n_seg);
             memcpy(seg_len + c_seg, E.seg_len, sizeof(double) * E.n_seg);
             memcpy(seg_poly + 2 * HL_CAPSULE_VERTS * c_seg, E.seg_poly, sizeof(double) * 2 * HL_CAPSULE_VERTS * E.n_seg);
-            for (int i = 0; i < 4 * E.n_seg; ++i) seg32[4 * c_seg + i] = (float)(E.seg_xy[i] - D.origin[i & 1]);
         }
         if (E.n_crit) memcpy(crit64 + 2 * c_crit, E.crit_xy, sizeof(double) * 2 * E.n_crit);
-        for (int i = 0; i < E.n_guide; ++i) {
-            gx[c_guide + i] = E.guide[4 * i]; gy[c_guide + i] = E.guide[4 * i + 1];
-            gyaw[c_guide + i] = E.guide[4 * i + 2]; gs[c_guide + i] = E.guide[4 * i + 3];
-        }
+        if (E.n_guide) memcpy(guide + 4 * c_guide, E.guide, sizeof(double) * 4 * E.n_guide);
         if (E.n_aux) memcpy(aux64 + 4 * c_aux, E.aux_ext, sizeof(double) * 4 * E.n_aux);
     }
     };
@@ -274,8 +374,8 @@ extern "C" int hl_env_upload(hl_ctx* ctx, const HlEnvHost* h, int32_t n_env, hl_
         const char* lws = getenv("LOCAL_WORLD_SIZE");
         const int ranks = lws ? atoi(lws) : 1;
         if (ranks > 1) nt /= ranks;
-        nt = nt < 1 ? 1 : (nt > 8 ? 8 : nt);
-        if (n_env < 256) nt = 1;
+        nt = nt < 1 ? 1 : (nt > 4 ? 4 : nt);
+        if (n_env < 1024) nt = 1;
         std::vector<std::thread> th;
         for (int t = 1; t < nt; ++t) th.emplace_back(fill, (int)((long long)n_env * t / nt), (int)((long long)n_env * (t + 1) / nt));
         fill(0, (int)((long long)n_env / nt));
@@ -298,18 +398,30 @@ extern "C" int hl_env_upload(hl_ctx* ctx, const HlEnvHost* h, int32_t n_env, hl_
     } else if (cudaMalloc(&d, L.total) != cudaSuccess) { delete b; hl_set_error("hl_env_upload: cudaMalloc(%zu) failed", L.total); return 1; }
     b->allocs[b->n_allocs++] = d;
     cudaStream_t cs = (cudaStream_t)ctx->copy_stream;       // nullptr = legacy default stream
-    if (cudaMemcpyAsync(d, S, L.total, cudaMemcpyHostToDevice, cs) != cudaSuccess || cudaStreamSynchronize(cs) != cudaSuccess) {
-        hl_env_free(b); hl_set_error("hl_env_upload: copy failed"); return 1;
+    EnvDerive A;
+    A.desc = (EnvDesc*)(d + L.off[P_DESC]);
+    A.obs64 = (const double*)(d + L.off[P_OBS64]);     A.field64 = (const double*)(d + L.off[P_FIELD64]);
+    A.seg64 = (const double*)(d + L.off[P_SEG64]);     A.aux64 = (const double*)(d + L.off[P_AUX64]);
+    A.guide_aos = (const double*)(d + L.off[P_GUIDE_AOS]);
+    A.obs32 = (float*)(d + L.off[P_OBS32]); A.field32 = (float*)(d + L.off[P_FIELD32]); A.seg32 = (float*)(d + L.off[P_SEG32]);
+    A.gx = (double*)(d + L.off[P_GX]); A.gy = (double*)(d + L.off[P_GY]); A.gyaw = (double*)(d + L.off[P_GYAW]); A.gs = (double*)(d + L.off[P_GS]);
+    cudaError_t ce = cudaMemcpyAsync(d, S, L.host_bytes, cudaMemcpyHostToDevice, cs);
+    if (ce == cudaSuccess) {
+        k_env_derive<<<n_env, 128, 0, cs>>>(A, n_env);
+        ce = cudaGetLastError();
     }
-    b->dev.desc = (const EnvDesc*)(d + L.off[0]);
-    b->dev.obs32 = (const float*)(d + L.off[1]);   b->dev.obs64 = (const double*)(d + L.off[2]);
-    b->dev.field32 = (const float*)(d + L.off[3]); b->dev.field64 = (const double*)(d + L.off[4]);
-    b->dev.seg32 = (const float*)(d + L.off[5]);   b->dev.seg64 = (const double*)(d + L.off[6]);
-    b->dev.seg_len = (const double*)(d + L.off[7]); b->dev.seg_poly = (const double*)(d + L.off[8]);
-    b->dev.crit64 = (const double*)(d + L.off[9]);
-    b->dev.guide_x = (const double*)(d + L.off[10]); b->dev.guide_y = (const double*)(d + L.off[11]);
-    b->dev.guide_yaw = (const double*)(d + L.off[12]); b->dev.guide_s = (const double*)(d + L.off[13]);
-    b->dev.aux64 = (const double*)(d + L.off[14]);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(cs);
+    if (ce != cudaSuccess) {
+        hl_env_free(b); hl_set_error("hl_env_upload: copy / k_env_derive failed: %s", cudaGetErrorString(ce)); return 1;
+    }
+    b->dev.desc = A.desc;
+    b->dev.obs32 = A.obs32;     b->dev.obs64 = A.obs64;
+    b->dev.field32 = A.field32; b->dev.field64 = A.field64;
+    b->dev.seg32 = A.seg32;     b->dev.seg64 = A.seg64;
+    b->dev.seg_len = (const double*)(d + L.off[P_SEGLEN]); b->dev.seg_poly = (const double*)(d + L.off[P_SEGPOLY]);
+    b->dev.crit64 = (const double*)(d + L.off[P_CRIT64]);
+    b->dev.guide_x = A.gx; b->dev.guide_y = A.gy; b->dev.guide_yaw = A.gyaw; b->dev.guide_s = A.gs;
+    b->dev.aux64 = A.aux64;
     *out = b;
     return 0;
 }

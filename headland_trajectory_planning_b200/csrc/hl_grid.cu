@@ -124,7 +124,7 @@ extern "C" int hl_distance_field(hl_ctx* ctx, const uint8_t* d_occ, int32_t w, i
         hl_set_error("hl_distance_field: goal (%d,%d) must be strictly inside the occupied border", gi, gj);
         return 1;
     }
-    HL_CUDA_OK(cudaSetDevice(ctx->device));
+    if (hl_enter(ctx, nullptr, d_out, "hl_distance_field")) return 1;
     cudaStream_t st = (cudaStream_t)stream;
     DfMoves mv;
     memset(&mv, 0, sizeof(mv));
@@ -192,7 +192,7 @@ __global__ void k_grid_pack(const uint8_t* __restrict__ occ, long long cells, ui
 
 extern "C" int hl_grid_pack(hl_ctx* ctx, const uint8_t* d_occ, int32_t w, int32_t h, uint32_t* d_bits, void* stream) {
     if (!ctx || !d_occ || !d_bits || w <= 0 || h <= 0) { hl_set_error("hl_grid_pack: bad arguments"); return 1; }
-    HL_CUDA_OK(cudaSetDevice(ctx->device));
+    if (hl_enter(ctx, nullptr, d_bits, "hl_grid_pack")) return 1;
     long long cells = (long long)w * h, n_words = (cells + 31) / 32;
     k_grid_pack<<<(unsigned)((n_words + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_occ, cells, d_bits);
     HL_CUDA_OK(cudaGetLastError());
@@ -268,7 +268,7 @@ extern "C" int hl_grid_footprint_check(hl_ctx* ctx, const uint32_t* d_occ_bits, 
         hl_set_error("hl_grid_footprint_check: bad arguments"); return 1;
     }
     if (n == 0) return 0;
-    HL_CUDA_OK(cudaSetDevice(ctx->device));
+    if (hl_enter(ctx, nullptr, d_out, "hl_grid_footprint_check")) return 1;
     k_grid_footprint<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         d_occ_bits, w, h, res, d_poses, (long long)n, body_ext[0], body_ext[1], body_ext[2], body_ext[3], d_out);
     HL_CUDA_OK(cudaGetLastError());

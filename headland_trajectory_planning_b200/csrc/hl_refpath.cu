@@ -219,7 +219,7 @@ extern "C" int hl_ref_path_count(hl_ctx* ctx, const double* d_x, const double* d
         hl_set_error("hl_ref_path_count: bad arguments"); return 1;
     }
     if (n_paths == 0) return 0;
-    HL_CUDA_OK(cudaSetDevice(ctx->device));
+    if (hl_enter(ctx, nullptr, d_counts, "hl_ref_path_count")) return 1;
     const int grid = (int)((n_paths + 127) / 128 < 1184 ? (n_paths + 127) / 128 : 1184);
     k_refpath_count<<<grid, 128, 0, (cudaStream_t)stream>>>(d_x, d_y, d_dir, (const long long*)d_in_offsets, (long long)n_paths,
                                                             ds, (long long*)d_counts, d_status);
@@ -236,7 +236,7 @@ extern "C" int hl_ref_path_fill(hl_ctx* ctx, const double* d_x, const double* d_
         hl_set_error("hl_ref_path_fill: bad arguments"); return 1;
     }
     if (n_paths == 0) return 0;
-    HL_CUDA_OK(cudaSetDevice(ctx->device));
+    if (hl_enter(ctx, nullptr, d_out, "hl_ref_path_fill")) return 1;
     long long want = (n_paths + 3) / 4;
     const long long cap = (long long)ctx->sm_count * 8;
     const int grid = (int)(want < cap ? want : cap);

@@ -218,7 +218,7 @@ extern "C" int hl_rs_all_paths(hl_ctx* ctx, const hl_env_batch* envs, const int3
                                int32_t* d_order, void* stream) {
     if (!ctx || !d_start_goal || !d_words || !d_count || n < 0) { hl_set_error("hl_rs_all_paths: bad arguments"); return 1; }
     if (n == 0) return 0;
-    HL_CUDA_OK(cudaSetDevice(ctx->device));
+    if (hl_enter(ctx, envs, d_words, "hl_rs_all_paths")) return 1;
     long long blocks = (n + RS_WARPS - 1) / RS_WARPS;
     long long cap = (long long)ctx->sm_count * 8;
     int grid = (int)(blocks < cap ? blocks : cap);
@@ -239,7 +239,7 @@ extern "C" int hl_rs_sample(hl_ctx* ctx, const double* d_start, const HlRsWord* 
         hl_set_error("hl_rs_sample: bad arguments"); return 1;
     }
     if (m == 0) return 0;
-    HL_CUDA_OK(cudaSetDevice(ctx->device));
+    if (hl_enter(ctx, nullptr, d_x, "hl_rs_sample")) return 1;
     long long blocks = (m + RS_WARPS - 1) / RS_WARPS;
     long long cap = (long long)ctx->sm_count * 8;
     int grid = (int)(blocks < cap ? blocks : cap);

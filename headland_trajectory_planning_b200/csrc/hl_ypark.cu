@@ -137,7 +137,7 @@ extern "C" int hl_arc_paths(hl_ctx* ctx, const double* d_cand, const int64_t* d_
         hl_set_error("hl_arc_paths: bad arguments"); return 1;
     }
     if (n == 0) return 0;
-    HL_CUDA_OK(cudaSetDevice(ctx->device));
+    if (hl_enter(ctx, nullptr, d_poses, "hl_arc_paths")) return 1;
     const int threads = 128;
     const size_t smem = (size_t)(threads / 32) * 3 * YP_MAX_STEPS * sizeof(double);      // 48 KB
     HL_CUDA_OK(cudaFuncSetAttribute(k_arc_paths, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -155,7 +155,7 @@ extern "C" int hl_ypark_paths(hl_ctx* ctx, const double* d_cand, const int64_t* 
         hl_set_error("hl_ypark_paths: bad arguments"); return 1;
     }
     if (n == 0) return 0;
-    HL_CUDA_OK(cudaSetDevice(ctx->device));
+    if (hl_enter(ctx, nullptr, d_poses, "hl_ypark_paths")) return 1;
     const int threads = 128;
     const size_t smem = (size_t)(threads / 32) * 6 * YP_MAX_STEPS * sizeof(double);      // 96 KB
     HL_CUDA_OK(cudaFuncSetAttribute(k_ypark_paths, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

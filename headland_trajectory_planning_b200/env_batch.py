@@ -70,7 +70,8 @@ class EnvBatch:
 
     def __init__(self, records, device=None, structs=None):
         self.records = list(records)
-        self.ctx = _lib.get_ctx(device)
+        self.ctx = _lib.get_ctx(device)         # device=None: the CALLING thread's current device (thread-local in CUDA)
+        self.device = int(_lib.load_library().hl_ctx_device(self.ctx))
         arr = structs if structs is not None else pack_structs(self.records)
         h = C.c_void_p()
         _lib.check(_lib.load_library().hl_env_upload(self.ctx, arr, len(self.records), C.byref(h)),

@@ -12,12 +12,21 @@ def _torch():
     return torch
 
 
-def _device():
-    """Current CUDA device; without one every op fails loudly (no CPU fallback)."""
+def _device(envs=None, *tensors):
+    """Current CUDA device; without one every op fails loudly (no CPU fallback).  An environment batch or a CUDA
+    tensor that lives on ANOTHER device than the calling thread's current one raises instead of launching across
+    devices (the C ABI checks the same thing again, ``hl_enter``)."""
     import torch
     if not torch.cuda.is_available():
         raise _lib.HeadlandError("no CUDA device: headland_trajectory_planning_b200 has no CPU fallback")
-    return torch.device("cuda", torch.cuda.current_device())
+    cur = torch.cuda.current_device()
+    if envs is not None and getattr(envs, "device", cur) != cur:
+        raise _lib.HeadlandError(f"environment batch was uploaded to cuda:{envs.device} but the current device of this "
+                                 f"thread is cuda:{cur} (torch.cuda.set_device / EnvBatch(device=...))")
+    for t in tensors:
+        if torch.is_tensor(t) and (not t.is_cuda or t.device.index != cur):
+            raise _lib.HeadlandError(f"tensor on {t.device} passed to an op running on cuda:{cur}")
+    return torch.device("cuda", cur)
 
 
 def collision_check(envs, poses, env_id=None, pose_idx=None, flags=CHECK_OBSTACLES | CHECK_BOUNDARY,
@@ -27,7 +36,7 @@ def collision_check(envs, poses, env_id=None, pose_idx=None, flags=CHECK_OBSTACL
     within its path (implement rectangles are tested at even indices only)."""
     torch = _torch()
     lib = _lib.load_library()
-    dev = _device()
+    dev = _device(envs, poses, env_id, pose_idx)
     if not torch.is_tensor(poses):
         poses = torch.from_numpy(np.ascontiguousarray(np.asarray(poses, dtype=np.float64)[:, :3])).to(dev)
     poses = poses.contiguous()
@@ -149,7 +158,7 @@ def rs_all_paths(start_goal, maxc, step, max_steer=0.55, envs=None, env_id=None,
     ``rs_words_to_host`` to view the word records."""
     torch = _torch()
     lib = _lib.load_library()
-    dev = _device()
+    dev = _device(envs, start_goal, env_id)
     if not torch.is_tensor(start_goal):
         start_goal = torch.from_numpy(np.ascontiguousarray(start_goal, dtype=np.float64)).to(dev)
     start_goal = start_goal.contiguous()
@@ -205,7 +214,8 @@ def hybrid_astar_batch(envs, scenarios, params, path_capacity=None, to_host=True
     of scenario i: ``expanded_of(out, i)``) and the pooled path arrays (host numpy when ``to_host``)."""
     torch = _torch()
     lib = _lib.load_library()
-    dev = _device()
+    dev = _device(envs, scenarios)
+    _lib.apply_astar_variant(envs.ctx)
     if torch.is_tensor(scenarios):
         d_scen = scenarios
         n = d_scen.numel() // _lib.SCENARIO_DTYPE.itemsize

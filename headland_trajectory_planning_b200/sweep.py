@@ -45,47 +45,113 @@ def algorithmic_flops(recs, results, field="n_pose_checks_ref"):
     return total
 
 
-def gather_results(results_np, expanded_np, world_size, rank, device=None):
-    """Gather of the result records and pooled expanded keys to rank 0 -- the only collective of a sweep
-    (torch.distributed must be initialised).  Records are fixed-stride; the key pools are padded to the
-    largest pool (one all_reduce of a scalar).  On the GPU box the tensors live on the device so NCCL moves
-    them over NVLink; ``device="cpu"`` is the gloo path the CPU tests use."""
+_PATH_FIELDS = (("x", 8), ("y", 8), ("yaw", 8), ("k", 8), ("dir", 1))
+
+
+def _pack_layout(n_rows, kmax, pmax):
+    """Byte offsets of one rank's packed sweep output: result records | expanded keys | x | y | yaw | k | dir,
+    every section 16-byte aligned."""
+    al = lambda v: (v + 15) & ~15
+    off, o = {}, 0
+    off["results"] = o; o += al(n_rows * _lib.RESULT_DTYPE.itemsize)
+    off["expanded"] = o; o += al(kmax * 12)
+    for name, w in _PATH_FIELDS:
+        off[name] = o; o += al(pmax * w)
+    return off, o
+
+
+def gather_sweep(out, world_size, rank):
+    """The one data-path collective of a sweep: every rank's search output -- ``ops.hybrid_astar_batch(...,
+    to_host=False)``, still on the device -- goes to rank 0 over NCCL / NVLink and is copied to the host ONCE, there.
+    Two collectives: an all_gather of three int64 per rank (key rows, path poses, records: what each rank produced)
+    and one gather of a packed byte buffer padded to the largest rank.  Ranks other than 0 never copy anything to
+    the host.  With CPU tensors in ``out`` the same code runs over gloo (tests/test_sweep_gloo.py).
+
+    Returns on rank 0 a list (one entry per rank) of host dicts with ``results`` (structured), ``expanded``
+    [rows, 3] int32 and the pooled path arrays ``x, y, yaw, k, dir``; ``None`` on the other ranks."""
     import torch
     import torch.distributed as dist
-    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
-    t_res = torch.from_numpy(np.ascontiguousarray(results_np).view(np.uint8).reshape(-1).copy()).to(dev)
-    rows = torch.tensor([len(expanded_np)], dtype=torch.int64, device=dev)
-    dist.all_reduce(rows, op=dist.ReduceOp.MAX)
-    pad = np.zeros((int(rows.item()), 3), dtype=np.int32)
-    pad[:len(expanded_np)] = expanded_np
-    t_exp = torch.from_numpy(pad).to(dev)
-    if rank == 0:
-        g_res = [torch.empty_like(t_res) for _ in range(world_size)]
-        g_exp = [torch.empty_like(t_exp) for _ in range(world_size)]
-        dist.gather(t_res, g_res, dst=0)
-        dist.gather(t_exp, g_exp, dst=0)
-        return ([g.cpu().numpy().view(_lib.RESULT_DTYPE) for g in g_res], [g.cpu().numpy() for g in g_exp])
-    dist.gather(t_res, None, dst=0)
-    dist.gather(t_exp, None, dst=0)
-    return None, None
-
-
-def merge_shards(per_rank_results, per_rank_expanded, n_total, world_size):
-    """Undo the interleaved sharding: record i of rank r is scenario r + i*world_size.  Returns the
-    merged records (keys_offset rewritten) and one pooled key array in scenario order."""
-    res = np.zeros(n_total, dtype=_lib.RESULT_DTYPE)
-    chunks = [None] * n_total
+    res = out["results"]
+    dev = res.device
+    n = int(out["n"])
+    keys_cap, path_cap = out["expanded"].shape[0], out["x"].shape[0]
+    mine = torch.cat([out["kcursor"].reshape(1).to(torch.int64), out["cursor"].reshape(1).to(torch.int64),
+                      torch.tensor([n], dtype=torch.int64, device=dev)])
+    sizes = torch.empty(3 * world_size, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(sizes, mine)
+    sizes = sizes.cpu().numpy().reshape(world_size, 3)               # the step's one host sync on every rank
+    kused = np.minimum(sizes[:, 0], keys_cap)
+    pused = np.minimum(sizes[:, 1], path_cap)
+    kmax, pmax, n_rows = int(kused.max()), int(pused.max()), int(sizes[:, 2].max())
+    off, total = _pack_layout(n_rows, kmax, pmax)
+    buf = torch.empty(total, dtype=torch.uint8, device=dev)
+    nb = n * _lib.RESULT_DTYPE.itemsize
+    buf[off["results"]:off["results"] + nb].copy_(res.reshape(-1)[:nb])
+    k_me, p_me = int(kused[rank]), int(pused[rank])
+    if k_me:
+        buf[off["expanded"]:off["expanded"] + 12 * k_me].copy_(out["expanded"][:k_me].reshape(-1).view(torch.uint8))
+    for name, w in _PATH_FIELDS:
+        if p_me:
+            buf[off[name]:off[name] + w * p_me].copy_(out[name][:p_me].view(torch.uint8))
+    if rank != 0:
+        dist.gather(buf, None, dst=0)
+        return None
+    big = torch.empty((world_size, total), dtype=torch.uint8, device=dev)
+    dist.gather(buf, list(big.unbind(0)), dst=0)
+    if big.is_cuda:
+        host = _pinned(world_size * total).view(world_size, total)
+        host.copy_(big, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        host = host.numpy()
+    else:
+        host = big.numpy()
+    shards = []
     for r in range(world_size):
-        idx = shard_indices(n_total, r, world_size)
-        rr = per_rank_results[r][:len(idx)]
+        row = host[r]
+        nr, kr, pr = int(sizes[r, 2]), int(kused[r]), int(pused[r])
+        d = {"results": row[off["results"]:off["results"] + nr * _lib.RESULT_DTYPE.itemsize].view(_lib.RESULT_DTYPE),
+             "expanded": row[off["expanded"]:off["expanded"] + 12 * kr].view(np.int32).reshape(-1, 3),
+             "keys_used": int(sizes[r, 0]), "used": int(sizes[r, 1]), "n": nr}
+        for name, w in _PATH_FIELDS:
+            d[name] = row[off[name]:off[name] + w * pr].view(np.float64 if w == 8 else np.int8)
+        shards.append(d)
+    return shards
+
+
+_pinned_cache = {}
+
+
+def _pinned(nbytes):
+    """Grow-only pinned host buffer for the gathered sweep (cudaHostAlloc per step would cost more than the copy)."""
+    import torch
+    t = _pinned_cache.get("buf")
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8).pin_memory()
+        _pinned_cache["buf"] = t
+    return t[:nbytes]
+
+
+def merge_shards(shards, n_total, world_size):
+    """Undo the interleaved sharding (record i of rank r is scenario r + i*world_size).  The per-rank key and path
+    pools are concatenated rank-major and the records' ``keys_offset`` / ``path_offset`` rebased into them, so
+    nothing is re-ordered pose by pose.  Returns a host dict shaped like ``ops.hybrid_astar_batch(to_host=True)``
+    (``ops.expanded_of`` / ``hybrid_a_star_search.unpack_path`` work on it)."""
+    res = np.zeros(n_total, dtype=_lib.RESULT_DTYPE)
+    kbase = pbase = 0
+    for r in range(world_size):
+        sh = shards[r]
+        idx = np.arange(r, n_total, world_size)
+        rr = np.array(sh["results"][:len(idx)])
+        rr["keys_offset"] += kbase
+        rr["path_offset"] += pbase
         res[idx] = rr
-        for k, i in enumerate(idx):
-            a = int(rr[k]["keys_offset"])
-            chunks[i] = per_rank_expanded[r][a:a + int(rr[k]["n_expanded"])]
-    off = np.concatenate([[0], np.cumsum([len(c) for c in chunks])])
-    res["keys_offset"] = off[:-1]
-    exp = np.concatenate(chunks) if n_total else np.zeros((0, 3), np.int32)
-    return res, exp
+        kbase += len(sh["expanded"])
+        pbase += len(sh["x"])
+    merged = {"results": res, "n": n_total, "keys_used": kbase, "used": pbase,
+              "expanded": np.concatenate([sh["expanded"] for sh in shards]) if shards else np.zeros((0, 3), np.int32)}
+    for name, _ in _PATH_FIELDS:
+        merged[name] = np.concatenate([sh[name] for sh in shards])
+    return merged
 
 
 class UploadPrefetcher:
@@ -102,14 +168,23 @@ class UploadPrefetcher:
             envs.close()
     """
 
-    def __init__(self):
+    def __init__(self, device=None):
+        import torch
         from concurrent.futures import ThreadPoolExecutor
-        self._ex = ThreadPoolExecutor(max_workers=1)
+        # The CUDA current device is PER THREAD and a new thread starts on device 0: capture the device of the
+        # constructing thread (the rank's own GPU) and hand it to the worker explicitly.
+        self.device = int(torch.cuda.current_device() if device is None else device)
+        self._ex = ThreadPoolExecutor(max_workers=1, initializer=self._init_worker, initargs=(self.device,))
         self._fut = None
+
+    @staticmethod
+    def _init_worker(device):
+        import torch
+        torch.cuda.set_device(device)
 
     def submit(self, records, structs=None):
         from .env_batch import EnvBatch
-        self._fut = self._ex.submit(EnvBatch, records, structs=structs)
+        self._fut = self._ex.submit(EnvBatch, records, device=self.device, structs=structs)
 
     def result(self):
         fut, self._fut = self._fut, None

@@ -15,7 +15,12 @@
  *     owns every buffer (no ownership transfer);
  *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream);
  *     calls are asynchronous with respect to the host unless the name ends in _host;
- *   - no global state besides the opaque hl_ctx (one per device).
+ *   - no global state besides the opaque hl_ctx (one per device).  Every entry point selects the context's
+ *     device itself and REJECTS (non-zero + hl_last_error) an environment batch of another device / context and
+ *     a probed d_* argument that is host memory or lives on another device -- it never launches on the wrong GPU;
+ *   - entry points may be called from any host thread.  Searches (hl_hybrid_astar_batch) share one per-context
+ *     workspace: calls on different streams/threads of one context are serialised on the device (event wait),
+ *     everything else is independent per stream;
  *   - there is NO CPU fallback: without a CUDA device hl_ctx_create fails.
  */
 #ifndef HEADLAND_B200_H
@@ -27,7 +32,7 @@
 extern "C" {
 #endif
 
-#define HL_ABI_VERSION 1
+#define HL_ABI_VERSION 2
 
 /* ---- limits (compile-time capacities of the kernels) ---------------------- */
 #define HL_MAX_PRIMS        16   /* motion primitives per expansion (King: 14, Pawn: 8) */
@@ -148,6 +153,11 @@ int hl_abi_version(void);
 int hl_ctx_create(hl_ctx** out, int device);
 void hl_ctx_destroy(hl_ctx* ctx);
 int hl_ctx_sm_count(const hl_ctx* ctx);
+int hl_ctx_device(const hl_ctx* ctx);              /* CUDA device ordinal of the context (-1 for NULL)          */
+/* Search-kernel variant for A/B runs (results are identical): 0 = two warps per scenario with the analytic shot
+ * decoupled (default), 1 = one warp per scenario, 2 = level-synchronous graph.  The environment variable
+ * HL_ASTAR_VARIANT (spec|warp|level) is read once, at hl_ctx_create. */
+int hl_ctx_set_astar_variant(hl_ctx* ctx, int variant);
 
 /* ---- environments ----------------------------------------------------------- */
 /* Replaces the geometry that OrchardGeometryEnvironment / CarModel /
@@ -155,6 +165,7 @@ int hl_ctx_sm_count(const hl_ctx* ctx);
 int hl_env_upload(hl_ctx* ctx, const HlEnvHost* h_envs, int32_t n_env, hl_env_batch** out);
 void hl_env_free(hl_env_batch* envs);
 int32_t hl_env_count(const hl_env_batch* envs);
+int hl_env_device(const hl_env_batch* envs);       /* device the batch was uploaded to                           */
 
 /* ---- K1 footprint collision --------------------------------------------------
  * Replaces OrchardGeometryEnvironment.check_path_feasibility

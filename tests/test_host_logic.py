@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(built_library):
     lib = ctypes.CDLL(built_library)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.hl_abi_version() == 1
+    assert lib.hl_abi_version() == _lib.ABI_VERSION
 
 
 def test_struct_layouts_match_header(built_library):
@@ -145,3 +145,18 @@ def test_shard_indices_interleave():
     all_idx = sorted(i for r in range(8) for i in sweep.shard_indices(4096, r, 8))
     assert all_idx == list(range(4096))
     assert sweep.shard_indices(10, 1, 4) == [1, 5, 9]
+
+
+@pytest.mark.timeout(60)
+def test_failing_ctx_create_raises_instead_of_deadlocking(built_library, monkeypatch):
+    """hl_ctx_create fails in this container (no CUDA device).  get_ctx used to call check() -> last_error() ->
+    load_library() while holding the non-reentrant module lock: the failure hung forever instead of raising."""
+    import torch
+    from headland_trajectory_planning_b200 import _lib
+    if torch.cuda.is_available():
+        pytest.skip("needs a box without a CUDA device")
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
+    with pytest.raises(_lib.HeadlandError, match="hl_ctx_create"):
+        _lib.get_ctx(None)
+    assert 0 not in _lib._ctxs
