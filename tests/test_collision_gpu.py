@@ -107,3 +107,37 @@ def test_candidate_generators_empty(built_library):
     assert p.shape == (0, 3) and list(o) == [0]
     p, o = ops.arc_paths(np.zeros((0, 8)), 0.1)
     assert p.shape == (0, 3) and list(o) == [0]
+
+
+@pytest.mark.parametrize("aux", [None, H.SPRAYER_AUX])
+def test_staged_pipeline_equals_per_pose_filter(built_library, aux):
+    """K1 has two paths: the staged / compacted pipeline on a TMA-fed slice of one shared-memory environment, and the
+    monolithic per-pose filter on global memory for slices that mix environments.  Two copies of the same
+    environment with alternating env_id force the second path; both must give the same booleans on 1.5 M poses
+    (every flag combination, ragged tail, a pose pointer that is not 16-byte aligned = no bulk copy)."""
+    import torch
+    from headland_trajectory_planning_b200 import ops
+    from headland_trajectory_planning_b200.env_batch import EnvBatch, make_record
+    rows = H.canonical_rows(l_std=0.5)
+    start = np.array([0.0, 3.75, math.pi])
+    goal = np.array([-1.5, 11.0, 0.3])
+    way = np.array([[0.0, 3.75], [-4.5, 5.0], [-4.06, 7.5], [-3.62, 10.0], [-1.5, 11.0]])
+    (_, _, _), (g_env, g_car, g_h) = H.make_pair(rows, axle_to_front=2.85, aux=aux, waypoints=way, goal=goal)
+    rec = make_record(g_env, g_car, g_h)
+    envs = EnvBatch([rec, rec])
+    rng = np.random.default_rng(5)
+    n = 1_500_000 + 77
+    poses = H.headland_poses(rng, n, rows)
+    poses[::1000, 0] = np.nan                      # undecidable poses go to the float64 path in both
+    poses[7::1000, 0] = 5e4                        # beyond the environment's reach
+    d_poses = torch.from_numpy(poses).cuda()
+    idx = torch.arange(n, dtype=torch.int32, device="cuda")
+    alt = (idx & 1).to(torch.int32)
+    for flags in (1, 3, 8, 11, 7 if aux else 2, 15 if aux else 9):
+        fast = ops.collision_check(envs, d_poses, pose_idx=idx, flags=flags)
+        slow = ops.collision_check(envs, d_poses, env_id=alt, pose_idx=idx, flags=flags)
+        assert torch.equal(fast, slow), f"flags={flags}: {(fast != slow).sum().item()} booleans differ"
+        assert 0.01 < fast.float().mean().item() < 0.995
+        # unaligned source: the same poses shifted by one row (24 bytes)
+        un = ops.collision_check(envs, d_poses[1:], pose_idx=idx[1:].contiguous(), flags=flags)
+        assert torch.equal(un, fast[1:]), f"flags={flags}: unaligned source differs"
