@@ -6,28 +6,30 @@
 // (reference_line_heuristic.py:105-118), decomposed per pose.
 //
 // Round-2 structure:
-//   * a CTA of 8 warps walks 1024-pose tiles; every warp owns a 128-pose slice (4 poses per lane);
-//   * the slice's poses (3 KB, contiguous) are fetched by ONE cp.async.bulk (TMA, 1-D) into the warp's landing zone,
-//     completion on the warp's mbarrier; the copy of the NEXT slice is issued as soon as the current one has been
+//   * a CTA of 8 warps walks 1024-pose tiles; the tile's poses (24 KB, contiguous) arrive by ONE cp.async.bulk
+//     (TMA, 1-D) on the CTA's mbarrier, and the copy of the NEXT tile is issued as soon as the current one has been
 //     converted to the float32 frame, so HBM latency hides behind the filter stages;
-//   * the environment's float32 records are staged per CTA by three bulk copies on a CTA mbarrier and read with
-//     ld.shared.v4 (LDS, broadcast) -- never through a generic pointer;
-//   * the float32 filter runs as STAGES over the slice, cheapest and most decisive first -- lane centre test,
-//     obstacles (box-box SAT), field-edge pass, nearby field edges, lane corners -- and between stages the warp
-//     COMPACTS the poses that are still undecided (ballot + popc into a byte list), so the expensive stages run on
-//     dense warps instead of dragging 32 unrelated poses through every section;
-//   * poses inside the float32 error band are resolved by the whole warp with the float64 predicates (hl_geom.cuh).
-// Slices that cannot use this path (environment larger than the staging area, several environments in one slice,
+//   * the environment's float32 records are staged by three bulk copies and read with LDS.128 (broadcast);
+//   * the float32 filter runs as STAGES over the tile, cheapest and most decisive first -- lane centre test,
+//     obstacles (box-box SAT), field-edge pass, nearby field edges, lane corners.  Between stages the CTA COMPACTS
+//     the poses that are still undecided into a shared list (ballot + popc + one shared atomic per warp), so every
+//     stage runs on dense warps instead of dragging 32 unrelated poses through every section, and the 8 warps of
+//     a CTA execute the same stage at the same time: a stage's code is fetched into the 32 KB instruction cache
+//     once per 1024 poses (the first cut with per-warp lists ran at 72-88 % instruction-cache hit rate and 68 %
+//     lane occupancy, profiles/r2b-r2d);
+//   * poses inside the float32 error band are resolved by a whole warp with the float64 predicates (hl_geom.cuh).
+// Tiles that cannot use this path (environment larger than the staging area, several environments in one tile,
 // non-rectangular obstacle quads) take the monolithic per-pose filter on global memory (k1_slow_slice).
 // Roofline: FP32 ALU (24 B of HBM traffic per ~2.5 kflop check).
 #include "hl_geom.cuh"
 
+#ifndef K1_WARPS
 #define K1_WARPS 8
+#endif
 #define K1_THREADS (K1_WARPS * 32)
-#define K1_TILE 128                       // poses per warp slice
-#define K1_PER_LANE (K1_TILE / 32)
-#define K1_CTA_TILE (K1_WARPS * K1_TILE)
-#define K1_PAIRS 256                      // capacity of a warp's (pose, obstacle) / (pose, field edge) pair list
+#define K1_TILE (K1_WARPS * 128)          // poses per CTA tile
+#define K1_PER_THREAD (K1_TILE / K1_THREADS)
+#define K1_SLICE (K1_TILE / K1_WARPS)     // poses per warp in the per-pose fallback
 #define K1_ENV_FLOATS 1024                // staged float32 records (canonical environment: 432 floats)
 #ifndef K1_MIN_CTAS
 #define K1_MIN_CTAS 4
@@ -63,24 +65,22 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
 // ------------------------------------------------------------------ shared-memory layout
-struct __align__(16) K1Warp {
-    double raw[K1_TILE * 3];              // TMA landing zone: x, y, yaw of the slice
-    float4 pose[K1_TILE];                 // px, py (relative to the environment origin), cos, sin
-    unsigned short pairs[K1_PAIRS];       // (pose q | record k << 8) work items of the obstacle / field-edge passes
+struct __align__(16) K1Cta {
+    double raw[K1_TILE * 3];              // TMA landing zone: x, y, yaw of the tile                        24 KB
+    float px[K1_TILE], py[K1_TILE];       // pose relative to the environment origin                         8 KB
+    float yr[K1_TILE];                    // heading reduced to [-pi, pi]                                    4 KB
+    unsigned nearm[K1_TILE];              // field edges whose line passes within the circumradius           4 KB
+    unsigned short la[K1_TILE], lb[K1_TILE], lc[K1_TILE];      // compacted pose lists                       6 KB
     unsigned char st[K1_TILE];            // K1S_* bits
     unsigned char amb[K1_TILE];           // HL_CHECK_* bits inside the float32 band
-    unsigned char la[K1_TILE], lb[K1_TILE], lc[K1_TILE];     // compacted pose lists
-    unsigned long long bar;               // mbarrier of the landing zone
-};
-struct __align__(16) K1Cta {
-    float env[K1_ENV_FLOATS];             // obstacle records | field-edge records | lane segments
+    float env[K1_ENV_FLOATS];             // obstacle records | field-edge records | lane segments           4 KB
     float4 segd[HL_MAX_SEGS];             // per lane segment: ex, ey, 1/len^2, 1/len (derived once per staging)
-    float4 fld[32][2];                    // per field edge, for the first pass: (Ax, Ay, Ex, Ey) with the endpoints
+    float4 fld[32][2];                    // per field edge, first pass: (Ax, Ay, Ex, Ey) with the endpoints
                                           // ordered so that Ey >= 0, and (nx, ny, c, By) -- see k1_field1
-    unsigned long long bar;
-    K1Warp w[K1_WARPS];
+    unsigned long long bar_env, bar_raw;  // mbarriers of the two kinds of bulk copy
+    int cnt[4];                           // list counters: la, lb, lc, pending
 };
-enum { K1S_HIT = 1, K1S_INSIDE = 2, K1S_NOTCLEAR = 4, K1S_CORNERS = 8, K1S_DONE = 16, K1S_FAR = 32, K1S_OFF = 64 };
+enum { K1S_HIT = 1, K1S_INSIDE = 2, K1S_CORNERS = 8, K1S_DONE = 16, K1S_FAR = 32, K1S_OFF = 64 };
 
 struct K1Env {                            // staged environment (shared memory, uniform per CTA)
     const float* obs_a; const float* field_a; const float* seg_a; const float* segd_a; const float* fld_a;
@@ -113,16 +113,20 @@ __device__ __noinline__ void warp_resolve(bool need, double x, double y, double 
     }
 }
 
-// OR `bit` into byte q of a shared byte array (several lanes may hold pairs of the same pose)
-__device__ __forceinline__ void st_or(unsigned char* arr, int q, unsigned bit) {
-    atomicOr(reinterpret_cast<unsigned*>(arr) + (q >> 2), bit << (8 * (q & 3)));
+// appends q to the CTA list for every lane with `pred`: one shared atomic per warp
+__device__ __forceinline__ void cta_append(unsigned short* list, int* cnt, bool pred, int q, int lane) {
+    const unsigned m = __ballot_sync(0xffffffffu, pred);
+    int base = 0;
+    if (lane == 0 && m) base = atomicAdd(cnt, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (pred) list[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)q;
 }
 
-// appends q to `list` for every lane with `pred`; returns the new (warp-uniform) count
-__device__ __forceinline__ int warp_append(unsigned char* list, int cnt, bool pred, int q, int lane) {
-    const unsigned m = __ballot_sync(0xffffffffu, pred);
-    if (pred) list[cnt + __popc(m & ((1u << lane) - 1u))] = (unsigned char)q;
-    return cnt + __popc(m);
+// pose of list entry q: px, py, cos, sin (the hardware sine / cosine of the reduced heading: abs. error 2^-21.4 in
+// [-pi, pi], < 2e-6 m on a footprint corner, far inside the band eps)
+__device__ __forceinline__ float4 k1_pose(const K1Cta& S, int q) {
+    const float yr = S.yr[q];
+    return make_float4(S.px[q], S.py[q], __cosf(yr), __sinf(yr));
 }
 
 // ------------------------------------------------------------------ filter stages (float32, staged environment)
@@ -143,6 +147,7 @@ __device__ __forceinline__ int k1_lane_centre(const K1Env& E, const K1Rect& R, f
     const float Cx = fmaf(P.z, R.mx, fmaf(-P.w, R.my, P.x)), Cy = fmaf(P.w, R.mx, fmaf(P.z, R.my, P.y));
     const float rin = (float)HL_LANE_RIN - E.eps, rout = (float)HL_LANE_R + E.eps;
     bool accepted = false, need = false;
+#pragma unroll 1
     for (int i = 0; i < E.n_seg; ++i) {
         const float4 sg = lds4(E.seg_a + 4 * i), sd = lds4(E.segd_a + 4 * i);
         const float qx = Cx - sg.x, qy = Cy - sg.y;
@@ -155,59 +160,25 @@ __device__ __forceinline__ int k1_lane_centre(const K1Env& E, const K1Rect& R, f
     return accepted ? 0 : (need ? 2 : 1);
 }
 
-// Stage B, first pass: which obstacles can the rectangle touch at all?  Centre of the rectangle against the
-// obstacle box grown by the circumradius (+ band), in the obstacle's own frame: ~12 instructions per obstacle.  A box
-// that fails this is separated from the rectangle by more than eps along one of its own axes.
-__device__ __forceinline__ unsigned k1_obstacle_mask(const K1Env& E, const K1Rect& R, float4 P, float rho_eps) {
+// Stage B: rectangular obstacles, 4-axis box-box separating test on (centre, axis, half extents).
+__device__ __forceinline__ void k1_obstacles(const K1Env& E, const K1Rect& R, float4 P, bool& hit, bool& amb) {
     const float c = P.z, s = P.w;
     const float Cx = fmaf(c, R.mx, fmaf(-s, R.my, P.x)), Cy = fmaf(s, R.mx, fmaf(c, R.my, P.y));
-    unsigned m = 0;
+    hit = false; amb = false;
+#pragma unroll 2
     for (int k = 0; k < E.n_obs; ++k) {
         const float4 b0 = lds4(E.obs_a + HL_OBS32_STRIDE * k + 20);      // flag, cx, cy, ax
         const float4 b1 = lds4(E.obs_a + HL_OBS32_STRIDE * k + 24);      // ay, ha, hb, pad
         const float dx = b0.y - Cx, dy = b0.z - Cy;
-        const float da = fabsf(fmaf(dx, b0.w, dy * b1.x)), db = fabsf(fmaf(dy, b0.w, -dx * b1.x));
-        m |= (unsigned)(!(da > b1.y + rho_eps) && !(db > b1.z + rho_eps)) << k;
+        const float ax = b0.w, ay = b1.x, ha = b1.y, hb = b1.z;
+        const float p = fabsf(fmaf(ax, c, ay * s)), q = fabsf(fmaf(ay, c, -ax * s));
+        const float du = fabsf(fmaf(dx, c, dy * s)), dv = fabsf(fmaf(dy, c, -dx * s));
+        const float da = fabsf(fmaf(dx, ax, dy * ay)), db = fabsf(fmaf(dy, ax, -dx * ay));
+        const float sep = fmaxf(fmaxf(du - fmaf(ha, p, fmaf(hb, q, R.hx)), dv - fmaf(ha, q, fmaf(hb, p, R.hy))),
+                                fmaxf(da - fmaf(R.hx, p, fmaf(R.hy, q, ha)), db - fmaf(R.hx, q, fmaf(R.hy, p, hb))));
+        hit |= sep < -E.eps;
+        amb |= fabsf(sep) <= E.eps;
     }
-    return m;
-}
-
-// Stage B, second pass: one (pose, obstacle) pair -- 4-axis box-box separating test on (centre, axis, half extents).
-__device__ __forceinline__ void k1_obstacle_one(const K1Env& E, const K1Rect& R, float4 P, int k, bool& hit, bool& amb) {
-    const float c = P.z, s = P.w;
-    const float Cx = fmaf(c, R.mx, fmaf(-s, R.my, P.x)), Cy = fmaf(s, R.mx, fmaf(c, R.my, P.y));
-    const float4 b0 = lds4(E.obs_a + HL_OBS32_STRIDE * k + 20);      // flag, cx, cy, ax
-    const float4 b1 = lds4(E.obs_a + HL_OBS32_STRIDE * k + 24);      // ay, ha, hb, pad
-    const float dx = b0.y - Cx, dy = b0.z - Cy;
-    const float ax = b0.w, ay = b1.x, ha = b1.y, hb = b1.z;
-    const float p = fabsf(fmaf(ax, c, ay * s)), q = fabsf(fmaf(ay, c, -ax * s));
-    const float du = fabsf(fmaf(dx, c, dy * s)), dv = fabsf(fmaf(dy, c, -dx * s));
-    const float da = fabsf(fmaf(dx, ax, dy * ay)), db = fabsf(fmaf(dy, ax, -dx * ay));
-    const float sep = fmaxf(fmaxf(du - fmaf(ha, p, fmaf(hb, q, R.hx)), dv - fmaf(ha, q, fmaf(hb, p, R.hy))),
-                            fmaxf(da - fmaf(R.hx, p, fmaf(R.hy, q, ha)), db - fmaf(R.hx, q, fmaf(R.hy, p, hb))));
-    hit = sep < -E.eps;
-    amb = fabsf(sep) <= E.eps;
-}
-
-// Appends this lane's pairs (q | k << 8 for every set bit k of `m`) to the warp's pair list, flushing the list through
-// `process` first when it would overflow.  Returns false when this chunk alone exceeds the capacity (caller falls
-// back to a per-pose loop).
-template <class F>
-__device__ __forceinline__ bool k1_push_pairs(K1Warp& W, int& n_pairs, unsigned m, int q, int lane, F&& process) {
-    int cnt = __popc(m), off = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, off, o); if (lane >= o) off += t; }
-    const int total = __shfl_sync(0xffffffffu, off, 31);
-    if (total > K1_PAIRS) return false;
-    if (n_pairs + total > K1_PAIRS) { process(n_pairs); n_pairs = 0; __syncwarp(); }
-    off += n_pairs - cnt;
-    while (m) {
-        const int k = __ffs(m) - 1;
-        m &= m - 1;
-        W.pairs[off++] = (unsigned short)(q | (k << 8));
-    }
-    n_pairs += total;
-    return true;
 }
 
 // Stage C: one pass over the field edges -- crossing parity of the centre + mask of the edges whose LINE passes
@@ -220,6 +191,7 @@ __device__ __forceinline__ void k1_field1(const K1Env& E, const K1Rect& R, float
     const float c = P.z, s = P.w;
     const float Cx = fmaf(c, R.mx, fmaf(-s, R.my, P.x)), Cy = fmaf(s, R.mx, fmaf(c, R.my, P.y));
     unsigned nm = 0, par = 0;
+#pragma unroll 2
     for (int i = 0; i < E.n_field; ++i) {
         const float4 f0 = lds4(E.fld_a + 8 * i);          // Ax, Ay, Ex, Ey   (Ay <= By)
         const float4 f1 = lds4(E.fld_a + 8 * i + 4);      // nx, ny, c, By
@@ -231,43 +203,53 @@ __device__ __forceinline__ void k1_field1(const K1Env& E, const K1Rect& R, float
     near_mask = nm; inside = par != 0;
 }
 
-// Stage D: one (pose, nearby field edge) pair.  0 = the edge is clear of the rectangle, 1 = it may touch it (band),
-// 2 = it definitely cuts it (Liang-Barsky against the rectangle shrunk by eps).
-__device__ __forceinline__ int k1_field2_one(const K1Env& E, const K1Rect& R, float4 P, int i) {
+// Stage D: the nearby edges of one pose (support radius along the normal, extent along the edge, Liang-Barsky
+// against the shrunken rectangle), then the field verdict.  Returns HL_HIT / HL_FREE / HL_AMBIG.
+__device__ __forceinline__ int k1_field2(const K1Env& E, const K1Rect& R, float4 P, unsigned near_mask, bool inside) {
     const float eps = E.eps;
     const float px = P.x, py = P.y, c = P.z, s = P.w;
     const float Cx = fmaf(c, R.mx, fmaf(-s, R.my, px)), Cy = fmaf(s, R.mx, fmaf(c, R.my, py));
-    const float4 r0 = lds4(E.field_a + HL_FIELD32_STRIDE * i);        // Ax, Ay, Ex, Ey
-    const float4 r1 = lds4(E.field_a + HL_FIELD32_STRIDE * i + 4);    // nx, ny, c, By
-    const float4 r2 = lds4(E.field_a + HL_FIELD32_STRIDE * i + 8);    // t.A, t.B
-    const float Ax = r0.x, Ay = r0.y, Bx = Ax + r0.z, By = r1.w, nx = r1.x, ny = r1.y;
-    const float nu = fmaf(nx, c, ny * s), nv = fmaf(ny, c, -nx * s);
-    const float sd = fmaf(nx, Cx, fmaf(ny, Cy, -r1.z));                  // signed distance of the centre to the line
-    if (fabsf(sd) > fmaf(R.hx, fabsf(nu), R.hy * fabsf(nv)) + eps) return 0;   // clear by the support radius along n
-    const float ct = fmaf(-ny, Cx, nx * Cy);
-    const float rt = fmaf(R.hx, fabsf(nv), R.hy * fabsf(nu));
-    if (ct - rt > fmaxf(r2.x, r2.y) + eps || ct + rt < fminf(r2.x, r2.y) - eps) return 0;
-    const float dxa = Ax - px, dya = Ay - py, dxb = Bx - px, dyb = By - py;
-    const float ua = fmaf(c, dxa, s * dya), wa = fmaf(c, dya, -s * dxa);
-    const float ub = fmaf(c, dxb, s * dyb), wb = fmaf(c, dyb, -s * dxb);
-    if ((fminf(ua, ub) > R.x1 + eps) || (fmaxf(ua, ub) < R.x0 - eps) ||
-        (fminf(wa, wb) > R.y1 + eps) || (fmaxf(wa, wb) < R.y0 - eps)) return 0;
-    float t0 = 0.f, t1 = 1.f;
-    bool dead = false;
-    const float a2[2] = {ua, wa}, d2v[2] = {ub - ua, wb - wa};
-    const float lo2[2] = {R.x0 + eps, R.y0 + eps}, hi2[2] = {R.x1 - eps, R.y1 - eps};
+    bool all_clear = true, cut = false;
+#pragma unroll 1
+    while (near_mask) {
+        const int i = __ffs(near_mask) - 1;
+        near_mask &= near_mask - 1;
+        const float4 r0 = lds4(E.field_a + HL_FIELD32_STRIDE * i);        // Ax, Ay, Ex, Ey
+        const float4 r1 = lds4(E.field_a + HL_FIELD32_STRIDE * i + 4);    // nx, ny, c, By
+        const float4 r2 = lds4(E.field_a + HL_FIELD32_STRIDE * i + 8);    // t.A, t.B
+        const float Ax = r0.x, Ay = r0.y, Bx = Ax + r0.z, By = r1.w, nx = r1.x, ny = r1.y;
+        const float nu = fmaf(nx, c, ny * s), nv = fmaf(ny, c, -nx * s);
+        const float sd = fmaf(nx, Cx, fmaf(ny, Cy, -r1.z));                  // signed distance of the centre to the line
+        if (fabsf(sd) > fmaf(R.hx, fabsf(nu), R.hy * fabsf(nv)) + eps) continue;   // clear by the support radius along n
+        const float ct = fmaf(-ny, Cx, nx * Cy);
+        const float rt = fmaf(R.hx, fabsf(nv), R.hy * fabsf(nu));
+        if (ct - rt > fmaxf(r2.x, r2.y) + eps || ct + rt < fminf(r2.x, r2.y) - eps) continue;
+        const float dxa = Ax - px, dya = Ay - py, dxb = Bx - px, dyb = By - py;
+        const float ua = fmaf(c, dxa, s * dya), wa = fmaf(c, dya, -s * dxa);
+        const float ub = fmaf(c, dxb, s * dyb), wb = fmaf(c, dyb, -s * dxb);
+        if ((fminf(ua, ub) > R.x1 + eps) || (fmaxf(ua, ub) < R.x0 - eps) ||
+            (fminf(wa, wb) > R.y1 + eps) || (fmaxf(wa, wb) < R.y0 - eps)) continue;
+        all_clear = false;
+        float t0 = 0.f, t1 = 1.f;
+        bool dead = false;
+        const float a2[2] = {ua, wa}, d2v[2] = {ub - ua, wb - wa};
+        const float lo2[2] = {R.x0 + eps, R.y0 + eps}, hi2[2] = {R.x1 - eps, R.y1 - eps};
 #pragma unroll
-    for (int ax = 0; ax < 2; ++ax) {
-        if (fabsf(d2v[ax]) < 1e-12f) {
-            if (a2[ax] <= lo2[ax] || a2[ax] >= hi2[ax]) dead = true;
-        } else {
-            const float inv = f_rcp(d2v[ax]);
-            const float tl = (lo2[ax] - a2[ax]) * inv, th = (hi2[ax] - a2[ax]) * inv;
-            t0 = fmaxf(t0, fminf(tl, th));
-            t1 = fminf(t1, fmaxf(tl, th));
+        for (int ax = 0; ax < 2; ++ax) {
+            if (fabsf(d2v[ax]) < 1e-12f) {
+                if (a2[ax] <= lo2[ax] || a2[ax] >= hi2[ax]) dead = true;
+            } else {
+                const float inv = f_rcp(d2v[ax]);
+                const float tl = (lo2[ax] - a2[ax]) * inv, th = (hi2[ax] - a2[ax]) * inv;
+                t0 = fmaxf(t0, fminf(tl, th));
+                t1 = fminf(t1, fmaxf(tl, th));
+            }
         }
+        if (!dead && (t1 - t0) * f_sqrt(fmaf(d2v[0], d2v[0], d2v[1] * d2v[1])) > 8.0f * eps) { cut = true; break; }
     }
-    return (!dead && (t1 - t0) * f_sqrt(fmaf(d2v[0], d2v[0], d2v[1] * d2v[1])) > 8.0f * eps) ? 2 : 1;
+    if (cut) return HL_HIT;
+    if (all_clear) return inside ? HL_FREE : HL_HIT;
+    return HL_AMBIG;
 }
 
 // corner_in_capsule (hl_geom.cuh) on the staged segment + its derived record
@@ -313,6 +295,7 @@ __device__ __forceinline__ int k1_lane_corners(const K1Env& E, const K1Rect& R, 
     }
     bool one_holds_all = false;
     unsigned maybe = 0;
+#pragma unroll 1
     for (int i = 0; i < E.n_seg; ++i) {
         const float4 sg = lds4(E.seg_a + 4 * i), sd = lds4(E.segd_a + 4 * i);
         bool all_in = true;
@@ -356,7 +339,7 @@ __device__ __forceinline__ int k1_lane_corners(const K1Env& E, const K1Rect& R, 
 __device__ __noinline__ void k1_slow_slice(const EnvBatchDev& eb, const int32_t* env_id, const double* poses,
                                            const int32_t* pose_idx, long long n, long long base, unsigned flags,
                                            uint8_t* out, unsigned long long* n_exact, int lane) {
-    for (int j = 0; j < K1_PER_LANE; ++j) {
+    for (int j = 0; j < (K1_SLICE / 32); ++j) {
         const long long i = base + j * 32 + lane;
         const bool active = i < n;
         const int e = active ? (env_id ? env_id[i] : 0) : 0;
@@ -407,15 +390,13 @@ k_collision(EnvBatchDev eb, const int32_t* __restrict__ env_id, const double* __
             uint8_t* __restrict__ out, unsigned long long* n_exact, int use_tma) {
     extern __shared__ __align__(16) unsigned char k1_smem[];
     K1Cta& S = *reinterpret_cast<K1Cta*>(k1_smem);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    K1Warp& W = S.w[warp];
-    const unsigned wbar = smem_u32(&W.bar), cbar = smem_u32(&S.bar);
-    const long long n_tiles = (n + K1_CTA_TILE - 1) / K1_CTA_TILE;
-    if (threadIdx.x == 0) mbar_init(cbar, 1);
-    if (lane == 0) mbar_init(wbar, 1);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned rbar = smem_u32(&S.bar_raw), ebar = smem_u32(&S.bar_env);
+    const long long n_tiles = (n + K1_TILE - 1) / K1_TILE;
+    if (tid == 0) { mbar_init(rbar, 1); mbar_init(ebar, 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
-    unsigned wphase = 0, cphase = 0;
+    unsigned rphase = 0, ephase = 0;
     int staged_env = -1;
     bool env_ok = false;                               // staged environment usable by the pipeline
     K1Env E;
@@ -423,50 +404,45 @@ k_collision(EnvBatchDev eb, const int32_t* __restrict__ env_id, const double* __
     E.fld_a = reinterpret_cast<const float*>(S.fld);
     E.n_obs = E.n_field = E.n_seg = 0; E.eps = 0.f;
 
-    // does this warp's slice of `tile` arrive by TMA?  (full slice, 16-byte aligned source)
-    auto slice_tma = [&](long long tile) -> bool {
-        const long long b = tile * K1_CTA_TILE + (long long)warp * K1_TILE;
-        return use_tma && tile < n_tiles && b + K1_TILE <= n;
-    };
-    auto issue_slice = [&](long long tile) {
-        if (lane == 0 && slice_tma(tile)) {
-            const long long b = tile * K1_CTA_TILE + (long long)warp * K1_TILE;
-            mbar_expect_tx(wbar, K1_TILE * 24);
-            bulk_g2s(smem_u32(W.raw), poses + 3 * b, K1_TILE * 24, wbar);
+    // does `tile` arrive by TMA?  (full tile, 16-byte aligned source)
+    auto tile_tma = [&](long long tile) -> bool { return use_tma && tile < n_tiles && (tile + 1) * K1_TILE <= n; };
+    auto issue_tile = [&](long long tile) {
+        if (tid == 0 && tile_tma(tile)) {
+            mbar_expect_tx(rbar, K1_TILE * 24);
+            bulk_g2s(smem_u32(S.raw), poses + 3 * tile * K1_TILE, K1_TILE * 24, rbar);
         }
     };
-    issue_slice(blockIdx.x);
+    issue_tile(blockIdx.x);
 
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long long cta_base = tile * K1_CTA_TILE;
-        const long long base = cta_base + (long long)warp * K1_TILE;
+        const long long base = tile * K1_TILE;
         // ---- environment of the tile (CTA-uniform): staged by bulk copies when it changes
-        const int e0 = env_id ? env_id[cta_base] : 0;
+        const int e0 = env_id ? env_id[base] : 0;
         if (e0 != staged_env) {
             __syncthreads();                           // nobody still reads the previous environment
             const EnvDesc& D0 = eb.desc[e0];
             const int n_o = D0.n_obs * HL_OBS32_STRIDE, n_f = D0.n_field * HL_FIELD32_STRIDE, n_s = D0.n_seg * 4;
-            env_ok = (n_o + n_f + n_s <= K1_ENV_FLOATS) && D0.all_rect && D0.n_seg <= HL_MAX_SEGS && D0.n_field <= 32 && D0.n_obs <= 32;
+            env_ok = (n_o + n_f + n_s <= K1_ENV_FLOATS) && D0.all_rect && D0.n_seg <= HL_MAX_SEGS && D0.n_field <= 32;
             if (env_ok) {
-                if (threadIdx.x == 0) {
+                if (tid == 0) {
                     fence_proxy_async();
                     const unsigned bytes = 4u * (unsigned)(n_o + n_f + n_s);
                     if (bytes) {
-                        mbar_expect_tx(cbar, bytes);
-                        if (n_o) bulk_g2s(smem_u32(S.env), eb.obs32 + (size_t)HL_OBS32_STRIDE * D0.obs_off, 4u * n_o, cbar);
-                        if (n_f) bulk_g2s(smem_u32(S.env + n_o), eb.field32 + (size_t)HL_FIELD32_STRIDE * D0.field_off, 4u * n_f, cbar);
-                        if (n_s) bulk_g2s(smem_u32(S.env + n_o + n_f), eb.seg32 + 4 * (size_t)D0.seg_off, 4u * n_s, cbar);
+                        mbar_expect_tx(ebar, bytes);
+                        if (n_o) bulk_g2s(smem_u32(S.env), eb.obs32 + (size_t)HL_OBS32_STRIDE * D0.obs_off, 4u * n_o, ebar);
+                        if (n_f) bulk_g2s(smem_u32(S.env + n_o), eb.field32 + (size_t)HL_FIELD32_STRIDE * D0.field_off, 4u * n_f, ebar);
+                        if (n_s) bulk_g2s(smem_u32(S.env + n_o + n_f), eb.seg32 + 4 * (size_t)D0.seg_off, 4u * n_s, ebar);
                     }
                 }
-                if (n_o + n_f + n_s) { mbar_wait(cbar, cphase); cphase ^= 1u; }
-                if (threadIdx.x < D0.n_seg) {          // derived per-segment record: ex, ey, 1/len^2, 1/len
-                    const float* sg = S.env + n_o + n_f + 4 * threadIdx.x;
+                if (n_o + n_f + n_s) { mbar_wait(ebar, ephase); ephase ^= 1u; }
+                if (tid < D0.n_seg) {                  // derived per-segment record: ex, ey, 1/len^2, 1/len
+                    const float* sg = S.env + n_o + n_f + 4 * tid;
                     const float ex = sg[2] - sg[0], ey = sg[3] - sg[1];
                     const float len2 = fmaf(ex, ex, ey * ey);
-                    S.segd[threadIdx.x] = make_float4(ex, ey, f_rcp(len2), rsqrtf(len2));
+                    S.segd[tid] = make_float4(ex, ey, f_rcp(len2), rsqrtf(len2));
                 }
-                if (threadIdx.x >= 32 && threadIdx.x < 32 + D0.n_field) {     // first-pass field records, endpoints ordered by y
-                    const int i = threadIdx.x - 32;
+                if (tid >= 32 && tid < 32 + D0.n_field) {     // first-pass field records, endpoints ordered by y
+                    const int i = tid - 32;
                     const float* e = S.env + n_o + HL_FIELD32_STRIDE * i;
                     const bool up = !(e[1] > e[7]);                    // Ay <= By
                     S.fld[i][0] = up ? make_float4(e[0], e[1], e[2], e[3]) : make_float4(e[0] + e[2], e[7], -e[2], -e[3]);
@@ -476,50 +452,46 @@ k_collision(EnvBatchDev eb, const int32_t* __restrict__ env_id, const double* __
                 E.n_obs = D0.n_obs; E.n_field = D0.n_field; E.n_seg = D0.n_seg; E.eps = D0.eps;
             }
             staged_env = e0;
-            __syncthreads();
         }
-        if (base >= n) { continue; }                   // warp without poses in this (last) tile
         const EnvDesc& D = eb.desc[e0];
-        const bool tma = slice_tma(tile);
-        if (tma) { mbar_wait(wbar, wphase); wphase ^= 1u; }
-        // ---- stage 0: poses -> float32 frame; is the whole slice in the staged environment?
+        const bool tma = tile_tma(tile);
+        if (tid < 4) S.cnt[tid] = 0;
+        if (tma) { mbar_wait(rbar, rphase); rphase ^= 1u; }
+        // ---- stage 0: poses -> float32 frame; is the whole tile in the staged environment?
         bool same_env = env_ok;
+        {
+            const double ox = D.origin[0], oy = D.origin[1];
+            const float reach = D.reach;
 #pragma unroll 1
-        for (int j = 0; j < K1_PER_LANE; ++j) {
-            const int q = j * 32 + lane;
-            const long long i = base + q;
-            const bool active = i < n;
-            double x = 0.0, y = 0.0, yaw = 0.0;
-            if (active) {
-                if (tma) { x = W.raw[3 * q]; y = W.raw[3 * q + 1]; yaw = W.raw[3 * q + 2]; }
-                else { x = poses[3 * i]; y = poses[3 * i + 1]; yaw = poses[3 * i + 2]; }
-                if (env_id && env_id[i] != e0) same_env = false;
+            for (int j = 0; j < K1_PER_THREAD; ++j) {
+                const int q = j * K1_THREADS + tid;
+                const long long i = base + q;
+                const bool active = i < n;
+                double x = 0.0, y = 0.0, yaw = 0.0;
+                if (active) {
+                    if (tma) { x = S.raw[3 * q]; y = S.raw[3 * q + 1]; yaw = S.raw[3 * q + 2]; }
+                    else { x = poses[3 * i]; y = poses[3 * i + 1]; yaw = poses[3 * i + 2]; }
+                    if (env_id && env_id[i] != e0) same_env = false;
+                }
+                const float px = (float)(x - ox), py = (float)(y - oy);
+                const bool beyond = fabsf(px) > reach || fabsf(py) > reach;
+                const bool far = !beyond && (!(fabs(yaw) < 1e6) || !(px == px) || !(py == py));
+                // the heading is reduced to [-pi, pi] in float64 (exact enough for any |yaw| < 1e6)
+                const double kk = rint(yaw * 0.15915494309189535);
+                S.px[q] = px; S.py[q] = py; S.yr[q] = (float)fma(-kk, 6.283185307179586, yaw);
+                unsigned char st = 0;
+                if (!active) st = K1S_OFF | K1S_DONE;
+                else if (beyond) st = K1S_DONE | (far_status(flags, D.n_seg) == HL_HIT ? K1S_HIT : 0) | K1S_OFF;   // no aux test either
+                else if (far) st = K1S_FAR;
+                S.st[q] = st;
+                S.amb[q] = 0;
             }
-            const float px = (float)(x - D.origin[0]), py = (float)(y - D.origin[1]);
-            const bool beyond = fabsf(px) > D.reach || fabsf(py) > D.reach;
-            const bool far = !beyond && (!(fabs(yaw) < 1e6) || !(px == px) || !(py == py));
-            // float32 sine / cosine for the filter: the angle is reduced to [-pi, pi] in float64 (exact enough for any
-            // |yaw| < 1e6), then the hardware approximations (abs. error 2^-21.4 there) -- an error of < 2e-6 m on
-            // a footprint corner, far inside the band eps
-            const double kk = rint(yaw * 0.15915494309189535);
-            const float yr = (float)fma(-kk, 6.283185307179586, yaw);
-            const float sf = __sinf(yr), cf = __cosf(yr);
-            W.pose[q] = make_float4(px, py, cf, sf);
-            unsigned char st = 0;
-            if (!active) st = K1S_OFF | K1S_DONE;
-            else if (beyond) st = K1S_DONE | (far_status(flags, D.n_seg) == HL_HIT ? K1S_HIT : 0) | K1S_OFF;   // no aux test either
-            else if (far) st = K1S_FAR;
-            W.st[q] = st;
-            W.amb[q] = 0;
         }
-        same_env = __all_sync(0xffffffffu, same_env);
-        __syncwarp();
-        if (tma || slice_tma(tile + gridDim.x)) {      // the landing zone is free again: fetch the next slice
-            if (lane == 0) fence_proxy_async();
-            issue_slice(tile + gridDim.x);
-        }
+        same_env = __syncthreads_and(same_env);        // also: every read of the landing zone is done
+        if (tid == 0) fence_proxy_async();
+        issue_tile(tile + gridDim.x);                  // fetch the next tile behind the filter stages
         if (!same_env) {
-            k1_slow_slice(eb, env_id, poses, pose_idx, n, base, flags, out, n_exact, lane);
+            k1_slow_slice(eb, env_id, poses, pose_idx, n, base + (long long)warp * K1_SLICE, flags, out, n_exact, lane);
             continue;
         }
         // ---- rectangles of the footprint: 0 = body (obstacles, field, lane), 1.. = implement rectangles (obstacles +
@@ -536,166 +508,117 @@ k_collision(EnvBatchDev eb, const int32_t* __restrict__ env_id, const double* __
             const unsigned rflags = rect == 0 ? flags : (flags & (HL_CHECK_OBSTACLES | HL_CHECK_BOUNDARY));
             const bool do_lane = rect == 0 && (flags & HL_CHECK_LANE) && E.n_seg > 0;
             const float rho = sqrtf(fmaf(R.hx, R.hx, R.hy * R.hy));
+            const float rho_eps = rho + E.eps;
             // ---- stage A: input list.  Body: every live pose, minus those the lane centre test rejects (cheapest
             // test, decides every pose far from the guide).  Implement: live poses at even path indices.
-            int n_a = 0;
 #pragma unroll 1
-            for (int j = 0; j < K1_PER_LANE; ++j) {
-                const int q = j * 32 + lane;
-                unsigned char st = W.st[q];
+            for (int j = 0; j < K1_PER_THREAD; ++j) {
+                const int q = j * K1_THREADS + tid;
+                unsigned char st = S.st[q];
                 bool live = !(st & (K1S_DONE | K1S_FAR));
                 if (rect > 0) {
                     const bool with_aux = !(st & (K1S_DONE | K1S_OFF)) && (pose_idx ? ((pose_idx[base + q] & 1) == 0) : true);
                     live = live && with_aux;
-                    W.amb[q] = (with_aux && (st & K1S_FAR)) ? (unsigned char)rflags : (unsigned char)0;
+                    S.amb[q] = (with_aux && (st & K1S_FAR)) ? (unsigned char)rflags : (unsigned char)0;
                 } else if (live && do_lane) {
-                    const int r = k1_lane_centre(E, R, W.pose[q], rho);
+                    const int r = k1_lane_centre(E, R, k1_pose(S, q), rho);
                     if (r == 1) { st |= K1S_HIT; live = false; }
                     else if (r == 2) st |= K1S_CORNERS;
-                    W.st[q] = st;
+                    S.st[q] = st;
                 }
-                n_a = warp_append(W.la, n_a, live, q, lane);
+                cta_append(S.la, &S.cnt[0], live, q, lane);
             }
-            __syncwarp();
-            const float rho_eps = rho + E.eps;
-            // ---- stage B: obstacles (la -> lb).  Pass 1 culls per pose to the obstacles within the circumradius, pass 2
-            // runs the separating-axis test on dense (pose, obstacle) pairs.
-            int n_b = 0;
+            __syncthreads();
+            const int n_a = S.cnt[0];
+            // ---- stage B: obstacles (la -> lb)
+            int n_b = n_a;
+            const unsigned short* lb = S.la;
             if (rflags & HL_CHECK_OBSTACLES) {
-                int n_pairs = 0;
-                auto process = [&](int np) {
-                    __syncwarp();
 #pragma unroll 1
-                    for (int t = lane; t < np; t += 32) {
-                        const unsigned pr = W.pairs[t];
-                        const int q = pr & 0xFF;
-                        bool hit, amb;
-                        k1_obstacle_one(E, R, W.pose[q], (int)(pr >> 8), hit, amb);
-                        if (hit) st_or(W.st, q, K1S_HIT);
-                        else if (amb) st_or(W.amb, q, HL_CHECK_OBSTACLES);
-                    }
-                };
-#pragma unroll 1
-                for (int k = 0; k < n_a; k += 32) {
+                for (int k = warp * 32; k < n_a; k += K1_THREADS) {
                     const int idx = k + lane;
                     const bool v = idx < n_a;
-                    const int q = v ? W.la[idx] : 0;
-                    const unsigned m = v ? k1_obstacle_mask(E, R, W.pose[q], rho_eps) : 0u;
-                    if (!k1_push_pairs(W, n_pairs, m, q, lane, process)) {       // > K1_PAIRS pairs in one chunk: per pose
-                        unsigned mm = m;
-                        while (mm) {
-                            const int ob = __ffs(mm) - 1;
-                            mm &= mm - 1;
-                            bool hit, amb;
-                            k1_obstacle_one(E, R, W.pose[q], ob, hit, amb);
-                            if (hit) W.st[q] |= K1S_HIT;
-                            else if (amb) W.amb[q] |= HL_CHECK_OBSTACLES;
-                        }
+                    const int q = v ? S.la[idx] : 0;
+                    bool hit = false, amb = false;
+                    if (v) {
+                        k1_obstacles(E, R, k1_pose(S, q), hit, amb);
+                        if (hit) S.st[q] |= K1S_HIT;
+                        else if (amb) S.amb[q] |= HL_CHECK_OBSTACLES;
                     }
+                    cta_append(S.lb, &S.cnt[1], v && !hit, q, lane);
                 }
-                process(n_pairs);
-                __syncwarp();
-#pragma unroll 1
-                for (int k = 0; k < n_a; k += 32) {
-                    const int idx = k + lane;
-                    const bool v = idx < n_a;
-                    const int q = v ? W.la[idx] : 0;
-                    n_b = warp_append(W.lb, n_b, v && !(W.st[q] & K1S_HIT), q, lane);
-                }
-            } else {
-                for (int k = lane; k < n_a; k += 32) W.lb[k] = W.la[k];
-                n_b = n_a;
+                __syncthreads();
+                n_b = S.cnt[1];
+                lb = S.lb;
             }
-            __syncwarp();
-            // ---- stages C + D: field polygon (lb -> survivors in lc; poses with nearby edges wait in la)
-            int n_c = 0;
+            // ---- stages C + D: field polygon (lb -> survivors in lc; poses with nearby edges wait in the third list)
+            int n_c = n_b;
+            const unsigned short* lc = lb;
             if (rflags & HL_CHECK_BOUNDARY) {
-                int n_d = 0, n_pairs = 0;
-                auto process = [&](int np) {
-                    __syncwarp();
+                unsigned short* pend = (lb == S.la) ? S.lb : S.la;
 #pragma unroll 1
-                    for (int t = lane; t < np; t += 32) {
-                        const unsigned pr = W.pairs[t];
-                        const int q = pr & 0xFF;
-                        const int r = k1_field2_one(E, R, W.pose[q], (int)(pr >> 8));
-                        if (r == 2) st_or(W.st, q, K1S_HIT);
-                        else if (r == 1) st_or(W.st, q, K1S_NOTCLEAR);
-                    }
-                };
-#pragma unroll 1
-                for (int k = 0; k < n_b; k += 32) {
+                for (int k = warp * 32; k < n_b; k += K1_THREADS) {
                     const int idx = k + lane;
                     const bool v = idx < n_b;
-                    const int q = v ? W.lb[idx] : 0;
+                    const int q = v ? lb[idx] : 0;
                     bool keep = false, need2 = false;
-                    unsigned nm = 0;
                     if (v) {
-                        bool inside;
-                        k1_field1(E, R, W.pose[q], rho_eps, nm, inside);
+                        unsigned nm; bool inside;
+                        k1_field1(E, R, k1_pose(S, q), rho_eps, nm, inside);
                         if (nm == 0) {                            // every edge clear: the parity of the centre decides
-                            if (inside) keep = true; else W.st[q] |= K1S_HIT;
+                            if (inside) keep = true; else S.st[q] |= K1S_HIT;
                         } else {
                             need2 = true;
-                            W.st[q] = (unsigned char)((W.st[q] & ~(K1S_INSIDE | K1S_NOTCLEAR)) | (inside ? K1S_INSIDE : 0));
+                            S.nearm[q] = nm;
+                            S.st[q] = (unsigned char)((S.st[q] & ~K1S_INSIDE) | (inside ? K1S_INSIDE : 0));
                         }
                     }
-                    n_c = warp_append(W.lc, n_c, keep, q, lane);
-                    n_d = warp_append(W.la, n_d, need2, q, lane);
-                    __syncwarp();
-                    if (!k1_push_pairs(W, n_pairs, nm, q, lane, process)) {
-                        while (nm) {
-                            const int ed = __ffs(nm) - 1;
-                            nm &= nm - 1;
-                            const int r = k1_field2_one(E, R, W.pose[q], ed);
-                            if (r == 2) W.st[q] |= K1S_HIT;
-                            else if (r == 1) W.st[q] |= K1S_NOTCLEAR;
-                        }
-                    }
+                    cta_append(S.lc, &S.cnt[2], keep, q, lane);
+                    cta_append(pend, &S.cnt[3], need2, q, lane);
                 }
-                process(n_pairs);
-                __syncwarp();
+                __syncthreads();
+                const int n_d = S.cnt[3];
 #pragma unroll 1
-                for (int k = 0; k < n_d; k += 32) {               // verdict of the poses that had nearby edges
+                for (int k = warp * 32; k < n_d; k += K1_THREADS) {
                     const int idx = k + lane;
                     const bool v = idx < n_d;
-                    const int q = v ? W.la[idx] : 0;
+                    const int q = v ? pend[idx] : 0;
                     bool keep = false;
                     if (v) {
-                        const unsigned char st = W.st[q];
-                        if (st & K1S_HIT) {}
-                        else if (st & K1S_NOTCLEAR) { keep = true; W.amb[q] |= HL_CHECK_BOUNDARY; }
-                        else if (st & K1S_INSIDE) keep = true;
-                        else W.st[q] = st | K1S_HIT;
+                        const unsigned char st = S.st[q];
+                        const int r = k1_field2(E, R, k1_pose(S, q), S.nearm[q], (st & K1S_INSIDE) != 0);
+                        if (r == HL_HIT) S.st[q] = st | K1S_HIT;
+                        else { keep = true; if (r == HL_AMBIG) S.amb[q] |= HL_CHECK_BOUNDARY; }
                     }
-                    n_c = warp_append(W.lc, n_c, keep, q, lane);
+                    cta_append(S.lc, &S.cnt[2], keep, q, lane);
                 }
-            } else {
-                for (int k = lane; k < n_b; k += 32) W.lc[k] = W.lb[k];
-                n_c = n_b;
+                __syncthreads();
+                n_c = S.cnt[2];
+                lc = S.lc;
             }
-            __syncwarp();
             // ---- stage E: lane corners of the body survivors that need them
             if (do_lane) {
 #pragma unroll 1
-                for (int k = 0; k < n_c; k += 32) {
+                for (int k = warp * 32; k < n_c; k += K1_THREADS) {
                     const int idx = k + lane;
                     if (idx < n_c) {
-                        const int q = W.lc[idx];
-                        if (W.st[q] & K1S_CORNERS) {
-                            const int r = k1_lane_corners(E, R, W.pose[q]);
-                            if (r == HL_HIT) W.st[q] |= K1S_HIT;
-                            else if (r == HL_AMBIG) W.amb[q] |= HL_CHECK_LANE;
+                        const int q = lc[idx];
+                        if (S.st[q] & K1S_CORNERS) {
+                            const int r = k1_lane_corners(E, R, k1_pose(S, q));
+                            if (r == HL_HIT) S.st[q] |= K1S_HIT;
+                            else if (r == HL_AMBIG) S.amb[q] |= HL_CHECK_LANE;
                         }
                     }
                 }
-                __syncwarp();
             }
+            __syncthreads();                               // every list and counter of this rectangle has been consumed
+            if (tid < 4) S.cnt[tid] = 0;
             // ---- float64 resolution of this rectangle; then "infeasible" becomes K1S_DONE | K1S_HIT
 #pragma unroll 1
-            for (int j = 0; j < K1_PER_LANE; ++j) {
-                const int q = j * 32 + lane;
-                unsigned char st = W.st[q];
-                const unsigned amb = (rect == 0 && (st & K1S_FAR)) ? rflags : (unsigned)W.amb[q];
+            for (int j = 0; j < K1_PER_THREAD; ++j) {
+                const int q = j * K1_THREADS + tid;
+                unsigned char st = S.st[q];
+                const unsigned amb = (rect == 0 && (st & K1S_FAR)) ? rflags : (unsigned)S.amb[q];
                 const bool need = !(st & (K1S_HIT | K1S_DONE)) && amb != 0;
                 if (__any_sync(0xffffffffu, need)) {        // rare: keep the call (and its spills) off the common path
                     const long long i = base + q;
@@ -706,25 +629,25 @@ k_collision(EnvBatchDev eb, const int32_t* __restrict__ env_id, const double* __
                     if (b2) st |= K1S_HIT;
                 }
                 if (st & K1S_HIT) st |= K1S_DONE;
-                W.st[q] = st;
-                W.amb[q] = 0;
+                S.st[q] = st;
+                S.amb[q] = 0;
             }
-            __syncwarp();
+            __syncthreads();
         }
-        // ---- verdicts: 4 poses per lane, one 32-bit store per lane when the output is aligned
+        // ---- verdicts: 4 consecutive poses per thread, one 32-bit store when the output is aligned
         if (base + K1_TILE <= n && ((reinterpret_cast<uintptr_t>(out) & 3) == 0)) {
-            const uchar4 s4 = *reinterpret_cast<const uchar4*>(&W.st[4 * lane]);
+            const uchar4 s4 = *reinterpret_cast<const uchar4*>(&S.st[4 * tid]);
             uchar4 o4;
             o4.x = s4.x & K1S_HIT; o4.y = s4.y & K1S_HIT; o4.z = s4.z & K1S_HIT; o4.w = s4.w & K1S_HIT;
-            *reinterpret_cast<uchar4*>(out + base + 4 * lane) = o4;
+            *reinterpret_cast<uchar4*>(out + base + 4 * tid) = o4;
         } else {
 #pragma unroll 1
-            for (int j = 0; j < K1_PER_LANE; ++j) {
-                const long long i = base + j * 32 + lane;
-                if (i < n) out[i] = (W.st[j * 32 + lane] & K1S_HIT) ? 1 : 0;
+            for (int j = 0; j < K1_PER_THREAD; ++j) {
+                const long long i = base + j * K1_THREADS + tid;
+                if (i < n) out[i] = (S.st[j * K1_THREADS + tid] & K1S_HIT) ? 1 : 0;
             }
         }
-        __syncwarp();
+        __syncthreads();                                   // S.st / lists are rewritten by the next tile
     }
 }
 
@@ -751,7 +674,7 @@ extern "C" int hl_collision_check(hl_ctx* ctx, const hl_env_batch* envs, const i
     const int smem_bytes = (int)sizeof(K1Cta);
     static_assert(sizeof(K1Cta) * K1_MIN_CTAS + 1024 * K1_MIN_CTAS <= 227 * 1024, "K1 shared memory exceeds the SM");
     HL_CUDA_OK(cudaFuncSetAttribute(k_collision, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    const long long tiles = (n + K1_CTA_TILE - 1) / K1_CTA_TILE;
+    const long long tiles = (n + K1_TILE - 1) / K1_TILE;
     const long long cap = (long long)ctx->sm_count * K1_MIN_CTAS;
     const int grid = (int)(tiles < cap ? tiles : cap);
     const int use_tma = (((uintptr_t)d_poses) & 15) == 0 ? 1 : 0;     // cp.async.bulk needs a 16-byte aligned source
