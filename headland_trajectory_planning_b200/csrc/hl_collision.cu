@@ -34,6 +34,14 @@
 #ifndef K1_MIN_CTAS
 #define K1_MIN_CTAS 4
 #endif
+#ifndef K1_UNROLL_OBS
+#define K1_UNROLL_OBS 2
+#endif
+#ifndef K1_UNROLL_FLD
+#define K1_UNROLL_FLD 2
+#endif
+#define K1_PRAGMA(x) _Pragma(#x)
+#define K1_UNROLL(n) K1_PRAGMA(unroll n)
 
 // ------------------------------------------------------------------ PTX: mbarrier + 1-D bulk copy (TMA)
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -165,7 +173,7 @@ __device__ __forceinline__ void k1_obstacles(const K1Env& E, const K1Rect& R, fl
     const float c = P.z, s = P.w;
     const float Cx = fmaf(c, R.mx, fmaf(-s, R.my, P.x)), Cy = fmaf(s, R.mx, fmaf(c, R.my, P.y));
     hit = false; amb = false;
-#pragma unroll 2
+    K1_UNROLL(K1_UNROLL_OBS)
     for (int k = 0; k < E.n_obs; ++k) {
         const float4 b0 = lds4(E.obs_a + HL_OBS32_STRIDE * k + 20);      // flag, cx, cy, ax
         const float4 b1 = lds4(E.obs_a + HL_OBS32_STRIDE * k + 24);      // ay, ha, hb, pad
@@ -191,7 +199,7 @@ __device__ __forceinline__ void k1_field1(const K1Env& E, const K1Rect& R, float
     const float c = P.z, s = P.w;
     const float Cx = fmaf(c, R.mx, fmaf(-s, R.my, P.x)), Cy = fmaf(s, R.mx, fmaf(c, R.my, P.y));
     unsigned nm = 0, par = 0;
-#pragma unroll 2
+    K1_UNROLL(K1_UNROLL_FLD)
     for (int i = 0; i < E.n_field; ++i) {
         const float4 f0 = lds4(E.fld_a + 8 * i);          // Ax, Ay, Ex, Ey   (Ay <= By)
         const float4 f1 = lds4(E.fld_a + 8 * i + 4);      // nx, ny, c, By
