@@ -28,7 +28,7 @@ __global__ void k_df_init(const uint8_t* __restrict__ occ, int W, int H, int gi,
     if (idx >= (long long)W * H) return;
     int i = (int)(idx / H), j = (int)(idx % H);
     out[idx] = (i == gi && j == gj) ? 0.0 : INFINITY;
-    if ((i == 0 || j == 0 || i == W - 1 || j == H - 1) && !occ[idx]) atomicOr(bad, 1);   // open border: wrap quirk reachable
+    if ((i == 0 || j == 0 || i == W - 1 || j == H - 1) && !occ[idx]) atomicOr(bad, 1);   // open border: aliases reachable
     if (i == gi && j == gj) {
         int ti = i / DF_TILE, tj = j / DF_TILE;
         for (int a = -1; a <= 1; ++a)
@@ -116,14 +116,116 @@ k_df_relax(const uint8_t* __restrict__ occ, int W, int H, int gi, int gj, DfMove
     }
 }
 
+// ---- the reference's index wrap-around (a_star_utils.py:49-64) --------------------------------------------
+// Validity is `abs(index) < dim` and obstacles[i][j] is read with Python's negative indexing, so the reference
+// really searches the EXTENDED grid of nodes (i, j), -W < i < W, -H < j < H, whose occupancy is the map's at
+// (i mod W, j mod H); every closed node writes holonomicCost[i][j] (again with negative indexing) in closing order,
+// so a map cell ends up with the cost of its LAST-closed alias.  Nodes close in the order of their heap entries
+// (priority at push time, index tuple) -- there is no decrease-key (:131), so the priority of a node is the cost
+// offered by its FIRST-closed neighbour, not its final cost.  All of it has a relaxation-order-free form:
+//   C = least fixed point of the cost relaxation on the extended grid            (k_df_relax, as for closed maps)
+//   P(v) = C(u*) + w(u* -> v),  u* = the neighbour of v with the smallest (P(u), i_u, j_u)      (fixed point, k_df_prio)
+//   out[cell] = C(alias of the cell with the largest (P, i, j))                                   (k_df_fold)
+// oracle/distance_field.py (pinned bit-for-bit on the reference) agrees on every tested grid
+// (tests/test_grid_gpu.py::test_wrap_around_quirk_matches_reference).
+__global__ void k_df_ext_occ(const uint8_t* __restrict__ occ, int W, int H, uint8_t* __restrict__ eocc) {
+    const int EW = 2 * W - 1, EH = 2 * H - 1;
+    long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (idx >= (long long)EW * EH) return;
+    const int a = (int)(idx / EH), b = (int)(idx % EH);
+    const int i = a - (W - 1), j = b - (H - 1);
+    eocc[idx] = occ[(long long)(i < 0 ? i + W : i) * H + (j < 0 ? j + H : j)];
+}
+
+__global__ void k_df_prio(const double* __restrict__ C, const double* __restrict__ Pin, double* __restrict__ Pout,
+                          int EW, int EH, DfMoves mv, int ga, int gb, int* __restrict__ changed) {
+    long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (idx >= (long long)EW * EH) return;
+    const int a = (int)(idx / EH), b = (int)(idx % EH);
+    double np_ = INFINITY;
+    if (a == ga && b == gb) np_ = 0.0;
+    else if (C[idx] < INFINITY) {
+        double bp = INFINITY; int ba = 0x7fffffff, bb = 0x7fffffff;
+        for (int m = 0; m < mv.n; ++m) {
+            const int ua = a - mv.di[m], ub = b - mv.dj[m];
+            if (ua < 0 || ub < 0 || ua >= EW || ub >= EH) continue;
+            const long long u = (long long)ua * EH + ub;
+            const double cu = C[u];
+            if (!(cu < INFINITY)) continue;
+            const double pu = Pin[u];
+            if (pu < bp || (pu == bp && (ua < ba || (ua == ba && ub < bb)))) { bp = pu; ba = ua; bb = ub; np_ = __dadd_rn(cu, mv.w[m]); }
+        }
+    }
+    if (np_ != Pin[idx]) *changed = 1;
+    Pout[idx] = np_;
+}
+
+__global__ void k_df_fold(const double* __restrict__ C, const double* __restrict__ P, int W, int H, double* __restrict__ out) {
+    long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (idx >= (long long)W * H) return;
+    const int ci = (int)(idx / H), cj = (int)(idx % H);
+    const int EH = 2 * H - 1;
+    double best_c = INFINITY, best_p = -INFINITY;
+    int best_i = -0x7fffffff, best_j = -0x7fffffff;
+    for (int ai = 0; ai < 2; ++ai) {
+        if (ai == 1 && ci < 1) continue;
+        const int i = ai == 0 ? ci : ci - W;
+        for (int aj = 0; aj < 2; ++aj) {
+            if (aj == 1 && cj < 1) continue;
+            const int j = aj == 0 ? cj : cj - H;
+            const long long v = (long long)(i + W - 1) * EH + (j + H - 1);
+            const double c = C[v];
+            if (!(c < INFINITY)) continue;
+            const double p = P[v];
+            if (p > best_p || (p == best_p && (i > best_i || (i == best_i && j > best_j)))) { best_p = p; best_i = i; best_j = j; best_c = c; }
+        }
+    }
+    out[idx] = best_c;
+}
+
+// Tiled wavefront to the fixed point on a w x h grid (cells outside count as occupied).  *open_border is set when
+// a border cell is free (only when `open_border` is given; nothing is relaxed then).
+static int df_solve(const uint8_t* d_occ, int w, int h, int gi, int gj, const DfMoves& mv, double* d_out,
+                    cudaStream_t st, int* open_border, int* sweeps_out) {
+    const int tiles_i = (w + DF_TILE - 1) / DF_TILE, tiles_j = (h + DF_TILE - 1) / DF_TILE;
+    const int n_tiles = tiles_i * tiles_j;
+    unsigned char* dirty = nullptr;
+    int* flags = nullptr;
+    HL_CUDA_OK(cudaMalloc(&dirty, 2 * (size_t)n_tiles));
+    if (cudaMalloc(&flags, 2 * sizeof(int)) != cudaSuccess) { cudaFree(dirty); hl_set_error("hl_distance_field: cudaMalloc failed"); return 1; }
+    int rc = 0, sweeps = 0;
+    do {
+        if (cudaMemsetAsync(dirty, 0, 2 * (size_t)n_tiles, st) != cudaSuccess || cudaMemsetAsync(flags, 0, 2 * sizeof(int), st) != cudaSuccess) { rc = 1; break; }
+        long long cells = (long long)w * h;
+        k_df_init<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(d_occ, w, h, gi, gj, d_out, dirty, tiles_i, tiles_j, flags);
+        int host_flags[2] = {0, 0};
+        if (cudaMemcpyAsync(host_flags, flags, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) { rc = 1; break; }
+        if (open_border) { *open_border = host_flags[0]; if (host_flags[0]) break; }
+        unsigned char* cur = dirty;
+        unsigned char* nxt = dirty + n_tiles;
+        const int max_sweeps = 8 * (tiles_i + tiles_j) * DF_TILE + 64;
+        while (sweeps < max_sweeps) {
+            cudaMemsetAsync(nxt, 0, n_tiles, st);
+            cudaMemsetAsync(flags + 1, 0, sizeof(int), st);
+            k_df_relax<<<n_tiles, DF_THREADS, 0, st>>>(d_occ, w, h, gi, gj, mv, d_out, cur, nxt, tiles_i, tiles_j, flags + 1);
+            ++sweeps;
+            if (cudaMemcpyAsync(host_flags + 1, flags + 1, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) { rc = 1; break; }
+            if (!host_flags[1]) break;
+            unsigned char* t = cur; cur = nxt; nxt = t;
+        }
+        if (rc == 0 && sweeps >= max_sweeps) { hl_set_error("hl_distance_field: no convergence after %d launches", sweeps); rc = 2; }
+    } while (0);
+    if (rc == 1) hl_set_error("hl_distance_field: CUDA error: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(dirty); cudaFree(flags);
+    if (sweeps_out) *sweeps_out += sweeps;
+    return rc;
+}
+
 extern "C" int hl_distance_field(hl_ctx* ctx, const uint8_t* d_occ, int32_t w, int32_t h, int32_t gi,
                                  int32_t gj, int32_t motion_type, double* d_out, int32_t* h_sweeps,
                                  void* stream) {
-    if (!ctx || !d_occ || !d_out || w < 3 || h < 3) { hl_set_error("hl_distance_field: bad arguments"); return 1; }
-    if (gi <= 0 || gj <= 0 || gi >= w - 1 || gj >= h - 1) {
-        hl_set_error("hl_distance_field: goal (%d,%d) must be strictly inside the occupied border", gi, gj);
-        return 1;
-    }
+    if (!ctx || !d_occ || !d_out || w < 1 || h < 1) { hl_set_error("hl_distance_field: bad arguments"); return 1; }
+    if (gi < 0 || gj < 0 || gi >= w || gj >= h) { hl_set_error("hl_distance_field: goal (%d,%d) outside the %dx%d grid", gi, gj, w, h); return 1; }
     if (hl_enter(ctx, nullptr, d_out, "hl_distance_field")) return 1;
     cudaStream_t st = (cudaStream_t)stream;
     DfMoves mv;
@@ -137,44 +239,52 @@ extern "C" int hl_distance_field(hl_ctx* ctx, const uint8_t* d_occ, int32_t w, i
         mv.n = 5;
         for (int m = 0; m < 5; ++m) { mv.di[m] = k[m][0]; mv.dj[m] = k[m][1]; mv.w[m] = hypot((double)k[m][0], (double)k[m][1]); }
     } else { hl_set_error("hl_distance_field: motion_type must be 0 (King) or 1 (Pawn)"); return 1; }
-    const int tiles_i = (w + DF_TILE - 1) / DF_TILE, tiles_j = (h + DF_TILE - 1) / DF_TILE;
-    const int n_tiles = tiles_i * tiles_j;
-    unsigned char* dirty = nullptr;
-    int* flags = nullptr;
-    HL_CUDA_OK(cudaMalloc(&dirty, 2 * (size_t)n_tiles));
-    HL_CUDA_OK(cudaMalloc(&flags, 2 * sizeof(int)));
-    HL_CUDA_OK(cudaMemsetAsync(dirty, 0, 2 * (size_t)n_tiles, st));
-    HL_CUDA_OK(cudaMemsetAsync(flags, 0, 2 * sizeof(int), st));
-    long long cells = (long long)w * h;
-    k_df_init<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(d_occ, w, h, gi, gj, d_out, dirty, tiles_i, tiles_j, flags);
-    int host_flags[2] = {0, 0};
-    HL_CUDA_OK(cudaMemcpyAsync(host_flags, flags, sizeof(int), cudaMemcpyDeviceToHost, st));
-    HL_CUDA_OK(cudaStreamSynchronize(st));
-    if (host_flags[0]) {
-        cudaFree(dirty); cudaFree(flags);
-        hl_set_error("hl_distance_field: the grid border is not fully occupied; the reference's index wrap-around "
-                     "(a_star_utils.py:54-61) would be reachable and is not reproduced");
+    int sweeps = 0;
+    // fast path: every border cell occupied and the goal strictly inside -> no alias is reachable, the map itself is
+    // the whole search space
+    if (w >= 3 && h >= 3 && gi > 0 && gj > 0 && gi < w - 1 && gj < h - 1) {
+        int open_border = 0;
+        const int rc = df_solve(d_occ, w, h, gi, gj, mv, d_out, st, &open_border, &sweeps);
+        if (rc) return 1;
+        if (!open_border) { if (h_sweeps) *h_sweeps = sweeps; return 0; }
+    }
+    // general path: the extended grid of the reference's index wrap-around
+    const int EW = 2 * w - 1, EH = 2 * h - 1;
+    const long long ecells = (long long)EW * EH;
+    uint8_t* eocc = nullptr;
+    double* buf = nullptr;                   // C | P0 | P1
+    int* changed = nullptr;
+    if (cudaMalloc(&eocc, (size_t)ecells) != cudaSuccess || cudaMalloc(&buf, 3 * sizeof(double) * (size_t)ecells) != cudaSuccess ||
+        cudaMalloc(&changed, sizeof(int)) != cudaSuccess) {
+        if (eocc) cudaFree(eocc);
+        if (buf) cudaFree(buf);
+        hl_set_error("hl_distance_field: cudaMalloc failed for the %dx%d extended grid", EW, EH);
         return 1;
     }
-    unsigned char* cur = dirty;
-    unsigned char* nxt = dirty + n_tiles;
-    int sweeps = 0;
-    const int max_sweeps = 8 * (tiles_i + tiles_j) * DF_TILE + 64;
-    while (sweeps < max_sweeps) {
-        HL_CUDA_OK(cudaMemsetAsync(nxt, 0, n_tiles, st));
-        HL_CUDA_OK(cudaMemsetAsync(flags + 1, 0, sizeof(int), st));
-        k_df_relax<<<n_tiles, DF_THREADS, 0, st>>>(d_occ, w, h, gi, gj, mv, d_out, cur, nxt, tiles_i, tiles_j, flags + 1);
-        ++sweeps;
-        HL_CUDA_OK(cudaMemcpyAsync(host_flags + 1, flags + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
-        HL_CUDA_OK(cudaStreamSynchronize(st));
-        if (!host_flags[1]) break;
-        unsigned char* t = cur; cur = nxt; nxt = t;
-    }
-    HL_CUDA_OK(cudaGetLastError());
-    cudaFree(dirty); cudaFree(flags);
+    double* C = buf; double* P0 = buf + ecells; double* P1 = buf + 2 * ecells;
+    const unsigned eblocks = (unsigned)((ecells + 255) / 256);
+    int rc = 0;
+    do {
+        k_df_ext_occ<<<eblocks, 256, 0, st>>>(d_occ, w, h, eocc);
+        if (df_solve(eocc, EW, EH, gi + w - 1, gj + h - 1, mv, C, st, nullptr, &sweeps)) { rc = 1; break; }
+        if (cudaMemcpyAsync(P0, C, sizeof(double) * (size_t)ecells, cudaMemcpyDeviceToDevice, st) != cudaSuccess) { rc = 2; break; }
+        int it = 0, h_changed = 1;
+        while (h_changed && it < 4 * (EW + EH)) {
+            cudaMemsetAsync(changed, 0, sizeof(int), st);
+            k_df_prio<<<eblocks, 256, 0, st>>>(C, P0, P1, EW, EH, mv, gi + w - 1, gj + h - 1, changed);
+            if (cudaMemcpyAsync(&h_changed, changed, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) { rc = 2; break; }
+            double* t = P0; P0 = P1; P1 = t;
+            ++it; ++sweeps;
+        }
+        if (rc) break;
+        if (h_changed) { hl_set_error("hl_distance_field: closing-order priorities did not converge"); rc = 1; break; }
+        k_df_fold<<<(unsigned)(((long long)w * h + 255) / 256), 256, 0, st>>>(C, P0, w, h, d_out);
+        if (cudaStreamSynchronize(st) != cudaSuccess) { rc = 2; break; }
+    } while (0);
+    if (rc == 2) hl_set_error("hl_distance_field: CUDA error: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(eocc); cudaFree(buf); cudaFree(changed);
     if (h_sweeps) *h_sweeps = sweeps;
-    if (sweeps >= max_sweeps) { hl_set_error("hl_distance_field: no convergence after %d launches", sweeps); return 1; }
-    return 0;
+    return rc ? 1 : 0;
 }
 
 // ------------------------------------------------------------------------- K7

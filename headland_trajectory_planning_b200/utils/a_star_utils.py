@@ -16,7 +16,9 @@ def forward_holonomic_motion_commands():
 
 
 def holonomic_costs_with_obstacles(goal_index, obstacles, motion_type="King"):
-    """a_star_utils.py:75-142.  Grids whose border is not fully occupied would trigger the
-    reference's index wrap-around (:54-61); those raise instead of returning different numbers."""
+    """a_star_utils.py:75-142, INCLUDING the reference's index wrap-around on grids whose border is not fully
+    occupied (validity is ``abs(index) < dim`` and the occupancy / cost arrays are read and written with Python's
+    negative indexing, :49-64,138-140): e.g. a free 8 x 8 grid with goal (1, 1) returns 11.3137... at the goal cell,
+    like the reference does.  ``hl_distance_field`` detects the open border and runs the extended-grid formulation."""
     out, _ = ops.distance_field(np.asarray(obstacles), goal_index, motion_type)
     return out.cpu().numpy()

@@ -284,13 +284,16 @@ int64_t hl_hybrid_astar_workspace_bytes(const hl_ctx* ctx, const HlSearchParams*
 int hl_astar_phase_cycles(hl_ctx* ctx, uint64_t* h_out, int32_t n, int32_t reset);
 
 /* ---- K6 grid distance field ---------------------------------------------------
- * Replaces holonomic_costs_with_obstacles (path_planner/utils/a_star_utils.py:75-142)
- * on grids whose border cells are occupied (the reference's index wrap-around quirk,
- * :54-61, is unreachable there; otherwise returns an error).
+ * Replaces holonomic_costs_with_obstacles (path_planner/utils/a_star_utils.py:75-142), the reference's index
+ * wrap-around included (:49-64: validity is abs(index) < dim and the arrays are indexed with Python's negative
+ * indices, so on a map with free border cells the search continues onto aliased cells and a cell reports the cost
+ * of its last-closed alias -- e.g. 11.31 at the goal of a free 8 x 8 grid).  Maps whose border is occupied take
+ * the plain tiled wavefront; any other map runs the same wavefront on the (2W-1) x (2H-1) extended grid plus the
+ * closing-order pass (csrc/hl_grid.cu).  Results are bit-identical to the reference in float64.
  *   d_occ [W][H] uint8 (non-zero = occupied), row-major like obstacles[i][j]
  *   d_out [W][H] float64, +inf where unreachable
  *   motion_type 0 = King (8 moves, :8-21), 1 = Pawn (5 moves, :24-34)
- *   h_sweeps optional host int: relaxation rounds used (synchronises the stream)       */
+ *   h_sweeps optional host int: relaxation launches used.  Synchronises the stream.                    */
 int hl_distance_field(hl_ctx* ctx, const uint8_t* d_occ, int32_t w, int32_t h, int32_t gi,
                       int32_t gj, int32_t motion_type, double* d_out, int32_t* h_sweeps,
                       void* stream);

@@ -22,11 +22,37 @@ def test_distance_field_bit_exact(built_library, n, motion):
     assert np.isfinite(want).sum() > n
 
 
-def test_distance_field_rejects_open_border(built_library):
-    from headland_trajectory_planning_b200 import HeadlandError
+def test_wrap_around_quirk_matches_reference(built_library):
+    """Grids with free border cells: the reference's index wrap-around (a_star_utils.py:49-64) is reproduced -- the
+    oracle port is pinned bit for bit on the reference's own module, known answers included: a free 8 x 8 grid with
+    goal (1, 1) gives 11.3137... AT THE GOAL CELL in King mode and an all-inf column 0 in Pawn mode."""
     from headland_trajectory_planning_b200.utils import a_star_utils
-    with pytest.raises(HeadlandError):
-        a_star_utils.holonomic_costs_with_obstacles((1, 1), np.zeros((8, 8), dtype=bool), "King")
+    free = np.zeros((8, 8), dtype=bool)
+    king = a_star_utils.holonomic_costs_with_obstacles((1, 1), free, "King")
+    assert np.array_equal(king, DF.holonomic_costs_with_obstacles((1, 1), free, "King"))
+    assert abs(king[1, 1] - 8 * math.sqrt(2.0)) < 1e-12
+    pawn = a_star_utils.holonomic_costs_with_obstacles((1, 1), free, "Pawn")
+    assert np.array_equal(pawn, DF.holonomic_costs_with_obstacles((1, 1), free, "Pawn"))
+    assert np.isinf(pawn[:, 0]).all()
+    rng = np.random.default_rng(0)
+    for _ in range(60):
+        n, m = int(rng.integers(3, 40)), int(rng.integers(3, 40))
+        occ = rng.random((n, m)) < rng.choice([0.0, 0.1, 0.25])
+        cells = np.argwhere(~occ) if rng.random() < 0.8 else np.argwhere(np.ones_like(occ))    # sometimes an occupied goal
+        g = tuple(int(v) for v in cells[rng.integers(len(cells))])
+        for motion in ("King", "Pawn"):
+            want = DF.holonomic_costs_with_obstacles(g, occ, motion)
+            got = a_star_utils.holonomic_costs_with_obstacles(g, occ, motion)
+            assert np.array_equal(want, got), (n, m, g, motion)
+    # a half-open map (two occupied sides) and a closed border with the goal ON the border
+    occ, goal = DF.synthetic_grid(96, seed=3)
+    occ[0, :] = False
+    occ[:, -1] = False
+    assert np.array_equal(DF.holonomic_costs_with_obstacles(goal, occ, "King"),
+                          a_star_utils.holonomic_costs_with_obstacles(goal, occ, "King"))
+    occ, _ = DF.synthetic_grid(64, seed=5)
+    assert np.array_equal(DF.holonomic_costs_with_obstacles((0, 10), occ, "King"),
+                          a_star_utils.holonomic_costs_with_obstacles((0, 10), occ, "King"))
 
 
 def test_distance_field_properties_full_size(built_library):

@@ -4,8 +4,17 @@ import numpy as np, torch
 from headland_trajectory_planning_b200 import ops, scenarios as SC, sweep
 from headland_trajectory_planning_b200.env_batch import EnvBatch
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
-scns = SC.make_scenarios_gpu(list(range(n)))
-recs, scen, car = sweep.build_records(scns)
+import pickle
+cache = f"/tmp/hl_k4_scen_{n}.pkl"            # scenario construction takes ~10 s: reuse it across variant builds
+if os.path.exists(cache):
+    recs, scen, car = pickle.load(open(cache, "rb"))
+else:
+    scns = SC.make_scenarios_gpu(list(range(n)))
+    recs, scen, car = sweep.build_records(scns)
+    try:
+        pickle.dump((recs, scen, car), open(cache, "wb"))
+    except Exception:
+        pass
 envs = EnvBatch(recs)
 params = sweep.search_params(car)
 d_scen = torch.from_numpy(scen.view(np.uint8).reshape(-1)).cuda()
