@@ -163,6 +163,30 @@ def gen_astar(n):
     print("astar_golden.npz:", n, "scenarios; counters", [r["counter"] for r in res][:20], "...")
 
 
+def gen_astar_full(n):
+    """Compact golden for ALL scenarios of the benchmarked sweep (bench.py: config 5, 0..n-1): the discrete outcome of
+    every search -- status, counter, number of expanded nodes, CRC-32 of the expanded-key sequence (int32 [k, 3]
+    bytes), path length, the oracle's pose-check tally -- plus two float64 checksums of the path (sum of x, sum of
+    y).  tests/test_astar_gpu.py::test_full_sweep_golden compares the GPU sweep with it scenario by scenario."""
+    import multiprocessing as mp
+    import zlib
+    with mp.get_context("fork").Pool(os.cpu_count()) as pool:
+        res = pool.map(_astar_one, range(n), chunksize=4)
+    status_code = {"ok": 0, "start_goal_blocked": 1, "open_empty": 2, "max_nodes": 3}
+    np.savez_compressed(
+        os.path.join(GOLD, "astar_full_golden.npz"),
+        status=np.array([status_code[r["status"]] for r in res], dtype=np.int8),
+        counter=np.array([r["counter"] for r in res], dtype=np.int32),
+        n_expanded=np.array([len(r["expanded"]) for r in res], dtype=np.int32),
+        keys_crc=np.array([zlib.crc32(np.ascontiguousarray(r["expanded"], dtype=np.int32).tobytes()) for r in res], dtype=np.uint32),
+        path_len=np.array([len(r["x"]) for r in res], dtype=np.int32),
+        path_sum=np.array([[np.sum(r["x"]), np.sum(r["y"])] for r in res], dtype=np.float64),
+        feas_crc=np.array([zlib.crc32(np.packbits(r["feas"]).tobytes()) for r in res], dtype=np.uint32),
+        goal=np.array([r["goal"] for r in res]),
+        pose_checks_ref=np.array([r["stats"]["rs_poses"] + r["stats"]["primitive_poses"] for r in res], dtype=np.int64))
+    print("astar_full_golden.npz:", n, "scenarios; status histogram", np.bincount([status_code[r["status"]] for r in res]))
+
+
 YPARK_PARAM_SETS = [
     # (max_steer_backward, max_steer_forward, max_backward_distance, max_forward_distance,
     #  min_forward_distance, min_backward_distance, min_steer_backward, min_steer_forward, step)
@@ -341,6 +365,8 @@ if __name__ == "__main__":
         gen_df()
     if "astar" in args:
         gen_astar(int(args[args.index("astar") + 1]))
+    if "astar_full" in args:
+        gen_astar_full(int(args[args.index("astar_full") + 1]))
     if "astar_ref" in args:
         gen_astar_ref(int(args[args.index("astar_ref") + 1]))
     if "refpath" in args:

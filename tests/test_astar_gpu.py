@@ -179,3 +179,55 @@ def test_level_variant_sub_batches(built_library, monkeypatch):
         assert np.array_equal(a["results"][f], b["results"][f]), f
     for i in (0, 5000, 8191, 8192, len(big) - 1):
         assert np.array_equal(ops.expanded_of(a, i), ops.expanded_of(b, i))
+
+
+def _sweep_4096():
+    from headland_trajectory_planning_b200 import ops, scenarios as SC, sweep
+    from headland_trajectory_planning_b200.env_batch import EnvBatch
+    n = 4096
+    scns = SC.make_scenarios_gpu(list(range(n)))
+    recs, scen, car = sweep.build_records(scns)
+    envs = EnvBatch(recs)
+    params = sweep.search_params(car)
+    return scns, envs, scen, params, lambda: ops.hybrid_astar_batch(envs, scen, params, path_capacity=1024 * n)
+
+
+def test_full_sweep_golden_and_determinism(built_library):
+    """The BENCHMARKED workload itself -- config 5, scenarios 0..4095 in one launch (bench.py) -- against the oracle's
+    compact golden (tests/golden/astar_full_golden.npz, generator ``oracle/gen_golden.py astar_full``): the goal
+    pose (= Y-park feasibility booleans), status, counter, expanded-node count, CRC-32 of the whole expanded-key
+    sequence, path length, the algorithmic pose-check tally and two path checksums of EVERY scenario.  Then the
+    sweep is run again: records, key sequences and paths must be bit-identical run to run (the executed-work
+    counters n_pose_checks / n_exact / cycles depend on how the two roles of a scenario interleave and are exempt)."""
+    import os
+    import zlib
+    from headland_trajectory_planning_b200 import ops
+    from headland_trajectory_planning_b200.hybrid_a_star_search import unpack_path
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "astar_full_golden.npz"))
+    scns, envs, scen, params, run = _sweep_4096()
+    n = len(scns)
+    assert np.array_equal(np.array([s["goal"] for s in scns]), g["goal"])
+    a = run()
+    res = a["results"]
+    assert np.array_equal(res["status"], g["status"])
+    assert np.array_equal(res["counter"], g["counter"])
+    assert np.array_equal(res["n_expanded"], g["n_expanded"])
+    assert np.array_equal(res["path_len"], g["path_len"])
+    crc = np.array([zlib.crc32(np.ascontiguousarray(ops.expanded_of(a, i)).tobytes()) for i in range(n)], dtype=np.uint32)
+    bad = np.nonzero(crc != g["keys_crc"])[0]
+    assert len(bad) == 0, f"expanded-key sequences differ for {len(bad)} scenarios: {bad[:10]}"
+    sums = np.zeros((n, 2))
+    for i in range(n):
+        o, l = int(res["path_offset"][i]), int(res["path_len"][i])
+        sums[i] = [a["x"][o:o + l].sum(), a["y"][o:o + l].sum()]
+    np.testing.assert_allclose(sums, g["path_sum"], rtol=1e-9, atol=1e-6)
+    sel = (res["status"] != 1) & (res["arrival"] != 2)
+    assert np.array_equal(res["n_pose_checks_ref"][sel], g["pose_checks_ref"][sel])
+    # run-to-run determinism of everything the caller consumes
+    b = run()
+    for f in ("status", "counter", "n_expanded", "arrival", "path_len", "rs_word", "goal_cost", "n_pose_checks_ref"):
+        assert np.array_equal(res[f], b["results"][f]), f
+    for i in range(n):
+        assert np.array_equal(ops.expanded_of(a, i), ops.expanded_of(b, i))
+        if res["path_len"][i]:
+            assert unpack_path(a, i) == unpack_path(b, i)

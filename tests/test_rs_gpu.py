@@ -169,3 +169,34 @@ def test_rs_sweep_config3_full_size(built_library):
             np.testing.assert_allclose(w["len"][a_i, k, :len(p.lengths)], p.lengths, rtol=RTOL, atol=1e-9)
             want = not o_env.check_path_feasibility(o_car, np.array([p.x, p.y, p.yaw]).T, boundary_check=False)
             assert bool(w["collide"][a_i, k]) == want, (i, k)
+
+
+def test_config1_fishtail_notebook_case(built_library):
+    """BASELINE config 1 = test/classic_planner.ipynb cells 3-4, 6, 10-11 through the CUDA path: the notebook orchard
+    (np.random.seed(1), l_std = 1.0), the fish-tail Reeds-Shepp query between the safe start / end poses, every word
+    checked with boundary_check=False -> exactly one feasible word, an R-L-R (cell 11 stdout).  Both ways a caller
+    can do it: hl_rs_all_paths with the environment (per-word collision flag), and calc_all_paths +
+    check_path_feasibility like the notebook."""
+    import math
+    import numpy as np
+    import hl_helpers as H
+    from headland_trajectory_planning_b200 import ops
+    from headland_trajectory_planning_b200.utils import reeds_shepp as rs_curves
+    rows = H.canonical_rows(l_std=1.0)
+    (o_env, o_car, _), (g_env, g_car, _) = H.make_pair(rows, axle_to_front=2.85)
+    sx = -1.30805046
+    sg = np.array([[sx, 3.75, math.pi, sx, 8.75, 0.0]])
+    envs = g_env._env_batch(g_car)
+    words, count, _ = ops.rs_all_paths(sg, g_car.curvature, 0.1, envs=envs, flags=ops.CHECK_OBSTACLES)
+    w = ops.rs_words_to_host(words)[0][:int(count[0].item())]
+    letters = ["".join(rs_curves.row_letters(int(c))) for c in w["cand"]]
+    assert letters == ["LRL", "RLR", "RLR"]
+    assert [l for l, c in zip(letters, w["collide"]) if not c] == ["RLR"]
+    feas = []
+    for p in rs_curves.calc_all_paths(sx, 3.75, math.pi, sx, 8.75, 0.0, g_car.curvature, 0.1):
+        traj = np.array([p.x, p.y, p.yaw]).T
+        ok = g_env.check_path_feasibility(g_car, traj, boundary_check=False)
+        assert ok == o_env.check_path_feasibility(o_car, traj, boundary_check=False)
+        if ok:
+            feas.append("".join(p.ctypes))
+    assert feas == ["RLR"]
