@@ -236,6 +236,30 @@ def main():
     max_ms = float(t.item())
     value = total * args.steps / (max_ms * 1e-3)
 
+    # strong scaling (N > 1 only): the SAME 4096 scenarios split over the N ranks; every rank searches the first
+    # 4096 / N scenarios of its interleaved shard.  One 401-pop scenario alone takes ~15 ms, so this cannot scale
+    # like the weak run: the floor is the latency of the slowest scenario, and the line says so.
+    strong = None
+    if world > 1:
+        m = max(1, args.scenarios_per_gpu // world)
+        d_sub = d_scen[: m * _lib.SCENARIO_DTYPE.itemsize]
+        for _ in range(2):
+            ops.hybrid_astar_batch(envs, d_sub, params, path_capacity=path_cap, to_host=False)
+        barrier()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for s in range(args.steps):
+            flush.fill_(s & 0xFF)
+            evs[s][0].record()
+            ops.hybrid_astar_batch(envs, d_sub, params, path_capacity=path_cap, to_host=False)
+            evs[s][1].record()
+        barrier()
+        ts = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], dtype=torch.float64, device=dev)
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        strong = {"scaling": "strong", "total_scenarios": m * world, "scenarios_per_gpu": m,
+                  "ms_per_step": float(ts.item()) / args.steps, "value": m * world * args.steps / (float(ts.item()) * 1e-3),
+                  "unit": UNIT, "floor": "one max_nodes scenario alone on a GPU takes ~15 ms (profiles/r2g_k4_tail_regime.txt): "
+                                         "with the sweep's 546 such scenarios the step time cannot drop below that however many GPUs share them"}
+
     res = out["results"].cpu().numpy().view(_lib.RESULT_DTYPE)
     flops = sweep.algorithmic_flops(recs, res)                              # reference-equivalent checks x F_check
     flops_exec = sweep.algorithmic_flops(recs, res, field="n_pose_checks")   # what the kernel actually executed
@@ -298,6 +322,8 @@ def main():
     ypark = None
     rs_sweep = None
     refpath = None
+    dfield = None
+    single = None
     fp32_peak = None
     if rank == 0:
         fp32_peak = ops.measure_fp32_peak(local_rank)
@@ -308,6 +334,8 @@ def main():
         ypark = ypark_microbench(args, dev, world == 1 and not args.no_cpu_baseline)
         rs_sweep = rs_microbench(args, dev, world == 1 and not args.no_cpu_baseline)
         refpath = refpath_microbench(out, car.WHEEL_BASE, world == 1 and not args.no_cpu_baseline)
+        dfield = distance_field_microbench(dev, world == 1 and not args.no_cpu_baseline)
+        single = single_scenario_microbench(dev)
 
     # ---------------- CPU baseline (rank 0, N = 1 only)
     cpu = None
@@ -349,13 +377,16 @@ def main():
                                  "(SURVEY 8d); executed_frac counts only the checks the kernel ran after its early "
                                  "exits; peak = FFMA micro-benchmark measured in this run; the kernel is a "
                                  "latency-bound search, see kernels.k_collision for the ALU-bound kernel"},
-            "kernels": {"k_collision": coll, "k_collision_path_ordered": coll_paths, "ypark_sweep": ypark, "rs_sweep": rs_sweep, "ref_path": refpath},
+            "kernels": {"k_collision": coll, "k_collision_path_ordered": coll_paths, "ypark_sweep": ypark, "rs_sweep": rs_sweep, "ref_path": refpath,
+                        "distance_field": dfield, "single_scenario": single},
             "search": {"expansions": expansions, "pose_checks": n_checks, "pose_checks_algorithmic": n_checks_ref,
                        "exact_escalations": n_exact,
                        "status": status_hist},
         }
         if cpu:
             line["cpu_baseline"] = cpu
+        if strong:
+            line["strong_scaling"] = strong
         emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -432,9 +463,9 @@ def collision_microbench(args, dev, fp32_peak):
             "roofline": {"bound": "alu_fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp32_peak if fp32_peak else None,
                          "hbm_GBps": checks * 25 * 1e-9,
-                         # 35.9 B of DRAM traffic per pose (ncu --set full, 4 Mi poses, profiles/r1h_ncu_full_summary.txt)
-                         # against 25 B algorithmic (24 B pose in + 1 B flag out)
-                         "traffic": int(35.9 * n)}}
+                         # 31.4 B of DRAM traffic per pose (ncu --set full, 4 Mi poses, profiles/r2e_k1_ncu_full_summary.txt:
+                         # 102.8 MB read + 29.0 MB written) against 25 B algorithmic (24 B pose in + 1 B flag out)
+                         "traffic": int(31.4 * n)}}
 
 
 def hbm_view(bytes_per_launch, ms_per_launch):
@@ -480,6 +511,92 @@ def refpath_microbench(out, wheel_base, with_cpu):
         res["cpu_baseline"] = {"value": done / (time.perf_counter() - t0), "unit": "paths/s", "cores": 1, "kind": "port",
                                "sample": f"first {done} paths, oracle (scipy CubicSpline like the reference)"}
     return res
+
+
+def distance_field_microbench(dev, with_cpu):
+    """BASELINE config 4: holonomic grid distance field of a 4096 x 4096 occupancy grid (0.05 m cells), King moves
+    (hl_distance_field).  Algorithmic bytes per cell: 1 B occupancy in + 8 B float64 cost out (float64 keeps the result
+    bit-identical to the reference's sequential sums).  The kernel is bound by the dependency depth of the wavefront
+    (thousands of frontier steps), not by HBM -- the line reports both."""
+    import time
+    import torch
+    from headland_trajectory_planning_b200 import ops
+    from headland_trajectory_planning_b200.utils.occupancy_grid_utils import synthetic_grid
+    n = 4096
+    occ, goal = synthetic_grid(n, seed=1)
+    d_occ = torch.from_numpy(occ.astype(np.uint8)).to(dev)
+    ops.distance_field(d_occ, goal, "King")
+    torch.cuda.synchronize()
+    ms, sweeps = 0.0, 0
+    reps = 2
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out, sweeps = ops.distance_field(d_occ, goal, "King")
+        b.record()
+        torch.cuda.synchronize()
+        ms += a.elapsed_time(b) / reps
+    cells = n * n
+    res = {"metric": "distance_field_cells_per_sec", "value": cells / (ms * 1e-3), "unit": "cells/s", "grid": f"{n}x{n}",
+           "motion_type": "King", "ms_per_field": ms, "relaxation_launches": int(sweeps),
+           "reachable_cells": int(torch.isfinite(out).sum().item()),
+           "roofline": dict(hbm_view(9 * cells, ms), bound="hbm (nominal; really the wavefront's dependency depth)",
+                            algorithmic_bytes=9 * cells)}
+    if with_cpu:
+        from oracle import distance_field as DF
+        rates = {}
+        for m in (128, 256):
+            o2, g2 = DF.synthetic_grid(m, seed=1)
+            t0 = time.perf_counter()
+            DF.holonomic_costs_with_obstacles(g2, o2, "King")
+            rates[m] = m * m / (time.perf_counter() - t0)
+        res["cpu_baseline"] = {"value": rates[256], "unit": "cells/s", "cores": 1, "kind": "port",
+                               "sample": "256 x 256 instance of the same generator (128 x 128: "
+                                         f"{rates[128]:.0f} cells/s), oracle port pinned bit for bit on the reference's a_star_utils.py",
+                               "extrapolated_4096x4096_s": cells / rates[256]}
+    return res
+
+
+def single_scenario_microbench(dev):
+    """BASELINE config 2: ONE mower scenario (test/obca.ipynb: 8 rows, tractor + mower implement, King, step 0.2 m,
+    max_nodes 400) through the drop-in class -- HybridAStarSearch(...).hybrid_a_star_search(max_nodes=400) -- host
+    geometry in, path lists out: environment upload, search and download included.  Latency, not throughput."""
+    import contextlib
+    import io
+    import math
+    import time
+    import torch
+    from headland_trajectory_planning_b200.car_model import CarModel
+    from headland_trajectory_planning_b200.hybrid_a_star_search import HybridAStarSearch
+    from headland_trajectory_planning_b200.orchard_geometry_environment import OrchardGeometryEnvironment
+    from headland_trajectory_planning_b200.reference_line_heuristic import ReferenceLineHeuristic
+    from headland_trajectory_planning_b200.utils import map_utils
+    np.random.seed(1)
+    rows = map_utils.create_tree_rows(8, 2.5, 20, slope_angle=math.radians(10), l_std=0.0)
+    env = OrchardGeometryEnvironment(rows, [], tree_width=0.3, headland_width=6.0)
+    car = CarModel(max_steer=0.55, axle_to_front=3, axle_to_back=0.55, width=1.48,
+                   aux_poly_features=[[[-1.84, 0.5], 1.0, 1.1]], with_aux=True)
+    out = {"metric": "single_scenario_latency_ms", "unit": "ms", "config": "mower, King, step 0.2 m, max_nodes 400"}
+    for name, start, goal in (("rs_shot_first_pop", map_utils.get_base_pose(1, rows, -1.0, side=map_utils.NEAR_SIDE, pose_type=map_utils.LEAVE_POSE),
+                               np.array([-2.11713892, 8.75, 0.0])),
+                              ("multi_expansion", map_utils.get_base_pose(1, rows, 0.0, side=map_utils.NEAR_SIDE, pose_type=map_utils.LEAVE_POSE),
+                               map_utils.get_base_pose(4, rows, 2.0, side=map_utils.NEAR_SIDE, pose_type=map_utils.ENTER_POSE))):
+        ends = rows[:, 0, :]
+        way = np.vstack((start[:2], [[ends[i, 0] - 4.5, ends[i, 1]] for i in (2, 3)], goal[:2]))
+        heur = ReferenceLineHeuristic(way, goal, car)
+        lat = []
+        counter = 0
+        for rep in range(6):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            with contextlib.redirect_stdout(io.StringIO()):
+                r = HybridAStarSearch(start, goal, env, car, heur, motion_type="King", plan_resolution=0.2).hybrid_a_star_search(max_nodes=400)
+            lat.append((time.perf_counter() - t0) * 1e3)
+            counter = r[5]
+        out[name] = {"counter": int(counter), "first_call_ms": lat[0], "warm_ms_median": sorted(lat[1:])[len(lat[1:]) // 2],
+                     "path_poses": len(r[0])}
+    out["value"] = out["multi_expansion"]["warm_ms_median"]
+    return out
 
 
 def rs_microbench(args, dev, with_cpu):

@@ -78,6 +78,7 @@ EXPORTS = [
     "hl_ctx_set_astar_variant", "hl_env_upload", "hl_env_free", "hl_env_count", "hl_env_device", "hl_collision_check", "hl_path_reduce",
     "hl_rs_all_paths", "hl_rs_sample", "hl_hybrid_astar_batch", "hl_hybrid_astar_workspace_bytes", "hl_astar_phase_cycles",
     "hl_distance_field", "hl_grid_pack", "hl_grid_footprint_check", "hl_measure_fp32_peak", "hl_ypark_paths", "hl_arc_paths", "hl_ref_path_count", "hl_ref_path_fill",
+    "hl_dubins_count", "hl_dubins_knots", "hl_dubins_fill", "hl_min_boundary_distance", "hl_corridor_hits",
 ]
 
 
@@ -160,6 +161,11 @@ def load_library():
         lib.hl_arc_paths.argtypes = [vp, vp, vp, i64, dbl, vp, vp]
         lib.hl_ref_path_count.argtypes = [vp, vp, vp, vp, vp, i64, dbl, vp, vp, vp]
         lib.hl_ref_path_fill.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, dbl, dbl, dbl, vp, vp, vp]
+        lib.hl_dubins_count.argtypes = [vp, vp, i64, dbl, dbl, dbl, i32, vp, vp, vp, vp]
+        lib.hl_dubins_knots.argtypes = [vp, vp, i64, dbl, dbl, dbl, i32, vp, vp, vp, vp, vp, vp]
+        lib.hl_min_boundary_distance.argtypes = [vp, vp, vp, vp, vp, i64, i32, vp, vp]
+        lib.hl_corridor_hits.argtypes = [vp, vp, vp, vp, vp, i64, dbl, vp, vp]
+        lib.hl_dubins_fill.argtypes = [vp, i64, dbl, vp, vp, vp, vp, vp, vp]
         if lib.hl_abi_version() != ABI_VERSION:
             raise HeadlandError("libheadland_b200.so ABI version mismatch")
         _lib = lib

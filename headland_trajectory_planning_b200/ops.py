@@ -144,6 +144,92 @@ def ref_path_batch(x, y, direction, in_offsets, wheel_base, desired_v=0.5, ds=0.
     return traj, out_off.cpu().numpy(), status[:n].cpu().numpy()
 
 
+def min_boundary_distance(envs, poses, path_start, env_id=None, with_aux=True):
+    """``get_min_distance_to_boundary`` of many paths (K10).  ``poses`` pooled [N,3] float64 (CUDA tensor or host),
+    ``path_start`` [n+1] int64 (host array or CUDA tensor).  Returns a float64 CUDA tensor [n]."""
+    torch = _torch()
+    lib = _lib.load_library()
+    dev = _device(envs, poses, env_id)
+    if not torch.is_tensor(poses):
+        poses = torch.from_numpy(np.ascontiguousarray(np.asarray(poses, dtype=np.float64)[:, :3])).to(dev)
+    poses = poses.contiguous()
+    if not torch.is_tensor(path_start):
+        path_start = torch.from_numpy(np.ascontiguousarray(path_start, dtype=np.int64)).to(dev)
+    if env_id is not None and not torch.is_tensor(env_id):
+        env_id = torch.from_numpy(np.ascontiguousarray(env_id, dtype=np.int32)).to(dev)
+    n = path_start.numel() - 1
+    out = torch.empty(max(n, 0), dtype=torch.float64, device=dev)
+    if n > 0:
+        _lib.check(lib.hl_min_boundary_distance(envs.ctx, envs.handle, _lib.ptr(env_id), _lib.ptr(poses), _lib.ptr(path_start),
+                                                n, 1 if with_aux else 0, _lib.ptr(out), _lib.stream_ptr()),
+                   "hl_min_boundary_distance")
+    return out
+
+
+def corridor_hits(envs, points, line_start, radius, env_id=None):
+    """Does the flat-capped, round-joined buffer of each polyline meet an obstacle?  (K11.)  ``points`` pooled [N,2],
+    ``line_start`` [n+1].  Returns a uint8 CUDA tensor [n]."""
+    torch = _torch()
+    lib = _lib.load_library()
+    dev = _device(envs, points, env_id)
+    if not torch.is_tensor(points):
+        points = torch.from_numpy(np.ascontiguousarray(np.asarray(points, dtype=np.float64).reshape(-1, 2))).to(dev)
+    points = points.contiguous()
+    if not torch.is_tensor(line_start):
+        line_start = torch.from_numpy(np.ascontiguousarray(line_start, dtype=np.int64)).to(dev)
+    if env_id is not None and not torch.is_tensor(env_id):
+        env_id = torch.from_numpy(np.ascontiguousarray(env_id, dtype=np.int32)).to(dev)
+    n = line_start.numel() - 1
+    out = torch.zeros(max(n, 0), dtype=torch.uint8, device=dev)
+    if n > 0:
+        _lib.check(lib.hl_corridor_hits(envs.ctx, envs.handle, _lib.ptr(env_id), _lib.ptr(points), _lib.ptr(line_start), n,
+                                        float(radius), _lib.ptr(out), _lib.stream_ptr()), "hl_corridor_hits")
+    return out
+
+
+def dubins_course_batch(pairs, turning_radius, step=0.1, ds=0.1, append_goal=False, want_samples=False):
+    """Dubins shortest paths of many (start, end) pose pairs + their cubic-spline course (K9).  ``pairs``: [n,6] float64
+    (sx, sy, syaw, ex, ey, eyaw), host array or CUDA tensor.  Returns (rows [T,4] float64 CUDA tensor: x, y, yaw,
+    curvature; row_offsets [n+1] int64 host; word [n] int32 host (0..5 = LSL LSR RSL RSR RLR LRL, -1 none);
+    length [n] float64 host) -- plus, with ``want_samples``, the raw ``sample_many`` configurations [slots,3] and the
+    slot offsets.  A pair whose course cannot be built (coincident poses) has no rows."""
+    torch = _torch()
+    lib = _lib.load_library()
+    dev = _device(None, pairs)
+    if not torch.is_tensor(pairs):
+        pairs = torch.from_numpy(np.ascontiguousarray(np.asarray(pairs, dtype=np.float64).reshape(-1, 6))).to(dev)
+    pairs = pairs.contiguous()
+    n = pairs.shape[0]
+    ctx = _lib.get_ctx(dev.index)
+    rho, step, ds, ag = float(turning_radius), float(step), float(ds), 1 if append_goal else 0
+    slots = torch.zeros(max(n, 1), dtype=torch.int64, device=dev)
+    word = torch.full((max(n, 1),), -1, dtype=torch.int32, device=dev)
+    length = torch.zeros(max(n, 1), dtype=torch.float64, device=dev)
+    if n == 0:
+        return torch.empty((0, 4), dtype=torch.float64, device=dev), np.zeros(1, np.int64), np.zeros(0, np.int32), np.zeros(0)
+    _lib.check(lib.hl_dubins_count(ctx, _lib.ptr(pairs), n, rho, step, ds, ag, _lib.ptr(slots), _lib.ptr(word),
+                                   _lib.ptr(length), _lib.stream_ptr()), "hl_dubins_count")
+    slot_off = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    slot_off[1:] = torch.cumsum(slots[:n], 0)
+    total_slots = int(slot_off[-1].item())
+    ws = torch.empty(9 * max(total_slots, 1), dtype=torch.float64, device=dev)
+    n_knots = torch.zeros(n, dtype=torch.int32, device=dev)
+    n_rows = torch.zeros(n, dtype=torch.int64, device=dev)
+    samples = torch.empty((max(total_slots, 1), 3), dtype=torch.float64, device=dev) if want_samples else None
+    _lib.check(lib.hl_dubins_knots(ctx, _lib.ptr(pairs), n, rho, step, ds, ag, _lib.ptr(slot_off), _lib.ptr(ws),
+                                   _lib.ptr(n_knots), _lib.ptr(n_rows), _lib.ptr(samples), _lib.stream_ptr()), "hl_dubins_knots")
+    row_off = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    row_off[1:] = torch.cumsum(n_rows, 0)
+    total = int(row_off[-1].item())
+    out = torch.empty((max(total, 1), 4), dtype=torch.float64, device=dev)
+    _lib.check(lib.hl_dubins_fill(ctx, n, ds, _lib.ptr(slot_off), _lib.ptr(row_off), _lib.ptr(n_knots), _lib.ptr(ws),
+                                  _lib.ptr(out), _lib.stream_ptr()), "hl_dubins_fill")
+    res = (out[:total], row_off.cpu().numpy(), word[:n].cpu().numpy(), length[:n].cpu().numpy())
+    if want_samples:                      # raw sample_many configurations: pair p owns slots slot_off[p] .. slot_off[p+1]-2
+        return res + (samples, slot_off.cpu().numpy())
+    return res
+
+
 def measure_fp32_peak(device=None):
     lib = _lib.load_library()
     v = C.c_double()

@@ -51,3 +51,26 @@ def check_poses_on_grid(features, car_model, path):
     ``check_path_feasibility_with_grid_map``): uint8 CUDA tensor, 1 = body meets an occupied cell."""
     return ops.grid_footprint_check(features.device_bits, features.obstacles_boolean.shape, features.resolution,
                                     np.asarray(path, dtype=np.float64)[:, :3], car_model.body_ext)
+
+
+def synthetic_grid(n, seed=1, n_rows=None, n_blocks=None):
+    """BASELINE config-4 occupancy grid, n x n cells of 0.05 m: occupied 1-cell border, tree rows as
+    8-cell-wide bars with headland gaps, random 6 x 6 blocks.  Returns (bool grid, goal cell = the free cell nearest
+    the centre).  Workload generator of ``bench.py``'s distance-field line and of the grid tests."""
+    rng = np.random.default_rng(seed)
+    occ = np.zeros((n, n), dtype=bool)
+    occ[0, :] = occ[-1, :] = occ[:, 0] = occ[:, -1] = True
+    n_rows = n_rows if n_rows is not None else max(2, n // 64)
+    gap = max(8, n // 10)
+    pitch = max(16, (n - 2 * gap) // n_rows)
+    for r in range(n_rows):
+        j = gap + r * pitch
+        occ[gap:n - gap, j:j + min(8, max(1, pitch // 3))] = True
+    n_blocks = n_blocks if n_blocks is not None else max(4, (n * n) // 8192)
+    for _ in range(n_blocks):
+        a, b = rng.integers(1, n - 7, 2)
+        occ[a:a + 6, b:b + 6] = True
+    c = n // 2
+    free = np.argwhere(~occ)
+    goal = tuple(int(v) for v in free[np.argmin(np.abs(free[:, 0] - c) + np.abs(free[:, 1] - c))])
+    return occ, goal

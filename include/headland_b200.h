@@ -232,6 +232,44 @@ int hl_ref_path_fill(hl_ctx* ctx, const double* d_x, const double* d_y, const in
                      int64_t n_paths, double wheel_base, double desired_v, double ds, double* d_workspace,
                      double* d_out, void* stream);
 
+/* ---- K9 Dubins paths + spline course ---------------------------
+ * Replaces, for MANY pose pairs at once, get_dubins_path (path_planner/utils/navigation_utils.py:206-215:
+ * dubins.shortest_path(q0, q1, rho) + sample_many(step)) followed by calc_spline_course(x, y, ds)
+ * (path_planner/utils/cubic_spline.py:92-112) = get_dubins_path_full (path_planner/safety_forward_path_plan.py:286-297)
+ * and, with append_goal = 1, HybridAStarSearch.get_dubins_path (path_planner/hybrid_a_star_search.py:289-304).
+ * pydubins is un-vendored and un-pinned (requirements.txt:14): the published dubins.c algorithm is restated,
+ * parity unpinned.
+ *   hl_dubins_count: d_slots[p] = workspace slots of pair p (samples + 1, 0 = no path), d_word[p] = 0..5
+ *                    (LSL LSR RSL RSR RLR LRL), d_length[p] = path length; the caller turns d_slots into
+ *                    d_slot_offsets [n+1] (exclusive prefix sum) and provides 9 doubles per slot of workspace
+ *   hl_dubins_knots: samples every path, builds the spline knots in the workspace; d_n_knots[p] (0 = a spline
+ *                    cannot be built: the reference raises), d_n_rows[p] = rows of the course
+ *   hl_dubins_fill:  d_out [row_offsets[n]][4] float64 rows (x, y, yaw, curvature)                             */
+int hl_dubins_count(hl_ctx* ctx, const double* d_pairs, int64_t n, double rho, double step, double ds,
+                    int32_t append_goal, int64_t* d_slots, int32_t* d_word, double* d_length, void* stream);
+int hl_dubins_knots(hl_ctx* ctx, const double* d_pairs, int64_t n, double rho, double step, double ds,
+                    int32_t append_goal, const int64_t* d_slot_offsets, double* d_workspace,
+                    int32_t* d_n_knots, int64_t* d_n_rows, double* d_samples /* optional [slots][3]: the raw
+                    sample_many configurations (x, y, yaw) of pair p at slot_offsets[p] .. +slots[p]-1 */, void* stream);
+int hl_dubins_fill(hl_ctx* ctx, int64_t n, double ds, const int64_t* d_slot_offsets, const int64_t* d_row_offsets,
+                   const int32_t* d_n_knots, double* d_workspace, double* d_out, void* stream);
+
+/* ---- K10 distance of a swept path to the field boundary -----------------
+ * Replaces OrchardGeometryEnvironment.get_min_distance_to_boundary (path_planner/orchard_geometry_environment.py:
+ * 393-412): smallest signed distance (negative outside the field) from the exterior vertices of the swept footprint
+ * unions (body at every pose; with_aux: every implement rectangle at every 2nd pose, car_model.py:39-73) to the
+ * ring of field_range_poly.  One value per path; GEOS unavailable, parity unpinned.
+ *   d_env_id [n_paths] or NULL; d_poses pooled [.,3]; d_path_start [n_paths+1]; d_out [n_paths] float64          */
+int hl_min_boundary_distance(hl_ctx* ctx, const hl_env_batch* envs, const int32_t* d_env_id, const double* d_poses,
+                             const int64_t* d_path_start, int64_t n_paths, int32_t with_aux, double* d_out, void* stream);
+
+/* ---- K11 corridor test ---------------------------------------------------
+ * Replaces the per-word test of classic_circle_back_turning_path (path_planner/safety_forward_path_plan.py:811-822):
+ * LineString(xy).buffer(radius, cap_style=flat, join_style=round) intersects the obstacle / tree-row polygons.
+ *   d_points pooled [.,2] float64 polyline vertices; d_line_start [n_lines+1]; d_out [n_lines] uint8 (1 = meets)  */
+int hl_corridor_hits(hl_ctx* ctx, const hl_env_batch* envs, const int32_t* d_env_id, const double* d_points,
+                     const int64_t* d_line_start, int64_t n_lines, double radius, uint8_t* d_out, void* stream);
+
 /* ---- K2/K3 Reeds-Shepp --------------------------------------------------------
  * Replaces reeds_shepp.calc_all_paths (path_planner/utils/reeds_shepp.py:39-65):
  * generate_path + set_path dedup (:565-582, :68-87) and the sample count of

@@ -326,9 +326,13 @@ class HybridAStarSearch:
         self.car_model = car_model
         self.search_heuristic = search_heuristic
         self.motion_type = motion_type
-        if motion_type != "King":
-            raise NotImplementedError("Pawn mode needs pydubins (un-vendored); SURVEY 8f rank 3")
-        self.motion_steers = self._get_motion_steers_reeds_shepp()
+        if motion_type == "King":
+            self.motion_steers = self._get_motion_steers_reeds_shepp()
+        elif motion_type == "Pawn":
+            # Dubins goal extension: pydubins is un-vendored -> oracle.dubins_port restates dubins.c (parity unpinned)
+            self.motion_steers = self._get_motion_steers_dubins()
+        else:
+            raise ValueError(f"unknown motion_type {motion_type!r}")
         self.start_node = self.init_node(start_pose)
         self.goal_node = self.init_node(goal_pose)
         # audit trail for parity tests (not in the reference)
@@ -343,6 +347,57 @@ class HybridAStarSearch:
         x, y, yaw = pose[0], pose[1], pose[2]
         idx = self.calculate_node_index(x, y, yaw)
         return Node(idx, [[x, y, yaw]], [0], 0, [1], idx)
+
+    def _get_motion_steers_dubins(self):
+        """hybrid_a_star_search.py:331-341: 8 steers 0.55 .. -0.67173, all forward."""
+        steer_ranges = np.arange(self.car_model.MAX_STEER, -(self.car_model.MAX_STEER + self.yaw_resolution),
+                                 -self.yaw_resolution)
+        return np.vstack((steer_ranges, np.ones_like(steer_ranges))).T
+
+    def get_dubins_path(self, start_x, start_y, start_yaw, goal_x, goal_y, goal_yaw, curvature):
+        """hybrid_a_star_search.py:289-304: shortest Dubins path sampled at plan_resolution, the goal pose appended,
+        then a cubic-spline course (scipy not-a-knot) resampled at plan_resolution -> rows (x, y, yaw, k)."""
+        from . import dubins_port as dubins
+        from .obca_util import calc_spline_course
+        path = dubins.shortest_path([start_x, start_y, start_yaw], [goal_x, goal_y, goal_yaw], 1.0 / curvature)
+        dubins_path, _ = path.sample_many(self.plan_resolution)
+        dubins_path = np.vstack([np.array(dubins_path), np.array([[goal_x, goal_y, goal_yaw]])])
+        xs, ys, yaws, ks, _ = calc_spline_course(dubins_path[:, 0], dubins_path[:, 1], ds=self.plan_resolution)
+        return np.array([xs, ys, yaws, ks]).T
+
+    def calculate_dubins_path_cost(self, current_node, path):
+        """hybrid_a_star_search.py:162-182.  [Q] ``path[:, -1]`` is the CURVATURE column of the 4-column array the
+        caller passes, so the "steer cost" is the wrapped spread of the curvatures; the method returns a tuple and
+        the caller stores that tuple as the goal node's cost (:203, :219-226) -- harmless, the search ends there."""
+        cost = current_node.cost
+        path_length = calculate_path_length(path[:, 0], path[:, 1])
+        cost += path_length * self.DISTANCE_COST
+        delta_yaw = angle_wrap(np.max(path[:, -1]) - np.min(path[:, -1]))
+        cost += delta_yaw * self.STEER_COST
+        return cost, path_length
+
+    def _get_goal_extension_with_dubins_path(self, current_node):
+        """hybrid_a_star_search.py:184-230."""
+        sx, sy, syaw = current_node.traj[-1][0], current_node.traj[-1][1], current_node.traj[-1][2]
+        gx, gy, gyaw = self.goal_node.traj[-1][0], self.goal_node.traj[-1][1], self.goal_node.traj[-1][2]
+        dubin_path = self.get_dubins_path(sx, sy, syaw, gx, gy, gyaw, self.car_model.curvature)
+        cost = self.calculate_dubins_path_cost(current_node, dubin_path)
+        traj = np.copy(dubin_path[:, :3])
+        traj[:, -1] = angle_wrap(traj[:, -1])
+        path_length = calculate_path_length(dubin_path[:, 0], dubin_path[:, 1])
+        ks = list(dubin_path[:, 3])
+        self.stats["rs_words"] += 1
+        self.stats["rs_poses"] += len(traj)
+        if not self.check_collision(traj) and path_length < self.MIN_LENGTH_TO_GOAL:
+            return Node(self.goal_node.get_hybrid_index(), traj, ks, cost, np.ones_like(ks).tolist(),
+                        current_node.get_hybrid_index())
+        return None
+
+    def get_goal_extension_path(self, current_node):
+        """hybrid_a_star_search.py:456-462."""
+        if self.motion_type == "King":
+            return self._get_goal_extension_with_reeds_shepp_path(current_node)
+        return self._get_goal_extension_with_dubins_path(current_node)
 
     def _get_motion_steers_reeds_shepp(self):
         """hybrid_a_star_search.py:343-354."""
@@ -507,7 +562,7 @@ class HybridAStarSearch:
             current_node = open_set.pop(current_idx)
             closed_set[current_idx] = current_node
             self.expanded.append(current_idx)
-            goal_ext = self._get_goal_extension_with_reeds_shepp_path(current_node)
+            goal_ext = self.get_goal_extension_path(current_node)
             goal_node = self.check_the_arrival(goal_ext, current_node)
             if goal_node is not None:
                 closed_set[goal_node.get_hybrid_index()] = goal_node
