@@ -12,7 +12,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_NAME = "libheadland_b200.so"
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 HL_MAX_PRIMS = 16
 HL_CAPSULE_VERTS = 66
 HL_RS_CANDIDATES = 46
@@ -58,6 +58,7 @@ class HlSearchParams(C.Structure):
         ("direction_change_cost", C.c_double), ("reverse_cost", C.c_double),
         ("hybrid_cost", C.c_double), ("min_length_to_goal", C.c_double),
         ("max_nodes", C.c_int32), ("max_path_poses", C.c_int32),
+        ("motion_type", C.c_int32), ("dubins_capacity", C.c_int32),
     ]
 
 

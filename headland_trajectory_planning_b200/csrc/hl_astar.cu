@@ -63,6 +63,7 @@ struct AwSmem {                          // one per warp
     };
     RsProblem rs_prob;
     int rs_n, rs_pick;
+    int dub_rows;                        // Pawn: rows of the accepted Dubins course (kept in the slot's global scratch)
     int phit[HL_MAX_PRIMS];
     // stats
     unsigned long long n_checks, n_exact, n_ref;
@@ -144,7 +145,7 @@ __device__ __noinline__ void finalize_scenario(AwSmem& S, const AsWs& W, const A
                 W.hslot[len++] = node;
                 poses += W.nsteps[node] + 1;
             }
-            if (S.arrival == 1) rs_pts = (S.rs_pick < AW_MAX_PLANS ? S.plans[S.rs_pick] : S.plan_tmp).npts;
+            if (S.arrival == 1) rs_pts = P.pawn ? S.dub_rows : (S.rs_pick < AW_MAX_PLANS ? S.plans[S.rs_pick] : S.plan_tmp).npts;
         }
         S.chain_len = len;
         S.path_len = poses + rs_pts;
@@ -183,7 +184,16 @@ __device__ __noinline__ void finalize_scenario(AwSmem& S, const AsWs& W, const A
                 O.path_dir[off + i] = (int8_t)P.dir[p];
             }
         }
-        if (S.arrival == 1) {
+        if (S.arrival == 1 && P.pawn) {                 // the Dubins course of the goal extension: rows kept in the scratch
+            const int cnt = S.dub_rows;
+            const double* rx = W.dub + 9 * (size_t)P.dub_cap;
+            const double* ry = rx + P.dub_cap; const double* ryaw = ry + P.dub_cap; const double* rk = ryaw + P.dub_cap;
+            const long long off = S.path_off + (S.path_len - cnt);
+            for (int j = lane; j < cnt; j += 32) {
+                O.path_x[off + j] = rx[j]; O.path_y[off + j] = ry[j]; O.path_yaw[off + j] = ryaw[j];
+                O.path_k[off + j] = rk[j]; O.path_dir[off + j] = (int8_t)1;
+            }
+        } else if (S.arrival == 1) {
             const RsPlan& plan = (S.rs_pick < AW_MAX_PLANS) ? S.plans[S.rs_pick] : S.plan_tmp;
             const double q0[3] = {S.cx, S.cy, S.cyaw};
             const double cq = m_cos(-q0[2]), sq = m_sin(-q0[2]);
@@ -263,6 +273,74 @@ __device__ __noinline__ void setup_scenario(AwSmem& S, const AsWs& W, const AsPa
     __syncwarp();
 }
 
+// Pawn goal extension (_get_goal_extension_with_dubins_path, hybrid_a_star_search.py:184-230 with get_dubins_path
+// :289-304 and calculate_dubins_path_cost :162-182): shortest Dubins path from the popped node to the goal, sampled at
+// plan_resolution, the goal pose appended, cubic-spline course at plan_resolution, yaws wrapped, footprint check of
+// every row, length below MIN_LENGTH_TO_GOAL.  One warp; the knots and the rows live in the slot's global scratch.
+__device__ __noinline__ void pawn_shot(AwSmem& S, const AsWs& W, const AsParams& P, const EnvBatchDev& eb, const EnvDesc& D,
+                                       const EnvSmem& E, unsigned FLAGS, int lane) {
+    const int cap = P.dub_cap;
+    double* ts = W.dub; double* kx = ts + cap; double* ky = kx + cap; double* ks = ky + cap; double* dx = ks + cap;
+    double* dy = dx + cap; double* cp = dy + cap; double* bx = cp + cap; double* by = bx + cap;
+    double* rx = by + cap; double* ry = rx + cap; double* ryaw = ry + cap; double* rk = ryaw + cap;
+    const double q0[3] = {S.cx, S.cy, S.cyaw};
+    DubPath path;
+    dub_shortest(q0, S.goal, xdiv(1.0, P.maxc), path);
+    if (path.type < 0) { if (lane == 0) S.status = HL_STATUS_RS_ASSERT; __syncwarp(); return; }   // dubins raises
+    const long long n_s = dub_n_samples(dub_length(path), P.res);
+    if (n_s + 1 > cap) { if (lane == 0) S.status = HL_STATUS_CAPACITY; __syncwarp(); return; }
+    const int m = dub_course_knots(path, P.res, true, S.goal, n_s, ts, kx, ky, ks, lane);
+    if (m < 2) { if (lane == 0) S.status = HL_STATUS_RS_ASSERT; __syncwarp(); return; }          // scipy raises on < 2 knots
+    if (lane == 0) rp_derivs(ks, kx, ky, m, dx, dy, cp, bx, by);
+    __syncwarp();
+    const long long cnt = rp_count(ks[m - 1], P.res);
+    if (cnt > cap) { if (lane == 0) S.status = HL_STATUS_CAPACITY; __syncwarp(); return; }
+    for (long long i = lane; i < cnt; i += 32) {
+        const double t = xmul((double)i, P.res);
+        double x, x1, x2, y, y1, y2;
+        rp_eval(ks, kx, dx, m, t, x, x1, x2);
+        rp_eval(ks, ky, dy, m, t, y, y1, y2);
+        const double q = x1 * x1 + y1 * y1;
+        rx[i] = x; ry[i] = y; ryaw[i] = angle_wrap(m_atan2(y1, x1));
+        rk[i] = (y2 * x1 - x2 * y1) / (q * sqrt(q));
+    }
+    __syncwarp();
+    if (lane == 0) S.n_ref += (unsigned long long)cnt;
+    int infeasible = 0;
+    for (long long base = 0; base < cnt && !infeasible; base += 32) {
+        const long long i = base + lane;
+        int st = HL_FREE;
+        unsigned amb = 0;
+        if (i < cnt) st = pose_filter(D, E, rx[i], ry[i], ryaw[i], FLAGS, &amb);
+        const unsigned livem = __ballot_sync(FULL, i < cnt);
+        const unsigned hitm = __ballot_sync(FULL, st == HL_HIT);
+        const unsigned ambm = __ballot_sync(FULL, st == HL_AMBIG);
+        infeasible = hitm != 0;
+        if (!infeasible && ambm) {
+            int bad = 0;
+            if (st == HL_AMBIG) bad = pose_exact(eb, D, rx[i], ry[i], ryaw[i], amb) ? 1 : 0;
+            if (lane == 0) S.n_exact += (unsigned long long)__popc(ambm);
+            infeasible = __any_sync(FULL, bad);
+        }
+        if (lane == 0) S.n_checks += (unsigned long long)__popc(livem);
+    }
+    if (!infeasible && lane == 0) {
+        // calculate_path_length (np.hypot of the diffs, cumsum) and the spread of the curvature column ([Q]: the
+        // reference takes path[:, -1] of the 4-column array for its "delta yaw")
+        double len = 0.0, kmin = rk[0], kmax = rk[0];
+        for (long long i = 0; i + 1 < cnt; ++i) {
+            const double dsl = hypot_cr(xsub(rx[i + 1], rx[i]), xsub(ry[i + 1], ry[i]));
+            len = (i == 0) ? dsl : xadd(len, dsl);
+        }
+        for (long long i = 1; i < cnt; ++i) { kmin = fmin(kmin, rk[i]); kmax = fmax(kmax, rk[i]); }
+        if (len < P.min_len_goal) {
+            S.arrival = 1; S.rs_word = path.type; S.dub_rows = (int)cnt;
+            S.goal_cost = xadd(xadd(S.cg, len), xmul(angle_wrap(xsub(kmax, kmin)), P.steer_cost));
+        }
+    }
+    __syncwarp();
+}
+
 __global__ void __launch_bounds__(AW_WARPS * 32, AW_MIN_CTAS)
 k_hybrid_astar_w(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen, AsParams P, char* ws_base,
                  size_t ws_stride, unsigned int* work_counter, AwOut O) {
@@ -270,7 +348,7 @@ k_hybrid_astar_w(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     AwSmem& S = reinterpret_cast<AwSmem*>(smem_raw)[wid];
     const AsWs W = as_carve(ws_base + ((size_t)blockIdx.x * AW_WARPS + wid) * ws_stride, P.cap_nodes, P.hash_size,
-                            P.max_nodes);
+                            P.max_nodes, P.dub_cap);
     const int hmask = P.hash_size - 1;
     const unsigned FLAGS = HL_CHECK_OBSTACLES | HL_CHECK_BOUNDARY | HL_CHECK_LANE;
 
@@ -338,14 +416,18 @@ k_hybrid_astar_w(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                         S.cprim = W.nprim[cur];
                         S.rs_pick = -1;
                         const double q0n[3] = {S.cx, S.cy, S.cyaw};
-                        S.rs_prob = rs_normalise(q0n, S.goal, P.maxc);      // generate_path (:565-572), once per pop
+                        if (!P.pawn) S.rs_prob = rs_normalise(q0n, S.goal, P.maxc);   // generate_path (:565-572), once per pop
                     }
                 }
             }
             __syncwarp();
             TICK(PH_POP);
         }
-        if (live && S.status < 0) {
+        if (live && S.status < 0 && P.pawn) {
+            pawn_shot(S, W, P, eb, D, E, FLAGS, lane);
+            TICK(PH_RS_SAMPLE);
+        }
+        if (live && S.status < 0 && !P.pawn) {
             // ---- analytic shot: 46 candidate words (:249-258)
             const double q0[3] = {S.cx, S.cy, S.cyaw};
             for (int c = lane; c < HL_RS_CANDIDATES; c += 32) {
@@ -385,7 +467,7 @@ k_hybrid_astar_w(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
         }
         if (live && S.status < 0) {
             const double q0[3] = {S.cx, S.cy, S.cyaw};
-            const int m = S.rs_n;
+            const int m = P.pawn ? 0 : S.rs_n;
             const double stepn = xmul(P.res, P.maxc);
             const double cq = m_cos(-q0[2]), sq = m_sin(-q0[2]);
             // sampling plans of the first AW_MAX_PLANS words in pop order, one lane each
@@ -624,6 +706,8 @@ static void fill_params(const hl_ctx* ctx, const HlSearchParams* h, AsParams& P)
     int hs = 1024;
     while (hs < 2 * P.cap_nodes) hs <<= 1;
     P.hash_size = hs;
+    P.pawn = h->motion_type == 1 ? 1 : 0;
+    P.dub_cap = P.pawn ? (h->dubins_capacity > 0 ? h->dubins_capacity : 2048) : 0;
 }
 
 
@@ -714,7 +798,7 @@ static int ls_run(hl_ctx* ctx, const hl_env_batch* envs, const HlScenario* d_sce
                   const AwOut& O, cudaStream_t st) {
     LsState* L = nullptr;
     if (ls_state_get(ctx, &L)) return 1;
-    const size_t stride = as_ws_bytes(P.cap_nodes, P.hash_size, P.max_nodes);
+    const size_t stride = as_ws_bytes(P.cap_nodes, P.hash_size, P.max_nodes, P.dub_cap);
     const int nb_max = n_scen < LS_MAX_BATCH ? n_scen : LS_MAX_BATCH;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t r = off; off += as_align(bytes); return r; };
@@ -810,7 +894,7 @@ extern "C" int64_t hl_hybrid_astar_workspace_bytes(const hl_ctx* ctx, const HlSe
     if (!ctx || !h) return -1;
     AsParams P;
     fill_params(ctx, h, P);
-    return (int64_t)as_ws_bytes(P.cap_nodes, P.hash_size, P.max_nodes);
+    return (int64_t)as_ws_bytes(P.cap_nodes, P.hash_size, P.max_nodes, P.dub_cap);
 }
 
 extern "C" int hl_hybrid_astar_batch(hl_ctx* ctx, const hl_env_batch* envs, const HlScenario* d_scen,
@@ -832,6 +916,9 @@ extern "C" int hl_hybrid_astar_batch(hl_ctx* ctx, const hl_env_batch* envs, cons
     if (h_params->n_prims < 1 || h_params->n_prims > HL_MAX_PRIMS || h_params->max_nodes < 0) {
         hl_set_error("hl_hybrid_astar_batch: n_prims/max_nodes out of range"); return 1;
     }
+    if (h_params->motion_type != 0 && h_params->motion_type != 1) {
+        hl_set_error("hl_hybrid_astar_batch: motion_type must be 0 (King) or 1 (Pawn)"); return 1;
+    }
     if (hl_enter(ctx, envs, d_results, "hl_hybrid_astar_batch")) return 1;
     AsParams P;
     fill_params(ctx, h_params, P);
@@ -842,8 +929,9 @@ extern "C" int hl_hybrid_astar_batch(hl_ctx* ctx, const hl_env_batch* envs, cons
     // variant: "spec" = two warps per scenario with the analytic shot decoupled (hl_astar_spec.cuh),
     // "warp" = one warp per scenario, "level" = level-synchronous graph (hl_ctx_set_astar_variant / HL_ASTAR_VARIANT
     // at context creation; A/B runs only, the results are identical).
-    const bool level = ctx->astar_variant == HL_ASTAR_LEVEL;
-    const bool spec = ctx->astar_variant != HL_ASTAR_WARP;
+    // Pawn mode (Dubins goal extension) exists in the one-warp-per-scenario kernel only
+    const bool level = !P.pawn && ctx->astar_variant == HL_ASTAR_LEVEL;
+    const bool spec = !P.pawn && ctx->astar_variant != HL_ASTAR_WARP;
     cudaStream_t st = (cudaStream_t)stream;
     HL_CUDA_OK(cudaStreamWaitEvent(st, (cudaEvent_t)ctx->astar_done, 0));      // no-op until the first record
     AwOut O;
@@ -878,7 +966,7 @@ extern "C" int hl_hybrid_astar_batch(hl_ctx* ctx, const hl_env_batch* envs, cons
     long long want = ((long long)n_scen + slots - 1) / slots;
     long long cap = (long long)ctx->sm_count * per_sm;
     const int grid = (int)(want < cap ? want : cap);
-    const size_t stride = as_ws_bytes(P.cap_nodes, P.hash_size, P.max_nodes);
+    const size_t stride = as_ws_bytes(P.cap_nodes, P.hash_size, P.max_nodes, P.dub_cap);
     const size_t need = stride * (size_t)grid * slots;
     if (need > ctx->astar_ws_bytes) {
         if (ctx->astar_ws) cudaFree(ctx->astar_ws);          // synchronises the device: the previous search is done

@@ -24,6 +24,7 @@
 #include <cstring>
 #include "hl_geom.cuh"
 #include "hl_rs.cuh"
+#include "hl_dubins.cuh"
 
 #ifndef AS_THREADS
 #define AS_THREADS 128
@@ -49,6 +50,8 @@ struct AsParams {
     double steer_cost, delta_steer_cost, dir_change_cost, reverse_cost, hybrid_cost, min_len_goal;
     int max_nodes, max_path_poses;
     int cap_nodes, hash_size;
+    int pawn;                 // motion_type "Pawn": forward-only primitives, Dubins goal extension (:184-230, :289-304)
+    int dub_cap;              // capacity (samples / course rows) of the Dubins scratch of one scenario slot
 };
 
 // per-CTA workspace in global memory (L2 resident while the scenario runs)
@@ -61,11 +64,12 @@ struct AsWs {
     double* hprio; int* hslot;
     int* corder;
     long long* cref;          // algorithmic primitive-pose checks done BEFORE pop i was expanded
+    double* dub;              // Pawn mode: 13 x dub_cap doubles (ts kx ky ks dx dy cp bx by | rx ry ryaw rk), else unused
 };
 
 __host__ __device__ inline size_t as_align(size_t x) { return (x + 255) & ~(size_t)255; }
 
-__host__ __device__ inline size_t as_ws_bytes(int cap, int hsize, int max_nodes) {
+__host__ __device__ inline size_t as_ws_bytes(int cap, int hsize, int max_nodes, int dub_cap = 0) {
     size_t b = 0;
     b += 4 * as_align(sizeof(double) * cap);           // nx ny nyaw ng
     b += as_align(sizeof(long long) * cap);            // nkey
@@ -75,10 +79,11 @@ __host__ __device__ inline size_t as_ws_bytes(int cap, int hsize, int max_nodes)
     b += as_align(sizeof(double) * cap) + as_align(sizeof(int) * cap);
     b += as_align(sizeof(int) * (max_nodes + 4));
     b += as_align(sizeof(long long) * (max_nodes + 4));
+    b += as_align(sizeof(double) * 13 * (size_t)dub_cap);
     return b;
 }
 
-__device__ inline AsWs as_carve(char* base, int cap, int hsize, int max_nodes) {
+__device__ inline AsWs as_carve(char* base, int cap, int hsize, int max_nodes, int dub_cap = 0) {
     AsWs w;
     char* p = base;
     auto take = [&](size_t bytes) { char* r = p; p += as_align(bytes); return r; };
@@ -92,6 +97,7 @@ __device__ inline AsWs as_carve(char* base, int cap, int hsize, int max_nodes) {
     w.hprio = (double*)take(sizeof(double) * cap); w.hslot = (int*)take(sizeof(int) * cap);
     w.corder = (int*)take(sizeof(int) * (max_nodes + 4));
     w.cref = (long long*)take(sizeof(long long) * (max_nodes + 4));
+    w.dub = (double*)take(sizeof(double) * 13 * (size_t)dub_cap);
     return w;
 }
 

@@ -13,19 +13,23 @@ from .env_batch import EnvBatch, make_record
 
 def make_search_params(car_model, motion_type="King", yaw_resolution=math.radians(10), plan_resolution=0.1,
                        max_nodes=2000, max_path_poses=16384, costs=None):
-    """HlSearchParams with the primitive table of ``_get_motion_steers_reeds_shepp``
-    (hybrid_a_star_search.py:343-354) and the per-primitive constants of
-    ``kinematic_simulation_node`` / ``simulated_path_cost`` (:370-375, :322, :402), all
-    evaluated on the host with the reference's own numpy / math calls."""
-    if motion_type != "King":
-        raise NotImplementedError("motion_type='Pawn' needs the un-vendored pydubins goal extension "
-                                  "(hybrid_a_star_search.py:184-230); only 'King' runs on the GPU")
+    """HlSearchParams with the primitive table of ``_get_motion_steers_reeds_shepp`` ("King",
+    hybrid_a_star_search.py:343-354) or ``_get_motion_steers_dubins`` ("Pawn", :331-341) and the per-primitive constants
+    of ``kinematic_simulation_node`` / ``simulated_path_cost`` (:370-375, :322, :402), all evaluated on the host with the
+    reference's own numpy / math calls.  "Pawn" selects the Dubins goal extension (:184-230) in the kernel; the Dubins
+    solver restates the un-vendored pydubins (parity unpinned)."""
+    if motion_type not in ("King", "Pawn"):
+        raise ValueError(f"unknown motion_type {motion_type!r}")
     c = dict(STEER_COST=1, DELTA_STEER_COST=5, DIRECTION_CHANGE_COST=1000, REVERSE_COST=5000, HYBRID_COST=50,
              MIN_LENGTH_TO_GOAL=1000)
     c.update(costs or {})
-    steers = np.arange(car_model.MAX_STEER, -(car_model.MAX_STEER + yaw_resolution / 2.0), -yaw_resolution / 2.0)
-    dirs = np.ones_like(steers)
-    dirs[1:len(dirs):2] = -1
+    if motion_type == "King":
+        steers = np.arange(car_model.MAX_STEER, -(car_model.MAX_STEER + yaw_resolution / 2.0), -yaw_resolution / 2.0)
+        dirs = np.ones_like(steers)
+        dirs[1:len(dirs):2] = -1
+    else:
+        steers = np.arange(car_model.MAX_STEER, -(car_model.MAX_STEER + yaw_resolution), -yaw_resolution)
+        dirs = np.ones_like(steers)
     if len(steers) > _lib.HL_MAX_PRIMS:
         raise _lib.HeadlandError(f"{len(steers)} primitives exceed HL_MAX_PRIMS={_lib.HL_MAX_PRIMS}")
     p = _lib.HlSearchParams()
@@ -52,6 +56,8 @@ def make_search_params(car_model, motion_type="King", yaw_resolution=math.radian
     p.min_length_to_goal = c["MIN_LENGTH_TO_GOAL"]
     p.max_nodes = int(max_nodes)
     p.max_path_poses = int(max_path_poses)
+    p.motion_type = 0 if motion_type == "King" else 1
+    p.dubins_capacity = 0
     return p, np.vstack((steers, dirs)).T
 
 

@@ -113,6 +113,14 @@ class OrchardGeometryEnvironment(object):
     def check_path_feasibility(self, car_model, path, boundary_check=True, aux_check=False):
         return not bool(self.pose_flags(car_model, path, boundary_check, aux_check).any().item())
 
+    def get_min_distance_to_boundary(self, car_model, path, with_aux=True):
+        """orchard_geometry_environment.py:393-412: smallest signed distance of the swept footprint unions' exterior
+        vertices to the field boundary (negative outside) -- K10 ``hl_min_boundary_distance``, a batch of one path."""
+        path = np.asarray(path, dtype=np.float64)
+        d = ops.min_boundary_distance(self._env_batch(car_model), path[:, :3], np.array([0, len(path)], dtype=np.int64),
+                                      with_aux=with_aux)
+        return float(d[0].item())
+
     # ---- host-side topology helpers used by the orchestration (:49-64, 93-127, 199-248)
     def check_side_of_a_point(self, point):
         row_centers = np.mean(self.map_tree_rows[:, :, :], axis=1)

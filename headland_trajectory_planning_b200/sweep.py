@@ -28,8 +28,8 @@ def build_records(scns):
     return recs, scen, car0
 
 
-def search_params(car, step_size=0.2, max_nodes=400, max_path_poses=16384):
-    p, _ = make_search_params(car, "King", plan_resolution=step_size, max_nodes=max_nodes,
+def search_params(car, step_size=0.2, max_nodes=400, max_path_poses=16384, motion_type="King"):
+    p, _ = make_search_params(car, motion_type, plan_resolution=step_size, max_nodes=max_nodes,
                               max_path_poses=max_path_poses)
     return p
 

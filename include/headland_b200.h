@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define HL_ABI_VERSION 2
+#define HL_ABI_VERSION 3
 
 /* ---- limits (compile-time capacities of the kernels) ---------------------- */
 #define HL_MAX_PRIMS        16   /* motion primitives per expansion (King: 14, Pawn: 8) */
@@ -105,6 +105,9 @@ typedef struct {
     double min_length_to_goal;         /* :36 */
     int32_t max_nodes;                 /* hybrid_a_star_search(max_nodes=..), :497 */
     int32_t max_path_poses;            /* capacity of one scenario's output path */
+    int32_t motion_type;               /* 0 = "King" (Reeds-Shepp goal extension, :232-287), 1 = "Pawn" (forward primitives
+                                          :331-341, Dubins goal extension :184-230; pydubins parity unpinned) */
+    int32_t dubins_capacity;           /* Pawn: samples / course rows the Dubins scratch of one scenario holds (0 = 2048) */
 } HlSearchParams;
 
 /* One search problem: HybridAStarSearch(start_pose, goal_pose, env, car, heuristic). */

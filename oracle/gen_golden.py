@@ -187,6 +187,77 @@ def gen_astar_full(n):
     print("astar_full_golden.npz:", n, "scenarios; status histogram", np.bincount([status_code[r["status"]] for r in res]))
 
 
+SAMPLING_CASES = [
+    # (l_std, slope_deg, row_width, headland_width, aux, axle_to_front, start_row, end_row, dubins accuracy, rs accuracy)
+    (0.0, 10.0, 2.5, 9.0, "mower", 3.0, 1, 4, 0.5, 1.0),
+    (0.5, 10.0, 2.5, 8.0, "mower", 2.85, 2, 5, 0.6, 1.2),
+    (0.0, 0.0, 3.0, 10.0, "sprayer", 2.85, 1, 3, 0.7, 1.5),
+    (1.0, 5.0, 2.8, 9.0, "pruner", 3.0, 0, 2, 0.6, 1.2),
+    (0.0, 12.0, 2.5, 7.0, "none", 3.5, 3, 4, 0.5, 1.0),
+]
+_AUX = {"mower": [[[-1.84, 0.5], 1.0, 1.1]], "pruner": [[[3.259, -0.175], 1.325, 0.3]],
+        "sprayer": [[[-2.1, 1.0 / 2], 1.0, 1.22], [[-1.0, 4.3 / 2], 0.4, 0.5], [[-1.0, -4.3 / 2 + 0.4], 0.4, 0.5]], "none": []}
+
+
+def _sampling_objects(case):
+    from . import planner as OP
+    l_std, slope, rw, hw, aux, atf = case[:6]
+    np.random.seed(1)
+    rows = OP.create_tree_rows(8, rw, 20, slope_angle=math.radians(slope), l_std=l_std)
+    env = OP.OrchardGeometryEnvironment(rows, [], tree_width=0.3, headland_width=hw)
+    car = OP.CarModel(max_steer=0.55, axle_to_front=atf, axle_to_back=0.55, width=1.48, aux_poly_features=_AUX[aux],
+                      with_aux=bool(_AUX[aux]))
+    return rows, env, car
+
+
+def _sampling_one(k):
+    """The REFERENCE's own sampling / turn functions (path_planner/safety_forward_path_plan.py, loaded unmodified with
+    ``dubins`` := oracle.dubins_port and the oracle's duck-typed environment / car) on one case."""
+    from . import ref_loader
+    case = SAMPLING_CASES[k]
+    rows, env, car = _sampling_objects(case)
+    ref = ref_loader.load_planner("safety_forward_path_plan", dubins_port=True)
+    s_row, e_row, acc_d, acc_r = case[6:]
+    out = {"case": k}
+
+    def pack(r):
+        return np.full(8, np.nan) if r is None else np.concatenate([np.asarray(r[0], float), np.asarray(r[1], float), [r[2], r[3]]])
+    out["dubins"] = pack(_quiet(ref.sample_start_end_pose_for_dubins, rows, s_row, e_row, car, env, accuracy=acc_d))
+    out["rs"] = pack(_quiet(ref.sample_start_end_pose_for_reeds_shepp, rows, s_row, e_row, car, env, accuracy=acc_r))
+    out["circle"] = pack(_quiet(ref.sample_start_end_pose_for_circle_back, rows, s_row, s_row + 1, car, env))
+    start, end = ref.get_start_end_pose(rows, s_row, s_row + 1)
+    out["circle_path"] = np.asarray(_quiet(ref.get_circle_back_path_full, np.asarray(start, float), end, 1.0 / car.curvature, car))
+    sb = ref.get_base_pose(s_row, rows, 0.3, pose_type=ref.LEAVE_POSE)
+    eb = ref.get_base_pose(e_row, rows, 0.5, pose_type=ref.ENTER_POSE)
+    sb[0] -= 1.5
+    eb[0] -= 1.0
+    dp = np.asarray(_quiet(ref.get_dubins_path_full, sb, eb, 1.0 / car.curvature))
+    out["dubins_pair"] = np.concatenate([sb, eb])
+    out["dubins_path"] = dp
+    out["dubins_min_dist"] = env.get_min_distance_to_boundary(car, dp[:, :3], with_aux=True)
+    out["dubins_feasible"] = env.check_path_feasibility(car, dp[:, :3], boundary_check=False, aux_check=True)
+    return out
+
+
+def gen_sampling():
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(min(len(SAMPLING_CASES), os.cpu_count())) as pool:
+        res = pool.map(_sampling_one, range(len(SAMPLING_CASES)), chunksize=1)
+    np.savez_compressed(
+        os.path.join(GOLD, "sampling_golden.npz"),
+        dubins=np.array([r["dubins"] for r in res]), rs=np.array([r["rs"] for r in res]),
+        circle=np.array([r["circle"] for r in res]),
+        circle_path=np.concatenate([r["circle_path"] for r in res]),
+        circle_path_len=np.array([len(r["circle_path"]) for r in res]),
+        dubins_pair=np.array([r["dubins_pair"] for r in res]),
+        dubins_path=np.concatenate([r["dubins_path"] for r in res]),
+        dubins_path_len=np.array([len(r["dubins_path"]) for r in res]),
+        dubins_min_dist=np.array([r["dubins_min_dist"] for r in res]),
+        dubins_feasible=np.array([r["dubins_feasible"] for r in res]))
+    print("sampling_golden.npz:", len(res), "cases;", [tuple(np.round(r["dubins"][6:], 2)) for r in res],
+          [tuple(np.round(r["rs"][6:], 2)) for r in res], [tuple(np.round(r["circle"][6:], 2)) for r in res])
+
+
 YPARK_PARAM_SETS = [
     # (max_steer_backward, max_steer_forward, max_backward_distance, max_forward_distance,
     #  min_forward_distance, min_backward_distance, min_steer_backward, min_steer_forward, step)
@@ -271,6 +342,52 @@ def gen_astar_ref(n):
                         path=np.concatenate([r["path"] for r in res]))
     print("astar_ref_golden.npz:", n, "scenarios run by the reference's own search loop; counters",
           [r["counter"] for r in res][:24])
+
+
+PAWN_MAX_NODES = 120
+
+
+def _pawn_one(i):
+    """Pawn mode (forward primitives + Dubins goal extension) on config-5 scenario i, step 0.2 m: the REFERENCE's own
+    hybrid_a_star_search.py (dubins := oracle.dubins_port, heapdict := the port, oracle geometry) next to the oracle's
+    restatement; both must agree before the golden is written.  The expanded-key sequence comes from the oracle."""
+    from . import baseline as OB
+    from . import planner as OP
+    from . import ref_loader
+    sys.path.insert(0, os.path.dirname(HERE))
+    from headland_trajectory_planning_b200 import scenarios as SC
+    R = ref_loader.load_planner("hybrid_a_star_search", dubins_port=True)
+    sp = SC.scenario_spec(i)
+    scn = SC.finalize(sp, OB.candidate_feasibility(sp))
+    env = OP.OrchardGeometryEnvironment(scn["rows"], [], tree_width=scn["tree_width"], headland_width=scn["headland_width"])
+    car = OP.CarModel(**scn["car"])
+    heur = OP.ReferenceLineHeuristic(scn["waypoints"], scn["goal"], car)
+    s = _quiet(R.HybridAStarSearch, scn["start"], scn["goal"], env, car, heur, motion_type="Pawn", plan_resolution=scn["step_size"])
+    x, y, yaw, dirs, ks, counter = _quiet(s.hybrid_a_star_search, max_nodes=PAWN_MAX_NODES)
+    o = OP.HybridAStarSearch(scn["start"], scn["goal"], env, car, heur, motion_type="Pawn", plan_resolution=scn["step_size"])
+    ox, oy, oyaw, odirs, oks, ocounter = _quiet(o.hybrid_a_star_search, max_nodes=PAWN_MAX_NODES)
+    assert counter == ocounter and len(x) == len(ox), (i, counter, ocounter)
+    if len(x):
+        assert np.array_equal(np.asarray(x, float), np.asarray(ox, float)) and np.array_equal(np.asarray(ks, float), np.asarray(oks, float))
+    path = np.stack([np.asarray(x, float), np.asarray(y, float), np.asarray(yaw, float), np.asarray(ks, float),
+                     np.asarray(dirs, float)], axis=1).reshape(-1, 5)
+    status_code = {"ok": 0, "start_goal_blocked": 1, "open_empty": 2, "max_nodes": 3}
+    return dict(index=i, counter=int(counter), path=path, status=status_code[o.status],
+                expanded=np.array(o.expanded, dtype=np.int32).reshape(-1, 3), feas=np.array(OB.candidate_feasibility(sp), dtype=bool))
+
+
+def gen_pawn(n):
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(os.cpu_count()) as pool:
+        res = pool.map(_pawn_one, range(n), chunksize=1)
+    np.savez_compressed(os.path.join(GOLD, "pawn_golden.npz"), index=np.array([r["index"] for r in res]),
+                        status=np.array([r["status"] for r in res]), counter=np.array([r["counter"] for r in res]),
+                        n_expanded=np.array([len(r["expanded"]) for r in res]),
+                        expanded=np.concatenate([r["expanded"] for r in res]),
+                        path_len=np.array([len(r["path"]) for r in res]), path=np.concatenate([r["path"] for r in res]),
+                        feas=np.array([r["feas"] for r in res]), max_nodes=np.array(PAWN_MAX_NODES))
+    print("pawn_golden.npz:", n, "scenarios (reference loop == oracle); counters", [r["counter"] for r in res][:32],
+          "status", np.bincount([r["status"] for r in res]))
 
 
 def _offset_one(i):
@@ -365,6 +482,10 @@ if __name__ == "__main__":
         gen_df()
     if "astar" in args:
         gen_astar(int(args[args.index("astar") + 1]))
+    if "pawn" in args:
+        gen_pawn(int(args[args.index("pawn") + 1]))
+    if "sampling" in args:
+        gen_sampling()
     if "astar_full" in args:
         gen_astar_full(int(args[args.index("astar_full") + 1]))
     if "astar_ref" in args:

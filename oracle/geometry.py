@@ -358,3 +358,67 @@ class Lane:
             if ((u > x0) & (u < x1) & (w > y0) & (w < y1)).any():
                 return False
         return True
+
+
+# ------------------------------------------------- union of footprint rectangles: boundary vertices
+def union_boundary_vertices(poses, ext, tol=1e-12):
+    """Vertices of ``unary_union`` of the rectangles ``ext`` at ``poses`` (car_model.py:39-53): rectangle corners that
+    no other rectangle covers (strictly) plus proper crossings of two rectangles' edges that no third rectangle
+    covers.  GEOS is unavailable: this DEFINES the vertex set for the oracle (parity unpinned); vertices on holes of
+    the union, which ``.exterior`` would skip, are included."""
+    poses = np.asarray(poses, dtype=np.float64).reshape(-1, 3)
+    R = len(poses)
+    corners = rect_corners(poses, ext)                      # (R,4,2)
+    c, s = np.cos(poses[:, 2]), np.sin(poses[:, 2])
+    x0, x1, y0, y1 = ext
+
+    def covered(pts, skip):
+        """pts (M,2); skip: list of rectangle indices per point not to test -> (M,) bool"""
+        dx = pts[:, None, 0] - poses[None, :, 0]
+        dy = pts[:, None, 1] - poses[None, :, 1]
+        u = c[None, :] * dx + s[None, :] * dy
+        w = c[None, :] * dy - s[None, :] * dx
+        ins = (u > x0 + tol) & (u < x1 - tol) & (w > y0 + tol) & (w < y1 - tol)
+        for m, sk in enumerate(skip):
+            ins[m, list(sk)] = False
+        return ins.any(axis=1)
+
+    pts = corners.reshape(-1, 2)
+    keep = ~covered(pts, [(i // 4,) for i in range(4 * R)])
+    out = [pts[keep]]
+    cross, skips = [], []
+    for i in range(R):
+        A0 = corners[i]
+        A1 = np.roll(A0, -1, axis=0)
+        for j in range(i + 1, R):
+            B0 = corners[j]
+            B1 = np.roll(B0, -1, axis=0)
+            r = (A1 - A0)[:, None, :]
+            sv = (B1 - B0)[None, :, :]
+            qp = B0[None, :, :] - A0[:, None, :]
+            den = r[..., 0] * sv[..., 1] - r[..., 1] * sv[..., 0]
+            with np.errstate(divide="ignore", invalid="ignore"):
+                t = (qp[..., 0] * sv[..., 1] - qp[..., 1] * sv[..., 0]) / den
+                uu = (qp[..., 0] * r[..., 1] - qp[..., 1] * r[..., 0]) / den
+            hit = (np.abs(den) >= 1e-14) & (t >= 0) & (t <= 1) & (uu >= 0) & (uu <= 1)
+            for a, b in zip(*np.nonzero(hit)):
+                cross.append(A0[a] + t[a, b] * (A1[a] - A0[a]))
+                skips.append((i, j))
+    if cross:
+        cross = np.array(cross)
+        out.append(cross[~covered(cross, skips)])
+    return np.concatenate(out)
+
+
+def signed_distance_to_ring(pts, poly):
+    """Distance of every point to the ring of ``poly``, negative unless the point is strictly inside."""
+    pts = np.asarray(pts, dtype=np.float64).reshape(-1, 2)
+    best = np.full(len(pts), np.inf)
+    n = len(poly)
+    for i in range(n):
+        a, b = poly[i], poly[(i + 1) % n]
+        e = b - a
+        t = np.clip(((pts[:, 0] - a[0]) * e[0] + (pts[:, 1] - a[1]) * e[1]) / (e[0] * e[0] + e[1] * e[1]), 0.0, 1.0)
+        best = np.minimum(best, np.hypot(pts[:, 0] - (a[0] + t * e[0]), pts[:, 1] - (a[1] + t * e[1])))
+    inside = points_in_closed_polygon(pts[:, 0], pts[:, 1], poly) & (best > 0)
+    return np.where(inside, best, -best)

@@ -78,6 +78,11 @@ def get_base_pose(row_id, map_tree_rows, min_offset, side=NEAR_SIDE, pose_type=L
 
 
 # ------------------------------------------------------------------ car model
+class _Bounds:
+    def __init__(self, ext):
+        self.bounds = (ext[0], ext[2], ext[1], ext[3])
+
+
 class CarModel:
     def __init__(self, max_steer=0.55, wheel_base=1.9, axle_to_front=2.85, axle_to_back=0.5,
                  width=1.48, head_out=0.542, head_side=0.44, body_vertices=[],
@@ -91,6 +96,26 @@ class CarModel:
         self.with_aux = with_aux
         self.body_ext = geo.body_extent(axle_to_back, axle_to_front, width)
         self.aux_exts = [geo.aux_extent(f) for f in aux_poly_features] if with_aux else []
+        # what the orchestration code reads from the shapely polygons: .bounds = (minx, miny, maxx, maxy)
+        self.car_poly = _Bounds(self.body_ext)
+        self.aux_polys = [_Bounds(e) for e in self.aux_exts]
+
+    def calculate_motion_path_new(self, init_pose, motion_dir, steer_dir, turning_radius, delta_yaw, step_size=0.1):
+        """car_model.py:236-269."""
+        turning_radius = max(1.0 / self.curvature, turning_radius)
+        steer_angle = math.atan(self.WHEEL_BASE / turning_radius) * steer_dir
+        arc_length = abs(delta_yaw * turning_radius)
+        num_steps = int(arc_length / step_size)
+        actual_step_size = arc_length / num_steps
+        yaw_step = motion_dir * actual_step_size / self.WHEEL_BASE * math.tan(steer_angle)
+        init_x, init_y = init_pose[0], init_pose[1]
+        init_yaw = angle_wrap(init_pose[-1])
+        yaws = angle_wrap(np.linspace(init_yaw, init_yaw + yaw_step * num_steps, num_steps + 1))
+        xs = init_x + turning_radius * (np.sin(yaws) - np.sin(init_yaw)) * steer_dir
+        ys = init_y - turning_radius * (np.cos(yaws) - np.cos(init_yaw)) * steer_dir
+        path = np.vstack([init_pose, np.vstack([xs, ys, yaws]).T])
+        curvature = math.tan(steer_angle) / self.WHEEL_BASE if abs(steer_angle) > 0.00001 else 0
+        return np.hstack((path, np.ones((len(path), 1)) * curvature, np.ones((len(path), 1)) * motion_dir))
 
     def get_turn_radius(self, max_steer_angle=None):
         if max_steer_angle is None:
@@ -182,6 +207,16 @@ class OrchardGeometryEnvironment:
     def check_path_feasibility(self, car_model, path, boundary_check=True, aux_check=False):
         """orchard_geometry_environment.py:423-458."""
         return not self.pose_flags(car_model, path, boundary_check, aux_check).any()
+
+    def get_min_distance_to_boundary(self, car_model, path, with_aux=True):
+        """orchard_geometry_environment.py:393-412 (the union's vertex set is oracle.geometry.union_boundary_vertices)."""
+        path = np.asarray(path, dtype=np.float64)
+        pts = [geo.union_boundary_vertices(path[:, :3], car_model.body_ext)]
+        if with_aux:
+            for ext in car_model.aux_exts:
+                pts.append(geo.union_boundary_vertices(path[0:len(path):2, :3], ext))
+        d = geo.signed_distance_to_ring(np.concatenate(pts), geo.ccw(self.field_poly))
+        return float(d.min())
 
     def get_row_ids_between_start_and_end(self, start_pose, end_pose):
         """orchard_geometry_environment.py:93-127."""

@@ -72,7 +72,7 @@ class _StubModule(types.ModuleType):
 _ABSENT = ("shapely", "heapdict", "dubins", "skspatial", "matplotlib", "casadi", "cv2")
 
 
-def load_planner(name, heapdict_port=True):
+def load_planner(name, heapdict_port=True, dubins_port=False):
     """Import ``path_planner/<name>.py`` of the reference FOR REAL, with the absent third-party packages
     (shapely, heapdict, dubins, skspatial, ...) replaced by inert stubs.  Everything that does not touch those
     packages -- the Y-type parking sweep, the motion-path rollout, the odom transform
@@ -109,6 +109,9 @@ def load_planner(name, heapdict_port=True):
             hd = types.ModuleType("heapdict")
             hd.heapdict = _hp.HeapDict
             sys.modules["heapdict"] = hd
+        if dubins_port:                        # ``import dubins`` resolves to the restated dubins.c (oracle.dubins_port)
+            from . import dubins_port as _dp
+            sys.modules["dubins"] = _dp
         sys.path.insert(0, os.path.join(REFERENCE_ROOT, "path_planner", "utils"))   # notebooks put both on sys.path
         sys.path.insert(0, os.path.join(REFERENCE_ROOT, "path_planner"))
         return importlib.import_module(name)

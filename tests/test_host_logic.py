@@ -118,8 +118,14 @@ def test_search_params_table():
         st, d = o.motion_steers[i]
         assert p.prim_yaw_step[i] == d * 0.2 / 1.9 * math.tan(st)
         assert p.prim_curv[i] == np.tan(st) / 1.9
-    with pytest.raises(NotImplementedError):
-        make_search_params(car, "Pawn")
+    # Pawn (hybrid_a_star_search.py:331-341): 8 forward-only steers, the last one beyond -MAX_STEER
+    pp, psteers = make_search_params(car, "Pawn", plan_resolution=0.1)
+    op = OP.HybridAStarSearch([0, 0, 0], [1, 1, 0], None, OP.CarModel(max_steer=0.55, axle_to_front=3, axle_to_back=0.55, width=1.48),
+                              None, motion_type="Pawn", plan_resolution=0.1)
+    assert pp.n_prims == 8 and pp.motion_type == 1 and np.array_equal(psteers, op.motion_steers)
+    assert (psteers[:, 1] == 1).all() and abs(psteers[-1, 0] + 0.67173048) < 1e-8
+    with pytest.raises(ValueError):
+        make_search_params(car, "Rook")
 
 
 def test_scenarios_are_deterministic_plain_data():
