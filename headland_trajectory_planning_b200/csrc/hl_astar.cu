@@ -925,7 +925,7 @@ extern "C" int hl_hybrid_astar_batch(hl_ctx* ctx, const hl_env_batch* envs, cons
     // The node/hash workspace, the work-queue counter and the level variant's state are PER CONTEXT: the host part
     // runs under the context mutex and the launch waits for the previous search of this context (event recorded
     // below), so searches issued from several threads or streams of one device serialise instead of sharing scratch.
-    std::lock_guard<std::recursive_mutex> lock(*(std::recursive_mutex*)ctx->mu);
+    std::lock_guard<std::recursive_mutex> lock(*(std::recursive_mutex*)ctx->ws_mu);
     // variant: "spec" = two warps per scenario with the analytic shot decoupled (hl_astar_spec.cuh),
     // "warp" = one warp per scenario, "level" = level-synchronous graph (hl_ctx_set_astar_variant / HL_ASTAR_VARIANT
     // at context creation; A/B runs only, the results are identical).

@@ -73,6 +73,8 @@ struct hl_ctx {
     size_t env_cache_bytes[2];
     void* copy_stream;        // non-blocking stream of hl_env_upload's H2D copy (does not wait for running kernels)
     void* mu;                 // std::recursive_mutex*: one upload / cache hand-over at a time (uploads may come from a prefetch thread)
+    void* ws_mu;              // std::recursive_mutex*: the search workspace / variant (NOT `mu`: a search must be launchable
+                              // while a prefetch thread spends milliseconds inside hl_env_upload)
     void* ls_state;           // level-synchronous search: graph, streams, pools (hl_astar.cu)
     void (*ls_free)(void*);
     int astar_variant;        // HL_ASTAR_SPEC / _WARP / _LEVEL (HL_ASTAR_VARIANT read ONCE at hl_ctx_create; hl_ctx_set_astar_variant)

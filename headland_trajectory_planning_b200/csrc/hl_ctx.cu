@@ -54,6 +54,7 @@ extern "C" int hl_ctx_create(hl_ctx** out, int device) {
     c->ls_free = nullptr;
     c->copy_stream = nullptr;
     c->mu = new std::recursive_mutex();
+    c->ws_mu = new std::recursive_mutex();
     {
         cudaStream_t cs = nullptr;
         if (cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) == cudaSuccess) c->copy_stream = cs;
@@ -73,6 +74,7 @@ extern "C" int hl_ctx_create(hl_ctx** out, int device) {
         if (c->astar_done) cudaEventDestroy((cudaEvent_t)c->astar_done);
         if (c->copy_stream) cudaStreamDestroy((cudaStream_t)c->copy_stream);
         delete (std::recursive_mutex*)c->mu;
+        delete (std::recursive_mutex*)c->ws_mu;
         delete c;
         return 1;
     }
@@ -86,7 +88,7 @@ extern "C" int hl_env_device(const hl_env_batch* envs) { return envs ? envs->dev
 
 extern "C" int hl_ctx_set_astar_variant(hl_ctx* ctx, int variant) {
     if (!ctx || variant < HL_ASTAR_SPEC || variant > HL_ASTAR_LEVEL) { hl_set_error("hl_ctx_set_astar_variant: bad arguments"); return 1; }
-    std::lock_guard<std::recursive_mutex> lock(*(std::recursive_mutex*)ctx->mu);
+    std::lock_guard<std::recursive_mutex> lock(*(std::recursive_mutex*)ctx->ws_mu);
     ctx->astar_variant = variant;
     return 0;
 }
@@ -127,6 +129,7 @@ extern "C" void hl_ctx_destroy(hl_ctx* ctx) {
     if (ctx->copy_stream) cudaStreamDestroy((cudaStream_t)ctx->copy_stream);
     if (ctx->astar_done) cudaEventDestroy((cudaEvent_t)ctx->astar_done);
     delete (std::recursive_mutex*)ctx->mu;
+    delete (std::recursive_mutex*)ctx->ws_mu;
     delete ctx;
 }
 

@@ -46,29 +46,53 @@ def algorithmic_flops(recs, results, field="n_pose_checks_ref"):
 
 
 _PATH_FIELDS = (("x", 8), ("y", 8), ("yaw", 8), ("k", 8), ("dir", 1))
+_SECTIONS = (("results", None), ("expanded", 12)) + _PATH_FIELDS
 
 
-def _pack_layout(n_rows, kmax, pmax):
-    """Byte offsets of one rank's packed sweep output: result records | expanded keys | x | y | yaw | k | dir,
-    every section 16-byte aligned."""
-    al = lambda v: (v + 15) & ~15
+def _gather_layout(sizes, keys_cap, path_cap):
+    """Byte layout of rank 0's gathered buffer: one SECTION per output array (result records | expanded keys | x | y |
+    yaw | k | dir), and inside a section the ranks' pieces back to back in rank order -- i.e. the rank-major pools
+    ``merge_shards`` hands out, so that nothing is copied again after the gather.  ``sizes`` is [world, 3] = (key rows,
+    path poses, records) per rank.  Returns (per-section byte offsets [world + 1], per-rank counts, total bytes)."""
+    kused = np.minimum(sizes[:, 0], keys_cap).astype(np.int64)
+    pused = np.minimum(sizes[:, 1], path_cap).astype(np.int64)
+    nrec = sizes[:, 2].astype(np.int64)
     off, o = {}, 0
-    off["results"] = o; o += al(n_rows * _lib.RESULT_DTYPE.itemsize)
-    off["expanded"] = o; o += al(kmax * 12)
-    for name, w in _PATH_FIELDS:
-        off[name] = o; o += al(pmax * w)
-    return off, o
+    for name, w in _SECTIONS:
+        if name == "results":
+            nbytes = nrec * _lib.RESULT_DTYPE.itemsize
+        elif name == "expanded":
+            nbytes = kused * w
+        else:
+            nbytes = pused * w
+        off[name] = o + np.concatenate([[0], np.cumsum(nbytes)])
+        o = (int(off[name][-1]) + 15) & ~15
+    return off, (kused, pused, nrec), max(o, 16)
+
+
+def _piece(out, name, count):
+    """uint8 view of the used part of one output array of this rank."""
+    import torch
+    if name == "results":
+        return out["results"].reshape(-1)[:count * _lib.RESULT_DTYPE.itemsize]
+    if name == "expanded":
+        return out["expanded"][:count].reshape(-1).view(torch.uint8)
+    return out[name][:count].view(torch.uint8)
 
 
 def gather_sweep(out, world_size, rank):
     """The one data-path collective of a sweep: every rank's search output -- ``ops.hybrid_astar_batch(...,
     to_host=False)``, still on the device -- goes to rank 0 over NCCL / NVLink and is copied to the host ONCE, there.
     Two collectives: an all_gather of three int64 per rank (key rows, path poses, records: what each rank produced)
-    and one gather of a packed byte buffer padded to the largest rank.  Ranks other than 0 never copy anything to
-    the host.  With CPU tensors in ``out`` the same code runs over gloo (tests/test_sweep_gloo.py).
+    and one grouped send / recv (a gatherv: every rank sends exactly the used part of each output array, straight from
+    the search's own buffers, and rank 0 receives each piece at its FINAL place in the rank-major pools -- no padding,
+    no packing copy, no merge copy).  Ranks other than 0 never copy anything to the host.  With CPU tensors in ``out``
+    the same code runs over gloo (tests/test_sweep_gloo.py).
 
-    Returns on rank 0 a list (one entry per rank) of host dicts with ``results`` (structured), ``expanded``
-    [rows, 3] int32 and the pooled path arrays ``x, y, yaw, k, dir``; ``None`` on the other ranks."""
+    Returns on rank 0 a dict with the rank-major host pools ``expanded`` [rows, 3] int32, ``x, y, yaw, k, dir``, the
+    structured ``results`` of all ranks rank-major, and ``counts`` = per-rank (key rows, path poses, records) for
+    ``merge_shards``; ``None`` on the other ranks.  The host arrays are views of one pinned buffer that the NEXT
+    gather_sweep call overwrites (copy what must outlive it)."""
     import torch
     import torch.distributed as dist
     res = out["results"]
@@ -80,42 +104,46 @@ def gather_sweep(out, world_size, rank):
     sizes = torch.empty(3 * world_size, dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(sizes, mine)
     sizes = sizes.cpu().numpy().reshape(world_size, 3)               # the step's one host sync on every rank
-    kused = np.minimum(sizes[:, 0], keys_cap)
-    pused = np.minimum(sizes[:, 1], path_cap)
-    kmax, pmax, n_rows = int(kused.max()), int(pused.max()), int(sizes[:, 2].max())
-    off, total = _pack_layout(n_rows, kmax, pmax)
-    buf = torch.empty(total, dtype=torch.uint8, device=dev)
-    nb = n * _lib.RESULT_DTYPE.itemsize
-    buf[off["results"]:off["results"] + nb].copy_(res.reshape(-1)[:nb])
-    k_me, p_me = int(kused[rank]), int(pused[rank])
-    if k_me:
-        buf[off["expanded"]:off["expanded"] + 12 * k_me].copy_(out["expanded"][:k_me].reshape(-1).view(torch.uint8))
-    for name, w in _PATH_FIELDS:
-        if p_me:
-            buf[off[name]:off[name] + w * p_me].copy_(out[name][:p_me].view(torch.uint8))
+    off, (kused, pused, nrec), total = _gather_layout(sizes, keys_cap, path_cap)
+    count_of = {"results": nrec, "expanded": kused}
     if rank != 0:
-        dist.gather(buf, None, dst=0)
+        ops_ = []
+        for name, _ in _SECTIONS:
+            c = int(count_of.get(name, pused)[rank])
+            if c:
+                ops_.append(dist.P2POp(dist.isend, _piece(out, name, c), 0))
+        for w in (dist.batch_isend_irecv(ops_) if ops_ else []):
+            w.wait()
         return None
-    big = torch.empty((world_size, total), dtype=torch.uint8, device=dev)
-    dist.gather(buf, list(big.unbind(0)), dst=0)
+    big = torch.empty(total, dtype=torch.uint8, device=dev)
+    ops_ = []
+    for name, _ in _SECTIONS:
+        o = off[name]
+        c0 = int(count_of.get(name, pused)[0])
+        if c0:
+            big[int(o[0]):int(o[1])].copy_(_piece(out, name, c0))
+        for r in range(1, world_size):
+            if o[r + 1] > o[r]:
+                ops_.append(dist.P2POp(dist.irecv, big[int(o[r]):int(o[r + 1])], r))
+    for w in (dist.batch_isend_irecv(ops_) if ops_ else []):
+        w.wait()
     if big.is_cuda:
-        host = _pinned(world_size * total).view(world_size, total)
+        host = _pinned(total)
         host.copy_(big, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         host = host.numpy()
     else:
         host = big.numpy()
-    shards = []
-    for r in range(world_size):
-        row = host[r]
-        nr, kr, pr = int(sizes[r, 2]), int(kused[r]), int(pused[r])
-        d = {"results": row[off["results"]:off["results"] + nr * _lib.RESULT_DTYPE.itemsize].view(_lib.RESULT_DTYPE),
-             "expanded": row[off["expanded"]:off["expanded"] + 12 * kr].view(np.int32).reshape(-1, 3),
-             "keys_used": int(sizes[r, 0]), "used": int(sizes[r, 1]), "n": nr}
-        for name, w in _PATH_FIELDS:
-            d[name] = row[off[name]:off[name] + w * pr].view(np.float64 if w == 8 else np.int8)
-        shards.append(d)
-    return shards
+    g = {"counts": np.stack([kused, pused, nrec], axis=1), "keys_produced": sizes[:, 0].copy(), "poses_produced": sizes[:, 1].copy()}
+    for name, w in _SECTIONS:
+        sec = host[int(off[name][0]):int(off[name][-1])]
+        if name == "results":
+            g[name] = sec.view(_lib.RESULT_DTYPE)
+        elif name == "expanded":
+            g[name] = sec.view(np.int32).reshape(-1, 3)
+        else:
+            g[name] = sec.view(np.float64 if w == 8 else np.int8)
+    return g
 
 
 _pinned_cache = {}
@@ -126,31 +154,30 @@ def _pinned(nbytes):
     import torch
     t = _pinned_cache.get("buf")
     if t is None or t.numel() < nbytes:
-        t = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8).pin_memory()
+        t = torch.empty(max(nbytes + nbytes // 4, 1 << 20), dtype=torch.uint8).pin_memory()
         _pinned_cache["buf"] = t
     return t[:nbytes]
 
 
-def merge_shards(shards, n_total, world_size):
-    """Undo the interleaved sharding (record i of rank r is scenario r + i*world_size).  The per-rank key and path
-    pools are concatenated rank-major and the records' ``keys_offset`` / ``path_offset`` rebased into them, so
-    nothing is re-ordered pose by pose.  Returns a host dict shaped like ``ops.hybrid_astar_batch(to_host=True)``
-    (``ops.expanded_of`` / ``hybrid_a_star_search.unpack_path`` work on it)."""
+def merge_shards(gathered, n_total, world_size):
+    """Undo the interleaved sharding (record i of rank r is scenario r + i*world_size).  The key and path pools stay
+    rank-major exactly as ``gather_sweep`` received them (views, not copies); only the 80-byte result records are
+    put back into scenario order, their ``keys_offset`` / ``path_offset`` rebased into the pools.  Returns a host dict
+    shaped like ``ops.hybrid_astar_batch(to_host=True)`` (``ops.expanded_of`` / ``hybrid_a_star_search.unpack_path``
+    work on it)."""
+    counts = gathered["counts"]
     res = np.zeros(n_total, dtype=_lib.RESULT_DTYPE)
-    kbase = pbase = 0
+    kbase = pbase = rbase = 0
     for r in range(world_size):
-        sh = shards[r]
         idx = np.arange(r, n_total, world_size)
-        rr = np.array(sh["results"][:len(idx)])
+        rr = np.array(gathered["results"][rbase:rbase + len(idx)])
         rr["keys_offset"] += kbase
         rr["path_offset"] += pbase
         res[idx] = rr
-        kbase += len(sh["expanded"])
-        pbase += len(sh["x"])
-    merged = {"results": res, "n": n_total, "keys_used": kbase, "used": pbase,
-              "expanded": np.concatenate([sh["expanded"] for sh in shards]) if shards else np.zeros((0, 3), np.int32)}
+        kbase += int(counts[r, 0]); pbase += int(counts[r, 1]); rbase += int(counts[r, 2])
+    merged = {"results": res, "n": n_total, "keys_used": kbase, "used": pbase, "expanded": gathered["expanded"]}
     for name, _ in _PATH_FIELDS:
-        merged[name] = np.concatenate([sh[name] for sh in shards])
+        merged[name] = gathered[name]
     return merged
 
 
