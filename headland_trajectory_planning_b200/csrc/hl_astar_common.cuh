@@ -134,54 +134,78 @@ __device__ __noinline__ int hash_find(const AsWs& w, int hmask, long long key, i
 }
 
 // ---- heapdict replay (oracle/heapdict_port.py) on (hprio, hslot) with nheap[] positions
-__device__ __forceinline__ void heap_swap(const AsWs& w, int i, int j) {
-    double pi = w.hprio[i], pj = w.hprio[j];
-    int si = w.hslot[i], sj = w.hslot[j];
-    w.hprio[i] = pj; w.hslot[i] = sj; w.nheap[sj] = i;
-    w.hprio[j] = pi; w.hslot[j] = si; w.nheap[si] = j;
-}
+// heapdict moves entries by swaps; here the moving entry is carried in registers and the entries it passes are
+// shifted into the hole -- the arrangement after every operation is the one the swaps produce (comparisons look at the
+// priority only, strict `<`, left child first), with half the memory operations on the dependent chain.
+// The first HS heap positions (the top log2(HS+1) levels, where every sift spends most of its steps) may live in
+// SHARED memory (sp / ss): an LDS is ~30 cycles, a workspace load that misses L1 several hundred, and the sifts are a
+// serial chain on one lane (K4 spec variant: pop + merge were 25 % of the expander's time on global memory).
+template <int HS> struct HeapRef {
+    const AsWs& w; double* sp; int* ss;
+    __device__ __forceinline__ double prio(int i) const { return (HS > 0 && i < HS) ? sp[i] : w.hprio[i]; }
+    __device__ __forceinline__ int slot(int i) const { return (HS > 0 && i < HS) ? ss[i] : w.hslot[i]; }
+    __device__ __forceinline__ void put(int i, double p, int s) const {
+        if (HS > 0 && i < HS) { sp[i] = p; ss[i] = s; } else { w.hprio[i] = p; w.hslot[i] = s; }
+        w.nheap[s] = i;
+    }
+};
 
-__device__ __noinline__ void heap_decrease_key(const AsWs& w, int i) {
+// _decrease_key (or, with `always`, the unconditional bubbling of __delitem__) of the entry (prio, slot) at position i
+template <int HS> __device__ __forceinline__ void heap_up_t(const HeapRef<HS>& H, int i, double prio, int slot, bool always) {
     while (i) {
-        int parent = (i - 1) >> 1;
-        if (w.hprio[parent] < w.hprio[i]) break;
-        heap_swap(w, i, parent);
+        const int parent = (i - 1) >> 1;
+        const double pp = H.prio(parent);
+        if (!always && pp < prio) break;
+        H.put(i, pp, H.slot(parent));
         i = parent;
     }
+    H.put(i, prio, slot);
 }
 
-__device__ __noinline__ int heap_popitem(const AsWs& w, int& n) {
-    int top = w.hslot[0];
+template <int HS> __device__ __forceinline__ int heap_popitem_t(const HeapRef<HS>& H, int& n) {
+    const int top = H.slot(0);
     --n;
     if (n > 0) {
-        w.hprio[0] = w.hprio[n]; w.hslot[0] = w.hslot[n]; w.nheap[w.hslot[0]] = 0;
+        const double prio = H.prio(n);                 // heap[0] = heap.pop(); _min_heapify(0)
+        const int slot = H.slot(n);
         int i = 0;
         while (true) {
-            int l = (i << 1) + 1, r = (i + 1) << 1, low = i;
-            if (l < n && w.hprio[l] < w.hprio[i]) low = l;
-            if (r < n && w.hprio[r] < w.hprio[low]) low = r;
+            const int l = (i << 1) + 1, r = l + 1;
+            int low = i;
+            double lowp = prio;
+            if (l < n) {
+                const double pl = H.prio(l);
+                const double pr = (r < n) ? H.prio(r) : 0.0;
+                if (pl < lowp) { low = l; lowp = pl; }
+                if (r < n && pr < lowp) { low = r; lowp = pr; }
+            }
             if (low == i) break;
-            heap_swap(w, i, low);
+            H.put(i, lowp, H.slot(low));
             i = low;
         }
+        H.put(i, prio, slot);
     }
-    w.nheap[top] = -1;
+    H.w.nheap[top] = -1;
     return top;
 }
 
-__device__ __noinline__ void heap_set(const AsWs& w, int& n, int slot, double prio) {
-    if (w.nheap[slot] >= 0) {                      // __setitem__ on an existing key: pop(key) first
-        int i = w.nheap[slot];
-        while (i) {                                // __delitem__: bubble to the root unconditionally
-            int parent = (i - 1) >> 1;
-            heap_swap(w, i, parent);
-            i = parent;
-        }
-        heap_popitem(w, n);
+template <int HS> __device__ __forceinline__ void heap_set_t(const HeapRef<HS>& H, int& n, int slot, double prio) {
+    const int at = H.w.nheap[slot];
+    if (at >= 0) {                                     // __setitem__ on an existing key: pop(key) first
+        heap_up_t<HS>(H, at, 0.0, slot, true);         // __delitem__: bubble to the root unconditionally
+        heap_popitem_t<HS>(H, n);
     }
-    int i = n++;
-    w.hprio[i] = prio; w.hslot[i] = slot; w.nheap[slot] = i;
-    heap_decrease_key(w, i);
+    heap_up_t<HS>(H, n++, prio, slot, false);
+}
+
+// workspace-only heap (one-warp-per-scenario and level-synchronous variants)
+__device__ __noinline__ int heap_popitem(const AsWs& w, int& n) {
+    const HeapRef<0> H{w, nullptr, nullptr};
+    return heap_popitem_t<0>(H, n);
+}
+__device__ __noinline__ void heap_set(const AsWs& w, int& n, int slot, double prio) {
+    const HeapRef<0> H{w, nullptr, nullptr};
+    heap_set_t<0>(H, n, slot, prio);
 }
 
 // Ternary footprint status of one pose (body only): HL_FREE / HL_HIT / HL_AMBIG(+mask)

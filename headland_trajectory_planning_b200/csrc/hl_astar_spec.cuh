@@ -29,6 +29,13 @@
                                        // 2-3 shooters measured slower: the expander is the critical path)
 #endif
 #define AQ_WARPS_PER_SLOT (AQ_EXPANDERS + AQ_SHOOTERS)
+#ifndef AQ_HEAP_SM
+#define AQ_HEAP_SM 1023                // open-list entries kept in shared memory (top 10 levels of the heap); 0 = all in the workspace
+#endif
+#ifndef AQ_GUIDE_CAP
+#define AQ_GUIDE_CAP 192               // guide polyline points staged in shared memory (longer polylines are read from HBM / L2)
+#endif
+#define AQ_SUB (AQ_TEAM / 16)          // lanes per primitive in the batched guide-distance pass
 #define AQ_TEAM (32 * AQ_EXPANDERS)
 #define AQ_NO_HIT 0x7fffffff
 #ifndef AQ_TIMERS
@@ -49,6 +56,7 @@ struct AqShot {                          // scratch of one shooter warp
     int rs_acc[HL_RS_CANDIDATES], rs_order[HL_RS_CANDIDATES];
     unsigned char rs_valid[HL_RS_CANDIDATES + 2], rs_accept[HL_RS_CANDIDATES + 2];
     RsProblem rs_prob;
+    int rs_npts[HL_RS_CANDIDATES];       // sample count of every word planned so far (evaluation order)
     int rs_n, rs_pick, rs_word, rs_assert;
     double rs_goal_cost;
     RsPlan plans[AQ_MAX_PLANS];
@@ -90,6 +98,12 @@ struct AqSmem {                          // one per scenario slot, shared by its
     double goal_cost;
     long long path_off;
     __align__(16) float envf[AW_ENV_FLOATS];
+    double gx[AQ_GUIDE_CAP], gy[AQ_GUIDE_CAP];       // guide polyline of the scenario (calculate_state_cost's argmin)
+    int guide_staged;
+#if AQ_HEAP_SM > 0
+    double hp_prio[AQ_HEAP_SM];                     // top of the open-list heap (HeapRef)
+    int hp_slot[AQ_HEAP_SM];
+#endif
 };
 static_assert(sizeof(AqSmem) * AQ_SLOTS <= 227 * 1024, "per-CTA shared memory exceeds 227 KB");
 
@@ -140,6 +154,117 @@ __device__ __forceinline__ int warp_read(volatile int* p, int lane) {
     int v = 0;
     if (lane == 0) v = *p;
     return __shfl_sync(FULL, v, 0);
+}
+
+__device__ __noinline__ int aq_heap_pop(AqSmem& S, const AsWs& w, int& n) {
+#if AQ_HEAP_SM > 0
+    const HeapRef<AQ_HEAP_SM> H{w, S.hp_prio, S.hp_slot};
+#else
+    const HeapRef<0> H{w, nullptr, nullptr};
+#endif
+    return heap_popitem_t<AQ_HEAP_SM>(H, n);
+}
+__device__ __noinline__ void aq_heap_set(AqSmem& S, const AsWs& w, int& n, int slot, double prio) {
+#if AQ_HEAP_SM > 0
+    const HeapRef<AQ_HEAP_SM> H{w, S.hp_prio, S.hp_slot};
+#else
+    const HeapRef<0> H{w, nullptr, nullptr};
+#endif
+    heap_set_t<AQ_HEAP_SM>(H, n, slot, prio);
+}
+
+// calculate_state_cost (reference_line_heuristic.py:131-158) of EVERY primitive that needs one, the whole expander
+// team at once: AQ_SUB lanes per primitive walk the guide polyline (shared memory) with stride AQ_SUB -- one pass for
+// the minimum squared distance (ordering filter), one for the exact hypot of the near-minimal points (first minimum
+// wins, np.argmin) -- and one lane per primitive finishes the cost.  Same arithmetic as warp_state_cost; the serial
+// part (7 calls per warp, 5-step 64-bit shuffle reductions, the fmod tail) is what it replaces.
+__device__ __noinline__ void team_state_costs(AqSmem& S, const EnvBatchDev& eb, const EnvDesc& D, const AsParams& P,
+                                              int nst, int tl, int lane) {
+    const unsigned needm = __ballot_sync(FULL, lane < P.n_prims && !S.phit[lane] && S.pneed[lane]);
+    const int slot = tl / AQ_SUB, sub = tl - slot * AQ_SUB;
+    const int p = slot < __popc(needm) ? (int)__fns(needm, 0, slot + 1) : -1;
+    const int n = D.n_guide;
+    const double* gx = S.guide_staged ? S.gx : eb.guide_x + D.guide_off;
+    const double* gy = S.guide_staged ? S.gy : eb.guide_y + D.guide_off;
+    const double x = p >= 0 ? S.tx[p][nst] : 0.0, y = p >= 0 ? S.ty[p][nst] : 0.0;
+    double best = INFINITY;
+#pragma unroll 2
+    for (int i = sub; i < n; i += AQ_SUB) {
+        const double dx = gx[i] - x, dy = gy[i] - y;
+        best = fmin(best, dx * dx + dy * dy);
+    }
+#pragma unroll
+    for (int o = AQ_SUB / 2; o; o >>= 1) best = fmin(best, __shfl_xor_sync(FULL, best, o));
+    const double thr = best * (1.0 + 1e-9) + 1e-300;
+    double bh = INFINITY;
+    int bi = 0x7fffffff;
+#pragma unroll 1
+    for (int i = sub; i < n; i += AQ_SUB) {
+        const double dx = xsub(gx[i], x), dy = xsub(gy[i], y);
+        if (dx * dx + dy * dy <= thr) {
+            const double h = hypot_cr(dx, dy);
+            if (h < bh || (h == bh && i < bi)) { bh = h; bi = i; }
+        }
+    }
+#pragma unroll
+    for (int o = AQ_SUB / 2; o; o >>= 1) {
+        const double oh = __shfl_xor_sync(FULL, bh, o);
+        const int oi = __shfl_xor_sync(FULL, bi, o);
+        if (oh < bh || (oh == bh && oi < bi)) { bh = oh; bi = oi; }
+    }
+    if (p >= 0 && sub == 0) {
+        double h = 0.0;
+        if (n > 0) {
+            double dist = xmul(bh, 100.0);
+            const double yaw_diff = fabs(angle_wrap(xsub(eb.guide_yaw[D.guide_off + bi], S.pyaw[p][nst])));
+            if (dist > 2.0) dist = 100.0;
+            const double to_goal = xsub(eb.guide_s[D.guide_off + n - 1], eb.guide_s[D.guide_off + bi]);
+            h = xadd(xadd(dist, xmul(yaw_diff, 0.2)), xmul(to_goal, 5.0));
+        }
+        S.pprio[p] = xmul(P.hybrid_cost, h);
+    }
+}
+
+// Footprint check of ONE planned Reeds-Shepp word by a whole warp: 32 poses per pass, lane-strided, float32 filter first
+// and the float64 predicate only for the poses inside the band when no other pose of the pass decided the word.
+// Returns true when the word collides.
+__device__ __noinline__ bool aq_word_collides(const EnvSmem& Ers, const EnvBatchDev& eb, const EnvDesc& D, const RsPlan& plan,
+                                              const double* q0, double cq, double sq, double maxc, float inv_maxc,
+                                              unsigned FLAGS, AqShot& T, int lane) {
+    const int npts = plan.npts;
+    int infeasible = 0;
+    const int passes = (npts + 31) >> 5;
+#pragma unroll 1
+    for (int pass = 0; pass < passes && !infeasible; ++pass) {
+        const int j = lane * passes + pass;
+        int st2 = HL_FREE;
+        unsigned amb = 0;
+        if (j < npts) {
+            float fx, fy, fc, fs;
+            rs_sample_world32(plan, j, inv_maxc, fx, fy, fc, fs);
+            if (fabsf(fx) > Ers.reach || fabsf(fy) > Ers.reach) st2 = far_status(FLAGS, Ers.n_seg);
+            else if (!(fx == fx) || !(fy == fy) || !(fc == fc)) { st2 = HL_AMBIG; amb = FLAGS; }
+            else st2 = filter_part(Ers, fx, fy, fc, fs, Ers.ext, FLAGS, &amb);
+        }
+        const unsigned livem = __ballot_sync(FULL, j < npts);
+        const unsigned hitm = __ballot_sync(FULL, st2 == HL_HIT);
+        const unsigned ambm = __ballot_sync(FULL, st2 == HL_AMBIG);
+        infeasible = hitm != 0;
+        if (!infeasible && ambm) {
+            int bad2 = 0;
+            if (st2 == HL_AMBIG) {
+                double lx, ly, lyaw, wx, wy, wyaw;
+                int cs, dir;
+                rs_sample_local(plan, j, maxc, lx, ly, lyaw, cs, dir);
+                rs_to_world(q0, cq, sq, lx, ly, lyaw, wx, wy, wyaw);
+                bad2 = pose_exact(eb, D, wx, wy, wyaw, amb) ? 1 : 0;
+            }
+            if (lane == 0) T.s_exact += (unsigned long long)__popc(ambm);
+            infeasible = __any_sync(FULL, bad2);
+        }
+        if (lane == 0) T.s_checks += (unsigned long long)__popc(livem);
+    }
+    return infeasible != 0;
 }
 
 // Result record + path of a finished scenario (expander warp, after the shooter reported).
@@ -365,12 +490,34 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                 if (lane == 0) {
                     const int cur = W.corder[i];
                     T.s_cur = cur; T.sx = W.nx[cur]; T.sy = W.ny[cur]; T.syaw = W.nyaw[cur]; T.sg = W.ng[cur];
-                    const double q0n[3] = {T.sx, T.sy, T.syaw};
-                    T.rs_prob = rs_normalise(q0n, S.goal, P.maxc);
                     T.rs_pick = -1;
                 }
                 __syncwarp();
                 q0[0] = T.sx; q0[1] = T.sy; q0[2] = T.syaw;
+                {
+                    // generate_path's normalisation (reeds_shepp.py:565-572, rs_normalise): the sine / cosine of the
+                    // node heading and of the heading difference are ONE sincos each, on two lanes at the same time
+                    // (sincos == sin, cos and sin odd / cos even bit for bit: tools/sincos_check.cu); the node
+                    // heading's pair also gives cq / sq = cos(-yaw), sin(-yaw) of the local -> world rotation.
+                    const double phi = xsub(S.goal[2], q0[2]);
+                    double sn, cs;
+                    m_sincos(lane == 1 ? phi : q0[2], &sn, &cs);
+                    const double c0 = __shfl_sync(FULL, cs, 0), s0 = __shfl_sync(FULL, sn, 0);
+                    const double cp = __shfl_sync(FULL, cs, 1), sp = __shfl_sync(FULL, sn, 1);
+                    cq = c0; sq = -s0;
+                    if (lane == 0) {
+                        RsProblem Pr;
+                        const double dx = xsub(S.goal[0], q0[0]), dy = xsub(S.goal[1], q0[1]);
+                        Pr.phi = phi;
+                        Pr.x = xmul(xadd(xmul(c0, dx), xmul(s0, dy)), P.maxc);
+                        Pr.y = xmul(xadd(xmul(-s0, dx), xmul(c0, dy)), P.maxc);
+                        Pr.sp = sp; Pr.cp = cp;
+                        Pr.xb = xadd(xmul(Pr.x, cp), xmul(Pr.y, sp));
+                        Pr.yb = xsub(xmul(Pr.x, sp), xmul(Pr.y, cp));
+                        T.rs_prob = Pr;
+                    }
+                    __syncwarp();
+                }
                 // two passes with DISJOINT solver sets (30 + 16 rows): the lanes of a pass diverge over the solver
                 // switch, so each formula's code runs once per shot instead of once per pass
 #pragma unroll 1
@@ -399,25 +546,19 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                     if (a1 == 1) { int k = n0 + __popc(b1 & lt); T.rs_acc[k] = lane + 32; T.rs_L[k] = T.rs_Lc[lane + 32]; }
                     m = bad ? 0 : n0 + __popc(b1);
                     __syncwarp();
-#pragma unroll 1
-                    for (int k = lane; k < m; k += 32)
-                        T.rs_prio[k] = rs_path_cost(T.sg, T.rs_acc[k], T.rs_lens[T.rs_acc[k]], P.max_steer,
-                                                    P.reverse_cost, P.dir_change_cost, P.steer_cost);
-                    __syncwarp();
-                    if (lane == 0) {
-                        if (bad) T.rs_assert = 1;
-                        T.rs_n = m;
-                        if (m > 0) heapdict_order(T.rs_prio, m, T.rs_order);
-                    }
+                    if (lane == 0) { if (bad) T.rs_assert = 1; T.rs_n = m; }
                     __syncwarp();
                     if (bad) success = true;     // the reference would raise here: report it as the end of the search
                 }
                 STICK(PH_RS_SELECT);
-                cq = m_cos(-q0[2]); sq = m_sin(-q0[2]);
+                // The words are planned and refuted in EVALUATION order: a failing shot (every pop but the last one of
+                // a scenario) must refute every word whatever the order, so the cost queue (rs_path_cost + heapdict
+                // replay, hybrid_a_star_search.py:265-271) is only built when some word turns out to be free.
                 if (lane < m && lane < AQ_MAX_PLANS) {
-                    int c = T.rs_acc[T.rs_order[lane]];
+                    const int c = T.rs_acc[lane];
                     rs_make_plan(c, T.rs_lens[c], P.maxc, stepn, T.plans[lane]);
                     rs_plan_world32(T.plans[lane], q0, cq, sq, Dp->origin);
+                    T.rs_npts[lane] = T.plans[lane].npts;
                 }
                 __syncwarp();
                 STICK(PH_RS_PLAN);
@@ -461,60 +602,74 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                     if (lane == 0) T.s_checks += (unsigned long long)__popc(livem);
                 }
 #endif
+                int first_free = -1;
+                unsigned long long ref_all = 0;              // poses of the words refuted so far (lane 0's tally)
 #pragma unroll 1
-                for (int r = 0; r < m; ++r) {
-                    if (dead & (1u << r)) { if (lane == 0) T.s_ref += (unsigned long long)T.plans[r].npts; continue; }
-                    const int k = T.rs_order[r];
+                for (int k = 0; k < m; ++k) {
+                    if (dead & (1u << k)) { ref_all += (unsigned long long)T.plans[k].npts; continue; }
                     const int c = T.rs_acc[k];
-                    if (r >= AQ_MAX_PLANS) {
+                    if (k >= AQ_MAX_PLANS) {
                         __syncwarp();
                         if (lane == 0) {
                             rs_make_plan(c, T.rs_lens[c], P.maxc, stepn, T.plan_tmp);
                             rs_plan_world32(T.plan_tmp, q0, cq, sq, D.origin);
+                            T.rs_npts[k] = T.plan_tmp.npts;
                         }
                         __syncwarp();
                     }
-                    const RsPlan& plan = (r < AQ_MAX_PLANS) ? T.plans[r] : T.plan_tmp;
-                    const int npts = plan.npts;
-                    if (lane == 0) T.s_ref += (unsigned long long)npts;
-                    int infeasible = 0;
-                    const int passes = (npts + 31) >> 5;
+                    const RsPlan& plan = (k < AQ_MAX_PLANS) ? T.plans[k] : T.plan_tmp;
+                    ref_all += (unsigned long long)plan.npts;
+                    const bool hit = aq_word_collides(Ers, eb, D, plan, q0, cq, sq, P.maxc, inv_maxc, FLAGS, T, lane);
+                    if (!hit && xdiv(T.rs_L[k], P.maxc) < P.min_len_goal) { first_free = k; break; }
+                }
+                if (first_free < 0) {
+                    if (lane == 0) T.s_ref += ref_all;       // every word tried and refuted (:272-287 falls through)
+                } else {
+                    // Some word is free: the reference returns the FIRST free word in the pop order of its cost queue.
+                    // Words before `first_free` in evaluation order are refuted, the ones after it are examined here
+                    // only as far as the pop order reaches them.
+                    __syncwarp();
 #pragma unroll 1
-                    for (int pass = 0; pass < passes && !infeasible; ++pass) {
-                        const int j = lane * passes + pass;
-                        int st2 = HL_FREE;
-                        unsigned amb = 0;
-                        if (j < npts) {
-                            float fx, fy, fc, fs;
-                            rs_sample_world32(plan, j, inv_maxc, fx, fy, fc, fs);
-                            if (fabsf(fx) > Ers.reach || fabsf(fy) > Ers.reach) st2 = far_status(FLAGS, Ers.n_seg);
-                            else if (!(fx == fx) || !(fy == fy) || !(fc == fc)) { st2 = HL_AMBIG; amb = FLAGS; }
-                            else st2 = filter_part(Ers, fx, fy, fc, fs, Ers.ext, FLAGS, &amb);
-                        }
-                        const unsigned livem = __ballot_sync(FULL, j < npts);
-                        const unsigned hitm = __ballot_sync(FULL, st2 == HL_HIT);
-                        const unsigned ambm = __ballot_sync(FULL, st2 == HL_AMBIG);
-                        infeasible = hitm != 0;
-                        if (!infeasible && ambm) {
-                            int bad2 = 0;
-                            if (st2 == HL_AMBIG) {
-                                double lx, ly, lyaw, wx, wy, wyaw;
-                                int cs, dir;
-                                rs_sample_local(plan, j, P.maxc, lx, ly, lyaw, cs, dir);
-                                rs_to_world(q0, cq, sq, lx, ly, lyaw, wx, wy, wyaw);
-                                bad2 = pose_exact(eb, D, wx, wy, wyaw, amb) ? 1 : 0;
+                    for (int k = lane; k < m; k += 32)
+                        T.rs_prio[k] = rs_path_cost(T.sg, T.rs_acc[k], T.rs_lens[T.rs_acc[k]], P.max_steer,
+                                                    P.reverse_cost, P.dir_change_cost, P.steer_cost);
+                    __syncwarp();
+                    if (lane == 0) heapdict_order(T.rs_prio, m, T.rs_order);
+                    __syncwarp();
+                    unsigned long long tally = 0;
+                    int winner = -1;
+#pragma unroll 1
+                    for (int r = 0; r < m && winner < 0; ++r) {
+                        const int k = T.rs_order[r];
+                        if (k < first_free) { tally += (unsigned long long)T.rs_npts[k]; continue; }
+                        if (k == first_free) { tally += (unsigned long long)T.rs_npts[k]; winner = k; break; }
+                        const int c = T.rs_acc[k];
+                        if (k >= AQ_MAX_PLANS) {
+                            __syncwarp();
+                            if (lane == 0) {
+                                rs_make_plan(c, T.rs_lens[c], P.maxc, stepn, T.plan_tmp);
+                                rs_plan_world32(T.plan_tmp, q0, cq, sq, D.origin);
+                                T.rs_npts[k] = T.plan_tmp.npts;
                             }
-                            if (lane == 0) T.s_exact += (unsigned long long)__popc(ambm);
-                            infeasible = __any_sync(FULL, bad2);
+                            __syncwarp();
                         }
-                        if (lane == 0) T.s_checks += (unsigned long long)__popc(livem);
+                        const RsPlan& plan = (k < AQ_MAX_PLANS) ? T.plans[k] : T.plan_tmp;
+                        tally += (unsigned long long)plan.npts;
+                        const bool hit = aq_word_collides(Ers, eb, D, plan, q0, cq, sq, P.maxc, inv_maxc, FLAGS, T, lane);
+                        if (!hit && xdiv(T.rs_L[k], P.maxc) < P.min_len_goal) winner = k;
                     }
-                    const bool short_enough = xdiv(T.rs_L[k], P.maxc) < P.min_len_goal;
-                    if (!infeasible && short_enough) {
-                        if (lane == 0) { T.rs_pick = r; T.rs_word = c; T.rs_goal_cost = T.rs_prio[k]; }
-                        success = true;
-                        break;
+                    __syncwarp();
+                    if (lane == 0) {
+                        const int c = T.rs_acc[winner];
+                        if (winner >= AQ_MAX_PLANS) {            // the winner's plan for the result path
+                            rs_make_plan(c, T.rs_lens[c], P.maxc, stepn, T.plan_tmp);
+                            rs_plan_world32(T.plan_tmp, q0, cq, sq, D.origin);
+                        }
+                        T.s_ref += tally;
+                        T.rs_pick = winner < AQ_MAX_PLANS ? winner : AQ_MAX_PLANS;
+                        T.rs_word = c; T.rs_goal_cost = T.rs_prio[winner];
                     }
+                    success = true;
                 }
                 __syncwarp();
                 STICK(PH_RS_SAMPLE);
@@ -568,6 +723,10 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
         Dp = eb.desc + S.env;
         const EnvDesc& D = *Dp;
         stage_env_warp(eb, D, S.envf, AW_ENV_FLOATS, E, lane);
+        if (D.n_guide <= AQ_GUIDE_CAP) {
+            for (int i = lane; i < D.n_guide; i += 32) { S.gx[i] = eb.guide_x[D.guide_off + i]; S.gy[i] = eb.guide_y[D.guide_off + i]; }
+        }
+        if (lane == 0) S.guide_staged = D.n_guide <= AQ_GUIDE_CAP ? 1 : 0;
         // start / goal feasibility and start node (shared helper works on an AwSmem-like view)
         {
             int bad = 0;
@@ -597,7 +756,7 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                     S.n_nodes = 1;
                     double prio = xmul(P.hybrid_cost, h);
                     prio = (prio > 0.0) ? prio : 0.0;
-                    heap_set(W, S.heap_n, 0, prio);
+                    aq_heap_set(S, W, S.heap_n, 0, prio);
                 }
             }
             __syncwarp();
@@ -625,7 +784,7 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                     S.counter += 1;
                     if (S.heap_n == 0) S.ew_status = HL_STATUS_OPEN_EMPTY;
                     else {
-                        int cur = heap_popitem(W, S.heap_n);
+                        int cur = aq_heap_pop(S, W, S.heap_n);
                         W.nstate[cur] = 1;
                         W.cref[S.n_closed] = (long long)S.e_ref;
                         W.corder[S.n_closed++] = cur;
@@ -783,19 +942,8 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                 if (slot2 >= 0 && (W.nstate[slot2] == 1 || !(cost < W.ng[slot2]))) S.pneed[p] = 0;
             }
             team_sync(slot);
-            {
-                int q = 0;                                   // needed primitives are dealt round-robin to the team's warps
-#pragma unroll 1
-                for (int p = 0; p < P.n_prims; ++p) {
-                    if (!S.phit[p] && S.pneed[p]) {
-                        if ((q % AQ_EXPANDERS) == ew) {
-                            double h = warp_state_cost(eb, D, S.tx[p][n], S.ty[p][n], S.pyaw[p][n], lane);
-                            if (lane == 0) S.pprio[p] = xmul(P.hybrid_cost, h);
-                        }
-                        ++q;
-                    }
-                }
-            }
+            if (ew == 0) ETICK(PH_ARRIVE);                   // (timer slot reused: g-cost + key + hash probe)
+            team_state_costs(S, eb, D, P, n, tl, lane);
             team_sync(slot);
             if (ew == 0) ETICK(PH_COST_HEUR);
             if (tl == 0) {
@@ -821,7 +969,7 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                     W.nx[slot2] = S.tx[p][n]; W.ny[slot2] = S.ty[p][n]; W.nyaw[slot2] = S.pyaw[p][n];
                     W.ng[slot2] = g; W.nparent[slot2] = S.cur; W.nprim[slot2] = (signed char)p;
                     W.nsteps[slot2] = (signed char)n;
-                    heap_set(W, S.heap_n, slot2, prio);
+                    aq_heap_set(S, W, S.heap_n, slot2, prio);
                 }
             }
             __syncwarp();
