@@ -275,36 +275,38 @@ def main():
     h2d = int(sum(r.obs.nbytes + r.field.nbytes + r.seg_xy.nbytes + r.seg_polys.nbytes + r.seg_len.nbytes +
                   r.crit.nbytes + r.guide.nbytes + r.aux.nbytes + 32 for r in recs) + host_scen.numel())
     d2h = 0
-    def e2e_steps(pf, k_steps):
-        """k_steps double-buffered steps: the upload of step k+1 (host packing + H2D on the context's copy stream, in a
-        worker thread) overlaps the search of step k.  Every step uploads its own inputs from host memory and
-        downloads its own results."""
+    def e2e_steps(pf, dl, k_steps):
+        """k_steps pipelined steps.  Every step uploads its own inputs from host memory (environment geometry through
+        hl_env_upload, scenario records) and downloads its own results (records, key sequences, paths; over NCCL to
+        rank 0 when N > 1) into host memory; the upload of step k+1 (worker thread, the context's copy stream) and the
+        device -> host copy + merge of step k-1 (side stream, copy engine) overlap the search of step k."""
         nbytes = 0
+        pending = None
         pf.submit(recs, host_structs)                                       # H2D environment geometry of step 0
         for s in range(k_steps):
             envs_e = pf.result()
             if s + 1 < k_steps:
                 pf.submit(recs, host_structs)                               # ... of step s+1, behind step s's search
             d_s = host_scen.to(dev, non_blocking=True)                      # H2D scenario records
-            if world == 1:
-                o = ops.hybrid_astar_batch(envs_e, d_s, params, path_capacity=path_cap, to_host=True)   # search + D2H
-            else:
-                # search; the output stays on the device, goes to rank 0 over NCCL/NVLink and is copied to the host
-                # once, there (records, key sequences AND paths of all ranks), then merged into scenario order
-                o = ops.hybrid_astar_batch(envs_e, d_s, params, path_capacity=path_cap, to_host=False)
-                shards = sweep.gather_sweep(o, world, rank)
-                o = sweep.merge_shards(shards, total, world) if rank == 0 else None
-            envs_e.close()
-            if o is not None:
-                nbytes = int(o["results"].nbytes + o["expanded"].nbytes + sum(o[k].nbytes for k in ("x", "y", "yaw", "k", "dir")))
+            o = ops.hybrid_astar_batch(envs_e, d_s, params, path_capacity=path_cap, to_host=False)   # queued
+            done = dl.finish(pending, total) if pending is not None else None                      # step s-1 on the host
+            # size exchange (returns when search s is finished), NVLink gatherv to rank 0, D2H queued on the side stream
+            pending = dl.begin(o, release=envs_e.close)
+            if done is not None:
+                nbytes = int(done["results"].nbytes + done["expanded"].nbytes + sum(done[k].nbytes for k in ("x", "y", "yaw", "k", "dir")))
+        done = dl.finish(pending, total)
+        if done is not None:
+            nbytes = int(done["results"].nbytes + done["expanded"].nbytes + sum(done[k].nbytes for k in ("x", "y", "yaw", "k", "dir")))
+            assert len(done["results"]) == total and int((done["results"]["status"] >= 0).sum()) == total
         return nbytes
 
     pf = sweep.UploadPrefetcher()
-    e2e_steps(pf, max(3, args.warmup))                                      # untimed warm-up of the very same path
+    dl = sweep.SweepDownloader(world, rank)
+    e2e_steps(pf, dl, max(3, args.warmup))                                  # untimed warm-up of the very same path
     barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    d2h = e2e_steps(pf, args.steps)                                         # EXACTLY K timed steps
+    d2h = e2e_steps(pf, dl, args.steps)                                     # EXACTLY K timed steps
     torch.cuda.synchronize()
     barrier()
     e2e_wall = time.perf_counter() - t0

@@ -91,8 +91,33 @@ def gather_sweep(out, world_size, rank):
 
     Returns on rank 0 a dict with the rank-major host pools ``expanded`` [rows, 3] int32, ``x, y, yaw, k, dir``, the
     structured ``results`` of all ranks rank-major, and ``counts`` = per-rank (key rows, path poses, records) for
-    ``merge_shards``; ``None`` on the other ranks.  The host arrays are views of one pinned buffer that the NEXT
-    gather_sweep call overwrites (copy what must outlive it)."""
+    ``merge_shards``; ``None`` on the other ranks.  The host arrays are views of one pinned buffer that a later
+    gather_sweep call overwrites (copy what must outlive it).  ``SweepDownloader`` is the pipelined form."""
+    return gather_sweep_begin(out, world_size, rank).finish()
+
+
+class _Pending:
+    """A sweep output on its way to the host (``gather_sweep_begin`` / ``SweepDownloader.begin``)."""
+
+    def __init__(self, keep, event, build):
+        self._keep, self._event, self._build = keep, event, build
+
+    def finish(self):
+        """Wait for the device -> host copy and return the host dict (``None`` on ranks other than 0)."""
+        if self._event is not None:
+            self._event.synchronize()
+        out = self._build() if self._build is not None else None
+        self._keep = self._build = None                     # device buffers go back to the allocator
+        return out
+
+
+def gather_sweep_begin(out, world_size, rank, stream=None, release=None, slot=0):
+    """First half of ``gather_sweep``: the size exchange (the step's one host sync: it returns when this rank's search
+    is finished), the gatherv, and on rank 0 the device -> host copy QUEUED on ``stream`` (a side stream: the copy
+    engine then moves the gathered sweep while the SMs already run the next search).  ``release`` is called after the
+    searches are known to be finished and before the copy is queued (e.g. ``EnvBatch.close``, which synchronises the
+    device and would otherwise wait for the copy).  ``slot`` picks one of two pinned buffers, so the arrays of the
+    previous sweep stay valid while this one lands.  Returns a handle whose ``finish()`` gives gather_sweep's dict."""
     import torch
     import torch.distributed as dist
     res = out["results"]
@@ -101,8 +126,11 @@ def gather_sweep(out, world_size, rank):
     keys_cap, path_cap = out["expanded"].shape[0], out["x"].shape[0]
     mine = torch.cat([out["kcursor"].reshape(1).to(torch.int64), out["cursor"].reshape(1).to(torch.int64),
                       torch.tensor([n], dtype=torch.int64, device=dev)])
-    sizes = torch.empty(3 * world_size, dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(sizes, mine)
+    if world_size > 1:
+        sizes = torch.empty(3 * world_size, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(sizes, mine)
+    else:
+        sizes = mine
     sizes = sizes.cpu().numpy().reshape(world_size, 3)               # the step's one host sync on every rank
     off, (kused, pused, nrec), total = _gather_layout(sizes, keys_cap, path_cap)
     count_of = {"results": nrec, "expanded": kused}
@@ -114,7 +142,9 @@ def gather_sweep(out, world_size, rank):
                 ops_.append(dist.P2POp(dist.isend, _piece(out, name, c), 0))
         for w in (dist.batch_isend_irecv(ops_) if ops_ else []):
             w.wait()
-        return None
+        if release is not None:
+            release()
+        return _Pending(out, None, None)
     big = torch.empty(total, dtype=torch.uint8, device=dev)
     ops_ = []
     for name, _ in _SECTIONS:
@@ -127,35 +157,80 @@ def gather_sweep(out, world_size, rank):
                 ops_.append(dist.P2POp(dist.irecv, big[int(o[r]):int(o[r + 1])], r))
     for w in (dist.batch_isend_irecv(ops_) if ops_ else []):
         w.wait()
+    if release is not None:
+        release()
+    event = None
     if big.is_cuda:
-        host = _pinned(total)
-        host.copy_(big, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        host = _pinned(total, slot)
+        ready = torch.cuda.Event()
+        ready.record()                                              # pools complete on the current stream
+        st = stream if stream is not None else torch.cuda.current_stream()
+        with torch.cuda.stream(st):
+            st.wait_event(ready)
+            host.copy_(big, non_blocking=True)
+            event = torch.cuda.Event()
+            event.record()
         host = host.numpy()
     else:
         host = big.numpy()
-    g = {"counts": np.stack([kused, pused, nrec], axis=1), "keys_produced": sizes[:, 0].copy(), "poses_produced": sizes[:, 1].copy()}
-    for name, w in _SECTIONS:
-        sec = host[int(off[name][0]):int(off[name][-1])]
-        if name == "results":
-            g[name] = sec.view(_lib.RESULT_DTYPE)
-        elif name == "expanded":
-            g[name] = sec.view(np.int32).reshape(-1, 3)
-        else:
-            g[name] = sec.view(np.float64 if w == 8 else np.int8)
-    return g
+
+    def build():
+        g = {"counts": np.stack([kused, pused, nrec], axis=1), "keys_produced": sizes[:, 0].copy(),
+             "poses_produced": sizes[:, 1].copy()}
+        for name, w in _SECTIONS:
+            sec = host[int(off[name][0]):int(off[name][-1])]
+            if name == "results":
+                g[name] = sec.view(_lib.RESULT_DTYPE)
+            elif name == "expanded":
+                g[name] = sec.view(np.int32).reshape(-1, 3)
+            else:
+                g[name] = sec.view(np.float64 if w == 8 else np.int8)
+        return g
+    return _Pending((out, big), event, build)
+
+
+class SweepDownloader:
+    """Pipelined download for back-to-back sweeps (the counterpart of ``UploadPrefetcher``): the device -> host copy
+    of sweep k runs on a side stream (copy engine) while the SMs search sweep k+1, so only the size exchange and the
+    NVLink gatherv stay between two searches.
+
+        dl = SweepDownloader(world_size, rank)
+        pending = None
+        for k in range(n):
+            out = ops.hybrid_astar_batch(envs_k, scen_k, params, to_host=False)       # queued, asynchronous
+            if pending is not None: results_of_k_minus_1 = dl.finish(pending, n_total)
+            pending = dl.begin(out, release=envs_k.close)     # returns when search k is done; its copy is in flight
+        results_of_last = dl.finish(pending, n_total)
+
+    ``finish`` returns (rank 0) the merged host dict of ``merge_shards`` -- scenario order, shaped like
+    ``ops.hybrid_astar_batch(to_host=True)``; its arrays are views of one of two alternating pinned buffers and stay
+    valid until the sweep after the next one lands."""
+
+    def __init__(self, world_size=1, rank=0, device=None):
+        import torch
+        self.world_size, self.rank = int(world_size), int(rank)
+        self.stream = torch.cuda.Stream(device) if torch.cuda.is_available() else None
+        self._k = 0
+
+    def begin(self, out, release=None):
+        self._k ^= 1
+        return gather_sweep_begin(out, self.world_size, self.rank, stream=self.stream, release=release, slot=self._k)
+
+    def finish(self, pending, n_total):
+        g = pending.finish()
+        return merge_shards(g, n_total, self.world_size) if g is not None else None
 
 
 _pinned_cache = {}
 
 
-def _pinned(nbytes):
-    """Grow-only pinned host buffer for the gathered sweep (cudaHostAlloc per step would cost more than the copy)."""
+def _pinned(nbytes, slot=0):
+    """Grow-only pinned host buffers for the gathered sweep (cudaHostAlloc per step would cost more than the copy)."""
     import torch
-    t = _pinned_cache.get("buf")
+    t = _pinned_cache.get(slot)
     if t is None or t.numel() < nbytes:
         t = torch.empty(max(nbytes + nbytes // 4, 1 << 20), dtype=torch.uint8).pin_memory()
-        _pinned_cache["buf"] = t
+        _pinned_cache[slot] = t
     return t[:nbytes]
 
 

@@ -132,3 +132,49 @@ def test_two_rank_nccl_sweep_equals_single_gpu(built_library, tmp_path):
     for i in range(n_total):
         assert np.array_equal(ops.expanded_of(m, i), ops.expanded_of(one, i))
         assert unpack_path(m, i) == unpack_path(one, i)
+
+
+def test_pipelined_upload_search_download_single_gpu(built_library):
+    """bench.py's end-to-end loop on one GPU: UploadPrefetcher + SweepDownloader keep three sweeps in flight (upload of
+    k+1, search of k, device -> host copy of k-1 on a side stream); every sweep's merged host result must equal the
+    plain ``to_host=True`` call, and the arrays of sweep k must stay intact while sweep k+1 lands."""
+    from headland_trajectory_planning_b200 import ops, sweep
+    from headland_trajectory_planning_b200.env_batch import EnvBatch, pack_structs
+    from headland_trajectory_planning_b200.hybrid_a_star_search import unpack_path
+    n = 96
+    scns, g = _golden(n)
+    subsets = [list(range(0, n)), list(range(0, n, 2)), list(range(1, n, 3)), list(range(5, 60))]
+    built = []
+    for sub in subsets:
+        recs, scen, car = sweep.build_records([scns[i] for i in sub])
+        built.append((recs, pack_structs(recs), scen, sweep.search_params(car)))
+    want = []
+    for recs, _, scen, params in built:
+        envs = EnvBatch(recs)
+        want.append(ops.hybrid_astar_batch(envs, scen, params, path_capacity=2048 * len(recs)))
+        envs.close()
+    def same(m, w):
+        for f in ("status", "counter", "n_expanded", "arrival", "path_len", "rs_word", "goal_cost", "n_pose_checks_ref"):
+            assert np.array_equal(m["results"][f], w["results"][f]), f
+        for i in range(len(w["results"])):
+            assert np.array_equal(ops.expanded_of(m, i), ops.expanded_of(w, i))
+            assert unpack_path(m, i) == unpack_path(w, i)
+
+    pf, dl = sweep.UploadPrefetcher(), sweep.SweepDownloader()
+    done, pending, prev = 0, None, None
+    pf.submit(built[0][0], built[0][1])
+    for k, (recs, structs, scen, params) in enumerate(built):
+        envs = pf.result()
+        if k + 1 < len(built):
+            pf.submit(built[k + 1][0], built[k + 1][1])
+        out = ops.hybrid_astar_batch(envs, scen, params, path_capacity=2048 * len(recs), to_host=False)
+        if pending is not None:
+            prev = dl.finish(pending[0], pending[1])
+            same(prev, want[done])
+        pending = (dl.begin(out, release=envs.close), len(recs))
+        if prev is not None:                    # the views of sweep k-1 stay valid while sweep k lands (two pinned buffers)
+            same(prev, want[done])
+            done += 1
+            prev = None
+    same(dl.finish(pending[0], pending[1]), want[done])
+    pf.close()
