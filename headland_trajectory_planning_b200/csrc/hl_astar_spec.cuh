@@ -225,6 +225,137 @@ __device__ __noinline__ void team_state_costs(AqSmem& S, const EnvBatchDev& eb, 
     }
 }
 
+// `while px[-1] == 0.0: pop` of generate_local_course (reeds_shepp.py:520-528) for a word whose end point has a local
+// x of exactly 0: the end point goes, then loop samples as long as their x is exactly 0.0.  Rare; one lane.
+__device__ __noinline__ void aq_plan_trailing_pops(RsPlan& P, double maxc) {
+    int npts = P.npts - 1;
+#pragma unroll 1
+    while (npts > 1) {
+        const int j = npts - 1;
+        int si = P.nseg - 1;
+#pragma unroll 1
+        while (si > 0 && j < P.seg[si].first) --si;
+        const RsSegPlan& S = P.seg[si];
+        double pd = S.pd0;
+#pragma unroll 1
+        for (int k = 0; k < j - S.first; ++k) pd = xadd(pd, S.d);
+        double px, py, pyaw;
+        rs_interp(pd, S.letter, maxc, S.ox, S.oy, S.oyaw, px, py, pyaw);
+        if (px != 0.0) break;
+        npts -= 1;
+    }
+    P.npts = npts;
+}
+
+// Plans of up to AQ_MAX_PLANS words at once, one warp: rs_make_plan + rs_plan_world32 re-arranged so that the
+// expensive part -- the sine / cosine of every segment's length and start heading, 4 float64 transcendentals per
+// segment in rs_interp -- runs on one lane per (word, segment) as TWO sincos calls in lock-step instead of 20 serial
+// calls per word.  Lane 5w + i holds segment i of word k0 + w.  Bit-identical to rs_make_plan in everything that feeds
+// a decision (sample counts, segment origins and headings: same operations in the same order; sincos == sin, cos and
+// sin odd / cos even bit for bit, tools/sincos_check.cu).  The float32 view (fox, foy, fc0, fs0) takes the cosine /
+// sine of the world heading from the angle-addition formula in float64 instead of another sincos: it only feeds the
+// conservative float32 filter.
+__device__ __noinline__ void aq_make_plans(AqShot& T, int k0, int nw, RsPlan* dst, const double* q0, double cq, double sq,
+                                           const double* origin, double maxc, double step, int lane) {
+    const int w = lane / 5, i = lane - 5 * w;
+    const bool wact = w < nw;
+    const int c = wact ? T.rs_acc[k0 + w] : 0;
+    const RsRow row = c_rs_rows[c];
+    const int nseg = row.nseg;
+    const bool act = wact && i < nseg;
+    const double* lens = T.rs_lens[c];
+    if (wact && i == 0) {
+        // sample bookkeeping of the whole word (generate_local_course's pd / ll / ind chain): sequential, cheap
+        RsPlan& P = dst[w];
+        P.nseg = nseg;
+        P.dir0 = (lens[0] > 0.0) ? 1 : -1;
+        double ll = 0.0;
+        int ind = 1;
+#pragma unroll 1
+        for (int j = 0; j < nseg; ++j) {
+            const double l = lens[j];
+            const double d = (l > 0.0) ? step : -step;
+            RsSegPlan& S = P.seg[j];
+            S.l = l; S.d = d; S.letter = rs_letter(row.letters, j);
+            ind -= 1;
+            double pd = (j >= 1 && xmul(lens[j - 1], lens[j]) > 0.0) ? xsub(-d, ll) : xsub(d, ll);
+            S.pd0 = pd;
+            S.first = ind + 1;
+            int cnt = 0;
+            const double al = fabs(l);
+            if (fabs(pd) <= al) {
+                const double a = (d > 0.0) ? pd : -pd;
+                const double r = (al - a) / step;
+                const double kf = floor(r);
+                if (r - kf > 1e-7 && kf + 1.0 - r > 1e-7 && r < 1e7) {
+                    cnt = (int)kf + 1;
+                    pd = xadd(pd, xmul((double)cnt, d));
+                } else {
+#pragma unroll 1
+                    while (fabs(pd) <= al) { ++cnt; pd = xadd(pd, d); }
+                }
+            }
+            S.count = cnt;
+            ind += cnt;
+            ll = xsub(xsub(l, pd), d);
+            ind += 1;
+        }
+        P.npts = ind + 1;
+    }
+    // heading at the start of segment i: oyaw accumulates +-l over the arcs before it, in the reference's order
+    double oyaw = 0.0;
+#pragma unroll 1
+    for (int j = 0; j < HL_RS_MAX_SEGS - 1; ++j) {
+        if (act && j < i) {
+            const int lt = rs_letter(row.letters, j);
+            if (lt == RS_L) oyaw = xadd(oyaw, lens[j]);
+            else if (lt == RS_R) oyaw = xsub(oyaw, lens[j]);
+        }
+    }
+    const double l = act ? lens[i] : 0.0;
+    const int letter = rs_letter(row.letters, i);
+    double sl, cl, so, co;
+    m_sincos(l, &sl, &cl);
+    m_sincos(oyaw, &so, &co);
+    // displacement of segment i in the local frame (rs_interp with cos(-oyaw) = co, sin(-oyaw) = -so)
+    double gdx, gdy;
+    if (letter == RS_S) {
+        const double lm = xdiv(l, maxc);
+        gdx = xmul(lm, co); gdy = xmul(lm, so);
+    } else {
+        const double ldx = xdiv(sl, maxc);
+        const double ldy = xdiv(xsub(1.0, cl), letter == RS_L ? maxc : -maxc);
+        gdx = xadd(xmul(co, ldx), xmul(-so, ldy));
+        gdy = xadd(xmul(so, ldx), xmul(co, ldy));
+    }
+    // origin of segment i: ((0 + g_0) + g_1) + ... in order
+    double ox = 0.0, oy = 0.0;
+#pragma unroll
+    for (int j = 0; j < HL_RS_MAX_SEGS - 1; ++j) {
+        const int src = min(5 * w + j, 31);
+        const double gx = __shfl_sync(FULL, gdx, src), gy = __shfl_sync(FULL, gdy, src);
+        if (j < i) { ox = xadd(ox, gx); oy = xadd(oy, gy); }
+    }
+    const double ex = xadd(ox, gdx);                             // end point of segment i (x only: the pop test)
+    const double end_x = __shfl_sync(FULL, ex, min(5 * w + nseg - 1, 31));
+    if (act) {
+        RsSegPlan& S = dst[w].seg[i];
+        S.ox = ox; S.oy = oy; S.oyaw = oyaw;
+        const double wx = xadd(xadd(xmul(cq, ox), xmul(sq, oy)), q0[0]);
+        const double wy = xadd(xadd(xmul(-sq, ox), xmul(cq, oy)), q0[1]);
+        S.fox = (float)(wx - origin[0]);
+        S.foy = (float)(wy - origin[1]);
+        S.fc0 = (float)(co * cq + so * sq);                      // cos(oyaw + yaw0), sin(oyaw + yaw0): cq = cos yaw0, sq = -sin yaw0
+        S.fs0 = (float)(so * cq - co * sq);
+    }
+    __syncwarp();
+    if (wact && i == 0) {
+        if (end_x == 0.0) aq_plan_trailing_pops(dst[w], maxc);
+        T.rs_npts[k0 + w] = dst[w].npts;
+    }
+    __syncwarp();
+}
+
 // Footprint check of ONE planned Reeds-Shepp word by a whole warp: 32 poses per pass, lane-strided, float32 filter first
 // and the float64 predicate only for the poses inside the band when no other pose of the pass decided the word.
 // Returns true when the word collides.
@@ -554,14 +685,6 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                 // The words are planned and refuted in EVALUATION order: a failing shot (every pop but the last one of
                 // a scenario) must refute every word whatever the order, so the cost queue (rs_path_cost + heapdict
                 // replay, hybrid_a_star_search.py:265-271) is only built when some word turns out to be free.
-                if (lane < m && lane < AQ_MAX_PLANS) {
-                    const int c = T.rs_acc[lane];
-                    rs_make_plan(c, T.rs_lens[c], P.maxc, stepn, T.plans[lane]);
-                    rs_plan_world32(T.plans[lane], q0, cq, sq, Dp->origin);
-                    T.rs_npts[lane] = T.plans[lane].npts;
-                }
-                __syncwarp();
-                STICK(PH_RS_PLAN);
                 shooting = true;
             }
             } while (0);
@@ -572,55 +695,51 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
             if (!shooting) continue;
             const EnvDesc& D = *Dp;
             {
-                // Coarse pass: almost every word of a failing shot collides somewhere, and ONE hit kills a word.  Probe
-                // the first min(m, AQ_MAX_PLANS) words together, 32 / nw evenly spaced poses each, before any word
-                // gets its own 32-pose passes.  Only definite float32 HITs count; everything else goes on below.
-                unsigned dead = 0;
-#if AQ_COARSE
-                if (m >= 2) {
-                    const int nw = m < AQ_MAX_PLANS ? m : AQ_MAX_PLANS;
-                    const int per = 32 / nw;
-                    const int r = lane / per, q = lane - r * per;
-                    int st2 = HL_FREE;
-                    if (r < nw) {
-                        const RsPlan& plan = T.plans[r];
-                        const int npts = plan.npts;
-                        const int j = (int)(((long long)(2 * q + 1) * npts) / (2 * per));
-                        if (j < npts) {
-                            float fx, fy, fc, fs;
-                            unsigned amb = 0;
-                            rs_sample_world32(plan, j, inv_maxc, fx, fy, fc, fs);
-                            if (fabsf(fx) > Ers.reach || fabsf(fy) > Ers.reach) st2 = far_status(FLAGS, Ers.n_seg);
-                            else if (!(fx == fx) || !(fy == fy) || !(fc == fc)) st2 = HL_AMBIG;
-                            else st2 = filter_part(Ers, fx, fy, fc, fs, Ers.ext, FLAGS, &amb);
-                        }
-                    }
-                    const unsigned hitm = __ballot_sync(FULL, st2 == HL_HIT);
-                    const unsigned livem = __ballot_sync(FULL, r < nw);
-                    for (int w = 0; w < nw; ++w)
-                        if (hitm & (((per >= 32) ? 0xffffffffu : ((1u << per) - 1u)) << (w * per))) dead |= 1u << w;
-                    if (lane == 0) T.s_checks += (unsigned long long)__popc(livem);
-                }
-#endif
+                // Words in batches of AQ_MAX_PLANS: plan the batch (one warp-wide call), probe all its words coarsely --
+                // almost every word of a failing shot collides somewhere and ONE hit kills a word: 32 / nw evenly spaced
+                // poses each, only definite float32 HITs count -- then the survivors get their own 32-pose passes.
                 int first_free = -1;
                 unsigned long long ref_all = 0;              // poses of the words refuted so far (lane 0's tally)
 #pragma unroll 1
-                for (int k = 0; k < m; ++k) {
-                    if (dead & (1u << k)) { ref_all += (unsigned long long)T.plans[k].npts; continue; }
-                    const int c = T.rs_acc[k];
-                    if (k >= AQ_MAX_PLANS) {
-                        __syncwarp();
-                        if (lane == 0) {
-                            rs_make_plan(c, T.rs_lens[c], P.maxc, stepn, T.plan_tmp);
-                            rs_plan_world32(T.plan_tmp, q0, cq, sq, D.origin);
-                            T.rs_npts[k] = T.plan_tmp.npts;
+                for (int k0 = 0; k0 < m && first_free < 0; k0 += AQ_MAX_PLANS) {
+                    const int nw = (m - k0) < AQ_MAX_PLANS ? (m - k0) : AQ_MAX_PLANS;
+                    aq_make_plans(T, k0, nw, T.plans, q0, cq, sq, D.origin, P.maxc, stepn, lane);
+                    STICK(PH_RS_PLAN);
+                    unsigned dead = 0;
+#if AQ_COARSE
+                    if (nw >= 2) {
+                        const int per = 32 / nw;
+                        const int r = lane / per, q = lane - r * per;
+                        int st2 = HL_FREE;
+                        if (r < nw) {
+                            const RsPlan& plan = T.plans[r];
+                            const int npts = plan.npts;
+                            const int j = (int)(((long long)(2 * q + 1) * npts) / (2 * per));
+                            if (j < npts) {
+                                float fx, fy, fc, fs;
+                                unsigned amb = 0;
+                                rs_sample_world32(plan, j, inv_maxc, fx, fy, fc, fs);
+                                if (fabsf(fx) > Ers.reach || fabsf(fy) > Ers.reach) st2 = far_status(FLAGS, Ers.n_seg);
+                                else if (!(fx == fx) || !(fy == fy) || !(fc == fc)) st2 = HL_AMBIG;
+                                else st2 = filter_part(Ers, fx, fy, fc, fs, Ers.ext, FLAGS, &amb);
+                            }
                         }
-                        __syncwarp();
+                        const unsigned hitm = __ballot_sync(FULL, st2 == HL_HIT);
+                        const unsigned livem = __ballot_sync(FULL, r < nw);
+                        for (int w = 0; w < nw; ++w)
+                            if (hitm & (((per >= 32) ? 0xffffffffu : ((1u << per) - 1u)) << (w * per))) dead |= 1u << w;
+                        if (lane == 0) T.s_checks += (unsigned long long)__popc(livem);
                     }
-                    const RsPlan& plan = (k < AQ_MAX_PLANS) ? T.plans[k] : T.plan_tmp;
-                    ref_all += (unsigned long long)plan.npts;
-                    const bool hit = aq_word_collides(Ers, eb, D, plan, q0, cq, sq, P.maxc, inv_maxc, FLAGS, T, lane);
-                    if (!hit && xdiv(T.rs_L[k], P.maxc) < P.min_len_goal) { first_free = k; break; }
+#endif
+#pragma unroll 1
+                    for (int w = 0; w < nw; ++w) {
+                        const RsPlan& plan = T.plans[w];
+                        ref_all += (unsigned long long)plan.npts;
+                        if (dead & (1u << w)) continue;
+                        const bool hit = aq_word_collides(Ers, eb, D, plan, q0, cq, sq, P.maxc, inv_maxc, FLAGS, T, lane);
+                        if (!hit && xdiv(T.rs_L[k0 + w], P.maxc) < P.min_len_goal) { first_free = k0 + w; break; }
+                    }
+                    STICK(PH_RS_SAMPLE);
                 }
                 if (first_free < 0) {
                     if (lane == 0) T.s_ref += ref_all;       // every word tried and refuted (:272-287 falls through)
@@ -643,31 +762,18 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                         const int k = T.rs_order[r];
                         if (k < first_free) { tally += (unsigned long long)T.rs_npts[k]; continue; }
                         if (k == first_free) { tally += (unsigned long long)T.rs_npts[k]; winner = k; break; }
-                        const int c = T.rs_acc[k];
-                        if (k >= AQ_MAX_PLANS) {
-                            __syncwarp();
-                            if (lane == 0) {
-                                rs_make_plan(c, T.rs_lens[c], P.maxc, stepn, T.plan_tmp);
-                                rs_plan_world32(T.plan_tmp, q0, cq, sq, D.origin);
-                                T.rs_npts[k] = T.plan_tmp.npts;
-                            }
-                            __syncwarp();
-                        }
-                        const RsPlan& plan = (k < AQ_MAX_PLANS) ? T.plans[k] : T.plan_tmp;
+                        aq_make_plans(T, k, 1, &T.plan_tmp, q0, cq, sq, D.origin, P.maxc, stepn, lane);
+                        const RsPlan& plan = T.plan_tmp;
                         tally += (unsigned long long)plan.npts;
                         const bool hit = aq_word_collides(Ers, eb, D, plan, q0, cq, sq, P.maxc, inv_maxc, FLAGS, T, lane);
                         if (!hit && xdiv(T.rs_L[k], P.maxc) < P.min_len_goal) winner = k;
                     }
                     __syncwarp();
+                    aq_make_plans(T, winner, 1, &T.plan_tmp, q0, cq, sq, D.origin, P.maxc, stepn, lane);   // the result path's plan
                     if (lane == 0) {
-                        const int c = T.rs_acc[winner];
-                        if (winner >= AQ_MAX_PLANS) {            // the winner's plan for the result path
-                            rs_make_plan(c, T.rs_lens[c], P.maxc, stepn, T.plan_tmp);
-                            rs_plan_world32(T.plan_tmp, q0, cq, sq, D.origin);
-                        }
                         T.s_ref += tally;
-                        T.rs_pick = winner < AQ_MAX_PLANS ? winner : AQ_MAX_PLANS;
-                        T.rs_word = c; T.rs_goal_cost = T.rs_prio[winner];
+                        T.rs_pick = AQ_MAX_PLANS;                // = plan_tmp (finalize_spec)
+                        T.rs_word = T.rs_acc[winner]; T.rs_goal_cost = T.rs_prio[winner];
                     }
                     success = true;
                 }
