@@ -36,6 +36,9 @@
 #define AQ_GUIDE_CAP 192               // guide polyline points staged in shared memory (longer polylines are read from HBM / L2)
 #endif
 #define AQ_SUB (AQ_TEAM / 16)          // lanes per primitive in the batched guide-distance pass
+#ifndef AQ_FAR
+#define AQ_FAR 4                       // poses per primitive (farthest first) in the first filter round
+#endif
 #define AQ_TEAM (32 * AQ_EXPANDERS)
 #define AQ_NO_HIT 0x7fffffff
 #ifndef AQ_TIMERS
@@ -99,7 +102,9 @@ struct AqSmem {                          // one per scenario slot, shared by its
     long long path_off;
     __align__(16) float envf[AW_ENV_FLOATS];
     double gx[AQ_GUIDE_CAP], gy[AQ_GUIDE_CAP];       // guide polyline of the scenario (calculate_state_cost's argmin)
-    int guide_staged;
+    double gyaw[AQ_GUIDE_CAP], gs[AQ_GUIDE_CAP];     // ... its headings and arc lengths
+    double pds[HL_MAX_PRIMS][AS_ROLL];               // step lengths of the rolled-out primitives (g-cost)
+    int guide_staged, need_seg;
 #if AQ_HEAP_SM > 0
     double hp_prio[AQ_HEAP_SM];                     // top of the open-list heap (HeapRef)
     int hp_slot[AQ_HEAP_SM];
@@ -173,6 +178,31 @@ __device__ __noinline__ void aq_heap_set(AqSmem& S, const AsWs& w, int& n, int s
     heap_set_t<AQ_HEAP_SM>(H, n, slot, prio);
 }
 
+// Open-list insertion of a NEW key by a whole warp (heapdict.__setitem__ -> append + _decrease_key): lane L looks at
+// the L-th ancestor of the insertion position, a ballot finds the first ancestor that stays (strictly smaller
+// priority), the ancestors below it move down one level in parallel and the new entry takes the freed position --
+// the arrangement the sequential swaps produce, in one step instead of up to 13 dependent ones.
+__device__ __forceinline__ void aq_heap_push_warp(AqSmem& S, const AsWs& w, int slot, double prio, int lane) {
+#if AQ_HEAP_SM > 0
+    const HeapRef<AQ_HEAP_SM> H{w, S.hp_prio, S.hp_slot};
+#else
+    const HeapRef<0> H{w, nullptr, nullptr};
+#endif
+    const int i = S.heap_n;
+    const int depth = 31 - __clz(i + 1);                 // the root is the depth-th ancestor
+    const bool mine = lane >= 1 && lane <= depth;
+    const int a = ((i + 1) >> lane) - 1;
+    double ap = 0.0;
+    int as = 0;
+    if (mine) { ap = H.prio(a); as = H.slot(a); }
+    const unsigned stopm = __ballot_sync(FULL, mine && ap < prio);
+    const int stop = stopm ? (__ffs(stopm) - 1) : depth + 1;
+    __syncwarp();
+    if (mine && lane < stop) H.put(((i + 1) >> (lane - 1)) - 1, ap, as);
+    if (lane == 0) { H.put(((i + 1) >> (stop - 1)) - 1, prio, slot); S.heap_n = i + 1; }
+    __syncwarp();
+}
+
 // calculate_state_cost (reference_line_heuristic.py:131-158) of EVERY primitive that needs one, the whole expander
 // team at once: AQ_SUB lanes per primitive walk the guide polyline (shared memory) with stride AQ_SUB -- one pass for
 // the minimum squared distance (ordering filter), one for the exact hypot of the near-minimal points (first minimum
@@ -188,7 +218,7 @@ __device__ __noinline__ void team_state_costs(AqSmem& S, const EnvBatchDev& eb, 
     const double* gy = S.guide_staged ? S.gy : eb.guide_y + D.guide_off;
     const double x = p >= 0 ? S.tx[p][nst] : 0.0, y = p >= 0 ? S.ty[p][nst] : 0.0;
     double best = INFINITY;
-#pragma unroll 2
+#pragma unroll 4
     for (int i = sub; i < n; i += AQ_SUB) {
         const double dx = gx[i] - x, dy = gy[i] - y;
         best = fmin(best, dx * dx + dy * dy);
@@ -216,13 +246,163 @@ __device__ __noinline__ void team_state_costs(AqSmem& S, const EnvBatchDev& eb, 
         double h = 0.0;
         if (n > 0) {
             double dist = xmul(bh, 100.0);
-            const double yaw_diff = fabs(angle_wrap(xsub(eb.guide_yaw[D.guide_off + bi], S.pyaw[p][nst])));
+            const double* gyaw = S.guide_staged ? S.gyaw : eb.guide_yaw + D.guide_off;
+            const double* gs = S.guide_staged ? S.gs : eb.guide_s + D.guide_off;
+            const double yaw_diff = fabs(angle_wrap(xsub(gyaw[bi], S.pyaw[p][nst])));
             if (dist > 2.0) dist = 100.0;
-            const double to_goal = xsub(eb.guide_s[D.guide_off + n - 1], eb.guide_s[D.guide_off + bi]);
+            const double to_goal = xsub(gs[n - 1], gs[bi]);
             h = xadd(xadd(dist, xmul(yaw_diff, 0.2)), xmul(to_goal, 5.0));
         }
         S.pprio[p] = xmul(P.hybrid_cost, h);
     }
+}
+
+// The 46 candidate rows of generate_path (reeds_shepp.py:565-582) in two warp-wide passes built around UNIFORM calls of
+// the float64 transcendentals.  rs_solve's switch makes the lanes of a pass run every formula one after the other
+// (~3700 dependent instructions per shot); here a pass is a fixed sequence of slots -- polar, atan2 / asin, the two
+// M() folds; in pass B also acos, sincos, tan -- that all lanes enter together with their own arguments, and the
+// solver-specific arithmetic between the slots is a few selects.  Pass A: LSL, LSR, LRL, LRSL, LRSR rows (32 lanes, all
+// start with R(x -+ sin phi, y - 1 +- cos phi)).  Pass B: LRLRn / LRLRp on lanes 0-7, LRSLR on 8-11, SLS on 12-13; lanes
+// 16-23 and 28-29 are HELPERS of lanes 0-7 / 12-13: they repeat the cheap prefix and take the second transcendental of
+// the same kind (sincos(delta) next to sincos(u); tan(phi/2) next to tan(phi)).  Every value is produced by the same
+// float64 operations in the same order as rs_solve / rs_candidate (cos(v) = cos(u) for v = +-u: cos is even bit for bit).
+static __constant__ signed char c_aq_pass_a[32] = {2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17,
+                                                   26, 27, 28, 29, 34, 35, 36, 37, 30, 31, 32, 33, 38, 39, 40, 41};
+static __constant__ signed char c_aq_pass_b[16] = {18, 19, 20, 21, 22, 23, 24, 25, 42, 43, 44, 45, 0, 1, -1, -1};
+
+__device__ __forceinline__ void aq_store_candidate(AqShot& T, int c, const RsRow& row, bool ok, double t, double u, double v) {
+    double l[HL_RS_MAX_SEGS] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    if (ok) {
+        const double H = xmul(-0.5, HL_PI);
+        switch (row.pattern) {
+        case RP_TUV:   l[0] = t; l[1] = u; l[2] = v; break;
+        case RP_VUT:   l[0] = v; l[1] = u; l[2] = t; break;
+        case RP_TUnUV: l[0] = t; l[1] = u; l[2] = -u; l[3] = v; break;
+        case RP_TUUV:  l[0] = t; l[1] = u; l[2] = u; l[3] = v; break;
+        case RP_THUV:  l[0] = t; l[1] = H; l[2] = u; l[3] = v; break;
+        case RP_VUHT:  l[0] = v; l[1] = u; l[2] = H; l[3] = t; break;
+        default:       l[0] = t; l[1] = H; l[2] = u; l[3] = H; l[4] = v; break;
+        }
+        if (row.neg_x)
+#pragma unroll
+            for (int k = 0; k < HL_RS_MAX_SEGS; ++k) l[k] = (k < row.nseg) ? -l[k] : l[k];
+    }
+    T.rs_valid[c] = ok ? 1 : 0;
+#pragma unroll
+    for (int k = 0; k < HL_RS_MAX_SEGS; ++k) T.rs_lens[c][k] = l[k];
+}
+
+__device__ __noinline__ void aq_rs_candidates(AqShot& T, int lane) {
+    const double PI = HL_PI;
+    const RsProblem Pb = T.rs_prob;
+    {   // ------------------------------------------------ pass A
+        const int c = c_aq_pass_a[lane];
+        const RsRow row = c_rs_rows[c];
+        double x = row.backwards ? Pb.xb : Pb.x, y = row.backwards ? Pb.yb : Pb.y;
+        if (row.neg_x) x = -x;
+        if (row.neg_y) y = -y;
+        const bool negphi = row.neg_x != row.neg_y;
+        const double phi = negphi ? -Pb.phi : Pb.phi, sphi = negphi ? -Pb.sp : Pb.sp, cphi = Pb.cp;
+        const int solver = row.solver;
+        const bool plus = solver == RS_LSR || solver == RS_LRSR;
+        const double xi = plus ? xadd(x, sphi) : xsub(x, sphi);
+        const double eta = plus ? xsub(xsub(y, 1.0), cphi) : xadd(xsub(y, 1.0), cphi);
+        const double X = (solver == RS_LRSR) ? -eta : xi, Y = (solver == RS_LRSR) ? xi : eta;
+        const double r = hypot_cr(X, Y);                     // slot: R(X, Y)
+        const double th = m_atan2(Y, X);
+        bool ok = true;
+        double u = r, r2 = 0.0;
+        if (solver == RS_LSR) { const double u1 = xmul(r, r); ok = u1 >= 4.0; u = sqrt(xsub(u1, 4.0)); }
+        else if (solver == RS_LRSL) { ok = r >= 2.0; r2 = sqrt(xsub(xmul(r, r), 4.0)); u = xsub(2.0, r2); }
+        else if (solver == RS_LRSR) { ok = r >= 2.0; u = xsub(2.0, r); }
+        else if (solver == RS_LRL) ok = r <= 4.0;
+        double aux = 0.0;
+        if (solver == RS_LSR || solver == RS_LRSL)           // slot: atan2(2, u) / atan2(r, -2)
+            aux = m_atan2(solver == RS_LSR ? 2.0 : r2, solver == RS_LSR ? u : -2.0);
+        if (solver == RS_LRL) u = xmul(-2.0, m_asin(xmul(0.25, r)));       // slot: asin
+        const bool tmod = solver == RS_LSR || solver == RS_LRL || solver == RS_LRSL;
+        const double targ = (solver == RS_LRL) ? xadd(xadd(th, xmul(0.5, u)), PI) : xadd(th, aux);
+        const double tm = rs_mod2pi(tmod ? targ : 0.0);      // slot: M(t)
+        const double t = tmod ? tm : th;
+        double varg;
+        if (solver == RS_LSL) varg = xsub(phi, t);
+        else if (solver == RS_LSR) varg = xsub(t, phi);
+        else if (solver == RS_LRL) varg = xadd(xsub(phi, t), u);
+        else if (solver == RS_LRSL) varg = xsub(xsub(phi, xmul(0.5, PI)), t);
+        else varg = xsub(xadd(t, xmul(0.5, PI)), phi);
+        const double v = rs_mod2pi(varg);                    // slot: M(v)
+        if (solver == RS_LSL || solver == RS_LSR) ok = ok && t >= 0.0 && v >= 0.0;
+        else if (solver == RS_LRL) ok = ok && t >= 0.0 && u <= 0.0;
+        else ok = ok && t >= 0.0 && u <= 0.0 && v <= 0.0;
+        aq_store_candidate(T, c, row, ok, t, u, v);
+    }
+    __syncwarp();
+    {   // ------------------------------------------------ pass B
+        const bool helper = lane >= 16;
+        const int c = c_aq_pass_b[lane & 15];
+        const bool have = c >= 0;
+        const RsRow row = c_rs_rows[have ? c : 0];
+        double x = row.backwards ? Pb.xb : Pb.x, y = row.backwards ? Pb.yb : Pb.y;
+        if (row.neg_x) x = -x;
+        if (row.neg_y) y = -y;
+        const bool negphi = row.neg_x != row.neg_y;
+        const double phi = negphi ? -Pb.phi : Pb.phi, sphi = negphi ? -Pb.sp : Pb.sp, cphi = Pb.cp;
+        const int solver = have ? (int)row.solver : -1;
+        const bool lrlr = solver == RS_LRLRN || solver == RS_LRLRP, isn = solver == RS_LRLRN;
+        const bool sls = solver == RS_SLS, lrslr = solver == RS_LRSLR;
+        const double xi = xadd(x, sphi);
+        const double eta = xsub(xsub(y, 1.0), cphi);
+        const double r = hypot_cr(xi, eta);                  // slot: rho of R(xi, eta) (LRSLR; its theta is not used)
+        bool ok = have;
+        double rho = 0.5;
+        if (isn) { rho = xmul(0.25, xadd(2.0, sqrt(xadd(xmul(xi, xi), xmul(eta, eta))))); ok = rho <= 1.0; }
+        else if (lrlr) { rho = xdiv(xsub(xsub(20.0, xmul(xi, xi)), xmul(eta, eta)), 16.0); ok = 0.0 <= rho && rho <= 1.0; }
+        const double ac = m_acos(lrlr ? rho : 0.5);          // slot: acos
+        const double uu = isn ? ac : -ac, vv = isn ? -uu : uu;
+        if (lrlr && !isn) ok = ok && uu >= xmul(-0.5, PI);
+        const double m1 = rs_mod2pi(sls ? phi : xsub(uu, vv));   // slot: M(phi) (SLS) / delta = M(u - v)
+        double sn, cs;
+        m_sincos(lrlr ? (helper ? m1 : uu) : 0.0, &sn, &cs);    // slot: sincos(u) | sincos(delta)
+        const double osn = __shfl_xor_sync(FULL, sn, 16), ocs = __shfl_xor_sync(FULL, cs, 16);
+        const double s_uu = helper ? osn : sn, c_uu = helper ? ocs : cs, s_de = helper ? sn : osn, c_de = helper ? cs : ocs;
+        const double tn = m_tan(sls ? (helper ? xdiv(m1, 2.0) : m1) : 0.0);   // slot: tan(phi) | tan(phi / 2)
+        const double otn = __shfl_xor_sync(FULL, tn, 16);
+        const double tan_phi = helper ? otn : tn, tan_half = helper ? tn : otn;
+        double a_y = 0.0, a_x = 1.0, u = 0.0;
+        if (lrlr) {
+            const double A = xsub(s_uu, s_de);
+            const double B = xsub(xsub(c_uu, c_de), 1.0);
+            a_y = xsub(xmul(eta, A), xmul(xi, B)); a_x = xadd(xmul(xi, A), xmul(eta, B));
+            u = uu;
+        } else if (lrslr) {
+            ok = ok && r >= 2.0;
+            u = xsub(4.0, sqrt(xsub(xmul(r, r), 4.0)));
+            ok = ok && u <= 0.0;
+            a_y = xsub(xmul(xsub(4.0, u), xi), xmul(2.0, eta)); a_x = xadd(xmul(-2.0, xi), xmul(xsub(u, 4.0), eta));
+        }
+        const double at = m_atan2(a_y, a_x);                 // slot: atan2
+        double targ = at;
+        if (lrlr) {
+            const double t2 = xadd(xmul(2.0, xsub(xsub(c_de, c_uu), c_uu)), 3.0);     // cos(v) = cos(u)
+            if (t2 < 0) targ = xadd(at, PI);
+        }
+        double t = rs_mod2pi(targ);                          // slot: M(t)
+        const double varg = lrlr ? xsub(xadd(xsub(t, uu), vv), phi) : xsub(t, phi);
+        double v = rs_mod2pi(varg);                          // slot: M(v)
+        if (lrlr) ok = ok && t >= 0.0 && (isn ? v <= 0.0 : v >= 0.0);
+        else if (lrslr) ok = ok && t >= 0.0 && v >= 0.0;
+        else if (sls) {
+            ok = (y > 0.0 || y < 0.0) && 0.0 < m1 && m1 < xmul(PI, 0.99);
+            const double xd = xadd(xdiv(-y, tan_phi), x);
+            t = xsub(xd, tan_half);
+            u = m1;
+            const double dx = xsub(x, xd);
+            const double rt = sqrt(xadd(xmul(dx, dx), xmul(y, y)));
+            v = (y > 0.0) ? xsub(rt, tan_half) : xsub(-rt, tan_half);
+        }
+        if (have && !helper) aq_store_candidate(T, c, row, ok, t, u, v);
+    }
+    __syncwarp();
 }
 
 // `while px[-1] == 0.0: pop` of generate_local_course (reeds_shepp.py:520-528) for a word whose end point has a local
@@ -540,7 +720,7 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
 #pragma unroll 1
         for (int i = lane; i < P.hash_size; i += 32) W.hkey[i] = KEY_EMPTY;
         if (lane == 0) {
-            S.x_expanding = 0; S.x_finished = 0;
+            S.x_expanding = 0; S.x_finished = 0; S.need_seg = 0;
             S.state = ST_IDLE; S.epoch = 0; S.popped = 0; S.ew_done = 0; S.shot_best = AQ_NO_HIT;
             for (int k = 0; k < AQ_SHOOTERS; ++k) S.sh[k].done_epoch = 0;
         }
@@ -649,20 +829,7 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                     }
                     __syncwarp();
                 }
-                // two passes with DISJOINT solver sets (30 + 16 rows): the lanes of a pass diverge over the solver
-                // switch, so each formula's code runs once per shot instead of once per pass
-#pragma unroll 1
-                for (int pass = 0; pass < 2; ++pass) {
-                    const int c = c_rs_pass_cand[pass][lane];
-                    if (c >= 0) {
-                        double l[HL_RS_MAX_SEGS] = {0, 0, 0, 0, 0};
-                        bool ok = rs_candidate(c, T.rs_prob, l);
-                        T.rs_valid[c] = ok ? 1 : 0;
-                        for (int k = 0; k < HL_RS_MAX_SEGS; ++k) T.rs_lens[c][k] = l[k];
-                    }
-                    __syncwarp();
-                }
-                __syncwarp();
+                aq_rs_candidates(T, lane);
                 STICK(PH_RS_CAND);
                 if (lane < RS_N_GROUPS) rs_select_group(lane, T.rs_valid, T.rs_lens, T.rs_accept, T.rs_Lc);
                 __syncwarp();
@@ -830,7 +997,10 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
         const EnvDesc& D = *Dp;
         stage_env_warp(eb, D, S.envf, AW_ENV_FLOATS, E, lane);
         if (D.n_guide <= AQ_GUIDE_CAP) {
-            for (int i = lane; i < D.n_guide; i += 32) { S.gx[i] = eb.guide_x[D.guide_off + i]; S.gy[i] = eb.guide_y[D.guide_off + i]; }
+            for (int i = lane; i < D.n_guide; i += 32) {
+                S.gx[i] = eb.guide_x[D.guide_off + i]; S.gy[i] = eb.guide_y[D.guide_off + i];
+                S.gyaw[i] = eb.guide_yaw[D.guide_off + i]; S.gs[i] = eb.guide_s[D.guide_off + i];
+            }
         }
         if (lane == 0) S.guide_staged = D.n_guide <= AQ_GUIDE_CAP ? 1 : 0;
         // start / goal feasibility and start node (shared helper works on an AwSmem-like view)
@@ -902,13 +1072,27 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                         double xd = fabs(xsub(S.cx, S.goal[0])), yd = fabs(xsub(S.cy, S.goal[1]));
                         double wd = fabs(angle_wrap(xsub(S.cyaw, S.goal[2])));
                         if (xd < P.res && yd < P.res && wd < P.yaw_res) { S.ew_arrival2 = 1; S.ew_status = HL_STATUS_OK; }
-                        else {
-                            int seg = exact_search_segment(eb, D, S.cx, S.cy);
-                            double len = seg < 0 ? D.default_len : eb.seg_len[D.seg_off + seg];
-                            S.nsteps = (int)rint(xdiv(len, P.res));
-                            if (S.nsteps + 1 > HL_MAX_ROLLOUT || S.nsteps < 1) S.ew_status = HL_STATUS_CAPACITY;
-                        }
+                        else S.need_seg = 1;
                     }
+                }
+            }
+            __syncwarp();
+            const int need_seg = S.need_seg;
+            __syncwarp();
+            if (need_seg) {
+                // search length of this node (reference_line_heuristic.py:120-129: LAST capsule whose interior holds
+                // the point), one capsule per lane
+                bool in = false;
+                if (lane < D.n_seg)
+                    in = exact_point_in_capsule(eb.seg64 + 4 * (size_t)(D.seg_off + lane),
+                                                eb.seg_poly + 2 * HL_CAPSULE_VERTS * (size_t)(D.seg_off + lane), S.cx, S.cy, true);
+                const unsigned inm = __ballot_sync(FULL, in);
+                if (lane == 0) {
+                    const int seg = inm ? 31 - __clz(inm) : -1;
+                    const double len = seg < 0 ? D.default_len : eb.seg_len[D.seg_off + seg];
+                    S.nsteps = (int)rint(xdiv(len, P.res));
+                    if (S.nsteps + 1 > HL_MAX_ROLLOUT || S.nsteps < 1) S.ew_status = HL_STATUS_CAPACITY;
+                    S.need_seg = 0;
                 }
             }
             if (lane < HL_MAX_PRIMS) { S.phit[lane] = 0; S.pneed[lane] = 1; }
@@ -980,7 +1164,7 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
             // One hit kills a primitive, and a primitive that collides does so far from the (feasible) node it starts
             // at: test the two farthest poses of every primitive first, then only the live primitives' other poses.
             {
-                const int far_cnt = np1 < 2 ? np1 : 2;
+                const int far_cnt = np1 < AQ_FAR ? np1 : AQ_FAR;
 #pragma unroll 1
                 for (int idx = tl; idx < P.n_prims * far_cnt; idx += AQ_TEAM) {
                     const int p = idx / far_cnt, j = n - (idx - p * far_cnt);
@@ -1021,14 +1205,18 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
         if (expanding) {
             {
             const int n = S.nsteps, np1 = n + 1;
+            // step lengths of calculate_path_length (np.hypot of np.diff), one lane per (primitive, step)
+#pragma unroll 1
+            for (int idx = tl; idx < P.n_prims * n; idx += AQ_TEAM) {
+                const int p = idx / n, i = idx - p * n;
+                if (!S.phit[p]) S.pds[p][i] = hypot_cr(xsub(S.tx[p][i + 1], S.tx[p][i]), xsub(S.ty[p][i + 1], S.ty[p][i]));
+            }
+            team_sync(slot);
             if (tl < P.n_prims && !S.phit[lane]) {
                 const int p = lane;
                 double len = 0.0;
 #pragma unroll 1
-                for (int i = 0; i + 1 < np1; ++i) {
-                    double ds = hypot_cr(xsub(S.tx[p][i + 1], S.tx[p][i]), xsub(S.ty[p][i + 1], S.ty[p][i]));
-                    len = (i == 0) ? ds : xadd(len, ds);
-                }
+                for (int i = 0; i + 1 < np1; ++i) len = (i == 0) ? S.pds[p][0] : xadd(len, S.pds[p][i]);
                 double cost = xadd(S.cg, len);
                 if (P.dir[p] == -1.0) cost = xadd(cost, P.reverse_cost);
                 cost = xadd(cost, xmul(P.steer[p], P.steer_cost));
@@ -1052,30 +1240,47 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
             team_state_costs(S, eb, D, P, n, tl, lane);
             team_sync(slot);
             if (ew == 0) ETICK(PH_COST_HEUR);
-            if (tl == 0) {
+            if (ew == 0) {
+                // merge into the open list (:580-596) in primitive order, the whole warp in step: the lookups are
+                // uniform (broadcast) loads, lane 0 writes the node, the heap insertion is warp-wide
+                unsigned todo = __ballot_sync(FULL, lane < P.n_prims && !S.phit[lane]);
 #pragma unroll 1
-                for (int p = 0; p < P.n_prims; ++p) {
-                    if (S.phit[p]) continue;
-                    if (!S.pkey_ok[p]) { S.ew_status = HL_STATUS_CAPACITY; break; }
+                while (todo) {
+                    const int p = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    if (!S.pkey_ok[p]) { if (lane == 0) S.ew_status = HL_STATUS_CAPACITY; break; }
                     int pos = S.ppos[p];
                     int slot2 = S.pslot[p];
                     if (slot2 < 0 ? (W.hkey[pos] != KEY_EMPTY) : false) slot2 = hash_find(W, hmask, S.pkey[p], &pos);
                     const double g = S.pg[p];
                     const double prio = (S.pprio[p] > g) ? S.pprio[p] : g;
+                    int at = -1;                                 // position of an existing OPEN entry of this key
                     if (slot2 >= 0) {
                         if (W.nstate[slot2] == 1) continue;
                         if (!(g < W.ng[slot2])) continue;
-                        if (!S.pneed[p]) { S.ew_status = HL_STATUS_CAPACITY; break; }
+                        if (!S.pneed[p]) { if (lane == 0) S.ew_status = HL_STATUS_CAPACITY; break; }
+                        at = W.nheap[slot2];
                     } else {
-                        if (S.n_nodes >= P.cap_nodes) { S.ew_status = HL_STATUS_CAPACITY; break; }
-                        slot2 = S.n_nodes++;
-                        W.hkey[pos] = S.pkey[p]; W.hval[pos] = slot2; W.nhpos[slot2] = pos;
-                        W.nkey[slot2] = S.pkey[p]; W.nstate[slot2] = 0; W.nheap[slot2] = -1;
+                        const int nn = S.n_nodes;
+                        if (nn >= P.cap_nodes) { if (lane == 0) S.ew_status = HL_STATUS_CAPACITY; break; }
+                        slot2 = nn;
+                        __syncwarp();
+                        if (lane == 0) {
+                            S.n_nodes = nn + 1;
+                            W.hkey[pos] = S.pkey[p]; W.hval[pos] = slot2; W.nhpos[slot2] = pos;
+                            W.nkey[slot2] = S.pkey[p]; W.nstate[slot2] = 0; W.nheap[slot2] = -1;
+                        }
                     }
-                    W.nx[slot2] = S.tx[p][n]; W.ny[slot2] = S.ty[p][n]; W.nyaw[slot2] = S.pyaw[p][n];
-                    W.ng[slot2] = g; W.nparent[slot2] = S.cur; W.nprim[slot2] = (signed char)p;
-                    W.nsteps[slot2] = (signed char)n;
-                    aq_heap_set(S, W, S.heap_n, slot2, prio);
+                    if (lane == 0) {
+                        W.nx[slot2] = S.tx[p][n]; W.ny[slot2] = S.ty[p][n]; W.nyaw[slot2] = S.pyaw[p][n];
+                        W.ng[slot2] = g; W.nparent[slot2] = S.cur; W.nprim[slot2] = (signed char)p;
+                        W.nsteps[slot2] = (signed char)n;
+                    }
+                    __syncwarp();
+                    if (at >= 0) {                               // re-keying an open node: heapdict pops it first (rare)
+                        if (lane == 0) aq_heap_set(S, W, S.heap_n, slot2, prio);
+                        __syncwarp();
+                    } else aq_heap_push_warp(S, W, slot2, prio, lane);
                 }
             }
             __syncwarp();
