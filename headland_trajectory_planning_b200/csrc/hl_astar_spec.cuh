@@ -1241,9 +1241,60 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
             team_sync(slot);
             if (ew == 0) ETICK(PH_COST_HEUR);
             if (ew == 0) {
-                // merge into the open list (:580-596) in primitive order, the whole warp in step: the lookups are
-                // uniform (broadcast) loads, lane 0 writes the node, the heap insertion is warp-wide
-                unsigned todo = __ballot_sync(FULL, lane < P.n_prims && !S.phit[lane]);
+                // merge into the open list (:580-596).  What the cost phase looked up (hash position, existing node,
+                // "not needed") stays valid unless two children of THIS expansion meet in the hash table -- the same
+                // empty position or the same node.  Without such a meeting (the rule) every child is written by its own
+                // lane -- new node ids by a prefix count over the primitives, in order -- and only the open-list
+                // insertions are serialised (warp-wide pushes, primitive order).  Otherwise (rare) the ordered
+                // re-probing loop below does everything.
+                const bool live = lane < P.n_prims && !S.phit[lane];
+                const int my_pos = live ? S.ppos[lane] : -1, my_slot = live ? S.pslot[lane] : -1;
+                bool meet = live && !S.pkey_ok[lane];
+                if (live) {
+#pragma unroll 1
+                    for (int q = 0; q < lane; ++q) {
+                        if (S.phit[q]) continue;
+                        if (my_slot < 0 ? (S.pslot[q] < 0 && S.ppos[q] == my_pos) : (S.pslot[q] == my_slot)) meet = true;
+                    }
+                }
+                const unsigned newm = __ballot_sync(FULL, live && my_slot < 0);
+                const bool slow = __any_sync(FULL, meet) || S.n_nodes + __popc(newm) > P.cap_nodes;
+                unsigned todo = __ballot_sync(FULL, live);
+                if (!slow) {
+                    const unsigned pushm = __ballot_sync(FULL, live && (my_slot < 0 || S.pneed[lane]));
+                    const int base = S.n_nodes;
+                    __syncwarp();
+                    if (live && (my_slot < 0 || S.pneed[lane])) {
+                        const int p = lane;
+                        int slot2 = my_slot;
+                        if (slot2 < 0) {
+                            slot2 = base + __popc(newm & ((1u << lane) - 1u));
+                            W.hkey[my_pos] = S.pkey[p]; W.hval[my_pos] = slot2; W.nhpos[slot2] = my_pos;
+                            W.nkey[slot2] = S.pkey[p]; W.nstate[slot2] = 0; W.nheap[slot2] = -1;
+                            S.pslot[p] = -1 - slot2;             // new node: id handed to the push loop
+                        }
+                        W.nx[slot2] = S.tx[p][n]; W.ny[slot2] = S.ty[p][n]; W.nyaw[slot2] = S.pyaw[p][n];
+                        W.ng[slot2] = S.pg[p]; W.nparent[slot2] = S.cur; W.nprim[slot2] = (signed char)p;
+                        W.nsteps[slot2] = (signed char)n;
+                    }
+                    if (lane == 0) S.n_nodes = base + __popc(newm);
+                    __syncwarp();
+                    unsigned push = pushm;
+#pragma unroll 1
+                    while (push) {
+                        const int p = __ffs(push) - 1;
+                        push &= push - 1;
+                        const double g = S.pg[p];
+                        const double prio = (S.pprio[p] > g) ? S.pprio[p] : g;
+                        const int ps = S.pslot[p];
+                        if (ps < 0) aq_heap_push_warp(S, W, -1 - ps, prio, lane);
+                        else {                                   // an open node got cheaper: heapdict re-keys it
+                            if (lane == 0) aq_heap_set(S, W, S.heap_n, ps, prio);
+                            __syncwarp();
+                        }
+                    }
+                    todo = 0;
+                }
 #pragma unroll 1
                 while (todo) {
                     const int p = __ffs(todo) - 1;
