@@ -362,7 +362,7 @@ def main():
                        "setup_s_untimed": round(setup_s, 1)},
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": args.steps,
+            "gpu_launches": args.steps * ops.astar_launches_per_call(envs, n),
             "roofline": {"bound": "alu_fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp32_peak if fp32_peak else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one k_hybrid_astar_s launch on this very

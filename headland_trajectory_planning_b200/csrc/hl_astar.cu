@@ -112,6 +112,12 @@ struct AwOut {
     long long path_capacity;
     unsigned long long* path_cursor;
     unsigned long long* phase_cycles;
+    // two-phase sweeps (k_hybrid_astar_s): `order` lists the scenarios to run (NULL = 0 .. n-1; `order_count` then holds
+    // their number on the device); with `first_only` a scenario whose FIRST analytic shot fails is not searched but
+    // appended to `defer_list` for the second launch
+    const int* order; const int* order_count;
+    int* defer_list; int* defer_count;
+    int first_only;
 };
 
 // Results of a finished scenario: expanded keys, path (get_path_from_expanded_nodes, :429-454), record.
@@ -940,6 +946,7 @@ extern "C" int hl_hybrid_astar_batch(hl_ctx* ctx, const hl_env_batch* envs, cons
     O.path_x = d_path_x; O.path_y = d_path_y; O.path_yaw = d_path_yaw; O.path_k = d_path_k; O.path_dir = d_path_dir;
     O.path_capacity = (long long)path_capacity; O.path_cursor = d_path_cursor;
     O.phase_cycles = (unsigned long long*)(ctx->d_counters + 16);
+    O.order = nullptr; O.order_count = nullptr; O.defer_list = nullptr; O.defer_count = nullptr; O.first_only = 0;
     if (level) {
         HL_CUDA_OK(cudaMemsetAsync(d_path_cursor, 0, sizeof(unsigned long long), st));
         HL_CUDA_OK(cudaMemsetAsync(d_keys_cursor, 0, sizeof(unsigned long long), st));
@@ -977,7 +984,32 @@ extern "C" int hl_hybrid_astar_batch(hl_ctx* ctx, const hl_env_batch* envs, cons
     HL_CUDA_OK(cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned int), st));
     HL_CUDA_OK(cudaMemsetAsync(d_path_cursor, 0, sizeof(unsigned long long), st));
     HL_CUDA_OK(cudaMemsetAsync(d_keys_cursor, 0, sizeof(unsigned long long), st));
-    if (spec)
+    // Two-phase sweep: when the batch is several times larger than the resident scenario slots, a first launch runs
+    // only the FIRST analytic shot of every scenario (most headland scenarios end there: 72 % of config 5) and lists
+    // the rest; the second launch searches the listed ones, which then all start at once instead of waiting in the
+    // work queue behind trivial scenarios (the sweep's tail is the start time of its longest searches).  Results are
+    // identical: the second launch redoes a listed scenario from its first pop.
+    static const bool two_phase_on = getenv("HL_ASTAR_SINGLE_PHASE") == nullptr;
+    if (spec && two_phase_on && (long long)n_scen > 2LL * grid * slots) {
+        if ((size_t)n_scen > ctx->astar_defer_cap) {
+            if (ctx->astar_defer) cudaFree(ctx->astar_defer);
+            ctx->astar_defer = nullptr; ctx->astar_defer_cap = 0;
+            HL_CUDA_OK(cudaMalloc(&ctx->astar_defer, sizeof(int) * (size_t)n_scen));
+            ctx->astar_defer_cap = (size_t)n_scen;
+        }
+        int* defer_count = (int*)(ctx->d_counters + 4);
+        HL_CUDA_OK(cudaMemsetAsync(ctx->d_counters + 4, 0, sizeof(unsigned int), st));
+        HL_CUDA_OK(cudaMemsetAsync(ctx->d_counters + 8, 0, sizeof(unsigned int), st));
+        AwOut O1 = O;
+        O1.first_only = 1; O1.defer_list = ctx->astar_defer; O1.defer_count = defer_count;
+        k_hybrid_astar_s<<<grid, threads, smem, st>>>(envs->dev, d_scen, n_scen, P, (char*)ctx->astar_ws, stride,
+                                                      ctx->d_counters, O1);
+        HL_CUDA_OK(cudaGetLastError());
+        AwOut O2 = O;
+        O2.order = ctx->astar_defer; O2.order_count = defer_count;
+        k_hybrid_astar_s<<<grid, threads, smem, st>>>(envs->dev, d_scen, n_scen, P, (char*)ctx->astar_ws, stride,
+                                                      ctx->d_counters + 8, O2);
+    } else if (spec)
         k_hybrid_astar_s<<<grid, threads, smem, st>>>(envs->dev, d_scen, n_scen, P, (char*)ctx->astar_ws, stride,
                                                       ctx->d_counters, O);
     else

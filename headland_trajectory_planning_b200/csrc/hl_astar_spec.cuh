@@ -41,6 +41,7 @@
 #endif
 #define AQ_TEAM (32 * AQ_EXPANDERS)
 #define AQ_NO_HIT 0x7fffffff
+#define AQ_STATUS_DEFER 100              // internal: first shot failed in a first-shot-only launch -> second launch
 #ifndef AQ_TIMERS
 #define AQ_TIMERS 1                    // per-role phase timers (hl_astar_phase_cycles); 0 removes ~26 hot timing sites
 #endif
@@ -975,9 +976,13 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
         if (mode == 0) {
         // ---- next scenario
         int sc = 0;
-        if (lane == 0) sc = (int)atomicAdd(work_counter, 1u);
+        if (lane == 0) {
+            sc = (int)atomicAdd(work_counter, 1u);
+            const int n_eff = O.order_count ? *O.order_count : n_scen;
+            sc = sc < n_eff ? (O.order ? O.order[sc] : sc) : -1;
+        }
         sc = __shfl_sync(FULL, sc, 0);
-        if (sc >= n_scen) { if (lane == 0) { __threadfence_block(); S.state = ST_DONE; } finished = true; break; }
+        if (sc < 0) { if (lane == 0) { __threadfence_block(); S.state = ST_DONE; } finished = true; break; }
         if (lane == 0) {
             const HlScenario s = scen[sc];
             S.scen = sc; S.env = s.env_id;
@@ -1097,6 +1102,10 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
             }
             if (lane < HL_MAX_PRIMS) { S.phit[lane] = 0; S.pneed[lane] = 1; }
             __syncwarp();
+            if (O.first_only && S.ew_status < 0) {           // first-shot-only launch: the shooter decides this scenario's fate
+                if (lane == 0) S.ew_status = AQ_STATUS_DEFER;
+                __syncwarp();
+            }
             ETICK(PH_POP);
             if (S.ew_status >= 0) mode = 2; else expanding = true;
         }
@@ -1377,7 +1386,11 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
             }
         }
         __syncwarp();
-        finalize_spec(S, W, P, O, lane);
+        if (S.status == AQ_STATUS_DEFER) {                   // not decided by its first shot: hand it to the second launch
+            if (lane == 0) O.defer_list[atomicAdd(O.defer_count, 1)] = S.scen;
+            for (int i = lane; i < S.n_nodes; i += 32) W.hkey[W.nhpos[i]] = KEY_EMPTY;
+            __syncwarp();
+        } else finalize_spec(S, W, P, O, lane);
             mode = 0;
         }
     }

@@ -77,6 +77,8 @@ struct hl_ctx {
                               // while a prefetch thread spends milliseconds inside hl_env_upload)
     void* ls_state;           // level-synchronous search: graph, streams, pools (hl_astar.cu)
     void (*ls_free)(void*);
+    int* astar_defer;         // two-phase sweeps: scenarios left over by the first-shot launch (hl_astar.cu)
+    size_t astar_defer_cap;
     int astar_variant;        // HL_ASTAR_SPEC / _WARP / _LEVEL (HL_ASTAR_VARIANT read ONCE at hl_ctx_create; hl_ctx_set_astar_variant)
     void* astar_done;         // cudaEvent_t recorded after the last search launch: the workspace / work counter are
                               // per context, so a search on another stream waits for it (searches serialise per ctx)

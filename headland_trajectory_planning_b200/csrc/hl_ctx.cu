@@ -45,6 +45,8 @@ extern "C" int hl_ctx_create(hl_ctx** out, int device) {
     c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     c->astar_ws = nullptr;
     c->astar_ws_bytes = 0;
+    c->astar_defer = nullptr;
+    c->astar_defer_cap = 0;
     c->d_counters = nullptr;
     c->stage = nullptr;
     c->stage_bytes = 0;
@@ -122,6 +124,7 @@ extern "C" void hl_ctx_destroy(hl_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->astar_ws) cudaFree(ctx->astar_ws);
+    if (ctx->astar_defer) cudaFree(ctx->astar_defer);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->stage) cudaFreeHost(ctx->stage);
     for (int k = 0; k < 2; ++k) if (ctx->env_cache[k]) cudaFree(ctx->env_cache[k]);

@@ -338,6 +338,17 @@ def hybrid_astar_batch(envs, scenarios, params, path_capacity=None, to_host=True
     return out
 
 
+def astar_launches_per_call(envs, n_scenarios):
+    """Kernel launches one ``hybrid_astar_batch`` call makes (the default two-warp variant runs sweeps several times
+    larger than the resident scenario slots in two launches: first shots only, then the scenarios they left over)."""
+    import os
+    sm = int(_lib.load_library().hl_ctx_sm_count(envs.ctx))
+    if os.environ.get("HL_ASTAR_SINGLE_PHASE") is None and os.environ.get("HL_ASTAR_VARIANT", "spec") == "spec" \
+            and n_scenarios > 2 * sm * 5:
+        return 2
+    return 1
+
+
 def distance_field(occ, goal, motion_type="King"):
     """Grid distance field from ``goal`` (hl_distance_field).  ``occ``: [W,H] bool/uint8
     (host array or CUDA tensor).  Returns (float64 CUDA tensor [W,H], relaxation launches)."""
