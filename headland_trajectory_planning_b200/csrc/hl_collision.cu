@@ -31,6 +31,8 @@
 #define K1_PER_THREAD (K1_TILE / K1_THREADS)
 #define K1_SLICE (K1_TILE / K1_WARPS)     // poses per warp in the per-pose fallback
 #define K1_ENV_FLOATS 1024                // staged float32 records (canonical environment: 432 floats)
+#define K1_PAIR_CAP 2048                  // (pose, nearby edge) pairs per tile; poses beyond it go to the float64 predicate
+#define K1_QBITS 11                       // bits of the pose index inside a pair (K1_TILE <= 2048, edges < 32)
 #ifndef K1_MIN_CTAS
 #define K1_MIN_CTAS 4
 #endif
@@ -73,22 +75,30 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
 // ------------------------------------------------------------------ shared-memory layout
+// A pose inside the float32 band needs the float64 predicates: a whole warp for ~25 us while the 7 other warps of the
+// CTA wait at the next barrier (2e-4 of the poses, but 12 % of the kernel's stall samples).  Such poses are QUEUED
+// instead; the float32 pipeline goes on as if the ambiguous test had passed (a later verdict can only add "hit"), and
+// when the CTA has no tile left its warps resolve the queue, one entry per warp at a time, all in parallel.
+#define K1_DEFER_CAP 48
+struct K1Defer { long long i; int env; unsigned amb; int rect; int pad; };
 struct __align__(16) K1Cta {
     double raw[K1_TILE * 3];              // TMA landing zone: x, y, yaw of the tile                        24 KB
     float px[K1_TILE], py[K1_TILE];       // pose relative to the environment origin                         8 KB
     float yr[K1_TILE];                    // heading reduced to [-pi, pi]                                    4 KB
-    unsigned nearm[K1_TILE];              // field edges whose line passes within the circumradius           4 KB
+    unsigned short pairs[K1_PAIR_CAP];    // (pose, nearby field edge) pairs of the tile: q | edge << K1_QBITS       4 KB
     unsigned short la[K1_TILE], lb[K1_TILE], lc[K1_TILE];      // compacted pose lists                       6 KB
     unsigned char st[K1_TILE];            // K1S_* bits
     unsigned char amb[K1_TILE];           // HL_CHECK_* bits inside the float32 band
     float env[K1_ENV_FLOATS];             // obstacle records | field-edge records | lane segments           4 KB
     float4 segd[HL_MAX_SEGS];             // per lane segment: ex, ey, 1/len^2, 1/len (derived once per staging)
-    float4 fld[32][2];                    // per field edge, first pass: (Ax, Ay, Ex, Ey) with the endpoints
-                                          // ordered so that Ey >= 0, and (nx, ny, c, By) -- see k1_field1
+    float4 fld[32][3];                    // per field edge, first pass: (Ax, Ay, Ex, Ey) with the endpoints
+                                          // ordered so that Ey >= 0, (nx, ny, c, By), (tmin, tmax, -, -) -- see k1_field1
     unsigned long long bar_env, bar_raw;  // mbarriers of the two kinds of bulk copy
-    int cnt[4];                           // list counters: la, lb, lc, pending
+    int cnt[8];                           // list counters: la, lb, lc, pending, pairs
+    K1Defer dq[K1_DEFER_CAP];             // poses waiting for the float64 predicates (drained when the CTA has no tile left)
+    int dq_cnt;
 };
-enum { K1S_HIT = 1, K1S_INSIDE = 2, K1S_CORNERS = 8, K1S_DONE = 16, K1S_FAR = 32, K1S_OFF = 64 };
+enum { K1S_HIT = 1, K1S_INSIDE = 2, K1S_NOTCLEAR = 4, K1S_CORNERS = 8, K1S_DONE = 16, K1S_FAR = 32, K1S_OFF = 64, K1S_CUT = 128 };
 
 struct K1Env {                            // staged environment (shared memory, uniform per CTA)
     const float* obs_a; const float* field_a; const float* seg_a; const float* segd_a; const float* fld_a;
@@ -201,12 +211,16 @@ __device__ __forceinline__ void k1_field1(const K1Env& E, const K1Rect& R, float
     unsigned nm = 0, par = 0;
     K1_UNROLL(K1_UNROLL_FLD)
     for (int i = 0; i < E.n_field; ++i) {
-        const float4 f0 = lds4(E.fld_a + 8 * i);          // Ax, Ay, Ex, Ey   (Ay <= By)
-        const float4 f1 = lds4(E.fld_a + 8 * i + 4);      // nx, ny, c, By
+        const float4 f0 = lds4(E.fld_a + 12 * i);         // Ax, Ay, Ex, Ey   (Ay <= By)
+        const float4 f1 = lds4(E.fld_a + 12 * i + 4);     // nx, ny, c, By
+        const float2 f2 = *reinterpret_cast<const float2*>(E.fld_a + 12 * i + 8);   // extent of the edge along its direction
         const float lhs = (Cx - f0.x) * f0.w, rhs = f0.z * (Cy - f0.y);
         par ^= (unsigned)(!(f0.y > Cy) && (f1.w > Cy) && (lhs < rhs));
         const float sd = fmaf(f1.x, Cx, fmaf(f1.y, Cy, -f1.z));
-        nm |= (unsigned)(!(fabsf(sd) > rho_eps)) << i;
+        const float ct = fmaf(-f1.y, Cx, f1.x * Cy);
+        // near = the circumcircle of the rectangle reaches the edge's line AND overlaps the edge's extent along it (a
+        // field boundary is mostly runs of collinear edges: the line test alone flags the whole run)
+        nm |= (unsigned)(!(fabsf(sd) > rho_eps) && !(ct - rho_eps > f2.y) && !(ct + rho_eps < f2.x)) << i;
     }
     near_mask = nm; inside = par != 0;
 }
@@ -258,6 +272,46 @@ __device__ __forceinline__ int k1_field2(const K1Env& E, const K1Rect& R, float4
     if (cut) return HL_HIT;
     if (all_clear) return inside ? HL_FREE : HL_HIT;
     return HL_AMBIG;
+}
+
+// Stage D, pair form: ONE nearby edge of one pose (the body of k1_field2's loop).  0 = the edge is clear of the rectangle,
+// 1 = not certified clear, 2 = the edge definitely cuts the rectangle.
+__device__ __forceinline__ int k1_field_pair(const K1Env& E, const K1Rect& R, float4 P, int i) {
+    const float eps = E.eps;
+    const float px = P.x, py = P.y, c = P.z, s = P.w;
+    const float Cx = fmaf(c, R.mx, fmaf(-s, R.my, px)), Cy = fmaf(s, R.mx, fmaf(c, R.my, py));
+    const float4 r0 = lds4(E.field_a + HL_FIELD32_STRIDE * i);        // Ax, Ay, Ex, Ey
+    const float4 r1 = lds4(E.field_a + HL_FIELD32_STRIDE * i + 4);    // nx, ny, c, By
+    const float4 r2 = lds4(E.field_a + HL_FIELD32_STRIDE * i + 8);    // t.A, t.B
+    const float Ax = r0.x, Ay = r0.y, Bx = Ax + r0.z, By = r1.w, nx = r1.x, ny = r1.y;
+    const float nu = fmaf(nx, c, ny * s), nv = fmaf(ny, c, -nx * s);
+    const float sd = fmaf(nx, Cx, fmaf(ny, Cy, -r1.z));
+    if (fabsf(sd) > fmaf(R.hx, fabsf(nu), R.hy * fabsf(nv)) + eps) return 0;
+    const float ct = fmaf(-ny, Cx, nx * Cy);
+    const float rt = fmaf(R.hx, fabsf(nv), R.hy * fabsf(nu));
+    if (ct - rt > fmaxf(r2.x, r2.y) + eps || ct + rt < fminf(r2.x, r2.y) - eps) return 0;
+    const float dxa = Ax - px, dya = Ay - py, dxb = Bx - px, dyb = By - py;
+    const float ua = fmaf(c, dxa, s * dya), wa = fmaf(c, dya, -s * dxa);
+    const float ub = fmaf(c, dxb, s * dyb), wb = fmaf(c, dyb, -s * dxb);
+    if ((fminf(ua, ub) > R.x1 + eps) || (fmaxf(ua, ub) < R.x0 - eps) ||
+        (fminf(wa, wb) > R.y1 + eps) || (fmaxf(wa, wb) < R.y0 - eps)) return 0;
+    float t0 = 0.f, t1 = 1.f;
+    bool dead = false;
+    const float a2[2] = {ua, wa}, d2v[2] = {ub - ua, wb - wa};
+    const float lo2[2] = {R.x0 + eps, R.y0 + eps}, hi2[2] = {R.x1 - eps, R.y1 - eps};
+#pragma unroll
+    for (int ax = 0; ax < 2; ++ax) {
+        if (fabsf(d2v[ax]) < 1e-12f) {
+            if (a2[ax] <= lo2[ax] || a2[ax] >= hi2[ax]) dead = true;
+        } else {
+            const float inv = f_rcp(d2v[ax]);
+            const float tl = (lo2[ax] - a2[ax]) * inv, th = (hi2[ax] - a2[ax]) * inv;
+            t0 = fmaxf(t0, fminf(tl, th));
+            t1 = fminf(t1, fmaxf(tl, th));
+        }
+    }
+    if (!dead && (t1 - t0) * f_sqrt(fmaf(d2v[0], d2v[0], d2v[1] * d2v[1])) > 8.0f * eps) return 2;
+    return 1;
 }
 
 // corner_in_capsule (hl_geom.cuh) on the staged segment + its derived record
@@ -401,7 +455,7 @@ k_collision(EnvBatchDev eb, const int32_t* __restrict__ env_id, const double* __
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned rbar = smem_u32(&S.bar_raw), ebar = smem_u32(&S.bar_env);
     const long long n_tiles = (n + K1_TILE - 1) / K1_TILE;
-    if (tid == 0) { mbar_init(rbar, 1); mbar_init(ebar, 1); }
+    if (tid == 0) { mbar_init(rbar, 1); mbar_init(ebar, 1); S.dq_cnt = 0; }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
     unsigned rphase = 0, ephase = 0;
@@ -455,6 +509,7 @@ k_collision(EnvBatchDev eb, const int32_t* __restrict__ env_id, const double* __
                     const bool up = !(e[1] > e[7]);                    // Ay <= By
                     S.fld[i][0] = up ? make_float4(e[0], e[1], e[2], e[3]) : make_float4(e[0] + e[2], e[7], -e[2], -e[3]);
                     S.fld[i][1] = make_float4(e[4], e[5], e[6], up ? e[7] : e[1]);
+                    S.fld[i][2] = make_float4(fminf(e[8], e[9]), fmaxf(e[8], e[9]), 0.f, 0.f);
                 }
                 E.obs_a = S.env; E.field_a = S.env + n_o; E.seg_a = S.env + n_o + n_f;
                 E.n_obs = D0.n_obs; E.n_field = D0.n_field; E.n_seg = D0.n_seg; E.eps = D0.eps;
@@ -463,7 +518,7 @@ k_collision(EnvBatchDev eb, const int32_t* __restrict__ env_id, const double* __
         }
         const EnvDesc& D = eb.desc[e0];
         const bool tma = tile_tma(tile);
-        if (tid < 4) S.cnt[tid] = 0;
+        if (tid < 8) S.cnt[tid] = 0;
         if (tma) { mbar_wait(rbar, rphase); rphase ^= 1u; }
         // ---- stage 0: poses -> float32 frame; is the whole tile in the staged environment?
         bool same_env = env_ok;
@@ -559,59 +614,94 @@ k_collision(EnvBatchDev eb, const int32_t* __restrict__ env_id, const double* __
                 n_b = S.cnt[1];
                 lb = S.lb;
             }
-            // ---- stages C + D: field polygon (lb -> survivors in lc; poses with nearby edges wait in the third list)
-            int n_c = n_b;
+            // ---- stages C + D: field polygon.  C: one pass over the edges per pose (crossing parity + mask of the edges
+            // whose line passes nearby); poses without nearby edges are decided, the others go to `pend` and emit one
+            // (pose, edge) PAIR per nearby edge.  D: the pairs, one per lane -- dense warps and one short uniform body
+            // instead of a divergent per-pose loop over 1..8 edges (it was 17 % of the kernel's instructions).
+            int n_c = n_b, n_d = 0;
             const unsigned short* lc = lb;
+            const unsigned short* pend = nullptr;
             if (rflags & HL_CHECK_BOUNDARY) {
-                unsigned short* pend = (lb == S.la) ? S.lb : S.la;
+                unsigned short* pendw = (lb == S.la) ? S.lb : S.la;
 #pragma unroll 1
                 for (int k = warp * 32; k < n_b; k += K1_THREADS) {
                     const int idx = k + lane;
                     const bool v = idx < n_b;
                     const int q = v ? lb[idx] : 0;
                     bool keep = false, need2 = false;
+                    unsigned nm = 0;
                     if (v) {
-                        unsigned nm; bool inside;
+                        bool inside;
                         k1_field1(E, R, k1_pose(S, q), rho_eps, nm, inside);
                         if (nm == 0) {                            // every edge clear: the parity of the centre decides
                             if (inside) keep = true; else S.st[q] |= K1S_HIT;
                         } else {
                             need2 = true;
-                            S.nearm[q] = nm;
-                            S.st[q] = (unsigned char)((S.st[q] & ~K1S_INSIDE) | (inside ? K1S_INSIDE : 0));
+                            S.st[q] = (unsigned char)((S.st[q] & ~(K1S_INSIDE | K1S_NOTCLEAR | K1S_CUT)) | (inside ? K1S_INSIDE : 0));
                         }
                     }
                     cta_append(S.lc, &S.cnt[2], keep, q, lane);
-                    cta_append(pend, &S.cnt[3], need2, q, lane);
+                    cta_append(pendw, &S.cnt[3], need2, q, lane);
+                    // pairs: warp prefix sum of the edge counts, one shared atomic per warp
+                    const int c = __popc(nm);
+                    int incl = c;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+                    const int total = __shfl_sync(0xffffffffu, incl, 31);
+                    if (total) {
+                        int base = 0;
+                        if (lane == 0) base = atomicAdd(&S.cnt[4], total);
+                        base = __shfl_sync(0xffffffffu, base, 0) + incl - c;
+                        if (c) {
+                            if (base + c > K1_PAIR_CAP) {             // list full: this pose goes to the float64 predicate
+                                S.st[q] |= K1S_NOTCLEAR;
+                            } else {
+                                unsigned m = nm;
+#pragma unroll 1
+                                while (m) {
+                                    const int i = __ffs(m) - 1;
+                                    m &= m - 1;
+                                    S.pairs[base++] = (unsigned short)(q | (i << K1_QBITS));
+                                }
+                            }
+                        }
+                    }
                 }
                 __syncthreads();
-                const int n_d = S.cnt[3];
+                n_d = S.cnt[3];
+                const int n_p = min(S.cnt[4], K1_PAIR_CAP);
+                unsigned* st32 = reinterpret_cast<unsigned*>(S.st);
 #pragma unroll 1
-                for (int k = warp * 32; k < n_d; k += K1_THREADS) {
+                for (int k = warp * 32; k < n_p; k += K1_THREADS) {
                     const int idx = k + lane;
-                    const bool v = idx < n_d;
-                    const int q = v ? pend[idx] : 0;
-                    bool keep = false;
-                    if (v) {
-                        const unsigned char st = S.st[q];
-                        const int r = k1_field2(E, R, k1_pose(S, q), S.nearm[q], (st & K1S_INSIDE) != 0);
-                        if (r == HL_HIT) S.st[q] = st | K1S_HIT;
-                        else { keep = true; if (r == HL_AMBIG) S.amb[q] |= HL_CHECK_BOUNDARY; }
+                    if (idx < n_p) {
+                        const unsigned e = S.pairs[idx];
+                        const int q = e & ((1u << K1_QBITS) - 1u), i = e >> K1_QBITS;
+                        const int r = k1_field_pair(E, R, k1_pose(S, q), i);
+                        if (r) atomicOr(st32 + (q >> 2), (unsigned)(r == 2 ? (K1S_CUT | K1S_NOTCLEAR) : K1S_NOTCLEAR) << (8 * (q & 3)));
                     }
-                    cta_append(S.lc, &S.cnt[2], keep, q, lane);
                 }
                 __syncthreads();
                 n_c = S.cnt[2];
                 lc = S.lc;
+                pend = pendw;
             }
-            // ---- stage E: lane corners of the body survivors that need them
-            if (do_lane) {
+            // ---- stage E: verdict of the pending poses (field), then the lane corners of the body survivors that need them
+            {
+                const int n_e = n_c + n_d;
 #pragma unroll 1
-                for (int k = warp * 32; k < n_c; k += K1_THREADS) {
+                for (int k = warp * 32; k < n_e; k += K1_THREADS) {
                     const int idx = k + lane;
-                    if (idx < n_c) {
-                        const int q = lc[idx];
-                        if (S.st[q] & K1S_CORNERS) {
+                    if (idx < n_e) {
+                        const int q = idx < n_c ? lc[idx] : pend[idx - n_c];
+                        unsigned char st = S.st[q];
+                        if (idx >= n_c) {                         // field verdict: cut -> HIT; all clear -> parity; else band
+                            if (st & K1S_CUT) st |= K1S_HIT;
+                            else if (!(st & K1S_NOTCLEAR)) { if (!(st & K1S_INSIDE)) st |= K1S_HIT; }
+                            else S.amb[q] |= HL_CHECK_BOUNDARY;
+                            S.st[q] = st;
+                        }
+                        if (do_lane && !(st & K1S_HIT) && (st & K1S_CORNERS)) {
                             const int r = k1_lane_corners(E, R, k1_pose(S, q));
                             if (r == HL_HIT) S.st[q] |= K1S_HIT;
                             else if (r == HL_AMBIG) S.amb[q] |= HL_CHECK_LANE;
@@ -620,15 +710,24 @@ k_collision(EnvBatchDev eb, const int32_t* __restrict__ env_id, const double* __
                 }
             }
             __syncthreads();                               // every list and counter of this rectangle has been consumed
-            if (tid < 4) S.cnt[tid] = 0;
+            if (tid < 8) S.cnt[tid] = 0;
             // ---- float64 resolution of this rectangle; then "infeasible" becomes K1S_DONE | K1S_HIT
 #pragma unroll 1
             for (int j = 0; j < K1_PER_THREAD; ++j) {
                 const int q = j * K1_THREADS + tid;
                 unsigned char st = S.st[q];
                 const unsigned amb = (rect == 0 && (st & K1S_FAR)) ? rflags : (unsigned)S.amb[q];
-                const bool need = !(st & (K1S_HIT | K1S_DONE)) && amb != 0;
-                if (__any_sync(0xffffffffu, need)) {        // rare: keep the call (and its spills) off the common path
+                bool need = !(st & (K1S_HIT | K1S_DONE)) && amb != 0;
+                if (need) {                                  // queue it; resolved after the CTA's last tile
+                    const int slot = atomicAdd(&S.dq_cnt, 1);
+                    if (slot < K1_DEFER_CAP) {
+                        K1Defer d;
+                        d.i = base + q; d.env = e0; d.amb = amb; d.rect = rect; d.pad = 0;
+                        S.dq[slot] = d;
+                        need = false;
+                    }
+                }
+                if (__any_sync(0xffffffffu, need)) {        // queue full (rare): resolve in place
                     const long long i = base + q;
                     double x = 0.0, y = 0.0, yaw = 0.0;
                     if (need) { x = poses[3 * i]; y = poses[3 * i + 1]; yaw = poses[3 * i + 2]; }
@@ -656,6 +755,26 @@ k_collision(EnvBatchDev eb, const int32_t* __restrict__ env_id, const double* __
             }
         }
         __syncthreads();                                   // S.st / lists are rewritten by the next tile
+    }
+    // ---- the queued float64 resolutions: one entry per warp at a time, every warp busy
+    const int nq = min(S.dq_cnt, K1_DEFER_CAP);
+#pragma unroll 1
+    for (int e = warp; e < nq; e += K1_WARPS) {
+        const K1Defer d = S.dq[e];
+        const EnvDesc& D = eb.desc[d.env];
+        const double* ext64 = d.rect == 0 ? D.body_ext : eb.aux64 + 4 * (size_t)(D.aux_off + d.rect - 1);
+        Pose64 p;
+        p.x = poses[3 * d.i]; p.y = poses[3 * d.i + 1];
+        const double yaw = poses[3 * d.i + 2];
+        p.c = cos(yaw); p.s = sin(yaw);
+        double e4[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) e4[k] = ext64[k];
+        const bool res = warp_exact_part_check(p, e4, eb, D, d.amb, lane);
+        if (lane == 0) {
+            if (res) out[d.i] = 1;
+            if (n_exact) atomicAdd(n_exact, 1ULL);
+        }
     }
 }
 
