@@ -95,6 +95,7 @@ struct __align__(16) K1Cta {
                                           // ordered so that Ey >= 0, (nx, ny, c, By), (tmin, tmax, -, -) -- see k1_field1
     unsigned long long bar_env, bar_raw;  // mbarriers of the two kinds of bulk copy
     int cnt[8];                           // list counters: la, lb, lc, pending, pairs
+    float aabb[8];                        // field polygon: xmin, xmax, ymin, ymax; all obstacles: xmin, xmax, ymin, ymax
     K1Defer dq[K1_DEFER_CAP];             // poses waiting for the float64 predicates (drained when the CTA has no tile left)
     int dq_cnt;
 };
@@ -131,11 +132,19 @@ __device__ __noinline__ void warp_resolve(bool need, double x, double y, double 
     }
 }
 
+// shared-memory fetch-and-add as ONE instruction (ATOMS.ADD): `atomicAdd` makes the compiler wrap its own warp
+// aggregation (vote / popc / shuffle, ~15 instructions) around an atomic that one elected lane already issues alone
+__device__ __forceinline__ int atoms_add(int* p, int v) {
+    int old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
+    return old;
+}
+
 // appends q to the CTA list for every lane with `pred`: one shared atomic per warp
 __device__ __forceinline__ void cta_append(unsigned short* list, int* cnt, bool pred, int q, int lane) {
     const unsigned m = __ballot_sync(0xffffffffu, pred);
     int base = 0;
-    if (lane == 0 && m) base = atomicAdd(cnt, __popc(m));
+    if (lane == 0 && m) base = atoms_add(cnt, __popc(m));
     base = __shfl_sync(0xffffffffu, base, 0);
     if (pred) list[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)q;
 }
@@ -511,6 +520,29 @@ k_collision(EnvBatchDev eb, const int32_t* __restrict__ env_id, const double* __
                     S.fld[i][1] = make_float4(e[4], e[5], e[6], up ? e[7] : e[1]);
                     S.fld[i][2] = make_float4(fminf(e[8], e[9]), fmaxf(e[8], e[9]), 0.f, 0.f);
                 }
+                if (warp == 2) {                       // bounding boxes of the field polygon and of all obstacles
+                    float lo_x = INFINITY, hi_x = -INFINITY, lo_y = INFINITY, hi_y = -INFINITY;
+                    for (int i = lane; i < D0.n_field; i += 32) {
+                        const float* e = S.env + n_o + HL_FIELD32_STRIDE * i;
+                        lo_x = fminf(lo_x, e[0]); hi_x = fmaxf(hi_x, e[0]); lo_y = fminf(lo_y, e[1]); hi_y = fmaxf(hi_y, e[1]);
+                    }
+                    float olo_x = INFINITY, ohi_x = -INFINITY, olo_y = INFINITY, ohi_y = -INFINITY;
+                    for (int i = lane; i < 4 * D0.n_obs; i += 32) {
+                        const float* v = S.env + HL_OBS32_STRIDE * (i >> 2) + 2 * (i & 3);
+                        olo_x = fminf(olo_x, v[0]); ohi_x = fmaxf(ohi_x, v[0]); olo_y = fminf(olo_y, v[1]); ohi_y = fmaxf(ohi_y, v[1]);
+                    }
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) {
+                        lo_x = fminf(lo_x, __shfl_xor_sync(0xffffffffu, lo_x, o)); hi_x = fmaxf(hi_x, __shfl_xor_sync(0xffffffffu, hi_x, o));
+                        lo_y = fminf(lo_y, __shfl_xor_sync(0xffffffffu, lo_y, o)); hi_y = fmaxf(hi_y, __shfl_xor_sync(0xffffffffu, hi_y, o));
+                        olo_x = fminf(olo_x, __shfl_xor_sync(0xffffffffu, olo_x, o)); ohi_x = fmaxf(ohi_x, __shfl_xor_sync(0xffffffffu, ohi_x, o));
+                        olo_y = fminf(olo_y, __shfl_xor_sync(0xffffffffu, olo_y, o)); ohi_y = fmaxf(ohi_y, __shfl_xor_sync(0xffffffffu, ohi_y, o));
+                    }
+                    if (lane == 0) {
+                        S.aabb[0] = lo_x; S.aabb[1] = hi_x; S.aabb[2] = lo_y; S.aabb[3] = hi_y;
+                        S.aabb[4] = olo_x; S.aabb[5] = ohi_x; S.aabb[6] = olo_y; S.aabb[7] = ohi_y;
+                    }
+                }
                 E.obs_a = S.env; E.field_a = S.env + n_o; E.seg_a = S.env + n_o + n_f;
                 E.n_obs = D0.n_obs; E.n_field = D0.n_field; E.n_seg = D0.n_seg; E.eps = D0.eps;
             }
@@ -572,8 +604,14 @@ k_collision(EnvBatchDev eb, const int32_t* __restrict__ env_id, const double* __
             const bool do_lane = rect == 0 && (flags & HL_CHECK_LANE) && E.n_seg > 0;
             const float rho = sqrtf(fmaf(R.hx, R.hx, R.hy * R.hy));
             const float rho_eps = rho + E.eps;
-            // ---- stage A: input list.  Body: every live pose, minus those the lane centre test rejects (cheapest
-            // test, decides every pose far from the guide).  Implement: live poses at even path indices.
+            // ---- stage A: input lists.  Two bounding-box culls on the rectangle centre come first: a centre outside the
+            // box of the field polygon is outside the polygon (HIT, 4 comparisons instead of lane + obstacle + field
+            // stages); a centre farther than the circumradius from the box of all obstacles cannot touch any of them and
+            // goes straight to the obstacle stage's OUTPUT list.  Body: then the lane centre test (decides every pose far
+            // from the guide).  Implement: live poses at even path indices.
+            const bool cull_f = (rflags & HL_CHECK_BOUNDARY) && E.n_field > 0, cull_o = (rflags & HL_CHECK_OBSTACLES) != 0;
+            const float fx0 = S.aabb[0] - E.eps, fx1 = S.aabb[1] + E.eps, fy0 = S.aabb[2] - E.eps, fy1 = S.aabb[3] + E.eps;
+            const float ox0 = S.aabb[4] - rho_eps, ox1 = S.aabb[5] + rho_eps, oy0 = S.aabb[6] - rho_eps, oy1 = S.aabb[7] + rho_eps;
 #pragma unroll 1
             for (int j = 0; j < K1_PER_THREAD; ++j) {
                 const int q = j * K1_THREADS + tid;
@@ -583,13 +621,24 @@ k_collision(EnvBatchDev eb, const int32_t* __restrict__ env_id, const double* __
                     const bool with_aux = !(st & (K1S_DONE | K1S_OFF)) && (pose_idx ? ((pose_idx[base + q] & 1) == 0) : true);
                     live = live && with_aux;
                     S.amb[q] = (with_aux && (st & K1S_FAR)) ? (unsigned char)rflags : (unsigned char)0;
-                } else if (live && do_lane) {
-                    const int r = k1_lane_centre(E, R, k1_pose(S, q), rho);
-                    if (r == 1) { st |= K1S_HIT; live = false; }
-                    else if (r == 2) st |= K1S_CORNERS;
+                }
+                bool skip_obs = false;
+                if (live) {
+                    const float4 P = k1_pose(S, q);
+                    const float Cx = fmaf(P.z, R.mx, fmaf(-P.w, R.my, P.x)), Cy = fmaf(P.w, R.mx, fmaf(P.z, R.my, P.y));
+                    if (cull_f && (Cx < fx0 || Cx > fx1 || Cy < fy0 || Cy > fy1)) { st |= K1S_HIT; live = false; }
+                    else {
+                        skip_obs = cull_o && (Cx < ox0 || Cx > ox1 || Cy < oy0 || Cy > oy1);
+                        if (do_lane) {
+                            const int r = k1_lane_centre(E, R, P, rho);
+                            if (r == 1) { st |= K1S_HIT; live = false; }
+                            else if (r == 2) st |= K1S_CORNERS;
+                        }
+                    }
                     S.st[q] = st;
                 }
-                cta_append(S.la, &S.cnt[0], live, q, lane);
+                cta_append(S.la, &S.cnt[0], live && !skip_obs, q, lane);
+                if (cull_o) cta_append(S.lb, &S.cnt[1], live && skip_obs, q, lane);
             }
             __syncthreads();
             const int n_a = S.cnt[0];
@@ -650,7 +699,7 @@ k_collision(EnvBatchDev eb, const int32_t* __restrict__ env_id, const double* __
                     const int total = __shfl_sync(0xffffffffu, incl, 31);
                     if (total) {
                         int base = 0;
-                        if (lane == 0) base = atomicAdd(&S.cnt[4], total);
+                        if (lane == 0) base = atoms_add(&S.cnt[4], total);
                         base = __shfl_sync(0xffffffffu, base, 0) + incl - c;
                         if (c) {
                             if (base + c > K1_PAIR_CAP) {             // list full: this pose goes to the float64 predicate
