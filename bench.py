@@ -466,9 +466,9 @@ def collision_microbench(args, dev, fp32_peak):
             "roofline": {"bound": "alu_fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp32_peak if fp32_peak else None,
                          "hbm_GBps": checks * 25 * 1e-9,
-                         # 31.4 B of DRAM traffic per pose (ncu --set full, 4 Mi poses, profiles/r2e_k1_ncu_full_summary.txt:
-                         # 102.8 MB read + 29.0 MB written) against 25 B algorithmic (24 B pose in + 1 B flag out)
-                         "traffic": int(31.4 * n)}}
+                         # 30.6 B of DRAM traffic per pose (ncu --set full, 4 Mi poses, profiles/r2s_k1_ncu_full_summary.txt:
+                         # 103.1 MB read + 25.4 MB written) against 25 B algorithmic (24 B pose in + 1 B flag out)
+                         "traffic": int(30.6 * n)}}
 
 
 def hbm_view(bytes_per_launch, ms_per_launch):
