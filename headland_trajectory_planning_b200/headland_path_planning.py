@@ -101,7 +101,7 @@ def search_y_type_parking_path(car_model, config_env, end_pose, backward_steer_d
     """headland_path_planning.py:382-451 -- same arguments and returns; one K5 + K1 + reduce launch."""
     if not config_env.check_path_feasibility(car_model, np.array([end_pose], dtype=np.float64)):
         print(" [Y-type Planner] The end pose is interfered with the environment!")
-        return ([], []) if debug else []
+        return [], []                      # a TUPLE whatever `debug` says, like the reference (:400-402)
     cands = y_park_candidates(max_steer_backward, max_steer_forward, max_backward_distance, max_forward_distance,
                               min_forward_distance, min_backward_distance, min_steer_backward, min_steer_forward)
     if len(cands) == 0:

@@ -700,7 +700,7 @@ def search_y_type_parking_path(car_model, config_env, end_pose, backward_steer_d
                                min_steer_backward=0.3, min_steer_forward=0.3, step_size=0.1, debug=False):
     """headland_path_planning.py:382-451: the first feasible candidate in loop order wins."""
     if not config_env.check_path_feasibility(car_model, np.array([end_pose])):
-        return ([], []) if debug else []
+        return [], []                      # :400-402: a tuple whatever `debug` says
     cands = y_park_candidates(backward_steer_dir, forward_steer_dir, max_steer_backward, max_steer_forward,
                               max_backward_distance, max_forward_distance, min_forward_distance,
                               min_backward_distance, min_steer_backward, min_steer_forward)
