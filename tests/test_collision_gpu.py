@@ -141,3 +141,40 @@ def test_staged_pipeline_equals_per_pose_filter(built_library, aux):
         # unaligned source: the same poses shifted by one row (24 bytes)
         un = ops.collision_check(envs, d_poses[1:], pose_idx=idx[1:].contiguous(), flags=flags)
         assert torch.equal(un, fast[1:]), f"flags={flags}: unaligned source differs"
+
+
+def test_float64_queue_overflow_and_culls(built_library):
+    """K1 queues the poses that need the float64 predicates (48 per CTA) and resolves them after the CTA's last tile;
+    when the queue is full they are resolved in place.  A block of 6000 consecutive undecidable poses (NaN position /
+    absurd heading) overflows the queue of every CTA that meets it; the booleans must still equal the per-pose filter on
+    global memory (second K1 path) and the oracle on a sample.  The bounding-box culls are exercised by poses far
+    outside the field polygon's box and far from every obstacle."""
+    import torch
+    from headland_trajectory_planning_b200 import ops
+    from headland_trajectory_planning_b200.env_batch import EnvBatch, make_record
+    rows = H.canonical_rows(l_std=0.3)
+    way = np.array([[0.0, 3.75], [-4.5, 5.0], [-4.06, 7.5], [-3.62, 10.0], [-1.5, 11.0]])
+    (o_env, o_car, o_h), (g_env, g_car, g_h) = H.make_pair(rows, aux=H.SPRAYER_AUX, waypoints=way, goal=np.array([-1.5, 11.0, 0.3]))
+    rec = make_record(g_env, g_car, g_h)
+    envs = EnvBatch([rec, rec])
+    rng = np.random.default_rng(11)
+    n = 300_000
+    poses = H.headland_poses(rng, n, rows)
+    poses[50_000:53_000, 0] = np.nan
+    poses[53_000:56_000, 2] = 3e7                   # |yaw| >= 1e6: the float32 heading reduction is not trusted
+    poses[100_000:110_000, 0] -= 40.0               # far outside the box of the field polygon
+    poses[120_000:130_000, 1] += 60.0
+    d_poses = torch.from_numpy(poses).cuda()
+    idx = torch.arange(n, dtype=torch.int32, device="cuda")
+    alt = (idx & 1).to(torch.int32)
+    for flags in (3, 7, 15):
+        fast = ops.collision_check(envs, d_poses, pose_idx=idx, flags=flags)
+        slow = ops.collision_check(envs, d_poses, env_id=alt, pose_idx=idx, flags=flags)
+        assert torch.equal(fast, slow), f"flags={flags}: {(fast != slow).sum().item()} booleans differ"
+        got = fast.cpu().numpy().astype(bool)
+        assert got[50_000:53_000].all()             # NaN position: infeasible
+        assert got[100_000:110_000].all() and got[120_000:130_000].all()
+    sel = np.concatenate([np.arange(0, 3000), np.arange(53_000, 53_200), np.arange(100_000, 100_200)])
+    want = o_env.pose_flags(o_car, poses[sel])
+    got = ops.collision_check(envs, d_poses[torch.from_numpy(sel).cuda()], flags=ops.CHECK_OBSTACLES | ops.CHECK_BOUNDARY).cpu().numpy().astype(bool)
+    assert (want == got).all()
