@@ -258,285 +258,6 @@ __device__ __noinline__ void team_state_costs(AqSmem& S, const EnvBatchDev& eb, 
     }
 }
 
-// The 46 candidate rows of generate_path (reeds_shepp.py:565-582) in two warp-wide passes built around UNIFORM calls of
-// the float64 transcendentals.  rs_solve's switch makes the lanes of a pass run every formula one after the other
-// (~3700 dependent instructions per shot); here a pass is a fixed sequence of slots -- polar, atan2 / asin, the two
-// M() folds; in pass B also acos, sincos, tan -- that all lanes enter together with their own arguments, and the
-// solver-specific arithmetic between the slots is a few selects.  Pass A: LSL, LSR, LRL, LRSL, LRSR rows (32 lanes, all
-// start with R(x -+ sin phi, y - 1 +- cos phi)).  Pass B: LRLRn / LRLRp on lanes 0-7, LRSLR on 8-11, SLS on 12-13; lanes
-// 16-23 and 28-29 are HELPERS of lanes 0-7 / 12-13: they repeat the cheap prefix and take the second transcendental of
-// the same kind (sincos(delta) next to sincos(u); tan(phi/2) next to tan(phi)).  Every value is produced by the same
-// float64 operations in the same order as rs_solve / rs_candidate (cos(v) = cos(u) for v = +-u: cos is even bit for bit).
-static __constant__ signed char c_aq_pass_a[32] = {2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17,
-                                                   26, 27, 28, 29, 34, 35, 36, 37, 30, 31, 32, 33, 38, 39, 40, 41};
-static __constant__ signed char c_aq_pass_b[16] = {18, 19, 20, 21, 22, 23, 24, 25, 42, 43, 44, 45, 0, 1, -1, -1};
-
-__device__ __forceinline__ void aq_store_candidate(AqShot& T, int c, const RsRow& row, bool ok, double t, double u, double v) {
-    double l[HL_RS_MAX_SEGS] = {0.0, 0.0, 0.0, 0.0, 0.0};
-    if (ok) {
-        const double H = xmul(-0.5, HL_PI);
-        switch (row.pattern) {
-        case RP_TUV:   l[0] = t; l[1] = u; l[2] = v; break;
-        case RP_VUT:   l[0] = v; l[1] = u; l[2] = t; break;
-        case RP_TUnUV: l[0] = t; l[1] = u; l[2] = -u; l[3] = v; break;
-        case RP_TUUV:  l[0] = t; l[1] = u; l[2] = u; l[3] = v; break;
-        case RP_THUV:  l[0] = t; l[1] = H; l[2] = u; l[3] = v; break;
-        case RP_VUHT:  l[0] = v; l[1] = u; l[2] = H; l[3] = t; break;
-        default:       l[0] = t; l[1] = H; l[2] = u; l[3] = H; l[4] = v; break;
-        }
-        if (row.neg_x)
-#pragma unroll
-            for (int k = 0; k < HL_RS_MAX_SEGS; ++k) l[k] = (k < row.nseg) ? -l[k] : l[k];
-    }
-    T.rs_valid[c] = ok ? 1 : 0;
-#pragma unroll
-    for (int k = 0; k < HL_RS_MAX_SEGS; ++k) T.rs_lens[c][k] = l[k];
-}
-
-__device__ __noinline__ void aq_rs_candidates(AqShot& T, int lane) {
-    const double PI = HL_PI;
-    const RsProblem Pb = T.rs_prob;
-    {   // ------------------------------------------------ pass A
-        const int c = c_aq_pass_a[lane];
-        const RsRow row = c_rs_rows[c];
-        double x = row.backwards ? Pb.xb : Pb.x, y = row.backwards ? Pb.yb : Pb.y;
-        if (row.neg_x) x = -x;
-        if (row.neg_y) y = -y;
-        const bool negphi = row.neg_x != row.neg_y;
-        const double phi = negphi ? -Pb.phi : Pb.phi, sphi = negphi ? -Pb.sp : Pb.sp, cphi = Pb.cp;
-        const int solver = row.solver;
-        const bool plus = solver == RS_LSR || solver == RS_LRSR;
-        const double xi = plus ? xadd(x, sphi) : xsub(x, sphi);
-        const double eta = plus ? xsub(xsub(y, 1.0), cphi) : xadd(xsub(y, 1.0), cphi);
-        const double X = (solver == RS_LRSR) ? -eta : xi, Y = (solver == RS_LRSR) ? xi : eta;
-        const double r = hypot_cr(X, Y);                     // slot: R(X, Y)
-        const double th = m_atan2(Y, X);
-        bool ok = true;
-        double u = r, r2 = 0.0;
-        if (solver == RS_LSR) { const double u1 = xmul(r, r); ok = u1 >= 4.0; u = sqrt(xsub(u1, 4.0)); }
-        else if (solver == RS_LRSL) { ok = r >= 2.0; r2 = sqrt(xsub(xmul(r, r), 4.0)); u = xsub(2.0, r2); }
-        else if (solver == RS_LRSR) { ok = r >= 2.0; u = xsub(2.0, r); }
-        else if (solver == RS_LRL) ok = r <= 4.0;
-        double aux = 0.0;
-        if (solver == RS_LSR || solver == RS_LRSL)           // slot: atan2(2, u) / atan2(r, -2)
-            aux = m_atan2(solver == RS_LSR ? 2.0 : r2, solver == RS_LSR ? u : -2.0);
-        if (solver == RS_LRL) u = xmul(-2.0, m_asin(xmul(0.25, r)));       // slot: asin
-        const bool tmod = solver == RS_LSR || solver == RS_LRL || solver == RS_LRSL;
-        const double targ = (solver == RS_LRL) ? xadd(xadd(th, xmul(0.5, u)), PI) : xadd(th, aux);
-        const double tm = rs_mod2pi(tmod ? targ : 0.0);      // slot: M(t)
-        const double t = tmod ? tm : th;
-        double varg;
-        if (solver == RS_LSL) varg = xsub(phi, t);
-        else if (solver == RS_LSR) varg = xsub(t, phi);
-        else if (solver == RS_LRL) varg = xadd(xsub(phi, t), u);
-        else if (solver == RS_LRSL) varg = xsub(xsub(phi, xmul(0.5, PI)), t);
-        else varg = xsub(xadd(t, xmul(0.5, PI)), phi);
-        const double v = rs_mod2pi(varg);                    // slot: M(v)
-        if (solver == RS_LSL || solver == RS_LSR) ok = ok && t >= 0.0 && v >= 0.0;
-        else if (solver == RS_LRL) ok = ok && t >= 0.0 && u <= 0.0;
-        else ok = ok && t >= 0.0 && u <= 0.0 && v <= 0.0;
-        aq_store_candidate(T, c, row, ok, t, u, v);
-    }
-    __syncwarp();
-    {   // ------------------------------------------------ pass B
-        const bool helper = lane >= 16;
-        const int c = c_aq_pass_b[lane & 15];
-        const bool have = c >= 0;
-        const RsRow row = c_rs_rows[have ? c : 0];
-        double x = row.backwards ? Pb.xb : Pb.x, y = row.backwards ? Pb.yb : Pb.y;
-        if (row.neg_x) x = -x;
-        if (row.neg_y) y = -y;
-        const bool negphi = row.neg_x != row.neg_y;
-        const double phi = negphi ? -Pb.phi : Pb.phi, sphi = negphi ? -Pb.sp : Pb.sp, cphi = Pb.cp;
-        const int solver = have ? (int)row.solver : -1;
-        const bool lrlr = solver == RS_LRLRN || solver == RS_LRLRP, isn = solver == RS_LRLRN;
-        const bool sls = solver == RS_SLS, lrslr = solver == RS_LRSLR;
-        const double xi = xadd(x, sphi);
-        const double eta = xsub(xsub(y, 1.0), cphi);
-        const double r = hypot_cr(xi, eta);                  // slot: rho of R(xi, eta) (LRSLR; its theta is not used)
-        bool ok = have;
-        double rho = 0.5;
-        if (isn) { rho = xmul(0.25, xadd(2.0, sqrt(xadd(xmul(xi, xi), xmul(eta, eta))))); ok = rho <= 1.0; }
-        else if (lrlr) { rho = xdiv(xsub(xsub(20.0, xmul(xi, xi)), xmul(eta, eta)), 16.0); ok = 0.0 <= rho && rho <= 1.0; }
-        const double ac = m_acos(lrlr ? rho : 0.5);          // slot: acos
-        const double uu = isn ? ac : -ac, vv = isn ? -uu : uu;
-        if (lrlr && !isn) ok = ok && uu >= xmul(-0.5, PI);
-        const double m1 = rs_mod2pi(sls ? phi : xsub(uu, vv));   // slot: M(phi) (SLS) / delta = M(u - v)
-        double sn, cs;
-        m_sincos(lrlr ? (helper ? m1 : uu) : 0.0, &sn, &cs);    // slot: sincos(u) | sincos(delta)
-        const double osn = __shfl_xor_sync(FULL, sn, 16), ocs = __shfl_xor_sync(FULL, cs, 16);
-        const double s_uu = helper ? osn : sn, c_uu = helper ? ocs : cs, s_de = helper ? sn : osn, c_de = helper ? cs : ocs;
-        const double tn = m_tan(sls ? (helper ? xdiv(m1, 2.0) : m1) : 0.0);   // slot: tan(phi) | tan(phi / 2)
-        const double otn = __shfl_xor_sync(FULL, tn, 16);
-        const double tan_phi = helper ? otn : tn, tan_half = helper ? tn : otn;
-        double a_y = 0.0, a_x = 1.0, u = 0.0;
-        if (lrlr) {
-            const double A = xsub(s_uu, s_de);
-            const double B = xsub(xsub(c_uu, c_de), 1.0);
-            a_y = xsub(xmul(eta, A), xmul(xi, B)); a_x = xadd(xmul(xi, A), xmul(eta, B));
-            u = uu;
-        } else if (lrslr) {
-            ok = ok && r >= 2.0;
-            u = xsub(4.0, sqrt(xsub(xmul(r, r), 4.0)));
-            ok = ok && u <= 0.0;
-            a_y = xsub(xmul(xsub(4.0, u), xi), xmul(2.0, eta)); a_x = xadd(xmul(-2.0, xi), xmul(xsub(u, 4.0), eta));
-        }
-        const double at = m_atan2(a_y, a_x);                 // slot: atan2
-        double targ = at;
-        if (lrlr) {
-            const double t2 = xadd(xmul(2.0, xsub(xsub(c_de, c_uu), c_uu)), 3.0);     // cos(v) = cos(u)
-            if (t2 < 0) targ = xadd(at, PI);
-        }
-        double t = rs_mod2pi(targ);                          // slot: M(t)
-        const double varg = lrlr ? xsub(xadd(xsub(t, uu), vv), phi) : xsub(t, phi);
-        double v = rs_mod2pi(varg);                          // slot: M(v)
-        if (lrlr) ok = ok && t >= 0.0 && (isn ? v <= 0.0 : v >= 0.0);
-        else if (lrslr) ok = ok && t >= 0.0 && v >= 0.0;
-        else if (sls) {
-            ok = (y > 0.0 || y < 0.0) && 0.0 < m1 && m1 < xmul(PI, 0.99);
-            const double xd = xadd(xdiv(-y, tan_phi), x);
-            t = xsub(xd, tan_half);
-            u = m1;
-            const double dx = xsub(x, xd);
-            const double rt = sqrt(xadd(xmul(dx, dx), xmul(y, y)));
-            v = (y > 0.0) ? xsub(rt, tan_half) : xsub(-rt, tan_half);
-        }
-        if (have && !helper) aq_store_candidate(T, c, row, ok, t, u, v);
-    }
-    __syncwarp();
-}
-
-// `while px[-1] == 0.0: pop` of generate_local_course (reeds_shepp.py:520-528) for a word whose end point has a local
-// x of exactly 0: the end point goes, then loop samples as long as their x is exactly 0.0.  Rare; one lane.
-__device__ __noinline__ void aq_plan_trailing_pops(RsPlan& P, double maxc) {
-    int npts = P.npts - 1;
-#pragma unroll 1
-    while (npts > 1) {
-        const int j = npts - 1;
-        int si = P.nseg - 1;
-#pragma unroll 1
-        while (si > 0 && j < P.seg[si].first) --si;
-        const RsSegPlan& S = P.seg[si];
-        double pd = S.pd0;
-#pragma unroll 1
-        for (int k = 0; k < j - S.first; ++k) pd = xadd(pd, S.d);
-        double px, py, pyaw;
-        rs_interp(pd, S.letter, maxc, S.ox, S.oy, S.oyaw, px, py, pyaw);
-        if (px != 0.0) break;
-        npts -= 1;
-    }
-    P.npts = npts;
-}
-
-// Plans of up to AQ_MAX_PLANS words at once, one warp: rs_make_plan + rs_plan_world32 re-arranged so that the
-// expensive part -- the sine / cosine of every segment's length and start heading, 4 float64 transcendentals per
-// segment in rs_interp -- runs on one lane per (word, segment) as TWO sincos calls in lock-step instead of 20 serial
-// calls per word.  Lane 5w + i holds segment i of word k0 + w.  Bit-identical to rs_make_plan in everything that feeds
-// a decision (sample counts, segment origins and headings: same operations in the same order; sincos == sin, cos and
-// sin odd / cos even bit for bit, tools/sincos_check.cu).  The float32 view (fox, foy, fc0, fs0) takes the cosine /
-// sine of the world heading from the angle-addition formula in float64 instead of another sincos: it only feeds the
-// conservative float32 filter.
-__device__ __noinline__ void aq_make_plans(AqShot& T, int k0, int nw, RsPlan* dst, const double* q0, double cq, double sq,
-                                           const double* origin, double maxc, double step, int lane) {
-    const int w = lane / 5, i = lane - 5 * w;
-    const bool wact = w < nw;
-    const int c = wact ? T.rs_acc[k0 + w] : 0;
-    const RsRow row = c_rs_rows[c];
-    const int nseg = row.nseg;
-    const bool act = wact && i < nseg;
-    const double* lens = T.rs_lens[c];
-    if (wact && i == 0) {
-        // sample bookkeeping of the whole word (generate_local_course's pd / ll / ind chain): sequential, cheap
-        RsPlan& P = dst[w];
-        P.nseg = nseg;
-        P.dir0 = (lens[0] > 0.0) ? 1 : -1;
-        double ll = 0.0;
-        int ind = 1;
-#pragma unroll 1
-        for (int j = 0; j < nseg; ++j) {
-            const double l = lens[j];
-            const double d = (l > 0.0) ? step : -step;
-            RsSegPlan& S = P.seg[j];
-            S.l = l; S.d = d; S.letter = rs_letter(row.letters, j);
-            ind -= 1;
-            double pd = (j >= 1 && xmul(lens[j - 1], lens[j]) > 0.0) ? xsub(-d, ll) : xsub(d, ll);
-            S.pd0 = pd;
-            S.first = ind + 1;
-            int cnt = 0;
-            const double al = fabs(l);
-            if (fabs(pd) <= al) {
-                const double a = (d > 0.0) ? pd : -pd;
-                const double r = (al - a) / step;
-                const double kf = floor(r);
-                if (r - kf > 1e-7 && kf + 1.0 - r > 1e-7 && r < 1e7) {
-                    cnt = (int)kf + 1;
-                    pd = xadd(pd, xmul((double)cnt, d));
-                } else {
-#pragma unroll 1
-                    while (fabs(pd) <= al) { ++cnt; pd = xadd(pd, d); }
-                }
-            }
-            S.count = cnt;
-            ind += cnt;
-            ll = xsub(xsub(l, pd), d);
-            ind += 1;
-        }
-        P.npts = ind + 1;
-    }
-    // heading at the start of segment i: oyaw accumulates +-l over the arcs before it, in the reference's order
-    double oyaw = 0.0;
-#pragma unroll 1
-    for (int j = 0; j < HL_RS_MAX_SEGS - 1; ++j) {
-        if (act && j < i) {
-            const int lt = rs_letter(row.letters, j);
-            if (lt == RS_L) oyaw = xadd(oyaw, lens[j]);
-            else if (lt == RS_R) oyaw = xsub(oyaw, lens[j]);
-        }
-    }
-    const double l = act ? lens[i] : 0.0;
-    const int letter = rs_letter(row.letters, i);
-    double sl, cl, so, co;
-    m_sincos(l, &sl, &cl);
-    m_sincos(oyaw, &so, &co);
-    // displacement of segment i in the local frame (rs_interp with cos(-oyaw) = co, sin(-oyaw) = -so)
-    double gdx, gdy;
-    if (letter == RS_S) {
-        const double lm = xdiv(l, maxc);
-        gdx = xmul(lm, co); gdy = xmul(lm, so);
-    } else {
-        const double ldx = xdiv(sl, maxc);
-        const double ldy = xdiv(xsub(1.0, cl), letter == RS_L ? maxc : -maxc);
-        gdx = xadd(xmul(co, ldx), xmul(-so, ldy));
-        gdy = xadd(xmul(so, ldx), xmul(co, ldy));
-    }
-    // origin of segment i: ((0 + g_0) + g_1) + ... in order
-    double ox = 0.0, oy = 0.0;
-#pragma unroll
-    for (int j = 0; j < HL_RS_MAX_SEGS - 1; ++j) {
-        const int src = min(5 * w + j, 31);
-        const double gx = __shfl_sync(FULL, gdx, src), gy = __shfl_sync(FULL, gdy, src);
-        if (j < i) { ox = xadd(ox, gx); oy = xadd(oy, gy); }
-    }
-    const double ex = xadd(ox, gdx);                             // end point of segment i (x only: the pop test)
-    const double end_x = __shfl_sync(FULL, ex, min(5 * w + nseg - 1, 31));
-    if (act) {
-        RsSegPlan& S = dst[w].seg[i];
-        S.ox = ox; S.oy = oy; S.oyaw = oyaw;
-        const double wx = xadd(xadd(xmul(cq, ox), xmul(sq, oy)), q0[0]);
-        const double wy = xadd(xadd(xmul(-sq, ox), xmul(cq, oy)), q0[1]);
-        S.fox = (float)(wx - origin[0]);
-        S.foy = (float)(wy - origin[1]);
-        S.fc0 = (float)(co * cq + so * sq);                      // cos(oyaw + yaw0), sin(oyaw + yaw0): cq = cos yaw0, sq = -sin yaw0
-        S.fs0 = (float)(so * cq - co * sq);
-    }
-    __syncwarp();
-    if (wact && i == 0) {
-        if (end_x == 0.0) aq_plan_trailing_pops(dst[w], maxc);
-        T.rs_npts[k0 + w] = dst[w].npts;
-    }
-    __syncwarp();
-}
-
 // Footprint check of ONE planned Reeds-Shepp word by a whole warp: 32 poses per pass, lane-strided, float32 filter first
 // and the float64 predicate only for the poses inside the band when no other pose of the pass decided the word.
 // Returns true when the word collides.
@@ -830,7 +551,7 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                     }
                     __syncwarp();
                 }
-                aq_rs_candidates(T, lane);
+                rs_candidates_warp(T.rs_prob, T.rs_valid, T.rs_lens, lane);
                 STICK(PH_RS_CAND);
                 if (lane < RS_N_GROUPS) rs_select_group(lane, T.rs_valid, T.rs_lens, T.rs_accept, T.rs_Lc);
                 __syncwarp();
@@ -871,7 +592,7 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
 #pragma unroll 1
                 for (int k0 = 0; k0 < m && first_free < 0; k0 += AQ_MAX_PLANS) {
                     const int nw = (m - k0) < AQ_MAX_PLANS ? (m - k0) : AQ_MAX_PLANS;
-                    aq_make_plans(T, k0, nw, T.plans, q0, cq, sq, D.origin, P.maxc, stepn, lane);
+                    rs_make_plans_warp(T.rs_acc, T.rs_lens, T.rs_npts, k0, nw, T.plans, q0, cq, sq, D.origin, P.maxc, stepn, lane);
                     STICK(PH_RS_PLAN);
                     unsigned dead = 0;
 #if AQ_COARSE
@@ -930,14 +651,14 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                         const int k = T.rs_order[r];
                         if (k < first_free) { tally += (unsigned long long)T.rs_npts[k]; continue; }
                         if (k == first_free) { tally += (unsigned long long)T.rs_npts[k]; winner = k; break; }
-                        aq_make_plans(T, k, 1, &T.plan_tmp, q0, cq, sq, D.origin, P.maxc, stepn, lane);
+                        rs_make_plans_warp(T.rs_acc, T.rs_lens, T.rs_npts, k, 1, &T.plan_tmp, q0, cq, sq, D.origin, P.maxc, stepn, lane);
                         const RsPlan& plan = T.plan_tmp;
                         tally += (unsigned long long)plan.npts;
                         const bool hit = aq_word_collides(Ers, eb, D, plan, q0, cq, sq, P.maxc, inv_maxc, FLAGS, T, lane);
                         if (!hit && xdiv(T.rs_L[k], P.maxc) < P.min_len_goal) winner = k;
                     }
                     __syncwarp();
-                    aq_make_plans(T, winner, 1, &T.plan_tmp, q0, cq, sq, D.origin, P.maxc, stepn, lane);   // the result path's plan
+                    rs_make_plans_warp(T.rs_acc, T.rs_lens, T.rs_npts, winner, 1, &T.plan_tmp, q0, cq, sq, D.origin, P.maxc, stepn, lane);   // the result path's plan
                     if (lane == 0) {
                         T.s_ref += tally;
                         T.rs_pick = AQ_MAX_PLANS;                // = plan_tmp (finalize_spec)

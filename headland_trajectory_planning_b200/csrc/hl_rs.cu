@@ -15,7 +15,7 @@
 #include "hl_rs.cuh"
 
 #define RS_WARPS 4
-#define RS_PLANS 8              // sampling plans built lane-parallel per round
+#define RS_PLANS 6              // sampling plans built per round: one lane per (word, segment), rs_make_plans_warp
 
 struct RsWarpSmem {
     double lens[HL_RS_CANDIDATES][HL_RS_MAX_SEGS];
@@ -44,20 +44,32 @@ k_rs_all_paths(EnvBatchDev eb, int have_env, const int32_t* __restrict__ env_id,
     for (long long i = (long long)blockIdx.x * RS_WARPS + wid; i < n; i += n_warps) {
         double q0[3] = {sg[6 * i], sg[6 * i + 1], sg[6 * i + 2]};
         double q1[3] = {sg[6 * i + 3], sg[6 * i + 4], sg[6 * i + 5]};
-        if (lane == 0) W.prob = rs_normalise(q0, q1, maxc);
-        __syncwarp();
-        // ---- the 46 word solvers (two passes with disjoint solver sets)
-        HL_LOOP
-        for (int pass = 0; pass < 2; ++pass) {
-            const int c = c_rs_pass_cand[pass][lane];
-            if (c >= 0) {
-                double l[HL_RS_MAX_SEGS] = {0, 0, 0, 0, 0};
-                bool ok = rs_candidate(c, W.prob, l);
-                W.valid[c] = ok ? 1 : 0;
-                for (int k = 0; k < HL_RS_MAX_SEGS; ++k) W.lens[c][k] = l[k];
+        double cq, sq;
+        {
+            // generate_path's normalisation (rs_normalise): the two sine / cosine pairs are one sincos each on two lanes
+            // (sincos == sin, cos and sin odd / cos even bit for bit, tools/sincos_check.cu); the start heading's pair
+            // also gives cos(-yaw), sin(-yaw) of the local -> world rotation
+            const double phi = xsub(q1[2], q0[2]);
+            double sn, cs;
+            m_sincos(lane == 1 ? phi : q0[2], &sn, &cs);
+            const double c0 = __shfl_sync(0xffffffffu, cs, 0), s0 = __shfl_sync(0xffffffffu, sn, 0);
+            const double cp = __shfl_sync(0xffffffffu, cs, 1), sp = __shfl_sync(0xffffffffu, sn, 1);
+            cq = c0; sq = -s0;
+            if (lane == 0) {
+                RsProblem Pr;
+                const double dx = xsub(q1[0], q0[0]), dy = xsub(q1[1], q0[1]);
+                Pr.phi = phi;
+                Pr.x = xmul(xadd(xmul(c0, dx), xmul(s0, dy)), maxc);
+                Pr.y = xmul(xadd(xmul(-s0, dx), xmul(c0, dy)), maxc);
+                Pr.sp = sp; Pr.cp = cp;
+                Pr.xb = xadd(xmul(Pr.x, cp), xmul(Pr.y, sp));
+                Pr.yb = xsub(xmul(Pr.x, sp), xmul(Pr.y, cp));
+                W.prob = Pr;
             }
             __syncwarp();
         }
+        // ---- the 46 word solvers: two passes of lock-step transcendental slots (rs_candidates_warp)
+        rs_candidates_warp(W.prob, W.valid, W.lens, lane);
         // ---- set_path dedup per letter group (lane-parallel), compaction in evaluation order, costs, heapdict order
         if (lane < RS_N_GROUPS) rs_select_group(lane, W.valid, W.lens, W.accept, W.Lc);
         __syncwarp();
@@ -90,23 +102,20 @@ k_rs_all_paths(EnvBatchDev eb, int have_env, const int32_t* __restrict__ env_id,
         const int e = (have_env && env_id) ? env_id[i] : 0;
         const EnvDesc* Dp = have_env ? &eb.desc[e] : nullptr;
         EnvSmem E;
-        double cq = 1.0, sq = 0.0;
         if (have_env && mm > 0) {
             global_env(eb, *Dp, E);
             E.eps += 6e-5f;                               // float32 sampling error of rs_sample_world32
-            cq = m_cos(-q0[2]); sq = m_sin(-q0[2]);
         }
         // ---- words in rounds of RS_PLANS: plans lane-parallel, records out, then each word sampled and checked
         HL_LOOP
         for (int k0 = 0; k0 < mm; k0 += RS_PLANS) {
             const int nk = (mm - k0) < RS_PLANS ? (mm - k0) : RS_PLANS;
             __syncwarp();
+            rs_make_plans_warp(W.acc, W.lens, nullptr, k0, nk, W.plans, q0, cq, sq, have_env ? Dp->origin : nullptr, maxc, stepn, lane);
             if (lane < nk) {
                 const int k = k0 + lane;
                 const int c = W.acc[k];
-                RsPlan& plan = W.plans[lane];
-                rs_make_plan(c, W.lens[c], maxc, stepn, plan);
-                if (have_env) rs_plan_world32(plan, q0, cq, sq, Dp->origin);
+                const RsPlan& plan = W.plans[lane];
                 HlRsWord w;
                 w.cand = c; w.n_seg = plan.nseg; w.npts = plan.npts; w.collide = -1;
                 w.L = xdiv(W.L[k], maxc);
