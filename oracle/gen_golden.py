@@ -434,6 +434,77 @@ def gen_offset(n):
     print("offset_golden.npz:", len(res), "sweeps; distances", sorted(set(np.round([r["dist"] for r in res], 1)))[:30])
 
 
+def oge_cases():
+    """Orchards for the OBCA obstacle extraction (``OGE_OBCA.py``): slopes, jittered row ends, an explicit field contour;
+    turns on both sides over one and over several rows."""
+    from . import planner as OP
+    cases = []
+    for k, (n_rows, width, slope, l_std, headland, tree_w) in enumerate([
+            (8, 2.5, 10.0, 0.0, 6.0, 0.3), (8, 2.5, 0.0, 0.0, 7.0, 0.5), (10, 3.0, -8.0, 0.5, 6.5, 0.4),
+            (8, 2.2, 15.0, 1.0, 5.5, 0.3), (12, 2.8, 4.0, 0.2, 8.0, 0.5), (8, 2.5, 10.0, 0.3, 6.0, 0.3)]):
+        np.random.seed(100 + k)
+        rows = OP.create_tree_rows(n_rows, width, 20, slope_angle=math.radians(slope), l_std=l_std)
+        contour = []
+        if k == 5:                      # explicit field contour: a wavy 14-gon around the rows
+            lo, hi = rows[:, :, 1].min() - 3.0, rows[:, :, 1].max() + 3.0
+            ys = np.linspace(lo, hi, 7)
+            near = np.stack([rows[:, 0, 0].min() - 6.0 + 0.4 * np.sin(ys), ys], axis=1)
+            far = np.stack([rows[:, 1, 0].max() + 6.5 + 0.5 * np.cos(ys[::-1]), ys[::-1]], axis=1)
+            contour = np.vstack([near, far])
+        turns = []
+        for (a, b) in ((1, 4), (5, 2), (2, 3), (0, n_rows - 2)):
+            for side in (1, -1):
+                col = 0 if side == 1 else 1
+                ya = 0.5 * (rows[a, col, 1] + rows[a + 1, col, 1])
+                yb = 0.5 * (rows[b, col, 1] + rows[b + 1, col, 1])
+                x = rows[a, col, 0] - 1.0 * side
+                turns.append((np.array([x, ya, math.pi if side == 1 else 0.0]), np.array([x, yb, 0.0 if side == 1 else math.pi]), side))
+        cases.append(dict(rows=rows, contour=contour, headland=headland, tree_width=tree_w, turns=turns, seed=500 + k))
+    return cases
+
+
+def oge_outputs(cls, case):
+    """The calls of ``test/obca.ipynb`` cell 12 (+ ``get_tree_row_obstacles``) on one orchard; the jitter of the fit line
+    (``np.random.uniform`` inside ``create_headland_countour_lines``) is seeded the same way for every implementation."""
+    env = cls(case["rows"], [], contour_points=case["contour"], tree_width=case["tree_width"], headland_width=case["headland"])
+    np.random.seed(case["seed"])
+    boundary = env.create_boundary_polygons()
+    out = {"near": list(boundary[0]), "far": list(boundary[1]), "low": list(boundary[2]), "up": list(boundary[3])}
+    for t, (start, end, side) in enumerate(case["turns"]):
+        rows_polys = env.get_obstacle_tree_rows(start, end)
+        out[f"rows{t}"] = list(rows_polys)
+        out[f"block{t}"] = list(env.get_tree_row_obstacles(start, end))
+        out[f"obca{t}"] = list(env.get_obstacles_for_OBCA(boundary, rows_polys, start, end, side=side))
+    return out
+
+
+def pack_polys(polys):
+    return (np.vstack([np.asarray(p, dtype=np.float64).reshape(-1, 2) for p in polys]) if len(polys) else np.zeros((0, 2)),
+            np.array([len(p) for p in polys], dtype=np.int64))
+
+
+def unpack_polys(v, n):
+    off = np.concatenate([[0], np.cumsum(n)])
+    return [v[off[i]:off[i + 1]] for i in range(len(n))]
+
+
+def gen_oge():
+    """tests/golden/oge_golden.npz: the reference's own ``OGE_OBCA.orchard_environment_OBCA`` (``ref_loader.load_oge_obca``)
+    on ``oge_cases()``."""
+    from . import ref_loader as RL
+    ref = RL.load_oge_obca()
+    store = {"n_cases": np.int64(len(oge_cases()))}
+    total = 0
+    for c, case in enumerate(oge_cases()):
+        for name, polys in oge_outputs(ref.orchard_environment_OBCA, case).items():
+            v, n = pack_polys(polys)
+            store[f"c{c}_{name}_v"] = v
+            store[f"c{c}_{name}_n"] = n
+            total += len(n)
+    np.savez_compressed(os.path.join(GOLD, "oge_golden.npz"), **store)
+    print(f"oge: {len(oge_cases())} orchards, {total} polygons")
+
+
 def gen_refpath():
     """obca_py/util.get_init_ref_path of the REFERENCE on the paths of astar_golden.npz (+ synthetic paths with
     several direction changes, repeated poses and 2- / 3-pose pieces)."""
@@ -492,6 +563,8 @@ if __name__ == "__main__":
         gen_astar_ref(int(args[args.index("astar_ref") + 1]))
     if "refpath" in args:
         gen_refpath()
+    if "oge" in args:
+        gen_oge()
     if "offset" in args:
         gen_offset(int(args[args.index("offset") + 1]))
     if "ypark" in args:

@@ -69,10 +69,10 @@ class _StubModule(types.ModuleType):
         return _Anything
 
 
-_ABSENT = ("shapely", "heapdict", "dubins", "skspatial", "matplotlib", "casadi", "cv2")
+_ABSENT = ("shapely", "heapdict", "dubins", "skspatial", "matplotlib", "casadi", "cv2", "pypoman", "rdp")
 
 
-def load_planner(name, heapdict_port=True, dubins_port=False):
+def load_planner(name, heapdict_port=True, dubins_port=False, extra=None):
     """Import ``path_planner/<name>.py`` of the reference FOR REAL, with the absent third-party packages
     (shapely, heapdict, dubins, skspatial, ...) replaced by inert stubs.  Everything that does not touch those
     packages -- the Y-type parking sweep, the motion-path rollout, the odom transform
@@ -112,6 +112,8 @@ def load_planner(name, heapdict_port=True, dubins_port=False):
         if dubins_port:                        # ``import dubins`` resolves to the restated dubins.c (oracle.dubins_port)
             from . import dubins_port as _dp
             sys.modules["dubins"] = _dp
+        for k, v in (extra or {}).items():     # functional stand-ins a caller provides (load_oge_obca)
+            sys.modules[k] = v
         sys.path.insert(0, os.path.join(REFERENCE_ROOT, "path_planner", "utils"))   # notebooks put both on sys.path
         sys.path.insert(0, os.path.join(REFERENCE_ROOT, "path_planner"))
         return importlib.import_module(name)
@@ -122,6 +124,55 @@ def load_planner(name, heapdict_port=True, dubins_port=False):
                 del sys.modules[k]
         sys.modules.update(stash)
         sys.path[:] = saved_path
+
+
+class _Ring:
+    def __init__(self, pts):
+        self.coords = [tuple(p) for p in pts]
+        self.xy = ([p[0] for p in pts], [p[1] for p in pts])
+
+
+class _MiniPolygon:
+    """What ``OGE_OBCA.py`` and the constructor of ``orchard_geometry_environment.py`` read of a shapely Polygon:
+    the closed exterior ring in the order given (shapely keeps the caller's orientation) and an empty ``interiors``."""
+
+    def __init__(self, pts=()):
+        import numpy as np
+        pts = np.asarray(list(pts), dtype=float).reshape(-1, 2)
+        if len(pts) and not (pts[0] == pts[-1]).all():
+            pts = np.vstack([pts, pts[:1]])
+        self.exterior = _Ring(pts)
+        self.interiors = []
+
+
+class _MiniGeom:
+    def __init__(self, *a, **k):
+        pass
+
+    def buffer(self, *a, **k):
+        return _MiniGeom()
+
+
+def load_oge_obca():
+    """``path_planner/OGE_OBCA.py`` of the reference FOR REAL (class ``orchard_environment_OBCA`` on top of the
+    reference's own ``OrchardGeometryEnvironment``): shapely is replaced by the few attributes these two files read
+    (``Polygon(pts).exterior.coords``; buffers and the STRtree are built and never queried by the obstacle extraction),
+    ``rdp`` by the independent recursive restatement ``oracle.rdp_port`` (the package is not installable: parity with
+    it unpinned), pypoman / matplotlib by inert stubs; numpy and scipy's ConvexHull are the real ones."""
+    from . import rdp_port
+    geom = types.ModuleType("shapely.geometry")
+    geom.Polygon = _MiniPolygon
+    geom.Point = _MiniGeom
+    geom.LineString = _MiniGeom
+    geom.MultiPolygon = _MiniGeom
+    strtree = types.ModuleType("shapely.strtree")
+    strtree.STRtree = _MiniGeom
+    shp = _StubModule("shapely")
+    shp.geometry = geom
+    shp.strtree = strtree
+    rdp_mod = types.ModuleType("rdp")
+    rdp_mod.rdp = rdp_port.rdp
+    return load_planner("OGE_OBCA", extra={"shapely": shp, "shapely.geometry": geom, "shapely.strtree": strtree, "rdp": rdp_mod})
 
 
 def load_obca_util():
