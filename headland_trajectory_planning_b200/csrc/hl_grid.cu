@@ -39,87 +39,112 @@ __global__ void k_df_init(const uint8_t* __restrict__ occ, int W, int H, int gi,
     }
 }
 
-__global__ void __launch_bounds__(DF_THREADS)
-k_df_relax(const uint8_t* __restrict__ occ, int W, int H, int gi, int gj, DfMoves mv, double* __restrict__ D,
+// DF_CPT cells per thread of a 32 x 32 tile (1024 / DF_CPT threads), the move set a template parameter: the 8 (King) or 5
+// (Pawn) predecessors are compile-time offsets into the shared tile, so an iteration of the relaxation is 8 LDS.64 + 8
+// DADD + 8 DMNMX per cell between two barriers (the first version walked a move table in a rolled loop: ~500
+// instructions and 1.4 us per iteration).  Only the neighbours that read an improved border cell in their halo are
+// flagged for the next launch.  Measured on the 4096 x 4096 King field: 16.1 ms (one CTA per map tile, move table, a
+// host look per launch) -> 14.4 (frontier list, launches queued 16 at a time) -> 13.3 (constant offsets) -> 9.2
+// (directional flags) -> 7.8 (two cells per thread, no memset between launches; tools/variants_df.sh: 1 / 2 / 4 cells
+// per thread 9.2 / 7.8 / 10.0 ms, with the per-launch memset 8.2).  Tried and slower: one WARP per tile with Gauss-Seidel sweeps (W->E, E->W, N->S, S->N, 32
+// warp-synchronous steps each, repeated to the local fixed point; 32x fewer thread-cycles per visit, but a visit is
+// 2-3 passes of 128 dependent steps = 12.1 ms: what a launch costs is the LATENCY of the slowest tile visit).
+#ifndef DF_CPT
+#define DF_CPT 2
+#endif
+#define DF_RELAX_THREADS (DF_TILE * DF_TILE / DF_CPT)
+template <bool KING>
+__global__ void __launch_bounds__(DF_RELAX_THREADS)
+k_df_relax(const uint8_t* __restrict__ occ, int W, int H, int gi, int gj, double* __restrict__ D,
            const int* __restrict__ list_cur, const int* __restrict__ count_cur, int* __restrict__ list_next,
-           int* __restrict__ count_next, int* __restrict__ mark_next, int tiles_i, int tiles_j, int* __restrict__ any_next) {
+           int* __restrict__ count_next, int* __restrict__ mark_next, int* __restrict__ mark_cur, int* __restrict__ count_clear,
+           int tiles_i, int tiles_j, int* __restrict__ any_next) {
     // the frontier is a LIST of tiles walked by a small grid with a stride (instead of one CTA per tile of the map, 16 k
-    // CTAs of which a few hundred have work).  What a launch costs is the depth of the relaxation INSIDE a tile (>= 32
-    // iterations of two barriers each to cross it): 4096 x 4096 King 16.1 -> 14.4 ms with the list and batched launches
+    // CTAs of which a few hundred have work).  No memset between launches: a tile clears its own mark when it is
+    // processed, and the counter the launch after next appends to is zeroed here (three counters rotate).
+    if (blockIdx.x == 0 && threadIdx.x == 0) *count_clear = 0;
     __shared__ double sd[DF_TILE + 2][DF_TILE + 3];
     __shared__ unsigned char so[DF_TILE + 2][DF_TILE + 2];
     __shared__ int s_border_changed;
+    const double W1 = 1.0, W2 = 1.4142135623730951;       // hypot(1, 0), hypot(1, 1) as the host's libm gives them
     const int n_cur = *count_cur;
-    for (int li = blockIdx.x; li < n_cur; li += gridDim.x) {
-    const int tile = list_cur[li];
-    const int ti = tile / tiles_j, tj = tile % tiles_j;
-    const int i0 = ti * DF_TILE - 1, j0 = tj * DF_TILE - 1;
     const int tid = threadIdx.x;
-    if (tid == 0) s_border_changed = 0;
-    for (int k = tid; k < (DF_TILE + 2) * (DF_TILE + 2); k += DF_THREADS) {
-        int a = k / (DF_TILE + 2), b = k % (DF_TILE + 2);
-        int i = i0 + a, j = j0 + b;
-        bool in = i >= 0 && j >= 0 && i < W && j < H;
-        sd[a][b] = in ? D[(long long)i * H + j] : INFINITY;
-        so[a][b] = in ? occ[(long long)i * H + j] : 1;
-    }
-    __syncthreads();
-    // each thread owns 4 interior cells; remember their initial values
-    double init[4];
-    int ca[4], cb[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        int k = tid + q * DF_THREADS;
-        ca[q] = 1 + k / DF_TILE; cb[q] = 1 + k % DF_TILE;
-        init[q] = sd[ca[q]][cb[q]];
-    }
-    while (true) {
-        int changed = 0;
-        double nv[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int a = ca[q], b = cb[q];
-            double best = sd[a][b];
-            const int gi_ = i0 + a, gj_ = j0 + b;
-            // occupied cells are never entered (the goal cell itself is exempt: it starts closed at 0)
-            if (!so[a][b] && gi_ < W && gj_ < H) {
-                for (int m = 0; m < mv.n; ++m) {
-                    double u = sd[a - mv.di[m]][b - mv.dj[m]];          // predecessor v - m
-                    double c = __dadd_rn(u, mv.w[m]);
-                    if (c < best) best = c;
-                }
-            }
-            nv[q] = best;
+    const int a0 = 1 + (tid >> 5), b = 1 + (tid & 31);    // cell q of this thread: row a0 + q * (DF_TILE / DF_CPT), column b
+    for (int li = blockIdx.x; li < n_cur; li += gridDim.x) {
+        const int tile = list_cur[li];
+        const int ti = tile / tiles_j, tj = tile % tiles_j;
+        const int i0 = ti * DF_TILE - 1, j0 = tj * DF_TILE - 1;
+        if (tid == 0) { s_border_changed = 0; mark_cur[tile] = 0; }
+        for (int k = tid; k < (DF_TILE + 2) * (DF_TILE + 2); k += DF_RELAX_THREADS) {
+            const int x = k / (DF_TILE + 2), y = k % (DF_TILE + 2);
+            const int i = i0 + x, j = j0 + y;
+            const bool in = i >= 0 && j >= 0 && i < W && j < H;
+            sd[x][y] = in ? D[(long long)i * H + j] : INFINITY;
+            so[x][y] = in ? occ[(long long)i * H + j] : 1;
         }
         __syncthreads();
+        double init[DF_CPT], cur[DF_CPT];
+        bool enter[DF_CPT];
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-            if (nv[q] < sd[ca[q]][cb[q]]) { sd[ca[q]][cb[q]] = nv[q]; changed = 1; }
-        if (!__syncthreads_or(changed)) break;
-    }
-    int my_border = 0;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int a = ca[q], b = cb[q];
-        const int i = i0 + a, j = j0 + b;
-        double v = sd[a][b];
-        if (v < init[q] && i < W && j < H) {
-            D[(long long)i * H + j] = v;
-            if (a == 1 || b == 1 || a == DF_TILE || b == DF_TILE) my_border = 1;
+        for (int q = 0; q < DF_CPT; ++q) {
+            const int a = a0 + q * (DF_TILE / DF_CPT);
+            init[q] = cur[q] = sd[a][b];
+            // occupied cells are never entered (the goal cell itself is exempt: it starts closed at 0)
+            enter[q] = !so[a][b] && i0 + a < W && j0 + b < H;
         }
-    }
-    if (my_border) s_border_changed = 1;
-    __syncthreads();
-    if (tid == 0 && s_border_changed) {
-        for (int a = -1; a <= 1; ++a)
-            for (int b = -1; b <= 1; ++b) {
-                int x = ti + a, y = tj + b;
-                if ((a || b) && x >= 0 && y >= 0 && x < tiles_i && y < tiles_j && atomicExch(&mark_next[x * tiles_j + y], 1) == 0)
-                    list_next[atomicAdd(count_next, 1)] = x * tiles_j + y;
+        while (true) {
+            double best[DF_CPT];
+#pragma unroll
+            for (int q = 0; q < DF_CPT; ++q) {
+                const int a = a0 + q * (DF_TILE / DF_CPT);
+                double v = cur[q];
+                if (enter[q]) {                                     // predecessor of move (di, dj) is (a - di, b - dj)
+                    v = fmin(v, __dadd_rn(sd[a + 1][b], W1));                           // (-1,  0)
+                    v = fmin(v, __dadd_rn(sd[a][b - 1], W1));                           // ( 0,  1)
+                    v = fmin(v, __dadd_rn(sd[a + 1][b - 1], W2));                       // (-1,  1)
+                    v = fmin(v, __dadd_rn(sd[a - 1][b - 1], W2));                       // ( 1,  1)
+                    v = fmin(v, __dadd_rn(sd[a - 1][b], W1));                           // ( 1,  0)
+                    if (KING) {
+                        v = fmin(v, __dadd_rn(sd[a - 1][b + 1], W2));                   // ( 1, -1)
+                        v = fmin(v, __dadd_rn(sd[a][b + 1], W1));                       // ( 0, -1)
+                        v = fmin(v, __dadd_rn(sd[a + 1][b + 1], W2));                   // (-1, -1)
+                    }
+                }
+                best[q] = v;
             }
-        *any_next = 1;
-    }
-    __syncthreads();                                   // the shared tile is reused by the next list entry
+            __syncthreads();
+            bool ch = false;
+#pragma unroll
+            for (int q = 0; q < DF_CPT; ++q)
+                if (best[q] < cur[q]) { sd[a0 + q * (DF_TILE / DF_CPT)][b] = best[q]; cur[q] = best[q]; ch = true; }
+            if (!__syncthreads_or(ch)) break;
+        }
+#pragma unroll
+        for (int q = 0; q < DF_CPT; ++q) {
+            const int a = a0 + q * (DF_TILE / DF_CPT);
+            const int i = i0 + a, j = j0 + b;
+            if (cur[q] < init[q] && i < W && j < H) {
+                D[(long long)i * H + j] = cur[q];
+                // which neighbouring tiles read this cell in their halo: bit 3 * (x + 1) + (y + 1) for neighbour (x, y)
+                // (a side cell is read by that side's neighbour only, a corner cell also by the diagonal neighbour)
+                const int x = (a == 1) ? -1 : (a == DF_TILE ? 1 : 0), y = (b == 1) ? -1 : (b == DF_TILE ? 1 : 0);
+                if (x || y) {
+                    unsigned m = 0;
+                    if (x) m |= 1u << (3 * (x + 1) + 1);
+                    if (y) m |= 1u << (3 + (y + 1));
+                    if (x && y) m |= 1u << (3 * (x + 1) + (y + 1));
+                    atomicOr(&s_border_changed, (int)m);
+                }
+            }
+        }
+        __syncthreads();
+        if (tid < 9 && tid != 4 && (s_border_changed >> tid) & 1) {
+            const int tx = ti + tid / 3 - 1, ty = tj + tid % 3 - 1;
+            if (tx >= 0 && ty >= 0 && tx < tiles_i && ty < tiles_j && atomicExch(&mark_next[tx * tiles_j + ty], 1) == 0)
+                list_next[atomicAdd(count_next, 1)] = tx * tiles_j + ty;
+            *any_next = 1;
+        }
+        __syncthreads();                                   // the shared tile is reused by the next list entry
     }
 }
 
@@ -201,16 +226,17 @@ static int df_solve(const uint8_t* d_occ, int w, int h, int gi, int gj, const Df
     // DF_BATCH at a time and the host looks at the "frontier not empty" flags once per batch (one stream
     // synchronisation per launch before); a launch with an empty frontier list costs a few microseconds.
     enum { DF_BATCH = 16 };
-    const size_t ws_ints = 4 * (size_t)n_tiles + 2 + 1 + DF_BATCH;
+    const size_t ws_ints = 4 * (size_t)n_tiles + 4 + 1 + DF_BATCH;
     HL_CUDA_OK(cudaMalloc(&ws, ws_ints * sizeof(int)));
     int* list[2] = {ws, ws + n_tiles};
     int* mark[2] = {ws + 2 * (size_t)n_tiles, ws + 3 * (size_t)n_tiles};
     int* count = ws + 4 * (size_t)n_tiles;
-    int* flags = count + 2;
+    int* flags = count + 4;                  // count[0..2]: three rotating frontier counters
     int rc = 0, sweeps = 0;
     int sm = 148;
     { int dev_id = 0; cudaGetDevice(&dev_id); cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev_id); }
-    const int grid = n_tiles < sm * 6 ? n_tiles : sm * 6;
+    const int per_sm = 2048 / DF_RELAX_THREADS;            // resident CTAs per SM (thread-limited)
+    const int grid = n_tiles < sm * per_sm ? n_tiles : sm * per_sm;
     do {
         if (cudaMemsetAsync(ws, 0, ws_ints * sizeof(int), st) != cudaSuccess) { rc = 1; break; }
         long long cells = (long long)w * h;
@@ -218,18 +244,24 @@ static int df_solve(const uint8_t* d_occ, int w, int h, int gi, int gj, const Df
         int host_flags[1 + DF_BATCH] = {0};
         if (cudaMemcpyAsync(host_flags, flags, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) { rc = 1; break; }
         if (open_border) { *open_border = host_flags[0]; if (host_flags[0]) break; }
-        int cur = 0;
+        int cur = 0;                            // launch number: lists / marks alternate (cur & 1), counters rotate (cur % 3)
         const int max_sweeps = 8 * (tiles_i + tiles_j) * DF_TILE + 64;
         bool converged = false;
         while (!converged && sweeps < max_sweeps) {
             cudaMemsetAsync(flags + 1, 0, DF_BATCH * sizeof(int), st);
             for (int k = 0; k < DF_BATCH; ++k) {
-                const int nxt = cur ^ 1;
-                cudaMemsetAsync(mark[nxt], 0, sizeof(int) * (size_t)n_tiles, st);
-                cudaMemsetAsync(count + nxt, 0, sizeof(int), st);
-                k_df_relax<<<grid, DF_THREADS, 0, st>>>(d_occ, w, h, gi, gj, mv, d_out, list[cur], count + cur, list[nxt], count + nxt,
-                                                        mark[nxt], tiles_i, tiles_j, flags + 1 + k);
-                cur = nxt;
+                const int lc = cur & 1, ln = lc ^ 1;
+#ifdef DF_MEMSET
+                cudaMemsetAsync(mark[ln], 0, sizeof(int) * (size_t)n_tiles, st);
+#endif
+                int* c_cur = count + cur % 3; int* c_nxt = count + (cur + 1) % 3; int* c_clr = count + (cur + 2) % 3;
+                if (mv.n == 8)
+                    k_df_relax<true><<<grid, DF_RELAX_THREADS, 0, st>>>(d_occ, w, h, gi, gj, d_out, list[lc], c_cur, list[ln], c_nxt,
+                                                                        mark[ln], mark[lc], c_clr, tiles_i, tiles_j, flags + 1 + k);
+                else
+                    k_df_relax<false><<<grid, DF_RELAX_THREADS, 0, st>>>(d_occ, w, h, gi, gj, d_out, list[lc], c_cur, list[ln], c_nxt,
+                                                                         mark[ln], mark[lc], c_clr, tiles_i, tiles_j, flags + 1 + k);
+                ++cur;
             }
             if (cudaMemcpyAsync(host_flags + 1, flags + 1, DF_BATCH * sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) { rc = 1; break; }
             for (int k = 0; k < DF_BATCH && !converged; ++k) {   // launches after the first empty frontier did nothing
