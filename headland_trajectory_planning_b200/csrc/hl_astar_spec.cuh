@@ -215,8 +215,8 @@ __device__ __noinline__ void team_state_costs(AqSmem& S, const EnvBatchDev& eb, 
     const int slot = tl / AQ_SUB, sub = tl - slot * AQ_SUB;
     const int p = slot < __popc(needm) ? (int)__fns(needm, 0, slot + 1) : -1;
     const int n = D.n_guide;
-    const double* gx = S.guide_staged ? S.gx : eb.guide_x + D.guide_off;
-    const double* gy = S.guide_staged ? S.gy : eb.guide_y + D.guide_off;
+    const double* gx = S.gx;                             // shared memory (LDS): the caller takes the per-primitive
+    const double* gy = S.gy;                             // warp_state_cost path when the polyline was too long to stage
     const double x = p >= 0 ? S.tx[p][nst] : 0.0, y = p >= 0 ? S.ty[p][nst] : 0.0;
     double best = INFINITY;
 #pragma unroll 4
@@ -247,11 +247,9 @@ __device__ __noinline__ void team_state_costs(AqSmem& S, const EnvBatchDev& eb, 
         double h = 0.0;
         if (n > 0) {
             double dist = xmul(bh, 100.0);
-            const double* gyaw = S.guide_staged ? S.gyaw : eb.guide_yaw + D.guide_off;
-            const double* gs = S.guide_staged ? S.gs : eb.guide_s + D.guide_off;
-            const double yaw_diff = fabs(angle_wrap(xsub(gyaw[bi], S.pyaw[p][nst])));
+            const double yaw_diff = fabs(angle_wrap(xsub(S.gyaw[bi], S.pyaw[p][nst])));
             if (dist > 2.0) dist = 100.0;
-            const double to_goal = xsub(gs[n - 1], gs[bi]);
+            const double to_goal = xsub(S.gs[n - 1], S.gs[bi]);
             h = xadd(xadd(dist, xmul(yaw_diff, 0.2)), xmul(to_goal, 5.0));
         }
         S.pprio[p] = xmul(P.hybrid_cost, h);
@@ -967,7 +965,20 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
             }
             team_sync(slot);
             if (ew == 0) ETICK(PH_ARRIVE);                   // (timer slot reused: g-cost + key + hash probe)
-            team_state_costs(S, eb, D, P, n, tl, lane);
+            if (S.guide_staged) team_state_costs(S, eb, D, P, n, tl, lane);
+            else {                                           // polyline longer than AQ_GUIDE_CAP: one warp call per primitive
+                int q = 0;
+#pragma unroll 1
+                for (int p = 0; p < P.n_prims; ++p) {
+                    if (!S.phit[p] && S.pneed[p]) {
+                        if ((q % AQ_EXPANDERS) == ew) {
+                            const double h = warp_state_cost(eb, D, S.tx[p][n], S.ty[p][n], S.pyaw[p][n], lane);
+                            if (lane == 0) S.pprio[p] = xmul(P.hybrid_cost, h);
+                        }
+                        ++q;
+                    }
+                }
+            }
             team_sync(slot);
             if (ew == 0) ETICK(PH_COST_HEUR);
             if (ew == 0) {
