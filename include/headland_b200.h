@@ -99,8 +99,10 @@ typedef struct {
     double prim_yaw_step[HL_MAX_PRIMS];/* dir*res/WB*tan(steer), :370-375       */
     double prim_curv[HL_MAX_PRIMS];    /* np.tan(steer)/WB, :402                */
     double prim_steer_eff[HL_MAX_PRIMS];/* math.atan(curv*WB), :322             */
-    int32_t steps_default;             /* round(default_search_length/res), :369 (banker's) */
-    int32_t steps_large;               /* round(1.0/res)                        */
+    int32_t steps_default;             /* informational only: the kernels take the per-environment search length from
+                                          HlEnvHost.default_search_length and HlEnvHost.seg_len (the heuristic's values,
+                                          reference_line_heuristic.py:120-131) and round it per node like :369 */
+    int32_t steps_large;               /* informational only, see steps_default */
     double steer_cost, delta_steer_cost, direction_change_cost, reverse_cost, hybrid_cost;
     double min_length_to_goal;         /* :36 */
     int32_t max_nodes;                 /* hybrid_a_star_search(max_nodes=..), :497 */
