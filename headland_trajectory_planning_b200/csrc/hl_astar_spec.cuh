@@ -35,6 +35,11 @@
 #ifndef AQ_GUIDE_CAP
 #define AQ_GUIDE_CAP 192               // guide polyline points staged in shared memory (longer polylines are read from HBM / L2)
 #endif
+#ifndef AQ_GD_UNROLL
+#define AQ_GD_UNROLL 4                // unroll factor of the guide-distance loop (team_state_costs)
+#endif
+#define AQ_PRAGMA_(x) _Pragma(#x)
+#define AQ_PRAGMA_UNROLL(n) AQ_PRAGMA_(unroll n)
 #define AQ_SUB (AQ_TEAM / 16)          // lanes per primitive in the batched guide-distance pass
 #ifndef AQ_FAR
 #define AQ_FAR 4                       // poses per primitive (farthest first) in the first filter round
@@ -116,6 +121,9 @@ static_assert(sizeof(AqSmem) * AQ_SLOTS <= 227 * 1024, "per-CTA shared memory ex
 // Alignment of the AQ_SLOTS warps of one role (named barrier `id`, all threads of those warps) with an AND
 // reduction: keeps the role's warps inside the same code region (instruction cache) and tells them when
 // every one of them is finished.
+#ifndef AQ_WARP_MAP
+#define AQ_WARP_MAP 0                  // 1: same-role warps share a scheduler (measured: see DESIGN.md)
+#endif
 #ifndef AQ_ALIGN
 #define AQ_ALIGN 1                     // 0: no role alignment (each warp leaves when its own queue is drained)
 #endif
@@ -219,7 +227,7 @@ __device__ __noinline__ void team_state_costs(AqSmem& S, const EnvBatchDev& eb, 
     const double* gy = S.gy;                             // warp_state_cost path when the polyline was too long to stage
     const double x = p >= 0 ? S.tx[p][nst] : 0.0, y = p >= 0 ? S.ty[p][nst] : 0.0;
     double best = INFINITY;
-#pragma unroll 4
+AQ_PRAGMA_UNROLL(AQ_GD_UNROLL)
     for (int i = sub; i < n; i += AQ_SUB) {
         const double dx = gx[i] - x, dy = gy[i] - y;
         best = fmin(best, dx * dx + dy * dy);
@@ -426,8 +434,15 @@ k_hybrid_astar_s(EnvBatchDev eb, const HlScenario* __restrict__ scen, int n_scen
                  size_t ws_stride, unsigned int* work_counter, AwOut O) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#if AQ_WARP_MAP == 1 && AQ_SLOTS == 5 && AQ_WARPS_PER_SLOT == 3
+    // warps of the same role on the same scheduler (warp w issues on sub-partition w % 4): sub-partition 0 holds four
+    // shooters, 1 four lead expanders, 2 four helpers, 3 the three warps of slot 4
+    const int slot = (wid & 3) == 3 ? 4 : wid >> 2;
+    const int wrole = (wid & 3) == 3 ? (wid == 3 ? 2 : (wid == 7 ? 0 : 1)) : ((wid & 3) == 0 ? 2 : (wid & 3) - 1);
+#else
     const int slot = wid / AQ_WARPS_PER_SLOT;
     const int wrole = wid % AQ_WARPS_PER_SLOT;          // 0 .. AQ_EXPANDERS-1 = expander team, then the shooters
+#endif
     const int ew = wrole;                               // index inside the expander team
     const int role = wrole < AQ_EXPANDERS ? 0 : wrole - AQ_EXPANDERS + 1;   // 0 = expander, 1.. = shooters
     const int tl = ew * 32 + lane;                      // lane inside the expander team

@@ -80,6 +80,11 @@ __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cas
 // instead; the float32 pipeline goes on as if the ambiguous test had passed (a later verdict can only add "hit"), and
 // when the CTA has no tile left its warps resolve the queue, one entry per warp at a time, all in parallel.
 #define K1_DEFER_CAP 48
+#ifndef K1_DRAIN_MID
+#define K1_DRAIN_MID 0                    // 1: drain the float64 queue between tiles as soon as every warp gets an entry.
+                                          // Measured SLOWER (16.86 vs 17.43 G checks/s, 16 Mi random poses): tiles are assigned
+                                          // by a fixed stride, so a CTA that stops to drain simply finishes that much later
+#endif
 struct K1Defer { long long i; int env; unsigned amb; int rect; int pad; };
 struct __align__(16) K1Cta {
     double raw[K1_TILE * 3];              // TMA landing zone: x, y, yaw of the tile                        24 KB
@@ -483,6 +488,29 @@ k_collision(EnvBatchDev eb, const int32_t* __restrict__ env_id, const double* __
             bulk_g2s(smem_u32(S.raw), poses + 3 * tile * K1_TILE, K1_TILE * 24, rbar);
         }
     };
+    // The queued float64 resolutions, one entry per warp at a time.  Called by all threads of the CTA (between two
+    // tiles: after the verdict store of the tile that queued the entries, so a drained "hit" lands on top of it).
+    auto drain_queue = [&]() {
+        const int nq = min(S.dq_cnt, K1_DEFER_CAP);
+#pragma unroll 1
+        for (int e = warp; e < nq; e += K1_WARPS) {
+            const K1Defer d = S.dq[e];
+            const EnvDesc& D = eb.desc[d.env];
+            const double* ext64 = d.rect == 0 ? D.body_ext : eb.aux64 + 4 * (size_t)(D.aux_off + d.rect - 1);
+            Pose64 p;
+            p.x = poses[3 * d.i]; p.y = poses[3 * d.i + 1];
+            const double yaw = poses[3 * d.i + 2];
+            p.c = cos(yaw); p.s = sin(yaw);
+            double e4[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) e4[k] = ext64[k];
+            const bool res = warp_exact_part_check(p, e4, eb, D, d.amb, lane);
+            if (lane == 0) {
+                if (res) out[d.i] = 1;
+                if (n_exact) atomicAdd(n_exact, 1ULL);
+            }
+        }
+    };
     issue_tile(blockIdx.x);
 
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -804,27 +832,23 @@ k_collision(EnvBatchDev eb, const int32_t* __restrict__ env_id, const double* __
             }
         }
         __syncthreads();                                   // S.st / lists are rewritten by the next tile
-    }
-    // ---- the queued float64 resolutions: one entry per warp at a time, every warp busy
-    const int nq = min(S.dq_cnt, K1_DEFER_CAP);
-#pragma unroll 1
-    for (int e = warp; e < nq; e += K1_WARPS) {
-        const K1Defer d = S.dq[e];
-        const EnvDesc& D = eb.desc[d.env];
-        const double* ext64 = d.rect == 0 ? D.body_ext : eb.aux64 + 4 * (size_t)(D.aux_off + d.rect - 1);
-        Pose64 p;
-        p.x = poses[3 * d.i]; p.y = poses[3 * d.i + 1];
-        const double yaw = poses[3 * d.i + 2];
-        p.c = cos(yaw); p.s = sin(yaw);
-        double e4[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) e4[k] = ext64[k];
-        const bool res = warp_exact_part_check(p, e4, eb, D, d.amb, lane);
-        if (lane == 0) {
-            if (res) out[d.i] = 1;
-            if (n_exact) atomicAdd(n_exact, 1ULL);
+#if K1_DRAIN_MID
+        // experiment (off): drain the queue BETWEEN tiles once every warp gets an entry, and whatever is pending before
+        // the CTA's last tile, so that the other CTAs of the SM keep the pipes busy meanwhile
+        {
+            const int nq = S.dq_cnt;                       // CTA-uniform: read behind the barrier
+            const bool last_next = tile + gridDim.x < n_tiles && tile + 2 * (long long)gridDim.x >= n_tiles;
+            if (nq >= K1_WARPS || (last_next && nq > 0)) {
+                drain_queue();
+                __syncthreads();
+                if (tid == 0) S.dq_cnt = 0;
+                __syncthreads();
+            }
         }
+#endif
     }
+    // ---- what is still queued: one entry per warp at a time, every warp busy
+    drain_queue();
 }
 
 __global__ void k_path_reduce(const uint8_t* __restrict__ pose_bad, const long long* __restrict__ path_start,

@@ -129,6 +129,16 @@ static __device__ HL_CODE double m_asin(double x) { return asin(x); }
 static __device__ HL_CODE double m_acos(double x) { return acos(x); }
 static __device__ HL_CODE double m_fmod(double a, double b) { return fmod(a, b); }
 static __device__ HL_CODE void m_sincos(double x, double* s, double* c) { sincos(x, s, c); }
+// fmod(a, m) for m > 0.  fmod is EXACT, so the two ranges every angle on this path falls into need no libdevice loop:
+// |a| < m leaves a as it is, m <= |a| < 2m takes m off once (exact by Sterbenz's lemma); anything else (NaN / inf
+// included) goes to fmod.  Same bits as fmod(a, m) for every input (a == -m gives +0 instead of -0; the only caller,
+// py_mod_pos, maps both to +0).
+static __device__ HL_CODE double m_fmod_pos(double a, double m) {
+    const double aa = fabs(a);
+    if (aa < m) return a;
+    if (aa < 2.0 * m) return (a > 0.0) ? __dadd_rn(a, -m) : __dadd_rn(a, m);
+    return fmod(a, m);
+}
 // float64 arithmetic that must not be contracted into FMAs: the oracle evaluates
 // the same expressions with one rounding per operation.
 __device__ __forceinline__ double xmul(double a, double b) { return __dmul_rn(a, b); }
@@ -139,7 +149,7 @@ static __device__ HL_TINY double xdiv(double a, double b) { return __ddiv_rn(a, 
 // Python / numpy floored modulo for a positive modulus (CPython float_rem,
 // numpy npy_divmod): fmod, then shift negative remainders up.
 static __device__ HL_TINY double py_mod_pos(double a, double m) {
-    double r = m_fmod(a, m);         // exact in CUDA
+    double r = m_fmod_pos(a, m);     // exact
     if (r != 0.0) {
         if (r < 0.0) r = xadd(r, m);
     } else {
