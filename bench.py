@@ -366,9 +366,10 @@ def main():
             "roofline": {"bound": "alu_fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp32_peak if fp32_peak else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one k_hybrid_astar_s launch on this very
-                         # workload (4096 scenarios), ncu --set full, profiles/r2n_k4_ncu_full_summary.txt
-                         # (199.9 MB read + 291.8 MB written: node / hash / open-list scratch of 740 scenario slots)
-                         "traffic": 491697152 if args.scenarios_per_gpu == 4096 else None,
+                         # workload (4096 scenarios; the search launch of the two-phase sweep), ncu --set full,
+                         # profiles/r2u_k4_ncu_full_summary.txt (170.2 MB read + 281.5 MB written: node / hash /
+                         # open-list scratch of 740 scenario slots)
+                         "traffic": 451706112 if args.scenarios_per_gpu == 4096 else None,
                          "kernel": "k_hybrid_astar_s",
                          # the same launch against the HBM roof (this path is not bandwidth-bound): algorithmic
                          # bytes = environments + scenario records in, result records + key sequences + paths out
