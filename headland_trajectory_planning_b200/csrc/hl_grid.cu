@@ -40,21 +40,63 @@ __global__ void k_df_init(const uint8_t* __restrict__ occ, int W, int H, int gi,
 }
 
 // DF_CPT cells per thread of a 32 x 32 tile (1024 / DF_CPT threads), the move set a template parameter: the 8 (King) or 5
-// (Pawn) predecessors are compile-time offsets into the shared tile, so an iteration of the relaxation is 8 LDS.64 + 8
-// DADD + 8 DMNMX per cell between two barriers (the first version walked a move table in a rolled loop: ~500
-// instructions and 1.4 us per iteration).  Only the neighbours that read an improved border cell in their halo are
-// flagged for the next launch.  Measured on the 4096 x 4096 King field: 16.1 ms (one CTA per map tile, move table, a
-// host look per launch) -> 14.4 (frontier list, launches queued 16 at a time) -> 13.3 (constant offsets) -> 9.2
-// (directional flags) -> 7.8 (two cells per thread, no memset between launches; tools/variants_df.sh: 1 / 2 / 4 cells
-// per thread 9.2 / 7.8 / 10.0 ms, with the per-launch memset 8.2).  Tried and slower: one WARP per tile with Gauss-Seidel sweeps (W->E, E->W, N->S, S->N, 32
-// warp-synchronous steps each, repeated to the local fixed point; 32x fewer thread-cycles per visit, but a visit is
-// 2-3 passes of 128 dependent steps = 12.1 ms: what a launch costs is the LATENCY of the slowest tile visit).
+// (Pawn) predecessors are compile-time offsets into the shared tile.  Only the neighbours that read an improved border
+// cell in their halo are flagged for the next launch.  History on the 4096 x 4096 King field:
+//   16.1 ms  one CTA per map tile, move table in a rolled loop, a host look per launch
+//   14.4     frontier list, launches queued 16 at a time          13.3  constant offsets
+//    9.2     directional flags                                      7.8  two cells per thread, no memset between launches
+//   (tools/variants_df.sh: 1 / 2 / 4 cells per thread 9.2 / 7.8 / 10.0 ms; tried and slower: one WARP per tile with
+//    Gauss-Seidel sweeps, 12.1 ms -- what a launch costs is the latency of the slowest tile visit)
+// ncu on that version (profiles/r2v_k6_*): a launch is ISSUE-bound, 74 % issue-active, FP64 pipe 26 %, and two thirds of
+// the instructions were fmin's NaN handling (DSETP.MIN + fix-up + moves, 7 per minimum).  Costs are never NaN, so:
+//    6.1 ms  minimum as compare + two selects                       5.7  a thread's two cells vertically ADJACENT (10 loads
+//                                                                        of the shared 3-column neighbourhood instead of 16)
+//    5.0     the compare on the FP64 pipe (DSETP.LT, 3 instructions) instead of a 64-bit integer compare (4)
+//    4.6     a warp skips an iteration when no row it can see changed (the wave crosses a tile as a band)
+//    4.26    minimum of the predecessors FIRST, one addition per weight (exact: fl(x + w) is monotone in x)
+// (3 CTAs per SM at 35 registers: 4.79; 4 cells per thread: 4.71; first host look after (tiles_i + tiles_j) / 2 launches.)
 #ifndef DF_CPT
 #define DF_CPT 2
 #endif
+#ifndef DF_ADJ
+#define DF_ADJ 1                       // 1: a thread's cells are vertically ADJACENT (rows a0 .. a0 + DF_CPT - 1): the three-column
+#endif                                 // neighbourhood of the cells overlaps, 5 + 5 (King) loads for 2 cells instead of 16;
+                                       // 0: rows DF_TILE / DF_CPT apart (round-2 first version)
 #define DF_RELAX_THREADS (DF_TILE * DF_TILE / DF_CPT)
+#if DF_ADJ
+#define DF_ROW0(tid) (1 + DF_CPT * ((tid) >> 5))
+#define DF_ROW(a0, q) ((a0) + (q))
+#else
+#define DF_ROW0(tid) (1 + ((tid) >> 5))
+#define DF_ROW(a0, q) ((a0) + (q) * (DF_TILE / DF_CPT))
+#endif
+// min of two costs.  Costs are +0, positive or +inf, never NaN: their bit patterns order like integers, so the minimum is
+// an integer compare + two selects (4 ALU instructions) instead of fmin's DSETP.MIN + NaN fix-up + moves (7, one of
+// them on the FP64 pipe).  The relaxation kernel is issue-bound (ncu: issue-active 74 %), instructions are time.
+#ifndef DF_MIN_MODE
+#define DF_MIN_MODE 1                  // 0: integer compare (4 ALU instructions); 1: DSETP.LT + two selects (3, one on the FP64 pipe);
+                                       // 2: half each.  Measured (4096 x 4096 King, row skip on): 4.93 / 4.57 / 4.81 ms
+#endif
+__device__ __forceinline__ double df_min_i(double a, double b) {
+    const long long x = __double_as_longlong(a), y = __double_as_longlong(b);
+    return __longlong_as_double(y < x ? y : x);
+}
+__device__ __forceinline__ double df_min_d(double a, double b) { return (b < a) ? b : a; }
+// df_min serves the straight moves, df_min2 the diagonal ones (mode 2: integer / FP64 compare, half each)
+__device__ __forceinline__ double df_min(double a, double b) { return DF_MIN_MODE == 1 ? df_min_d(a, b) : df_min_i(a, b); }
+__device__ __forceinline__ double df_min2(double a, double b) { return DF_MIN_MODE == 0 ? df_min_i(a, b) : df_min_d(a, b); }
+__device__ __forceinline__ bool df_less(double a, double b) { return __double_as_longlong(a) < __double_as_longlong(b); }
+#ifndef DF_MIN_CTAS
+#define DF_MIN_CTAS 2                    // 64 registers: two 512-thread CTAs per SM (66 would leave one)
+#endif
+#ifndef DF_MIN_TREE
+#define DF_MIN_TREE 1                   // one addition per weight: min of the predecessors first (exact, see the loop)
+#endif
+#ifndef DF_ROWSKIP
+#define DF_ROWSKIP 1                    // a warp sits an iteration out when no row its cells can see changed in the previous one
+#endif
 template <bool KING>
-__global__ void __launch_bounds__(DF_RELAX_THREADS)
+__global__ void __launch_bounds__(DF_RELAX_THREADS, DF_MIN_CTAS)
 k_df_relax(const uint8_t* __restrict__ occ, int W, int H, int gi, int gj, double* __restrict__ D,
            const int* __restrict__ list_cur, const int* __restrict__ count_cur, int* __restrict__ list_next,
            int* __restrict__ count_next, int* __restrict__ mark_next, int* __restrict__ mark_cur, int* __restrict__ count_clear,
@@ -66,15 +108,22 @@ k_df_relax(const uint8_t* __restrict__ occ, int W, int H, int gi, int gj, double
     __shared__ double sd[DF_TILE + 2][DF_TILE + 3];
     __shared__ unsigned char so[DF_TILE + 2][DF_TILE + 2];
     __shared__ int s_border_changed;
+#if DF_ROWSKIP
+    __shared__ int s_rowchg[2][DF_TILE + 2];            // rows that changed in the previous / this iteration
+#endif
     const double W1 = 1.0, W2 = 1.4142135623730951;       // hypot(1, 0), hypot(1, 1) as the host's libm gives them
     const int n_cur = *count_cur;
     const int tid = threadIdx.x;
-    const int a0 = 1 + (tid >> 5), b = 1 + (tid & 31);    // cell q of this thread: row a0 + q * (DF_TILE / DF_CPT), column b
+    const int a0 = DF_ROW0(tid), b = 1 + (tid & 31);      // cell q of this thread: row DF_ROW(a0, q), column b
     for (int li = blockIdx.x; li < n_cur; li += gridDim.x) {
         const int tile = list_cur[li];
         const int ti = tile / tiles_j, tj = tile % tiles_j;
         const int i0 = ti * DF_TILE - 1, j0 = tj * DF_TILE - 1;
         if (tid == 0) { s_border_changed = 0; mark_cur[tile] = 0; }
+#if DF_ROWSKIP
+        if (tid < DF_TILE + 2) { s_rowchg[0][tid] = 1; s_rowchg[1][tid] = 0; }      // first iteration: every row counts as changed
+        int it = 0;
+#endif
         for (int k = tid; k < (DF_TILE + 2) * (DF_TILE + 2); k += DF_RELAX_THREADS) {
             const int x = k / (DF_TILE + 2), y = k % (DF_TILE + 2);
             const int i = i0 + x, j = j0 + y;
@@ -87,41 +136,120 @@ k_df_relax(const uint8_t* __restrict__ occ, int W, int H, int gi, int gj, double
         bool enter[DF_CPT];
 #pragma unroll
         for (int q = 0; q < DF_CPT; ++q) {
-            const int a = a0 + q * (DF_TILE / DF_CPT);
+            const int a = DF_ROW(a0, q);
             init[q] = cur[q] = sd[a][b];
             // occupied cells are never entered (the goal cell itself is exempt: it starts closed at 0)
             enter[q] = !so[a][b] && i0 + a < W && j0 + b < H;
         }
         while (true) {
             double best[DF_CPT];
+#if DF_ROWSKIP && DF_ADJ
+            // a cell can only change if a cell of rows a0 - 1 .. a0 + DF_CPT changed in the previous iteration: the warp
+            // (one group of DF_CPT rows) sits the iteration out otherwise (the wave crosses a tile as a band)
+            int seen = 0;
+#pragma unroll
+            for (int r = 0; r < DF_CPT + 2; ++r) seen |= s_rowchg[it & 1][a0 - 1 + r];
+            if (!seen) {
+#pragma unroll
+                for (int q = 0; q < DF_CPT; ++q) best[q] = cur[q];
+            } else {
+#endif
+#if DF_ADJ
+            // columns b - 1, b, b + 1 of rows a0 - 1 .. a0 + DF_CPT; the thread's own cells (column b) are in registers,
+            // and a cell sees the value its upper neighbour in the same thread was just given (any relaxation order
+            // reaches the same fixed point)
+            double L[DF_CPT + 2], M[DF_CPT + 2], R[DF_CPT + 2];
+#pragma unroll
+            for (int r = 0; r < DF_CPT + 2; ++r) {
+                L[r] = sd[a0 - 1 + r][b - 1];
+                R[r] = KING ? sd[a0 - 1 + r][b + 1] : 0.0;
+            }
+            M[0] = sd[a0 - 1][b]; M[DF_CPT + 1] = sd[a0 + DF_CPT][b];
+#pragma unroll
+            for (int q = 0; q < DF_CPT; ++q) M[q + 1] = cur[q];
+#if DF_MIN_TREE
+            // fl(x + w) is monotone in x, so min(fl(x + w), fl(y + w)) == fl(min(x, y) + w) bit for bit: ONE addition per
+            // weight and cell (the minimum of the straight predecessors + 1, of the diagonal ones + sqrt 2) instead of
+            // eight, and the minimum of a row's left and right cell serves the cell between them (straight) and the two
+            // cells above / below it (diagonal).  Pawn moves only come from column b - 1.
+            double hr[DF_CPT + 2];
+#pragma unroll
+            for (int r = 0; r < DF_CPT + 2; ++r) hr[r] = KING ? df_min(L[r], R[r]) : L[r];
 #pragma unroll
             for (int q = 0; q < DF_CPT; ++q) {
-                const int a = a0 + q * (DF_TILE / DF_CPT);
+                const int r = q + 1;
+                double v = cur[q];
+                if (enter[q]) {
+                    const double m1 = df_min(df_min(M[r - 1], M[r + 1]), hr[r]);
+                    const double m2 = df_min(hr[r - 1], hr[r + 1]);
+                    v = df_min(v, df_min(__dadd_rn(m1, W1), __dadd_rn(m2, W2)));
+                }
+                best[q] = v;
+                M[r] = v;
+            }
+#else
+#pragma unroll
+            for (int q = 0; q < DF_CPT; ++q) {
+                const int r = q + 1;
                 double v = cur[q];
                 if (enter[q]) {                                     // predecessor of move (di, dj) is (a - di, b - dj)
-                    v = fmin(v, __dadd_rn(sd[a + 1][b], W1));                           // (-1,  0)
-                    v = fmin(v, __dadd_rn(sd[a][b - 1], W1));                           // ( 0,  1)
-                    v = fmin(v, __dadd_rn(sd[a + 1][b - 1], W2));                       // (-1,  1)
-                    v = fmin(v, __dadd_rn(sd[a - 1][b - 1], W2));                       // ( 1,  1)
-                    v = fmin(v, __dadd_rn(sd[a - 1][b], W1));                           // ( 1,  0)
+                    v = df_min(v, __dadd_rn(M[r + 1], W1));                             // (-1,  0)
+                    v = df_min(v, __dadd_rn(L[r], W1));                                 // ( 0,  1)
+                    v = df_min2(v, __dadd_rn(L[r + 1], W2));                             // (-1,  1)
+                    v = df_min2(v, __dadd_rn(L[r - 1], W2));                             // ( 1,  1)
+                    v = df_min(v, __dadd_rn(M[r - 1], W1));                             // ( 1,  0)
                     if (KING) {
-                        v = fmin(v, __dadd_rn(sd[a - 1][b + 1], W2));                   // ( 1, -1)
-                        v = fmin(v, __dadd_rn(sd[a][b + 1], W1));                       // ( 0, -1)
-                        v = fmin(v, __dadd_rn(sd[a + 1][b + 1], W2));                   // (-1, -1)
+                        v = df_min2(v, __dadd_rn(R[r - 1], W2));                         // ( 1, -1)
+                        v = df_min(v, __dadd_rn(R[r], W1));                             // ( 0, -1)
+                        v = df_min2(v, __dadd_rn(R[r + 1], W2));                         // (-1, -1)
+                    }
+                }
+                best[q] = v;
+                M[r] = v;
+            }
+#endif
+#if DF_ROWSKIP
+            }
+#endif
+#else
+#pragma unroll
+            for (int q = 0; q < DF_CPT; ++q) {
+                const int a = DF_ROW(a0, q);
+                double v = cur[q];
+                if (enter[q]) {                                     // predecessor of move (di, dj) is (a - di, b - dj)
+                    v = df_min(v, __dadd_rn(sd[a + 1][b], W1));                           // (-1,  0)
+                    v = df_min(v, __dadd_rn(sd[a][b - 1], W1));                           // ( 0,  1)
+                    v = df_min(v, __dadd_rn(sd[a + 1][b - 1], W2));                       // (-1,  1)
+                    v = df_min(v, __dadd_rn(sd[a - 1][b - 1], W2));                       // ( 1,  1)
+                    v = df_min(v, __dadd_rn(sd[a - 1][b], W1));                           // ( 1,  0)
+                    if (KING) {
+                        v = df_min(v, __dadd_rn(sd[a - 1][b + 1], W2));                   // ( 1, -1)
+                        v = df_min(v, __dadd_rn(sd[a][b + 1], W1));                       // ( 0, -1)
+                        v = df_min(v, __dadd_rn(sd[a + 1][b + 1], W2));                   // (-1, -1)
                     }
                 }
                 best[q] = v;
             }
+#endif
             __syncthreads();
             bool ch = false;
 #pragma unroll
             for (int q = 0; q < DF_CPT; ++q)
-                if (best[q] < cur[q]) { sd[a0 + q * (DF_TILE / DF_CPT)][b] = best[q]; cur[q] = best[q]; ch = true; }
+                if (df_less(best[q], cur[q])) {
+                    sd[DF_ROW(a0, q)][b] = best[q]; cur[q] = best[q]; ch = true;
+#if DF_ROWSKIP && DF_ADJ
+                    s_rowchg[(it + 1) & 1][DF_ROW(a0, q)] = 1;
+#endif
+                }
+#if DF_ROWSKIP && DF_ADJ
+            if (tid < DF_TILE + 2) s_rowchg[it & 1][tid] = 0;      // read before the barrier above, written again in iteration it + 2
+            ++it;
+#endif
             if (!__syncthreads_or(ch)) break;
         }
 #pragma unroll
         for (int q = 0; q < DF_CPT; ++q) {
-            const int a = a0 + q * (DF_TILE / DF_CPT);
+            const int a = DF_ROW(a0, q);
             const int i = i0 + a, j = j0 + b;
             if (cur[q] < init[q] && i < W && j < H) {
                 D[(long long)i * H + j] = cur[q];
@@ -225,8 +353,14 @@ static int df_solve(const uint8_t* d_occ, int w, int h, int gi, int gj, const Df
     // The wavefront needs one launch per tile it crosses (~150 for a 4096 x 4096 map), so the launches are queued
     // DF_BATCH at a time and the host looks at the "frontier not empty" flags once per batch (one stream
     // synchronisation per launch before); a launch with an empty frontier list costs a few microseconds.
-    enum { DF_BATCH = 16 };
-    const size_t ws_ints = 4 * (size_t)n_tiles + 4 + 1 + DF_BATCH;
+    // Launches are queued DF_BATCH at a time with one host look per batch (launches behind the first empty frontier do
+    // nothing and cost ~2 us each).  The wavefront needs about one launch per tile it crosses, so the first look comes
+    // after (tiles_i + tiles_j) / 2 launches, the later ones every 32: 2 host looks for the 4096 x 4096 field (157
+    // launches) instead of 10 -- every look is a stream synchronisation, i.e. an idle GPU for as long as the host
+    // thread takes to come back.
+    enum { DF_BATCH_MAX = 128, DF_BATCH_NEXT = 32 };
+    int DF_BATCH = (tiles_i + tiles_j) / 2 < 16 ? 16 : ((tiles_i + tiles_j) / 2 > DF_BATCH_MAX ? DF_BATCH_MAX : (tiles_i + tiles_j) / 2);
+    const size_t ws_ints = 4 * (size_t)n_tiles + 4 + 1 + DF_BATCH_MAX;
     HL_CUDA_OK(cudaMalloc(&ws, ws_ints * sizeof(int)));
     int* list[2] = {ws, ws + n_tiles};
     int* mark[2] = {ws + 2 * (size_t)n_tiles, ws + 3 * (size_t)n_tiles};
@@ -235,13 +369,16 @@ static int df_solve(const uint8_t* d_occ, int w, int h, int gi, int gj, const Df
     int rc = 0, sweeps = 0;
     int sm = 148;
     { int dev_id = 0; cudaGetDevice(&dev_id); cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev_id); }
-    const int per_sm = 2048 / DF_RELAX_THREADS;            // resident CTAs per SM (thread-limited)
+    int per_sm = 2;                                        // resident CTAs per SM (register-limited: 512 threads x <= 64)
+    if (mv.n == 8) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_df_relax<true>, DF_RELAX_THREADS, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_df_relax<false>, DF_RELAX_THREADS, 0);
+    if (per_sm < 1) per_sm = 1;
     const int grid = n_tiles < sm * per_sm ? n_tiles : sm * per_sm;
     do {
         if (cudaMemsetAsync(ws, 0, ws_ints * sizeof(int), st) != cudaSuccess) { rc = 1; break; }
         long long cells = (long long)w * h;
         k_df_init<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(d_occ, w, h, gi, gj, d_out, list[0], count, tiles_i, tiles_j, flags);
-        int host_flags[1 + DF_BATCH] = {0};
+        int host_flags[1 + DF_BATCH_MAX] = {0};
         if (cudaMemcpyAsync(host_flags, flags, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) { rc = 1; break; }
         if (open_border) { *open_border = host_flags[0]; if (host_flags[0]) break; }
         int cur = 0;                            // launch number: lists / marks alternate (cur & 1), counters rotate (cur % 3)
@@ -268,6 +405,7 @@ static int df_solve(const uint8_t* d_occ, int w, int h, int gi, int gj, const Df
                 ++sweeps;
                 if (!host_flags[1 + k]) converged = true;
             }
+            DF_BATCH = DF_BATCH_NEXT;
         }
         if (rc == 0 && !converged) { hl_set_error("hl_distance_field: no convergence after %d launches", sweeps); rc = 2; }
     } while (0);
