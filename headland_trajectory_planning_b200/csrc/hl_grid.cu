@@ -369,10 +369,14 @@ static int df_solve(const uint8_t* d_occ, int w, int h, int gi, int gj, const Df
     int rc = 0, sweeps = 0;
     int sm = 148;
     { int dev_id = 0; cudaGetDevice(&dev_id); cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev_id); }
-    int per_sm = 2;                                        // resident CTAs per SM (register-limited: 512 threads x <= 64)
-    if (mv.n == 8) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_df_relax<true>, DF_RELAX_THREADS, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_df_relax<false>, DF_RELAX_THREADS, 0);
-    if (per_sm < 1) per_sm = 1;
+    // CTAs per SM in the grid: MORE than are resident (2, register-limited).  The frontier list is walked with a grid
+    // stride, so with a grid of exactly the resident CTAs a CTA that drew a slow tile keeps its second tile waiting; with
+    // twice as many the block scheduler hands the next list entry to whichever SM frees a slot first
+    // (4096 x 4096 King: 2 per SM 4.87 ms, 4 per SM 4.26 ms).
+#ifndef DF_GRID_PER_SM
+#define DF_GRID_PER_SM 4
+#endif
+    const int per_sm = DF_GRID_PER_SM;
     const int grid = n_tiles < sm * per_sm ? n_tiles : sm * per_sm;
     do {
         if (cudaMemsetAsync(ws, 0, ws_ints * sizeof(int), st) != cudaSuccess) { rc = 1; break; }
