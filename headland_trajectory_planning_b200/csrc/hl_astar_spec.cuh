@@ -230,7 +230,8 @@ __device__ __noinline__ void team_state_costs(AqSmem& S, const EnvBatchDev& eb, 
 AQ_PRAGMA_UNROLL(AQ_GD_UNROLL)
     for (int i = sub; i < n; i += AQ_SUB) {
         const double dx = gx[i] - x, dy = gy[i] - y;
-        best = fmin(best, dx * dx + dy * dy);
+        const double d2 = dx * dx + dy * dy;
+        best = d2 < best ? d2 : best;                    // = fmin (a NaN never replaces best) without its NaN fix-up code
     }
 #pragma unroll
     for (int o = AQ_SUB / 2; o; o >>= 1) best = fmin(best, __shfl_xor_sync(FULL, best, o));

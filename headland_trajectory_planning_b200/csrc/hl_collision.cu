@@ -875,7 +875,10 @@ extern "C" int hl_collision_check(hl_ctx* ctx, const hl_env_batch* envs, const i
     static_assert(sizeof(K1Cta) * K1_MIN_CTAS + 1024 * K1_MIN_CTAS <= 227 * 1024, "K1 shared memory exceeds the SM");
     HL_CUDA_OK(cudaFuncSetAttribute(k_collision, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     const long long tiles = (n + K1_TILE - 1) / K1_TILE;
-    const long long cap = (long long)ctx->sm_count * K1_MIN_CTAS;
+#ifndef K1_GRID_MULT
+#define K1_GRID_MULT 1                    // CTAs in the grid per resident CTA
+#endif
+    const long long cap = (long long)ctx->sm_count * K1_MIN_CTAS * K1_GRID_MULT;
     const int grid = (int)(tiles < cap ? tiles : cap);
     const int use_tma = (((uintptr_t)d_poses) & 15) == 0 ? 1 : 0;     // cp.async.bulk needs a 16-byte aligned source
     k_collision<<<grid, K1_THREADS, smem_bytes, (cudaStream_t)stream>>>(
