@@ -257,7 +257,7 @@ def main():
         dist.all_reduce(ts, op=dist.ReduceOp.MAX)
         strong = {"scaling": "strong", "total_scenarios": m * world, "scenarios_per_gpu": m,
                   "ms_per_step": float(ts.item()) / args.steps, "value": m * world * args.steps / (float(ts.item()) * 1e-3),
-                  "unit": UNIT, "floor": "one max_nodes scenario alone on a GPU takes ~15 ms (profiles/r2g_k4_tail_regime.txt): "
+                  "unit": UNIT, "floor": "one max_nodes scenario alone on a GPU takes ~10 ms and ~13-17 ms next to others on its SM (profiles/r2u_k4_lockstep_probe.txt): "
                                          "with the sweep's 546 such scenarios the step time cannot drop below that however many GPUs share them"}
 
     res = out["results"].cpu().numpy().view(_lib.RESULT_DTYPE)
