@@ -17,7 +17,9 @@
 #include <cstring>
 #include "hl_common.cuh"
 
-#define DF_TILE 32
+#ifndef DF_TILE
+#define DF_TILE 16                      // tile edge: 16 -> 310 launches of 13 us for the 4096 x 4096 field (4.03 ms), 32 -> 157 of 27 us
+#endif                                   // (4.26 ms), 64 -> 79 of 80 us (6.37 ms): short visits and a long frontier list win
 #define DF_THREADS 256
 
 struct DfMoves { int n; int di[8]; int dj[8]; double w[8]; };
@@ -64,10 +66,10 @@ __global__ void k_df_init(const uint8_t* __restrict__ occ, int W, int H, int gi,
                                        // 0: rows DF_TILE / DF_CPT apart (round-2 first version)
 #define DF_RELAX_THREADS (DF_TILE * DF_TILE / DF_CPT)
 #if DF_ADJ
-#define DF_ROW0(tid) (1 + DF_CPT * ((tid) >> 5))
+#define DF_ROW0(tid) (1 + DF_CPT * ((tid) / DF_TILE))
 #define DF_ROW(a0, q) ((a0) + (q))
 #else
-#define DF_ROW0(tid) (1 + ((tid) >> 5))
+#define DF_ROW0(tid) (1 + ((tid) / DF_TILE))
 #define DF_ROW(a0, q) ((a0) + (q) * (DF_TILE / DF_CPT))
 #endif
 // min of two costs.  Costs are +0, positive or +inf, never NaN: their bit patterns order like integers, so the minimum is
@@ -114,7 +116,7 @@ k_df_relax(const uint8_t* __restrict__ occ, int W, int H, int gi, int gj, double
     const double W1 = 1.0, W2 = 1.4142135623730951;       // hypot(1, 0), hypot(1, 1) as the host's libm gives them
     const int n_cur = *count_cur;
     const int tid = threadIdx.x;
-    const int a0 = DF_ROW0(tid), b = 1 + (tid & 31);      // cell q of this thread: row DF_ROW(a0, q), column b
+    const int a0 = DF_ROW0(tid), b = 1 + (tid % DF_TILE);      // cell q of this thread: row DF_ROW(a0, q), column b
     for (int li = blockIdx.x; li < n_cur; li += gridDim.x) {
         const int tile = list_cur[li];
         const int ti = tile / tiles_j, tj = tile % tiles_j;
@@ -372,9 +374,10 @@ static int df_solve(const uint8_t* d_occ, int w, int h, int gi, int gj, const Df
     // CTAs per SM in the grid: MORE than are resident (2, register-limited).  The frontier list is walked with a grid
     // stride, so with a grid of exactly the resident CTAs a CTA that drew a slow tile keeps its second tile waiting; with
     // twice as many the block scheduler hands the next list entry to whichever SM frees a slot first
-    // (4096 x 4096 King: 2 per SM 4.87 ms, 4 per SM 4.26 ms).
+    // (4096 x 4096 King, 32 x 32 tiles of 512 threads: 2 per SM 4.87 ms, 4 per SM 4.26 ms; 16 x 16 tiles of 128 threads:
+    // 16 or 32 per SM 4.03 ms).
 #ifndef DF_GRID_PER_SM
-#define DF_GRID_PER_SM 4
+#define DF_GRID_PER_SM 16
 #endif
     const int per_sm = DF_GRID_PER_SM;
     const int grid = n_tiles < sm * per_sm ? n_tiles : sm * per_sm;
