@@ -91,6 +91,9 @@ __device__ __forceinline__ bool df_less(double a, double b) { return __double_as
 #ifndef DF_MIN_CTAS
 #define DF_MIN_CTAS 2                    // 64 registers: two 512-thread CTAs per SM (66 would leave one)
 #endif
+#ifndef DF_PDL
+#define DF_PDL 1                        // relaxation launches with programmatic stream serialization (griddepcontrol)
+#endif
 #ifndef DF_MIN_TREE
 #define DF_MIN_TREE 1                   // one addition per weight: min of the predecessors first (exact, see the loop)
 #endif
@@ -106,6 +109,13 @@ k_df_relax(const uint8_t* __restrict__ occ, int W, int H, int gi, int gj, double
     // the frontier is a LIST of tiles walked by a small grid with a stride (instead of one CTA per tile of the map, 16 k
     // CTAs of which a few hundred have work).  No memset between launches: a tile clears its own mark when it is
     // processed, and the counter the launch after next appends to is zeroed here (three counters rotate).
+#if DF_PDL
+    // programmatic dependent launch: this grid was scheduled while the previous relaxation launch was still running;
+    // nothing that launch wrote is read before it has completed, and the NEXT launch may be scheduled from here on
+    // (its CTAs wait at the same point), so the ~2 us between two dependent launches overlap with the work
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
     if (blockIdx.x == 0 && threadIdx.x == 0) *count_clear = 0;
     __shared__ double sd[DF_TILE + 2][DF_TILE + 3];
     __shared__ unsigned char so[DF_TILE + 2][DF_TILE + 2];
@@ -399,12 +409,31 @@ static int df_solve(const uint8_t* d_occ, int w, int h, int gi, int gj, const Df
                 cudaMemsetAsync(mark[ln], 0, sizeof(int) * (size_t)n_tiles, st);
 #endif
                 int* c_cur = count + cur % 3; int* c_nxt = count + (cur + 1) % 3; int* c_clr = count + (cur + 2) % 3;
+#if DF_PDL
+                cudaLaunchConfig_t cfg;
+                memset(&cfg, 0, sizeof(cfg));
+                cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(DF_RELAX_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                attr[0].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = attr; cfg.numAttrs = 1;
+                const uint8_t* a_occ = d_occ; double* a_out = d_out;
+                const int* a_lc = list[lc]; const int* a_cc = c_cur;
+                int* a_fl = flags + 1 + k;
+                if (mv.n == 8)
+                    cudaLaunchKernelEx(&cfg, k_df_relax<true>, a_occ, w, h, gi, gj, a_out, a_lc, a_cc, list[ln], c_nxt, mark[ln], mark[lc],
+                                       c_clr, tiles_i, tiles_j, a_fl);
+                else
+                    cudaLaunchKernelEx(&cfg, k_df_relax<false>, a_occ, w, h, gi, gj, a_out, a_lc, a_cc, list[ln], c_nxt, mark[ln], mark[lc],
+                                       c_clr, tiles_i, tiles_j, a_fl);
+#else
                 if (mv.n == 8)
                     k_df_relax<true><<<grid, DF_RELAX_THREADS, 0, st>>>(d_occ, w, h, gi, gj, d_out, list[lc], c_cur, list[ln], c_nxt,
                                                                         mark[ln], mark[lc], c_clr, tiles_i, tiles_j, flags + 1 + k);
                 else
                     k_df_relax<false><<<grid, DF_RELAX_THREADS, 0, st>>>(d_occ, w, h, gi, gj, d_out, list[lc], c_cur, list[ln], c_nxt,
                                                                          mark[ln], mark[lc], c_clr, tiles_i, tiles_j, flags + 1 + k);
+#endif
                 ++cur;
             }
             if (cudaMemcpyAsync(host_flags + 1, flags + 1, DF_BATCH * sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) { rc = 1; break; }
