@@ -57,6 +57,8 @@ __global__ void k_df_init(const uint8_t* __restrict__ occ, int W, int H, int gi,
 //    4.6     a warp skips an iteration when no row it can see changed (the wave crosses a tile as a band)
 //    4.26    minimum of the predecessors FIRST, one addition per weight (exact: fl(x + w) is monotone in x)
 // (3 CTAs per SM at 35 registers: 4.79; 4 cells per thread: 4.71; first host look after (tiles_i + tiles_j) / 2 launches.)
+//    4.03    16 x 16 tiles of 128 threads (310 launches of 13 us, four times the frontier list)
+//    3.47    launches chained by programmatic dependent launch (DF_PDL)
 #ifndef DF_CPT
 #define DF_CPT 2
 #endif
@@ -381,7 +383,7 @@ static int df_solve(const uint8_t* d_occ, int w, int h, int gi, int gj, const Df
     int rc = 0, sweeps = 0;
     int sm = 148;
     { int dev_id = 0; cudaGetDevice(&dev_id); cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev_id); }
-    // CTAs per SM in the grid: MORE than are resident (2, register-limited).  The frontier list is walked with a grid
+    // CTAs per SM in the grid: MORE than are resident.  The frontier list is walked with a grid
     // stride, so with a grid of exactly the resident CTAs a CTA that drew a slow tile keeps its second tile waiting; with
     // twice as many the block scheduler hands the next list entry to whichever SM frees a slot first
     // (4096 x 4096 King, 32 x 32 tiles of 512 threads: 2 per SM 4.87 ms, 4 per SM 4.26 ms; 16 x 16 tiles of 128 threads:
