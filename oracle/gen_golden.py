@@ -544,6 +544,48 @@ def gen_refpath():
     print("refpath_golden.npz:", len(keep), "paths;", int(sum(len(t) == 0 for t in trajs)), "raise in the reference")
 
 
+def dubins_ref_cases(n=2000, seed=77):
+    """Seeded (q0, q1, rho) cases of the Dubins cross-check (shared by the generator and the live test)."""
+    rng = np.random.default_rng(seed)
+    q = np.empty((n, 7))
+    q[:, [0, 1, 3, 4]] = rng.uniform(-10, 10, (n, 4))
+    q[:, [2, 5]] = rng.uniform(-math.pi, math.pi, (n, 2))
+    q[:, 6] = rng.uniform(1.0, 4.0, n)
+    # the shapes the planner asks for: opposite headings one row spacing apart (fish-tail / Omega turns)
+    q[: n // 10, 2] = math.pi / 2
+    q[: n // 10, 5] = -math.pi / 2
+    q[: n // 10, 4] = q[: n // 10, 1]
+    return q
+
+
+def dubins_ref_outputs(mod, cases):
+    """Word and length (metres) the reference's own pure-Python Dubins planner (path_planner/utils/dubins_path.py)
+    gives: ``planning_from_origin`` tries LSL, RSR, LSR, RSL, RLR, LRL and keeps the first minimum."""
+    names = ("LSL", "LSR", "RSL", "RSR", "RLR", "LRL")             # pydubins / dubins.c word numbering
+    word = np.empty(len(cases), dtype=np.int32)
+    length = np.empty(len(cases))
+    for k, c in enumerate(cases):
+        r = mod.calc_dubins_path(c[0], c[1], c[2], c[3], c[4], c[5], 1.0 / c[6], step_size=0.5)[0]
+        word[k] = names.index("".join(r.mode))
+        length[k] = r.L * c[6]
+    return word, length
+
+
+def gen_dubins_ref():
+    """tests/golden/dubins_ref_golden.npz: the reference repository carries a second, pure-Python Dubins planner
+    (path_planner/utils/dubins_path.py) next to the un-vendored pydubins its planner imports; it runs here
+    unmodified (matplotlib and its sibling ``draw`` stubbed: plotting only).  Pins the WORD and LENGTH of
+    oracle/dubins_port.py and of the K9 kernels on code of the reference itself."""
+    import types
+    from . import ref_loader
+    sys.modules.setdefault("draw", types.ModuleType("draw"))
+    mod = ref_loader.load("dubins_path")
+    cases = dubins_ref_cases()
+    word, length = dubins_ref_outputs(mod, cases)
+    np.savez_compressed(os.path.join(GOLD, "dubins_ref_golden.npz"), cases=cases, word=word, length=length)
+    print("dubins_ref:", len(cases), "cases, words", np.bincount(word, minlength=6).tolist())
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     args = sys.argv[1:]
@@ -567,5 +609,7 @@ if __name__ == "__main__":
         gen_oge()
     if "offset" in args:
         gen_offset(int(args[args.index("offset") + 1]))
+    if "dubins_ref" in args:
+        gen_dubins_ref()
     if "ypark" in args:
         gen_ypark(int(args[args.index("ypark") + 1]))

@@ -223,3 +223,22 @@ def test_pawn_mode_search_equals_reference(built_library):
     assert s.motion_type == "Pawn"
     r = s.hybrid_a_star_search(max_nodes=int(g["max_nodes"]))
     assert r[5] == g["counter"][2] and len(r[0]) == g["path_len"][2]
+
+
+def test_dubins_word_and_length_equal_reference_dubins_path(built_library):
+    """K9 against the reference's OWN pure-Python Dubins planner (path_planner/utils/dubins_path.py run unmodified,
+    tests/golden/dubins_ref_golden.npz, generator oracle/gen_golden.py dubins_ref): same word, same length.
+    The first 100 cases go through the `dubins` drop-in as given; all 2000 in one batch scaled to a unit turning
+    radius (a Dubins path scales with rho)."""
+    from headland_trajectory_planning_b200 import dubins, ops
+    g = np.load(os.path.join(GOLD, "dubins_ref_golden.npz"))
+    cases, word, length = g["cases"], g["word"], g["length"]
+    for c, w, ln in zip(cases[:100], word[:100], length[:100]):
+        p = dubins.shortest_path(tuple(c[:3]), tuple(c[3:6]), float(c[6]))
+        assert p.path_type() == int(w)
+        assert abs(p.path_length() - ln) <= 1e-9                       # metres; tolerance as in tests/test_dubins_ref.py
+    pairs = cases[:, :6].copy()
+    pairs[:, [0, 1, 3, 4]] /= cases[:, 6:7]
+    _, _, got_word, got_len = ops.dubins_course_batch(pairs, 1.0, step=1.0, ds=1.0)
+    assert np.array_equal(np.asarray(got_word), word)
+    assert np.allclose(np.asarray(got_len) * cases[:, 6], length, rtol=1e-12, atol=1e-9)
