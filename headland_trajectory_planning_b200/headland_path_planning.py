@@ -134,26 +134,32 @@ def search_y_type_parking_path_batch(envs, env_ids, end_poses, backward_steer_di
     end_poses = np.asarray(end_poses, dtype=np.float64).reshape(-1, 3)
     n, c = len(env_ids), len(cands)
     cands = np.asarray(cands, dtype=np.float64).reshape(-1, 4)
-    rows = np.empty((n, c, 8), dtype=np.float64)
-    bdir = np.asarray(backward_steer_dirs, dtype=np.float64)[:, None]
-    rows[:, :, 0] = cands[None, :, 0]
-    rows[:, :, 1] = cands[None, :, 1]
-    rows[:, :, 2] = cands[None, :, 2] * bdir
-    rows[:, :, 3] = cands[None, :, 3] * -bdir
-    rows[:, :, 4:7] = end_poses[:, None, :]
-    rows[:, :, 7] = np.asarray(wheel_bases, dtype=np.float64)[:, None]
+    dev = torch.device("cuda", envs.device)
+    # the [n, C, 8] candidate table is built ON THE DEVICE from its factors (a few KB up instead of n * C * 64 bytes);
+    # the signed steers are products with +-1, exact on either side
+    d_cands = torch.from_numpy(cands).to(dev)
+    d_bdir = torch.from_numpy(np.asarray(backward_steer_dirs, dtype=np.float64)).to(dev)[:, None]
+    d_end = torch.from_numpy(end_poses).to(dev)
+    d_wb = torch.from_numpy(np.asarray(wheel_bases, dtype=np.float64)).to(dev)[:, None]
+    rows = torch.empty((n, c, 8), dtype=torch.float64, device=dev)
+    rows[:, :, 0] = d_cands[None, :, 0]
+    rows[:, :, 1] = d_cands[None, :, 1]
+    rows[:, :, 2] = d_cands[None, :, 2] * d_bdir
+    rows[:, :, 3] = d_cands[None, :, 3] * -d_bdir
+    rows[:, :, 4:7] = d_end[:, None, :]
+    rows[:, :, 7] = d_wb
     poses, offsets = ops.ypark_paths(rows.reshape(-1, 8), step_size)
     # environment id of every pose, expanded on the device (plumbing only)
-    counts = torch.from_numpy(np.diff(offsets)).to(poses.device)
-    cand_env = torch.from_numpy(np.repeat(env_ids, c)).to(poses.device)
+    counts = offsets[1:] - offsets[:-1]
+    cand_env = torch.from_numpy(env_ids).to(dev).repeat_interleave(c)
     pose_env = torch.repeat_interleave(cand_env, counts).to(torch.int32)
     bad = ops.collision_check(envs, poses, env_id=pose_env, flags=ops.CHECK_OBSTACLES | ops.CHECK_BOUNDARY)
-    path_bad = ops.path_reduce(envs, bad, torch.from_numpy(offsets).to(bad.device))
+    path_bad = ops.path_reduce(envs, bad, offsets)
     feasible = (path_bad.reshape(n, c) == 0)
     any_free = feasible.any(dim=1)
     first = torch.where(any_free, feasible.to(torch.int8).argmax(dim=1), torch.full_like(any_free, -1, dtype=torch.int64))
+    sel = torch.clamp(first, min=0) + torch.arange(n, device=dev) * c
+    goal = poses[offsets[sel]].cpu().numpy()
     first_h = first.cpu().numpy().astype(np.int64)
-    sel = np.where(first_h >= 0, first_h, 0) + np.arange(n) * c
-    goal = poses[torch.from_numpy(offsets[sel]).to(poses.device)].cpu().numpy()
     goal[first_h < 0] = np.nan
     return first_h, feasible.cpu().numpy(), goal

@@ -70,9 +70,26 @@ def path_reduce(envs, pose_bad, path_start):
 def ypark_paths(cand, step):
     """Candidate paths of the Y-type parking sweep (K5, ``hl_ypark_paths``).  ``cand``: [n,8] float64 rows
     (backward_length, forward_length, signed backward_steer, signed forward_steer, end_x, end_y, end_yaw,
-    wheel_base).  Returns (poses [total,3] float64 CUDA tensor, offsets [n+1] int64 host array)."""
+    wheel_base).  Returns (poses [total,3] float64 CUDA tensor, offsets [n+1] int64).  A host array gives host offsets;
+    a CUDA tensor stays on the device (pose counts and offsets are computed there, one scalar read for the pool size)
+    and gives a CUDA offsets tensor -- the batched sweep builds its candidate table on the device."""
     torch = _torch()
     lib = _lib.load_library()
+    if torch.is_tensor(cand) and cand.is_cuda:
+        dev = _device(None, cand)
+        d_cand = cand.to(torch.float64).reshape(-1, 8).contiguous()
+        n = d_cand.shape[0]
+        # Python round() == rint (ties to even) == torch.round; the same IEEE division as on the host
+        counts = (torch.round(d_cand[:, 0] / step) + torch.round(d_cand[:, 1] / step) + 2).to(torch.int64)
+        d_off = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        if n:
+            d_off[1:] = torch.cumsum(counts, 0)
+        total = int(d_off[-1].item()) if n else 0
+        poses = torch.empty((total, 3), dtype=torch.float64, device=dev)
+        if n:
+            _lib.check(lib.hl_ypark_paths(_lib.get_ctx(dev.index), _lib.ptr(d_cand), _lib.ptr(d_off), n, float(step),
+                                          _lib.ptr(poses), _lib.stream_ptr()), "hl_ypark_paths")
+        return poses, d_off
     dev = _device()
     cand = np.ascontiguousarray(np.asarray(cand, dtype=np.float64).reshape(-1, 8))
     n = cand.shape[0]
