@@ -5,7 +5,7 @@
 // hypot(1,1) accumulated as sequential float64 sums.  Because fl(d + w) is monotone in d,
 // its result is the least fixed point of D(v) = min_m fl(D(v - m) + w(m)), which ANY
 // relaxation order reaches bit-exactly in float64 -- so the GPU runs a tiled wavefront:
-// a CTA pulls a 32x32 tile (+1 halo) into shared memory, relaxes it to its local fixed
+// a CTA pulls a DF_TILE x DF_TILE tile (16 x 16, +1 halo) into shared memory, relaxes it to its local fixed
 // point there, writes it back and flags the neighbouring tiles whose halo changed.  Only
 // flagged tiles do work in the next launch (the frontier), so the traffic per launch is
 // the frontier's, not the map's.  Roofline: nominally HBM, really launch/dependency
@@ -41,7 +41,7 @@ __global__ void k_df_init(const uint8_t* __restrict__ occ, int W, int H, int gi,
     }
 }
 
-// DF_CPT cells per thread of a 32 x 32 tile (1024 / DF_CPT threads), the move set a template parameter: the 8 (King) or 5
+// DF_CPT cells per thread of a DF_TILE x DF_TILE tile (DF_TILE^2 / DF_CPT threads), the move set a template parameter: the 8 (King) or 5
 // (Pawn) predecessors are compile-time offsets into the shared tile.  Only the neighbours that read an improved border
 // cell in their halo are flagged for the next launch.  History on the 4096 x 4096 King field:
 //   16.1 ms  one CTA per map tile, move table in a rolled loop, a host look per launch
@@ -91,7 +91,7 @@ __device__ __forceinline__ double df_min(double a, double b) { return DF_MIN_MOD
 __device__ __forceinline__ double df_min2(double a, double b) { return DF_MIN_MODE == 0 ? df_min_i(a, b) : df_min_d(a, b); }
 __device__ __forceinline__ bool df_less(double a, double b) { return __double_as_longlong(a) < __double_as_longlong(b); }
 #ifndef DF_MIN_CTAS
-#define DF_MIN_CTAS 2                    // 64 registers: two 512-thread CTAs per SM (66 would leave one)
+#define DF_MIN_CTAS 2                    // launch bound (with 32 x 32 tiles: 64 registers = two 512-thread CTAs per SM, 66 would leave one)
 #endif
 #ifndef DF_PDL
 #define DF_PDL 1                        // relaxation launches with programmatic stream serialization (griddepcontrol)
