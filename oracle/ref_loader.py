@@ -175,6 +175,28 @@ def load_oge_obca():
     return load_planner("OGE_OBCA", extra={"shapely": shp, "shapely.geometry": geom, "shapely.strtree": strtree, "rdp": rdp_mod})
 
 
+def load_reference_line_heuristic():
+    """``path_planner/reference_line_heuristic.py`` of the reference for real, for the parts that are numpy only: the
+    guide polyline (``get_guide_line``, :50-82), the per-segment search lengths without obstacle polygons
+    (``create_segment_lengths``, :84-96 -- the call sites pass none) and ``calculate_state_cost`` (:131-158).
+    ``LineString(...).buffer(...)``, ``unary_union`` and ``STRtree`` are built and never queried by these, so they are
+    inert stand-ins; the lane predicates (``get_search_length``, ``check_path_feasibility``) are NOT exercised
+    (shapely: parity unpinned)."""
+    geom = types.ModuleType("shapely.geometry")
+    geom.Polygon = _MiniPolygon
+    geom.Point = _MiniGeom
+    geom.LineString = _MiniGeom
+    geom.MultiPolygon = _MiniGeom
+    strtree = types.ModuleType("shapely.strtree")
+    strtree.STRtree = _MiniGeom
+    ops_mod = types.ModuleType("shapely.ops")
+    ops_mod.unary_union = lambda geoms: _MiniGeom()
+    shp = _StubModule("shapely")
+    shp.geometry, shp.strtree, shp.ops = geom, strtree, ops_mod
+    return load_planner("reference_line_heuristic", extra={"shapely": shp, "shapely.geometry": geom,
+                                                           "shapely.strtree": strtree, "shapely.ops": ops_mod})
+
+
 def load_obca_util():
     """``obca_py/util.py`` of the reference for real (its ``car_model_obca`` import -- casadi -- is replaced by a stub;
     ``cubic_spline`` resolves to ``path_planner/utils/cubic_spline.py``, scipy is installed)."""
