@@ -197,6 +197,22 @@ def load_reference_line_heuristic():
                                                            "shapely.strtree": strtree, "shapely.ops": ops_mod})
 
 
+def load_car_model():
+    """``path_planner/car_model.py`` of the reference for real, for the part of the footprint that is numpy only: WHERE
+    the body rectangle and the implement rectangles of a path are (``get_car_poly`` :75-143, ``get_aux_shapely_polys``
+    :146-162, ``get_path_poly`` :39-73 -- rotation by a 2 x 2 ``np.dot``, implements on every second pose).  ``Polygon``
+    keeps the vertices it is given and ``unary_union`` returns the list of polygons instead of dissolving them, so the
+    caller sees every rectangle; what GEOS then DOES with them (intersects / contains) stays unpinned."""
+    geom = types.ModuleType("shapely.geometry")
+    geom.Polygon = _MiniPolygon
+    geom.Point = _MiniGeom
+    ops_mod = types.ModuleType("shapely.ops")
+    ops_mod.unary_union = lambda polys: list(polys)
+    shp = _StubModule("shapely")
+    shp.geometry, shp.ops = geom, ops_mod
+    return load_planner("car_model", extra={"shapely": shp, "shapely.geometry": geom, "shapely.ops": ops_mod})
+
+
 def load_obca_util():
     """``obca_py/util.py`` of the reference for real (its ``car_model_obca`` import -- casadi -- is replaced by a stub;
     ``cubic_spline`` resolves to ``path_planner/utils/cubic_spline.py``, scipy is installed)."""
