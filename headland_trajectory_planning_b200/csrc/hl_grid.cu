@@ -422,12 +422,14 @@ static int df_solve(const uint8_t* d_occ, int w, int h, int gi, int gj, const Df
                 const uint8_t* a_occ = d_occ; double* a_out = d_out;
                 const int* a_lc = list[lc]; const int* a_cc = c_cur;
                 int* a_fl = flags + 1 + k;
+                cudaError_t le;
                 if (mv.n == 8)
-                    cudaLaunchKernelEx(&cfg, k_df_relax<true>, a_occ, w, h, gi, gj, a_out, a_lc, a_cc, list[ln], c_nxt, mark[ln], mark[lc],
-                                       c_clr, tiles_i, tiles_j, a_fl);
+                    le = cudaLaunchKernelEx(&cfg, k_df_relax<true>, a_occ, w, h, gi, gj, a_out, a_lc, a_cc, list[ln], c_nxt, mark[ln],
+                                            mark[lc], c_clr, tiles_i, tiles_j, a_fl);
                 else
-                    cudaLaunchKernelEx(&cfg, k_df_relax<false>, a_occ, w, h, gi, gj, a_out, a_lc, a_cc, list[ln], c_nxt, mark[ln], mark[lc],
-                                       c_clr, tiles_i, tiles_j, a_fl);
+                    le = cudaLaunchKernelEx(&cfg, k_df_relax<false>, a_occ, w, h, gi, gj, a_out, a_lc, a_cc, list[ln], c_nxt, mark[ln],
+                                            mark[lc], c_clr, tiles_i, tiles_j, a_fl);
+                if (le != cudaSuccess) { rc = 1; break; }       // a launch that did not happen would read as "frontier empty"
 #else
                 if (mv.n == 8)
                     k_df_relax<true><<<grid, DF_RELAX_THREADS, 0, st>>>(d_occ, w, h, gi, gj, d_out, list[lc], c_cur, list[ln], c_nxt,
@@ -435,9 +437,11 @@ static int df_solve(const uint8_t* d_occ, int w, int h, int gi, int gj, const Df
                 else
                     k_df_relax<false><<<grid, DF_RELAX_THREADS, 0, st>>>(d_occ, w, h, gi, gj, d_out, list[lc], c_cur, list[ln], c_nxt,
                                                                          mark[ln], mark[lc], c_clr, tiles_i, tiles_j, flags + 1 + k);
+                if (cudaGetLastError() != cudaSuccess) { rc = 1; break; }
 #endif
                 ++cur;
             }
+            if (rc) { cudaStreamSynchronize(st); break; }
             if (cudaMemcpyAsync(host_flags + 1, flags + 1, DF_BATCH * sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) { rc = 1; break; }
             for (int k = 0; k < DF_BATCH && !converged; ++k) {   // launches after the first empty frontier did nothing
                 ++sweeps;
